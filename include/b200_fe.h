@@ -1,0 +1,143 @@
+/* b200_fe.h - C ABI of libb200fe.so: the B200 (sm_100a) replacement for the FE-training and
+ * gallery-matching hot path of MarQuisCheshire/Pets-Face-Recognition.
+ *
+ * The reference has no FFI of its own: the path sits behind a Python plugin API (config.model(),
+ * config.loss(), config.similarity_f(), engine.Controller / engine.Trainer - SURVEY.md section 8b) and every
+ * FLOP is a stock PyTorch operator.  This header is therefore the boundary a maintainer binds with
+ * ctypes from those Python hooks (INTEGRATION.md shows the stubs); each entry cites the reference
+ * lines whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative B200_ERR_* code; b200_last_error() gives the
+ *     thread-local message.  Nothing throws, allocates or frees caller memory, or synchronises the device.
+ *   - pointers are raw device pointers unless noted; `stream` is a cudaStream_t (void*).
+ *   - bf16 / fp16 tensors are passed as void*; "ld*" are row pitches in ELEMENTS; int64 labels.
+ *   - workspace sizes come from the *_bytes / *_blocks query functions; the caller allocates.
+ */
+#ifndef B200_FE_H_
+#define B200_FE_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_ERR_INVALID (-1)
+#define B200_ERR_CUDA (-2)
+#define B200_ERR_WORKSPACE (-3)
+#define B200_ERR_ARCH (-4)
+
+/* epilogues of b200_gemm_tn */
+#define B200_EPI_STORE 0   /* out = acc (+ bias)                                   nn.Linear                  */
+#define B200_EPI_GELU 1    /* out2 = acc + bias (optional), out = gelu_erf(out2)   models/swin.py:39-41       */
+#define B200_EPI_RESID 2   /* out = acc + bias + aux                               Residual, models/swin.py:22-23 */
+#define B200_EPI_DGELU 3   /* out = acc * gelu_erf'(aux)                           autograd of models/swin.py:41  */
+#define B200_EPI_PARTIAL 4 /* fp32 out[split] = acc   (split-K partial, weight gradients)                     */
+
+#define B200_OPT_SGD 0
+#define B200_OPT_ADAMW 1
+
+/* one parameter tensor of a fused optimizer step (device-resident table, see b200_optimizer_step) */
+typedef struct B200OptTensor {
+  void* param;       /* fp32 [numel], updated in place                                  */
+  const void* grad;  /* fp32 [numel]                                                     */
+  void* state1;      /* SGD: momentum buffer; AdamW: exp_avg                             */
+  void* state2;      /* AdamW: exp_avg_sq (unused for SGD)                               */
+  void* param_bf16;  /* optional bf16 copy refreshed by the same kernel, or NULL         */
+  long long numel;
+  float lr, weight_decay, beta1 /* SGD: momentum */, beta2, eps;
+  int step;          /* steps already taken (0 = first step: SGD buffer := grad)         */
+} B200OptTensor;
+
+const char* b200_last_error(void);
+int b200_device_check(void); /* B200_ERR_ARCH unless the current device is sm_100 */
+
+/* ---- linear layers: D[M,N] = A[M,K] * B[N,K]^T on tcgen05 tensor cores (TMA-fed, TMEM accumulators) ---------
+ * replaces nn.Linear forward and the two GEMMs autograd runs for its backward (models/swin.py:39-43,91,98,
+ * 160,166,216; "Linear" row of SURVEY.md appendix B).  A and B are 16-bit (is_bf16 ? bf16 : fp16), K-major. */
+int b200_gemm_tn(const void* a, long long lda, const void* b, long long ldb, int M, int N, int K, int is_bf16, int mode,
+                 void* out, long long ldo, int out_fp32, void* out2, long long ldo2, const float* bias, const void* aux,
+                 long long ldaux, int splits, long long split_stride, int block_n, void* stream);
+int b200_gemm_splits(int K, int splits); /* split count b200_gemm_tn will really use (sizes the partial buffer) */
+int b200_splitk_reduce(const float* partial, float* out, long long n, int splits, int accumulate, void* stream);
+
+/* ---- LayerNorm, nn.LayerNorm(C) eps 1e-5 (models/swin.py:29,215) -------------------------------------------- */
+int b200_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, long long M,
+                       int C, float eps, void* stream);
+int b200_layernorm_bwd_blocks(long long M, int C); /* rows of the [blocks, 2C] fp32 partial buffer */
+int b200_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                       const void* dres_in, void* dx_out, float* dgamma_dbeta, float* partial, long long M, int C,
+                       int accumulate, void* stream);
+
+/* ---- patch merging gather == nn.Unfold(k=s=df) + NHWC view (models/swin.py:159,162-165) ---------------------- */
+int b200_patch_gather_image(const float* img_nchw, void* cols, int B, int Cin, int H, int W, int df, long long ldo, void* stream);
+int b200_patch_gather_nhwc(void* x_nhwc, void* cols, int B, int H, int W, int C, int backward, void* stream);
+
+/* ---- x.mean(dim=[2,3]) (models/swin.py:224) and its backward -------------------------------------------------- */
+int b200_mean_pool(const void* in, void* out, int B, int T, int C, int backward, void* stream);
+
+/* ---- layout / dtype helpers ------------------------------------------------------------------------------------ */
+int b200_transpose16(const void* in, void* out, long long R, int Cc, long long ld_in, long long ld_out, void* stream);
+int b200_cast_transpose(const float* in, void* dst_bf16, void* dst_t_bf16, int R, int Cc, void* stream);
+int b200_cast_f32_bf16(const float* in, void* out, long long n, void* stream);
+int b200_colsum_blocks(long long M);
+int b200_colsum(const void* x, long long ld, long long M, int N, float* out, float* partial, int accumulate, void* stream);
+
+/* ---- (shifted-)window attention (models/swin.py:101-135, CyclicShift :8-14, create_mask :49-62,
+ *      get_relative_distances :65-68).  qkv: [B*H*W, 3C] bf16 = output of to_qkv; out: [B*H*W, C] bf16 = input of
+ *      to_out; the cyclic shift and window partition are folded into the addressing. ------------------------------ */
+int b200_window_attn_fwd(const void* qkv, const float* pos_embedding, void* out, float* lse, int B, int H, int W, int C,
+                         int heads, int shifted, void* stream);
+int b200_window_attn_bwd_blocks(int B, int H, int W, int heads); /* rows of the [blocks, 169] dpos partial buffer */
+int b200_window_attn_bwd(const void* qkv, const float* pos_embedding, const void* out, const float* lse, const void* dout,
+                         void* dqkv, float* dpos, float* dpos_partial, int accumulate_dpos, int B, int H, int W, int C,
+                         int heads, int shifted, void* stream);
+
+/* ---- large-margin head (losses/large_margin.py:30-40 AddMarginProduct, :69-84 ArcMarginProduct) and the loss
+ *      (losses/losses.py:22-28 FocalLoss; gamma = 0 == nn.CrossEntropyLoss mean) ---------------------------------- */
+int b200_unit_rows(const float* x, void* out16, float* inv_norm, long long R, int E, long long ld_out, float eps, int as_f16,
+                   void* stream); /* F.normalize rows -> bf16 (or fp16) */
+int b200_margin_logits(const void* emb_unit, const void* w_unit, int B, int C, int E, const long long* label, float s, float m,
+                       int kind /*0 arc, 1 cos*/, int easy_margin, float* logits, long long ldo, float* cos_label, void* stream);
+int b200_margin_ce(const float* logits, long long ldl, const long long* label, const float* cos_label, int B, int C, float s,
+                   float m, int kind, int easy_margin, float gamma, float* loss_rows, float* loss_mean, void* G, long long ldg,
+                   float* rdot, float* cdot, void* stream);
+int b200_unit_rows_bwd(const float* T, const float* x, const float* inv_norm, const float* dot, const float* scale_dev,
+                       float* out_f32, void* out_bf16, long long R, int E, int accumulate, void* stream);
+
+/* ---- fused multi-tensor optimizer step: torch.optim.SGD(momentum) as built at
+ *      configs/dog_fe/fe_dogs_config.py:123-133, torch.optim.AdamW of configs/dog_fe/body_dog_fe.py:123-131 -------- */
+int b200_opt_chunk_elems(void);
+int b200_optimizer_step(int kind, const void* tensors_dev, const void* chunks_dev, int n_chunks, float grad_scale, void* stream);
+
+/* ---- whole Swin backbone (models/swin.py:196-225): plan = shapes + buffer layout, no memory of its own --------- */
+void* b200_swin_create(int batch, int img, int channels, int hidden_dim, const int* layers, const int* heads,
+                       const int* downscaling, int num_classes, int head_dim, int window_size, int training);
+void b200_swin_destroy(void* plan);
+long long b200_swin_param_elems(const void* plan);
+int b200_swin_param_count(const void* plan);
+int b200_swin_param_offsets(const void* plan, long long* offsets, long long* numels, int n);
+long long b200_swin_wcache_bytes(const void* plan);
+long long b200_swin_workspace_bytes(const void* plan);
+int b200_swin_sync_weights(const void* plan, const float* params, void* wcache, void* stream);
+int b200_swin_forward(const void* plan, const float* params, const void* wcache, const float* img_nchw, float* emb,
+                      void* workspace, long long workspace_bytes, void* stream);
+int b200_swin_backward(const void* plan, const float* params, const void* wcache, const float* demb, float* grads,
+                       void* workspace, long long workspace_bytes, int stage_hi, int stage_lo, void* stream);
+
+/* ---- gallery matching: cosine scores + top-k (engine/controller.py:77-91, similarity_f of
+ *      configs/dog_fe/fe_dogs_config.py:89-93; query != gallery form: generate_tsv_to_reproduce2.py:63-119) ---------- */
+int b200_gallery_prepare(const float* emb, void* unit_f16, double* norm, long long n, int dim, void* stream);
+long long b200_cosine_topk_workspace_bytes(long long nq, long long ng, int dim, int k);
+int b200_cosine_topk(const float* q, const void* q_unit_f16, const double* q_norm, long long nq, const float* g,
+                     const void* g_unit_f16, const double* g_norm, long long ng, int dim, int k, long long exclude_self_offset,
+                     long long g_index_base, int* out_idx, double* out_score, void* workspace, long long workspace_bytes,
+                     void* stream);
+int b200_topk_merge(const double* scores, const int* idx, long long nq, int lists, int k_in, int k_out, int* out_idx,
+                    double* out_score, void* stream);
+int b200_recall_hits(const int* top_idx, long long nq, int k_stride, const long long* q_class, const long long* g_class,
+                     const int* ks, int n_ks, unsigned long long* hits, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_FE_H_ */

@@ -108,24 +108,22 @@ def _layer_norm(x, w, b):
     return F.layer_norm(x, (x.shape[-1],), w, b, 1e-5)   # nn.LayerNorm default eps, models/swin.py:29
 
 
-def window_attention(x, sd, pfx, heads, head_dim, ws, shifted):
-    """WindowAttention.forward, models/swin.py:101-135, on NHWC x (B, H, W, C)."""
-    B, H, W, C = x.shape
+def attention_core(qkv, pos, heads, head_dim, ws, shifted):
+    """The part of WindowAttention.forward between to_qkv and to_out, models/swin.py:102-130,133-134.
+    qkv: (B, H, W, 3*heads*head_dim) on the UNSHIFTED pixel grid; returns (B, H, W, heads*head_dim) on
+    the same grid.  roll(-d) means shifted[y] = x[(y + d) % H] (:83, :102-103); the inverse roll on the
+    way out puts every token's result back at its source pixel, so the shift is pure addressing."""
+    B, H, W, _ = qkv.shape
     nh, nw = H // ws, W // ws
-    d = ws // 2
-    qkv = x @ sd[pfx + 'to_qkv.weight'].t()                       # :107, no bias (:91)
-    # Source pixel of token (wy, r) of the (possibly shifted) window grid.  roll(-d) means
-    # shifted[y] = x[(y + d) % H]  (:83, :102-103); the inverse roll on the way out (:133-134)
-    # puts every token's result back at the same source pixel, so the shift is pure addressing.
-    off = d if shifted else 0
+    off = ws // 2 if shifted else 0
     ys = (torch.arange(H) + off) % H
     xs = (torch.arange(W) + off) % W
-    g = qkv[:, ys][:, :, xs]                                        # gather shifted grid
+    g = qkv[:, ys][:, :, xs]                                        # gather the shifted grid
     g = g.reshape(B, nh, ws, nw, ws, 3, heads, head_dim)            # [q|k|v] chunk, then (h d) :107-113
     g = g.permute(5, 0, 6, 1, 3, 2, 4, 7).reshape(3, B, heads, nh * nw, ws * ws, head_dim)
     q, k, v = g[0], g[1], g[2]
     dots = (q @ k.transpose(-1, -2)) * (head_dim ** -0.5)           # :115, :77
-    dots = dots + relative_bias(sd[pfx + 'pos_embedding'], ws).to(dots.dtype)   # :117-118
+    dots = dots + relative_bias(pos, ws).to(dots.dtype)             # :117-118
     if shifted:                                                     # :122-124
         ul = torch.isinf(shift_mask(ws, True, False))
         lr = torch.isinf(shift_mask(ws, False, True))
@@ -133,13 +131,20 @@ def window_attention(x, sd, pfx, heads, head_dim, ws, shifted):
         last_row = (widx // nw) == nh - 1                           # dots[:, :, -nw_w:]
         last_col = (widx % nw) == nw - 1                            # dots[:, :, nw_w-1::nw_w]
         banned = (last_row[:, None, None] & ul[None]) | (last_col[:, None, None] & lr[None])
-        dots = dots.masked_fill(banned[None, None], float('-inf'))
+        dots = dots.masked_fill(banned[None, None].to(dots.device), float('-inf'))
     attn = dots.softmax(dim=-1)                                     # :126
     out = attn @ v                                                  # :128
     out = out.reshape(B, heads, nh, nw, ws, ws, head_dim).permute(0, 2, 4, 3, 5, 1, 6)
     out = out.reshape(B, H, W, heads * head_dim)                    # :129-130, still on the shifted grid
     res = torch.empty_like(out)
     res[:, ys[:, None], xs[None, :]] = out                          # scatter back == cyclic_back_shift
+    return res
+
+
+def window_attention(x, sd, pfx, heads, head_dim, ws, shifted):
+    """WindowAttention.forward, models/swin.py:101-135, on NHWC x (B, H, W, C)."""
+    qkv = x @ sd[pfx + 'to_qkv.weight'].t()                       # :107, no bias (:91)
+    res = attention_core(qkv, sd[pfx + 'pos_embedding'], heads, head_dim, ws, shifted)
     return res @ sd[pfx + 'to_out.weight'].t() + sd[pfx + 'to_out.bias']   # :131 (linear commutes with the roll)
 
 

@@ -1,0 +1,93 @@
+"""Fused multi-tensor optimizer step (csrc/elementwise.cu: sgd_kernel / adamw_kernel).
+
+The reference's configs return stock ``torch.optim.SGD`` / ``torch.optim.AdamW`` objects from
+``config.optimizer(model_loss)`` (configs/dog_fe/fe_dogs_config.py:123-133, body_dog_fe.py:123-131).  To stay a
+drop-in, the trainer keeps those objects - their param_groups (lr, momentum, weight_decay; mutated by
+MultiStepLR) and their ``state`` (so ``optimizer.state_dict()`` checkpoints keep the torch layout) - and
+replaces only the arithmetic of ``optimizer.step()`` by ONE kernel launch over all parameters.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import abi, plan
+from .abi import B200Error, check, lib, stream_ptr
+
+
+class FusedStep:
+    def __init__(self, optimizer: torch.optim.Optimizer):
+        if isinstance(optimizer, torch.optim.AdamW):
+            self.kind = abi.OPT_ADAMW
+        elif isinstance(optimizer, torch.optim.SGD):
+            self.kind = abi.OPT_SGD
+        else:
+            raise B200Error(f'no fused step for {type(optimizer).__name__} (SGD and AdamW are built)')
+        for g in optimizer.param_groups:
+            if self.kind == abi.OPT_SGD and (g.get('nesterov') or g.get('dampening', 0) != 0 or g.get('maximize')):
+                raise B200Error('fused SGD implements momentum / weight_decay only (as the reference configs use it)')
+            if self.kind == abi.OPT_ADAMW and (g.get('amsgrad') or g.get('maximize')):
+                raise B200Error('fused AdamW: amsgrad / maximize are not built')
+        self.opt = optimizer
+        self._key = None
+        self._tensors_dev = self._chunks_dev = None
+        self._n_chunks = 0
+        self._chunk = lib().b200_opt_chunk_elems()
+
+    def _entries(self):
+        out = []
+        for g in self.opt.param_groups:
+            for p in g['params']:
+                if p.grad is None:           # torch skips these too (e.g. the requires_grad=False shift masks)
+                    continue
+                if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous() or not p.grad.is_contiguous():
+                    raise B200Error('fused optimizer step needs contiguous fp32 CUDA parameters and gradients')
+                st = self.opt.state[p]
+                if self.kind == abi.OPT_SGD:
+                    mom = float(g.get('momentum', 0.0))
+                    first = 'momentum_buffer' not in st or st['momentum_buffer'] is None
+                    if first:
+                        st['momentum_buffer'] = torch.zeros_like(p)
+                    out.append((p, p.grad, st['momentum_buffer'], None, float(g['lr']), float(g.get('weight_decay', 0.0)), mom, 0.0,
+                                0.0, 0 if first else 1))
+                else:
+                    if 'step' not in st:
+                        st['step'] = torch.tensor(0.0)
+                        st['exp_avg'] = torch.zeros_like(p)
+                        st['exp_avg_sq'] = torch.zeros_like(p)
+                    b1, b2 = g['betas']
+                    out.append((p, p.grad, st['exp_avg'], st['exp_avg_sq'], float(g['lr']), float(g.get('weight_decay', 0.0)),
+                                float(b1), float(b2), float(g['eps']), int(st['step'].item())))
+        return out
+
+    @torch.no_grad()
+    def step(self, grad_scale: float = 1.0) -> None:
+        ents = self._entries()
+        if not ents:
+            return
+        dev = ents[0][0].device
+        key = tuple((e[0].data_ptr(), e[1].data_ptr(), e[2].data_ptr(), e[4], e[5], e[6], e[7], e[8], e[9]) for e in ents)
+        if key != self._key:
+            arr = (abi.OptTensor * len(ents))()
+            chunks = []
+            for i, (p, g, s1, s2, lr, wd, b1, b2, eps, step) in enumerate(ents):
+                t = arr[i]
+                t.param, t.grad, t.state1 = p.data_ptr(), g.data_ptr(), s1.data_ptr()
+                t.state2 = s2.data_ptr() if s2 is not None else 0
+                t.param_bf16 = 0
+                t.numel, t.lr, t.weight_decay, t.beta1, t.beta2, t.eps, t.step = p.numel(), lr, wd, b1, b2, eps, step
+                chunks.extend((i, o) for o in range(0, p.numel(), self._chunk))
+            raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+            self._tensors_dev = raw.to(dev)
+            self._chunks_dev = torch.tensor(chunks, dtype=torch.int32).to(dev)
+            self._n_chunks = len(chunks)
+            self._key = key
+        check(lib().b200_optimizer_step(self.kind, self._tensors_dev.data_ptr(), self._chunks_dev.data_ptr(), self._n_chunks,
+                                        float(grad_scale), stream_ptr()), 'optimizer_step')
+        if self.kind == abi.OPT_ADAMW:
+            for g in self.opt.param_groups:
+                for p in g['params']:
+                    if p.grad is not None:
+                        self.opt.state[p]['step'] += 1
+        plan.bump_weight_epoch()

@@ -1,0 +1,597 @@
+// HBM-bound kernels of the Swin path: LayerNorm fwd/bwd, patch gather (nn.Unfold order), mean pool,
+// bf16 transpose, column sums (bias gradients), weight casts, fused multi-tensor SGD/AdamW.
+// All are coalesced / 16-B vectorised, fp32 statistics, bf16 storage.
+#include "common.cuh"
+
+#include "b200_fe.h"
+
+namespace {
+
+__device__ __forceinline__ void ld8(const bf16* p, float* x) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  float2 f;
+  f = unpack_bf16(u.x); x[0] = f.x; x[1] = f.y;
+  f = unpack_bf16(u.y); x[2] = f.x; x[3] = f.y;
+  f = unpack_bf16(u.z); x[4] = f.x; x[5] = f.y;
+  f = unpack_bf16(u.w); x[6] = f.x; x[7] = f.y;
+}
+__device__ __forceinline__ void st8(bf16* p, const float* x) {
+  uint4 u;
+  u.x = pack_bf16(x[0], x[1]); u.y = pack_bf16(x[2], x[3]); u.z = pack_bf16(x[4], x[5]); u.w = pack_bf16(x[6], x[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ void ld8f(const float* p, float* x) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p + 4));
+  x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+}
+template <int LPR>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm forward (nn.LayerNorm(C), eps 1e-5, models/swin.py:29,215).  LPR lanes cooperate on one
+// row, each lane holding up to MAXIT chunks of 8 channels in registers; two-pass statistics in fp32.
+// ---------------------------------------------------------------------------------------------
+template <int LPR, int MAXIT>
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, bf16* __restrict__ y,
+                                                            float* __restrict__ mean, float* __restrict__ rstd,
+                                                            long long M, int C, float eps) {
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, l = lane % LPR;
+  const long long warp_global = (1LL * blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = (1LL * gridDim.x * blockDim.x) >> 5;
+  const int chunks = C >> 3;
+  for (long long row0 = warp_global * RPW; row0 < M; row0 += nwarps * RPW) {
+    const long long row = row0 + sub;
+    const bool live = row < M;
+    float v[MAXIT][8];
+    float s = 0.f;
+#pragma unroll
+    for (int it = 0; it < MAXIT; ++it) {
+      const int ch = l + it * LPR;
+      if (live && ch < chunks) {
+        ld8(x + row * C + ch * 8, v[it]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += v[it][i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[it][i] = 0.f;
+      }
+    }
+    const float mu = group_sum<LPR>(s) / C;
+    float q = 0.f;
+#pragma unroll
+    for (int it = 0; it < MAXIT; ++it) {
+      const int ch = l + it * LPR;
+      if (ch < chunks) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const float d = v[it][i] - mu; q += d * d; }
+      }
+    }
+    const float rs = rsqrtf(group_sum<LPR>(q) / C + eps);
+    if (live) {
+#pragma unroll
+      for (int it = 0; it < MAXIT; ++it) {
+        const int ch = l + it * LPR;
+        if (ch < chunks) {
+          float g[8], b[8], o[8];
+          ld8f(gamma + ch * 8, g);
+          ld8f(beta + ch * 8, b);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = (v[it][i] - mu) * rs * g[i] + b[i];
+          st8(y + row * C + ch * 8, o);
+        }
+      }
+      if (l == 0) {
+        if (mean) mean[row] = mu;
+        if (rstd) rstd[row] = rs;
+      }
+    }
+  }
+}
+
+// LayerNorm backward.  dx = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * gamma; optional
+// fused residual-gradient add (dx_out = dres_in + dx).  dgamma/dbeta: register partials per thread
+// over its rows, CTA-reduced through smem, one [2C] partial row per CTA (reduced by splitk_reduce in
+// a fixed order -> deterministic).
+template <int LPR, int MAXIT>
+__global__ void __launch_bounds__(128) layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                            const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd, const bf16* dres,
+                                                            bf16* dx, float* __restrict__ partial,
+                                                            long long M, int C) {
+  constexpr int RPW = 32 / LPR;
+  extern __shared__ float red[];   // [warps][2][C]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane / LPR, l = lane % LPR;
+  const long long warp_global = (1LL * blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = (1LL * gridDim.x * blockDim.x) >> 5;
+  const int chunks = C >> 3;
+  float dg[MAXIT][8], db[MAXIT][8];
+#pragma unroll
+  for (int it = 0; it < MAXIT; ++it)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { dg[it][i] = 0.f; db[it][i] = 0.f; }
+
+  for (long long row0 = warp_global * RPW; row0 < M; row0 += nwarps * RPW) {
+    const long long row = row0 + sub;
+    const bool live = row < M;
+    const float mu = live ? mean[row] : 0.f, rs = live ? rstd[row] : 0.f;
+    float g[MAXIT][8], xh[MAXIT][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int it = 0; it < MAXIT; ++it) {
+      const int ch = l + it * LPR;
+      if (live && ch < chunks) {
+        float d[8], xv[8], gm[8];
+        ld8(dy + row * C + ch * 8, d);
+        ld8(x + row * C + ch * 8, xv);
+        ld8f(gamma + ch * 8, gm);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          xh[it][i] = (xv[i] - mu) * rs;
+          g[it][i] = d[i] * gm[i];
+          s1 += g[it][i];
+          s2 += g[it][i] * xh[it][i];
+          dg[it][i] += d[i] * xh[it][i];
+          db[it][i] += d[i];
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { g[it][i] = 0.f; xh[it][i] = 0.f; }
+      }
+    }
+    s1 = group_sum<LPR>(s1) / C;
+    s2 = group_sum<LPR>(s2) / C;
+    if (live) {
+#pragma unroll
+      for (int it = 0; it < MAXIT; ++it) {
+        const int ch = l + it * LPR;
+        if (ch < chunks) {
+          float o[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = rs * (g[it][i] - s1 - xh[it][i] * s2);
+          if (dres) {
+            float r[8];
+            ld8(dres + row * C + ch * 8, r);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] += r[i];
+          }
+          st8(dx + row * C + ch * 8, o);
+        }
+      }
+    }
+  }
+  // fold the RPW sub-rows of a warp, then the warps of the CTA
+#pragma unroll
+  for (int it = 0; it < MAXIT; ++it)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+      for (int o = 16; o >= LPR; o >>= 1) {
+        dg[it][i] += __shfl_xor_sync(0xffffffffu, dg[it][i], o);
+        db[it][i] += __shfl_xor_sync(0xffffffffu, db[it][i], o);
+      }
+    }
+  const int warps = blockDim.x >> 5;
+  if (sub == 0) {
+#pragma unroll
+    for (int it = 0; it < MAXIT; ++it) {
+      const int ch = l + it * LPR;
+      if (ch < chunks) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          red[(warp * 2 + 0) * C + ch * 8 + i] = dg[it][i];
+          red[(warp * 2 + 1) * C + ch * 8 + i] = db[it][i];
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
+    const int which = c / C, col = c % C;
+    float a = 0.f;
+    for (int w = 0; w < warps; ++w) a += red[(w * 2 + which) * C + col];
+    partial[1LL * blockIdx.x * 2 * C + c] = a;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Patch gather == nn.Unfold(k = s = df) + NHWC view (models/swin.py:162-166): out[m, c*df*df + kh*df + kw]
+// ---------------------------------------------------------------------------------------------
+// stage 1: fp32 NCHW image, df = 4 -> one thread per (output row, c, kh): float4 in, 4 bf16 out
+__global__ void patch_gather_image_kernel(const float* __restrict__ img, bf16* __restrict__ out, int B, int Cin, int H, int W,
+                                          int df, int ldo) {
+  const int Ho = H / df, Wo = W / df;
+  const int per_row = Cin * df;                       // (c, kh) pairs, each df(=4) contiguous kw
+  const long long total = 1LL * B * Ho * Wo * per_row;
+  for (long long idx = 1LL * blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += 1LL * gridDim.x * blockDim.x) {
+    const int j = static_cast<int>(idx % per_row);
+    const long long m = idx / per_row;
+    const int c = j / df, kh = j % df;
+    const int px = static_cast<int>(m % Wo);
+    const int py = static_cast<int>((m / Wo) % Ho);
+    const int b = static_cast<int>(m / (1LL * Wo * Ho));
+    const float4 v = __ldg(reinterpret_cast<const float4*>(img + ((1LL * b * Cin + c) * H + py * df + kh) * W + px * df));
+    uint2 o;
+    o.x = pack_bf16(v.x, v.y);
+    o.y = pack_bf16(v.z, v.w);
+    *reinterpret_cast<uint2*>(out + m * ldo + j * 4) = o;
+  }
+}
+
+// stages 2-4: bf16 NHWC, df = 2 -> one thread per (output row, channel pair): 4 x bf162 in, 16 B out
+// backward (scatter == exact inverse, every input pixel appears once) uses the same indexing.
+template <bool BACKWARD>
+__global__ void patch_gather_nhwc_kernel(bf16* __restrict__ x, bf16* __restrict__ cols, int B, int H, int W, int C) {
+  const int Ho = H / 2, Wo = W / 2, cp = C / 2;
+  const long long total = 1LL * B * Ho * Wo * cp;
+  for (long long idx = 1LL * blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += 1LL * gridDim.x * blockDim.x) {
+    const int c2 = static_cast<int>(idx % cp);
+    const long long m = idx / cp;
+    const int px = static_cast<int>(m % Wo);
+    const int py = static_cast<int>((m / Wo) % Ho);
+    const int b = static_cast<int>(m / (1LL * Wo * Ho));
+    bf16* base = x + ((1LL * b * H + py * 2) * W + px * 2) * C + c2 * 2;
+    bf16* dst = cols + m * (4LL * C) + c2 * 8;        // features (c, kh, kw) for c = 2*c2, 2*c2+1
+    if (!BACKWARD) {
+      const bf162 p00 = *reinterpret_cast<const bf162*>(base);
+      const bf162 p01 = *reinterpret_cast<const bf162*>(base + C);
+      const bf162 p10 = *reinterpret_cast<const bf162*>(base + 1LL * W * C);
+      const bf162 p11 = *reinterpret_cast<const bf162*>(base + 1LL * W * C + C);
+      bf162 o[4];
+      o[0] = bf162(p00.x, p01.x); o[1] = bf162(p10.x, p11.x);   // channel 2*c2  : (kh,kw) = 00,01,10,11
+      o[2] = bf162(p00.y, p01.y); o[3] = bf162(p10.y, p11.y);   // channel 2*c2+1
+      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<uint4*>(o);
+    } else {
+      bf162 o[4];
+      *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(dst);
+      *reinterpret_cast<bf162*>(base) = bf162(o[0].x, o[2].x);
+      *reinterpret_cast<bf162*>(base + C) = bf162(o[0].y, o[2].y);
+      *reinterpret_cast<bf162*>(base + 1LL * W * C) = bf162(o[1].x, o[3].x);
+      *reinterpret_cast<bf162*>(base + 1LL * W * C + C) = bf162(o[1].y, o[3].y);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// spatial mean (models/swin.py:224) and its backward (broadcast / T)
+// ---------------------------------------------------------------------------------------------
+__global__ void mean_pool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int B, int T, int C) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * (C / 2)) return;
+  const int c2 = idx % (C / 2), b = idx / (C / 2);
+  float a0 = 0.f, a1 = 0.f;
+  for (int t = 0; t < T; ++t) {
+    const float2 f = __bfloat1622float2(*reinterpret_cast<const bf162*>(x + (1LL * b * T + t) * C + c2 * 2));
+    a0 += f.x; a1 += f.y;
+  }
+  *reinterpret_cast<bf162*>(y + 1LL * b * C + c2 * 2) = __floats2bfloat162_rn(a0 / T, a1 / T);
+}
+__global__ void mean_pool_bwd_kernel(const bf16* __restrict__ dy, bf16* __restrict__ dx, int B, int T, int C) {
+  const long long idx = 1LL * blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 1LL * B * T * (C / 2)) return;
+  const int c2 = static_cast<int>(idx % (C / 2));
+  const int b = static_cast<int>(idx / (1LL * T * (C / 2)));
+  const float2 f = __bfloat1622float2(*reinterpret_cast<const bf162*>(dy + 1LL * b * C + c2 * 2));
+  *reinterpret_cast<bf162*>(dx + idx * 2) = __floats2bfloat162_rn(f.x / T, f.y / T);
+}
+
+// ---------------------------------------------------------------------------------------------
+// [R, Cc] -> [Cc, R] 16-bit transpose, 64x64 tiles through padded smem (coalesced both ways)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) transpose16_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out,
+                                                          long long R, int Cc, long long ld_in, long long ld_out) {
+  __shared__ uint16_t tile[64][66];
+  const long long r0 = 64LL * blockIdx.x;
+  const int c0 = 64 * blockIdx.y;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  for (int i = ty; i < 64; i += 8) {
+    const long long r = r0 + i;
+    const int c = c0 + tx * 2;
+    uint32_t v = 0;
+    if (r < R && c < Cc) v = *reinterpret_cast<const uint32_t*>(in + r * ld_in + c);   // Cc even
+    tile[i][tx * 2] = static_cast<uint16_t>(v & 0xffff);
+    tile[i][tx * 2 + 1] = static_cast<uint16_t>(v >> 16);
+  }
+  __syncthreads();
+  for (int i = ty; i < 64; i += 8) {
+    const int c = c0 + i;
+    const long long r = r0 + tx * 2;
+    if (c < Cc && r < R) {
+      const uint32_t v = static_cast<uint32_t>(tile[tx * 2][i]) | (static_cast<uint32_t>(tile[tx * 2 + 1][i]) << 16);
+      if (r + 1 < R) *reinterpret_cast<uint32_t*>(out + c * ld_out + r) = v;
+      else out[c * ld_out + r] = static_cast<uint16_t>(v & 0xffff);
+    }
+  }
+}
+
+// fp32 [R, Cc] -> bf16 [R, Cc] (dst) and/or bf16 [Cc, R] (dst_t).  Used for weights (small).
+__global__ void __launch_bounds__(256) cast_transpose_kernel(const float* __restrict__ in, bf16* __restrict__ dst,
+                                                             bf16* __restrict__ dst_t, int R, int Cc) {
+  __shared__ float tile[32][33];
+  const int r0 = 32 * blockIdx.x, c0 = 32 * blockIdx.y;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    float v = 0.f;
+    if (r < R && c < Cc) {
+      v = in[1LL * r * Cc + c];
+      if (dst) dst[1LL * r * Cc + c] = __float2bfloat16_rn(v);
+    }
+    tile[i][tx] = v;
+  }
+  __syncthreads();
+  if (dst_t) {
+    for (int i = ty; i < 32; i += 8) {
+      const int c = c0 + i, r = r0 + tx;
+      if (c < Cc && r < R) dst_t[1LL * c * R + r] = __float2bfloat16_rn(tile[tx][i]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// column sums of a bf16 [M, N] matrix (bias gradients): per-CTA row slab -> partial[blk][N]
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, float* __restrict__ partial, long long M, int N,
+                                                     long long ld, long long rows_per_block) {
+  const long long r0 = rows_per_block * blockIdx.x;
+  const long long r1 = min(M, r0 + rows_per_block);
+  for (int c2 = threadIdx.x; c2 < N / 2; c2 += blockDim.x) {
+    float a0 = 0.f, a1 = 0.f;
+    for (long long r = r0; r < r1; ++r) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const bf162*>(x + r * ld + c2 * 2));
+      a0 += f.x; a1 += f.y;
+    }
+    partial[1LL * blockIdx.x * N + c2 * 2] = a0;
+    partial[1LL * blockIdx.x * N + c2 * 2 + 1] = a1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused multi-tensor optimizer steps.  One launch updates every parameter: a device table lists the
+// tensors, a chunk table maps CTAs onto (tensor, offset) slabs of kChunk elements.
+// ---------------------------------------------------------------------------------------------
+constexpr int kChunk = 4096;
+
+// torch.optim.SGD(momentum, dampening 0, no nesterov): g += wd * p; buf = first ? g : mom * buf + g; p -= lr * buf
+__global__ void __launch_bounds__(256) sgd_kernel(const B200OptTensor* __restrict__ tensors, const int2* __restrict__ chunks,
+                                                  float grad_scale) {
+  const int2 ck = chunks[blockIdx.x];
+  const B200OptTensor t = tensors[ck.x];
+  float* p = reinterpret_cast<float*>(t.param);
+  const float* g = reinterpret_cast<const float*>(t.grad);
+  float* buf = reinterpret_cast<float*>(t.state1);
+  bf16* p16 = reinterpret_cast<bf16*>(t.param_bf16);
+  const long long end = min(t.numel, 1LL * ck.y + kChunk);
+  for (long long i = ck.y + threadIdx.x; i < end; i += blockDim.x) {
+    float pv = p[i];
+    float gv = g[i] * grad_scale + t.weight_decay * pv;
+    const float bv = t.step == 0 ? gv : t.beta1 * buf[i] + gv;
+    buf[i] = bv;
+    pv -= t.lr * bv;
+    p[i] = pv;
+    if (p16) p16[i] = __float2bfloat16_rn(pv);
+  }
+}
+
+// torch.optim.AdamW: p *= 1 - lr*wd; m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
+// p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+__global__ void __launch_bounds__(256) adamw_kernel(const B200OptTensor* __restrict__ tensors, const int2* __restrict__ chunks,
+                                                    float grad_scale) {
+  const int2 ck = chunks[blockIdx.x];
+  const B200OptTensor t = tensors[ck.x];
+  float* p = reinterpret_cast<float*>(t.param);
+  const float* g = reinterpret_cast<const float*>(t.grad);
+  float* m = reinterpret_cast<float*>(t.state1);
+  float* v = reinterpret_cast<float*>(t.state2);
+  bf16* p16 = reinterpret_cast<bf16*>(t.param_bf16);
+  const float stepf = static_cast<float>(t.step + 1);
+  const float bc1 = 1.0f - powf(t.beta1, stepf);
+  const float bc2s = sqrtf(1.0f - powf(t.beta2, stepf));
+  const long long end = min(t.numel, 1LL * ck.y + kChunk);
+  for (long long i = ck.y + threadIdx.x; i < end; i += blockDim.x) {
+    float pv = p[i] * (1.0f - t.lr * t.weight_decay);
+    const float gv = g[i] * grad_scale;
+    const float mv = t.beta1 * m[i] + (1.0f - t.beta1) * gv;
+    const float vv = t.beta2 * v[i] + (1.0f - t.beta2) * gv * gv;
+    m[i] = mv; v[i] = vv;
+    pv -= (t.lr / bc1) * mv / (sqrtf(vv) / bc2s + t.eps);
+    p[i] = pv;
+    if (p16) p16[i] = __float2bfloat16_rn(pv);
+  }
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, long long n) {
+  const long long i = (1LL * blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(in + i);
+    uint2 o;
+    o.x = pack_bf16(v.x, v.y); o.y = pack_bf16(v.z, v.w);
+    *reinterpret_cast<uint2*>(out + i) = o;
+  } else {
+    for (long long j = i; j < n; ++j) out[j] = __float2bfloat16_rn(in[j]);
+  }
+}
+
+int grid_for(long long work_items, int threads, int max_blocks) {
+  long long b = (work_items + threads - 1) / threads;
+  if (b > max_blocks) b = max_blocks;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
+template <int LPR, int MAXIT>
+int ln_fwd_launch(const bf16* x, const float* g, const float* b, bf16* y, float* mean, float* rstd, long long M, int C, float eps,
+                  cudaStream_t st) {
+  const int rpw = 32 / LPR;
+  const long long warps = (M + rpw - 1) / rpw;
+  const int blocks = grid_for(warps * 32, 256, b200_num_sms() * 8);
+  layernorm_fwd_kernel<LPR, MAXIT><<<blocks, 256, 0, st>>>(x, g, b, y, mean, rstd, M, C, eps);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+template <int LPR, int MAXIT>
+int ln_bwd_launch(const bf16* dy, const bf16* x, const float* g, const float* mean, const float* rstd, const bf16* dres, bf16* dx,
+                  float* partial, long long M, int C, int blocks, cudaStream_t st) {
+  const size_t smem = sizeof(float) * 4 * 2 * C;
+  if (smem > 48 * 1024)
+    B200_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<LPR, MAXIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  layernorm_bwd_kernel<LPR, MAXIT><<<blocks, 128, smem, st>>>(dy, x, g, mean, rstd, dres, dx, partial, M, C);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" int b200_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                                  long long M, int C, float eps, void* stream) {
+  B200_REQUIRE(C % 8 == 0 && C >= 8 && C <= 1536, "layernorm: C=%d unsupported (multiple of 8, <= 1536)", C);
+  if (M == 0) return B200_OK;
+  auto st = reinterpret_cast<cudaStream_t>(stream);
+  auto X = reinterpret_cast<const bf16*>(x);
+  auto Y = reinterpret_cast<bf16*>(y);
+  if (C <= 128) return ln_fwd_launch<16, 1>(X, gamma, beta, Y, mean, rstd, M, C, eps, st);
+  if (C <= 256) return ln_fwd_launch<32, 1>(X, gamma, beta, Y, mean, rstd, M, C, eps, st);
+  if (C <= 512) return ln_fwd_launch<32, 2>(X, gamma, beta, Y, mean, rstd, M, C, eps, st);
+  if (C <= 768) return ln_fwd_launch<32, 3>(X, gamma, beta, Y, mean, rstd, M, C, eps, st);
+  return ln_fwd_launch<32, 6>(X, gamma, beta, Y, mean, rstd, M, C, eps, st);
+}
+
+extern "C" int b200_layernorm_bwd_blocks(long long M, int C) {
+  (void)C;
+  long long b = (M + 63) / 64;
+  const int cap = b200_num_sms() * 4;
+  if (b > cap) b = cap;
+  return b < 1 ? 1 : static_cast<int>(b);
+}
+
+extern "C" int b200_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                                  const void* dres_in, void* dx_out, float* dgamma_dbeta, float* partial, long long M, int C,
+                                  int accumulate, void* stream) {
+  B200_REQUIRE(C % 8 == 0 && C >= 8 && C <= 1536, "layernorm_bwd: C=%d unsupported", C);
+  if (M == 0) return B200_OK;
+  auto st = reinterpret_cast<cudaStream_t>(stream);
+  const int blocks = b200_layernorm_bwd_blocks(M, C);
+  auto DY = reinterpret_cast<const bf16*>(dy);
+  auto X = reinterpret_cast<const bf16*>(x);
+  auto DR = reinterpret_cast<const bf16*>(dres_in);
+  auto DX = reinterpret_cast<bf16*>(dx_out);
+  int rc;
+  if (C <= 128) rc = ln_bwd_launch<16, 1>(DY, X, gamma, mean, rstd, DR, DX, partial, M, C, blocks, st);
+  else if (C <= 256) rc = ln_bwd_launch<32, 1>(DY, X, gamma, mean, rstd, DR, DX, partial, M, C, blocks, st);
+  else if (C <= 512) rc = ln_bwd_launch<32, 2>(DY, X, gamma, mean, rstd, DR, DX, partial, M, C, blocks, st);
+  else if (C <= 768) rc = ln_bwd_launch<32, 3>(DY, X, gamma, mean, rstd, DR, DX, partial, M, C, blocks, st);
+  else rc = ln_bwd_launch<32, 6>(DY, X, gamma, mean, rstd, DR, DX, partial, M, C, blocks, st);
+  if (rc) return rc;
+  // dgamma_dbeta = [dgamma (C) | dbeta (C)] contiguous, as norm.weight / norm.bias are in the flat grad buffer
+  return b200_splitk_reduce(partial, dgamma_dbeta, 2LL * C, blocks, accumulate, stream);
+}
+
+extern "C" int b200_patch_gather_image(const float* img, void* out, int B, int Cin, int H, int W, int df, long long ldo,
+                                       void* stream) {
+  B200_REQUIRE(df == 4 && H % 4 == 0 && W % 4 == 0, "patch_gather_image: downscaling factor 4 only (got %d)", df);
+  B200_REQUIRE(ldo % 4 == 0 && ldo >= Cin * 16, "patch_gather_image: bad ldo");
+  const long long total = 1LL * B * (H / 4) * (W / 4) * Cin * 4;
+  if (total == 0) return B200_OK;
+  patch_gather_image_kernel<<<grid_for(total, 256, b200_num_sms() * 16), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      img, reinterpret_cast<bf16*>(out), B, Cin, H, W, df, static_cast<int>(ldo));
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+extern "C" int b200_patch_gather_nhwc(void* x, void* cols, int B, int H, int W, int C, int backward, void* stream) {
+  B200_REQUIRE(H % 2 == 0 && W % 2 == 0 && C % 2 == 0, "patch_gather_nhwc: H, W, C must be even");
+  const long long total = 1LL * B * (H / 2) * (W / 2) * (C / 2);
+  if (total == 0) return B200_OK;
+  auto st = reinterpret_cast<cudaStream_t>(stream);
+  const int blocks = grid_for(total, 256, b200_num_sms() * 16);
+  if (backward) patch_gather_nhwc_kernel<true><<<blocks, 256, 0, st>>>(reinterpret_cast<bf16*>(x), reinterpret_cast<bf16*>(cols), B, H, W, C);
+  else patch_gather_nhwc_kernel<false><<<blocks, 256, 0, st>>>(reinterpret_cast<bf16*>(x), reinterpret_cast<bf16*>(cols), B, H, W, C);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+extern "C" int b200_mean_pool(const void* in, void* out, int B, int T, int C, int backward, void* stream) {
+  B200_REQUIRE(C % 2 == 0, "mean_pool: C must be even");
+  if (B == 0) return B200_OK;
+  auto st = reinterpret_cast<cudaStream_t>(stream);
+  if (!backward) {
+    const int n = B * (C / 2);
+    mean_pool_fwd_kernel<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const bf16*>(in), reinterpret_cast<bf16*>(out), B, T, C);
+  } else {
+    const long long n = 1LL * B * T * (C / 2);
+    mean_pool_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const bf16*>(in), reinterpret_cast<bf16*>(out), B, T, C);
+  }
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+extern "C" int b200_transpose16(const void* in, void* out, long long R, int Cc, long long ld_in, long long ld_out, void* stream) {
+  B200_REQUIRE(Cc % 2 == 0 && ld_in % 2 == 0 && ld_out % 2 == 0, "transpose16: even column count / pitches required");
+  if (R == 0 || Cc == 0) return B200_OK;
+  dim3 grid(static_cast<unsigned>((R + 63) / 64), (Cc + 63) / 64);
+  transpose16_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const uint16_t*>(in),
+                                                                              reinterpret_cast<uint16_t*>(out), R, Cc, ld_in, ld_out);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+extern "C" int b200_cast_transpose(const float* in, void* dst, void* dst_t, int R, int Cc, void* stream) {
+  if (R == 0 || Cc == 0) return B200_OK;
+  dim3 grid((R + 31) / 32, (Cc + 31) / 32);
+  cast_transpose_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(in, reinterpret_cast<bf16*>(dst),
+                                                                                 reinterpret_cast<bf16*>(dst_t), R, Cc);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+extern "C" int b200_cast_f32_bf16(const float* in, void* out, long long n, void* stream) {
+  if (n == 0) return B200_OK;
+  B200_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0, "cast: alignment");
+  const long long thr = (n + 3) / 4;
+  cast_f32_bf16_kernel<<<(unsigned)((thr + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(in, reinterpret_cast<bf16*>(out), n);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+extern "C" int b200_colsum_blocks(long long M) {
+  long long b = (M + 255) / 256;
+  const int cap = b200_num_sms() * 4;
+  if (b > cap) b = cap;
+  return b < 1 ? 1 : static_cast<int>(b);
+}
+
+extern "C" int b200_colsum(const void* x, long long ld, long long M, int N, float* out, float* partial, int accumulate, void* stream) {
+  B200_REQUIRE(N % 4 == 0 && ld % 2 == 0, "colsum: N %% 4, ld %% 2");
+  if (M == 0) return B200_OK;
+  const int blocks = b200_colsum_blocks(M);
+  const long long rpb = (M + blocks - 1) / blocks;
+  colsum_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const bf16*>(x), partial, M, N, ld, rpb);
+  B200_LAUNCH_CHECK();
+  return b200_splitk_reduce(partial, out, N, blocks, accumulate, stream);
+}
+
+extern "C" int b200_opt_chunk_elems(void) { return kChunk; }
+
+extern "C" int b200_optimizer_step(int kind, const void* tensors_dev, const void* chunks_dev, int n_chunks, float grad_scale,
+                                   void* stream) {
+  if (n_chunks == 0) return B200_OK;
+  auto st = reinterpret_cast<cudaStream_t>(stream);
+  auto T = reinterpret_cast<const B200OptTensor*>(tensors_dev);
+  auto Ck = reinterpret_cast<const int2*>(chunks_dev);
+  if (kind == B200_OPT_SGD) sgd_kernel<<<n_chunks, 256, 0, st>>>(T, Ck, grad_scale);
+  else if (kind == B200_OPT_ADAMW) adamw_kernel<<<n_chunks, 256, 0, st>>>(T, Ck, grad_scale);
+  else return b200_set_error(B200_ERR_INVALID, "optimizer_step: unknown kind %d", kind);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}

@@ -1,0 +1,309 @@
+// Linear-layer GEMMs on the tcgen05 core: forward (bias / GELU / residual epilogues), data-gradient
+// (optionally fused with GELU'), weight-gradient (split-K partials + deterministic reduce) and the
+// ArcFace logits GEMM with the margin + scale epilogue (losses/large_margin.py:69-84 of the reference).
+#include "gemm_core.cuh"
+
+#include <cmath>
+#include <mutex>
+
+#include "b200_fe.h"
+
+// ---------------------------------------------------------------------------------------------
+// library-wide error state + device info
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+int b200_set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+extern "C" const char* b200_last_error(void) { return g_err; }
+
+int b200_num_sms() {
+  static int sms[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (sms[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    sms[dev] = v;
+  }
+  return sms[dev];
+}
+
+extern "C" int b200_device_check(void) {
+  int dev = 0;
+  B200_CHECK_CUDA(cudaGetDevice(&dev));
+  int major = 0, minor = 0;
+  B200_CHECK_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  B200_CHECK_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  if (major != 10) return b200_set_error(B200_ERR_ARCH, "device %d is sm_%d%d; this library is sm_100a only", dev, major, minor);
+  return B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA descriptor encoding through the driver entry point (no link-time libcuda dependency)
+// ---------------------------------------------------------------------------------------------
+namespace gemm {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int encode_tmap_2d(CUtensorMap* map, bool is_bf16, const void* ptr, uint64_t inner, uint64_t outer, uint64_t pitch_elems,
+                   uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return b200_set_error(B200_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {pitch_elems * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                  const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return b200_set_error(B200_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) inner=%llu outer=%llu pitch=%llu box=%ux%u",
+                          (int)r, (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)pitch_elems,
+                          box_inner, box_outer);
+  return B200_OK;
+}
+
+// Tile width: N itself (rounded to 16) when it fits one tile, otherwise the width in [128,256] that
+// wastes the fewest padded columns (ties -> wider).  96->96, 288->144, 384->192, 768->256, 1152->192.
+int pick_block_n(int N) {
+  if (N <= kMaxBlockN) return (N + 15) / 16 * 16;
+  int best = kMaxBlockN;
+  long long best_pad = -1;
+  for (int d = kMaxBlockN; d >= 128; d -= 16) {
+    long long pad = 1LL * ((N + d - 1) / d) * d - N;
+    if (best_pad < 0 || pad < best_pad) { best_pad = pad; best = d; }
+  }
+  return best;
+}
+
+// ---------------------------------------------------------------------------------------------
+// epilogue for linear layers.  Each epilogue thread owns one output row and gets 16 consecutive
+// fp32 accumulator columns per call.
+// ---------------------------------------------------------------------------------------------
+struct EpiLinear {
+  struct Params {
+    int mode;                 // B200_EPI_*
+    void* out; long long ldo; int out_fp32;
+    bf16* out2; long long ldo2;         // GELU mode: pre-activation copy
+    const float* bias;                   // [N] or null
+    const bf16* aux; long long ldaux;   // RESID: residual input; DGELU: saved pre-activation
+    long long split_stride;              // PARTIAL: elements between the fp32 partials of two splits
+  };
+
+  __device__ static __forceinline__ void begin_tile(const Params&, const CoreParams&, int, int, int) {}
+  __device__ static __forceinline__ void end_tile(const Params&, const CoreParams&, int, int, int) {}
+
+  __device__ static __forceinline__ void store_bf16x8(bf16* dst, const float* x) {
+    uint4 u;
+    u.x = pack_bf16(x[0], x[1]); u.y = pack_bf16(x[2], x[3]); u.z = pack_bf16(x[4], x[5]); u.w = pack_bf16(x[6], x[7]);
+    *reinterpret_cast<uint4*>(dst) = u;
+  }
+  __device__ static __forceinline__ void load_bf16x8(const bf16* src, float* x) {
+    const uint4 u = *reinterpret_cast<const uint4*>(src);
+    float2 f;
+    f = unpack_bf16(u.x); x[0] = f.x; x[1] = f.y;
+    f = unpack_bf16(u.y); x[2] = f.x; x[3] = f.y;
+    f = unpack_bf16(u.z); x[4] = f.x; x[5] = f.y;
+    f = unpack_bf16(u.w); x[6] = f.x; x[7] = f.y;
+  }
+
+  __device__ static __forceinline__ void apply(const Params& ep, const CoreParams& p, int row, int col, int split,
+                                               const float (&v)[16]) {
+    if (row >= p.M || col >= p.N) return;
+    const int ngroups = (p.N - col) >= 16 ? 2 : 1;     // N % 8 == 0 is required by the launcher
+    float x[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = v[i];
+    if (ep.bias != nullptr) {
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        if (g < ngroups) {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + col + g * 8));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + col + g * 8 + 4));
+          x[g * 8 + 0] += b0.x; x[g * 8 + 1] += b0.y; x[g * 8 + 2] += b0.z; x[g * 8 + 3] += b0.w;
+          x[g * 8 + 4] += b1.x; x[g * 8 + 5] += b1.y; x[g * 8 + 6] += b1.z; x[g * 8 + 7] += b1.w;
+        }
+      }
+    }
+    if (ep.mode == B200_EPI_PARTIAL) {
+      float* dst = reinterpret_cast<float*>(ep.out) + split * ep.split_stride + 1LL * row * ep.ldo + col;
+#pragma unroll
+      for (int g = 0; g < 2; ++g)
+        if (g < ngroups) {
+          *reinterpret_cast<float4*>(dst + g * 8) = make_float4(x[g * 8], x[g * 8 + 1], x[g * 8 + 2], x[g * 8 + 3]);
+          *reinterpret_cast<float4*>(dst + g * 8 + 4) = make_float4(x[g * 8 + 4], x[g * 8 + 5], x[g * 8 + 6], x[g * 8 + 7]);
+        }
+      return;
+    }
+    if (ep.mode == B200_EPI_GELU) {
+#pragma unroll
+      for (int g = 0; g < 2; ++g)
+        if (g < ngroups && ep.out2 != nullptr) store_bf16x8(ep.out2 + 1LL * row * ep.ldo2 + col + g * 8, x + g * 8);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) x[i] = gelu_erf(x[i]);
+    } else if (ep.mode == B200_EPI_RESID) {
+#pragma unroll
+      for (int g = 0; g < 2; ++g)
+        if (g < ngroups) {
+          float r[8];
+          load_bf16x8(ep.aux + 1LL * row * ep.ldaux + col + g * 8, r);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) x[g * 8 + i] += r[i];
+        }
+    } else if (ep.mode == B200_EPI_DGELU) {
+#pragma unroll
+      for (int g = 0; g < 2; ++g)
+        if (g < ngroups) {
+          float r[8];
+          load_bf16x8(ep.aux + 1LL * row * ep.ldaux + col + g * 8, r);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) x[g * 8 + i] *= gelu_erf_grad(r[i]);
+        }
+    }
+    if (ep.out_fp32) {
+      float* dst = reinterpret_cast<float*>(ep.out) + 1LL * row * ep.ldo + col;
+#pragma unroll
+      for (int g = 0; g < 2; ++g)
+        if (g < ngroups) {
+          *reinterpret_cast<float4*>(dst + g * 8) = make_float4(x[g * 8], x[g * 8 + 1], x[g * 8 + 2], x[g * 8 + 3]);
+          *reinterpret_cast<float4*>(dst + g * 8 + 4) = make_float4(x[g * 8 + 4], x[g * 8 + 5], x[g * 8 + 6], x[g * 8 + 7]);
+        }
+    } else {
+      bf16* dst = reinterpret_cast<bf16*>(ep.out) + 1LL * row * ep.ldo + col;
+#pragma unroll
+      for (int g = 0; g < 2; ++g)
+        if (g < ngroups) store_bf16x8(dst + g * 8, x + g * 8);
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// ArcFace / CosFace logits epilogue: operands are the unit-norm bf16 rows of the embeddings and of
+// the class weights, so the accumulator IS cos(theta).  Margin on the label column, then * s.
+// ---------------------------------------------------------------------------------------------
+struct EpiMargin {
+  struct Params {
+    float* logits; long long ldo;        // [B, C] fp32
+    float* cos_label;                     // [B] cos(theta) at the label column (for backward)
+    const long long* label;               // [B] int64
+    float s, cos_m, sin_m, th, mm, m;
+    int kind;                             // 0 = ArcFace, 1 = CosFace (AddMarginProduct)
+    int easy_margin;
+  };
+  __device__ static __forceinline__ void begin_tile(const Params&, const CoreParams&, int, int, int) {}
+  __device__ static __forceinline__ void end_tile(const Params&, const CoreParams&, int, int, int) {}
+  __device__ static __forceinline__ void apply(const Params& ep, const CoreParams& p, int row, int col, int,
+                                               const float (&v)[16]) {
+    if (row >= p.M || col >= p.N) return;
+    const int lab = static_cast<int>(ep.label[row]);
+    float x[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      float c = v[i];
+      if (col + i == lab) {
+        ep.cos_label[row] = c;
+        if (ep.kind == 1) {
+          c = c - ep.m;
+        } else {
+          // reference takes sqrt(1 - cos^2) unclamped (NaN when rounding gives |cos| > 1); clamped here
+          const float sine = sqrtf(fmaxf(1.0f - c * c, 0.0f));
+          const float phi = c * ep.cos_m - sine * ep.sin_m;
+          c = ep.easy_margin ? (c > 0.0f ? phi : c) : (c > ep.th ? phi : c - ep.mm);
+        }
+      }
+      x[i] = c * ep.s;
+    }
+    float* dst = ep.logits + 1LL * row * ep.ldo + col;
+    const int n = min(16, p.N - col);
+    if (n == 16 && (ep.ldo & 3) == 0) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) *reinterpret_cast<float4*>(dst + 4 * g) = make_float4(x[4 * g], x[4 * g + 1], x[4 * g + 2], x[4 * g + 3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (i < n) dst[i] = x[i];
+    }
+  }
+};
+
+}  // namespace gemm
+
+// ---------------------------------------------------------------------------------------------
+// split-K reduce: out[i] (+)= sum_s partial[s][i], fixed order -> deterministic
+// ---------------------------------------------------------------------------------------------
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, long long n, int splits,
+                                     int accumulate) {
+  const long long i4 = (1LL * blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 >= n) return;
+  float4 acc = accumulate ? *reinterpret_cast<const float4*>(out + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s < splits; ++s) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(partial + 1LL * s * n + i4));
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  *reinterpret_cast<float4*>(out + i4) = acc;
+}
+
+int splitk_reduce(const float* partial, float* out, long long n, int splits, int accumulate, cudaStream_t stream) {
+  B200_REQUIRE(n % 4 == 0, "splitk_reduce: n %% 4 != 0");
+  const int threads = 256;
+  const long long blocks = (n / 4 + threads - 1) / threads;
+  splitk_reduce_kernel<<<(unsigned)blocks, threads, 0, stream>>>(partial, out, n, splits, accumulate);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" int b200_gemm_tn(const void* a, long long lda, const void* b, long long ldb, int M, int N, int K, int is_bf16,
+                            int mode, void* out, long long ldo, int out_fp32, void* out2, long long ldo2, const float* bias,
+                            const void* aux, long long ldaux, int splits, long long split_stride, int block_n, void* stream) {
+  B200_REQUIRE(N % 8 == 0, "gemm_tn: N must be a multiple of 8 (got %d)", N);
+  B200_REQUIRE(mode >= B200_EPI_STORE && mode <= B200_EPI_PARTIAL, "gemm_tn: bad epilogue mode %d", mode);
+  B200_REQUIRE(ldo % (out_fp32 || mode == B200_EPI_PARTIAL ? 4 : 8) == 0, "gemm_tn: ldo alignment");
+  if (mode == B200_EPI_GELU && out2 != nullptr) B200_REQUIRE(ldo2 % 8 == 0, "gemm_tn: ldo2 alignment");
+  if (mode == B200_EPI_RESID || mode == B200_EPI_DGELU) B200_REQUIRE(aux != nullptr && ldaux % 8 == 0, "gemm_tn: mode needs aux");
+  if (mode != B200_EPI_PARTIAL) B200_REQUIRE(splits <= 1, "gemm_tn: split-K only with the PARTIAL epilogue");
+  gemm::Operands o{a, (int)lda, b, (int)ldb, M, N, K, is_bf16 != 0, block_n, splits, 0};
+  gemm::EpiLinear::Params ep{mode, out, ldo, out_fp32, reinterpret_cast<bf16*>(out2), ldo2, bias,
+                             reinterpret_cast<const bf16*>(aux), ldaux, split_stride};
+  return gemm::launch<gemm::EpiLinear>(o, ep, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200_gemm_splits(int K, int splits) { return gemm::effective_splits(K, splits); }
+
+extern "C" int b200_splitk_reduce(const float* partial, float* out, long long n, int splits, int accumulate, void* stream) {
+  return splitk_reduce(partial, out, n, splits, accumulate, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int b200_margin_logits(const void* emb_unit, const void* w_unit, int B, int C, int E, const long long* label,
+                                  float s, float m, int kind, int easy_margin, float* logits, long long ldo,
+                                  float* cos_label, void* stream) {
+  B200_REQUIRE(E % 8 == 0, "margin_logits: embedding size must be a multiple of 8");
+  gemm::Operands o{emb_unit, E, w_unit, E, B, C, E, true, 0, 1, 0};
+  const double md = static_cast<double>(m), pi = 3.14159265358979323846;   // constants as in large_margin.py:64-67
+  gemm::EpiMargin::Params ep{logits, ldo, cos_label, label, s, (float)cos(md), (float)sin(md), (float)cos(pi - md),
+                             (float)(sin(pi - md) * md), m, kind, easy_margin};
+  return gemm::launch<gemm::EpiMargin>(o, ep, reinterpret_cast<cudaStream_t>(stream));
+}

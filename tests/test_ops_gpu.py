@@ -1,0 +1,207 @@
+"""Kernel-level parity (B200 only): every exported kernel, called through the C ABI, against the fp32
+oracle / a plain torch fp32 statement of the same op on the same seeded inputs.
+
+Tolerances: operands are bf16 (8 mantissa bits, eps = 2^-8 = 3.9e-3) with fp32 accumulation, so outputs are
+compared after the same bf16 rounding of the inputs, at ~2 bf16 ulps of the output magnitude.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
+
+DEV = 'cuda'
+bf16 = torch.bfloat16
+
+
+@pytest.fixture(scope='module', autouse=True)
+def _need_gpu():
+    from b200 import abi
+    abi.require_device()
+
+
+def rnd(*shape, seed=0, scale=1.0, dtype=bf16):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV).to(dtype)
+
+
+def rel_err(got, ref):
+    got, ref = got.float(), ref.float()
+    return ((got - ref).norm() / ref.norm().clamp_min(1e-20)).item()
+
+
+@pytest.mark.parametrize('M,N,K', [(128, 96, 64), (256, 96, 48), (1000, 192, 96), (130, 288, 96), (4096, 384, 96),
+                                   (392, 768, 3072), (257, 2304, 768), (64, 10000, 512), (2, 512, 768), (6272, 96, 384)])
+def test_gemm_store(M, N, K):
+    from b200 import ops
+    a, b = rnd(M, K, seed=1), rnd(N, K, seed=2)
+    bias = rnd(N, seed=3, dtype=torch.float32)
+    ref = a.float() @ b.float().t() + bias
+    out = ops.gemm_tn(a, b, bias=bias)
+    assert out.dtype == bf16 and out.shape == (M, N)
+    assert rel_err(out, ref) < 6e-3
+    out32 = ops.gemm_tn(a, b, bias=bias, out_fp32=True)
+    assert rel_err(out32, ref) < 1e-5 * math.sqrt(K) + 1e-6
+    assert (out32 - ref).abs().max().item() < 1e-3 * math.sqrt(K)
+
+
+def test_gemm_fp16_inputs():
+    from b200 import ops
+    a, b = rnd(300, 512, seed=4, dtype=torch.float16), rnd(700, 512, seed=5, dtype=torch.float16)
+    out = ops.gemm_tn(a, b, out_fp32=True)
+    assert rel_err(out, a.float() @ b.float().t()) < 1e-4
+
+
+def test_gemm_epilogues():
+    from b200 import abi, ops
+    M, N, K = 1024, 384, 96
+    a, b = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=0.2)
+    bias = rnd(N, seed=3, dtype=torch.float32)
+    pre_ref = a.float() @ b.float().t() + bias
+    act, pre = ops.gemm_tn(a, b, bias=bias, mode=abi.EPI_GELU, want_pre=True)
+    assert rel_err(pre, pre_ref) < 6e-3
+    assert rel_err(act, torch.nn.functional.gelu(pre_ref)) < 6e-3
+    res = rnd(M, N, seed=7)
+    out = ops.gemm_tn(a, b, bias=bias, mode=abi.EPI_RESID, aux=res)
+    assert rel_err(out, pre_ref + res.float()) < 6e-3
+    x = rnd(M, N, seed=8)
+    xr = x.float().requires_grad_(True)
+    torch.nn.functional.gelu(xr).sum().backward()
+    out = ops.gemm_tn(a, b, mode=abi.EPI_DGELU, aux=x)
+    assert rel_err(out, (a.float() @ b.float().t()) * xr.grad) < 6e-3
+
+
+@pytest.mark.parametrize('M,N,K,splits', [(384, 96, 50000, 37), (96, 48, 6272, 148), (768, 256, 1000, 3), (512, 768, 2, 4)])
+def test_gemm_splitk_partial(M, N, K, splits):
+    from b200 import abi, ops
+    a, b = rnd(M, K, seed=1, scale=0.1), rnd(N, K, seed=2, scale=0.1)
+    part = ops.gemm_tn(a, b, mode=abi.EPI_PARTIAL, splits=splits)
+    out = ops.splitk_reduce(part)
+    ref = a.float() @ b.float().t()
+    assert rel_err(out, ref) < 2e-5 * math.sqrt(K) + 1e-6
+    out2 = ops.splitk_reduce(part, out.clone(), accumulate=True)
+    assert rel_err(out2, 2 * ref) < 2e-5 * math.sqrt(K) + 1e-6
+
+
+@pytest.mark.parametrize('C', [96, 192, 384, 768])
+@pytest.mark.parametrize('M', [1, 49, 1000])
+def test_layernorm(C, M):
+    from b200 import ops
+    x = rnd(M, C, seed=1, scale=2.0) + 0.5
+    g = 1 + 0.1 * rnd(C, seed=2, dtype=torch.float32)
+    b = 0.1 * rnd(C, seed=3, dtype=torch.float32)
+    y, mean, rstd = ops.layernorm_fwd(x, g, b)
+    xr = x.float().requires_grad_(True)
+    gr, br = g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yr = torch.nn.functional.layer_norm(xr, (C,), gr, br, 1e-5)
+    assert (y.float() - yr).abs().max().item() < 4e-2 and rel_err(y, yr) < 5e-3
+    np.testing.assert_allclose(mean.cpu().numpy(), x.float().mean(1).cpu().numpy(), rtol=1e-4, atol=1e-5)
+    dy = rnd(M, C, seed=4)
+    dres = rnd(M, C, seed=5)
+    yr.backward(dy.float())
+    dx, dgam, dbet = ops.layernorm_bwd(dy, x, g, mean, rstd, dres=dres)
+    assert rel_err(dx, xr.grad + dres.float()) < 6e-3
+    assert rel_err(dgam, gr.grad) < 1e-3 and rel_err(dbet, br.grad) < 1e-3
+
+
+def test_patch_gather_matches_unfold():
+    from b200 import ops
+    from oracle.swin_oracle import patch_merge
+    img = torch.rand(3, 3, 56, 56, generator=torch.Generator().manual_seed(0)).to(DEV)
+    cols = ops.patch_gather_image(img)
+    eye = torch.eye(48, device=DEV)
+    ref = patch_merge(img.permute(0, 2, 3, 1), eye, torch.zeros(48, device=DEV), 4).reshape(-1, 48)
+    assert torch.equal(cols, ref.to(bf16))
+    # same order as nn.Unfold itself (models/swin.py:159,165)
+    unf = torch.nn.Unfold(4, stride=4)(img).view(3, 48, 14, 14).permute(0, 2, 3, 1).reshape(-1, 48)
+    assert torch.equal(cols, unf.to(bf16))
+    B, H, W, C = 2, 14, 28, 64
+    x = rnd(B * H * W, C, seed=3)
+    cols = ops.patch_gather_nhwc(x, B, H, W, C)
+    unf = torch.nn.Unfold(2, stride=2)(x.float().view(B, H, W, C).permute(0, 3, 1, 2)).view(B, 4 * C, H // 2, W // 2)
+    assert torch.equal(cols, unf.permute(0, 2, 3, 1).reshape(-1, 4 * C).to(bf16))
+    back = ops.patch_scatter_nhwc(cols, B, H, W, C)      # scatter is the exact inverse
+    assert torch.equal(back, x)
+
+
+def test_mean_pool_transpose_colsum_cast():
+    from b200 import ops
+    B, T, C = 5, 49, 768
+    x = rnd(B * T, C, seed=1)
+    y = ops.mean_pool(x, B, T, C)
+    assert rel_err(y, x.float().view(B, T, C).mean(1)) < 4e-3
+    dy = rnd(B, C, seed=2)
+    dx = ops.mean_pool_bwd(dy, B, T, C)
+    assert rel_err(dx, (dy.float() / T)[:, None, :].expand(B, T, C).reshape(-1, C)) < 4e-3
+    for R, Cc in [(100, 96), (3136, 384), (7, 48), (129, 130)]:
+        m = rnd(R, Cc, seed=R)
+        assert torch.equal(ops.transpose16(m), m.t())
+    w = rnd(288, 96, seed=9, dtype=torch.float32)
+    d, dt = ops.cast_transpose(w)
+    assert torch.equal(d, w.to(bf16)) and torch.equal(dt, w.to(bf16).t())
+    m = rnd(5000, 384, seed=11)
+    assert rel_err(ops.colsum(m), m.float().sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize('heads,H,W,shifted', [(3, 14, 14, 0), (3, 14, 14, 1), (6, 7, 7, 1), (2, 21, 14, 1), (24, 7, 7, 0), (1, 28, 28, 1)])
+def test_window_attention_fwd_bwd(heads, H, W, shifted):
+    from b200 import ops
+    from oracle.swin_oracle import attention_core
+    B, C = 2, heads * 32
+    qkv = rnd(B * H * W, 3 * C, seed=1)
+    pos = rnd(13, 13, seed=2, dtype=torch.float32)
+    out, lse = ops.window_attn_fwd(qkv, pos, B, H, W, C, heads, shifted)
+    q_ref = qkv.float().cpu().view(B, H, W, 3 * C).requires_grad_(True)
+    p_ref = pos.cpu().clone().requires_grad_(True)
+    ref = attention_core(q_ref, p_ref, heads, 32, 7, bool(shifted))
+    assert torch.isfinite(out.float()).all()
+    assert rel_err(out.cpu(), ref.reshape(-1, C)) < 8e-3
+    dout = rnd(B * H * W, C, seed=3)
+    ref.backward(dout.float().cpu().view(B, H, W, C))
+    dqkv, dpos = ops.window_attn_bwd(qkv, pos, out, lse, dout, B, H, W, C, heads, shifted)
+    assert torch.isfinite(dqkv.float()).all()
+    assert rel_err(dqkv.cpu(), q_ref.grad.reshape(-1, 3 * C)) < 1.5e-2
+    assert rel_err(dpos.cpu(), p_ref.grad) < 1e-2
+
+
+def test_margin_head_against_oracle_and_golden(golden_dir):
+    from b200 import ops
+    from oracle import head_oracle
+    g = np.load(golden_dir / 'heads_small.npz')
+    e = torch.tensor(g['emb']).to(DEV).requires_grad_(True)
+    w = torch.tensor(g['weight']).to(DEV).requires_grad_(True)
+    lab = torch.tensor(g['label']).to(DEV)
+    loss, logits = ops.margin_head(e, w, lab, 64.0, 0.5, 0, False, 0.0)
+    # bf16 unit vectors: |d cos| <~ 2^-9 -> |d logit| <~ 64 * 4e-3
+    np.testing.assert_allclose(logits.cpu().numpy(), g['arcface'], atol=0.35)
+    assert abs(loss.item() - float(g['focal_g0'])) < 0.05 * float(g['focal_g0']) + 0.05
+    loss.backward()
+    assert rel_err(e.grad.cpu(), torch.tensor(g['demb'])) < 3e-2
+    assert rel_err(w.grad.cpu(), torch.tensor(g['dweight'])) < 3e-2
+    _, lc = ops.margin_head(e.detach(), w.detach(), lab, 64.0, 0.5, 1, False, 0.0)
+    np.testing.assert_allclose(lc.cpu().numpy(), g['cosface'], atol=0.35)
+    # larger random case, gamma = 2, vs the oracle
+    B, Cn = 64, 1000
+    e2 = rnd(B, 512, seed=1, dtype=torch.float32).requires_grad_(True)
+    w2 = rnd(Cn, 512, seed=2, dtype=torch.float32, scale=0.05).requires_grad_(True)
+    lab2 = torch.randint(0, Cn, (B,), generator=torch.Generator().manual_seed(3)).to(DEV)
+    for gamma in (0.0, 2.0):
+        e2.grad = w2.grad = None
+        loss, logits = ops.margin_head(e2, w2, lab2, 64.0, 0.5, 0, False, gamma)
+        ec, wc = e2.detach().cpu().requires_grad_(True), w2.detach().cpu().requires_grad_(True)
+        lref = head_oracle.arcface_logits(ec, wc, lab2.cpu(), clamp_sine=True)
+        ref = head_oracle.focal_loss(lref, lab2.cpu(), gamma)
+        ref.backward()
+        assert (logits.cpu() - lref).abs().max().item() < 0.35
+        assert abs(loss.item() - ref.item()) < 2e-2 * abs(ref.item())
+        loss.backward()
+        assert rel_err(e2.grad.cpu(), ec.grad) < 3e-2
+        assert rel_err(w2.grad.cpu(), wc.grad) < 3e-2
+
+
+def test_cpu_tensors_are_rejected():
+    from b200 import abi, ops
+    with pytest.raises(abi.B200Error):
+        ops.layernorm_fwd(torch.zeros(4, 96, dtype=bf16), torch.ones(96), torch.zeros(96))
