@@ -33,6 +33,9 @@ extern "C" {
 #define B200_EPI_DGELU 3   /* out = acc * gelu_erf'(aux)                           autograd of models/swin.py:41  */
 #define B200_EPI_PARTIAL 4 /* fp32 out[split] = acc   (split-K partial, weight gradients)                     */
 
+/* b200_cosine_topk: pass as exclude_self_offset when no gallery row is to be skipped */
+#define B200_NO_EXCLUDE (-(1LL << 62))
+
 #define B200_OPT_SGD 0
 #define B200_OPT_ADAMW 1
 
@@ -65,7 +68,7 @@ int b200_layernorm_fwd(const void* x, const float* gamma, const float* beta, voi
                        int C, float eps, void* stream);
 int b200_layernorm_bwd_blocks(long long M, int C); /* rows of the [blocks, 2C] fp32 partial buffer */
 int b200_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
-                       const void* dres_in, void* dx_out, float* dgamma_dbeta, float* partial, long long M, int C,
+                       const void* dres_in, void* dx_out, float* dgamma, float* dbeta, float* partial, long long M, int C,
                        int accumulate, void* stream);
 
 /* ---- patch merging gather == nn.Unfold(k=s=df) + NHWC view (models/swin.py:159,162-165) ---------------------- */

@@ -43,7 +43,7 @@ _PROTOS = {
     'b200_splitk_reduce': (c_int, [c_vp, c_vp, c_ll, c_int, c_int, c_vp]),
     'b200_layernorm_fwd': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, c_int, c_float, c_vp]),
     'b200_layernorm_bwd_blocks': (c_int, [c_ll, c_int]),
-    'b200_layernorm_bwd': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, c_int, c_int, c_vp]),
+    'b200_layernorm_bwd': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, c_int, c_int, c_vp]),
     'b200_patch_gather_image': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_ll, c_vp]),
     'b200_patch_gather_nhwc': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
     'b200_mean_pool': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]),
@@ -83,7 +83,8 @@ _PROTOS = {
 }
 
 
-_PENDING = {'b200_gallery_prepare', 'b200_cosine_topk_workspace_bytes', 'b200_cosine_topk', 'b200_topk_merge', 'b200_recall_hits'}
+_PENDING = set()
+NO_EXCLUDE = -(1 << 62)
 
 
 def lib_path() -> Path:

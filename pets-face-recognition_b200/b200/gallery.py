@@ -1,0 +1,165 @@
+"""Gallery matching on the B200 kernels (csrc/gallery.cu): cosine top-k and Recall@K (candR@k).
+
+Replaces the O(N^2) Python loop of the reference's Controller.test_epoch_end / _evaluate
+(engine/controller.py:77-91, :143-160) and the all-pairs scoring of generate_tsv_to_reproduce2.py:63-119.
+Ranking is by cosine (similarity_f's (cos + 1) / 2 is monotone), under the deterministic order
+(score desc, gallery index asc) - see oracle/rank_oracle.py:topk_spec.
+"""
+from __future__ import annotations
+
+from typing import Dict, Iterable, Optional, Tuple
+
+import torch
+
+from . import abi
+from .abi import check, lib, ptr, stream_ptr
+
+
+def prepare(emb: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """fp32 [n, dim] -> (unit fp16 rows [n, dim], fp64 norms [n])."""
+    emb = emb.contiguous().float()
+    n, dim = emb.shape
+    unit = torch.empty(n, dim, device=emb.device, dtype=torch.float16)
+    norm = torch.empty(n, device=emb.device, dtype=torch.float64)
+    check(lib().b200_gallery_prepare(ptr(emb), ptr(unit), ptr(norm), n, dim, stream_ptr()), 'gallery_prepare')
+    return unit, norm
+
+
+def cosine_topk(q: torch.Tensor, g: torch.Tensor, k: int, exclude_self_offset: Optional[int] = None, g_index_base: int = 0,
+                q_prepared=None, g_prepared=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Top-k gallery rows per query: (idx int32 [nq, k] (+ g_index_base, -1 = none), score fp64 [nq, k]).
+    exclude_self_offset = o skips gallery row (o + i) for query i (leave-one-out, engine/controller.py:80)."""
+    abi.require_device()
+    q = q.contiguous().float()
+    g = g.contiguous().float()
+    nq, dim = q.shape
+    ng = g.shape[0]
+    qu, qn = q_prepared if q_prepared is not None else prepare(q)
+    gu, gn = g_prepared if g_prepared is not None else (
+        (qu, qn) if (g.data_ptr() == q.data_ptr() and ng == nq) else prepare(g))
+    idx = torch.empty(nq, k, device=q.device, dtype=torch.int32)
+    score = torch.empty(nq, k, device=q.device, dtype=torch.float64)
+    wsb = lib().b200_cosine_topk_workspace_bytes(nq, ng, dim, k)
+    ws = torch.empty(wsb, device=q.device, dtype=torch.uint8)
+    off = abi.NO_EXCLUDE if exclude_self_offset is None else int(exclude_self_offset)
+    check(lib().b200_cosine_topk(ptr(q), ptr(qu), ptr(qn), nq, ptr(g), ptr(gu), ptr(gn), ng, dim, k, off, g_index_base,
+                                 ptr(idx), ptr(score), ptr(ws), wsb, stream_ptr()), 'cosine_topk')
+    return idx, score
+
+
+def topk_merge(scores: torch.Tensor, idx: torch.Tensor, k_out: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Merge `lists` already-scored top lists per query.  scores fp64 / idx int32: [lists, nq, k_in]."""
+    lists, nq, k_in = scores.shape
+    out_idx = torch.empty(nq, k_out, device=scores.device, dtype=torch.int32)
+    out_score = torch.empty(nq, k_out, device=scores.device, dtype=torch.float64)
+    check(lib().b200_topk_merge(ptr(scores.contiguous()), ptr(idx.contiguous()), nq, lists, k_in, k_out, ptr(out_idx), ptr(out_score),
+                                stream_ptr()), 'topk_merge')
+    return out_idx, out_score
+
+
+def recall_hits(top_idx: torch.Tensor, q_class: torch.Tensor, g_class: torch.Tensor, ks: Iterable[int]) -> torch.Tensor:
+    """hits[i] = #queries with a same-class gallery row among their first ks[i] candidates (engine/controller.py:86-87)."""
+    ks = list(ks)
+    kst = torch.tensor(ks, dtype=torch.int32, device=top_idx.device)
+    hits = torch.zeros(len(ks), dtype=torch.int64, device=top_idx.device)
+    check(lib().b200_recall_hits(ptr(top_idx.contiguous()), top_idx.shape[0], top_idx.shape[1], ptr(q_class.contiguous().long()),
+                                 ptr(g_class.contiguous().long()), ptr(kst), len(ks), ptr(hits), stream_ptr()), 'recall_hits')
+    return hits
+
+
+def valid_queries(q_class: torch.Tensor, g_class: torch.Tensor, leave_one_out: bool) -> torch.Tensor:
+    """Denominator of engine/controller.py:88: queries with at least one same-class gallery row (other than themselves)."""
+    uniq, counts = torch.unique(g_class, return_counts=True)
+    pos = torch.searchsorted(uniq, q_class).clamp_(max=uniq.numel() - 1)
+    same = torch.where(uniq[pos] == q_class, counts[pos], torch.zeros_like(counts[pos]))
+    if leave_one_out:
+        same = same - 1
+    return (same > 0).sum()
+
+
+def recall_at_k(emb: torch.Tensor, classes: torch.Tensor, ks: Iterable[int] = (10, 100)) -> Dict[str, float]:
+    """Leave-one-out Recall@K over one embedding set, the metric Controller.test_epoch_end prints
+    (engine/controller.py:77-91).  k larger than N-1 behaves like the reference (all others ranked)."""
+    ks = list(ks)
+    n = emb.shape[0]
+    kmax = max(1, min(max(ks), 100, n - 1))
+    if max(ks) > 100:
+        raise abi.B200Error('Recall@K is built for K <= 100 (the reference uses 5, 10, 100)')
+    idx, _ = cosine_topk(emb, emb, kmax, exclude_self_offset=0)
+    hits = recall_hits(idx, classes, classes, ks).tolist()
+    valid = int(valid_queries(classes, classes, True).item())
+    return {f'Recall@K={k}': (h / valid if valid else float('nan')) for k, h in zip(ks, hits)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# multi-GPU: one process per GPU, torch.distributed for the plumbing (NCCL on GPUs; gloo in the CPU tests)
+# ---------------------------------------------------------------------------------------------------------
+def _all_gather_rows(x: torch.Tensor, group=None) -> Tuple[torch.Tensor, list]:
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    n = torch.tensor([x.shape[0]], device=x.device, dtype=torch.int64)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    m = max(sizes)
+    pad = torch.zeros((m,) + tuple(x.shape[1:]), device=x.device, dtype=x.dtype)
+    pad[:x.shape[0]] = x
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad, group=group)
+    return torch.cat([b[:s] for b, s in zip(bufs, sizes)], dim=0), sizes
+
+
+def recall_at_k_sharded(emb_local, classes_local, ks=(10, 100), group=None, topk_fn=None, hits_fn=None) -> Dict[str, float]:
+    """Leave-one-out Recall@K with the embedding set sharded by rows over the ranks: all-gather the
+    embeddings, every rank ranks ITS OWN queries against everything (no merge needed), all-reduce the counts.
+    topk_fn / hits_fn default to the CUDA kernels; the CPU gloo tests inject the oracle to exercise the host logic."""
+    import torch.distributed as dist
+    ks = list(ks)
+    rank = dist.get_rank(group)
+    emb_all, sizes = _all_gather_rows(emb_local.contiguous().float(), group)
+    cls_all, _ = _all_gather_rows(classes_local.contiguous().long(), group)
+    start = sum(sizes[:rank])
+    kmax = max(1, min(max(ks), 100, emb_all.shape[0] - 1))
+    topk_fn = topk_fn or (lambda q, g, k, off: cosine_topk(q, g, k, exclude_self_offset=off)[0])
+    hits_fn = hits_fn or recall_hits
+    if emb_local.shape[0] > 0:
+        idx = topk_fn(emb_local.contiguous().float(), emb_all, kmax, start)
+        hits = hits_fn(idx, classes_local.long(), cls_all, ks).to(torch.int64)
+        uniq, counts = torch.unique(cls_all, return_counts=True)
+        pos = torch.searchsorted(uniq, classes_local.long())
+        valid = ((counts[pos] - 1) > 0).sum().to(torch.int64)
+    else:
+        hits = torch.zeros(len(ks), dtype=torch.int64, device=emb_local.device)
+        valid = torch.zeros((), dtype=torch.int64, device=emb_local.device)
+    tot = torch.cat([hits.to(emb_local.device), valid.reshape(1).to(emb_local.device)])
+    dist.all_reduce(tot, group=group)
+    tot = tot.tolist()
+    return {f'Recall@K={k}': (h / tot[-1] if tot[-1] else float('nan')) for k, h in zip(ks, tot[:-1])}
+
+
+def cosine_topk_gallery_sharded(q_local, g_local, k, group=None, topk_fn=None, merge_fn=None):
+    """BASELINE config 4 layout: the gallery is sharded by rows, queries are sharded too.  All-gather the queries,
+    local fused top-k against the local gallery shard (indices offset to global), all-gather the partial lists and
+    merge the lists of this rank's own queries.  Returns (idx int32 [nq_local, k] global gallery rows, score fp64)."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    q_all, qsizes = _all_gather_rows(q_local.contiguous().float(), group)
+    gcount = torch.tensor([g_local.shape[0]], device=g_local.device, dtype=torch.int64)
+    gs = [torch.zeros_like(gcount) for _ in range(world)]
+    dist.all_gather(gs, gcount, group=group)
+    g_base = sum(int(s.item()) for s in gs[:rank])
+    topk_fn = topk_fn or (lambda q, g, kk, base: cosine_topk(q, g, kk, g_index_base=base))
+    merge_fn = merge_fn or topk_merge
+    kk = min(k, max(1, g_local.shape[0]))
+    idx, score = topk_fn(q_all, g_local.contiguous().float(), kk, g_base)
+    if kk < k:       # pad short lists so that every rank contributes the same shape
+        pad_i = torch.full((idx.shape[0], k - kk), -1, dtype=idx.dtype, device=idx.device)
+        pad_s = torch.full((idx.shape[0], k - kk), float('-inf'), dtype=score.dtype, device=idx.device)
+        idx, score = torch.cat([idx, pad_i], 1), torch.cat([score, pad_s], 1)
+    idx_all = [torch.empty_like(idx) for _ in range(world)]
+    sc_all = [torch.empty_like(score) for _ in range(world)]
+    dist.all_gather(idx_all, idx.contiguous(), group=group)
+    dist.all_gather(sc_all, score.contiguous(), group=group)
+    q0 = sum(qsizes[:rank])
+    q1 = q0 + qsizes[rank]
+    return merge_fn(torch.stack([s[q0:q1] for s in sc_all]), torch.stack([i[q0:q1] for i in idx_all]), k)

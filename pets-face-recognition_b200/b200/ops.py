@@ -64,7 +64,7 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None):
     dgb = torch.empty(2, Cc, device=x.device, dtype=torch.float32)
     blocks = lib().b200_layernorm_bwd_blocks(M, Cc)
     partial = torch.empty(blocks, 2 * Cc, device=x.device, dtype=torch.float32)
-    check(lib().b200_layernorm_bwd(ptr(dy), ptr(x), ptr(gamma), ptr(mean), ptr(rstd), ptr(dres), ptr(dx), ptr(dgb), ptr(partial),
+    check(lib().b200_layernorm_bwd(ptr(dy), ptr(x), ptr(gamma), ptr(mean), ptr(rstd), ptr(dres), ptr(dx), ptr(dgb[0]), ptr(dgb[1]), ptr(partial),
                                    M, Cc, 0, stream_ptr()), 'layernorm_bwd')
     return dx, dgb[0], dgb[1]
 

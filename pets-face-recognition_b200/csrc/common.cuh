@@ -39,7 +39,9 @@ int b200_set_error(int code, const char* fmt, ...);
 
 #define B200_LAUNCH_CHECK() B200_CHECK_CUDA(cudaGetLastError())
 
-int b200_num_sms();   // cached cudaDevAttrMultiProcessorCount of the current device (148 on B200)
+int b200_num_sms();
+// out[i] (+)= sum_s partial[s * stride + i], i < n, fixed order (deterministic); stride <= 0 means n
+int splitk_reduce(const float* partial, float* out, long long n, int splits, int accumulate, cudaStream_t stream, long long stride);   // cached cudaDevAttrMultiProcessorCount of the current device (148 on B200)
 
 // ---------------------------------------------------------------------------------------------
 // small device helpers

@@ -476,7 +476,7 @@ extern "C" int b200_layernorm_bwd_blocks(long long M, int C) {
 }
 
 extern "C" int b200_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
-                                  const void* dres_in, void* dx_out, float* dgamma_dbeta, float* partial, long long M, int C,
+                                  const void* dres_in, void* dx_out, float* dgamma, float* dbeta, float* partial, long long M, int C,
                                   int accumulate, void* stream) {
   B200_REQUIRE(C % 8 == 0 && C >= 8 && C <= 1536, "layernorm_bwd: C=%d unsupported", C);
   if (M == 0) return B200_OK;
@@ -493,8 +493,9 @@ extern "C" int b200_layernorm_bwd(const void* dy, const void* x, const float* ga
   else if (C <= 768) rc = ln_bwd_launch<32, 3>(DY, X, gamma, mean, rstd, DR, DX, partial, M, C, blocks, st);
   else rc = ln_bwd_launch<32, 6>(DY, X, gamma, mean, rstd, DR, DX, partial, M, C, blocks, st);
   if (rc) return rc;
-  // dgamma_dbeta = [dgamma (C) | dbeta (C)] contiguous, as norm.weight / norm.bias are in the flat grad buffer
-  return b200_splitk_reduce(partial, dgamma_dbeta, 2LL * C, blocks, accumulate, stream);
+  rc = splitk_reduce(partial, dgamma, C, blocks, accumulate, st, 2LL * C);
+  if (rc) return rc;
+  return splitk_reduce(partial + C, dbeta, C, blocks, accumulate, st, 2LL * C);
 }
 
 extern "C" int b200_patch_gather_image(const float* img, void* out, int B, int Cin, int H, int W, int df, long long ldo,

@@ -253,22 +253,23 @@ struct EpiMargin {
 // split-K reduce: out[i] (+)= sum_s partial[s][i], fixed order -> deterministic
 // ---------------------------------------------------------------------------------------------
 __global__ void splitk_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, long long n, int splits,
-                                     int accumulate) {
+                                     int accumulate, long long stride) {
   const long long i4 = (1LL * blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i4 >= n) return;
   float4 acc = accumulate ? *reinterpret_cast<const float4*>(out + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
   for (int s = 0; s < splits; ++s) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(partial + 1LL * s * n + i4));
+    const float4 v = __ldg(reinterpret_cast<const float4*>(partial + 1LL * s * stride + i4));
     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
   }
   *reinterpret_cast<float4*>(out + i4) = acc;
 }
 
-int splitk_reduce(const float* partial, float* out, long long n, int splits, int accumulate, cudaStream_t stream) {
-  B200_REQUIRE(n % 4 == 0, "splitk_reduce: n %% 4 != 0");
+int splitk_reduce(const float* partial, float* out, long long n, int splits, int accumulate, cudaStream_t stream, long long stride) {
+  if (stride <= 0) stride = n;
+  B200_REQUIRE(n % 4 == 0 && stride % 4 == 0, "splitk_reduce: n %% 4 != 0");
   const int threads = 256;
   const long long blocks = (n / 4 + threads - 1) / threads;
-  splitk_reduce_kernel<<<(unsigned)blocks, threads, 0, stream>>>(partial, out, n, splits, accumulate);
+  splitk_reduce_kernel<<<(unsigned)blocks, threads, 0, stream>>>(partial, out, n, splits, accumulate, stride);
   B200_LAUNCH_CHECK();
   return B200_OK;
 }
@@ -294,7 +295,7 @@ extern "C" int b200_gemm_tn(const void* a, long long lda, const void* b, long lo
 extern "C" int b200_gemm_splits(int K, int splits) { return gemm::effective_splits(K, splits); }
 
 extern "C" int b200_splitk_reduce(const float* partial, float* out, long long n, int splits, int accumulate, void* stream) {
-  return splitk_reduce(partial, out, n, splits, accumulate, reinterpret_cast<cudaStream_t>(stream));
+  return splitk_reduce(partial, out, n, splits, accumulate, reinterpret_cast<cudaStream_t>(stream), n);
 }
 
 extern "C" int b200_margin_logits(const void* emb_unit, const void* w_unit, int B, int C, int E, const long long* label,

