@@ -1,0 +1,321 @@
+"""bench.py - the headline metric of BASELINE.json on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1]): dog-head FE training step - Swin-T (224x224, 512-d) + ArcFace head
+(C = 10,000 classes, s = 64, m = 0.5) + mean CE + SGD(momentum 0.9, the config's three parameter groups),
+per-GPU batch 256, bf16 storage / fp32 accumulate, synthetic images and seeded random-init weights.
+N > 1 (torchrun, one rank per GPU): pure data parallel, weak scaling, NCCL all-reduce of the gradients.
+
+A "step" = forward + backward + (all-reduce) + optimizer step over one batch.
+  value  : whole-job images/s with the batch already resident in HBM (CUDA events, max over ranks).
+  e2e    : the same step through the public API (engine.Trainer.train_batches on HOST batches: pinned staging,
+           H2D of the images every step, D2H read of the loss every step).
+  roofline: the tcgen05 GEMM kernel (all Linear fwd/dgrad/wgrad + the ArcFace cosine GEMM): algorithmic FLOPs of
+           its launches / their CUDA-event durations, against MEASURED_PEAKS.json's sustained bf16 figure.
+  cpu_baseline: the oracle port (oracle/, plain PyTorch fp32) of the same step timed on this box's host cores.
+
+--impl reference times that CPU port alone (the reference itself needs pytorch-lightning and its datasets, neither
+installable offline; its arithmetic for this path is restated in oracle/ and pinned to it by tests/golden/).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+PKG = ROOT / 'pets-face-recognition_b200'
+for _p in (str(ROOT), str(PKG)):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+METRIC = 'FE train images/sec (Swin-T + ArcFace, 224x224, bf16)'
+UNIT = 'images/s'
+NUM_CLASS = 10000
+FWD_GFLOP = 8.980            # Swin-T forward per image
+
+
+def train_flops_per_image(num_class=NUM_CLASS):
+    return 3 * FWD_GFLOP * 1e9 + 6 * 512 * num_class      # 26.97 GFLOP at C = 10k
+
+
+def peaks():
+    p = ROOT / 'MEASURED_PEAKS.json'
+    if p.exists():
+        d = json.loads(p.read_text())
+        return d.get('bf16_tflops_sustained', d.get('bf16_tflops')), d.get('hbm_gbs'), 'measured (MEASURED_PEAKS.json, sustained)'
+    return 1400.0, 6650.0, 'fallback (B200_PROFILING.md: ~1.4 PFLOP/s sustained, 6.65 TB/s)'
+
+
+# ------------------------------------------------------------------------------------------------------ CPU side
+def oracle_train_setup(batch, num_class=NUM_CLASS):
+    from b200 import synth
+    from oracle.swin_oracle import SwinSpec, param_shapes
+    spec = SwinSpec()
+    sd = synth.synth_state_dict(param_shapes(spec), seed=123)
+    sd = {k: v.requires_grad_(not k.endswith('_mask')) for k, v in sd.items()}
+    w = synth.synth_tensor('add_margin.weight', (num_class, 512), seed=123).requires_grad_(True)
+    img = synth.synth_images(batch, seed=123)
+    label = synth.synth_labels(batch, num_class, seed=123)
+    return spec, sd, w, img, label
+
+
+def oracle_train_step(spec, sd, w, img, label, bufs):
+    """One reference-semantics step on the CPU: losses/__init__.py:37-46 forward, autograd backward, SGD(momentum) with the
+    groups of configs/dog_fe/fe_dogs_config.py:123-133."""
+    from oracle import head_oracle
+    from oracle.swin_oracle import swin_forward
+    params = [p for p in sd.values() if p.requires_grad] + [w]
+    for p in params:
+        p.grad = None
+    out = head_oracle.metric_learning_forward(lambda x: swin_forward(sd, x, spec), w, img, label)
+    out['loss'].backward()
+    with torch.no_grad():
+        n = len(params) - 1
+        new = head_oracle.sgd_momentum_step([p for p in params[:n]], [p.grad for p in params[:n]], bufs[:n], 5e-3, 0.9, 0.0)
+        new += head_oracle.sgd_momentum_step([params[n]], [params[n].grad], bufs[n:], 1e-2, 0.9, 1e-4)
+    return out['loss'].item(), new
+
+
+def time_oracle(batch, warmup, steps):
+    torch.set_num_threads(os.cpu_count() or 1)
+    spec, sd, w, img, label = oracle_train_setup(batch)
+    bufs = [None] * (sum(1 for p in sd.values() if p.requires_grad) + 1)
+    for _ in range(warmup):
+        _, bufs = oracle_train_step(spec, sd, w, img, label, bufs)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        _, bufs = oracle_train_step(spec, sd, w, img, label, bufs)
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps
+
+
+def reference_arm(args, rank):
+    if rank != 0:
+        return
+    batch = 8
+    ips, sec = time_oracle(batch, args.warmup, args.steps)
+    cores = torch.get_num_threads()
+    line = {'impl': 'reference', 'metric': METRIC, 'value': ips, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': f'dog-head FE train step, Swin-T + ArcFace(C={NUM_CLASS}) + SGD, CPU fp32, bounded sample: batch {batch} per step'},
+            'cpu_baseline': {'value': ips, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                             'sample': f'{args.steps} steps of batch {batch} after {args.warmup} warm-up, oracle/ port on {cores} threads'},
+            'e2e': {'value': ips, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------ GPU side
+class ClockSampler:
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace('.', '').isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith('active') for r in self.rows)]
+        pw = [float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace('.', '').isdigit()]
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
+                'power_w_max': max(pw) if pw else None, 'samples': len(self.rows)}
+
+
+def build_model(num_class, device):
+    from b200 import synth
+    from losses import SoftmaxBasedMetricLearning
+    from models import swin_t
+    model = swin_t(num_classes=512)
+    sd = synth.synth_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, seed=123)
+    model.load_state_dict(sd, strict=True)
+    wrap = SoftmaxBasedMetricLearning(model, num_class=num_class, embedding_size=512, is_focal=True, arc_margin=True)
+    wrap.add_margin.weight.data.copy_(synth.synth_tensor('add_margin.weight', (num_class, 512), seed=123))
+    return wrap.to(device)
+
+
+def make_optimizer(wrap):
+    # configs/dog_fe/fe_dogs_config.py:123-133
+    params1 = [p for i, p in wrap.module.named_parameters() if 'fc' not in i]
+    params2 = [p for i, p in wrap.module.named_parameters() if 'fc' in i]
+    d = [{'lr': 10 ** -2 / 2, 'params': params1}, {'lr': 10 ** -2, 'params': params2},
+         {'lr': 10 ** -2, 'params': wrap.add_margin.parameters(), 'weight_decay': 1 * (10 ** -4)}]
+    return torch.optim.SGD(d, 0.01, momentum=0.9)
+
+
+class _Module(torch.nn.Module):
+    """Minimal Controller-shaped module (engine/controller.py:27-29) around the loss wrapper for the e2e leg."""
+
+    def __init__(self, wrap):
+        super().__init__()
+        self.model_loss = wrap
+
+    def training_step(self, batch, batch_idx):
+        return self.model_loss(batch['x'], batch['label'])['loss']
+
+
+def gpu_arm(args, rank, world, local_rank):
+    import torch.distributed as dist
+    from b200 import abi, synth
+    from engine.trainer import Trainer
+    device = torch.device('cuda', local_rank)
+    torch.cuda.set_device(device)
+    abi.require_device()
+    L = abi.lib()
+    B = args.batch
+
+    wrap = build_model(NUM_CLASS, device)
+    module = _Module(wrap)
+    opt = make_optimizer(wrap)
+    trainer = Trainer(gpus=[local_rank], strategy='ddp' if world > 1 else None, max_epochs=1)
+    trainer._allreduce_hooks(module)
+
+    # two distinct device-resident batches (154 MB of images each: larger than the 126 MB L2), rank-offset data seed
+    dev_batches = [{'x': synth.synth_images(B, seed=1000 * rank + i).to(device), 'label': synth.synth_labels(B, NUM_CLASS, seed=1000 * rank + i).to(device)}
+                   for i in range(2)]
+
+    def step(i):
+        return trainer.run_training_batch(module, dev_batches[i % 2], [opt])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    check = abi.check
+    check(L.b200_prof_begin(1), 'prof_begin')
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        loss = step(i)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    gemm_ms, gemm_fl, gemm_n, total_n = C.c_double(), C.c_double(), C.c_longlong(), C.c_longlong()
+    check(L.b200_prof_end(C.byref(gemm_ms), C.byref(gemm_fl), C.byref(gemm_n), C.byref(total_n)), 'prof_end')
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    value = world * B * args.steps / (ms * 1e-3)
+    final_loss = float(loss.item())
+
+    # ---- end to end through the public API: host batches, pinned staging + H2D every step, loss D2H every step
+    host_batches = [{'x': synth.synth_images(B, seed=2000 * rank + i), 'label': synth.synth_labels(B, NUM_CLASS, seed=2000 * rank + i)}
+                    for i in range(2)]
+    host_batches = [{k: v.pin_memory() for k, v in b.items()} for b in host_batches]
+    h2d = sum(v.numel() * v.element_size() for v in host_batches[0].values())
+
+    def host_iter(n):
+        for i in range(n):
+            yield host_batches[i % 2]
+    trainer.train_batches(module, host_iter(max(2, args.warmup // 2)), [opt])
+    barrier()
+    t0 = time.perf_counter()
+    losses = trainer.train_batches(module, host_iter(args.steps), [opt], read_loss_every=1)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / t.item()
+
+    if rank != 0:
+        return
+    peak_tf, peak_hbm, peak_src = peaks()
+    achieved_tf = gemm_fl.value / (gemm_ms.value * 1e-3) / 1e12 if gemm_ms.value > 0 else 0.0
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
+        'data': 'synthetic',
+        'config': {'workload': f'configs[1]: dog-head FE training step, Swin-T 224x224 + ArcFace(C={NUM_CLASS}, s=64, m=0.5) + mean CE + '
+                               f'SGD(momentum 0.9, 3 param groups), per-GPU batch {B}, global batch {B * world}',
+                   'parallelism': f'dp{world}', 'l2': 'inputs larger than L2 (154 MB of images per batch, two batches alternated; '
+                                                      'each step streams > 10 GB of activations)',
+                   'flops_per_image': train_flops_per_image(), 'final_loss': final_loss},
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
+                'api': 'engine.Trainer.train_batches(module, host_batches, optimizers)'},
+        'gpu_launches': int(total_n.value),
+        'roofline': {'bound': 'tensor', 'kernel': 'gemm::gemm_tn_kernel (tcgen05, all Linear fwd/dgrad/wgrad + ArcFace cosine)',
+                     'achieved': achieved_tf, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved_tf / peak_tf if peak_tf else None,
+                     'traffic': None, 'peak_source': peak_src, 'launches_timed': int(gemm_n.value),
+                     'kernel_ms_per_step': gemm_ms.value / args.steps, 'step_share': gemm_ms.value / ms if ms else None,
+                     'whole_step_frac': value / world * train_flops_per_image() / (peak_tf * 1e12) if peak_tf else None},
+        'clocks': clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cb, steps_cb = 32, 2
+        ips, _ = time_oracle(cb, 1, steps_cb)
+        line['cpu_baseline'] = {'value': ips, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
+                                'sample': f'{steps_cb} steps of batch {cb} after 1 warm-up: same step (Swin-T + ArcFace(C={NUM_CLASS}) + SGD), '
+                                          f'oracle/ port, fp32, {torch.get_num_threads()} threads'}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=256)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    if args.impl == 'reference':
+        reference_arm(args, rank)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group('nccl')
+    try:
+        gpu_arm(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -54,6 +54,11 @@ typedef struct B200OptTensor {
 const char* b200_last_error(void);
 int b200_device_check(void); /* B200_ERR_ARCH unless the current device is sm_100 */
 
+/* ---- measurement hooks (bench.py): count the library's kernel launches; optionally bracket every tcgen05 GEMM launch
+ *      with CUDA events on its stream.  b200_prof_end synchronises the device. ------------------------------------ */
+int b200_prof_begin(int time_gemm_launches);
+int b200_prof_end(double* gemm_ms, double* gemm_flops, long long* gemm_launches, long long* total_launches);
+
 /* ---- linear layers: D[M,N] = A[M,K] * B[N,K]^T on tcgen05 tensor cores (TMA-fed, TMEM accumulators) ---------
  * replaces nn.Linear forward and the two GEMMs autograd runs for its backward (models/swin.py:39-43,91,98,
  * 160,166,216; "Linear" row of SURVEY.md appendix B).  A and B are 16-bit (is_bf16 ? bf16 : fp16), K-major. */

@@ -37,6 +37,8 @@ class OptTensor(C.Structure):
 _PROTOS = {
     'b200_last_error': (C.c_char_p, []),
     'b200_device_check': (c_int, []),
+    'b200_prof_begin': (c_int, [c_int]),
+    'b200_prof_end': (c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(c_ll), C.POINTER(c_ll)]),
     'b200_gemm_tn': (c_int, [c_vp, c_ll, c_vp, c_ll, c_int, c_int, c_int, c_int, c_int, c_vp, c_ll, c_int, c_vp, c_ll, c_vp,
                              c_vp, c_ll, c_int, c_ll, c_int, c_vp]),
     'b200_gemm_splits': (c_int, [c_int, c_int]),

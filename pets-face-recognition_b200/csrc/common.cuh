@@ -37,11 +37,20 @@ int b200_set_error(int code, const char* fmt, ...);
     if (!(cond)) return b200_set_error(B200_ERR_INVALID, __VA_ARGS__);       \
   } while (0)
 
-#define B200_LAUNCH_CHECK() B200_CHECK_CUDA(cudaGetLastError())
+// every kernel launch of the library goes through this: counts launches (b200_prof_end reports them)
+void b200_count_launch();
+#define B200_LAUNCH_CHECK()                    \
+  do {                                         \
+    b200_count_launch();                       \
+    B200_CHECK_CUDA(cudaGetLastError());       \
+  } while (0)
 
-int b200_num_sms();
+int b200_num_sms();   // cached cudaDevAttrMultiProcessorCount of the current device (148 on B200)
 // out[i] (+)= sum_s partial[s * stride + i], i < n, fixed order (deterministic); stride <= 0 means n
-int splitk_reduce(const float* partial, float* out, long long n, int splits, int accumulate, cudaStream_t stream, long long stride);   // cached cudaDevAttrMultiProcessorCount of the current device (148 on B200)
+int splitk_reduce(const float* partial, float* out, long long n, int splits, int accumulate, cudaStream_t stream, long long stride);
+// optional per-launch CUDA-event timing of the tcgen05 GEMM kernels (bench.py roofline): no-ops unless enabled
+bool b200_prof_gemm_begin(cudaStream_t stream, double flops);
+void b200_prof_gemm_end(cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------------
 // small device helpers

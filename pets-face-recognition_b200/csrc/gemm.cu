@@ -34,6 +34,59 @@ int b200_num_sms() {
   return sms[dev];
 }
 
+// ---------------------------------------------------------------------------------------------
+// profiling hooks: launch counter + optional CUDA-event pairs around every tcgen05 GEMM launch
+// ---------------------------------------------------------------------------------------------
+#include <atomic>
+#include <vector>
+static std::atomic<long long> g_launches{0};
+static bool g_prof_gemm = false;
+struct GemmEv { cudaEvent_t a, b; double flops; };
+static std::vector<GemmEv> g_gemm_events;
+static std::vector<cudaEvent_t> g_event_pool;
+
+void b200_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+static cudaEvent_t take_event() {
+  if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+bool b200_prof_gemm_begin(cudaStream_t stream, double flops) {
+  if (!g_prof_gemm) return false;
+  GemmEv ev{take_event(), take_event(), flops};
+  cudaEventRecord(ev.a, stream);
+  g_gemm_events.push_back(ev);
+  return true;
+}
+void b200_prof_gemm_end(cudaStream_t stream) { cudaEventRecord(g_gemm_events.back().b, stream); }
+
+extern "C" int b200_prof_begin(int time_gemm_launches) {
+  g_launches.store(0);
+  for (auto& e : g_gemm_events) { g_event_pool.push_back(e.a); g_event_pool.push_back(e.b); }
+  g_gemm_events.clear();
+  g_prof_gemm = time_gemm_launches != 0;
+  return B200_OK;
+}
+// Synchronises the device.  gemm_ms / gemm_flops / gemm_launches describe the timed tcgen05 GEMM launches since
+// b200_prof_begin (zeros if timing was off); total_launches counts every kernel launch of the library.
+extern "C" int b200_prof_end(double* gemm_ms, double* gemm_flops, long long* gemm_launches, long long* total_launches) {
+  g_prof_gemm = false;
+  B200_CHECK_CUDA(cudaDeviceSynchronize());
+  double ms = 0.0, fl = 0.0;
+  for (auto& e : g_gemm_events) {
+    float t = 0.f;
+    B200_CHECK_CUDA(cudaEventElapsedTime(&t, e.a, e.b));
+    ms += t; fl += e.flops;
+  }
+  if (gemm_ms) *gemm_ms = ms;
+  if (gemm_flops) *gemm_flops = fl;
+  if (gemm_launches) *gemm_launches = static_cast<long long>(g_gemm_events.size());
+  if (total_launches) *total_launches = g_launches.load();
+  return B200_OK;
+}
+
 extern "C" int b200_device_check(void) {
   int dev = 0;
   B200_CHECK_CUDA(cudaGetDevice(&dev));

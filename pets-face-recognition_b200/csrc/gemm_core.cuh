@@ -244,7 +244,9 @@ int launch(const Operands& o, const typename Epi::Params& ep, cudaStream_t strea
   const long long tiles = 1LL * p.m_blocks * p.n_blocks * p.splits;
   int ctas = o.max_ctas > 0 ? o.max_ctas : b200_num_sms();
   if (tiles < ctas) ctas = static_cast<int>(tiles);
+  const bool prof = b200_prof_gemm_begin(stream, 2.0 * o.M * o.N * o.K);
   gemm_tn_kernel<Epi><<<ctas, kThreads, kSmemBytes, stream>>>(ta, tb, p, ep);
+  if (prof) b200_prof_gemm_end(stream);
   B200_LAUNCH_CHECK();
   return B200_OK;
 }

@@ -1,0 +1,150 @@
+"""FE Controller - drop-in for the reference's engine/controller.py (a LightningModule there, a plain
+nn.Module here: Lightning is not a dependency).  Same constructor, hooks, config keys and printed metric
+names; the two hot pieces run on the B200 kernels:
+
+  training_step / validation_step / test_step  -> model_loss(...)  (models/swin.py + losses/*: native plan)
+  the O(N^2) Recall@K loop of test_epoch_end / _evaluate (:77-91, :143-160) -> b200.gallery.recall_at_k
+
+Pair scoring (similarity_f over pair_generator.corrected_indices, :60-68) and the ROC-type metrics stay
+host-side PyTorch, as SURVEY.md 8(a14) scopes them.
+"""
+from pathlib import Path
+from typing import Any, Optional
+
+import torch
+
+from b200 import gallery
+
+from . import metrics as M
+
+
+class Controller(torch.nn.Module):
+    logger = None
+    current_epoch = 0
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        model = self.config.model()
+        self.model_loss = self.config.loss(config, model)
+        self.hparams = {i: repr(config[i]) for i in config} if hasattr(config, '__iter__') else {}
+
+    def forward(self, *args, **kwargs) -> Any:
+        return self.model_loss(*args, **kwargs)
+
+    # ---- steps (engine/controller.py:27-46)
+    def training_step(self, batch, batch_idx):
+        loss = self.model_loss(batch['x'], batch['label'])
+        return loss['loss']
+
+    def validation_step(self, batch, batch_idx, dataset_idx=0) -> Optional[dict]:
+        out = self.model_loss(batch['x'])
+        return {'emb': out, 'label': batch['label'], 'index': batch['index']}
+
+    def test_step(self, batch, batch_idx, dataset_idx=0) -> Optional[dict]:
+        out = self.model_loss(batch['x'])
+        return {'emb': out, 'label': batch['label'], 'index': batch['index']}
+
+    def validation_epoch_end(self, outputs) -> None:
+        self._evaluate(outputs)
+        if self.logger is not None and hasattr(self.logger, 'log_artifacts'):
+            self.logger.log_artifacts(str(self.config.output))
+
+    # ---- shared pieces
+    @staticmethod
+    def _gather(outputs_i):
+        """:51-56 - concatenate the per-batch dicts and undo the loader order."""
+        emb = torch.cat([j['emb'] for j in outputs_i], dim=0)
+        classes = torch.cat([j['label'] for j in outputs_i], dim=0)
+        indices = torch.cat([j['index'] for j in outputs_i], dim=0)
+        s = torch.argsort(indices)
+        return emb[s], classes[s]
+
+    def _pair_scores(self, emb, i):
+        name, pair_generator = self.config.pair_generator(i)
+        scores = self.config.similarity_f([(emb[id1], emb[id2]) for id1, id2 in pair_generator.corrected_indices])
+        labels = torch.as_tensor(pair_generator.labels)
+        return name, scores.detach().float().cpu(), labels
+
+    def _recall_at_k(self, emb, classes, ks):
+        """engine/controller.py:77-91: leave-one-out ranking of every embedding against all others.  similarity_f in
+        every reference config is (cosine + 1) / 2, monotone in the cosine, so the fused cosine top-k ranks identically."""
+        ks = list(ks)
+        if not ks:
+            return {}
+        dev = emb.device if emb.is_cuda else torch.device('cuda')
+        return gallery.recall_at_k(emb.to(dev).float(), classes.to(dev).long(), ks)
+
+    # ---- test (engine/controller.py:48-93)
+    def test_epoch_end(self, outputs) -> None:
+        for i in range(len(outputs)):
+            emb, classes = self._gather(outputs[i])
+            name, scores, labels = self._pair_scores(emb, i)
+            fpr, tpr, thresholds = M.roc(scores, labels)
+            metrics = {'ROC AUC': M.auroc(scores, labels),
+                       'Accuracy': self.compute_accuracy(scores, labels, thresholds, fpr, 1 - tpr)}
+            metrics.update(self._recall_at_k(emb, classes, [10, 100]))
+            self.last_metrics = metrics
+            print('', *[f'{name} {k}\t{v}' for k, v in metrics.items()], sep='\n')
+
+    # ---- validation (engine/controller.py:95-203)
+    def _evaluate(self, outputs) -> None:
+        for i in range(len(outputs)):
+            emb, classes = self._gather(outputs[i])
+            name, scores, labels = self._pair_scores(emb, i)
+            fpr, tpr, thresholds = M.roc(scores, labels)
+            opt_thr = thresholds[torch.argmin(fpr + 1 - tpr)].item()
+            tp, fp, tn, fn = M.stat_scores(scores, labels, opt_thr)
+            print(name, f'\nConf Mat thr = {opt_thr}', torch.tensor([[tn, fp], [fn, tp]]))
+            metrics = {'ROC AUC': M.auroc(scores, labels), 'AveragePrecision': M.average_precision(scores, labels),
+                       'Accuracy': self.compute_accuracy(scores, labels, thresholds, fpr, 1 - tpr), 'Opt thr': opt_thr}
+            for thr in self.config.thrs:
+                tp, fp, tn, fn = M.stat_scores(scores, labels, float(thr))
+                metrics[f'Accuracy thr={thr}'] = (tp + tn) / max(1, tp + fp + tn + fn)
+                metrics[f'Precision thr={thr}'] = tp / max(1, tp + fp)
+                metrics[f'Recall thr={thr}'] = tp / max(1, tp + fn)
+            metrics.update(self._recall_at_k(emb, classes, self.config.k))
+            sorted_scores, perm = torch.sort(scores)
+            sorted_labels = labels[perm]
+            neg_scores, pos_scores = sorted_scores[sorted_labels == 0], sorted_scores[sorted_labels == 1]
+            for far_thr in self.config.get('far_thr', ()):
+                thr = neg_scores[-int(len(neg_scores) * far_thr)]
+                if thr not in (0, 1):
+                    metrics[f'TAR@FAR={far_thr}'] = M.stat_scores(scores, labels, thr.item())[0] / max(1, len(pos_scores))
+                    metrics[f'TH@FAR={far_thr}'] = thr.item()
+            for frr_thr in self.config.get('frr_thr', ()):
+                thr = pos_scores[int(len(pos_scores) * frr_thr)]
+                if thr not in (0, 1):
+                    metrics[f'TRR@FRR={frr_thr}'] = M.stat_scores(scores, labels, thr.item())[2] / max(1, len(neg_scores))
+                    metrics[f'TH@FRR={frr_thr}'] = thr.item()
+            self.last_metrics = metrics
+            print(*[f'{name} {k}\t{v}' for k, v in metrics.items()], sep='\n')
+            if self.logger is not None:
+                self.logger.log_metrics({f'{name} {k}': v for k, v in metrics.items()}, self.current_epoch)
+
+    @staticmethod
+    def compute_accuracy(scores, labels, thresholds, fpr, fnr):
+        gen_scores, imp_scores = scores[labels == 1], scores[labels == 0]
+        t = thresholds[torch.argmin(fpr + fnr)]
+        n_pairs = len(gen_scores) + len(imp_scores)
+        n_true = len(gen_scores[gen_scores > t]) + len(imp_scores[imp_scores <= t])
+        return n_true / n_pairs
+
+    # ---- dataloader / optimizer passthroughs (engine/controller.py:230-246)
+    def train_dataloader(self):
+        return self.config.train_dataloader()
+
+    def val_dataloader(self):
+        return self.config.val_dataloader()
+
+    def predict_dataloader(self):
+        return self.test_dataloader()
+
+    def test_dataloader(self):
+        dl = self.config.get('test_dataloader')
+        if dl is not None:
+            return dl()
+        return self.config.val_dataloader()
+
+    def configure_optimizers(self):
+        return self.config.optimizer(self.model_loss)

@@ -1,0 +1,284 @@
+"""Lightning-free Trainer with the reference's surface (engine/trainer.py:64-129 takes pl.Trainer's keyword list;
+the ones the reference actually passes - utils/__init__.py:122-134 - are honoured, the rest are accepted and ignored).
+
+Behaviours re-created from PL 1.5.9 as the reference relies on them:
+  * fit: configure_optimizers() -> ([optim], [sched]); per batch H2D -> training_step -> zero_grad -> backward ->
+    optimizer step; schedulers stepped once per epoch; validation every epoch in eval()/no_grad;
+  * *_epoch_end(outputs) always gets outputs[dataloader_idx][batch_idx] (engine/loops/eval_loop.py:30-37);
+  * num_sanity_val_steps = 0, enable_checkpointing via plain state_dict files (the format the reference's released
+    checkpoints use, eval_fe_dog_head_sgd.py:18-21).
+B200 specifics: the optimizer arithmetic is one fused multi-tensor kernel (b200/optim.py) driven by the config's own
+torch.optim object; host batches are staged through pinned memory on a copy stream one step ahead; with
+strategy='ddp' (one process per GPU, torchrun-style env) gradients are all-reduced with NCCL per stage bucket on a
+side stream, launched as soon as each stage's backward has been enqueued, and the 1/world factor is folded into
+the optimizer kernel.
+"""
+from __future__ import annotations
+
+import os
+import time
+from pathlib import Path
+from typing import Any, Dict, Iterable, List, Optional
+
+import torch
+
+from b200.optim import FusedStep
+
+
+def _to_device(batch, device, non_blocking=True):
+    if torch.is_tensor(batch):
+        return batch.to(device, non_blocking=non_blocking)
+    if isinstance(batch, dict):
+        return {k: _to_device(v, device, non_blocking) for k, v in batch.items()}
+    if isinstance(batch, (list, tuple)):
+        return type(batch)(_to_device(v, device, non_blocking) for v in batch)
+    return batch
+
+
+def _pin(batch):
+    if torch.is_tensor(batch):
+        return batch if (batch.is_cuda or batch.is_pinned()) else batch.pin_memory()
+    if isinstance(batch, dict):
+        return {k: _pin(v) for k, v in batch.items()}
+    if isinstance(batch, (list, tuple)):
+        return type(batch)(_pin(v) for v in batch)
+    return batch
+
+
+class _Prefetcher:
+    """Yields device batches; batch i+1 is copied host->device on a side stream while step i computes."""
+
+    def __init__(self, batches: Iterable, device):
+        self.it = iter(batches)
+        self.device = device
+        self.stream = torch.cuda.Stream(device=device) if device.type == 'cuda' else None
+        self._next = None
+        self._preload()
+
+    def _preload(self):
+        try:
+            host = next(self.it)
+        except StopIteration:
+            self._next = None
+            return
+        if self.stream is None:
+            self._next = _to_device(host, self.device, False)
+            return
+        host = _pin(host)
+        with torch.cuda.stream(self.stream):
+            self._next = (_to_device(host, self.device, True), host)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self._next is None:
+            raise StopIteration
+        if self.stream is None:
+            out = self._next
+        else:
+            torch.cuda.current_stream(self.device).wait_stream(self.stream)
+            out, _host = self._next
+            for t in (out.values() if isinstance(out, dict) else [out]):
+                if torch.is_tensor(t):
+                    t.record_stream(torch.cuda.current_stream(self.device))
+        self._preload()
+        return out
+
+
+class Trainer:
+    def __init__(self, gpus=None, default_root_dir=None, strategy=None, max_epochs=None, logger=False,
+                 enable_checkpointing=False, callbacks=None, precision='bf16', num_sanity_val_steps=0,
+                 check_val_every_n_epoch=1, limit_train_batches=None, limit_val_batches=None, benchmark=False,
+                 log_every_n_steps=50, **ignored):
+        self.gpus = gpus
+        self.default_root_dir = default_root_dir
+        self.strategy = strategy
+        self.max_epochs = max_epochs if max_epochs is not None else 1
+        self.logger = logger if logger not in (False, None) else None
+        self.enable_checkpointing = enable_checkpointing
+        self.callbacks = callbacks or []
+        self.precision = precision            # compute is always bf16 storage / fp32 accumulate on this path
+        self.check_val_every_n_epoch = check_val_every_n_epoch
+        self.limit_train_batches, self.limit_val_batches = limit_train_batches, limit_val_batches
+        self.log_every_n_steps = log_every_n_steps
+        self.ignored_kwargs = dict(ignored)
+        self.current_epoch = 0
+        self.global_step = 0
+        self.world_size, self.rank = 1, 0
+        self._comm_stream = None
+        self._fused: Dict[int, FusedStep] = {}
+        self.device = self._pick_device()
+        if strategy is not None:
+            self._init_distributed()
+
+    # ------------------------------------------------------------------ setup
+    def _pick_device(self) -> torch.device:
+        if not self.gpus:
+            return torch.device('cpu')
+        if 'LOCAL_RANK' in os.environ and self.strategy is not None:
+            return torch.device('cuda', int(os.environ['LOCAL_RANK']))
+        g = self.gpus
+        idx = g[0] if isinstance(g, (list, tuple)) else 0
+        return torch.device('cuda', int(idx))
+
+    def _init_distributed(self):
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            if 'RANK' not in os.environ:
+                raise RuntimeError("strategy='ddp' expects one process per GPU launched torchrun-style "
+                                   '(RANK / LOCAL_RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT in the environment)')
+            if self.device.type == 'cuda':
+                torch.cuda.set_device(self.device)
+            dist.init_process_group('nccl' if self.device.type == 'cuda' else 'gloo')
+        self.world_size, self.rank = dist.get_world_size(), dist.get_rank()
+
+    # ------------------------------------------------------------------ the hot step
+    def _allreduce_hooks(self, module):
+        """Install the per-stage gradient bucket all-reduce on every native Swin engine inside `module`."""
+        if self.world_size == 1:
+            return []
+        import torch.distributed as dist
+        engines = [m.engine for m in module.modules() if hasattr(m, '_engine') and hasattr(m, 'engine')]
+        if self._comm_stream is None and self.device.type == 'cuda':
+            self._comm_stream = torch.cuda.Stream(device=self.device)
+        for eng in engines:
+            def hook(stage, flat_grad, eng=eng):
+                begin, end = eng.stage_param_range(stage)
+                if self._comm_stream is None:
+                    dist.all_reduce(flat_grad[begin:end])
+                    return
+                ev = torch.cuda.Event()
+                ev.record()
+                with torch.cuda.stream(self._comm_stream):
+                    self._comm_stream.wait_event(ev)
+                    dist.all_reduce(flat_grad[begin:end])
+            eng.grad_hook = hook
+        return engines
+
+    def run_training_batch(self, module, batch, optimizers) -> torch.Tensor:
+        """One optimizer step == PL's optimizer.step(closure): training_step -> zero_grad -> backward -> step."""
+        for opt in optimizers:
+            opt.zero_grad(set_to_none=True)
+        loss = module.training_step(batch, self.global_step)
+        loss.backward()
+        if self.world_size > 1:
+            import torch.distributed as dist
+            covered = set()
+            for m in module.modules():
+                if hasattr(m, '_engine') and m._engine is not None and m._engine.last_flat_grad is not None:
+                    covered.update(id(p) for p in m._engine.params)
+            rest = [p.grad for p in module.parameters() if p.grad is not None and id(p) not in covered]
+            if self._comm_stream is not None:
+                ev = torch.cuda.Event(); ev.record()
+                with torch.cuda.stream(self._comm_stream):
+                    self._comm_stream.wait_event(ev)
+                    for g in rest:
+                        dist.all_reduce(g)
+                torch.cuda.current_stream().wait_stream(self._comm_stream)
+            else:
+                for g in rest:
+                    dist.all_reduce(g)
+        for opt in optimizers:
+            fused = self._fused.get(id(opt))
+            if fused is None:
+                fused = self._fused[id(opt)] = FusedStep(opt)
+            fused.step(grad_scale=1.0 / self.world_size)
+        self.global_step += 1
+        return loss.detach()
+
+    def train_batches(self, module, host_batches: Iterable, optimizers, read_loss_every: int = 1) -> List[float]:
+        """Run optimizer steps over an iterable of HOST batches (dicts of CPU tensors): pinned staging + async H2D one
+        step ahead, and a device->host read of the loss every `read_loss_every` steps."""
+        losses = []
+        for i, batch in enumerate(_Prefetcher(host_batches, self.device)):
+            loss = self.run_training_batch(module, batch, optimizers)
+            if read_loss_every and (i + 1) % read_loss_every == 0:
+                losses.append(float(loss.item()))
+        return losses
+
+    # ------------------------------------------------------------------ loops
+    def _unpack_optimizers(self, module):
+        cfg = module.configure_optimizers()
+        if isinstance(cfg, (list, tuple)) and len(cfg) == 2 and isinstance(cfg[0], (list, tuple)):
+            return list(cfg[0]), list(cfg[1])
+        if isinstance(cfg, (list, tuple)):
+            return list(cfg), []
+        return [cfg], []
+
+    def _run_eval(self, module, dataloaders, step_name: str, limit=None):
+        if not isinstance(dataloaders, (list, tuple)):
+            dataloaders = [dataloaders]
+        was_training = module.training
+        module.eval()
+        outputs = []
+        with torch.no_grad():
+            for dl_idx, dl in enumerate(dataloaders):
+                dl_out = []
+                for b_idx, batch in enumerate(_Prefetcher(dl, self.device)):
+                    if limit is not None and b_idx >= limit:
+                        break
+                    dl_out.append(getattr(module, step_name)(batch, b_idx, dl_idx))
+                outputs.append(dl_out)               # ALWAYS [dataloader][batch]
+        module.train(was_training)
+        return outputs
+
+    def fit(self, module) -> None:
+        module.to(self.device)
+        module.logger = self.logger
+        optimizers, schedulers = self._unpack_optimizers(module)
+        self._allreduce_hooks(module)
+        module.train()
+        for epoch in range(self.current_epoch, self.max_epochs):
+            self.current_epoch = module.current_epoch = epoch
+            t0, n_img, last = time.time(), 0, None
+            for b_idx, batch in enumerate(_Prefetcher(module.train_dataloader(), self.device)):
+                if self.limit_train_batches is not None and b_idx >= self.limit_train_batches:
+                    break
+                last = self.run_training_batch(module, batch, optimizers)
+                n_img += int(batch['x'].shape[0]) if isinstance(batch, dict) and 'x' in batch else 0
+                if self.log_every_n_steps and (b_idx + 1) % self.log_every_n_steps == 0 and self.rank == 0:
+                    print(f'epoch {epoch} step {b_idx + 1} loss {last.item():.4f}')
+            for s in schedulers:
+                s.step()
+            if self.rank == 0 and last is not None:
+                dt = time.time() - t0
+                print(f'epoch {epoch}: loss {last.item():.4f}  {n_img / max(dt, 1e-9):.1f} img/s')
+                if self.logger is not None and hasattr(self.logger, 'log_metrics'):
+                    self.logger.log_metrics({'train_loss': last.item()}, epoch)
+            if (epoch + 1) % self.check_val_every_n_epoch == 0 and self.rank == 0:
+                outputs = self._run_eval(module, module.val_dataloader(), 'validation_step', self.limit_val_batches)
+                module.validation_epoch_end(outputs)
+            if self.world_size > 1:
+                import torch.distributed as dist
+                dist.barrier()                        # engine/loops/train_loop.py:16-17
+            if self.enable_checkpointing and self.default_root_dir is not None and self.rank == 0:
+                ck = Path(self.default_root_dir)
+                ck.mkdir(parents=True, exist_ok=True)
+                torch.save(module.state_dict(), ck / f'epoch={epoch}-step={self.global_step}.ckpt')
+                torch.save({'optimizers': [o.state_dict() for o in optimizers], 'schedulers': [s.state_dict() for s in schedulers],
+                            'epoch': epoch + 1, 'global_step': self.global_step}, ck / 'trainer_state.pt')
+
+    def resume(self, module, optimizers, schedulers, path) -> None:
+        st = torch.load(Path(path) / 'trainer_state.pt')
+        for o, s in zip(optimizers, st['optimizers']):
+            o.load_state_dict(s)
+        for o, s in zip(schedulers, st['schedulers']):
+            o.load_state_dict(s)
+        self.current_epoch, self.global_step = st['epoch'], st['global_step']
+
+    def validate(self, module):
+        module.to(self.device)
+        outputs = self._run_eval(module, module.val_dataloader(), 'validation_step', self.limit_val_batches)
+        module.validation_epoch_end(outputs)
+        return getattr(module, 'last_metrics', None)
+
+    def test(self, module):
+        module.to(self.device)
+        outputs = self._run_eval(module, module.test_dataloader(), 'test_step')
+        module.test_epoch_end(outputs)
+        return getattr(module, 'last_metrics', None)
+
+    def predict(self, module):
+        module.to(self.device)
+        return self._run_eval(module, module.predict_dataloader(), 'test_step')

@@ -76,9 +76,13 @@ def test_large_scale_properties():
     assert torch.equal(idx_x, idx[:, 1:]) and torch.equal(score_x, score[:, 1:])   # exclusion == dropping rank 0
     qn, gn = torch.nn.functional.normalize(q), torch.nn.functional.normalize(emb)
     ref = (qn @ gn.t()).topk(100, dim=1)
-    gap_ok = (score[:, :-1] - score[:, 1:]).min(dim=1).values > 1e-5               # rows without fp32-level near-ties
-    assert gap_ok.float().mean().item() > 0.5
-    assert torch.equal(idx[gap_ok].long(), ref.indices[gap_ok])
+    # vs a plain fp32 matmul + topk: the ranked SCORE sequences agree to fp32 noise; indices may differ only where two
+    # candidates are closer than that noise (fp32 summation order decides there; our order is defined in fp64)
+    assert (score.float() - ref.values).abs().max().item() < 3e-6
+    same = idx.long() == ref.indices
+    assert same.float().mean().item() > 0.97
+    mine_in_fp32 = (qn[:, None, :] * gn[idx.long()]).sum(-1)
+    assert (mine_in_fp32 - ref.values)[~same].abs().max().item() < 3e-6
     # gallery split in 3 shards + merge == one pass
     bounds = [0, 40000, 90000, 120000]
     parts = [gallery.cosine_topk(q, emb[a:b], 100, g_index_base=a) for a, b in zip(bounds[:-1], bounds[1:])]
