@@ -27,13 +27,18 @@ def auroc(scores, labels) -> float:
 
 
 def average_precision(scores, labels) -> float:
+    """sum_n (R_n - R_{n-1}) P_n over the distinct score thresholds (ties form one threshold)."""
     scores = scores.detach().double().cpu().flatten()
     labels = labels.detach().cpu().flatten().bool()
     order = torch.argsort(scores, descending=True, stable=True)
-    l = labels[order].double()
-    tp = torch.cumsum(l, 0)
-    prec = tp / torch.arange(1, l.numel() + 1, dtype=torch.float64)
-    return float((prec * l).sum() / l.sum().clamp_min(1))
+    s, l = scores[order], labels[order].double()
+    distinct = torch.nonzero(s[1:] != s[:-1]).flatten()
+    ends = torch.cat([distinct, torch.tensor([s.numel() - 1])])
+    tp = torch.cumsum(l, 0)[ends]
+    prec = tp / (ends + 1).double()
+    rec = tp / l.sum().clamp_min(1)
+    prev = torch.cat([torch.zeros(1, dtype=torch.float64), rec[:-1]])
+    return float(((rec - prev) * prec).sum())
 
 
 def stat_scores(scores, labels, thr):

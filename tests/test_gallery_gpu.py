@@ -88,5 +88,5 @@ def test_large_scale_properties():
     parts = [gallery.cosine_topk(q, emb[a:b], 100, g_index_base=a) for a, b in zip(bounds[:-1], bounds[1:])]
     m_idx, m_score = gallery.topk_merge(torch.stack([p[1] for p in parts]), torch.stack([p[0] for p in parts]), 100)
     assert torch.equal(m_idx, idx) and torch.equal(m_score, score)
-    r = gallery.recall_at_k(emb[:20000], classes[:20000], (10, 100))
+    r = gallery.recall_at_k(emb[::6].contiguous(), classes[::6].contiguous(), (10, 100))   # stride 6 keeps both images of an identity
     assert 0.0 <= r['Recall@K=10'] <= r['Recall@K=100'] <= 1.0
