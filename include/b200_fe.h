@@ -65,6 +65,10 @@ int b200_prof_end(double* gemm_ms, double* gemm_flops, long long* gemm_launches,
 int b200_gemm_tn(const void* a, long long lda, const void* b, long long ldb, int M, int N, int K, int is_bf16, int mode,
                  void* out, long long ldo, int out_fp32, void* out2, long long ldo2, const float* bias, const void* aux,
                  long long ldaux, int splits, long long split_stride, int block_n, void* stream);
+/* weight gradient dW[N,K] = dY[tokens,N]^T * X[tokens,K] (bf16), split over the tokens into fp32 partials [splits][N][K];
+ * operands are consumed in place through MN-major UMMA descriptors (no transposed copies) */
+int b200_gemm_wgrad(const void* dy, long long ldy, const void* x, long long ldx, long long tokens, int N, int K, float* partial,
+                    int splits, int block_n, void* stream);
 int b200_gemm_splits(int K, int splits); /* split count b200_gemm_tn will really use (sizes the partial buffer) */
 int b200_splitk_reduce(const float* partial, float* out, long long n, int splits, int accumulate, void* stream);
 
@@ -95,7 +99,8 @@ int b200_colsum(const void* x, long long ld, long long M, int N, float* out, flo
  *      to_out; the cyclic shift and window partition are folded into the addressing. ------------------------------ */
 int b200_window_attn_fwd(const void* qkv, const float* pos_embedding, void* out, float* lse, int B, int H, int W, int C,
                          int heads, int shifted, void* stream);
-int b200_window_attn_bwd_blocks(int B, int H, int W, int heads); /* rows of the [blocks, 169] dpos partial buffer */
+int b200_window_attn_bwd_blocks(int B, int H, int W, int heads);
+long long b200_window_attn_bwd_scratch_floats(int blocks); /* size (floats) of the `dpos_partial` scratch buffer */
 int b200_window_attn_bwd(const void* qkv, const float* pos_embedding, const void* out, const float* lse, const void* dout,
                          void* dqkv, float* dpos, float* dpos_partial, int accumulate_dpos, int B, int H, int W, int C,
                          int heads, int shifted, void* stream);

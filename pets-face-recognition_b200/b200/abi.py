@@ -41,6 +41,7 @@ _PROTOS = {
     'b200_prof_end': (c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(c_ll), C.POINTER(c_ll)]),
     'b200_gemm_tn': (c_int, [c_vp, c_ll, c_vp, c_ll, c_int, c_int, c_int, c_int, c_int, c_vp, c_ll, c_int, c_vp, c_ll, c_vp,
                              c_vp, c_ll, c_int, c_ll, c_int, c_vp]),
+    'b200_gemm_wgrad': (c_int, [c_vp, c_ll, c_vp, c_ll, c_ll, c_int, c_int, c_vp, c_int, c_int, c_vp]),
     'b200_gemm_splits': (c_int, [c_int, c_int]),
     'b200_splitk_reduce': (c_int, [c_vp, c_vp, c_ll, c_int, c_int, c_vp]),
     'b200_layernorm_fwd': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, c_int, c_float, c_vp]),
@@ -56,6 +57,7 @@ _PROTOS = {
     'b200_colsum': (c_int, [c_vp, c_ll, c_ll, c_int, c_vp, c_vp, c_int, c_vp]),
     'b200_window_attn_fwd': (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
     'b200_window_attn_bwd_blocks': (c_int, [c_int, c_int, c_int, c_int]),
+    'b200_window_attn_bwd_scratch_floats': (c_ll, [c_int]),
     'b200_window_attn_bwd': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int,
                                      c_int, c_vp]),
     'b200_unit_rows': (c_int, [c_vp, c_vp, c_vp, c_ll, c_int, c_ll, c_float, c_int, c_vp]),

@@ -41,6 +41,16 @@ def gemm_tn(a, b, *, mode=abi.EPI_STORE, bias=None, aux=None, out_fp32=False, wa
     return (out, pre) if mode == abi.EPI_GELU and want_pre else out
 
 
+def gemm_wgrad(dy, x, splits=1, block_n=0):
+    """fp32 partials [splits, N, K] of dy[tokens, N]^T @ x[tokens, K] (bf16 operands read in place)."""
+    tokens, N = dy.shape
+    K = x.shape[1]
+    splits = lib().b200_gemm_splits(tokens, max(1, splits))
+    out = torch.empty(splits, N, K, device=dy.device, dtype=torch.float32)
+    check(lib().b200_gemm_wgrad(ptr(dy), dy.stride(0), ptr(x), x.stride(0), tokens, N, K, ptr(out), splits, block_n, stream_ptr()), 'gemm_wgrad')
+    return out
+
+
 def splitk_reduce(partial, out=None, accumulate=False):
     splits, n = partial.shape[0], partial[0].numel()
     if out is None:
@@ -135,7 +145,7 @@ def window_attn_bwd(qkv, pos, out, lse, dout, B, H, W, Cc, heads, shifted):
     dqkv = torch.empty_like(qkv)
     dpos = torch.empty(169, device=qkv.device, dtype=torch.float32)
     blocks = lib().b200_window_attn_bwd_blocks(B, H, W, heads)
-    partial = torch.empty(blocks, 169, device=qkv.device, dtype=torch.float32)
+    partial = torch.empty(lib().b200_window_attn_bwd_scratch_floats(blocks), device=qkv.device, dtype=torch.float32)
     check(lib().b200_window_attn_bwd(ptr(qkv), ptr(pos), ptr(out), ptr(lse), ptr(dout), ptr(dqkv), ptr(dpos), ptr(partial), 0,
                                      B, H, W, Cc, heads, int(shifted), stream_ptr()), 'window_attn_bwd')
     return dqkv, dpos.view(13, 13)

@@ -25,10 +25,18 @@ constexpr int kWs = 7;
 constexpr int kWt = 49;
 constexpr int kHd = 32;
 constexpr int kPitch = 40;                         // bf16 elements per smem row (80 B: conflict-free ldmatrix)
-constexpr int kTileBytes = 64 * kPitch * 2;        // 5120
+constexpr int kRowB = kPitch * 2;                  // 80 B
+constexpr int kTileRows = 50;                      // 49 token rows + one all-zero row that stands in for rows 49..63
+constexpr int kTileBytes = kTileRows * kRowB;      // 4000
+constexpr int kStageBytes = 16 * kRowB;            // 1280: one 16-row output tile
 constexpr int kWarps = 4;
 constexpr int kBins = 169;
+constexpr int kBiasPitch = 72;                     // floats per row of the 64 x 64 bias table (conflict-free float2 reads)
+constexpr int kBiasBytes = 64 * kBiasPitch * 4;    // 18432
+constexpr int kSlots = 4 * 7 * 4;                  // per-lane dS accumulators: [m-tile][n-tile < 7][fragment element]
 constexpr float kLog2e = 1.4426950408889634f;
+// bit j set <=> window column (j % 7) >= 4, i.e. token j lies in the wrapped part under the left/right mask
+constexpr unsigned long long kColHi = 0x1C3870E1C3870ULL;
 
 struct AttnArgs {
   const bf16* qkv;      // [B*H*W, 3C]
@@ -39,6 +47,7 @@ struct AttnArgs {
   const bf16* o;        // bwd: saved attention output
   bf16* dqkv;           // bwd: [B*H*W, 3C]
   float* dpos_partial;  // bwd: [gridDim.x, 169]
+  float* dslots;        // bwd: [gridDim.x * kWarps][kSlots][32] per-lane dS accumulators (L2-resident scratch)
   int B, H, W, C, heads, shifted;
   float scale;
 };
@@ -58,6 +67,19 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
+
+// byte offset of tile row r inside a slab: rows >= 49 all read the shared zero row (row 49)
+__device__ __forceinline__ uint32_t trow(int r) { return static_cast<uint32_t>(min(r, kWt) * kRowB); }
+// per-lane ldmatrix offsets.  A-type: 16 rows of m-tile `mt`, k-step kk (16 dims).
+__device__ __forceinline__ uint32_t off_a(int mt, int kk, int lane) { return trow(mt * 16 + (lane & 15)) + (kk * 16 + (lane >> 4) * 8) * 2; }
+// B operand from an [n][k] slab, non-transposed: n-tile pair np (16 rows), k-step kk
+__device__ __forceinline__ uint32_t off_b(int np, int kk, int lane) {
+  return trow(np * 16 + (lane & 7) + (lane >> 4) * 8) + (kk * 16 + ((lane >> 3) & 1) * 8) * 2;
+}
+// B operand from a [k][n] slab, transposed load: k-step kk (16 rows), n-tile pair np (16 dims)
+__device__ __forceinline__ uint32_t off_bt(int kk, int np, int lane) {
+  return trow(kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) + ((np * 2 + (lane >> 4)) * 8) * 2;
+}
 
 struct Task {
   int b, wy, wx, h;
@@ -88,17 +110,28 @@ __device__ __forceinline__ long long token_row(const AttnArgs& a, const Task& t,
   return (1LL * t.b * a.H + y) * a.W + x;
 }
 
-// additive score term for (query i, key j): relpos bias, -inf on masked / padded keys; padded query rows
-// get a harmless finite value.  models/swin.py:117-124.
-__device__ __forceinline__ float score_bias(const float* pos_s, const Task& t, int i, int j) {
-  if (j >= kWt) return -INFINITY;
-  if (i >= kWt) return 0.f;
-  const int ri = i / kWs, ci = i - ri * kWs;
-  const int rj = j / kWs, cj = j - rj * kWs;
-  constexpr int kSplit = kWs - kWs / 2;   // 4: rows/cols >= 4 are the wrapped part
-  if (t.ul && ((ri >= kSplit) != (rj >= kSplit))) return -INFINITY;
-  if (t.lr && ((ci >= kSplit) != (cj >= kSplit))) return -INFINITY;
-  return pos_s[(rj - ri + kWs - 1) * (2 * kWs - 1) + (cj - ci + kWs - 1)];
+// 64 x 64 additive score table shared by every window and head of the block (models/swin.py:117-118):
+// bias[i][j] = pos[r_j - r_i + 6][c_j - c_i + 6]; padded keys (j >= 49) -> -inf; padded queries (i >= 49) -> 0.
+__device__ __forceinline__ void build_bias_table(float* bias_s, const float* __restrict__ pos) {
+  for (int idx = threadIdx.x; idx < 64 * 64; idx += blockDim.x) {
+    const int i = idx >> 6, j = idx & 63;
+    float v;
+    if (j >= kWt) v = -INFINITY;
+    else if (i >= kWt) v = 0.f;
+    else {
+      const int ri = i / kWs, ci = i - ri * kWs, rj = j / kWs, cj = j - rj * kWs;
+      v = __ldg(pos + (rj - ri + kWs - 1) * (2 * kWs - 1) + (cj - ci + kWs - 1));
+    }
+    bias_s[i * kBiasPitch + j] = v;
+  }
+}
+
+// shift masks (models/swin.py:49-62, 122-124) in closed form: -inf where query and key fall on different sides of
+// the wrap boundary (window row >= 4 <=> token >= 28; window column >= 4 <=> bit of kColHi).
+__device__ __forceinline__ bool shift_masked(const Task& t, int i, int j) {
+  const bool ul = t.ul && ((i >= 28) != (j >= 28));
+  const bool lr = t.lr && ((((kColHi >> i) ^ (kColHi >> j)) & 1ULL) != 0ULL);
+  return ul || lr;
 }
 
 // load one 49 x 32 bf16 tile (row i of the tile = window token i, 64 B = 4 lanes x 16 B) into a padded slab
@@ -106,32 +139,36 @@ __device__ __forceinline__ void load_tile_async(uint32_t slab, const bf16* base,
 #pragma unroll
   for (int it = 0; it < 7; ++it) {
     const int row = it * 8 + (lane >> 2);
-    if (row < kWt) cp_async16(slab + row * (kPitch * 2) + (lane & 3) * 16, base + rows_s[row] * ld + col0 + (lane & 3) * 8);
+    if (row < kWt) cp_async16(slab + row * kRowB + (lane & 3) * 16, base + rows_s[row] * ld + col0 + (lane & 3) * 8);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
+constexpr int kFwdWarpBytes = 3 * kTileBytes;                                    // q, k, v (q rows double as the O staging rows)
+constexpr int kFwdSmem = kBiasBytes + kWarps * 64 * 8 + kWarps * kFwdWarpBytes;
+
 __global__ void __launch_bounds__(kWarps * 32) window_attn_fwd_kernel(const AttnArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, tq = lane & 3;
-  float* pos_s = reinterpret_cast<float*>(smem);                                  // 169 floats (pad to 704 B)
-  long long* rows_all = reinterpret_cast<long long*>(smem + 704);                 // [kWarps][64]
-  uint8_t* slabs = smem + 704 + kWarps * 64 * 8;
-  uint8_t* my = slabs + warp * 3 * kTileBytes;
+  float* bias_s = reinterpret_cast<float*>(smem);
+  long long* rows_all = reinterpret_cast<long long*>(smem + kBiasBytes);          // [kWarps][64]
+  uint8_t* my = smem + kBiasBytes + kWarps * 64 * 8 + warp * kFwdWarpBytes;
   const uint32_t qs = smem_u32(my), ks = qs + kTileBytes, vs = ks + kTileBytes;
   long long* rows_s = rows_all + warp * 64;
 
-  for (int i = threadIdx.x; i < kBins; i += blockDim.x) pos_s[i] = a.pos[i];
-  for (int i = lane; i < 3 * kTileBytes / 16; i += 32) reinterpret_cast<uint4*>(my)[i] = make_uint4(0, 0, 0, 0);
+  build_bias_table(bias_s, a.pos);
+  for (int i = lane; i < kFwdWarpBytes / 16; i += 32) reinterpret_cast<uint4*>(my)[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
 
   const long long ntasks = 1LL * a.B * (a.H / kWs) * (a.W / kWs) * a.heads;
   const long long ld_qkv = 3LL * a.C;
+  const float sc2 = a.scale * kLog2e;               // scores are kept in the log2 domain: one FFMA + EX2 per element
   for (long long task = 1LL * blockIdx.x * kWarps + warp; task < ntasks; task += 1LL * gridDim.x * kWarps) {
     const Task t = decode_task(a, task);
+    const bool flagged = t.ul || t.lr;
     for (int i = lane; i < kWt; i += 32) rows_s[i] = token_row(a, t, i);
     __syncwarp();
     load_tile_async(qs, a.qkv, ld_qkv, t.h * kHd, rows_s, lane);
@@ -146,16 +183,14 @@ __global__ void __launch_bounds__(kWarps * 32) window_attn_fwd_kernel(const Attn
     for (int np = 0; np < 4; ++np)
 #pragma unroll
       for (int kk = 0; kk < 2; ++kk)
-        ldsm_x4(ks + (np * 16 + (lane & 7) + (lane >> 4) * 8) * (kPitch * 2) + (kk * 16 + ((lane >> 3) & 1) * 8) * 2,
-                kf[2 * np][kk][0], kf[2 * np][kk][1], kf[2 * np + 1][kk][0], kf[2 * np + 1][kk][1]);
+        ldsm_x4(ks + off_b(np, kk, lane), kf[2 * np][kk][0], kf[2 * np][kk][1], kf[2 * np + 1][kk][0], kf[2 * np + 1][kk][1]);
     // V as the B operand of O = P V (k = key j, n = dim d): transposed ldmatrix of the [j][d] slab
     uint32_t vf[4][4][2];
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk)
 #pragma unroll
       for (int np = 0; np < 2; ++np)
-        ldsm_x4_t(vs + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * (kPitch * 2) + ((np * 2 + (lane >> 4)) * 8) * 2,
-                  vf[kk][2 * np][0], vf[kk][2 * np][1], vf[kk][2 * np + 1][0], vf[kk][2 * np + 1][1]);
+        ldsm_x4_t(vs + off_bt(kk, np, lane), vf[kk][2 * np][0], vf[kk][2 * np][1], vf[kk][2 * np + 1][0], vf[kk][2 * np + 1][1]);
 
 #pragma unroll 1
     for (int mt = 0; mt < 4; ++mt) {
@@ -165,19 +200,29 @@ __global__ void __launch_bounds__(kWarps * 32) window_attn_fwd_kernel(const Attn
 #pragma unroll
       for (int kk = 0; kk < 2; ++kk) {
         uint32_t a0, a1, a2, a3;
-        ldsm_x4(qs + (mt * 16 + (lane & 15)) * (kPitch * 2) + (kk * 16 + (lane >> 4) * 8) * 2, a0, a1, a2, a3);
+        ldsm_x4(qs + off_a(mt, kk, lane), a0, a1, a2, a3);
 #pragma unroll
         for (int n = 0; n < 8; ++n) mma16816(s[n], a0, a1, a2, a3, kf[n][kk][0], kf[n][kk][1]);
       }
       const int i0 = mt * 16 + g, i1 = i0 + 8;
+      const float* b0p = bias_s + i0 * kBiasPitch + tq * 2;
+      const float* b1p = bias_s + i1 * kBiasPitch + tq * 2;
       float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
       for (int n = 0; n < 8; ++n) {
-        const int j = n * 8 + tq * 2;
-        s[n][0] = s[n][0] * a.scale + score_bias(pos_s, t, i0, j);
-        s[n][1] = s[n][1] * a.scale + score_bias(pos_s, t, i0, j + 1);
-        s[n][2] = s[n][2] * a.scale + score_bias(pos_s, t, i1, j);
-        s[n][3] = s[n][3] * a.scale + score_bias(pos_s, t, i1, j + 1);
+        const float2 b0 = *reinterpret_cast<const float2*>(b0p + n * 8);
+        const float2 b1 = *reinterpret_cast<const float2*>(b1p + n * 8);
+        s[n][0] = fmaf(s[n][0], sc2, b0.x * kLog2e);
+        s[n][1] = fmaf(s[n][1], sc2, b0.y * kLog2e);
+        s[n][2] = fmaf(s[n][2], sc2, b1.x * kLog2e);
+        s[n][3] = fmaf(s[n][3], sc2, b1.y * kLog2e);
+        if (flagged) {
+          const int j = n * 8 + tq * 2;
+          if (shift_masked(t, i0, j)) s[n][0] = -INFINITY;
+          if (shift_masked(t, i0, j + 1)) s[n][1] = -INFINITY;
+          if (shift_masked(t, i1, j)) s[n][2] = -INFINITY;
+          if (shift_masked(t, i1, j + 1)) s[n][3] = -INFINITY;
+        }
         m0 = fmaxf(m0, fmaxf(s[n][0], s[n][1]));
         m1 = fmaxf(m1, fmaxf(s[n][2], s[n][3]));
       }
@@ -187,8 +232,8 @@ __global__ void __launch_bounds__(kWarps * 32) window_attn_fwd_kernel(const Attn
       uint32_t pf[8][2];
 #pragma unroll
       for (int n = 0; n < 8; ++n) {
-        const float p0 = exp2f((s[n][0] - m0) * kLog2e), p1 = exp2f((s[n][1] - m0) * kLog2e);
-        const float p2 = exp2f((s[n][2] - m1) * kLog2e), p3 = exp2f((s[n][3] - m1) * kLog2e);
+        const float p0 = exp2f(s[n][0] - m0), p1 = exp2f(s[n][1] - m0);
+        const float p2 = exp2f(s[n][2] - m1), p3 = exp2f(s[n][3] - m1);
         l0 += p0 + p1; l1 += p2 + p3;
         pf[n][0] = pack_bf16(p0, p1);
         pf[n][1] = pack_bf16(p2, p3);
@@ -211,9 +256,9 @@ __global__ void __launch_bounds__(kWarps * 32) window_attn_fwd_kernel(const Attn
         if (i0 < kWt) *reinterpret_cast<uint32_t*>(qrow + i0 * kPitch + n * 8 + tq * 2) = pack_bf16(o[n][0] * r0, o[n][1] * r0);
         if (i1 < kWt) *reinterpret_cast<uint32_t*>(qrow + i1 * kPitch + n * 8 + tq * 2) = pack_bf16(o[n][2] * r1, o[n][3] * r1);
       }
-      if (a.lse != nullptr && tq == 0) {
-        if (i0 < kWt) a.lse[rows_s[i0] * a.heads + t.h] = m0 + __logf(l0);
-        if (i1 < kWt) a.lse[rows_s[i1] * a.heads + t.h] = m1 + __logf(l1);
+      if (a.lse != nullptr && tq == 0) {            // natural-log LSE of the scaled + biased scores
+        if (i0 < kWt) a.lse[rows_s[i0] * a.heads + t.h] = (m0 + log2f(l0)) * 0.6931471805599453f;
+        if (i1 < kWt) a.lse[rows_s[i1] * a.heads + t.h] = (m1 + log2f(l1)) * 0.6931471805599453f;
       }
     }
     __syncwarp();
@@ -221,7 +266,7 @@ __global__ void __launch_bounds__(kWarps * 32) window_attn_fwd_kernel(const Attn
     for (int it = 0; it < 7; ++it) {
       const int row = it * 8 + (lane >> 2);
       if (row < kWt) {
-        const uint4 v = *reinterpret_cast<const uint4*>(my + row * (kPitch * 2) + (lane & 3) * 16);
+        const uint4 v = *reinterpret_cast<const uint4*>(my + row * kRowB + (lane & 3) * 16);
         *reinterpret_cast<uint4*>(a.out + rows_s[row] * a.C + t.h * kHd + (lane & 3) * 8) = v;
       }
     }
@@ -232,37 +277,45 @@ __global__ void __launch_bounds__(kWarps * 32) window_attn_fwd_kernel(const Attn
 // ---------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------
+constexpr int kBwdWarpBytes = 4 * kTileBytes + kStageBytes;                      // q, k, v, dO, 16-row output staging
+constexpr int kBwdSmem = kBiasBytes + 704 + kWarps * 64 * 8 + kWarps * 2 * 64 * 4 + kWarps * kBwdWarpBytes;
+
 __global__ void __launch_bounds__(kWarps * 32) window_attn_bwd_kernel(const AttnArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, tq = lane & 3;
-  float* pos_s = reinterpret_cast<float*>(smem);                                  // [169] (704 B)
-  float* bins = reinterpret_cast<float*>(smem + 704);                             // [169] (704 B)
-  long long* rows_all = reinterpret_cast<long long*>(smem + 1408);                // [kWarps][64]
-  float* stat_all = reinterpret_cast<float*>(smem + 1408 + kWarps * 64 * 8);      // [kWarps][2][64]: lse, D
-  uint8_t* slabs = smem + 1408 + kWarps * 64 * 8 + kWarps * 2 * 64 * 4;
-  uint8_t* my = slabs + warp * 5 * kTileBytes;                                    // q, k, v, dO, staging
+  float* bias_s = reinterpret_cast<float*>(smem);
+  float* bins = reinterpret_cast<float*>(smem + kBiasBytes);                                    // [169] (704 B)
+  long long* rows_all = reinterpret_cast<long long*>(smem + kBiasBytes + 704);                  // [kWarps][64]
+  float* stat_all = reinterpret_cast<float*>(smem + kBiasBytes + 704 + kWarps * 64 * 8);        // [kWarps][2][64]: lse (log2), D
+  uint8_t* my = smem + kBiasBytes + 704 + kWarps * 64 * 8 + kWarps * 2 * 64 * 4 + warp * kBwdWarpBytes;
   const uint32_t qs = smem_u32(my), ks = qs + kTileBytes, vs = ks + kTileBytes, dos = vs + kTileBytes;
   bf16* stage = reinterpret_cast<bf16*>(my + 4 * kTileBytes);
   long long* rows_s = rows_all + warp * 64;
   float* lse_s = stat_all + warp * 128;
   float* dsum_s = lse_s + 64;
+  float* slots = a.dslots + (1LL * blockIdx.x * kWarps + warp) * (kSlots * 32) + lane;          // [slot * 32]
 
-  for (int i = threadIdx.x; i < kBins; i += blockDim.x) { pos_s[i] = a.pos[i]; bins[i] = 0.f; }
-  for (int i = lane; i < 5 * kTileBytes / 16; i += 32) reinterpret_cast<uint4*>(my)[i] = make_uint4(0, 0, 0, 0);
+  build_bias_table(bias_s, a.pos);
+  for (int i = threadIdx.x; i < kBins; i += blockDim.x) bins[i] = 0.f;
+  for (int i = lane; i < kBwdWarpBytes / 16; i += 32) reinterpret_cast<uint4*>(my)[i] = make_uint4(0, 0, 0, 0);
+#pragma unroll 4
+  for (int sl = 0; sl < kSlots; ++sl) slots[sl * 32] = 0.f;
   __syncthreads();
 
   const long long ntasks = 1LL * a.B * (a.H / kWs) * (a.W / kWs) * a.heads;
   const long long ld_qkv = 3LL * a.C;
+  const float sc2 = a.scale * kLog2e;
   for (long long task = 1LL * blockIdx.x * kWarps + warp; task < ntasks; task += 1LL * gridDim.x * kWarps) {
     const Task t = decode_task(a, task);
+    const bool flagged = t.ul || t.lr;
     for (int i = lane; i < 64; i += 32) {
       if (i < kWt) {
         const long long r = token_row(a, t, i);
         rows_s[i] = r;
-        lse_s[i] = a.lse[r * a.heads + t.h];
+        lse_s[i] = a.lse[r * a.heads + t.h] * kLog2e;
       } else {
-        lse_s[i] = 0.f;
+        lse_s[i] = INFINITY;          // padded query rows: exp2(x - inf) = 0
         dsum_s[i] = 0.f;
       }
     }
@@ -302,13 +355,13 @@ __global__ void __launch_bounds__(kWarps * 32) window_attn_bwd_kernel(const Attn
 #pragma unroll
       for (int kk = 0; kk < 2; ++kk) {
         uint32_t k0, k1, k2, k3, v0, v1, v2, v3;
-        const uint32_t aoff = (jt * 16 + (lane & 15)) * (kPitch * 2) + (kk * 16 + (lane >> 4) * 8) * 2;
+        const uint32_t aoff = off_a(jt, kk, lane);
         ldsm_x4(ks + aoff, k0, k1, k2, k3);     // A = K rows (keys)
         ldsm_x4(vs + aoff, v0, v1, v2, v3);     // A = V rows (keys)
 #pragma unroll
         for (int np = 0; np < 4; ++np) {
           uint32_t b0, b1, b2, b3;
-          const uint32_t boff = (np * 16 + (lane & 7) + (lane >> 4) * 8) * (kPitch * 2) + (kk * 16 + ((lane >> 3) & 1) * 8) * 2;
+          const uint32_t boff = off_b(np, kk, lane);
           ldsm_x4(qs + boff, b0, b1, b2, b3);   // B = Q  (n = query i, k = d)
           mma16816(st[2 * np], k0, k1, k2, k3, b0, b1);
           mma16816(st[2 * np + 1], k0, k1, k2, k3, b2, b3);
@@ -326,9 +379,9 @@ __global__ void __launch_bounds__(kWarps * 32) window_attn_bwd_kernel(const Attn
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int ii = i + (e & 1), jj = (e < 2) ? j0 : j1;
-          const bool valid = ii < kWt && jj < kWt;
-          const float sc = st[n][e] * a.scale + score_bias(pos_s, t, ii, jj);
-          p[e] = valid ? exp2f((sc - lse_s[ii]) * kLog2e) : 0.f;
+          float sc = fmaf(st[n][e], sc2, bias_s[ii * kBiasPitch + jj] * kLog2e);
+          if (flagged && shift_masked(t, ii, jj)) sc = -INFINITY;
+          p[e] = exp2f(sc - lse_s[ii]);
           ds[e] = p[e] * (dpt[n][e] - dsum_s[ii]) * a.scale;
         }
         pf[n][0] = pack_bf16(p[0], p[1]); pf[n][1] = pack_bf16(p[2], p[3]);
@@ -342,7 +395,7 @@ __global__ void __launch_bounds__(kWarps * 32) window_attn_bwd_kernel(const Attn
 #pragma unroll
         for (int np = 0; np < 2; ++np) {
           uint32_t b0, b1, b2, b3;
-          const uint32_t boff = (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * (kPitch * 2) + ((np * 2 + (lane >> 4)) * 8) * 2;
+          const uint32_t boff = off_bt(kk, np, lane);
           ldsm_x4_t(dos + boff, b0, b1, b2, b3);   // B = dO (k = i, n = d)
           mma16816(dv[2 * np], pf[2 * kk][0], pf[2 * kk][1], pf[2 * kk + 1][0], pf[2 * kk + 1][1], b0, b1);
           mma16816(dv[2 * np + 1], pf[2 * kk][0], pf[2 * kk][1], pf[2 * kk + 1][0], pf[2 * kk + 1][1], b2, b3);
@@ -366,14 +419,14 @@ __global__ void __launch_bounds__(kWarps * 32) window_attn_bwd_kernel(const Attn
           const int r = it * 8 + (lane >> 2);
           const int j = jt * 16 + r;
           if (j < kWt) {
-            const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(stage) + r * (kPitch * 2) + (lane & 3) * 16);
+            const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(stage) + r * kRowB + (lane & 3) * 16);
             *reinterpret_cast<uint4*>(a.dqkv + rows_s[j] * ld_qkv + (which == 0 ? 1 : 2) * a.C + t.h * kHd + (lane & 3) * 8) = v;
           }
         }
       }
     }
 
-    // ---- pass B: query-major (rows = queries i): dQ = scale * dS K, dpos[bin(i,j)] += dS ----------------
+    // ---- pass B: query-major (rows = queries i): dQ = scale * dS K; dS summed per lane for the rel-pos gradient ----
 #pragma unroll 1
     for (int mt = 0; mt < 4; ++mt) {
       float s[8][4], dp[8][4];
@@ -382,13 +435,13 @@ __global__ void __launch_bounds__(kWarps * 32) window_attn_bwd_kernel(const Attn
 #pragma unroll
       for (int kk = 0; kk < 2; ++kk) {
         uint32_t q0, q1, q2, q3, d0, d1, d2, d3;
-        const uint32_t aoff = (mt * 16 + (lane & 15)) * (kPitch * 2) + (kk * 16 + (lane >> 4) * 8) * 2;
+        const uint32_t aoff = off_a(mt, kk, lane);
         ldsm_x4(qs + aoff, q0, q1, q2, q3);
         ldsm_x4(dos + aoff, d0, d1, d2, d3);
 #pragma unroll
         for (int np = 0; np < 4; ++np) {
           uint32_t b0, b1, b2, b3;
-          const uint32_t boff = (np * 16 + (lane & 7) + (lane >> 4) * 8) * (kPitch * 2) + (kk * 16 + ((lane >> 3) & 1) * 8) * 2;
+          const uint32_t boff = off_b(np, kk, lane);
           ldsm_x4(ks + boff, b0, b1, b2, b3);   // B = K (n = key j, k = d)
           mma16816(s[2 * np], q0, q1, q2, q3, b0, b1);
           mma16816(s[2 * np + 1], q0, q1, q2, q3, b2, b3);
@@ -398,25 +451,34 @@ __global__ void __launch_bounds__(kWarps * 32) window_attn_bwd_kernel(const Attn
         }
       }
       const int i0 = mt * 16 + g, i1 = i0 + 8;
+      const float* b0p = bias_s + i0 * kBiasPitch + tq * 2;
+      const float* b1p = bias_s + i1 * kBiasPitch + tq * 2;
+      const float l0 = lse_s[i0], l1 = lse_s[i1], D0 = dsum_s[i0], D1 = dsum_s[i1];
+      float* sl = slots + mt * (7 * 4 * 32);
       uint32_t df[8][2];
 #pragma unroll
       for (int n = 0; n < 8; ++n) {
-        const int j = n * 8 + tq * 2;
-        float ds[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int ii = (e < 2) ? i0 : i1, jj = j + (e & 1);
-          const bool valid = ii < kWt && jj < kWt;
-          const float sc = s[n][e] * a.scale + score_bias(pos_s, t, ii, jj);
-          const float p = valid ? exp2f((sc - lse_s[ii]) * kLog2e) : 0.f;
-          ds[e] = p * (dp[n][e] - dsum_s[ii]);
-          if (valid && p != 0.f) {
-            const int ri = ii / kWs, ci = ii - ri * kWs, rj = jj / kWs, cj = jj - rj * kWs;
-            atomicAdd(&bins[(rj - ri + kWs - 1) * (2 * kWs - 1) + (cj - ci + kWs - 1)], ds[e]);
-          }
-          ds[e] *= a.scale;
+        const float2 b0 = *reinterpret_cast<const float2*>(b0p + n * 8);
+        const float2 b1 = *reinterpret_cast<const float2*>(b1p + n * 8);
+        float sc[4];
+        sc[0] = fmaf(s[n][0], sc2, b0.x * kLog2e); sc[1] = fmaf(s[n][1], sc2, b0.y * kLog2e);
+        sc[2] = fmaf(s[n][2], sc2, b1.x * kLog2e); sc[3] = fmaf(s[n][3], sc2, b1.y * kLog2e);
+        if (flagged) {
+          const int j = n * 8 + tq * 2;
+          if (shift_masked(t, i0, j)) sc[0] = -INFINITY;
+          if (shift_masked(t, i0, j + 1)) sc[1] = -INFINITY;
+          if (shift_masked(t, i1, j)) sc[2] = -INFINITY;
+          if (shift_masked(t, i1, j + 1)) sc[3] = -INFINITY;
         }
-        df[n][0] = pack_bf16(ds[0], ds[1]); df[n][1] = pack_bf16(ds[2], ds[3]);
+        float ds[4];
+        ds[0] = exp2f(sc[0] - l0) * (dp[n][0] - D0); ds[1] = exp2f(sc[1] - l0) * (dp[n][1] - D0);
+        ds[2] = exp2f(sc[2] - l1) * (dp[n][2] - D1); ds[3] = exp2f(sc[3] - l1) * (dp[n][3] - D1);
+        if (n < 7) {     // keys 56..63 are padding; per-lane private accumulators, no atomics
+#pragma unroll
+          for (int e = 0; e < 4; ++e) sl[(n * 4 + e) * 32] += ds[e];
+        }
+        df[n][0] = pack_bf16(ds[0] * a.scale, ds[1] * a.scale);
+        df[n][1] = pack_bf16(ds[2] * a.scale, ds[3] * a.scale);
       }
       float dq[4][4];
 #pragma unroll
@@ -426,8 +488,7 @@ __global__ void __launch_bounds__(kWarps * 32) window_attn_bwd_kernel(const Attn
 #pragma unroll
         for (int np = 0; np < 2; ++np) {
           uint32_t b0, b1, b2, b3;
-          const uint32_t boff = (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * (kPitch * 2) + ((np * 2 + (lane >> 4)) * 8) * 2;
-          ldsm_x4_t(ks + boff, b0, b1, b2, b3);    // B = K (k = j, n = d)
+          ldsm_x4_t(ks + off_bt(kk, np, lane), b0, b1, b2, b3);    // B = K (k = j, n = d)
           mma16816(dq[2 * np], df[2 * kk][0], df[2 * kk][1], df[2 * kk + 1][0], df[2 * kk + 1][1], b0, b1);
           mma16816(dq[2 * np + 1], df[2 * kk][0], df[2 * kk][1], df[2 * kk + 1][0], df[2 * kk + 1][1], b2, b3);
         }
@@ -443,12 +504,22 @@ __global__ void __launch_bounds__(kWarps * 32) window_attn_bwd_kernel(const Attn
         const int r = it * 8 + (lane >> 2);
         const int i = mt * 16 + r;
         if (i < kWt) {
-          const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(stage) + r * (kPitch * 2) + (lane & 3) * 16);
+          const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(stage) + r * kRowB + (lane & 3) * 16);
           *reinterpret_cast<uint4*>(a.dqkv + rows_s[i] * ld_qkv + t.h * kHd + (lane & 3) * 8) = v;
         }
       }
     }
     __syncwarp();
+  }
+  // fold the per-lane accumulators into the 13 x 13 bins (once per warp), then one partial row per CTA
+#pragma unroll 1
+  for (int sl = 0; sl < kSlots; ++sl) {
+    const int mt = sl / 28, n = (sl % 28) >> 2, e = sl & 3;
+    const int i = mt * 16 + g + ((e & 2) ? 8 : 0), j = n * 8 + tq * 2 + (e & 1);
+    if (i < kWt && j < kWt) {
+      const int ri = i / kWs, ci = i - ri * kWs, rj = j / kWs, cj = j - rj * kWs;
+      atomicAdd(&bins[(rj - ri + kWs - 1) * (2 * kWs - 1) + (cj - ci + kWs - 1)], slots[sl * 32]);
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < kBins; i += blockDim.x) a.dpos_partial[1LL * blockIdx.x * kBins + i] = bins[i];
@@ -461,9 +532,6 @@ __global__ void dpos_reduce_kernel(const float* __restrict__ partial, float* __r
   for (int b = 0; b < blocks; ++b) acc += partial[1LL * b * kBins + i];
   out[i] = acc;
 }
-
-constexpr int kFwdSmem = 704 + kWarps * 64 * 8 + kWarps * 3 * kTileBytes;
-constexpr int kBwdSmem = 1408 + kWarps * 64 * 8 + kWarps * 2 * 64 * 4 + kWarps * 5 * kTileBytes;
 
 int check_shape(int B, int H, int W, int C, int heads) {
   B200_REQUIRE(B >= 0 && H > 0 && W > 0 && H % kWs == 0 && W % kWs == 0, "window_attn: H=%d W=%d must be multiples of 7", H, W);
@@ -485,7 +553,7 @@ extern "C" int b200_window_attn_fwd(const void* qkv, const float* pos, void* out
   if (!attr) { B200_CHECK_CUDA(cudaFuncSetAttribute(window_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem)); attr = true; }
   const long long ntasks = 1LL * B * (H / kWs) * (W / kWs) * heads;
   long long blocks = (ntasks + kWarps - 1) / kWarps;
-  const long long cap = 1LL * b200_num_sms() * 3 * 4;
+  const long long cap = 1LL * b200_num_sms() * 3 * 2;     // 3 resident CTAs per SM, 2 waves (the bias table is built per CTA)
   if (blocks > cap) blocks = cap;
   window_attn_fwd_kernel<<<static_cast<unsigned>(blocks), kWarps * 32, kFwdSmem, reinterpret_cast<cudaStream_t>(stream)>>>(a);
   B200_LAUNCH_CHECK();
@@ -500,20 +568,24 @@ extern "C" int b200_window_attn_bwd_blocks(int B, int H, int W, int heads) {
   return blocks < 1 ? 1 : static_cast<int>(blocks);
 }
 
+// floats per CTA of the scratch that follows the [blocks, 169] partial rows in `dpos_partial`
+extern "C" long long b200_window_attn_bwd_scratch_floats(int blocks) { return 1LL * blocks * (kBins + kWarps * kSlots * 32); }
+
 extern "C" int b200_window_attn_bwd(const void* qkv, const float* pos, const void* o, const float* lse, const void* dout,
                                     void* dqkv, float* dpos, float* dpos_partial, int accumulate_dpos, int B, int H, int W,
                                     int C, int heads, int shifted, void* stream) {
   int rc = check_shape(B, H, W, C, heads);
   if (rc) return rc;
   if (B == 0) return B200_OK;
+  const int blocks = b200_window_attn_bwd_blocks(B, H, W, heads);
   AttnArgs a{};
   a.qkv = reinterpret_cast<const bf16*>(qkv); a.pos = pos; a.o = reinterpret_cast<const bf16*>(o);
   a.lse = const_cast<float*>(lse); a.dout = reinterpret_cast<const bf16*>(dout); a.dqkv = reinterpret_cast<bf16*>(dqkv);
   a.dpos_partial = dpos_partial;
+  a.dslots = dpos_partial + 1LL * blocks * kBins;      // scratch layout: [blocks][169] partial rows, then the per-lane slots
   a.B = B; a.H = H; a.W = W; a.C = C; a.heads = heads; a.shifted = shifted; a.scale = 0.17677669529663687f;
   static bool attr = false;
   if (!attr) { B200_CHECK_CUDA(cudaFuncSetAttribute(window_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem)); attr = true; }
-  const int blocks = b200_window_attn_bwd_blocks(B, H, W, heads);
   auto st = reinterpret_cast<cudaStream_t>(stream);
   window_attn_bwd_kernel<<<blocks, kWarps * 32, kBwdSmem, st>>>(a);
   B200_LAUNCH_CHECK();

@@ -305,24 +305,54 @@ struct EpiMargin {
 // ---------------------------------------------------------------------------------------------
 // split-K reduce: out[i] (+)= sum_s partial[s][i], fixed order -> deterministic
 // ---------------------------------------------------------------------------------------------
-__global__ void splitk_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, long long n, int splits,
-                                     int accumulate, long long stride) {
-  const long long i4 = (1LL * blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  if (i4 >= n) return;
-  float4 acc = accumulate ? *reinterpret_cast<const float4*>(out + i4) : make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int s = 0; s < splits; ++s) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(partial + 1LL * s * stride + i4));
-    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+// SL split-lanes cooperate on one float4 column group: lane sx sums splits sx, sx+SL, ... in order, then a fixed
+// smem tree folds the SL partial sums.  The association order depends only on (splits, SL): deterministic.
+template <int SL>
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, long long n,
+                                                            int splits, int accumulate, long long stride) {
+  constexpr int CG = 256 / SL;                       // column groups (of 4 floats) per block
+  __shared__ float4 red[SL][CG];
+  const int cx = threadIdx.x % CG, sx = threadIdx.x / CG;
+  const long long col = (1LL * blockIdx.x * CG + cx) * 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (col < n)
+    for (int s = sx; s < splits; s += SL) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(partial + 1LL * s * stride + col));
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  if (SL > 1) {
+    red[sx][cx] = acc;
+    __syncthreads();
+#pragma unroll
+    for (int o = SL / 2; o > 0; o >>= 1) {
+      if (sx < o) {
+        const float4 a = red[sx][cx], b = red[sx + o][cx];
+        red[sx][cx] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+      }
+      __syncthreads();
+    }
+    acc = red[0][cx];
   }
-  *reinterpret_cast<float4*>(out + i4) = acc;
+  if (sx == 0 && col < n) {
+    if (accumulate) {
+      const float4 c = *reinterpret_cast<const float4*>(out + col);
+      acc.x += c.x; acc.y += c.y; acc.z += c.z; acc.w += c.w;
+    }
+    *reinterpret_cast<float4*>(out + col) = acc;
+  }
 }
 
 int splitk_reduce(const float* partial, float* out, long long n, int splits, int accumulate, cudaStream_t stream, long long stride) {
   if (stride <= 0) stride = n;
   B200_REQUIRE(n % 4 == 0 && stride % 4 == 0, "splitk_reduce: n %% 4 != 0");
-  const int threads = 256;
-  const long long blocks = (n / 4 + threads - 1) / threads;
-  splitk_reduce_kernel<<<(unsigned)blocks, threads, 0, stream>>>(partial, out, n, splits, accumulate, stride);
+  const long long groups = n / 4;
+  if (splits <= 4) {
+    splitk_reduce_kernel<1><<<(unsigned)((groups + 255) / 256), 256, 0, stream>>>(partial, out, n, splits, accumulate, stride);
+  } else if (splits <= 32 || groups >= 65536) {
+    splitk_reduce_kernel<8><<<(unsigned)((groups + 31) / 32), 256, 0, stream>>>(partial, out, n, splits, accumulate, stride);
+  } else {
+    splitk_reduce_kernel<32><<<(unsigned)((groups + 7) / 8), 256, 0, stream>>>(partial, out, n, splits, accumulate, stride);
+  }
   B200_LAUNCH_CHECK();
   return B200_OK;
 }
@@ -342,6 +372,15 @@ extern "C" int b200_gemm_tn(const void* a, long long lda, const void* b, long lo
   gemm::Operands o{a, (int)lda, b, (int)ldb, M, N, K, is_bf16 != 0, block_n, splits, 0};
   gemm::EpiLinear::Params ep{mode, out, ldo, out_fp32, reinterpret_cast<bf16*>(out2), ldo2, bias,
                              reinterpret_cast<const bf16*>(aux), ldaux, split_stride};
+  return gemm::launch<gemm::EpiLinear>(o, ep, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// dW[N,K] (fp32 split partials) = dY[tokens,N]^T * X[tokens,K]: both operands are read in place, MN-major - no transposes.
+extern "C" int b200_gemm_wgrad(const void* dy, long long ldy, const void* x, long long ldx, long long tokens, int N, int K,
+                               float* partial, int splits, int block_n, void* stream) {
+  B200_REQUIRE(K % 8 == 0 && N > 0 && tokens > 0 && tokens < (1LL << 31), "gemm_wgrad: bad shape tokens=%lld N=%d K=%d", tokens, N, K);
+  gemm::Operands o{dy, (int)ldy, x, (int)ldx, N, K, static_cast<int>(tokens), true, block_n, splits, 0, true};
+  gemm::EpiLinear::Params ep{B200_EPI_PARTIAL, partial, K, 1, nullptr, 0, nullptr, nullptr, 0, 1LL * N * K};
   return gemm::launch<gemm::EpiLinear>(o, ep, reinterpret_cast<cudaStream_t>(stream));
 }
 

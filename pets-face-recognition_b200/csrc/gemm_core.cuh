@@ -36,16 +36,20 @@ struct CoreParams {
   int k_blocks;              // ceil(K / 64) over the whole contraction
   int splits;                // split-K factor (>= 1)
   int k_blocks_per_split;
-  uint32_t idesc;            // tcgen05 instruction descriptor (formats, M=128, N=block_n)
+  uint32_t idesc;            // tcgen05 instruction descriptor (formats, majors, M=128, N=block_n)
+  int mn_major;              // 1: operands are [K, M] / [K, N] row-major (contraction index = row): weight gradients
+  int b_chunks;              // mn_major: 64-column chunks of the B tile = ceil(block_n / 64)
 };
 
 // instruction descriptor, kind::f16: [4,6) D fmt (1=f32), [7,10) A fmt, [10,13) B fmt (0=f16, 1=bf16),
 // [15] A major, [16] B major (0 = K-major), [17,23) N>>3, [24,29) M>>4
-inline uint32_t make_idesc(bool is_bf16, int block_n) {
+inline uint32_t make_idesc(bool is_bf16, int block_n, bool mn_major = false) {
   uint32_t d = 0;
   d |= 1u << 4;
   d |= (is_bf16 ? 1u : 0u) << 7;
   d |= (is_bf16 ? 1u : 0u) << 10;
+  d |= (mn_major ? 1u : 0u) << 15;
+  d |= (mn_major ? 1u : 0u) << 16;
   d |= static_cast<uint32_t>(block_n >> 3) << 17;
   d |= static_cast<uint32_t>(kBlockM >> 4) << 24;
   return d;
@@ -92,7 +96,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   const int num_tiles = p.m_blocks * p.n_blocks * p.splits;
-  const uint32_t tx_bytes = static_cast<uint32_t>((kBlockM + p.block_n) * kBlockK * 2);
+  // K-major: one [128 x 64] A box + one [block_n x 64] B box per stage.  MN-major: the tile is [64 contraction rows x
+  // 128 / block_n columns], loaded as [64 x 64] boxes (one 128-B swizzle row = 64 columns) 8 KB apart.
+  constexpr uint32_t kChunk = 64 * 64 * 2;
+  const uint32_t tx_bytes = p.mn_major ? static_cast<uint32_t>((2 + p.b_chunks) * kChunk)
+                                       : static_cast<uint32_t>((kBlockM + p.block_n) * kBlockK * 2);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -108,8 +116,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
           const uint32_t sa = smem_base + stage * kStageBytes;
-          tma_load_2d(sa, &tmap_a, full_bar(stage), kb * kBlockK, m_blk * kBlockM);
-          tma_load_2d(sa + kABytes, &tmap_b, full_bar(stage), kb * kBlockK, n_blk * p.block_n);
+          if (!p.mn_major) {
+            tma_load_2d(sa, &tmap_a, full_bar(stage), kb * kBlockK, m_blk * kBlockM);
+            tma_load_2d(sa + kABytes, &tmap_b, full_bar(stage), kb * kBlockK, n_blk * p.block_n);
+          } else {
+            for (int c = 0; c < 2; ++c) tma_load_2d(sa + c * kChunk, &tmap_a, full_bar(stage), m_blk * kBlockM + c * 64, kb * kBlockK);
+            for (int c = 0; c < p.b_chunks; ++c)
+              tma_load_2d(sa + kABytes + c * kChunk, &tmap_b, full_bar(stage), n_blk * p.block_n + c * 64, kb * kBlockK);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -131,13 +145,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * kStageBytes;
-          const uint64_t da = make_sw128_desc(sa, 16, 1024);
-          const uint64_t db = make_sw128_desc(sa + kABytes, 16, 1024);
+          // K-major : SBO = 1024 B between 8-row groups; a K=16 slice is +32 B inside the 128-B swizzle row (+2 in addr>>4)
+          // MN-major: LBO = 8 KB between 64-column chunks, SBO = 1024 B between 8-row (contraction) groups; a K=16 slice
+          //           is 16 rows = +2048 B (+128 in addr>>4)
+          const uint64_t da = p.mn_major ? make_sw128_desc(sa, kChunk, 1024) : make_sw128_desc(sa, 16, 1024);
+          const uint64_t db = p.mn_major ? make_sw128_desc(sa + kABytes, kChunk, 1024) : make_sw128_desc(sa + kABytes, 16, 1024);
+          const uint32_t kstep = p.mn_major ? 128u : 2u;
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            // +32 B per K=16 slice inside the 128-B swizzle row: +2 in the (addr >> 4) field
-            umma_f16(d_tmem, da + 2u * k, db + 2u * k, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < kBlockK / 16; ++k) umma_f16(d_tmem, da + kstep * k, db + kstep * k, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           umma_commit(empty_bar(stage));                 // smem slot reusable once these MMAs retire
           if (kb == kb1 - 1) umma_commit(tfull_bar(acc)); // accumulator complete
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -201,13 +216,14 @@ int encode_tmap_2d(CUtensorMap* map, bool is_bf16, const void* ptr, uint64_t inn
 int pick_block_n(int N);
 
 struct Operands {
-  const void* a; int lda;     // [M, K] row-major, 16-bit
-  const void* b; int ldb;     // [N, K] row-major, 16-bit
+  const void* a; int lda;     // [M, K] row-major, 16-bit           (mn_major: [K, M] row-major)
+  const void* b; int ldb;     // [N, K] row-major, 16-bit           (mn_major: [K, N] row-major)
   int M, N, K;
   bool is_bf16;
   int block_n;                // 0 = auto
   int splits;                 // <= 1 = no split-K
   int max_ctas;               // 0 = #SMs
+  bool mn_major = false;      // D = A^T B with the contraction over the ROWS of both operands (weight gradients)
 };
 
 template <class Epi>
@@ -228,12 +244,21 @@ int launch(const Operands& o, const typename Epi::Params& ep, cudaStream_t strea
   if (p.splits > p.k_blocks) p.splits = p.k_blocks;
   p.k_blocks_per_split = (p.k_blocks + p.splits - 1) / p.splits;
   p.splits = (p.k_blocks + p.k_blocks_per_split - 1) / p.k_blocks_per_split;   // no empty splits
-  p.idesc = make_idesc(o.is_bf16, p.block_n);
+  p.idesc = make_idesc(o.is_bf16, p.block_n, o.mn_major);
+  p.mn_major = o.mn_major ? 1 : 0;
+  p.b_chunks = (p.block_n + 63) / 64;
 
   CUtensorMap ta, tb;
-  int rc = encode_tmap_2d(&ta, o.is_bf16, o.a, o.K, o.M, o.lda, kBlockK, kBlockM);
-  if (rc) return rc;
-  rc = encode_tmap_2d(&tb, o.is_bf16, o.b, o.K, o.N, o.ldb, kBlockK, p.block_n);
+  int rc;
+  if (!o.mn_major) {
+    rc = encode_tmap_2d(&ta, o.is_bf16, o.a, o.K, o.M, o.lda, kBlockK, kBlockM);
+    if (rc) return rc;
+    rc = encode_tmap_2d(&tb, o.is_bf16, o.b, o.K, o.N, o.ldb, kBlockK, p.block_n);
+  } else {
+    rc = encode_tmap_2d(&ta, o.is_bf16, o.a, o.M, o.K, o.lda, 64, kBlockK);
+    if (rc) return rc;
+    rc = encode_tmap_2d(&tb, o.is_bf16, o.b, o.N, o.K, o.ldb, 64, kBlockK);
+  }
   if (rc) return rc;
 
   static bool attr_done = false;   // per instantiation

@@ -55,7 +55,7 @@ struct Plan {
   // head / tail activations
   long long pooled, pool_mean, pool_rstd, pooled_n;
   // backward transients
-  long long g_a, g_b, d_big, d_small, t_a, t_b, partial, red_partial, dpos_partial, demb16, dpooled;
+  long long g_a, g_b, d_big, d_small, partial, red_partial, dpos_partial, demb16, dpooled;
   long long partial_bytes;
 };
 
@@ -163,14 +163,12 @@ void build(Plan& p) {
     p.g_a = add_ws(p, maxMC * 2); p.g_b = add_ws(p, maxMC * 2);
     p.d_big = add_ws(p, big * 2);
     p.d_small = add_ws(p, maxMC * 2);
-    p.t_a = add_ws(p, big * 2);
-    p.t_b = add_ws(p, big * 2);
     // split-K partials: worst case is ~#SMs tiles of 128 x 256 fp32 (each CTA writes at most a few tiles)
     partial = 1LL * 4 * 160 * 128 * 256 * 4;
     p.partial_bytes = partial;
     p.partial = add_ws(p, partial);
     p.red_partial = add_ws(p, 1LL * 1024 * 3072 * 4);         // LN / colsum partial rows: <= 4*SMs rows x <= 3072 cols
-    p.dpos_partial = add_ws(p, 1LL * 1024 * 169 * 4);
+    p.dpos_partial = add_ws(p, b200_window_attn_bwd_scratch_floats(2 * 160) * 4);   // <= 2 CTAs per SM
     p.demb16 = add_ws(p, 1LL * p.B * p.num_classes * 2);
     p.dpooled = add_ws(p, 1LL * p.B * C4 * 2);
   }
@@ -197,14 +195,9 @@ int linear_dgrad(const Ctx& c, const bf16* dy, long long M, int N, const bf16* w
   return b200_gemm_tn(dy, N, w16t, N, static_cast<int>(M), K, N, 1, mode, dx, K, 0, nullptr, 0, nullptr, aux, K, 1, 0, 0, c.stv);
 }
 
-// dW[N,K] = dY[M,N]^T * X[M,K]: both operands transposed into K-major form, split-K over the tokens,
+// dW[N,K] = dY[M,N]^T * X[M,K]: operands read in place (MN-major tcgen05 descriptors), split-K over the tokens,
 // fp32 partials reduced in a fixed order.
 int linear_wgrad(const Ctx& c, const bf16* dy, long long M, int N, const bf16* x, int K, float* dw) {
-  const long long Mp = align_up(M, 8);
-  bf16* ta = c.W<bf16>(c.p.t_a);
-  bf16* tb = c.W<bf16>(c.p.t_b);
-  RC(b200_transpose16(dy, ta, M, N, N, Mp, c.stv));
-  RC(b200_transpose16(x, tb, M, K, K, Mp, c.stv));
   const int bn = (K <= 256) ? static_cast<int>(align_up(K, 16)) : 0;
   const int bn_eff = bn ? bn : 256;
   const long long tiles = ((N + 127) / 128) * ((K + bn_eff - 1) / bn_eff);
@@ -213,8 +206,7 @@ int linear_wgrad(const Ctx& c, const bf16* dy, long long M, int N, const bf16* x
   while (splits > 1 && 1LL * splits * N * K * 4 > c.p.partial_bytes) --splits;
   splits = b200_gemm_splits(static_cast<int>(M), splits);
   float* partial = c.W<float>(c.p.partial);
-  RC(b200_gemm_tn(ta, Mp, tb, Mp, N, K, static_cast<int>(M), 1, B200_EPI_PARTIAL, partial, K, 1, nullptr, 0, nullptr, nullptr, 0,
-                  splits, 1LL * N * K, bn, c.stv));
+  RC(b200_gemm_wgrad(dy, N, x, K, M, N, K, partial, splits, bn, c.stv));
   return b200_splitk_reduce(partial, dw, 1LL * N * K, splits, 0, c.stv);
 }
 

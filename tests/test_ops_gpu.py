@@ -86,6 +86,18 @@ def test_gemm_splitk_partial(M, N, K, splits):
     assert rel_err(out2, 2 * ref) < 2e-5 * math.sqrt(K) + 1e-6
 
 
+@pytest.mark.parametrize('tokens,N,K,splits', [(6272, 384, 96, 49), (1000, 96, 48, 7), (130, 768, 3072, 2), (2, 512, 768, 1),
+                                               (50000, 288, 96, 148), (392, 2304, 768, 3), (777, 96, 384, 5)])
+def test_gemm_wgrad_mn_major(tokens, N, K, splits):
+    """dW = dY^T X straight from the row-major activations (MN-major tcgen05 operands), vs fp32 matmul."""
+    from b200 import ops
+    dy, x = rnd(tokens, N, seed=1, scale=0.1), rnd(tokens, K, seed=2, scale=0.1)
+    out = ops.splitk_reduce(ops.gemm_wgrad(dy, x, splits=splits))
+    ref = dy.float().t() @ x.float()
+    assert out.shape == (N, K)
+    assert rel_err(out, ref) < 2e-5 * math.sqrt(tokens) + 1e-6
+
+
 @pytest.mark.parametrize('C', [96, 192, 384, 768])
 @pytest.mark.parametrize('M', [1, 49, 1000])
 def test_layernorm(C, M):
