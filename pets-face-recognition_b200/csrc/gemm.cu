@@ -137,6 +137,26 @@ int encode_tmap_2d(CUtensorMap* map, bool is_bf16, const void* ptr, uint64_t inn
   return B200_OK;
 }
 
+int encode_tmap_out(CUtensorMap* map, int elem_bytes, const void* ptr, uint64_t cols, uint64_t rows, uint64_t splits,
+                    uint64_t pitch_elems, uint64_t split_stride_elems, uint32_t box_cols) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return b200_set_error(B200_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[3] = {cols, rows, splits};
+  cuuint64_t strides[2] = {pitch_elems * elem_bytes, split_stride_elems * elem_bytes};
+  cuuint32_t box[3] = {box_cols, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  const uint32_t row_bytes = box_cols * elem_bytes;
+  const CUtensorMapSwizzle swz = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  if (row_bytes != 128 && row_bytes != 64 && row_bytes != 32)
+    return b200_set_error(B200_ERR_INVALID, "output box row of %u B unsupported", row_bytes);
+  CUresult r = fn(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims,
+                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return b200_set_error(B200_ERR_CUDA, "cuTensorMapEncodeTiled(out) failed (%d) cols=%llu rows=%llu splits=%llu pitch=%llu box=%u", (int)r,
+                          (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)splits, (unsigned long long)pitch_elems, box_cols);
+  return B200_OK;
+}
+
 // Tile width: N itself (rounded to 16) when it fits one tile, otherwise the width in [128,256] that
 // wastes the fewest padded columns (ties -> wider).  96->96, 288->144, 384->192, 768->256, 1152->192.
 int pick_block_n(int N) {
@@ -156,22 +176,11 @@ int pick_block_n(int N) {
 // ---------------------------------------------------------------------------------------------
 struct EpiLinear {
   struct Params {
-    int mode;                 // B200_EPI_*
-    void* out; long long ldo; int out_fp32;
-    bf16* out2; long long ldo2;         // GELU mode: pre-activation copy
+    int mode;                            // B200_EPI_*
     const float* bias;                   // [N] or null
     const bf16* aux; long long ldaux;   // RESID: residual input; DGELU: saved pre-activation
-    long long split_stride;              // PARTIAL: elements between the fp32 partials of two splits
   };
 
-  __device__ static __forceinline__ void begin_tile(const Params&, const CoreParams&, int, int, int) {}
-  __device__ static __forceinline__ void end_tile(const Params&, const CoreParams&, int, int, int) {}
-
-  __device__ static __forceinline__ void store_bf16x8(bf16* dst, const float* x) {
-    uint4 u;
-    u.x = pack_bf16(x[0], x[1]); u.y = pack_bf16(x[2], x[3]); u.z = pack_bf16(x[4], x[5]); u.w = pack_bf16(x[6], x[7]);
-    *reinterpret_cast<uint4*>(dst) = u;
-  }
   __device__ static __forceinline__ void load_bf16x8(const bf16* src, float* x) {
     const uint4 u = *reinterpret_cast<const uint4*>(src);
     float2 f;
@@ -181,72 +190,36 @@ struct EpiLinear {
     f = unpack_bf16(u.w); x[6] = f.x; x[7] = f.y;
   }
 
-  __device__ static __forceinline__ void apply(const Params& ep, const CoreParams& p, int row, int col, int split,
-                                               const float (&v)[16]) {
-    if (row >= p.M || col >= p.N) return;
-    const int ngroups = (p.N - col) >= 16 ? 2 : 1;     // N % 8 == 0 is required by the launcher
-    float x[16];
+  // v: 16 consecutive accumulator columns of one output row -> o (and o2 = pre-activation in GELU mode).
+  // Rows >= M / columns >= N are computed on zeros and clipped by the TMA store.
+  __device__ static __forceinline__ void compute(const Params& ep, const CoreParams& p, int row, int col, int /*split*/,
+                                                 const float (&v)[16], float (&o)[16], float (&o2)[16]) {
+    const bool live = row < p.M && col < p.N;
+    const int ngroups = !live ? 0 : ((p.N - col) >= 16 ? 2 : 1);     // N % 8 == 0 is required by the launcher
 #pragma unroll
-    for (int i = 0; i < 16; ++i) x[i] = v[i];
+    for (int i = 0; i < 16; ++i) o[i] = v[i];
     if (ep.bias != nullptr) {
 #pragma unroll
-      for (int g = 0; g < 2; ++g) {
+      for (int g = 0; g < 2; ++g)
         if (g < ngroups) {
           const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + col + g * 8));
           const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + col + g * 8 + 4));
-          x[g * 8 + 0] += b0.x; x[g * 8 + 1] += b0.y; x[g * 8 + 2] += b0.z; x[g * 8 + 3] += b0.w;
-          x[g * 8 + 4] += b1.x; x[g * 8 + 5] += b1.y; x[g * 8 + 6] += b1.z; x[g * 8 + 7] += b1.w;
+          o[g * 8 + 0] += b0.x; o[g * 8 + 1] += b0.y; o[g * 8 + 2] += b0.z; o[g * 8 + 3] += b0.w;
+          o[g * 8 + 4] += b1.x; o[g * 8 + 5] += b1.y; o[g * 8 + 6] += b1.z; o[g * 8 + 7] += b1.w;
         }
-      }
-    }
-    if (ep.mode == B200_EPI_PARTIAL) {
-      float* dst = reinterpret_cast<float*>(ep.out) + split * ep.split_stride + 1LL * row * ep.ldo + col;
-#pragma unroll
-      for (int g = 0; g < 2; ++g)
-        if (g < ngroups) {
-          *reinterpret_cast<float4*>(dst + g * 8) = make_float4(x[g * 8], x[g * 8 + 1], x[g * 8 + 2], x[g * 8 + 3]);
-          *reinterpret_cast<float4*>(dst + g * 8 + 4) = make_float4(x[g * 8 + 4], x[g * 8 + 5], x[g * 8 + 6], x[g * 8 + 7]);
-        }
-      return;
     }
     if (ep.mode == B200_EPI_GELU) {
 #pragma unroll
-      for (int g = 0; g < 2; ++g)
-        if (g < ngroups && ep.out2 != nullptr) store_bf16x8(ep.out2 + 1LL * row * ep.ldo2 + col + g * 8, x + g * 8);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) x[i] = gelu_erf(x[i]);
-    } else if (ep.mode == B200_EPI_RESID) {
+      for (int i = 0; i < 16; ++i) { o2[i] = o[i]; o[i] = gelu_erf(o[i]); }
+    } else if (ep.mode == B200_EPI_RESID || ep.mode == B200_EPI_DGELU) {
 #pragma unroll
       for (int g = 0; g < 2; ++g)
         if (g < ngroups) {
           float r[8];
           load_bf16x8(ep.aux + 1LL * row * ep.ldaux + col + g * 8, r);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) x[g * 8 + i] += r[i];
+          for (int i = 0; i < 8; ++i) o[g * 8 + i] = ep.mode == B200_EPI_RESID ? o[g * 8 + i] + r[i] : o[g * 8 + i] * gelu_erf_grad(r[i]);
         }
-    } else if (ep.mode == B200_EPI_DGELU) {
-#pragma unroll
-      for (int g = 0; g < 2; ++g)
-        if (g < ngroups) {
-          float r[8];
-          load_bf16x8(ep.aux + 1LL * row * ep.ldaux + col + g * 8, r);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) x[g * 8 + i] *= gelu_erf_grad(r[i]);
-        }
-    }
-    if (ep.out_fp32) {
-      float* dst = reinterpret_cast<float*>(ep.out) + 1LL * row * ep.ldo + col;
-#pragma unroll
-      for (int g = 0; g < 2; ++g)
-        if (g < ngroups) {
-          *reinterpret_cast<float4*>(dst + g * 8) = make_float4(x[g * 8], x[g * 8 + 1], x[g * 8 + 2], x[g * 8 + 3]);
-          *reinterpret_cast<float4*>(dst + g * 8 + 4) = make_float4(x[g * 8 + 4], x[g * 8 + 5], x[g * 8 + 6], x[g * 8 + 7]);
-        }
-    } else {
-      bf16* dst = reinterpret_cast<bf16*>(ep.out) + 1LL * row * ep.ldo + col;
-#pragma unroll
-      for (int g = 0; g < 2; ++g)
-        if (g < ngroups) store_bf16x8(dst + g * 8, x + g * 8);
     }
   }
 };
@@ -257,20 +230,16 @@ struct EpiLinear {
 // ---------------------------------------------------------------------------------------------
 struct EpiMargin {
   struct Params {
-    float* logits; long long ldo;        // [B, C] fp32
     float* cos_label;                     // [B] cos(theta) at the label column (for backward)
     const long long* label;               // [B] int64
     float s, cos_m, sin_m, th, mm, m;
     int kind;                             // 0 = ArcFace, 1 = CosFace (AddMarginProduct)
     int easy_margin;
   };
-  __device__ static __forceinline__ void begin_tile(const Params&, const CoreParams&, int, int, int) {}
-  __device__ static __forceinline__ void end_tile(const Params&, const CoreParams&, int, int, int) {}
-  __device__ static __forceinline__ void apply(const Params& ep, const CoreParams& p, int row, int col, int,
-                                               const float (&v)[16]) {
-    if (row >= p.M || col >= p.N) return;
-    const int lab = static_cast<int>(ep.label[row]);
-    float x[16];
+  __device__ static __forceinline__ void compute(const Params& ep, const CoreParams& p, int row, int col, int, const float (&v)[16],
+                                                 float (&o)[16], float (&)[16]) {
+    const bool live = row < p.M && col < p.N;
+    const int lab = live ? static_cast<int>(ep.label[row]) : -1;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       float c = v[i];
@@ -285,17 +254,7 @@ struct EpiMargin {
           c = ep.easy_margin ? (c > 0.0f ? phi : c) : (c > ep.th ? phi : c - ep.mm);
         }
       }
-      x[i] = c * ep.s;
-    }
-    float* dst = ep.logits + 1LL * row * ep.ldo + col;
-    const int n = min(16, p.N - col);
-    if (n == 16 && (ep.ldo & 3) == 0) {
-#pragma unroll
-      for (int g = 0; g < 4; ++g) *reinterpret_cast<float4*>(dst + 4 * g) = make_float4(x[4 * g], x[4 * g + 1], x[4 * g + 2], x[4 * g + 3]);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 16; ++i)
-        if (i < n) dst[i] = x[i];
+      o[i] = c * ep.s;
     }
   }
 };
@@ -365,14 +324,14 @@ extern "C" int b200_gemm_tn(const void* a, long long lda, const void* b, long lo
                             const void* aux, long long ldaux, int splits, long long split_stride, int block_n, void* stream) {
   B200_REQUIRE(N % 8 == 0, "gemm_tn: N must be a multiple of 8 (got %d)", N);
   B200_REQUIRE(mode >= B200_EPI_STORE && mode <= B200_EPI_PARTIAL, "gemm_tn: bad epilogue mode %d", mode);
-  B200_REQUIRE(ldo % (out_fp32 || mode == B200_EPI_PARTIAL ? 4 : 8) == 0, "gemm_tn: ldo alignment");
-  if (mode == B200_EPI_GELU && out2 != nullptr) B200_REQUIRE(ldo2 % 8 == 0, "gemm_tn: ldo2 alignment");
   if (mode == B200_EPI_RESID || mode == B200_EPI_DGELU) B200_REQUIRE(aux != nullptr && ldaux % 8 == 0, "gemm_tn: mode needs aux");
   if (mode != B200_EPI_PARTIAL) B200_REQUIRE(splits <= 1, "gemm_tn: split-K only with the PARTIAL epilogue");
+  if (mode != B200_EPI_GELU) out2 = nullptr;
+  const int eb = (out_fp32 || mode == B200_EPI_PARTIAL) ? 4 : 2;
   gemm::Operands o{a, (int)lda, b, (int)ldb, M, N, K, is_bf16 != 0, block_n, splits, 0};
-  gemm::EpiLinear::Params ep{mode, out, ldo, out_fp32, reinterpret_cast<bf16*>(out2), ldo2, bias,
-                             reinterpret_cast<const bf16*>(aux), ldaux, split_stride};
-  return gemm::launch<gemm::EpiLinear>(o, ep, reinterpret_cast<cudaStream_t>(stream));
+  gemm::Output od{out, ldo, eb, out2, ldo2, mode == B200_EPI_PARTIAL ? split_stride : 0};
+  gemm::EpiLinear::Params ep{mode, bias, reinterpret_cast<const bf16*>(aux), ldaux};
+  return gemm::launch<gemm::EpiLinear>(o, od, ep, reinterpret_cast<cudaStream_t>(stream));
 }
 
 // dW[N,K] (fp32 split partials) = dY[tokens,N]^T * X[tokens,K]: both operands are read in place, MN-major - no transposes.
@@ -380,8 +339,9 @@ extern "C" int b200_gemm_wgrad(const void* dy, long long ldy, const void* x, lon
                                float* partial, int splits, int block_n, void* stream) {
   B200_REQUIRE(K % 8 == 0 && N > 0 && tokens > 0 && tokens < (1LL << 31), "gemm_wgrad: bad shape tokens=%lld N=%d K=%d", tokens, N, K);
   gemm::Operands o{dy, (int)ldy, x, (int)ldx, N, K, static_cast<int>(tokens), true, block_n, splits, 0, true};
-  gemm::EpiLinear::Params ep{B200_EPI_PARTIAL, partial, K, 1, nullptr, 0, nullptr, nullptr, 0, 1LL * N * K};
-  return gemm::launch<gemm::EpiLinear>(o, ep, reinterpret_cast<cudaStream_t>(stream));
+  gemm::Output od{partial, K, 4, nullptr, 0, 1LL * N * K};
+  gemm::EpiLinear::Params ep{B200_EPI_PARTIAL, nullptr, nullptr, 0};
+  return gemm::launch<gemm::EpiLinear>(o, od, ep, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int b200_gemm_splits(int K, int splits) { return gemm::effective_splits(K, splits); }
@@ -396,7 +356,9 @@ extern "C" int b200_margin_logits(const void* emb_unit, const void* w_unit, int 
   B200_REQUIRE(E % 8 == 0, "margin_logits: embedding size must be a multiple of 8");
   gemm::Operands o{emb_unit, E, w_unit, E, B, C, E, true, 0, 1, 0};
   const double md = static_cast<double>(m), pi = 3.14159265358979323846;   // constants as in large_margin.py:64-67
-  gemm::EpiMargin::Params ep{logits, ldo, cos_label, label, s, (float)cos(md), (float)sin(md), (float)cos(pi - md),
+  B200_REQUIRE(ldo % 4 == 0, "margin_logits: logits pitch must be a multiple of 4");
+  gemm::Output od{logits, ldo, 4, nullptr, 0, 0};
+  gemm::EpiMargin::Params ep{cos_label, label, s, (float)cos(md), (float)sin(md), (float)cos(pi - md),
                              (float)(sin(pi - md) * md), m, kind, easy_margin};
-  return gemm::launch<gemm::EpiMargin>(o, ep, reinterpret_cast<cudaStream_t>(stream));
+  return gemm::launch<gemm::EpiMargin>(o, od, ep, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -1,9 +1,12 @@
 // tcgen05 GEMM core for sm_100a:  D[M,N] = A[M,K] * B[N,K]^T  (both operands K-major, 16-bit),
 // fp32 accumulation in TMEM, pluggable epilogue.
 //
-//   warp 0      TMA producer   : cp.async.bulk.tensor (SWIZZLE_128B boxes of 64 K-elements) -> 4-stage smem ring
+//   warp 0      TMA producer   : cp.async.bulk.tensor (SWIZZLE_128B boxes of 64 K-elements) -> 3-stage smem ring
 //   warp 1      MMA issuer     : one thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=block_n, K=16)
-//   warps 2..5  epilogue       : tcgen05.ld (32 lanes x 32 columns per warp) -> registers -> Epi::apply -> global
+//   warps 2..9  epilogue       : two warps per TMEM lane quarter, each taking a share of the tile's column boxes:
+//                                tcgen05.ld -> registers -> Epi::compute (bias / GELU / residual / ...) -> swizzled
+//                                smem box (32 rows x <=128 B) -> TMA bulk tensor STORE (coalesced, asynchronous,
+//                                clipped at the matrix edge), double-buffered per warp
 //
 // Persistent: grid = min(#tiles, #SMs); every role walks the same static tile sequence
 // (tile = blockIdx.x + i * gridDim.x; n fastest so the n-tiles of one A row-block run in the same wave
@@ -20,14 +23,17 @@ namespace gemm {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                       // 64 x 2 B = one 128-B swizzle row
-constexpr int kStages = 4;
+constexpr int kStages = 3;
 constexpr int kMaxBlockN = 256;
 constexpr int kABytes = kBlockM * kBlockK * 2;    // 16 KB
 constexpr int kBBytes = kMaxBlockN * kBlockK * 2; // 32 KB (upper bound; block_n rows are filled)
 constexpr int kStageBytes = kABytes + kBBytes;    // 48 KB
 constexpr int kTmemCols = 512;                    // 2 accumulator stages x 256 fp32 columns
-constexpr int kThreads = 192;
-constexpr int kSmemBytes = kStages * kStageBytes + 256 /*barriers*/ + 1024 /*alignment slack*/;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + kEpiWarps * 32;     // 320
+constexpr int kBoxBytes = 32 * 128;               // one output box: 32 rows x (at most) 128 B
+constexpr int kStagingPerWarp = 2 * kBoxBytes;    // double buffer (or the two outputs of the GELU epilogue)
+constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kStagingPerWarp + 256 /*barriers*/ + 1024 /*alignment slack*/;
 
 struct CoreParams {
   int M, N;                  // output rows (rows of A) / columns (rows of B)
@@ -39,6 +45,9 @@ struct CoreParams {
   uint32_t idesc;            // tcgen05 instruction descriptor (formats, majors, M=128, N=block_n)
   int mn_major;              // 1: operands are [K, M] / [K, N] row-major (contraction index = row): weight gradients
   int b_chunks;              // mn_major: 64-column chunks of the B tile = ceil(block_n / 64)
+  int out_bytes;             // bytes per output element (2 = bf16, 4 = fp32)
+  int box_cols;              // columns per output box (divides block_n; box row = box_cols * out_bytes in {32, 64, 128} B)
+  int n_out;                 // 1, or 2 when the epilogue also emits a second tensor (GELU pre-activation)
 };
 
 // instruction descriptor, kind::f16: [4,6) D fmt (1=f32), [7,10) A fmt, [10,13) B fmt (0=f16, 1=bf16),
@@ -58,10 +67,12 @@ inline uint32_t make_idesc(bool is_bf16, int block_n, bool mn_major = false) {
 template <class Epi>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_o2,
                const CoreParams p, const typename Epi::Params ep) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B wants 1024-B alignment
-  const uint32_t bar_base = smem_base + kStages * kStageBytes;
+  const uint32_t staging_base = smem_base + kStages * kStageBytes;
+  const uint32_t bar_base = staging_base + kEpiWarps * kStagingPerWarp;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
@@ -76,13 +87,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_o);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);   // one arrival per epilogue warp
+      mbar_init(tempty_bar(a), kEpiWarps);   // one arrival per epilogue warp
     }
     mbar_fence_init();
   }
@@ -163,7 +175,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
   } else {
-    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int ew = warp - 2;                // epilogue warp 0..7
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access (hardware rule: warp_id % 4)
+    const int nboxes = p.block_n / p.box_cols;
+    const int box_lo = (ew < 4) ? 0 : (nboxes + 1) / 2;          // the two warps of a quarter split the column boxes
+    const int box_hi = (ew < 4) ? (nboxes + 1) / 2 : nboxes;
+    const uint32_t stg = staging_base + ew * kStagingPerWarp;
+    const uint32_t row_bytes = static_cast<uint32_t>(p.box_cols * p.out_bytes);
+    const uint32_t swz_mask = (row_bytes >> 4) - 1u;             // 7 / 3 / 1 for the 128 / 64 / 32-B swizzle modes
+    int buf = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -176,27 +196,63 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       tc_fence_after();
       const int row = m_blk * kBlockM + q * 32 + lane;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * kMaxBlockN);
-      Epi::begin_tile(ep, p, row, n_blk * p.block_n, split);
-      for (int c = 0; c < p.block_n; c += 32) {
-        uint32_t r0[16], r1[16];
-        const bool two = (c + 16) < p.block_n;
-        tmem_ld16(taddr + c, r0);
-        if (two) tmem_ld16(taddr + c + 16, r1);
-        tmem_ld_wait();
-        if (!has_k) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) { r0[i] = 0u; r1[i] = 0u; }
+      for (int box = box_lo; box < box_hi; ++box) {
+        const int c_tile = box * p.box_cols;                     // first column of the box inside the tile
+        // the staging buffer about to be overwritten must have been drained by its previous bulk store
+        if (lane == 0) {
+          if (p.n_out == 2) bulk_wait_read<0>(); else bulk_wait_read<1>();
         }
-        Epi::apply(ep, p, row, n_blk * p.block_n + c, split, reinterpret_cast<const float(&)[16]>(r0));
-        if (two) Epi::apply(ep, p, row, n_blk * p.block_n + c + 16, split, reinterpret_cast<const float(&)[16]>(r1));
+        __syncwarp();
+        const uint32_t sbuf = stg + (p.n_out == 2 ? 0u : static_cast<uint32_t>(buf) * kBoxBytes);
+        for (int c = 0; c < p.box_cols; c += 16) {
+          uint32_t r[16];
+          tmem_ld16(taddr + c_tile + c, r);
+          tmem_ld_wait();
+          if (!has_k) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) r[i] = 0u;
+          }
+          float o[16], o2[16];
+          Epi::compute(ep, p, row, n_blk * p.block_n + c_tile + c, split, reinterpret_cast<const float(&)[16]>(r), o, o2);
+          const uint32_t a0 = static_cast<uint32_t>(lane) * row_bytes + static_cast<uint32_t>(c * p.out_bytes);
+          if (p.out_bytes == 2) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const uint32_t a = a0 + 16u * k;
+              const uint32_t sw = a ^ (((a >> 7) & swz_mask) << 4);
+              st_shared_v4(sbuf + sw, pack_bf16(o[8 * k], o[8 * k + 1]), pack_bf16(o[8 * k + 2], o[8 * k + 3]),
+                           pack_bf16(o[8 * k + 4], o[8 * k + 5]), pack_bf16(o[8 * k + 6], o[8 * k + 7]));
+              if (p.n_out == 2)
+                st_shared_v4(sbuf + kBoxBytes + sw, pack_bf16(o2[8 * k], o2[8 * k + 1]), pack_bf16(o2[8 * k + 2], o2[8 * k + 3]),
+                             pack_bf16(o2[8 * k + 4], o2[8 * k + 5]), pack_bf16(o2[8 * k + 6], o2[8 * k + 7]));
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t a = a0 + 16u * k;
+              const uint32_t sw = a ^ (((a >> 7) & swz_mask) << 4);
+              st_shared_v4(sbuf + sw, __float_as_uint(o[4 * k]), __float_as_uint(o[4 * k + 1]), __float_as_uint(o[4 * k + 2]),
+                           __float_as_uint(o[4 * k + 3]));
+            }
+          }
+        }
+        fence_proxy_async_smem();            // generic-proxy smem writes -> visible to the TMA (async proxy)
+        __syncwarp();
+        if (lane == 0) {
+          const int gc = n_blk * p.block_n + c_tile, gr = m_blk * kBlockM + q * 32;
+          tma_store_3d(&tmap_o, sbuf, gc, gr, split);
+          if (p.n_out == 2) tma_store_3d(&tmap_o2, sbuf + kBoxBytes, gc, gr, split);
+          bulk_commit();
+        }
+        buf ^= 1;
       }
-      Epi::end_tile(ep, p, row, n_blk * p.block_n, split);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
+    if (lane == 0) bulk_wait_all();          // smem must stay valid (and the writes must land) before the CTA exits
   }
 
   tc_fence_before();
@@ -212,6 +268,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 // ---------------------------------------------------------------------------------------------
 int encode_tmap_2d(CUtensorMap* map, bool is_bf16, const void* ptr, uint64_t inner, uint64_t outer,
                    uint64_t pitch_elems, uint32_t box_inner, uint32_t box_outer);
+// output tensor [splits][rows][cols] (elem_bytes 2 = bf16, 4 = fp32), box = [box_cols x 32 rows x 1], swizzle = box row bytes
+int encode_tmap_out(CUtensorMap* map, int elem_bytes, const void* ptr, uint64_t cols, uint64_t rows, uint64_t splits,
+                    uint64_t pitch_elems, uint64_t split_stride_elems, uint32_t box_cols);
 
 int pick_block_n(int N);
 
@@ -226,8 +285,23 @@ struct Operands {
   bool mn_major = false;      // D = A^T B with the contraction over the ROWS of both operands (weight gradients)
 };
 
+struct Output {
+  void* ptr; long long ld; int elem_bytes;          // primary output [M, N] (per split: + split_stride elements)
+  void* ptr2; long long ld2;                         // optional second bf16 output (GELU pre-activation), or nullptr
+  long long split_stride;                            // elements between split partials (0 when splits == 1)
+};
+
+inline int pick_box_cols(int block_n, int elem_bytes) {
+  const int widest = 128 / elem_bytes;               // 64 bf16 / 32 fp32 columns = one 128-B row
+  for (int w = widest; w >= 32; w >>= 1)             // prefer an even box count: the two warps of a quarter split it evenly
+    if (block_n % w == 0 && ((block_n / w) & 1) == 0) return w;
+  for (int w = widest; w >= 16; w >>= 1)
+    if (block_n % w == 0) return w;
+  return 16;
+}
+
 template <class Epi>
-int launch(const Operands& o, const typename Epi::Params& ep, cudaStream_t stream) {
+int launch(const Operands& o, const Output& out, const typename Epi::Params& ep, cudaStream_t stream) {
   B200_REQUIRE(o.M > 0 && o.N > 0 && o.K > 0, "gemm: empty problem M=%d N=%d K=%d", o.M, o.N, o.K);
   B200_REQUIRE(o.lda % 8 == 0 && o.ldb % 8 == 0, "gemm: row pitch must be a multiple of 8 elements (16 B)");
   B200_REQUIRE((reinterpret_cast<uintptr_t>(o.a) & 15) == 0 && (reinterpret_cast<uintptr_t>(o.b) & 15) == 0,
@@ -261,6 +335,23 @@ int launch(const Operands& o, const typename Epi::Params& ep, cudaStream_t strea
   }
   if (rc) return rc;
 
+  B200_REQUIRE(out.ptr != nullptr && (reinterpret_cast<uintptr_t>(out.ptr) & 15) == 0, "gemm: output must be 16-B aligned");
+  B200_REQUIRE((out.ld * out.elem_bytes) % 16 == 0 && (out.split_stride * out.elem_bytes) % 16 == 0, "gemm: output pitch must be a multiple of 16 B");
+  p.out_bytes = out.elem_bytes;
+  p.box_cols = pick_box_cols(p.block_n, out.elem_bytes);
+  p.n_out = out.ptr2 != nullptr ? 2 : 1;
+  CUtensorMap to, to2;
+  rc = encode_tmap_out(&to, out.elem_bytes, out.ptr, o.N, o.M, p.splits, out.ld, p.splits > 1 ? out.split_stride : 1LL * o.M * out.ld,
+                       p.box_cols);
+  if (rc) return rc;
+  if (out.ptr2 != nullptr) {
+    B200_REQUIRE(out.elem_bytes == 2 && (out.ld2 * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(out.ptr2) & 15) == 0, "gemm: second output must be bf16, 16-B aligned");
+    rc = encode_tmap_out(&to2, 2, out.ptr2, o.N, o.M, 1, out.ld2, 1LL * o.M * out.ld2, p.box_cols);
+    if (rc) return rc;
+  } else {
+    to2 = to;
+  }
+
   static bool attr_done = false;   // per instantiation
   if (!attr_done) {
     B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
@@ -270,7 +361,7 @@ int launch(const Operands& o, const typename Epi::Params& ep, cudaStream_t strea
   int ctas = o.max_ctas > 0 ? o.max_ctas : b200_num_sms();
   if (tiles < ctas) ctas = static_cast<int>(tiles);
   const bool prof = b200_prof_gemm_begin(stream, 2.0 * o.M * o.N * o.K);
-  gemm_tn_kernel<Epi><<<ctas, kThreads, kSmemBytes, stream>>>(ta, tb, p, ep);
+  gemm_tn_kernel<Epi><<<ctas, kThreads, kSmemBytes, stream>>>(ta, tb, to, to2, p, ep);
   if (prof) b200_prof_gemm_end(stream);
   B200_LAUNCH_CHECK();
   return B200_OK;

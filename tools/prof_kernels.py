@@ -1,0 +1,69 @@
+"""Drive single kernels at the bench's stage shapes (batch 256) for ncu captures.
+
+    ncu --set full --clock-control none --import-source on -k regex:<kernel> -c 1 -o gpurun_out/<name> python tools/prof_kernels.py <what>
+
+what: attn_bwd | attn_fwd | gemm_fc1 | gemm_qkv | gemm_fc2 | gemm_wgrad | ln | gallery
+Each op runs 3 times (the first launches warm the caches / instruction memory); capture with -s to skip warm-ups.
+"""
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path[:0] = [str(ROOT), str(ROOT / 'pets-face-recognition_b200')]
+
+import torch  # noqa: E402
+
+from b200 import abi, ops  # noqa: E402
+
+bf16 = torch.bfloat16
+
+
+def main(what, stage=0, B=256):
+    abi.require_device()
+    C = 96 << stage
+    H = 56 >> stage
+    M = B * H * H
+    heads = C // 32
+    g = torch.Generator(device='cuda').manual_seed(0)
+    rnd = lambda *s: (torch.randn(*s, device='cuda', generator=g) * 0.5).to(bf16)
+    if what in ('attn_fwd', 'attn_bwd'):
+        qkv, pos = rnd(M, 3 * C), torch.randn(13, 13, device='cuda')
+        for _ in range(3):
+            out, lse = ops.window_attn_fwd(qkv, pos, B, H, H, C, heads, 1)
+        if what == 'attn_bwd':
+            dout = rnd(M, C)
+            for _ in range(3):
+                ops.window_attn_bwd(qkv, pos, out, lse, dout, B, H, H, C, heads, 1)
+    elif what == 'gemm_fc1':
+        x, w, b = rnd(M, C), rnd(4 * C, C), torch.randn(4 * C, device='cuda')
+        for _ in range(3):
+            ops.gemm_tn(x, w, bias=b, mode=abi.EPI_GELU, want_pre=True)
+    elif what == 'gemm_qkv':
+        x, w = rnd(M, C), rnd(3 * C, C)
+        for _ in range(3):
+            ops.gemm_tn(x, w)
+    elif what == 'gemm_fc2':
+        x, w, b, r = rnd(M, 4 * C), rnd(C, 4 * C), torch.randn(C, device='cuda'), rnd(M, C)
+        for _ in range(3):
+            ops.gemm_tn(x, w, bias=b, mode=abi.EPI_RESID, aux=r)
+    elif what == 'gemm_wgrad':
+        dy, x = rnd(M, 4 * C), rnd(M, C)
+        for _ in range(3):
+            ops.splitk_reduce(ops.gemm_wgrad(dy, x, splits=49))
+    elif what == 'ln':
+        x, gm, bt = rnd(M, C), torch.ones(C, device='cuda'), torch.zeros(C, device='cuda')
+        for _ in range(3):
+            y, mean, rstd = ops.layernorm_fwd(x, gm, bt)
+            ops.layernorm_bwd(y, x, gm, mean, rstd, dres=y)
+    elif what == 'gallery':
+        from b200 import gallery
+        q = torch.randn(8192, 512, device='cuda', generator=g)
+        gal = torch.randn(262144, 512, device='cuda', generator=g)
+        for _ in range(2):
+            gallery.cosine_topk(q, gal, 100)
+    torch.cuda.synchronize()
+    print('done', what)
+
+
+if __name__ == '__main__':
+    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 0)
