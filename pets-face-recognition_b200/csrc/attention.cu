@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(kWarps * 32) window_attn_bwd_kernel(const Attn
   for (int i = threadIdx.x; i < kBins; i += blockDim.x) bins[i] = 0.f;
   for (int i = lane; i < kBwdWarpBytes / 16; i += 32) reinterpret_cast<uint4*>(my)[i] = make_uint4(0, 0, 0, 0);
 #pragma unroll 4
-  for (int sl = 0; sl < kSlots; ++sl) slots[sl * 32] = 0.f;
+  for (int sl = 0; sl < kSlots; ++sl) __stcg(slots + sl * 32, 0.f);
   __syncthreads();
 
   const long long ntasks = 1LL * a.B * (a.H / kWs) * (a.W / kWs) * a.heads;
@@ -432,6 +432,12 @@ __global__ void __launch_bounds__(kWarps * 32) window_attn_bwd_kernel(const Attn
       float s[8][4], dp[8][4];
 #pragma unroll
       for (int n = 0; n < 8; ++n) { s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f; dp[n][0] = dp[n][1] = dp[n][2] = dp[n][3] = 0.f; }
+      float* sl = slots + mt * (7 * 4 * 32);
+      // the running per-lane dS sums live in an L2-resident scratch: fetch them now so that the round trip overlaps
+      // the 64 MMAs below; add and write back once the scores are known
+      float sv[28];
+#pragma unroll
+      for (int i = 0; i < 28; ++i) sv[i] = __ldcg(sl + i * 32);
 #pragma unroll
       for (int kk = 0; kk < 2; ++kk) {
         uint32_t q0, q1, q2, q3, d0, d1, d2, d3;
@@ -454,7 +460,6 @@ __global__ void __launch_bounds__(kWarps * 32) window_attn_bwd_kernel(const Attn
       const float* b0p = bias_s + i0 * kBiasPitch + tq * 2;
       const float* b1p = bias_s + i1 * kBiasPitch + tq * 2;
       const float l0 = lse_s[i0], l1 = lse_s[i1], D0 = dsum_s[i0], D1 = dsum_s[i1];
-      float* sl = slots + mt * (7 * 4 * 32);
       uint32_t df[8][2];
 #pragma unroll
       for (int n = 0; n < 8; ++n) {
@@ -475,7 +480,7 @@ __global__ void __launch_bounds__(kWarps * 32) window_attn_bwd_kernel(const Attn
         ds[2] = exp2f(sc[2] - l1) * (dp[n][2] - D1); ds[3] = exp2f(sc[3] - l1) * (dp[n][3] - D1);
         if (n < 7) {     // keys 56..63 are padding; per-lane private accumulators, no atomics
 #pragma unroll
-          for (int e = 0; e < 4; ++e) sl[(n * 4 + e) * 32] += ds[e];
+          for (int e = 0; e < 4; ++e) __stcg(sl + (n * 4 + e) * 32, sv[n * 4 + e] + ds[e]);
         }
         df[n][0] = pack_bf16(ds[0] * a.scale, ds[1] * a.scale);
         df[n][1] = pack_bf16(ds[2] * a.scale, ds[3] * a.scale);
@@ -518,7 +523,7 @@ __global__ void __launch_bounds__(kWarps * 32) window_attn_bwd_kernel(const Attn
     const int i = mt * 16 + g + ((e & 2) ? 8 : 0), j = n * 8 + tq * 2 + (e & 1);
     if (i < kWt && j < kWt) {
       const int ri = i / kWs, ci = i - ri * kWs, rj = j / kWs, cj = j - rj * kWs;
-      atomicAdd(&bins[(rj - ri + kWs - 1) * (2 * kWs - 1) + (cj - ci + kWs - 1)], slots[sl * 32]);
+      atomicAdd(&bins[(rj - ri + kWs - 1) * (2 * kWs - 1) + (cj - ci + kWs - 1)], __ldcg(slots + sl * 32));
     }
   }
   __syncthreads();

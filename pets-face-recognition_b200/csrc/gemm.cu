@@ -157,13 +157,17 @@ int encode_tmap_out(CUtensorMap* map, int elem_bytes, const void* ptr, uint64_t 
   return B200_OK;
 }
 
-// Tile width: N itself (rounded to 16) when it fits one tile, otherwise the width in [128,256] that
-// wastes the fewest padded columns (ties -> wider).  96->96, 288->144, 384->192, 768->256, 1152->192.
+// Tile width.  Output boxes are 32 rows x {16, 32, 64} bf16 columns and small boxes cost TMA issue slots, so widths that
+// are multiples of 64 (then 32) are preferred: the largest such divisor of N in [64, 256], else the width in [128, 256]
+// with the fewest padded columns.  96->96, 288->96, 384->192, 576->192, 768->256, 1152->192, 10000->224.
 int pick_block_n(int N) {
   if (N <= kMaxBlockN) return (N + 15) / 16 * 16;
+  for (int step : {64, 32})
+    for (int d = kMaxBlockN; d >= 64; d -= step)
+      if (d % step == 0 && N % d == 0) return d;
   int best = kMaxBlockN;
   long long best_pad = -1;
-  for (int d = kMaxBlockN; d >= 128; d -= 16) {
+  for (int d = kMaxBlockN; d >= 128; d -= 32) {
     long long pad = 1LL * ((N + d - 1) / d) * d - N;
     if (best_pad < 0 || pad < best_pad) { best_pad = pad; best = d; }
   }
@@ -178,22 +182,13 @@ struct EpiLinear {
   struct Params {
     int mode;                            // B200_EPI_*
     const float* bias;                   // [N] or null
-    const bf16* aux; long long ldaux;   // RESID: residual input; DGELU: saved pre-activation
   };
 
-  __device__ static __forceinline__ void load_bf16x8(const bf16* src, float* x) {
-    const uint4 u = *reinterpret_cast<const uint4*>(src);
-    float2 f;
-    f = unpack_bf16(u.x); x[0] = f.x; x[1] = f.y;
-    f = unpack_bf16(u.y); x[2] = f.x; x[3] = f.y;
-    f = unpack_bf16(u.z); x[4] = f.x; x[5] = f.y;
-    f = unpack_bf16(u.w); x[6] = f.x; x[7] = f.y;
-  }
-
-  // v: 16 consecutive accumulator columns of one output row -> o (and o2 = pre-activation in GELU mode).
-  // Rows >= M / columns >= N are computed on zeros and clipped by the TMA store.
+  // v: 16 consecutive accumulator columns of one output row; ax: the matching 16 values of the aux input (RESID: residual,
+  // DGELU: saved pre-activation) -> o (and o2 = pre-activation in GELU mode).  Rows >= M / columns >= N are computed on
+  // zero-filled inputs and clipped by the TMA store.
   __device__ static __forceinline__ void compute(const Params& ep, const CoreParams& p, int row, int col, int /*split*/,
-                                                 const float (&v)[16], float (&o)[16], float (&o2)[16]) {
+                                                 const float (&v)[16], const float (&ax)[16], float (&o)[16], float (&o2)[16]) {
     const bool live = row < p.M && col < p.N;
     const int ngroups = !live ? 0 : ((p.N - col) >= 16 ? 2 : 1);     // N % 8 == 0 is required by the launcher
 #pragma unroll
@@ -211,15 +206,12 @@ struct EpiLinear {
     if (ep.mode == B200_EPI_GELU) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) { o2[i] = o[i]; o[i] = gelu_erf(o[i]); }
-    } else if (ep.mode == B200_EPI_RESID || ep.mode == B200_EPI_DGELU) {
+    } else if (ep.mode == B200_EPI_RESID) {
 #pragma unroll
-      for (int g = 0; g < 2; ++g)
-        if (g < ngroups) {
-          float r[8];
-          load_bf16x8(ep.aux + 1LL * row * ep.ldaux + col + g * 8, r);
+      for (int i = 0; i < 16; ++i) o[i] += ax[i];
+    } else if (ep.mode == B200_EPI_DGELU) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) o[g * 8 + i] = ep.mode == B200_EPI_RESID ? o[g * 8 + i] + r[i] : o[g * 8 + i] * gelu_erf_grad(r[i]);
-        }
+      for (int i = 0; i < 16; ++i) o[i] *= gelu_erf_grad(ax[i]);
     }
   }
 };
@@ -237,7 +229,7 @@ struct EpiMargin {
     int easy_margin;
   };
   __device__ static __forceinline__ void compute(const Params& ep, const CoreParams& p, int row, int col, int, const float (&v)[16],
-                                                 float (&o)[16], float (&)[16]) {
+                                                 const float (&)[16], float (&o)[16], float (&)[16]) {
     const bool live = row < p.M && col < p.N;
     const int lab = live ? static_cast<int>(ep.label[row]) : -1;
 #pragma unroll
@@ -329,8 +321,10 @@ extern "C" int b200_gemm_tn(const void* a, long long lda, const void* b, long lo
   if (mode != B200_EPI_GELU) out2 = nullptr;
   const int eb = (out_fp32 || mode == B200_EPI_PARTIAL) ? 4 : 2;
   gemm::Operands o{a, (int)lda, b, (int)ldb, M, N, K, is_bf16 != 0, block_n, splits, 0};
-  gemm::Output od{out, ldo, eb, out2, ldo2, mode == B200_EPI_PARTIAL ? split_stride : 0};
-  gemm::EpiLinear::Params ep{mode, bias, reinterpret_cast<const bf16*>(aux), ldaux};
+  const bool use_aux = mode == B200_EPI_RESID || mode == B200_EPI_DGELU;
+  B200_REQUIRE(!(use_aux && eb != 2), "gemm_tn: RESID / DGELU epilogues write bf16");
+  gemm::Output od{out, ldo, eb, out2, ldo2, mode == B200_EPI_PARTIAL ? split_stride : 0, use_aux ? aux : nullptr, use_aux ? ldaux : 0};
+  gemm::EpiLinear::Params ep{mode, bias};
   return gemm::launch<gemm::EpiLinear>(o, od, ep, reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -339,8 +333,8 @@ extern "C" int b200_gemm_wgrad(const void* dy, long long ldy, const void* x, lon
                                float* partial, int splits, int block_n, void* stream) {
   B200_REQUIRE(K % 8 == 0 && N > 0 && tokens > 0 && tokens < (1LL << 31), "gemm_wgrad: bad shape tokens=%lld N=%d K=%d", tokens, N, K);
   gemm::Operands o{dy, (int)ldy, x, (int)ldx, N, K, static_cast<int>(tokens), true, block_n, splits, 0, true};
-  gemm::Output od{partial, K, 4, nullptr, 0, 1LL * N * K};
-  gemm::EpiLinear::Params ep{B200_EPI_PARTIAL, nullptr, nullptr, 0};
+  gemm::Output od{partial, K, 4, nullptr, 0, 1LL * N * K, nullptr, 0};
+  gemm::EpiLinear::Params ep{B200_EPI_PARTIAL, nullptr};
   return gemm::launch<gemm::EpiLinear>(o, od, ep, reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -357,7 +351,7 @@ extern "C" int b200_margin_logits(const void* emb_unit, const void* w_unit, int 
   gemm::Operands o{emb_unit, E, w_unit, E, B, C, E, true, 0, 1, 0};
   const double md = static_cast<double>(m), pi = 3.14159265358979323846;   // constants as in large_margin.py:64-67
   B200_REQUIRE(ldo % 4 == 0, "margin_logits: logits pitch must be a multiple of 4");
-  gemm::Output od{logits, ldo, 4, nullptr, 0, 0};
+  gemm::Output od{logits, ldo, 4, nullptr, 0, 0, nullptr, 0};
   gemm::EpiMargin::Params ep{cos_label, label, s, (float)cos(md), (float)sin(md), (float)cos(pi - md),
                              (float)(sin(pi - md) * md), m, kind, easy_margin};
   return gemm::launch<gemm::EpiMargin>(o, od, ep, reinterpret_cast<cudaStream_t>(stream));

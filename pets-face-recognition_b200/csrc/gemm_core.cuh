@@ -1,12 +1,14 @@
-// tcgen05 GEMM core for sm_100a:  D[M,N] = A[M,K] * B[N,K]^T  (both operands K-major, 16-bit),
-// fp32 accumulation in TMEM, pluggable epilogue.
+// tcgen05 GEMM core for sm_100a:  D[M,N] = A[M,K] * B[N,K]^T  (16-bit operands, fp32 accumulation in TMEM),
+// pluggable epilogue.
 //
-//   warp 0      TMA producer   : cp.async.bulk.tensor (SWIZZLE_128B boxes of 64 K-elements) -> 3-stage smem ring
+//   warp 0      TMA producer   : cp.async.bulk.tensor (SWIZZLE_128B boxes of 64 K-elements) -> smem ring (3-8 stages,
+//                                sized at run time from block_n)
 //   warp 1      MMA issuer     : one thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=block_n, K=16)
 //   warps 2..9  epilogue       : two warps per TMEM lane quarter, each taking a share of the tile's column boxes:
-//                                tcgen05.ld -> registers -> Epi::compute (bias / GELU / residual / ...) -> swizzled
-//                                smem box (32 rows x <=128 B) -> TMA bulk tensor STORE (coalesced, asynchronous,
-//                                clipped at the matrix edge), double-buffered per warp
+//                                [TMA-prefetched aux box (residual / saved pre-activation) ->] tcgen05.ld -> registers ->
+//                                Epi::compute (bias / GELU / residual / GELU' / margin ...) -> swizzled smem box
+//                                (32 rows x <=128 B) -> TMA bulk tensor STORE (coalesced, asynchronous, clipped at the
+//                                matrix edge); two boxes per warp, so loads / math / stores of consecutive boxes overlap
 //
 // Persistent: grid = min(#tiles, #SMs); every role walks the same static tile sequence
 // (tile = blockIdx.x + i * gridDim.x; n fastest so the n-tiles of one A row-block run in the same wave
@@ -23,17 +25,17 @@ namespace gemm {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                       // 64 x 2 B = one 128-B swizzle row
-constexpr int kStages = 3;
+constexpr int kMaxStages = 8;
 constexpr int kMaxBlockN = 256;
 constexpr int kABytes = kBlockM * kBlockK * 2;    // 16 KB
-constexpr int kBBytes = kMaxBlockN * kBlockK * 2; // 32 KB (upper bound; block_n rows are filled)
-constexpr int kStageBytes = kABytes + kBBytes;    // 48 KB
+constexpr int kPipeBytes = 3 * (kABytes + kMaxBlockN * kBlockK * 2);   // 144 KB operand ring: 3 stages at block_n = 256, more below
 constexpr int kTmemCols = 512;                    // 2 accumulator stages x 256 fp32 columns
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 64 + kEpiWarps * 32;     // 320
 constexpr int kBoxBytes = 32 * 128;               // one output box: 32 rows x (at most) 128 B
 constexpr int kStagingPerWarp = 2 * kBoxBytes;    // double buffer (or the two outputs of the GELU epilogue)
-constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kStagingPerWarp + 256 /*barriers*/ + 1024 /*alignment slack*/;
+constexpr int kBarBytes = 512;
+constexpr int kSmemBytes = kPipeBytes + kEpiWarps * kStagingPerWarp + kBarBytes + 1024 /*alignment slack*/;
 
 struct CoreParams {
   int M, N;                  // output rows (rows of A) / columns (rows of B)
@@ -45,6 +47,9 @@ struct CoreParams {
   uint32_t idesc;            // tcgen05 instruction descriptor (formats, majors, M=128, N=block_n)
   int mn_major;              // 1: operands are [K, M] / [K, N] row-major (contraction index = row): weight gradients
   int b_chunks;              // mn_major: 64-column chunks of the B tile = ceil(block_n / 64)
+  int stages;                // operand ring depth
+  int stage_bytes;           // 16 KB (A) + B tile, 1024-aligned
+  int has_aux;               // epilogue consumes a bf16 [M, N] side input, streamed by TMA into the staging boxes
   int out_bytes;             // bytes per output element (2 = bf16, 4 = fp32)
   int box_cols;              // columns per output box (divides block_n; box row = box_cols * out_bytes in {32, 64, 128} B)
   int n_out;                 // 1, or 2 when the epilogue also emits a second tensor (GELU pre-activation)
@@ -64,20 +69,24 @@ inline uint32_t make_idesc(bool is_bf16, int block_n, bool mn_major = false) {
   return d;
 }
 
+__device__ __forceinline__ float bf16lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf16hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+
 template <class Epi>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_o2,
-               const CoreParams p, const typename Epi::Params ep) {
+               const __grid_constant__ CUtensorMap tmap_aux, const CoreParams p, const typename Epi::Params ep) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B wants 1024-B alignment
-  const uint32_t staging_base = smem_base + kStages * kStageBytes;
+  const uint32_t staging_base = smem_base + kPipeBytes;
   const uint32_t bar_base = staging_base + kEpiWarps * kStagingPerWarp;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kMaxStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kMaxStages + 2 + a); };
+  auto aux_bar = [&](int w, int b) { return bar_base + 8u * (2 * kMaxStages + 4 + 2 * w + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 4 + 2 * kEpiWarps);
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -88,9 +97,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     tma_prefetch_desc(&tmap_o);
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < kMaxStages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
+    }
+    for (int w = 0; w < kEpiWarps; ++w) {
+      mbar_init(aux_bar(w, 0), 1);
+      mbar_init(aux_bar(w, 1), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -127,7 +140,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
-          const uint32_t sa = smem_base + stage * kStageBytes;
+          const uint32_t sa = smem_base + stage * p.stage_bytes;
           if (!p.mn_major) {
             tma_load_2d(sa, &tmap_a, full_bar(stage), kb * kBlockK, m_blk * kBlockM);
             tma_load_2d(sa + kABytes, &tmap_b, full_bar(stage), kb * kBlockK, n_blk * p.block_n);
@@ -136,7 +149,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             for (int c = 0; c < p.b_chunks; ++c)
               tma_load_2d(sa + kABytes + c * kChunk, &tmap_b, full_bar(stage), n_blk * p.block_n + c * 64, kb * kBlockK);
           }
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -156,7 +169,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t sa = smem_base + stage * kStageBytes;
+          const uint32_t sa = smem_base + stage * p.stage_bytes;
           // K-major : SBO = 1024 B between 8-row groups; a K=16 slice is +32 B inside the 128-B swizzle row (+2 in addr>>4)
           // MN-major: LBO = 8 KB between 64-column chunks, SBO = 1024 B between 8-row (contraction) groups; a K=16 slice
           //           is 16 rows = +2048 B (+128 in addr>>4)
@@ -167,7 +180,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           for (int k = 0; k < kBlockK / 16; ++k) umma_f16(d_tmem, da + kstep * k, db + kstep * k, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           umma_commit(empty_bar(stage));                 // smem slot reusable once these MMAs retire
           if (kb == kb1 - 1) umma_commit(tfull_bar(acc)); // accumulator complete
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
         if (kb1 <= kb0) umma_commit(tfull_bar(acc));      // degenerate split: nothing to add
         acc ^= 1;
@@ -182,10 +195,22 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int box_hi = (ew < 4) ? (nboxes + 1) / 2 : nboxes;
     const uint32_t stg = staging_base + ew * kStagingPerWarp;
     const uint32_t row_bytes = static_cast<uint32_t>(p.box_cols * p.out_bytes);
+    const uint32_t box_bytes = 32u * row_bytes;
     const uint32_t swz_mask = (row_bytes >> 4) - 1u;             // 7 / 3 / 1 for the 128 / 64 / 32-B swizzle modes
+    const bool aux = p.has_aux != 0 && box_hi > box_lo;
     int buf = 0;
+    uint32_t aux_phase0 = 0, aux_phase1 = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    // stream the aux box of (tile, box) into staging buffer b (same geometry / swizzle as the output box)
+    auto issue_aux = [&](int tile, int box, int b) {
+      const int n_blk = tile % p.n_blocks;
+      const int m_blk = (tile / p.n_blocks) % p.m_blocks;
+      mbar_arrive_expect_tx(aux_bar(ew, b), box_bytes);
+      tma_load_3d(stg + static_cast<uint32_t>(b) * kBoxBytes, &tmap_aux, aux_bar(ew, b), n_blk * p.block_n + box * p.box_cols,
+                  m_blk * kBlockM + q * 32, 0);
+    };
+    if (aux && lane == 0 && static_cast<int>(blockIdx.x) < num_tiles) issue_aux(blockIdx.x, box_lo, 0);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int n_blk = tile % p.n_blocks;
       const int m_blk = (tile / p.n_blocks) % p.m_blocks;
@@ -198,23 +223,47 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * kMaxBlockN);
       for (int box = box_lo; box < box_hi; ++box) {
         const int c_tile = box * p.box_cols;                     // first column of the box inside the tile
-        // the staging buffer about to be overwritten must have been drained by its previous bulk store
         if (lane == 0) {
-          if (p.n_out == 2) bulk_wait_read<0>(); else bulk_wait_read<1>();
+          if (aux) {
+            // the OTHER buffer was last read by the store of the previous box: drain it, then stream the next aux box in
+            bulk_wait_read<0>();
+            const bool more_here = box + 1 < box_hi;
+            const int ntile = more_here ? tile : tile + static_cast<int>(gridDim.x);
+            if (ntile < num_tiles) issue_aux(ntile, more_here ? box + 1 : box_lo, buf ^ 1);
+          } else if (p.n_out == 2) {
+            bulk_wait_read<0>();               // both buffers are rewritten for every box
+          } else {
+            bulk_wait_read<1>();               // the buffer about to be rewritten was read by the store before last
+          }
         }
         __syncwarp();
         const uint32_t sbuf = stg + (p.n_out == 2 ? 0u : static_cast<uint32_t>(buf) * kBoxBytes);
+        if (aux) {
+          if (buf == 0) { mbar_wait(aux_bar(ew, 0), aux_phase0); aux_phase0 ^= 1u; }
+          else { mbar_wait(aux_bar(ew, 1), aux_phase1); aux_phase1 ^= 1u; }
+        }
         for (int c = 0; c < p.box_cols; c += 16) {
           uint32_t r[16];
           tmem_ld16(taddr + c_tile + c, r);
+          const uint32_t a0 = static_cast<uint32_t>(lane) * row_bytes + static_cast<uint32_t>(c * p.out_bytes);
+          float ax[16];
+          if (aux) {      // the bf16 side input sits exactly where the result will be written
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const uint32_t a = a0 + 16u * k;
+              uint32_t w0, w1, w2, w3;
+              ld_shared_v4(sbuf + (a ^ (((a >> 7) & swz_mask) << 4)), w0, w1, w2, w3);
+              ax[8 * k + 0] = bf16lo(w0); ax[8 * k + 1] = bf16hi(w0); ax[8 * k + 2] = bf16lo(w1); ax[8 * k + 3] = bf16hi(w1);
+              ax[8 * k + 4] = bf16lo(w2); ax[8 * k + 5] = bf16hi(w2); ax[8 * k + 6] = bf16lo(w3); ax[8 * k + 7] = bf16hi(w3);
+            }
+          }
           tmem_ld_wait();
           if (!has_k) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) r[i] = 0u;
           }
           float o[16], o2[16];
-          Epi::compute(ep, p, row, n_blk * p.block_n + c_tile + c, split, reinterpret_cast<const float(&)[16]>(r), o, o2);
-          const uint32_t a0 = static_cast<uint32_t>(lane) * row_bytes + static_cast<uint32_t>(c * p.out_bytes);
+          Epi::compute(ep, p, row, n_blk * p.block_n + c_tile + c, split, reinterpret_cast<const float(&)[16]>(r), ax, o, o2);
           if (p.out_bytes == 2) {
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
@@ -289,6 +338,7 @@ struct Output {
   void* ptr; long long ld; int elem_bytes;          // primary output [M, N] (per split: + split_stride elements)
   void* ptr2; long long ld2;                         // optional second bf16 output (GELU pre-activation), or nullptr
   long long split_stride;                            // elements between split partials (0 when splits == 1)
+  const void* aux; long long ldaux;                 // optional bf16 [M, N] epilogue input (residual / pre-activation)
 };
 
 inline int pick_box_cols(int block_n, int elem_bytes) {
@@ -321,6 +371,10 @@ int launch(const Operands& o, const Output& out, const typename Epi::Params& ep,
   p.idesc = make_idesc(o.is_bf16, p.block_n, o.mn_major);
   p.mn_major = o.mn_major ? 1 : 0;
   p.b_chunks = (p.block_n + 63) / 64;
+  const int b_bytes = o.mn_major ? p.b_chunks * 8192 : p.block_n * kBlockK * 2;
+  p.stage_bytes = (kABytes + b_bytes + 1023) / 1024 * 1024;
+  p.stages = kPipeBytes / p.stage_bytes;
+  if (p.stages > kMaxStages) p.stages = kMaxStages;
 
   CUtensorMap ta, tb;
   int rc;
@@ -340,7 +394,8 @@ int launch(const Operands& o, const Output& out, const typename Epi::Params& ep,
   p.out_bytes = out.elem_bytes;
   p.box_cols = pick_box_cols(p.block_n, out.elem_bytes);
   p.n_out = out.ptr2 != nullptr ? 2 : 1;
-  CUtensorMap to, to2;
+  p.has_aux = out.aux != nullptr ? 1 : 0;
+  CUtensorMap to, to2, tx;
   rc = encode_tmap_out(&to, out.elem_bytes, out.ptr, o.N, o.M, p.splits, out.ld, p.splits > 1 ? out.split_stride : 1LL * o.M * out.ld,
                        p.box_cols);
   if (rc) return rc;
@@ -350,6 +405,13 @@ int launch(const Operands& o, const Output& out, const typename Epi::Params& ep,
     if (rc) return rc;
   } else {
     to2 = to;
+  }
+  tx = to;
+  if (out.aux != nullptr) {
+    B200_REQUIRE(out.elem_bytes == 2 && out.ptr2 == nullptr && p.splits == 1, "gemm: an aux input needs a single bf16 output");
+    B200_REQUIRE((out.ldaux * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(out.aux) & 15) == 0, "gemm: aux must be 16-B aligned");
+    rc = encode_tmap_out(&tx, 2, out.aux, o.N, o.M, 1, out.ldaux, 1LL * o.M * out.ldaux, p.box_cols);
+    if (rc) return rc;
   }
 
   static bool attr_done = false;   // per instantiation
@@ -361,7 +423,7 @@ int launch(const Operands& o, const Output& out, const typename Epi::Params& ep,
   int ctas = o.max_ctas > 0 ? o.max_ctas : b200_num_sms();
   if (tiles < ctas) ctas = static_cast<int>(tiles);
   const bool prof = b200_prof_gemm_begin(stream, 2.0 * o.M * o.N * o.K);
-  gemm_tn_kernel<Epi><<<ctas, kThreads, kSmemBytes, stream>>>(ta, tb, to, to2, p, ep);
+  gemm_tn_kernel<Epi><<<ctas, kThreads, kSmemBytes, stream>>>(ta, tb, to, to2, tx, p, ep);
   if (prof) b200_prof_gemm_end(stream);
   B200_LAUNCH_CHECK();
   return B200_OK;
