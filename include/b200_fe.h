@@ -75,10 +75,10 @@ int b200_splitk_reduce(const float* partial, float* out, long long n, int splits
 /* ---- LayerNorm, nn.LayerNorm(C) eps 1e-5 (models/swin.py:29,215) -------------------------------------------- */
 int b200_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, long long M,
                        int C, float eps, void* stream);
-int b200_layernorm_bwd_blocks(long long M, int C); /* rows of the [blocks, 2C] fp32 partial buffer */
+int b200_layernorm_bwd_blocks(long long M, int C); /* rows of the [blocks, 3C] fp32 partial buffer */
 int b200_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
-                       const void* dres_in, void* dx_out, float* dgamma, float* dbeta, float* partial, long long M, int C,
-                       int accumulate, void* stream);
+                       const void* dres_in, void* dx_out, float* dgamma, float* dbeta, float* dres_colsum, float* partial,
+                       long long M, int C, int accumulate, void* stream);
 
 /* ---- patch merging gather == nn.Unfold(k=s=df) + NHWC view (models/swin.py:159,162-165) ---------------------- */
 int b200_patch_gather_image(const float* img_nchw, void* cols, int B, int Cin, int H, int W, int df, long long ldo, void* stream);

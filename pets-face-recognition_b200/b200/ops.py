@@ -68,15 +68,15 @@ def layernorm_fwd(x, gamma, beta, eps=1e-5):
     return y, mean, rstd
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None):
+def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None, want_dres_colsum=False):
     M, Cc = x.shape
     dx = torch.empty_like(x)
-    dgb = torch.empty(2, Cc, device=x.device, dtype=torch.float32)
+    dgb = torch.empty(3, Cc, device=x.device, dtype=torch.float32)
     blocks = lib().b200_layernorm_bwd_blocks(M, Cc)
-    partial = torch.empty(blocks, 2 * Cc, device=x.device, dtype=torch.float32)
-    check(lib().b200_layernorm_bwd(ptr(dy), ptr(x), ptr(gamma), ptr(mean), ptr(rstd), ptr(dres), ptr(dx), ptr(dgb[0]), ptr(dgb[1]), ptr(partial),
-                                   M, Cc, 0, stream_ptr()), 'layernorm_bwd')
-    return dx, dgb[0], dgb[1]
+    partial = torch.empty(blocks, 3 * Cc, device=x.device, dtype=torch.float32)
+    check(lib().b200_layernorm_bwd(ptr(dy), ptr(x), ptr(gamma), ptr(mean), ptr(rstd), ptr(dres), ptr(dx), ptr(dgb[0]), ptr(dgb[1]),
+                                   ptr(dgb[2]) if want_dres_colsum else 0, ptr(partial), M, Cc, 0, stream_ptr()), 'layernorm_bwd')
+    return (dx, dgb[0], dgb[1], dgb[2]) if want_dres_colsum else (dx, dgb[0], dgb[1])
 
 
 def patch_gather_image(img, df=4):

@@ -97,27 +97,28 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restri
 }
 
 // LayerNorm backward.  dx = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * gamma; optional
-// fused residual-gradient add (dx_out = dres_in + dx).  dgamma/dbeta: register partials per thread
-// over its rows, CTA-reduced through smem, one [2C] partial row per CTA (reduced by splitk_reduce in
-// a fixed order -> deterministic).
-template <int LPR, int MAXIT>
+// fused residual-gradient add (dx_out = dres_in + dx).  dgamma/dbeta - and, with WITH_RES, the column sums of
+// dres_in, which are the bias gradient of the Linear that produced the residual branch (fc2 / to_out) - are
+// register partials per thread over its rows, CTA-reduced through smem, one [3C] partial row per CTA
+// (reduced by splitk_reduce in a fixed order -> deterministic).
+template <int LPR, int MAXIT, bool WITH_RES>
 __global__ void __launch_bounds__(128) layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                                                             const float* __restrict__ gamma, const float* __restrict__ mean,
                                                             const float* __restrict__ rstd, const bf16* dres,
                                                             bf16* dx, float* __restrict__ partial,
                                                             long long M, int C) {
   constexpr int RPW = 32 / LPR;
-  extern __shared__ float red[];   // [warps][2][C]
+  extern __shared__ float red[];   // [warps][3][C]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane / LPR, l = lane % LPR;
   const long long warp_global = (1LL * blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = (1LL * gridDim.x * blockDim.x) >> 5;
   const int chunks = C >> 3;
-  float dg[MAXIT][8], db[MAXIT][8];
+  float dg[MAXIT][8], db[MAXIT][8], dr[WITH_RES ? MAXIT : 1][8];
 #pragma unroll
   for (int it = 0; it < MAXIT; ++it)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { dg[it][i] = 0.f; db[it][i] = 0.f; }
+    for (int i = 0; i < 8; ++i) { dg[it][i] = 0.f; db[it][i] = 0.f; if (WITH_RES) dr[it][i] = 0.f; }
 
   for (long long row0 = warp_global * RPW; row0 < M; row0 += nwarps * RPW) {
     const long long row = row0 + sub;
@@ -161,7 +162,7 @@ __global__ void __launch_bounds__(128) layernorm_bwd_kernel(const bf16* __restri
             float r[8];
             ld8(dres + row * C + ch * 8, r);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] += r[i];
+            for (int i = 0; i < 8; ++i) { o[i] += r[i]; if (WITH_RES) dr[it][i] += r[i]; }
           }
           st8(dx + row * C + ch * 8, o);
         }
@@ -177,6 +178,7 @@ __global__ void __launch_bounds__(128) layernorm_bwd_kernel(const bf16* __restri
       for (int o = 16; o >= LPR; o >>= 1) {
         dg[it][i] += __shfl_xor_sync(0xffffffffu, dg[it][i], o);
         db[it][i] += __shfl_xor_sync(0xffffffffu, db[it][i], o);
+        if (WITH_RES) dr[it][i] += __shfl_xor_sync(0xffffffffu, dr[it][i], o);
       }
     }
   const int warps = blockDim.x >> 5;
@@ -187,18 +189,19 @@ __global__ void __launch_bounds__(128) layernorm_bwd_kernel(const bf16* __restri
       if (ch < chunks) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          red[(warp * 2 + 0) * C + ch * 8 + i] = dg[it][i];
-          red[(warp * 2 + 1) * C + ch * 8 + i] = db[it][i];
+          red[(warp * 3 + 0) * C + ch * 8 + i] = dg[it][i];
+          red[(warp * 3 + 1) * C + ch * 8 + i] = db[it][i];
+          red[(warp * 3 + 2) * C + ch * 8 + i] = WITH_RES ? dr[it][i] : 0.f;
         }
       }
     }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
+  for (int c = threadIdx.x; c < 3 * C; c += blockDim.x) {
     const int which = c / C, col = c % C;
     float a = 0.f;
-    for (int w = 0; w < warps; ++w) a += red[(w * 2 + which) * C + col];
-    partial[1LL * blockIdx.x * 2 * C + c] = a;
+    for (int w = 0; w < warps; ++w) a += red[(w * 3 + which) * C + col];
+    partial[1LL * blockIdx.x * 3 * C + c] = a;
   }
 }
 
@@ -337,20 +340,39 @@ __global__ void __launch_bounds__(256) cast_transpose_kernel(const float* __rest
 }
 
 // ---------------------------------------------------------------------------------------------
-// column sums of a bf16 [M, N] matrix (bias gradients): per-CTA row slab -> partial[blk][N]
+// column sums of a bf16 [M, N] matrix (bias gradients): 256 threads = TX column lanes (16 B = 8 columns each) x
+// 256/TX row lanes; each CTA reduces a slab of rows -> partial[blk][N] (fixed order: deterministic)
 // ---------------------------------------------------------------------------------------------
+template <int TX>
 __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, float* __restrict__ partial, long long M, int N,
                                                      long long ld, long long rows_per_block) {
+  constexpr int TY = 256 / TX;
+  __shared__ float red[TY][TX * 8 + 1];
+  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+  const int col = (blockIdx.y * TX + tx) * 8;
   const long long r0 = rows_per_block * blockIdx.x;
   const long long r1 = min(M, r0 + rows_per_block);
-  for (int c2 = threadIdx.x; c2 < N / 2; c2 += blockDim.x) {
-    float a0 = 0.f, a1 = 0.f;
-    for (long long r = r0; r < r1; ++r) {
-      const float2 f = __bfloat1622float2(*reinterpret_cast<const bf162*>(x + r * ld + c2 * 2));
-      a0 += f.x; a1 += f.y;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (col < N) {
+#pragma unroll 4
+    for (long long r = r0 + ty; r < r1; r += TY) {
+      float v[8];
+      ld8(x + r * ld + col, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += v[i];
     }
-    partial[1LL * blockIdx.x * N + c2 * 2] = a0;
-    partial[1LL * blockIdx.x * N + c2 * 2 + 1] = a1;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[ty][tx * 8 + i] = acc[i];
+  __syncthreads();
+  for (int c = threadIdx.x; c < TX * 8; c += 256) {
+    const int gc = blockIdx.y * TX * 8 + c;
+    if (gc < N) {
+      float a = 0.f;
+#pragma unroll
+      for (int y = 0; y < TY; ++y) a += red[y][c];
+      partial[1LL * blockIdx.x * N + gc] = a;
+    }
   }
 }
 
@@ -439,11 +461,17 @@ int ln_fwd_launch(const bf16* x, const float* g, const float* b, bf16* y, float*
 }
 template <int LPR, int MAXIT>
 int ln_bwd_launch(const bf16* dy, const bf16* x, const float* g, const float* mean, const float* rstd, const bf16* dres, bf16* dx,
-                  float* partial, long long M, int C, int blocks, cudaStream_t st) {
-  const size_t smem = sizeof(float) * 4 * 2 * C;
-  if (smem > 48 * 1024)
-    B200_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<LPR, MAXIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  layernorm_bwd_kernel<LPR, MAXIT><<<blocks, 128, smem, st>>>(dy, x, g, mean, rstd, dres, dx, partial, M, C);
+                  float* partial, long long M, int C, int blocks, bool with_res, cudaStream_t st) {
+  const size_t smem = sizeof(float) * 4 * 3 * C;
+  if (with_res) {
+    if (smem > 48 * 1024)
+      B200_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<LPR, MAXIT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    layernorm_bwd_kernel<LPR, MAXIT, true><<<blocks, 128, smem, st>>>(dy, x, g, mean, rstd, dres, dx, partial, M, C);
+  } else {
+    if (smem > 48 * 1024)
+      B200_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<LPR, MAXIT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    layernorm_bwd_kernel<LPR, MAXIT, false><<<blocks, 128, smem, st>>>(dy, x, g, mean, rstd, dres, dx, partial, M, C);
+  }
   B200_LAUNCH_CHECK();
   return B200_OK;
 }
@@ -470,15 +498,18 @@ extern "C" int b200_layernorm_fwd(const void* x, const float* gamma, const float
 extern "C" int b200_layernorm_bwd_blocks(long long M, int C) {
   (void)C;
   long long b = (M + 63) / 64;
-  const int cap = b200_num_sms() * 4;
+  const int cap = b200_num_sms() * 8;
   if (b > cap) b = cap;
   return b < 1 ? 1 : static_cast<int>(b);
 }
 
+// partial: fp32 scratch of b200_layernorm_bwd_blocks(M, C) x 3C.  dres_colsum (optional, needs dres_in) receives the column
+// sums of dres_in: the bias gradient of the Linear whose output was added to the residual stream.
 extern "C" int b200_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
-                                  const void* dres_in, void* dx_out, float* dgamma, float* dbeta, float* partial, long long M, int C,
-                                  int accumulate, void* stream) {
+                                  const void* dres_in, void* dx_out, float* dgamma, float* dbeta, float* dres_colsum, float* partial,
+                                  long long M, int C, int accumulate, void* stream) {
   B200_REQUIRE(C % 8 == 0 && C >= 8 && C <= 1536, "layernorm_bwd: C=%d unsupported", C);
+  B200_REQUIRE(dres_colsum == nullptr || dres_in != nullptr, "layernorm_bwd: dres_colsum needs dres_in");
   if (M == 0) return B200_OK;
   auto st = reinterpret_cast<cudaStream_t>(stream);
   const int blocks = b200_layernorm_bwd_blocks(M, C);
@@ -486,16 +517,19 @@ extern "C" int b200_layernorm_bwd(const void* dy, const void* x, const float* ga
   auto X = reinterpret_cast<const bf16*>(x);
   auto DR = reinterpret_cast<const bf16*>(dres_in);
   auto DX = reinterpret_cast<bf16*>(dx_out);
+  const bool wr = dres_colsum != nullptr;
   int rc;
-  if (C <= 128) rc = ln_bwd_launch<16, 1>(DY, X, gamma, mean, rstd, DR, DX, partial, M, C, blocks, st);
-  else if (C <= 256) rc = ln_bwd_launch<32, 1>(DY, X, gamma, mean, rstd, DR, DX, partial, M, C, blocks, st);
-  else if (C <= 512) rc = ln_bwd_launch<32, 2>(DY, X, gamma, mean, rstd, DR, DX, partial, M, C, blocks, st);
-  else if (C <= 768) rc = ln_bwd_launch<32, 3>(DY, X, gamma, mean, rstd, DR, DX, partial, M, C, blocks, st);
-  else rc = ln_bwd_launch<32, 6>(DY, X, gamma, mean, rstd, DR, DX, partial, M, C, blocks, st);
+  if (C <= 128) rc = ln_bwd_launch<16, 1>(DY, X, gamma, mean, rstd, DR, DX, partial, M, C, blocks, wr, st);
+  else if (C <= 256) rc = ln_bwd_launch<32, 1>(DY, X, gamma, mean, rstd, DR, DX, partial, M, C, blocks, wr, st);
+  else if (C <= 512) rc = ln_bwd_launch<32, 2>(DY, X, gamma, mean, rstd, DR, DX, partial, M, C, blocks, wr, st);
+  else if (C <= 768) rc = ln_bwd_launch<32, 3>(DY, X, gamma, mean, rstd, DR, DX, partial, M, C, blocks, wr, st);
+  else rc = ln_bwd_launch<32, 6>(DY, X, gamma, mean, rstd, DR, DX, partial, M, C, blocks, wr, st);
   if (rc) return rc;
-  rc = splitk_reduce(partial, dgamma, C, blocks, accumulate, st, 2LL * C);
+  rc = splitk_reduce(partial, dgamma, C, blocks, accumulate, st, 3LL * C);
   if (rc) return rc;
-  return splitk_reduce(partial + C, dbeta, C, blocks, accumulate, st, 2LL * C);
+  rc = splitk_reduce(partial + C, dbeta, C, blocks, accumulate, st, 3LL * C);
+  if (rc || !wr) return rc;
+  return splitk_reduce(partial + 2 * C, dres_colsum, C, blocks, accumulate, st, 3LL * C);
 }
 
 extern "C" int b200_patch_gather_image(const float* img, void* out, int B, int Cin, int H, int W, int df, long long ldo,
@@ -566,8 +600,8 @@ extern "C" int b200_cast_f32_bf16(const float* in, void* out, long long n, void*
 }
 
 extern "C" int b200_colsum_blocks(long long M) {
-  long long b = (M + 255) / 256;
-  const int cap = b200_num_sms() * 4;
+  long long b = (M + 511) / 512;
+  const int cap = b200_num_sms() * 2;
   if (b > cap) b = cap;
   return b < 1 ? 1 : static_cast<int>(b);
 }
@@ -575,9 +609,15 @@ extern "C" int b200_colsum_blocks(long long M) {
 extern "C" int b200_colsum(const void* x, long long ld, long long M, int N, float* out, float* partial, int accumulate, void* stream) {
   B200_REQUIRE(N % 4 == 0 && ld % 2 == 0, "colsum: N %% 4, ld %% 2");
   if (M == 0) return B200_OK;
+  B200_REQUIRE(N % 8 == 0 && ld % 8 == 0, "colsum: N and ld must be multiples of 8");
   const int blocks = b200_colsum_blocks(M);
   const long long rpb = (M + blocks - 1) / blocks;
-  colsum_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const bf16*>(x), partial, M, N, ld, rpb);
+  auto st = reinterpret_cast<cudaStream_t>(stream);
+  if (N <= 128) {
+    colsum_kernel<16><<<dim3(blocks, (N + 127) / 128), 256, 0, st>>>(reinterpret_cast<const bf16*>(x), partial, M, N, ld, rpb);
+  } else {
+    colsum_kernel<32><<<dim3(blocks, (N + 255) / 256), 256, 0, st>>>(reinterpret_cast<const bf16*>(x), partial, M, N, ld, rpb);
+  }
   B200_LAUNCH_CHECK();
   return b200_splitk_reduce(partial, out, N, blocks, accumulate, stream);
 }

@@ -157,17 +157,22 @@ int encode_tmap_out(CUtensorMap* map, int elem_bytes, const void* ptr, uint64_t 
   return B200_OK;
 }
 
-// Tile width.  Output boxes are 32 rows x {16, 32, 64} bf16 columns and small boxes cost TMA issue slots, so widths that
-// are multiples of 64 (then 32) are preferred: the largest such divisor of N in [64, 256], else the width in [128, 256]
-// with the fewest padded columns.  96->96, 288->96, 384->192, 576->192, 768->256, 1152->192, 10000->224.
-int pick_block_n(int N) {
-  if (N <= kMaxBlockN) return (N + 15) / 16 * 16;
-  for (int step : {64, 32})
-    for (int d = kMaxBlockN; d >= 64; d -= step)
-      if (d % step == 0 && N % d == 0) return d;
+// Tile width.  The epilogue stores 32-row boxes whose rows are at most 128 B; 128-B rows (64 bf16 columns) are what the TMA
+// store path and L2 like, narrower rows roughly halve the achievable write bandwidth.  So widths are multiples of 64,
+// padded if necessary (fully out-of-range boxes are skipped, partially out-of-range ones clipped by the TMA).  For
+// small-K, store-bound layers an even number of boxes per tile keeps the two epilogue warps of a lane quarter balanced;
+// for large-K layers the widest tile wins (MMA efficiency, fewer re-reads of A).
+int pick_block_n(int N, int K) {
+  if (N <= 64) return (N + 15) / 16 * 16;
+  if (N <= kMaxBlockN) return (N + 63) / 64 * 64;
+  const int order_store[4] = {256, 128, 192, 64};
+  const int order_math[4] = {256, 192, 128, 64};
+  const int* order = (K <= 192) ? order_store : order_math;
+  for (int i = 0; i < 4; ++i)
+    if (N % order[i] == 0) return order[i];
   int best = kMaxBlockN;
   long long best_pad = -1;
-  for (int d = kMaxBlockN; d >= 128; d -= 32) {
+  for (int d = kMaxBlockN; d >= 128; d -= 64) {
     long long pad = 1LL * ((N + d - 1) / d) * d - N;
     if (best_pad < 0 || pad < best_pad) { best_pad = pad; best = d; }
   }

@@ -223,6 +223,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * kMaxBlockN);
       for (int box = box_lo; box < box_hi; ++box) {
         const int c_tile = box * p.box_cols;                     // first column of the box inside the tile
+        if (!aux && n_blk * p.block_n + c_tile >= p.N) continue; // padded tile: nothing of this box is inside the matrix
         if (lane == 0) {
           if (aux) {
             // the OTHER buffer was last read by the store of the previous box: drain it, then stream the next aux box in
@@ -321,7 +322,7 @@ int encode_tmap_2d(CUtensorMap* map, bool is_bf16, const void* ptr, uint64_t inn
 int encode_tmap_out(CUtensorMap* map, int elem_bytes, const void* ptr, uint64_t cols, uint64_t rows, uint64_t splits,
                     uint64_t pitch_elems, uint64_t split_stride_elems, uint32_t box_cols);
 
-int pick_block_n(int N);
+int pick_block_n(int N, int K);
 
 struct Operands {
   const void* a; int lda;     // [M, K] row-major, 16-bit           (mn_major: [K, M] row-major)
@@ -359,7 +360,7 @@ int launch(const Operands& o, const Output& out, const typename Epi::Params& ep,
   CoreParams p;
   p.M = o.M;
   p.N = o.N;
-  p.block_n = o.block_n > 0 ? o.block_n : pick_block_n(o.N);
+  p.block_n = o.block_n > 0 ? o.block_n : pick_block_n(o.N, o.K);
   B200_REQUIRE(p.block_n % 16 == 0 && p.block_n >= 16 && p.block_n <= kMaxBlockN, "gemm: bad block_n %d", p.block_n);
   p.m_blocks = (o.M + kBlockM - 1) / kBlockM;
   p.n_blocks = (o.N + p.block_n - 1) / p.block_n;

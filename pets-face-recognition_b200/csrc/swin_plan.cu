@@ -167,7 +167,7 @@ void build(Plan& p) {
     partial = 1LL * 4 * 160 * 128 * 256 * 4;
     p.partial_bytes = partial;
     p.partial = add_ws(p, partial);
-    p.red_partial = add_ws(p, 1LL * 1024 * 3072 * 4);         // LN / colsum partial rows: <= 4*SMs rows x <= 3072 cols
+    p.red_partial = add_ws(p, 1LL * 8 * 160 * 3 * 1536 * 4);  // LN (<= 8*SMs rows x 3C) / colsum (<= 2*SMs rows x 4C) partial rows
     p.dpos_partial = add_ws(p, b200_window_attn_bwd_scratch_floats(2 * 160) * 4);   // <= 2 CTAs per SM
     p.demb16 = add_ws(p, 1LL * p.B * p.num_classes * 2);
     p.dpooled = add_ws(p, 1LL * p.B * C4 * 2);
@@ -276,7 +276,7 @@ int backward(const Ctx& c, const float* demb, int stage_hi, int stage_lo) {
     RC(linear_dgrad(c, d16, p.B, p.num_classes, c.wc + p.head_w16t, L.C, B200_EPI_STORE, dpn, nullptr));
     bf16* dpool = c.W<bf16>(p.d_small);
     RC(b200_layernorm_bwd(dpn, c.W<bf16>(p.pooled), c.P(p.head_ln_w), c.W<float>(p.pool_mean), c.W<float>(p.pool_rstd), nullptr, dpool,
-                          c.G(p.head_ln_w), c.G(p.head_ln_b), c.W<float>(p.red_partial), p.B, L.C, 0, c.stv));
+                          c.G(p.head_ln_w), c.G(p.head_ln_b), nullptr, c.W<float>(p.red_partial), p.B, L.C, 0, c.stv));
     RC(b200_mean_pool(dpool, g, p.B, L.Hs * L.Hs, L.C, 1, c.stv));
     stage_hi = 3;
   }
@@ -294,22 +294,22 @@ int backward(const Ctx& c, const float* demb, int stage_hi, int stage_lo) {
       // ---- MLP: x_out = x_mid + W2 gelu(W1 LN2(x_mid) + b1) + b2
       RC(linear_dgrad(c, g, M, C, c.wc + q.w216t, 4 * C, B200_EPI_DGELU, dbig, c.W<bf16>(a.hpre)));   // d h_pre
       RC(linear_wgrad(c, g, M, C, c.W<bf16>(a.hact), 4 * C, c.G(q.w2)));
-      RC(bias_grad(c, g, M, C, c.G(q.b2)));
       RC(linear_dgrad(c, dbig, M, 4 * C, c.wc + q.w116t, C, B200_EPI_STORE, dsmall, nullptr));        // d xn2
       RC(linear_wgrad(c, dbig, M, 4 * C, c.W<bf16>(a.xn2), C, c.G(q.w1)));
       RC(bias_grad(c, dbig, M, 4 * C, c.G(q.b1)));
+      // g <- d x_mid; the same pass yields d b2 = colsum(g): g is dL/d(fc2 output)
       RC(b200_layernorm_bwd(dsmall, c.W<bf16>(a.xmid), c.P(q.ln2_w), c.W<float>(a.mean2), c.W<float>(a.rstd2), g, g,
-                            c.G(q.ln2_w), c.G(q.ln2_b), c.W<float>(p.red_partial), M, C, 0, c.stv));                 // g <- d x_mid
+                            c.G(q.ln2_w), c.G(q.ln2_b), c.G(q.b2), c.W<float>(p.red_partial), M, C, 0, c.stv));
       // ---- attention: x_mid = x_in + Wo attn(LN1(x_in)) + bo
       RC(linear_dgrad(c, g, M, C, c.wc + q.wo16t, C, B200_EPI_STORE, dsmall, nullptr));               // d attn_out
       RC(linear_wgrad(c, g, M, C, c.W<bf16>(a.attn), C, c.G(q.wo)));
-      RC(bias_grad(c, g, M, C, c.G(q.bo)));
       RC(b200_window_attn_bwd(c.W<bf16>(a.qkv), c.P(q.pos), c.W<bf16>(a.attn), c.W<float>(a.lse), dsmall, dbig, c.G(q.pos),
                               c.W<float>(p.dpos_partial), 0, p.B, S.Hs, S.Hs, C, S.heads, b & 1, c.stv));   // dbig <- d qkv
       RC(linear_dgrad(c, dbig, M, 3 * C, c.wc + q.wqkv16t, C, B200_EPI_STORE, dsmall, nullptr));      // d xn1
       RC(linear_wgrad(c, dbig, M, 3 * C, c.W<bf16>(a.xn1), C, c.G(q.wqkv)));
+      // g <- d x_in; d bo = colsum(g before the update): g is dL/d(to_out output)
       RC(b200_layernorm_bwd(dsmall, x_in, c.P(q.ln1_w), c.W<float>(a.mean1), c.W<float>(a.rstd1), g, g, c.G(q.ln1_w), c.G(q.ln1_b),
-                            c.W<float>(p.red_partial), M, C, 0, c.stv));                               // g <- d x_in
+                            c.G(q.bo), c.W<float>(p.red_partial), M, C, 0, c.stv));
     }
     // ---- patch merging linear (models/swin.py:162-167)
     RC(linear_wgrad(c, g, M, C, c.W<bf16>(S.cols), S.Kp, c.G(S.wp)));

@@ -117,6 +117,9 @@ def test_layernorm(C, M):
     dx, dgam, dbet = ops.layernorm_bwd(dy, x, g, mean, rstd, dres=dres)
     assert rel_err(dx, xr.grad + dres.float()) < 6e-3
     assert rel_err(dgam, gr.grad) < 1e-3 and rel_err(dbet, br.grad) < 1e-3
+    dx2, dgam2, dbet2, dcol = ops.layernorm_bwd(dy, x, g, mean, rstd, dres=dres, want_dres_colsum=True)
+    assert torch.equal(dx2, dx) and torch.equal(dgam2, dgam)
+    assert rel_err(dcol, dres.float().sum(0)) < 1e-4          # fused bias gradient of the residual branch's Linear
 
 
 def test_patch_gather_matches_unfold():
