@@ -256,6 +256,8 @@ def gpu_arm(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * B * args.steps / t.item()
 
+    gallery = gallery_leg(args, rank, world, device) if not args.no_gallery else None
+
     if rank != 0:
         return
     peak_tf, peak_hbm, peak_src = peaks()
@@ -279,6 +281,9 @@ def gpu_arm(args, rank, world, local_rank):
                      'whole_step_frac': value / world * train_flops_per_image() / (peak_tf * 1e12) if peak_tf else None},
         'clocks': clocks,
     }
+    if gallery is not None:
+        gallery['frac_of_peak'] = gallery['tflops'] / peak_tf if peak_tf else None
+        line['gallery'] = gallery
     if world == 1 and not args.no_cpu_baseline:
         cb, steps_cb = 32, 2
         ips, _ = time_oracle(cb, 1, steps_cb)
@@ -286,6 +291,50 @@ def gpu_arm(args, rank, world, local_rank):
                                 'sample': f'{steps_cb} steps of batch {cb} after 1 warm-up: same step (Swin-T + ArcFace(C={NUM_CLASS}) + SGD), '
                                           f'oracle/ port, fp32, {torch.get_num_threads()} threads'}
     print(json.dumps(line), flush=True)
+
+
+def gallery_leg(args, rank, world, device):
+    """Second half of BASELINE.json's metric: gallery queries/s (configs[3] shape, bounded): every rank holds a gallery shard of
+    1M / 8 = 125k x 512 rows (the per-GPU share of config 4) and matches `--gallery-queries` queries against it with the fused
+    cosine + top-100 kernel; value = queries/s against the FULL gallery of world * 125k rows (all ranks work in parallel on
+    their shards; the merge of the partial lists is included for world > 1)."""
+    import torch.distributed as dist
+    from b200 import gallery
+    g = torch.Generator(device=device).manual_seed(100 + rank)
+    nq, ng = args.gallery_queries, args.gallery_rows
+    gal = torch.nn.functional.normalize(torch.randn(ng, 512, device=device, generator=g))
+    q = torch.nn.functional.normalize(torch.randn(nq, 512, device=device, generator=torch.Generator(device=device).manual_seed(7)))
+    gprep = gallery.prepare(gal)
+
+    def once():
+        idx, score = gallery.cosine_topk(q, gal, 100, g_index_base=rank * ng, g_prepared=gprep)
+        if world > 1:
+            idx_all = [torch.empty_like(idx) for _ in range(world)]
+            sc_all = [torch.empty_like(score) for _ in range(world)]
+            dist.all_gather(idx_all, idx)
+            dist.all_gather(sc_all, score)
+            lo, hi = rank * nq // world, (rank + 1) * nq // world
+            idx, score = gallery.topk_merge(torch.stack([s[lo:hi] for s in sc_all]), torch.stack([i[lo:hi] for i in idx_all]), 100)
+        return idx
+    once()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    reps = 2
+    for _ in range(reps):
+        once()
+    ev1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([ev0.elapsed_time(ev1) / reps], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    flops = 2.0 * 512 * nq * ng            # per GPU
+    return {'metric': 'gallery queries/sec (cosine + top-100, 512-d, fp16 tensor-core pass + exact fp64 re-rank)', 'value': nq / (ms * 1e-3),
+            'unit': 'queries/s', 'queries': nq, 'gallery_rows_total': ng * world, 'gallery_rows_per_gpu': ng, 'ms': ms,
+            'tflops': flops / (ms * 1e-3) / 1e12}
 
 
 def main():
@@ -296,6 +345,9 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--batch', type=int, default=256)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-gallery', action='store_true')
+    ap.add_argument('--gallery-queries', type=int, default=8192)
+    ap.add_argument('--gallery-rows', type=int, default=125000)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     rank = int(os.environ.get('RANK', 0))
