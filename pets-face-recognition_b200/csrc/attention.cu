@@ -143,25 +143,6 @@ __device__ __forceinline__ void load_tile_async(uint32_t slab, const bf16* base,
   }
 }
 
-// Pull the 64-B row segments the NEXT task of this warp will load into L2 while the current task computes (a warp is
-// otherwise load -> wait -> compute, with nothing in flight during the compute phase).
-__device__ __forceinline__ void prefetch_task(const AttnArgs& a, long long task, long long ntasks, int lane, bool bwd) {
-  if (task >= ntasks) return;
-  const Task t = decode_task(a, task);
-  const long long ld_qkv = 3LL * a.C;
-  for (int i = lane; i < kWt; i += 32) {
-    const long long r = token_row(a, t, i);
-    const bf16* q = a.qkv + r * ld_qkv + t.h * kHd;
-    prefetch_l2(q);
-    prefetch_l2(q + a.C);
-    prefetch_l2(q + 2 * a.C);
-    if (bwd) {
-      prefetch_l2(a.dout + r * a.C + t.h * kHd);
-      prefetch_l2(a.o + r * a.C + t.h * kHd);
-    }
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
@@ -193,7 +174,6 @@ __global__ void __launch_bounds__(kWarps * 32) window_attn_fwd_kernel(const Attn
     load_tile_async(qs, a.qkv, ld_qkv, t.h * kHd, rows_s, lane);
     load_tile_async(ks, a.qkv, ld_qkv, a.C + t.h * kHd, rows_s, lane);
     load_tile_async(vs, a.qkv, ld_qkv, 2 * a.C + t.h * kHd, rows_s, lane);
-    prefetch_task(a, task + 1LL * gridDim.x * kWarps, ntasks, lane, false);
     cp_async_wait_all();
     __syncwarp();
 
@@ -344,7 +324,6 @@ __global__ void __launch_bounds__(kWarps * 32) window_attn_bwd_kernel(const Attn
     load_tile_async(ks, a.qkv, ld_qkv, a.C + t.h * kHd, rows_s, lane);
     load_tile_async(vs, a.qkv, ld_qkv, 2 * a.C + t.h * kHd, rows_s, lane);
     load_tile_async(dos, a.dout, a.C, t.h * kHd, rows_s, lane);
-    prefetch_task(a, task + 1LL * gridDim.x * kWarps, ntasks, lane, true);
     // D_i = sum_d dO[i,d] * O[i,d]  (== rowsum(dP o P)); straight from global while the tiles stream in
 #pragma unroll
     for (int it = 0; it < 7; ++it) {

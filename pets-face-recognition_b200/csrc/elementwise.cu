@@ -36,7 +36,7 @@ __device__ __forceinline__ float group_sum(float v) {
 // LayerNorm forward (nn.LayerNorm(C), eps 1e-5, models/swin.py:29,215).  LPR lanes cooperate on one
 // row, each lane holding up to MAXIT chunks of 8 channels in registers; two-pass statistics in fp32.
 // ---------------------------------------------------------------------------------------------
-template <int LPR, int MAXIT>
+template <int LPR, int MAXIT, int U>
 __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, bf16* __restrict__ y,
                                                             float* __restrict__ mean, float* __restrict__ rstd,
@@ -47,50 +47,59 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restri
   const long long warp_global = (1LL * blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = (1LL * gridDim.x * blockDim.x) >> 5;
   const int chunks = C >> 3;
-  for (long long row0 = warp_global * RPW; row0 < M; row0 += nwarps * RPW) {
-    const long long row = row0 + sub;
-    const bool live = row < M;
-    float v[MAXIT][8];
-    float s = 0.f;
+  // U row groups per iteration: all their loads are issued before any arithmetic (memory-level parallelism)
+  for (long long row0 = warp_global * (RPW * U); row0 < M; row0 += nwarps * (RPW * U)) {
+    float v[U][MAXIT][8];
 #pragma unroll
-    for (int it = 0; it < MAXIT; ++it) {
-      const int ch = l + it * LPR;
-      if (live && ch < chunks) {
-        ld8(x + row * C + ch * 8, v[it]);
+    for (int u = 0; u < U; ++u) {
+      const long long row = row0 + u * RPW + sub;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s += v[it][i];
-      } else {
+      for (int it = 0; it < MAXIT; ++it) {
+        const int ch = l + it * LPR;
+        if (row < M && ch < chunks) ld8(x + row * C + ch * 8, v[u][it]);
+        else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[it][i] = 0.f;
+          for (int i = 0; i < 8; ++i) v[u][it][i] = 0.f;
+        }
       }
     }
-    const float mu = group_sum<LPR>(s) / C;
-    float q = 0.f;
 #pragma unroll
-    for (int it = 0; it < MAXIT; ++it) {
-      const int ch = l + it * LPR;
-      if (ch < chunks) {
+    for (int u = 0; u < U; ++u) {
+      const long long row = row0 + u * RPW + sub;
+      const bool live = row < M;
+      float s = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { const float d = v[it][i] - mu; q += d * d; }
-      }
-    }
-    const float rs = rsqrtf(group_sum<LPR>(q) / C + eps);
-    if (live) {
+      for (int it = 0; it < MAXIT; ++it)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += v[u][it][i];
+      const float mu = group_sum<LPR>(s) / C;
+      float q = 0.f;
 #pragma unroll
       for (int it = 0; it < MAXIT; ++it) {
         const int ch = l + it * LPR;
         if (ch < chunks) {
-          float g[8], b[8], o[8];
-          ld8f(gamma + ch * 8, g);
-          ld8f(beta + ch * 8, b);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] = (v[it][i] - mu) * rs * g[i] + b[i];
-          st8(y + row * C + ch * 8, o);
+          for (int i = 0; i < 8; ++i) { const float d = v[u][it][i] - mu; q += d * d; }
         }
       }
-      if (l == 0) {
-        if (mean) mean[row] = mu;
-        if (rstd) rstd[row] = rs;
+      const float rs = rsqrtf(group_sum<LPR>(q) / C + eps);
+      if (live) {
+#pragma unroll
+        for (int it = 0; it < MAXIT; ++it) {
+          const int ch = l + it * LPR;
+          if (ch < chunks) {
+            float g[8], b[8], o[8];
+            ld8f(gamma + ch * 8, g);
+            ld8f(beta + ch * 8, b);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = (v[u][it][i] - mu) * rs * g[i] + b[i];
+            st8(y + row * C + ch * 8, o);
+          }
+        }
+        if (l == 0) {
+          if (mean) mean[row] = mu;
+          if (rstd) rstd[row] = rs;
+        }
       }
     }
   }
@@ -452,10 +461,11 @@ int grid_for(long long work_items, int threads, int max_blocks) {
 template <int LPR, int MAXIT>
 int ln_fwd_launch(const bf16* x, const float* g, const float* b, bf16* y, float* mean, float* rstd, long long M, int C, float eps,
                   cudaStream_t st) {
-  const int rpw = 32 / LPR;
+  constexpr int U = MAXIT == 1 ? 4 : (MAXIT <= 3 ? 2 : 1);
+  const int rpw = (32 / LPR) * U;
   const long long warps = (M + rpw - 1) / rpw;
   const int blocks = grid_for(warps * 32, 256, b200_num_sms() * 8);
-  layernorm_fwd_kernel<LPR, MAXIT><<<blocks, 256, 0, st>>>(x, g, b, y, mean, rstd, M, C, eps);
+  layernorm_fwd_kernel<LPR, MAXIT, U><<<blocks, 256, 0, st>>>(x, g, b, y, mean, rstd, M, C, eps);
   B200_LAUNCH_CHECK();
   return B200_OK;
 }

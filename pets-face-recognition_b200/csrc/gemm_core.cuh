@@ -35,8 +35,6 @@ constexpr int kThreads = 64 + kEpiWarps * 32;     // 320
 constexpr int kBoxBytes = 32 * 128;               // one output box: 32 rows x (at most) 128 B
 constexpr int kStagingPerWarp = 2 * kBoxBytes;    // double buffer (or the two outputs of the GELU epilogue)
 constexpr int kBarBytes = 512;
-constexpr int kPrefetchTiles = 3;                 // L2 prefetch distance of the A panels, in tiles of this CTA
-constexpr int kMaxPrefetchKb = 8;                 // ... and at most this many k-blocks (128 KB) per prefetched tile
 constexpr int kSmemBytes = kPipeBytes + kEpiWarps * kStagingPerWarp + kBarBytes + 1024 /*alignment slack*/;
 
 struct CoreParams {
@@ -139,23 +137,6 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int split = tile / (p.n_blocks * p.m_blocks);
         const int kb0 = split * p.k_blocks_per_split;
         const int kb1 = min(p.k_blocks, kb0 + p.k_blocks_per_split);
-        // The smem ring holds at most ~1.5 tiles of A for the small-K layers: far too few bytes in flight to cover HBM latency
-        // at 6.5 TB/s.  Pull the A panel this CTA will need kPrefetchTiles tiles from now into L2 already (B = weights is
-        // L2-resident anyway), so that the ring is refilled at L2 latency.
-        {
-          const int ptile = tile + kPrefetchTiles * static_cast<int>(gridDim.x);
-          if (ptile < num_tiles) {
-            const int pm = (ptile / p.n_blocks) % p.m_blocks, ps = ptile / (p.n_blocks * p.m_blocks);
-            const bool first_n = (ptile % p.n_blocks) == 0 || static_cast<int>(gridDim.x) % p.n_blocks != 0;
-            if (first_n) {
-              const int pk0 = ps * p.k_blocks_per_split, pk1 = min(p.k_blocks, pk0 + p.k_blocks_per_split);
-              for (int kb = pk0; kb < pk1 && kb < pk0 + kMaxPrefetchKb; ++kb) {
-                if (!p.mn_major) tma_prefetch_2d(&tmap_a, kb * kBlockK, pm * kBlockM);
-                else { tma_prefetch_2d(&tmap_a, pm * kBlockM, kb * kBlockK); tma_prefetch_2d(&tmap_a, pm * kBlockM + 64, kb * kBlockK); }
-              }
-            }
-          }
-        }
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
@@ -236,13 +217,6 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int split = tile / (p.n_blocks * p.m_blocks);
       const int kb0 = split * p.k_blocks_per_split;
       const bool has_k = min(p.k_blocks, kb0 + p.k_blocks_per_split) > kb0;
-      if (aux && lane == 0) {     // same latency argument for the side input: its boxes two tiles ahead go to L2 now
-        const int ptile = tile + 2 * static_cast<int>(gridDim.x);
-        if (ptile < num_tiles) {
-          const int pn = ptile % p.n_blocks, pm = (ptile / p.n_blocks) % p.m_blocks;
-          for (int box = box_lo; box < box_hi; ++box) tma_prefetch_3d(&tmap_aux, pn * p.block_n + box * p.box_cols, pm * kBlockM + q * 32, 0);
-        }
-      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const int row = m_blk * kBlockM + q * 32 + lane;
