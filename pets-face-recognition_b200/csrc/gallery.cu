@@ -44,6 +44,7 @@ struct FilterParams {
   uint32_t idesc;
   uint2* scratch;             // [gridDim.x][128][kCap] (score bits, idx)
   int* cand_idx;              // [q_blocks*128][chunks][kKP]
+  float* cand_score;          // [q_blocks*128][chunks][kKP] fp16-GEMM scores of the survivors (approximate)
   int* cand_cnt;              // [q_blocks*128][chunks]
 };
 
@@ -264,7 +265,8 @@ cosine_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         }
         __syncwarp();
         int* dst = p.cand_idx + (qrow * p.chunks + chunk) * kKP;
-        for (int i = 0; i < cnt; ++i) dst[i] = static_cast<int>(list[i].y);
+        float* dsc = p.cand_score + (qrow * p.chunks + chunk) * kKP;
+        for (int i = 0; i < cnt; ++i) { const uint2 e = list[i]; dst[i] = static_cast<int>(e.y); dsc[i] = __uint_as_float(e.x); }
         p.cand_cnt[qrow * p.chunks + chunk] = live ? cnt : 0;
         __syncwarp();
       }
@@ -301,9 +303,9 @@ __device__ void bitonic_sort(Cand* c, int n_pow2) {
 
 __global__ void __launch_bounds__(256) rerank_kernel(const float* __restrict__ q, const double* __restrict__ q_norm,
                                                      const float* __restrict__ g, const double* __restrict__ g_norm, int dim,
-                                                     const int* __restrict__ cand_idx, const int* __restrict__ cand_cnt, int chunks,
-                                                     int n_pow2, int k, long long g_index_base, int* __restrict__ out_idx,
-                                                     double* __restrict__ out_score) {
+                                                     const int* __restrict__ cand_idx, const float* __restrict__ cand_score,
+                                                     const int* __restrict__ cand_cnt, int chunks, int n_pow2, int k,
+                                                     long long g_index_base, int* __restrict__ out_idx, double* __restrict__ out_score) {
   extern __shared__ __align__(16) uint8_t sm[];
   Cand* cands = reinterpret_cast<Cand*>(sm);
   __shared__ int s_off[64];
@@ -316,14 +318,26 @@ __global__ void __launch_bounds__(256) rerank_kernel(const float* __restrict__ q
     s_total = t;
   }
   __syncthreads();
-  const int total = s_total;
+  int total = s_total;
   for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) { cands[i].score = -INFINITY; cands[i].idx = INT_MAX; }
   __syncthreads();
   for (int c = 0; c < chunks; ++c) {
     const int n = cand_cnt[qi * chunks + c];
-    for (int i = threadIdx.x; i < n; i += blockDim.x) cands[s_off[c] + i].idx = cand_idx[(qi * chunks + c) * kKP + i];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      cands[s_off[c] + i].idx = cand_idx[(qi * chunks + c) * kKP + i];
+      cands[s_off[c] + i].score = static_cast<double>(cand_score[(qi * chunks + c) * kKP + i]);
+    }
   }
   __syncthreads();
+  // level 1: the survivors of all gallery chunks, ranked by their approximate (fp16 tensor-core) score; only the best
+  // kKP overall can contain the exact top-k (same k + 28 slack argument as inside a chunk)
+  if (total > kKP) {
+    bitonic_sort(cands, n_pow2);
+    total = kKP;
+    for (int i = kKP + threadIdx.x; i < n_pow2; i += blockDim.x) { cands[i].score = -INFINITY; cands[i].idx = INT_MAX; }
+    __syncthreads();
+  }
+  // level 2: exact fp64 cosine of those <= kKP candidates from the fp32 embeddings
   const float* qr = q + qi * dim;
   const double nq = fmax(q_norm[qi], 1e-8);
   for (int i = warp; i < total; i += blockDim.x >> 5) {
@@ -343,7 +357,9 @@ __global__ void __launch_bounds__(256) rerank_kernel(const float* __restrict__ q
     if (lane == 0) cands[i].score = acc / (nq * fmax(g_norm[gi], 1e-8));
   }
   __syncthreads();
-  bitonic_sort(cands, n_pow2);
+  int m = 1;
+  while (m < total) m <<= 1;              // <= kKP; entries [total, m) are -inf padding
+  bitonic_sort(cands, m);
   for (int i = threadIdx.x; i < k; i += blockDim.x) {
     const bool ok = i < total;
     out_idx[qi * k + i] = ok ? static_cast<int>(cands[i].idx + g_index_base) : -1;
@@ -420,7 +436,7 @@ __global__ void recall_hits_kernel(const int* __restrict__ top_idx, long long nq
     if (first < ks[i]) atomicAdd(&hits[i], 1ULL);
 }
 
-struct Layout { long long scratch, cand_idx, cand_cnt, total; int chunks; long long chunk_rows; int q_blocks; int ctas; };
+struct Layout { long long scratch, cand_idx, cand_score, cand_cnt, total; int chunks; long long chunk_rows; int q_blocks; int ctas; };
 
 Layout plan_layout(long long nq, long long ng) {
   Layout L;
@@ -439,6 +455,7 @@ Layout plan_layout(long long nq, long long ng) {
   auto take = [&](long long bytes) { long long o = off; off = (off + bytes + 255) / 256 * 256; return o; };
   L.scratch = take(1LL * sms * kBM * kCap * 8);
   L.cand_idx = take(1LL * L.q_blocks * kBM * L.chunks * kKP * 4);
+  L.cand_score = take(1LL * L.q_blocks * kBM * L.chunks * kKP * 4);
   L.cand_cnt = take(1LL * L.q_blocks * kBM * L.chunks * 4);
   L.total = off;
   return L;
@@ -487,6 +504,7 @@ extern "C" int b200_cosine_topk(const float* q, const void* q_unit_f16, const do
   p.idesc = gemm::make_idesc(false, kBN);
   p.scratch = reinterpret_cast<uint2*>(ws + L.scratch);
   p.cand_idx = reinterpret_cast<int*>(ws + L.cand_idx);
+  p.cand_score = reinterpret_cast<float*>(ws + L.cand_score);
   p.cand_cnt = reinterpret_cast<int*>(ws + L.cand_cnt);
   CUtensorMap tq, tg;
   int rc = gemm::encode_tmap_2d(&tq, false, q_unit_f16, dim, nq, dim, kBK, kBM);
@@ -501,7 +519,7 @@ extern "C" int b200_cosine_topk(const float* q, const void* q_unit_f16, const do
   while (n_pow2 < L.chunks * kKP) n_pow2 <<= 1;
   const int smem2 = n_pow2 * static_cast<int>(sizeof(Cand));
   if (smem2 > 48 * 1024) B200_CHECK_CUDA(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
-  rerank_kernel<<<static_cast<unsigned>(nq), 256, smem2, st>>>(q, q_norm, g, g_norm, dim, p.cand_idx, p.cand_cnt, L.chunks, n_pow2, k,
+  rerank_kernel<<<static_cast<unsigned>(nq), 256, smem2, st>>>(q, q_norm, g, g_norm, dim, p.cand_idx, p.cand_score, p.cand_cnt, L.chunks, n_pow2, k,
                                                                g_index_base, out_idx, out_score);
   B200_LAUNCH_CHECK();
   return B200_OK;

@@ -183,38 +183,36 @@ int pick_block_n(int N, int K) {
 // epilogue for linear layers.  Each epilogue thread owns one output row and gets 16 consecutive
 // fp32 accumulator columns per call.
 // ---------------------------------------------------------------------------------------------
+template <int MODE>
 struct EpiLinear {
   struct Params {
-    int mode;                            // B200_EPI_*
     const float* bias;                   // [N] or null
   };
 
   // v: 16 consecutive accumulator columns of one output row; ax: the matching 16 values of the aux input (RESID: residual,
   // DGELU: saved pre-activation) -> o (and o2 = pre-activation in GELU mode).  Rows >= M / columns >= N are computed on
   // zero-filled inputs and clipped by the TMA store.
-  __device__ static __forceinline__ void compute(const Params& ep, const CoreParams& p, int row, int col, int /*split*/,
-                                                 const float (&v)[16], const float (&ax)[16], float (&o)[16], float (&o2)[16]) {
-    const bool live = row < p.M && col < p.N;
-    const int ngroups = !live ? 0 : ((p.N - col) >= 16 ? 2 : 1);     // N % 8 == 0 is required by the launcher
+  __device__ static __forceinline__ void compute(const Params& ep, const CoreParams& p, int /*row*/, int col, const float (&v)[16],
+                                                 const float (&ax)[16], float (&o)[16], float (&o2)[16]) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) o[i] = v[i];
     if (ep.bias != nullptr) {
 #pragma unroll
       for (int g = 0; g < 2; ++g)
-        if (g < ngroups) {
+        if (col + g * 8 < p.N) {                                   // N % 8 == 0 is required by the launcher
           const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + col + g * 8));
           const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + col + g * 8 + 4));
           o[g * 8 + 0] += b0.x; o[g * 8 + 1] += b0.y; o[g * 8 + 2] += b0.z; o[g * 8 + 3] += b0.w;
           o[g * 8 + 4] += b1.x; o[g * 8 + 5] += b1.y; o[g * 8 + 6] += b1.z; o[g * 8 + 7] += b1.w;
         }
     }
-    if (ep.mode == B200_EPI_GELU) {
+    if (MODE == B200_EPI_GELU) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) { o2[i] = o[i]; o[i] = gelu_erf(o[i]); }
-    } else if (ep.mode == B200_EPI_RESID) {
+    } else if (MODE == B200_EPI_RESID) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) o[i] += ax[i];
-    } else if (ep.mode == B200_EPI_DGELU) {
+    } else if (MODE == B200_EPI_DGELU) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) o[i] *= gelu_erf_grad(ax[i]);
     }
@@ -233,7 +231,7 @@ struct EpiMargin {
     int kind;                             // 0 = ArcFace, 1 = CosFace (AddMarginProduct)
     int easy_margin;
   };
-  __device__ static __forceinline__ void compute(const Params& ep, const CoreParams& p, int row, int col, int, const float (&v)[16],
+  __device__ static __forceinline__ void compute(const Params& ep, const CoreParams& p, int row, int col, const float (&v)[16],
                                                  const float (&)[16], float (&o)[16], float (&)[16]) {
     const bool live = row < p.M && col < p.N;
     const int lab = live ? static_cast<int>(ep.label[row]) : -1;
@@ -328,9 +326,20 @@ extern "C" int b200_gemm_tn(const void* a, long long lda, const void* b, long lo
   gemm::Operands o{a, (int)lda, b, (int)ldb, M, N, K, is_bf16 != 0, block_n, splits, 0};
   const bool use_aux = mode == B200_EPI_RESID || mode == B200_EPI_DGELU;
   B200_REQUIRE(!(use_aux && eb != 2), "gemm_tn: RESID / DGELU epilogues write bf16");
+  B200_REQUIRE(!(mode == B200_EPI_GELU && eb != 2), "gemm_tn: the GELU epilogue writes bf16");
   gemm::Output od{out, ldo, eb, out2, ldo2, mode == B200_EPI_PARTIAL ? split_stride : 0, use_aux ? aux : nullptr, use_aux ? ldaux : 0};
-  gemm::EpiLinear::Params ep{mode, bias};
-  return gemm::launch<gemm::EpiLinear>(o, od, ep, reinterpret_cast<cudaStream_t>(stream));
+  auto st = reinterpret_cast<cudaStream_t>(stream);
+  switch (mode) {
+    case B200_EPI_STORE:
+      if (eb == 2) return gemm::launch<gemm::EpiLinear<B200_EPI_STORE>, 2, false, false>(o, od, {bias}, st);
+      return gemm::launch<gemm::EpiLinear<B200_EPI_STORE>, 4, false, false>(o, od, {bias}, st);
+    case B200_EPI_GELU:
+      if (out2 != nullptr) return gemm::launch<gemm::EpiLinear<B200_EPI_GELU>, 2, true, false>(o, od, {bias}, st);
+      return gemm::launch<gemm::EpiLinear<B200_EPI_GELU>, 2, false, false>(o, od, {bias}, st);
+    case B200_EPI_RESID: return gemm::launch<gemm::EpiLinear<B200_EPI_RESID>, 2, false, true>(o, od, {bias}, st);
+    case B200_EPI_DGELU: return gemm::launch<gemm::EpiLinear<B200_EPI_DGELU>, 2, false, true>(o, od, {bias}, st);
+    default: return gemm::launch<gemm::EpiLinear<B200_EPI_PARTIAL>, 4, false, false>(o, od, {bias}, st);
+  }
 }
 
 // dW[N,K] (fp32 split partials) = dY[tokens,N]^T * X[tokens,K]: both operands are read in place, MN-major - no transposes.
@@ -339,8 +348,7 @@ extern "C" int b200_gemm_wgrad(const void* dy, long long ldy, const void* x, lon
   B200_REQUIRE(K % 8 == 0 && N > 0 && tokens > 0 && tokens < (1LL << 31), "gemm_wgrad: bad shape tokens=%lld N=%d K=%d", tokens, N, K);
   gemm::Operands o{dy, (int)ldy, x, (int)ldx, N, K, static_cast<int>(tokens), true, block_n, splits, 0, true};
   gemm::Output od{partial, K, 4, nullptr, 0, 1LL * N * K, nullptr, 0};
-  gemm::EpiLinear::Params ep{B200_EPI_PARTIAL, nullptr};
-  return gemm::launch<gemm::EpiLinear>(o, od, ep, reinterpret_cast<cudaStream_t>(stream));
+  return gemm::launch<gemm::EpiLinear<B200_EPI_PARTIAL>, 4, false, false>(o, od, {nullptr}, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int b200_gemm_splits(int K, int splits) { return gemm::effective_splits(K, splits); }
@@ -359,5 +367,5 @@ extern "C" int b200_margin_logits(const void* emb_unit, const void* w_unit, int 
   gemm::Output od{logits, ldo, 4, nullptr, 0, 0, nullptr, 0};
   gemm::EpiMargin::Params ep{cos_label, label, s, (float)cos(md), (float)sin(md), (float)cos(pi - md),
                              (float)(sin(pi - md) * md), m, kind, easy_margin};
-  return gemm::launch<gemm::EpiMargin>(o, od, ep, reinterpret_cast<cudaStream_t>(stream));
+  return gemm::launch<gemm::EpiMargin, 4, false, false>(o, od, ep, reinterpret_cast<cudaStream_t>(stream));
 }

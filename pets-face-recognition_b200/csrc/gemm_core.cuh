@@ -72,7 +72,10 @@ inline uint32_t make_idesc(bool is_bf16, int block_n, bool mn_major = false) {
 __device__ __forceinline__ float bf16lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
-template <class Epi>
+// Compile-time specialisation of the epilogue (the small-K layers are bound by the epilogue's instruction issue rate):
+//   Epi       what to compute per element          OUT_BYTES  2 = bf16 output, 4 = fp32 output
+//   DUAL      second bf16 output (GELU pre-activation)   AUX   bf16 side input streamed by TMA into the staging boxes
+template <class Epi, int OUT_BYTES, bool DUAL, bool AUX>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_o2,
@@ -194,10 +197,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int box_lo = (ew < 4) ? 0 : (nboxes + 1) / 2;          // the two warps of a quarter split the column boxes
     const int box_hi = (ew < 4) ? (nboxes + 1) / 2 : nboxes;
     const uint32_t stg = staging_base + ew * kStagingPerWarp;
-    const uint32_t row_bytes = static_cast<uint32_t>(p.box_cols * p.out_bytes);
+    const uint32_t row_bytes = static_cast<uint32_t>(p.box_cols * OUT_BYTES);
     const uint32_t box_bytes = 32u * row_bytes;
-    const uint32_t swz_mask = (row_bytes >> 4) - 1u;             // 7 / 3 / 1 for the 128 / 64 / 32-B swizzle modes
-    const bool aux = p.has_aux != 0 && box_hi > box_lo;
+    // this lane's row inside a staging box, and its swizzle term: the 16-B chunk index is XORed with address bits 7.. of
+    // the row (Swizzle<3|2|1,4,3> of the 128 / 64 / 32-B TMA modes); both are loop invariants
+    const uint32_t row_off = static_cast<uint32_t>(lane) * row_bytes;
+    const uint32_t swz = ((row_off >> 7) & ((row_bytes >> 4) - 1u)) << 4;
+    constexpr int kChunkBytes = 16 * OUT_BYTES;                   // bytes one 16-column chunk occupies in a box row
+    constexpr int kMaxChunks = 128 / kChunkBytes;                 // 4 (bf16) / 2 (fp32)
+    const bool aux = AUX && box_hi > box_lo;
     int buf = 0;
     uint32_t aux_phase0 = 0, aux_phase1 = 0;
     int acc = 0;
@@ -220,78 +228,79 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const int row = m_blk * kBlockM + q * 32 + lane;
+      const int col_tile = n_blk * p.block_n;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * kMaxBlockN);
       for (int box = box_lo; box < box_hi; ++box) {
         const int c_tile = box * p.box_cols;                     // first column of the box inside the tile
-        if (!aux && n_blk * p.block_n + c_tile >= p.N) continue; // padded tile: nothing of this box is inside the matrix
+        if (!AUX && col_tile + c_tile >= p.N) continue;          // padded tile: nothing of this box is inside the matrix
         if (lane == 0) {
-          if (aux) {
+          if (AUX) {
             // the OTHER buffer was last read by the store of the previous box: drain it, then stream the next aux box in
             bulk_wait_read<0>();
-            const bool more_here = box + 1 < box_hi;
-            const int ntile = more_here ? tile : tile + static_cast<int>(gridDim.x);
-            if (ntile < num_tiles) issue_aux(ntile, more_here ? box + 1 : box_lo, buf ^ 1);
-          } else if (p.n_out == 2) {
+            if (aux) {
+              const bool more_here = box + 1 < box_hi;
+              const int ntile = more_here ? tile : tile + static_cast<int>(gridDim.x);
+              if (ntile < num_tiles) issue_aux(ntile, more_here ? box + 1 : box_lo, buf ^ 1);
+            }
+          } else if (DUAL) {
             bulk_wait_read<0>();               // both buffers are rewritten for every box
           } else {
             bulk_wait_read<1>();               // the buffer about to be rewritten was read by the store before last
           }
         }
         __syncwarp();
-        const uint32_t sbuf = stg + (p.n_out == 2 ? 0u : static_cast<uint32_t>(buf) * kBoxBytes);
-        if (aux) {
+        const uint32_t sbuf = stg + (DUAL ? 0u : static_cast<uint32_t>(buf) * kBoxBytes);
+        if (AUX) {
           if (buf == 0) { mbar_wait(aux_bar(ew, 0), aux_phase0); aux_phase0 ^= 1u; }
           else { mbar_wait(aux_bar(ew, 1), aux_phase1); aux_phase1 ^= 1u; }
         }
-        for (int c = 0; c < p.box_cols; c += 16) {
-          uint32_t r[16];
-          tmem_ld16(taddr + c_tile + c, r);
-          const uint32_t a0 = static_cast<uint32_t>(lane) * row_bytes + static_cast<uint32_t>(c * p.out_bytes);
-          float ax[16];
-          if (aux) {      // the bf16 side input sits exactly where the result will be written
+        const uint32_t srow = sbuf + row_off;
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
-              const uint32_t a = a0 + 16u * k;
-              uint32_t w0, w1, w2, w3;
-              ld_shared_v4(sbuf + (a ^ (((a >> 7) & swz_mask) << 4)), w0, w1, w2, w3);
-              ax[8 * k + 0] = bf16lo(w0); ax[8 * k + 1] = bf16hi(w0); ax[8 * k + 2] = bf16lo(w1); ax[8 * k + 3] = bf16hi(w1);
-              ax[8 * k + 4] = bf16lo(w2); ax[8 * k + 5] = bf16hi(w2); ax[8 * k + 6] = bf16lo(w3); ax[8 * k + 7] = bf16hi(w3);
+        for (int ci = 0; ci < kMaxChunks; ++ci) {
+          if (ci * 16 < p.box_cols) {
+            uint32_t r[16];
+            tmem_ld16(taddr + c_tile + ci * 16, r);
+            float ax[16];
+            if (AUX) {      // the bf16 side input sits exactly where the result will be written
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                uint32_t w0, w1, w2, w3;
+                ld_shared_v4(srow + ((ci * kChunkBytes + 16 * k) ^ swz), w0, w1, w2, w3);
+                ax[8 * k + 0] = bf16lo(w0); ax[8 * k + 1] = bf16hi(w0); ax[8 * k + 2] = bf16lo(w1); ax[8 * k + 3] = bf16hi(w1);
+                ax[8 * k + 4] = bf16lo(w2); ax[8 * k + 5] = bf16hi(w2); ax[8 * k + 6] = bf16lo(w3); ax[8 * k + 7] = bf16hi(w3);
+              }
             }
-          }
-          tmem_ld_wait();
-          if (!has_k) {
+            tmem_ld_wait();
+            if (!has_k) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) r[i] = 0u;
-          }
-          float o[16], o2[16];
-          Epi::compute(ep, p, row, n_blk * p.block_n + c_tile + c, split, reinterpret_cast<const float(&)[16]>(r), ax, o, o2);
-          if (p.out_bytes == 2) {
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-              const uint32_t a = a0 + 16u * k;
-              const uint32_t sw = a ^ (((a >> 7) & swz_mask) << 4);
-              st_shared_v4(sbuf + sw, pack_bf16(o[8 * k], o[8 * k + 1]), pack_bf16(o[8 * k + 2], o[8 * k + 3]),
-                           pack_bf16(o[8 * k + 4], o[8 * k + 5]), pack_bf16(o[8 * k + 6], o[8 * k + 7]));
-              if (p.n_out == 2)
-                st_shared_v4(sbuf + kBoxBytes + sw, pack_bf16(o2[8 * k], o2[8 * k + 1]), pack_bf16(o2[8 * k + 2], o2[8 * k + 3]),
-                             pack_bf16(o2[8 * k + 4], o2[8 * k + 5]), pack_bf16(o2[8 * k + 6], o2[8 * k + 7]));
+              for (int i = 0; i < 16; ++i) r[i] = 0u;
             }
-          } else {
+            float o[16], o2[16];
+            Epi::compute(ep, p, row, col_tile + c_tile + ci * 16, reinterpret_cast<const float(&)[16]>(r), ax, o, o2);
+            if (OUT_BYTES == 2) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint32_t a = a0 + 16u * k;
-              const uint32_t sw = a ^ (((a >> 7) & swz_mask) << 4);
-              st_shared_v4(sbuf + sw, __float_as_uint(o[4 * k]), __float_as_uint(o[4 * k + 1]), __float_as_uint(o[4 * k + 2]),
-                           __float_as_uint(o[4 * k + 3]));
+              for (int k = 0; k < 2; ++k) {
+                const uint32_t sw = srow + ((ci * kChunkBytes + 16 * k) ^ swz);
+                st_shared_v4(sw, pack_bf16(o[8 * k], o[8 * k + 1]), pack_bf16(o[8 * k + 2], o[8 * k + 3]),
+                             pack_bf16(o[8 * k + 4], o[8 * k + 5]), pack_bf16(o[8 * k + 6], o[8 * k + 7]));
+                if (DUAL)
+                  st_shared_v4(sw + kBoxBytes, pack_bf16(o2[8 * k], o2[8 * k + 1]), pack_bf16(o2[8 * k + 2], o2[8 * k + 3]),
+                               pack_bf16(o2[8 * k + 4], o2[8 * k + 5]), pack_bf16(o2[8 * k + 6], o2[8 * k + 7]));
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                st_shared_v4(srow + ((ci * kChunkBytes + 16 * k) ^ swz), __float_as_uint(o[4 * k]), __float_as_uint(o[4 * k + 1]),
+                             __float_as_uint(o[4 * k + 2]), __float_as_uint(o[4 * k + 3]));
             }
           }
         }
         fence_proxy_async_smem();            // generic-proxy smem writes -> visible to the TMA (async proxy)
         __syncwarp();
         if (lane == 0) {
-          const int gc = n_blk * p.block_n + c_tile, gr = m_blk * kBlockM + q * 32;
+          const int gc = col_tile + c_tile, gr = m_blk * kBlockM + q * 32;
           tma_store_3d(&tmap_o, sbuf, gc, gr, split);
-          if (p.n_out == 2) tma_store_3d(&tmap_o2, sbuf + kBoxBytes, gc, gr, split);
+          if (DUAL) tma_store_3d(&tmap_o2, sbuf + kBoxBytes, gc, gr, split);
           bulk_commit();
         }
         buf ^= 1;
@@ -351,8 +360,9 @@ inline int pick_box_cols(int block_n, int elem_bytes) {
   return 16;
 }
 
-template <class Epi>
+template <class Epi, int OUT_BYTES, bool DUAL, bool AUX>
 int launch(const Operands& o, const Output& out, const typename Epi::Params& ep, cudaStream_t stream) {
+  B200_REQUIRE(out.elem_bytes == OUT_BYTES && (out.ptr2 != nullptr) == DUAL && (out.aux != nullptr) == AUX, "gemm: epilogue specialisation mismatch");
   B200_REQUIRE(o.M > 0 && o.N > 0 && o.K > 0, "gemm: empty problem M=%d N=%d K=%d", o.M, o.N, o.K);
   B200_REQUIRE(o.lda % 8 == 0 && o.ldb % 8 == 0, "gemm: row pitch must be a multiple of 8 elements (16 B)");
   B200_REQUIRE((reinterpret_cast<uintptr_t>(o.a) & 15) == 0 && (reinterpret_cast<uintptr_t>(o.b) & 15) == 0,
@@ -417,14 +427,14 @@ int launch(const Operands& o, const Output& out, const typename Epi::Params& ep,
 
   static bool attr_done = false;   // per instantiation
   if (!attr_done) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<Epi, OUT_BYTES, DUAL, AUX>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_done = true;
   }
   const long long tiles = 1LL * p.m_blocks * p.n_blocks * p.splits;
   int ctas = o.max_ctas > 0 ? o.max_ctas : b200_num_sms();
   if (tiles < ctas) ctas = static_cast<int>(tiles);
   const bool prof = b200_prof_gemm_begin(stream, 2.0 * o.M * o.N * o.K);
-  gemm_tn_kernel<Epi><<<ctas, kThreads, kSmemBytes, stream>>>(ta, tb, to, to2, tx, p, ep);
+  gemm_tn_kernel<Epi, OUT_BYTES, DUAL, AUX><<<ctas, kThreads, kSmemBytes, stream>>>(ta, tb, to, to2, tx, p, ep);
   if (prof) b200_prof_gemm_end(stream);
   B200_LAUNCH_CHECK();
   return B200_OK;
