@@ -29,7 +29,8 @@ constexpr int kRowB = kPitch * 2;                  // 80 B
 constexpr int kTileRows = 50;                      // 49 token rows + one all-zero row that stands in for rows 49..63
 constexpr int kTileBytes = kTileRows * kRowB;      // 4000
 constexpr int kStageBytes = 16 * kRowB;            // 1280: one 16-row output tile
-constexpr int kWarps = 4;
+constexpr int kWarps = 4;                          // forward: warps (= tasks in flight) per CTA
+constexpr int kBwdWarps = 5;                       // backward: 2 CTAs x 5 warps per SM (smem- and register-limited)
 constexpr int kBins = 169;
 constexpr int kBiasPitch = 72;                     // floats per row of the 64 x 64 bias table (conflict-free float2 reads)
 constexpr int kBiasBytes = 64 * kBiasPitch * 4;    // 18432
@@ -111,7 +112,8 @@ __device__ __forceinline__ long long token_row(const AttnArgs& a, const Task& t,
 }
 
 // 64 x 64 additive score table shared by every window and head of the block (models/swin.py:117-118):
-// bias[i][j] = pos[r_j - r_i + 6][c_j - c_i + 6]; padded keys (j >= 49) -> -inf; padded queries (i >= 49) -> 0.
+// bias[i][j] = log2(e) * pos[r_j - r_i + 6][c_j - c_i + 6] (scores live in the log2 domain: one FFMA + EX2 per element);
+// padded keys (j >= 49) -> -inf; padded queries (i >= 49) -> 0.
 __device__ __forceinline__ void build_bias_table(float* bias_s, const float* __restrict__ pos) {
   for (int idx = threadIdx.x; idx < 64 * 64; idx += blockDim.x) {
     const int i = idx >> 6, j = idx & 63;
@@ -120,7 +122,7 @@ __device__ __forceinline__ void build_bias_table(float* bias_s, const float* __r
     else if (i >= kWt) v = 0.f;
     else {
       const int ri = i / kWs, ci = i - ri * kWs, rj = j / kWs, cj = j - rj * kWs;
-      v = __ldg(pos + (rj - ri + kWs - 1) * (2 * kWs - 1) + (cj - ci + kWs - 1));
+      v = kLog2e * __ldg(pos + (rj - ri + kWs - 1) * (2 * kWs - 1) + (cj - ci + kWs - 1));
     }
     bias_s[i * kBiasPitch + j] = v;
   }
@@ -212,10 +214,10 @@ __global__ void __launch_bounds__(kWarps * 32) window_attn_fwd_kernel(const Attn
       for (int n = 0; n < 8; ++n) {
         const float2 b0 = *reinterpret_cast<const float2*>(b0p + n * 8);
         const float2 b1 = *reinterpret_cast<const float2*>(b1p + n * 8);
-        s[n][0] = fmaf(s[n][0], sc2, b0.x * kLog2e);
-        s[n][1] = fmaf(s[n][1], sc2, b0.y * kLog2e);
-        s[n][2] = fmaf(s[n][2], sc2, b1.x * kLog2e);
-        s[n][3] = fmaf(s[n][3], sc2, b1.y * kLog2e);
+        s[n][0] = fmaf(s[n][0], sc2, b0.x);
+        s[n][1] = fmaf(s[n][1], sc2, b0.y);
+        s[n][2] = fmaf(s[n][2], sc2, b1.x);
+        s[n][3] = fmaf(s[n][3], sc2, b1.y);
         if (flagged) {
           const int j = n * 8 + tq * 2;
           if (shift_masked(t, i0, j)) s[n][0] = -INFINITY;
@@ -278,23 +280,23 @@ __global__ void __launch_bounds__(kWarps * 32) window_attn_fwd_kernel(const Attn
 // backward
 // ---------------------------------------------------------------------------------------------
 constexpr int kBwdWarpBytes = 4 * kTileBytes + kStageBytes;                      // q, k, v, dO, 16-row output staging
-constexpr int kBwdSmem = kBiasBytes + 704 + kWarps * 64 * 8 + kWarps * 2 * 64 * 4 + kWarps * kBwdWarpBytes;
+constexpr int kBwdSmem = kBiasBytes + 704 + kBwdWarps * 64 * 8 + kBwdWarps * 2 * 64 * 4 + kBwdWarps * kBwdWarpBytes;
 
-__global__ void __launch_bounds__(kWarps * 32) window_attn_bwd_kernel(const AttnArgs a) {
+__global__ void __launch_bounds__(kBwdWarps * 32) window_attn_bwd_kernel(const AttnArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, tq = lane & 3;
   float* bias_s = reinterpret_cast<float*>(smem);
   float* bins = reinterpret_cast<float*>(smem + kBiasBytes);                                    // [169] (704 B)
-  long long* rows_all = reinterpret_cast<long long*>(smem + kBiasBytes + 704);                  // [kWarps][64]
-  float* stat_all = reinterpret_cast<float*>(smem + kBiasBytes + 704 + kWarps * 64 * 8);        // [kWarps][2][64]: lse (log2), D
-  uint8_t* my = smem + kBiasBytes + 704 + kWarps * 64 * 8 + kWarps * 2 * 64 * 4 + warp * kBwdWarpBytes;
+  long long* rows_all = reinterpret_cast<long long*>(smem + kBiasBytes + 704);                  // [kBwdWarps][64]
+  float* stat_all = reinterpret_cast<float*>(smem + kBiasBytes + 704 + kBwdWarps * 64 * 8);        // [kBwdWarps][2][64]: lse (log2), D
+  uint8_t* my = smem + kBiasBytes + 704 + kBwdWarps * 64 * 8 + kBwdWarps * 2 * 64 * 4 + warp * kBwdWarpBytes;
   const uint32_t qs = smem_u32(my), ks = qs + kTileBytes, vs = ks + kTileBytes, dos = vs + kTileBytes;
   bf16* stage = reinterpret_cast<bf16*>(my + 4 * kTileBytes);
   long long* rows_s = rows_all + warp * 64;
   float* lse_s = stat_all + warp * 128;
   float* dsum_s = lse_s + 64;
-  float* slots = a.dslots + (1LL * blockIdx.x * kWarps + warp) * (kSlots * 32) + lane;          // [slot * 32]
+  float* slots = a.dslots + (1LL * blockIdx.x * kBwdWarps + warp) * (kSlots * 32) + lane;          // [slot * 32]
 
   build_bias_table(bias_s, a.pos);
   for (int i = threadIdx.x; i < kBins; i += blockDim.x) bins[i] = 0.f;
@@ -306,7 +308,7 @@ __global__ void __launch_bounds__(kWarps * 32) window_attn_bwd_kernel(const Attn
   const long long ntasks = 1LL * a.B * (a.H / kWs) * (a.W / kWs) * a.heads;
   const long long ld_qkv = 3LL * a.C;
   const float sc2 = a.scale * kLog2e;
-  for (long long task = 1LL * blockIdx.x * kWarps + warp; task < ntasks; task += 1LL * gridDim.x * kWarps) {
+  for (long long task = 1LL * blockIdx.x * kBwdWarps + warp; task < ntasks; task += 1LL * gridDim.x * kBwdWarps) {
     const Task t = decode_task(a, task);
     const bool flagged = t.ul || t.lr;
     for (int i = lane; i < 64; i += 32) {
@@ -379,10 +381,10 @@ __global__ void __launch_bounds__(kWarps * 32) window_attn_bwd_kernel(const Attn
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int ii = i + (e & 1), jj = (e < 2) ? j0 : j1;
-          float sc = fmaf(st[n][e], sc2, bias_s[ii * kBiasPitch + jj] * kLog2e);
+          float sc = fmaf(st[n][e], sc2, bias_s[ii * kBiasPitch + jj] - lse_s[ii]);
           if (flagged && shift_masked(t, ii, jj)) sc = -INFINITY;
-          p[e] = exp2f(sc - lse_s[ii]);
-          ds[e] = p[e] * (dpt[n][e] - dsum_s[ii]) * a.scale;
+          p[e] = exp2f(sc);
+          ds[e] = p[e] * (dpt[n][e] - dsum_s[ii]);          // unscaled: `scale` is applied once to the dK accumulators
         }
         pf[n][0] = pack_bf16(p[0], p[1]); pf[n][1] = pack_bf16(p[2], p[3]);
         df[n][0] = pack_bf16(ds[0], ds[1]); df[n][1] = pack_bf16(ds[2], ds[3]);
@@ -410,8 +412,9 @@ __global__ void __launch_bounds__(kWarps * 32) window_attn_bwd_kernel(const Attn
 #pragma unroll
         for (int n = 0; n < 4; ++n) {
           const float(&src)[4] = which == 0 ? dk[n] : dv[n];
-          *reinterpret_cast<uint32_t*>(stage + g * kPitch + n * 8 + tq * 2) = pack_bf16(src[0], src[1]);
-          *reinterpret_cast<uint32_t*>(stage + (g + 8) * kPitch + n * 8 + tq * 2) = pack_bf16(src[2], src[3]);
+          const float f = which == 0 ? a.scale : 1.0f;
+          *reinterpret_cast<uint32_t*>(stage + g * kPitch + n * 8 + tq * 2) = pack_bf16(src[0] * f, src[1] * f);
+          *reinterpret_cast<uint32_t*>(stage + (g + 8) * kPitch + n * 8 + tq * 2) = pack_bf16(src[2] * f, src[3] * f);
         }
         __syncwarp();
 #pragma unroll
@@ -466,8 +469,8 @@ __global__ void __launch_bounds__(kWarps * 32) window_attn_bwd_kernel(const Attn
         const float2 b0 = *reinterpret_cast<const float2*>(b0p + n * 8);
         const float2 b1 = *reinterpret_cast<const float2*>(b1p + n * 8);
         float sc[4];
-        sc[0] = fmaf(s[n][0], sc2, b0.x * kLog2e); sc[1] = fmaf(s[n][1], sc2, b0.y * kLog2e);
-        sc[2] = fmaf(s[n][2], sc2, b1.x * kLog2e); sc[3] = fmaf(s[n][3], sc2, b1.y * kLog2e);
+        sc[0] = fmaf(s[n][0], sc2, b0.x - l0); sc[1] = fmaf(s[n][1], sc2, b0.y - l0);
+        sc[2] = fmaf(s[n][2], sc2, b1.x - l1); sc[3] = fmaf(s[n][3], sc2, b1.y - l1);
         if (flagged) {
           const int j = n * 8 + tq * 2;
           if (shift_masked(t, i0, j)) sc[0] = -INFINITY;
@@ -476,14 +479,14 @@ __global__ void __launch_bounds__(kWarps * 32) window_attn_bwd_kernel(const Attn
           if (shift_masked(t, i1, j + 1)) sc[3] = -INFINITY;
         }
         float ds[4];
-        ds[0] = exp2f(sc[0] - l0) * (dp[n][0] - D0); ds[1] = exp2f(sc[1] - l0) * (dp[n][1] - D0);
-        ds[2] = exp2f(sc[2] - l1) * (dp[n][2] - D1); ds[3] = exp2f(sc[3] - l1) * (dp[n][3] - D1);
+        ds[0] = exp2f(sc[0]) * (dp[n][0] - D0); ds[1] = exp2f(sc[1]) * (dp[n][1] - D0);
+        ds[2] = exp2f(sc[2]) * (dp[n][2] - D1); ds[3] = exp2f(sc[3]) * (dp[n][3] - D1);
         if (n < 7) {     // keys 56..63 are padding; per-lane private accumulators, no atomics
 #pragma unroll
           for (int e = 0; e < 4; ++e) __stcg(sl + (n * 4 + e) * 32, sv[n * 4 + e] + ds[e]);
         }
-        df[n][0] = pack_bf16(ds[0] * a.scale, ds[1] * a.scale);
-        df[n][1] = pack_bf16(ds[2] * a.scale, ds[3] * a.scale);
+        df[n][0] = pack_bf16(ds[0], ds[1]);          // unscaled: `scale` is applied once to the dQ accumulators
+        df[n][1] = pack_bf16(ds[2], ds[3]);
       }
       float dq[4][4];
 #pragma unroll
@@ -500,8 +503,8 @@ __global__ void __launch_bounds__(kWarps * 32) window_attn_bwd_kernel(const Attn
       __syncwarp();
 #pragma unroll
       for (int n = 0; n < 4; ++n) {
-        *reinterpret_cast<uint32_t*>(stage + g * kPitch + n * 8 + tq * 2) = pack_bf16(dq[n][0], dq[n][1]);
-        *reinterpret_cast<uint32_t*>(stage + (g + 8) * kPitch + n * 8 + tq * 2) = pack_bf16(dq[n][2], dq[n][3]);
+        *reinterpret_cast<uint32_t*>(stage + g * kPitch + n * 8 + tq * 2) = pack_bf16(dq[n][0] * a.scale, dq[n][1] * a.scale);
+        *reinterpret_cast<uint32_t*>(stage + (g + 8) * kPitch + n * 8 + tq * 2) = pack_bf16(dq[n][2] * a.scale, dq[n][3] * a.scale);
       }
       __syncwarp();
 #pragma unroll
@@ -567,14 +570,14 @@ extern "C" int b200_window_attn_fwd(const void* qkv, const float* pos, void* out
 
 extern "C" int b200_window_attn_bwd_blocks(int B, int H, int W, int heads) {
   const long long ntasks = 1LL * B * (H / kWs) * (W / kWs) * heads;
-  long long blocks = (ntasks + kWarps - 1) / kWarps;
+  long long blocks = (ntasks + kBwdWarps - 1) / kBwdWarps;
   const long long cap = 1LL * b200_num_sms() * 2;
   if (blocks > cap) blocks = cap;
   return blocks < 1 ? 1 : static_cast<int>(blocks);
 }
 
 // floats per CTA of the scratch that follows the [blocks, 169] partial rows in `dpos_partial`
-extern "C" long long b200_window_attn_bwd_scratch_floats(int blocks) { return 1LL * blocks * (kBins + kWarps * kSlots * 32); }
+extern "C" long long b200_window_attn_bwd_scratch_floats(int blocks) { return 1LL * blocks * (kBins + kBwdWarps * kSlots * 32); }
 
 extern "C" int b200_window_attn_bwd(const void* qkv, const float* pos, const void* o, const float* lse, const void* dout,
                                     void* dqkv, float* dpos, float* dpos_partial, int accumulate_dpos, int B, int H, int W,
@@ -592,7 +595,7 @@ extern "C" int b200_window_attn_bwd(const void* qkv, const float* pos, const voi
   static bool attr = false;
   if (!attr) { B200_CHECK_CUDA(cudaFuncSetAttribute(window_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem)); attr = true; }
   auto st = reinterpret_cast<cudaStream_t>(stream);
-  window_attn_bwd_kernel<<<blocks, kWarps * 32, kBwdSmem, st>>>(a);
+  window_attn_bwd_kernel<<<blocks, kBwdWarps * 32, kBwdSmem, st>>>(a);
   B200_LAUNCH_CHECK();
   dpos_reduce_kernel<<<1, 192, 0, st>>>(dpos_partial, dpos, blocks, accumulate_dpos);
   B200_LAUNCH_CHECK();
