@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restri
 // register partials per thread over its rows, CTA-reduced through smem, one [3C] partial row per CTA
 // (reduced by splitk_reduce in a fixed order -> deterministic).
 template <int LPR, int MAXIT, bool WITH_RES>
-__global__ void __launch_bounds__(128) layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                                                             const float* __restrict__ gamma, const float* __restrict__ mean,
                                                             const float* __restrict__ rstd, const bf16* dres,
                                                             bf16* dx, float* __restrict__ partial,
@@ -472,15 +472,15 @@ int ln_fwd_launch(const bf16* x, const float* g, const float* b, bf16* y, float*
 template <int LPR, int MAXIT>
 int ln_bwd_launch(const bf16* dy, const bf16* x, const float* g, const float* mean, const float* rstd, const bf16* dres, bf16* dx,
                   float* partial, long long M, int C, int blocks, bool with_res, cudaStream_t st) {
-  const size_t smem = sizeof(float) * 4 * 3 * C;
+  const size_t smem = sizeof(float) * 8 * 3 * C;
   if (with_res) {
     if (smem > 48 * 1024)
       B200_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<LPR, MAXIT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    layernorm_bwd_kernel<LPR, MAXIT, true><<<blocks, 128, smem, st>>>(dy, x, g, mean, rstd, dres, dx, partial, M, C);
+    layernorm_bwd_kernel<LPR, MAXIT, true><<<blocks, 256, smem, st>>>(dy, x, g, mean, rstd, dres, dx, partial, M, C);
   } else {
     if (smem > 48 * 1024)
       B200_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<LPR, MAXIT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    layernorm_bwd_kernel<LPR, MAXIT, false><<<blocks, 128, smem, st>>>(dy, x, g, mean, rstd, dres, dx, partial, M, C);
+    layernorm_bwd_kernel<LPR, MAXIT, false><<<blocks, 256, smem, st>>>(dy, x, g, mean, rstd, dres, dx, partial, M, C);
   }
   B200_LAUNCH_CHECK();
   return B200_OK;
@@ -505,10 +505,11 @@ extern "C" int b200_layernorm_fwd(const void* x, const float* gamma, const float
   return ln_fwd_launch<32, 6>(X, gamma, beta, Y, mean, rstd, M, C, eps, st);
 }
 
+// 256-thread CTAs; each CTA ends with a cross-warp reduction and one [3C] partial row, so CTAs are kept fat (>= 256
+// rows) and their number at the resident capacity (register-limited: 4 per SM for C <= 256, 2 per SM above)
 extern "C" int b200_layernorm_bwd_blocks(long long M, int C) {
-  (void)C;
-  long long b = (M + 63) / 64;
-  const int cap = b200_num_sms() * 8;
+  long long b = (M + 255) / 256;
+  const int cap = b200_num_sms() * (C <= 256 ? 4 : 2);
   if (b > cap) b = cap;
   return b < 1 ? 1 : static_cast<int>(b);
 }
