@@ -6,8 +6,12 @@
 //  phase 1  cosine_filter_kernel: fp16 unit rows, Q block (128 queries x dim) resident in smem, gallery tiles of
 //           256 rows streamed by TMA, tcgen05.mma into two 256-column TMEM accumulators; the epilogue never
 //           writes the N x M score matrix: each thread owns one query row, compares its 256 scores per tile
-//           against a running threshold (the KP-th best so far) and appends the rare survivors to a per-row
-//           candidate list, pruned warp-cooperatively by an exact radix select when it fills.
+//           against a running threshold (max-tree over 32 scores, one compare) and appends the rare survivors to a
+//           per-row candidate list, pruned warp-cooperatively by an exact radix select if it fills.
+//           Large galleries run it twice: a first pass over 1/16 of the rows yields, per query, the score of its
+//           KP-th best row there - a threshold that can only be BELOW the KP-th best of the whole gallery, hence safe -
+//           and the second pass over the remaining rows starts from that threshold, so it appends ~16 KP rows per query
+//           instead of flooding and re-pruning its lists in every chunk.
 //  phase 2  rerank_kernel: the <= KP candidates per (query, gallery chunk) are re-scored EXACTLY - fp64 cosine from
 //           the fp32 embeddings - and sorted by (score desc, gallery index asc): the deterministic order that
 //           oracle/rank_oracle.py:topk_spec defines, so indices are bit-exact regardless of fp16 error as long as
@@ -34,7 +38,11 @@ constexpr int kThreads = 192;
 constexpr int kSmem = kMaxKB * kQSlab + kBStages * kBStage + 256 + 1024;
 
 struct FilterParams {
-  long long nq, ng;
+  long long nq;
+  long long g_begin, ng;      // gallery rows [g_begin, ng) are scanned
+  const float* tau_init;      // [nq] starting threshold per query, or null (-inf)
+  float* tau_out;             // [nq] receives the score of the KP-th best row found (chunks == 1 only), or null
+  int list_base, lists;       // this launch fills candidate lists [list_base, list_base + chunks) of `lists` per query
   int kb;                     // dim / 64
   int chunks;                 // gallery chunks
   long long chunk_rows;       // multiple of 256
@@ -43,9 +51,9 @@ struct FilterParams {
   int exclude_self;
   uint32_t idesc;
   uint2* scratch;             // [gridDim.x][128][kCap] (score bits, idx)
-  int* cand_idx;              // [q_blocks*128][chunks][kKP]
-  float* cand_score;          // [q_blocks*128][chunks][kKP] fp16-GEMM scores of the survivors (approximate)
-  int* cand_cnt;              // [q_blocks*128][chunks]
+  int* cand_idx;              // [q_blocks*128][lists][kKP]
+  float* cand_score;          // [q_blocks*128][lists][kKP] fp16-GEMM scores of the survivors (approximate)
+  int* cand_cnt;              // [q_blocks*128][lists]
 };
 
 __device__ __forceinline__ uint32_t fkey(float f) {   // order-preserving float -> uint
@@ -141,7 +149,7 @@ cosine_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 
   const int units = p.q_blocks * p.chunks;
   auto tiles_of = [&](int chunk) -> int {
-    const long long g0 = 1LL * chunk * p.chunk_rows;
+    const long long g0 = p.g_begin + 1LL * chunk * p.chunk_rows;
     const long long g1 = min(p.ng, g0 + p.chunk_rows);
     return static_cast<int>((g1 - g0 + kBN - 1) / kBN);
   };
@@ -156,7 +164,7 @@ cosine_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         for (int kb = 0; kb < p.kb; ++kb) tma_load_2d(q_base + kb * kQSlab, &tmap_q, qfull_bar, kb * kBK, qb * kBM);
         qphase ^= 1u;
         const int nt = tiles_of(chunk);
-        const long long g0 = 1LL * chunk * p.chunk_rows;
+        const long long g0 = p.g_begin + 1LL * chunk * p.chunk_rows;
         for (int t = 0; t < nt; ++t)
           for (int kb = 0; kb < p.kb; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -207,10 +215,10 @@ cosine_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       const long long qrow = 1LL * qb * kBM + row;
       const bool live = qrow < p.nq;
       const long long self_col = p.exclude_self ? (p.self_offset + qrow) : LLONG_MIN;
-      const long long g0 = 1LL * chunk * p.chunk_rows;
+      const long long g0 = p.g_begin + 1LL * chunk * p.chunk_rows;
       const long long g1 = min(p.ng, g0 + p.chunk_rows);
       const int nt = tiles_of(chunk);
-      float tau = -INFINITY;
+      float tau = (live && p.tau_init != nullptr) ? p.tau_init[qrow] : -INFINITY;
       int cnt = 0;
       for (int t = 0; t < nt; ++t) {
         mbar_wait(tfull_bar(acc), acc_phase);
@@ -223,7 +231,11 @@ cosine_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
           tmem_ld16(taddr + c, r0);
           tmem_ld16(taddr + c + 16, r1);
           tmem_ld_wait();
-          if (live) {
+          // one max-tree + one compare per 32 scores; the element-wise scan runs only for the rare groups with a survivor
+          float mx = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(r0[i]), __uint_as_float(r1[i])));
+          if (live && mx > tau) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               const float v = __uint_as_float(i < 16 ? r0[i] : r1[i - 16]);
@@ -264,10 +276,18 @@ cosine_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
           if (lane == src) cnt = m;
         }
         __syncwarp();
-        int* dst = p.cand_idx + (qrow * p.chunks + chunk) * kKP;
-        float* dsc = p.cand_score + (qrow * p.chunks + chunk) * kKP;
-        for (int i = 0; i < cnt; ++i) { const uint2 e = list[i]; dst[i] = static_cast<int>(e.y); dsc[i] = __uint_as_float(e.x); }
-        p.cand_cnt[qrow * p.chunks + chunk] = live ? cnt : 0;
+        const long long li = qrow * p.lists + p.list_base + chunk;
+        int* dst = p.cand_idx + li * kKP;
+        float* dsc = p.cand_score + li * kKP;
+        float mn = INFINITY;
+        for (int i = 0; i < cnt; ++i) {
+          const uint2 e = list[i];
+          dst[i] = static_cast<int>(e.y);
+          dsc[i] = __uint_as_float(e.x);
+          mn = fminf(mn, __uint_as_float(e.x));
+        }
+        p.cand_cnt[li] = live ? cnt : 0;
+        if (p.tau_out != nullptr && live) p.tau_out[qrow] = (cnt >= kKP) ? mn : -INFINITY;
         __syncwarp();
       }
     }
@@ -436,27 +456,51 @@ __global__ void recall_hits_kernel(const int* __restrict__ top_idx, long long nq
     if (first < ks[i]) atomicAdd(&hits[i], 1ULL);
 }
 
-struct Layout { long long scratch, cand_idx, cand_score, cand_cnt, total; int chunks; long long chunk_rows; int q_blocks; int ctas; };
+struct Layout {
+  long long scratch, cand_idx, cand_score, cand_cnt, tau, total;
+  int q_blocks, lists;
+  long long pre_rows;          // rows of the threshold pass (0 = single pass)
+  int chunks;                  // gallery chunks of the main pass
+  long long chunk_rows;
+  int ctas_pre, ctas;
+};
+
+// chunks for `rows` gallery rows: enough (q_block, chunk) units to fill the SMs ~6 times, chunks >= 16 tiles, and the unit
+// count close to a multiple of the CTA count (the units are equal-sized: a ragged last wave is pure loss)
+void pick_chunks(long long rows, int q_blocks, int sms, int* chunks, long long* chunk_rows) {
+  const long long tiles = (rows + kBN - 1) / kBN;
+  long long want = (6LL * sms + q_blocks - 1) / q_blocks;
+  const long long cap = std::max<long long>(1, std::min<long long>(tiles / 16, 31));
+  want = std::max<long long>(1, std::min(want, cap));
+  long long best = want;
+  double best_waste = 1e9;
+  for (long long c = want; c <= std::min(cap, want * 2); ++c) {
+    const long long units = c * q_blocks, ctas = std::min<long long>(units, sms);
+    const double waste = static_cast<double>((units + ctas - 1) / ctas * ctas - units) / units;
+    if (waste < best_waste - 1e-9) { best_waste = waste; best = c; }
+  }
+  const long long tpc = (tiles + best - 1) / best;
+  *chunk_rows = tpc * kBN;
+  *chunks = static_cast<int>((tiles + tpc - 1) / tpc);
+}
 
 Layout plan_layout(long long nq, long long ng) {
   Layout L;
   L.q_blocks = static_cast<int>((nq + kBM - 1) / kBM);
   const int sms = b200_num_sms();
-  const long long tiles = (ng + kBN - 1) / kBN;
-  long long chunks = (6LL * sms + L.q_blocks - 1) / L.q_blocks;          // aim for >= 6 units per SM
-  chunks = std::min<long long>(chunks, std::max<long long>(1, tiles / 16)); // but keep chunks >= 16 tiles (4096 rows)
-  chunks = std::max<long long>(1, std::min<long long>(chunks, 32));
-  const long long tiles_per_chunk = (tiles + chunks - 1) / chunks;
-  L.chunk_rows = tiles_per_chunk * kBN;
-  L.chunks = static_cast<int>((tiles + tiles_per_chunk - 1) / tiles_per_chunk);
-  const long long units = 1LL * L.q_blocks * L.chunks;
-  L.ctas = static_cast<int>(std::min<long long>(units, sms));
+  L.pre_rows = 0;
+  if (ng >= 16LL * 4096) L.pre_rows = (ng / 16 + kBN - 1) / kBN * kBN;      // threshold pass over the first 1/16 of the rows
+  pick_chunks(ng - L.pre_rows, L.q_blocks, sms, &L.chunks, &L.chunk_rows);
+  L.lists = L.chunks + (L.pre_rows ? 1 : 0);
+  L.ctas_pre = std::min(L.q_blocks, sms);
+  L.ctas = static_cast<int>(std::min<long long>(1LL * L.q_blocks * L.chunks, sms));
   long long off = 0;
   auto take = [&](long long bytes) { long long o = off; off = (off + bytes + 255) / 256 * 256; return o; };
   L.scratch = take(1LL * sms * kBM * kCap * 8);
-  L.cand_idx = take(1LL * L.q_blocks * kBM * L.chunks * kKP * 4);
-  L.cand_score = take(1LL * L.q_blocks * kBM * L.chunks * kKP * 4);
-  L.cand_cnt = take(1LL * L.q_blocks * kBM * L.chunks * 4);
+  L.cand_idx = take(1LL * L.q_blocks * kBM * L.lists * kKP * 4);
+  L.cand_score = take(1LL * L.q_blocks * kBM * L.lists * kKP * 4);
+  L.cand_cnt = take(1LL * L.q_blocks * kBM * L.lists * 4);
+  L.tau = take(1LL * L.q_blocks * kBM * 4);
   L.total = off;
   return L;
 }
@@ -493,12 +537,12 @@ extern "C" int b200_cosine_topk(const float* q, const void* q_unit_f16, const do
     return b200_set_error(B200_ERR_INVALID, "cosine_topk: empty gallery");
   }
   const Layout L = plan_layout(nq, ng);
-  B200_REQUIRE(L.chunks <= 64, "cosine_topk: too many chunks");
+  B200_REQUIRE(L.lists <= 64, "cosine_topk: too many candidate lists");
   if (workspace_bytes < L.total)
     return b200_set_error(B200_ERR_WORKSPACE, "cosine_topk: workspace %lld < required %lld bytes", workspace_bytes, L.total);
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   FilterParams p;
-  p.nq = nq; p.ng = ng; p.kb = dim / kBK; p.chunks = L.chunks; p.chunk_rows = L.chunk_rows; p.q_blocks = L.q_blocks;
+  p.nq = nq; p.kb = dim / kBK; p.q_blocks = L.q_blocks; p.lists = L.lists;
   p.exclude_self = exclude_self_offset != B200_NO_EXCLUDE;
   p.self_offset = p.exclude_self ? exclude_self_offset : 0;
   p.idesc = gemm::make_idesc(false, kBN);
@@ -506,6 +550,7 @@ extern "C" int b200_cosine_topk(const float* q, const void* q_unit_f16, const do
   p.cand_idx = reinterpret_cast<int*>(ws + L.cand_idx);
   p.cand_score = reinterpret_cast<float*>(ws + L.cand_score);
   p.cand_cnt = reinterpret_cast<int*>(ws + L.cand_cnt);
+  float* tau = reinterpret_cast<float*>(ws + L.tau);
   CUtensorMap tq, tg;
   int rc = gemm::encode_tmap_2d(&tq, false, q_unit_f16, dim, nq, dim, kBK, kBM);
   if (rc) return rc;
@@ -513,13 +558,21 @@ extern "C" int b200_cosine_topk(const float* q, const void* q_unit_f16, const do
   if (rc) return rc;
   static bool attr = false;
   if (!attr) { B200_CHECK_CUDA(cudaFuncSetAttribute(cosine_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem)); attr = true; }
+  if (L.pre_rows > 0) {      // threshold pass: one chunk, exact streaming top-KP of the first rows
+    p.g_begin = 0; p.ng = L.pre_rows; p.chunks = 1; p.chunk_rows = L.pre_rows; p.list_base = 0;
+    p.tau_init = nullptr; p.tau_out = tau;
+    cosine_filter_kernel<<<L.ctas_pre, kThreads, kSmem, st>>>(tq, tg, p);
+    B200_LAUNCH_CHECK();
+  }
+  p.g_begin = L.pre_rows; p.ng = ng; p.chunks = L.chunks; p.chunk_rows = L.chunk_rows; p.list_base = L.pre_rows ? 1 : 0;
+  p.tau_init = L.pre_rows ? tau : nullptr; p.tau_out = nullptr;
   cosine_filter_kernel<<<L.ctas, kThreads, kSmem, st>>>(tq, tg, p);
   B200_LAUNCH_CHECK();
   int n_pow2 = 1;
-  while (n_pow2 < L.chunks * kKP) n_pow2 <<= 1;
+  while (n_pow2 < L.lists * kKP) n_pow2 <<= 1;
   const int smem2 = n_pow2 * static_cast<int>(sizeof(Cand));
   if (smem2 > 48 * 1024) B200_CHECK_CUDA(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
-  rerank_kernel<<<static_cast<unsigned>(nq), 256, smem2, st>>>(q, q_norm, g, g_norm, dim, p.cand_idx, p.cand_score, p.cand_cnt, L.chunks, n_pow2, k,
+  rerank_kernel<<<static_cast<unsigned>(nq), 256, smem2, st>>>(q, q_norm, g, g_norm, dim, p.cand_idx, p.cand_score, p.cand_cnt, L.lists, n_pow2, k,
                                                                g_index_base, out_idx, out_score);
   B200_LAUNCH_CHECK();
   return B200_OK;
