@@ -295,8 +295,8 @@ def gpu_arm(args, rank, world, local_rank):
 
 def gallery_leg(args, rank, world, device):
     """Second half of BASELINE.json's metric: gallery queries/s (configs[3] shape, bounded): every rank holds a gallery shard of
-    1M / 8 = 125k x 512 rows (the per-GPU share of config 4) and matches `--gallery-queries` queries against it with the fused
-    cosine + top-100 kernel; value = queries/s against the FULL gallery of world * 125k rows (all ranks work in parallel on
+    1M / 8 = 125k x 512 rows (the per-GPU share of config 4) and matches all `--gallery-queries` (50k) queries against it with the
+    fused cosine + top-100 kernel; value = queries/s against the FULL gallery of world * 125k rows (all ranks work in parallel on
     their shards; the merge of the partial lists is included for world > 1)."""
     import torch.distributed as dist
     from b200 import gallery
@@ -346,7 +346,7 @@ def main():
     ap.add_argument('--batch', type=int, default=256)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-gallery', action='store_true')
-    ap.add_argument('--gallery-queries', type=int, default=8192)
+    ap.add_argument('--gallery-queries', type=int, default=50000)
     ap.add_argument('--gallery-rows', type=int, default=125000)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup

@@ -287,7 +287,8 @@ cosine_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
           mn = fminf(mn, __uint_as_float(e.x));
         }
         p.cand_cnt[li] = live ? cnt : 0;
-        if (p.tau_out != nullptr && live) p.tau_out[qrow] = (cnt >= kKP) ? mn : -INFINITY;
+        if (p.tau_out != nullptr && live)      // KP-th best of the rows seen so far: a lower bound of the KP-th best overall
+          p.tau_out[qrow] = (cnt >= kKP) ? mn : (p.tau_init != nullptr ? p.tau_init[qrow] : -INFINITY);
         __syncwarp();
       }
     }
@@ -349,10 +350,40 @@ __global__ void __launch_bounds__(256) rerank_kernel(const float* __restrict__ q
     }
   }
   __syncthreads();
-  // level 1: the survivors of all gallery chunks, ranked by their approximate (fp16 tensor-core) score; only the best
-  // kKP overall can contain the exact top-k (same k + 28 slack argument as inside a chunk)
+  // level 1: of the survivors of all passes / chunks only the best kKP by approximate (fp16 tensor-core) score can contain
+  // the exact top-k (same k + 28 slack argument as inside a chunk).  Exact 64-bit radix select on the unique key
+  // (score desc, index asc) - O(n) per bit instead of sorting thousands of candidates.
   if (total > kKP) {
-    bitonic_sort(cands, n_pow2);
+    __shared__ int s_cnt[8];
+    __shared__ int s_slot;
+    unsigned long long thr = 0ULL;
+    auto key_of = [&](int i) -> unsigned long long {
+      return (static_cast<unsigned long long>(fkey(static_cast<float>(cands[i].score))) << 32) |
+             static_cast<unsigned long long>(0xffffffffu - static_cast<uint32_t>(cands[i].idx));
+    };
+#pragma unroll 1
+    for (int bit = 63; bit >= 0; --bit) {
+      const unsigned long long cand = thr | (1ULL << bit);
+      int c = 0;
+      for (int i = threadIdx.x; i < total; i += blockDim.x) c += (key_of(i) >= cand) ? 1 : 0;
+      c = __reduce_add_sync(0xffffffffu, c);
+      if (lane == 0) s_cnt[warp] = c;
+      __syncthreads();
+      int t = 0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += s_cnt[w];
+      if (t >= kKP) thr = cand;
+      __syncthreads();
+    }
+    // keys are unique, so exactly kKP candidates have key >= thr: move them to the front of a second array
+    Cand* sel = cands + n_pow2;
+    if (threadIdx.x == 0) s_slot = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < total; i += blockDim.x)
+      if (key_of(i) >= thr) { const int slot = atomicAdd(&s_slot, 1); sel[slot] = cands[i]; }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kKP; i += blockDim.x) cands[i] = sel[i];
+    __syncthreads();
     total = kKP;
     for (int i = kKP + threadIdx.x; i < n_pow2; i += blockDim.x) { cands[i].score = -INFINITY; cands[i].idx = INT_MAX; }
     __syncthreads();
@@ -459,7 +490,8 @@ __global__ void recall_hits_kernel(const int* __restrict__ top_idx, long long nq
 struct Layout {
   long long scratch, cand_idx, cand_score, cand_cnt, tau, total;
   int q_blocks, lists;
-  long long pre_rows;          // rows of the threshold pass (0 = single pass)
+  long long pre0_rows;         // rows [0, pre0_rows): seed pass (floods its lists, tiny)
+  long long pre_rows;          // rows [pre0_rows, pre_rows): threshold pass (0 = single pass over everything)
   int chunks;                  // gallery chunks of the main pass
   long long chunk_rows;
   int ctas_pre, ctas;
@@ -488,10 +520,13 @@ Layout plan_layout(long long nq, long long ng) {
   Layout L;
   L.q_blocks = static_cast<int>((nq + kBM - 1) / kBM);
   const int sms = b200_num_sms();
-  L.pre_rows = 0;
-  if (ng >= 16LL * 4096) L.pre_rows = (ng / 16 + kBN - 1) / kBN * kBN;      // threshold pass over the first 1/16 of the rows
+  L.pre_rows = L.pre0_rows = 0;
+  if (ng >= 16LL * 4096) {                                                   // thresholds from the first 1/16 of the rows,
+    L.pre_rows = (ng / 16 + kBN - 1) / kBN * kBN;                            // itself seeded from the first 1024 rows
+    L.pre0_rows = 4 * kBN;
+  }
   pick_chunks(ng - L.pre_rows, L.q_blocks, sms, &L.chunks, &L.chunk_rows);
-  L.lists = L.chunks + (L.pre_rows ? 1 : 0);
+  L.lists = L.chunks + (L.pre_rows ? 2 : 0);
   L.ctas_pre = std::min(L.q_blocks, sms);
   L.ctas = static_cast<int>(std::min<long long>(1LL * L.q_blocks * L.chunks, sms));
   long long off = 0;
@@ -558,19 +593,22 @@ extern "C" int b200_cosine_topk(const float* q, const void* q_unit_f16, const do
   if (rc) return rc;
   static bool attr = false;
   if (!attr) { B200_CHECK_CUDA(cudaFuncSetAttribute(cosine_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem)); attr = true; }
-  if (L.pre_rows > 0) {      // threshold pass: one chunk, exact streaming top-KP of the first rows
-    p.g_begin = 0; p.ng = L.pre_rows; p.chunks = 1; p.chunk_rows = L.pre_rows; p.list_base = 0;
+  if (L.pre_rows > 0) {      // threshold passes: one chunk each, exact streaming top-KP of the rows they scan
+    p.g_begin = 0; p.ng = L.pre0_rows; p.chunks = 1; p.chunk_rows = L.pre0_rows; p.list_base = 0;
     p.tau_init = nullptr; p.tau_out = tau;
     cosine_filter_kernel<<<L.ctas_pre, kThreads, kSmem, st>>>(tq, tg, p);
     B200_LAUNCH_CHECK();
+    p.g_begin = L.pre0_rows; p.ng = L.pre_rows; p.chunk_rows = L.pre_rows - L.pre0_rows; p.list_base = 1;
+    p.tau_init = tau; p.tau_out = tau;
+    cosine_filter_kernel<<<L.ctas_pre, kThreads, kSmem, st>>>(tq, tg, p);
+    B200_LAUNCH_CHECK();
   }
-  p.g_begin = L.pre_rows; p.ng = ng; p.chunks = L.chunks; p.chunk_rows = L.chunk_rows; p.list_base = L.pre_rows ? 1 : 0;
+  p.g_begin = L.pre_rows; p.ng = ng; p.chunks = L.chunks; p.chunk_rows = L.chunk_rows; p.list_base = L.pre_rows ? 2 : 0;
   p.tau_init = L.pre_rows ? tau : nullptr; p.tau_out = nullptr;
   cosine_filter_kernel<<<L.ctas, kThreads, kSmem, st>>>(tq, tg, p);
   B200_LAUNCH_CHECK();
-  int n_pow2 = 1;
-  while (n_pow2 < L.lists * kKP) n_pow2 <<= 1;
-  const int smem2 = n_pow2 * static_cast<int>(sizeof(Cand));
+  const int n_pow2 = L.lists * kKP;        // candidate capacity per query (the name is historical: no power of two needed)
+  const int smem2 = (n_pow2 + kKP) * static_cast<int>(sizeof(Cand));
   if (smem2 > 48 * 1024) B200_CHECK_CUDA(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
   rerank_kernel<<<static_cast<unsigned>(nq), 256, smem2, st>>>(q, q_norm, g, g_norm, dim, p.cand_idx, p.cand_score, p.cand_cnt, L.lists, n_pow2, k,
                                                                g_index_base, out_idx, out_score);
