@@ -325,47 +325,45 @@ __device__ void bitonic_sort(Cand* c, int n_pow2) {
 __global__ void __launch_bounds__(256) rerank_kernel(const float* __restrict__ q, const double* __restrict__ q_norm,
                                                      const float* __restrict__ g, const double* __restrict__ g_norm, int dim,
                                                      const int* __restrict__ cand_idx, const float* __restrict__ cand_score,
-                                                     const int* __restrict__ cand_cnt, int chunks, int n_pow2, int k,
+                                                     const int* __restrict__ cand_cnt, int lists, int cap, int k,
                                                      long long g_index_base, int* __restrict__ out_idx, double* __restrict__ out_score) {
   extern __shared__ __align__(16) uint8_t sm[];
-  Cand* cands = reinterpret_cast<Cand*>(sm);
+  Cand* sel = reinterpret_cast<Cand*>(sm);                                                     // [kKP] exact stage
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(sm + kKP * sizeof(Cand));   // [cap] approximate stage
   __shared__ int s_off[64];
   __shared__ int s_total;
+  __shared__ int s_cnt[8];
+  __shared__ int s_slot;
   const long long qi = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     int t = 0;
-    for (int c = 0; c < chunks; ++c) { s_off[c] = t; t += cand_cnt[qi * chunks + c]; }
+    for (int c = 0; c < lists; ++c) { s_off[c] = t; t += cand_cnt[qi * lists + c]; }
     s_total = t;
+    s_slot = 0;
   }
+  for (int i = threadIdx.x; i < kKP; i += blockDim.x) { sel[i].score = -INFINITY; sel[i].idx = INT_MAX; }
   __syncthreads();
   int total = s_total;
-  for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) { cands[i].score = -INFINITY; cands[i].idx = INT_MAX; }
-  __syncthreads();
-  for (int c = 0; c < chunks; ++c) {
-    const int n = cand_cnt[qi * chunks + c];
+  // unique order-preserving key: (approximate score desc, gallery index asc)  ==  larger key first
+  for (int c = 0; c < lists; ++c) {
+    const int n = cand_cnt[qi * lists + c];
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      cands[s_off[c] + i].idx = cand_idx[(qi * chunks + c) * kKP + i];
-      cands[s_off[c] + i].score = static_cast<double>(cand_score[(qi * chunks + c) * kKP + i]);
+      const long long src = (qi * lists + c) * kKP + i;
+      keys[s_off[c] + i] = (static_cast<unsigned long long>(fkey(cand_score[src])) << 32) |
+                           static_cast<unsigned long long>(0xffffffffu - static_cast<uint32_t>(cand_idx[src]));
     }
   }
   __syncthreads();
   // level 1: of the survivors of all passes / chunks only the best kKP by approximate (fp16 tensor-core) score can contain
-  // the exact top-k (same k + 28 slack argument as inside a chunk).  Exact 64-bit radix select on the unique key
-  // (score desc, index asc) - O(n) per bit instead of sorting thousands of candidates.
+  // the exact top-k (same k + 28 slack argument as inside a chunk): exact 64-bit radix select, O(n) per bit
+  unsigned long long thr = 0ULL;
   if (total > kKP) {
-    __shared__ int s_cnt[8];
-    __shared__ int s_slot;
-    unsigned long long thr = 0ULL;
-    auto key_of = [&](int i) -> unsigned long long {
-      return (static_cast<unsigned long long>(fkey(static_cast<float>(cands[i].score))) << 32) |
-             static_cast<unsigned long long>(0xffffffffu - static_cast<uint32_t>(cands[i].idx));
-    };
 #pragma unroll 1
     for (int bit = 63; bit >= 0; --bit) {
       const unsigned long long cand = thr | (1ULL << bit);
       int c = 0;
-      for (int i = threadIdx.x; i < total; i += blockDim.x) c += (key_of(i) >= cand) ? 1 : 0;
+      for (int i = threadIdx.x; i < total; i += blockDim.x) c += (keys[i] >= cand) ? 1 : 0;
       c = __reduce_add_sync(0xffffffffu, c);
       if (lane == 0) s_cnt[warp] = c;
       __syncthreads();
@@ -375,24 +373,16 @@ __global__ void __launch_bounds__(256) rerank_kernel(const float* __restrict__ q
       if (t >= kKP) thr = cand;
       __syncthreads();
     }
-    // keys are unique, so exactly kKP candidates have key >= thr: move them to the front of a second array
-    Cand* sel = cands + n_pow2;
-    if (threadIdx.x == 0) s_slot = 0;
-    __syncthreads();
-    for (int i = threadIdx.x; i < total; i += blockDim.x)
-      if (key_of(i) >= thr) { const int slot = atomicAdd(&s_slot, 1); sel[slot] = cands[i]; }
-    __syncthreads();
-    for (int i = threadIdx.x; i < kKP; i += blockDim.x) cands[i] = sel[i];
-    __syncthreads();
-    total = kKP;
-    for (int i = kKP + threadIdx.x; i < n_pow2; i += blockDim.x) { cands[i].score = -INFINITY; cands[i].idx = INT_MAX; }
-    __syncthreads();
   }
+  for (int i = threadIdx.x; i < total; i += blockDim.x)       // keys are unique: exactly min(total, kKP) pass
+    if (keys[i] >= thr) sel[atomicAdd(&s_slot, 1)].idx = static_cast<int>(0xffffffffu - static_cast<uint32_t>(keys[i] & 0xffffffffULL));
+  __syncthreads();
+  total = min(total, kKP);
   // level 2: exact fp64 cosine of those <= kKP candidates from the fp32 embeddings
   const float* qr = q + qi * dim;
   const double nq = fmax(q_norm[qi], 1e-8);
   for (int i = warp; i < total; i += blockDim.x >> 5) {
-    const int gi = cands[i].idx;
+    const int gi = sel[i].idx;
     const float* gr = g + 1LL * gi * dim;
     double acc = 0.0;
     for (int d = lane * 4; d < dim; d += 128) {
@@ -405,16 +395,14 @@ __global__ void __launch_bounds__(256) rerank_kernel(const float* __restrict__ q
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) cands[i].score = acc / (nq * fmax(g_norm[gi], 1e-8));
+    if (lane == 0) sel[i].score = acc / (nq * fmax(g_norm[gi], 1e-8));
   }
   __syncthreads();
-  int m = 1;
-  while (m < total) m <<= 1;              // <= kKP; entries [total, m) are -inf padding
-  bitonic_sort(cands, m);
+  bitonic_sort(sel, kKP);
   for (int i = threadIdx.x; i < k; i += blockDim.x) {
     const bool ok = i < total;
-    out_idx[qi * k + i] = ok ? static_cast<int>(cands[i].idx + g_index_base) : -1;
-    out_score[qi * k + i] = ok ? cands[i].score : -INFINITY;
+    out_idx[qi * k + i] = ok ? static_cast<int>(sel[i].idx + g_index_base) : -1;
+    out_score[qi * k + i] = ok ? sel[i].score : -INFINITY;
   }
 }
 
@@ -607,8 +595,8 @@ extern "C" int b200_cosine_topk(const float* q, const void* q_unit_f16, const do
   p.tau_init = L.pre_rows ? tau : nullptr; p.tau_out = nullptr;
   cosine_filter_kernel<<<L.ctas, kThreads, kSmem, st>>>(tq, tg, p);
   B200_LAUNCH_CHECK();
-  const int n_pow2 = L.lists * kKP;        // candidate capacity per query (the name is historical: no power of two needed)
-  const int smem2 = (n_pow2 + kKP) * static_cast<int>(sizeof(Cand));
+  const int n_pow2 = L.lists * kKP;        // candidate capacity per query
+  const int smem2 = kKP * static_cast<int>(sizeof(Cand)) + n_pow2 * 8;
   if (smem2 > 48 * 1024) B200_CHECK_CUDA(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
   rerank_kernel<<<static_cast<unsigned>(nq), 256, smem2, st>>>(q, q_norm, g, g_norm, dim, p.cand_idx, p.cand_score, p.cand_cnt, L.lists, n_pow2, k,
                                                                g_index_base, out_idx, out_score);
