@@ -15,6 +15,7 @@ namespace {
 // one warp per row: fp32 [R, E] -> unit bf16 rows (+ 1/max(|x|, eps))
 __global__ void __launch_bounds__(256) unit_rows_kernel(const float* __restrict__ x, bf16* __restrict__ out, float* __restrict__ inv_norm,
                                                         long long R, int E, long long ld_out, float eps, int as_f16) {
+  pdl_grid_sync();
   const long long row = (1LL * blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= R) return;
@@ -52,6 +53,7 @@ __global__ void __launch_bounds__(256) margin_ce_kernel(const float* __restrict_
                                                         const float* __restrict__ cos_label, int B, int C, float s, float cos_m, float sin_m,
                                                         float th, int kind, int easy, float gamma, float* __restrict__ loss_rows,
                                                         bf16* __restrict__ G, long long ldg, float* __restrict__ rdot) {
+  pdl_grid_sync();
   __shared__ float red[8];
   const int b = blockIdx.x;
   const float* lr = logits + 1LL * b * ldl;
@@ -102,6 +104,7 @@ __global__ void __launch_bounds__(256) margin_ce_kernel(const float* __restrict_
 __global__ void margin_coldot_kernel(const bf16* __restrict__ G, long long ldg, const float* __restrict__ logits, long long ldl,
                                      const long long* __restrict__ label, const float* __restrict__ cos_label, int B, int C, float s,
                                      float* __restrict__ cdot) {
+  pdl_grid_sync();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float acc = 0.f;
@@ -113,6 +116,7 @@ __global__ void margin_coldot_kernel(const bf16* __restrict__ G, long long ldg, 
 }
 
 __global__ void mean_kernel(const float* __restrict__ x, int n, float* __restrict__ out) {
+  pdl_grid_sync();
   __shared__ float red[8];
   float a = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) a += x[i];
@@ -125,6 +129,7 @@ __global__ void __launch_bounds__(256) unit_rows_bwd_kernel(const float* __restr
                                                             const float* __restrict__ inv_norm, const float* __restrict__ dot,
                                                             const float* __restrict__ scale_ptr, float* __restrict__ out_f32,
                                                             bf16* __restrict__ out_bf16, long long R, int E, int accumulate) {
+  pdl_grid_sync();
   const long long row = (1LL * blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= R) return;
@@ -155,7 +160,7 @@ extern "C" int b200_unit_rows(const float* x, void* out, float* inv_norm, long l
   B200_REQUIRE(E % 4 == 0 && ld_out % 4 == 0, "unit_rows: E and ld_out must be multiples of 4");
   if (R == 0) return B200_OK;
   const long long blocks = (R * 32 + 255) / 256;
-  unit_rows_kernel<<<static_cast<unsigned>(blocks), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_pdl(unit_rows_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       x, reinterpret_cast<bf16*>(out), inv_norm, R, E, ld_out, eps, as_f16);
   B200_LAUNCH_CHECK();
   return B200_OK;
@@ -167,15 +172,15 @@ extern "C" int b200_margin_ce(const float* logits, long long ldl, const long lon
   if (B == 0) return B200_OK;
   auto st = reinterpret_cast<cudaStream_t>(stream);
   const double md = m, pi = 3.14159265358979323846;
-  margin_ce_kernel<<<B, 256, 0, st>>>(logits, ldl, label, cos_label, B, C, s, (float)cos(md), (float)sin(md), (float)cos(pi - md), kind,
+  launch_pdl(margin_ce_kernel, dim3(B), dim3(256), 0, st, logits, ldl, label, cos_label, B, C, s, (float)cos(md), (float)sin(md), (float)cos(pi - md), kind,
                                       easy_margin, gamma, loss_rows, reinterpret_cast<bf16*>(G), ldg, rdot);
   B200_LAUNCH_CHECK();
   if (loss_mean) {
-    mean_kernel<<<1, 256, 0, st>>>(loss_rows, B, loss_mean);
+    launch_pdl(mean_kernel, dim3(1), dim3(256), 0, st, loss_rows, B, loss_mean);
     B200_LAUNCH_CHECK();
   }
   if (G != nullptr && cdot != nullptr) {
-    margin_coldot_kernel<<<(C + 255) / 256, 256, 0, st>>>(reinterpret_cast<const bf16*>(G), ldg, logits, ldl, label, cos_label, B, C, s, cdot);
+    launch_pdl(margin_coldot_kernel, dim3((C + 255) / 256), dim3(256), 0, st, reinterpret_cast<const bf16*>(G), ldg, logits, ldl, label, cos_label, B, C, s, cdot);
     B200_LAUNCH_CHECK();
   }
   return B200_OK;
@@ -186,7 +191,7 @@ extern "C" int b200_unit_rows_bwd(const float* T, const float* x, const float* i
   B200_REQUIRE(E % 4 == 0, "unit_rows_bwd: E must be a multiple of 4");
   if (R == 0) return B200_OK;
   const long long blocks = (R * 32 + 255) / 256;
-  unit_rows_bwd_kernel<<<static_cast<unsigned>(blocks), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_pdl(unit_rows_bwd_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       T, x, inv_norm, dot, scale_dev, out_f32, reinterpret_cast<bf16*>(out_bf16), R, E, accumulate);
   B200_LAUNCH_CHECK();
   return B200_OK;

@@ -161,9 +161,10 @@ __global__ void __launch_bounds__(kWarps * 32) window_attn_fwd_kernel(const Attn
   const uint32_t qs = smem_u32(my), ks = qs + kTileBytes, vs = ks + kTileBytes;
   long long* rows_s = rows_all + warp * 64;
 
-  build_bias_table(bias_s, a.pos);
+  build_bias_table(bias_s, a.pos);      // pos is a parameter: not produced by the preceding kernel
   for (int i = lane; i < kFwdWarpBytes / 16; i += 32) reinterpret_cast<uint4*>(my)[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
+  pdl_grid_sync();
 
   const long long ntasks = 1LL * a.B * (a.H / kWs) * (a.W / kWs) * a.heads;
   const long long ld_qkv = 3LL * a.C;
@@ -304,6 +305,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32) window_attn_bwd_kernel(const A
 #pragma unroll 4
   for (int sl = 0; sl < kSlots; ++sl) __stcg(slots + sl * 32, 0.f);
   __syncthreads();
+  pdl_grid_sync();
 
   const long long ntasks = 1LL * a.B * (a.H / kWs) * (a.W / kWs) * a.heads;
   const long long ld_qkv = 3LL * a.C;
@@ -534,6 +536,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32) window_attn_bwd_kernel(const A
 }
 
 __global__ void dpos_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, int blocks, int accumulate) {
+  pdl_grid_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= kBins) return;
   float acc = accumulate ? out[i] : 0.f;
@@ -563,7 +566,7 @@ extern "C" int b200_window_attn_fwd(const void* qkv, const float* pos, void* out
   long long blocks = (ntasks + kWarps - 1) / kWarps;
   const long long cap = 1LL * b200_num_sms() * 3 * 2;     // 3 resident CTAs per SM, 2 waves (the bias table is built per CTA)
   if (blocks > cap) blocks = cap;
-  window_attn_fwd_kernel<<<static_cast<unsigned>(blocks), kWarps * 32, kFwdSmem, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  launch_pdl(window_attn_fwd_kernel, dim3(static_cast<unsigned>(blocks)), dim3(kWarps * 32), kFwdSmem, reinterpret_cast<cudaStream_t>(stream), a);
   B200_LAUNCH_CHECK();
   return B200_OK;
 }
@@ -595,9 +598,9 @@ extern "C" int b200_window_attn_bwd(const void* qkv, const float* pos, const voi
   static bool attr = false;
   if (!attr) { B200_CHECK_CUDA(cudaFuncSetAttribute(window_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem)); attr = true; }
   auto st = reinterpret_cast<cudaStream_t>(stream);
-  window_attn_bwd_kernel<<<blocks, kBwdWarps * 32, kBwdSmem, st>>>(a);
+  launch_pdl(window_attn_bwd_kernel, dim3(blocks), dim3(kBwdWarps * 32), kBwdSmem, st, a);
   B200_LAUNCH_CHECK();
-  dpos_reduce_kernel<<<1, 192, 0, st>>>(dpos_partial, dpos, blocks, accumulate_dpos);
+  launch_pdl(dpos_reduce_kernel, dim3(1), dim3(192), 0, st, dpos_partial, dpos, blocks, accumulate_dpos);
   B200_LAUNCH_CHECK();
   return B200_OK;
 }

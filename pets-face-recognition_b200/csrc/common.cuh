@@ -10,6 +10,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <utility>
 
 // ---------------------------------------------------------------------------------------------
 // error plumbing: every extern "C" entry returns 0 or a negative code; text via b200_last_error()
@@ -44,6 +45,34 @@ void b200_count_launch();
     b200_count_launch();                       \
     B200_CHECK_CUDA(cudaGetLastError());       \
   } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch: every kernel of the library is launched with the stream-serialisation attribute and
+// starts with pdl_grid_sync() - griddepcontrol.wait (block until the previous kernel in the stream has completed and its
+// memory is visible) followed by griddepcontrol.launch_dependents (let the next kernel's CTAs be scheduled as SMs drain).
+// Placed after a kernel's data-independent prologue (barrier init, TMEM allocation, smem tables), this hides launch
+// latency and the ramp-down / ramp-up bubbles between the ~500 kernels of a training step.
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_grid_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(std::forward<Args>(args))...);
+}
+#endif
 
 int b200_num_sms();   // cached cudaDevAttrMultiProcessorCount of the current device (148 on B200)
 // out[i] (+)= sum_s partial[s * stride + i], i < n, fixed order (deterministic); stride <= 0 means n

@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restri
                                                             const float* __restrict__ beta, bf16* __restrict__ y,
                                                             float* __restrict__ mean, float* __restrict__ rstd,
                                                             long long M, int C, float eps) {
+  pdl_grid_sync();
   constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & 31;
   const int sub = lane / LPR, l = lane % LPR;
@@ -116,6 +117,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restri
                                                             const float* __restrict__ rstd, const bf16* dres,
                                                             bf16* dx, float* __restrict__ partial,
                                                             long long M, int C) {
+  pdl_grid_sync();
   constexpr int RPW = 32 / LPR;
   extern __shared__ float red[];   // [warps][3][C]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -220,6 +222,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restri
 // stage 1: fp32 NCHW image, df = 4 -> one thread per (output row, c, kh): float4 in, 4 bf16 out
 __global__ void patch_gather_image_kernel(const float* __restrict__ img, bf16* __restrict__ out, int B, int Cin, int H, int W,
                                           int df, int ldo) {
+  pdl_grid_sync();
   const int Ho = H / df, Wo = W / df;
   const int per_row = Cin * df;                       // (c, kh) pairs, each df(=4) contiguous kw
   const long long total = 1LL * B * Ho * Wo * per_row;
@@ -242,6 +245,7 @@ __global__ void patch_gather_image_kernel(const float* __restrict__ img, bf16* _
 // backward (scatter == exact inverse, every input pixel appears once) uses the same indexing.
 template <bool BACKWARD>
 __global__ void patch_gather_nhwc_kernel(bf16* __restrict__ x, bf16* __restrict__ cols, int B, int H, int W, int C) {
+  pdl_grid_sync();
   const int Ho = H / 2, Wo = W / 2, cp = C / 2;
   const long long total = 1LL * B * Ho * Wo * cp;
   for (long long idx = 1LL * blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += 1LL * gridDim.x * blockDim.x) {
@@ -276,6 +280,7 @@ __global__ void patch_gather_nhwc_kernel(bf16* __restrict__ x, bf16* __restrict_
 // spatial mean (models/swin.py:224) and its backward (broadcast / T)
 // ---------------------------------------------------------------------------------------------
 __global__ void mean_pool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int B, int T, int C) {
+  pdl_grid_sync();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * (C / 2)) return;
   const int c2 = idx % (C / 2), b = idx / (C / 2);
@@ -287,6 +292,7 @@ __global__ void mean_pool_fwd_kernel(const bf16* __restrict__ x, bf16* __restric
   *reinterpret_cast<bf162*>(y + 1LL * b * C + c2 * 2) = __floats2bfloat162_rn(a0 / T, a1 / T);
 }
 __global__ void mean_pool_bwd_kernel(const bf16* __restrict__ dy, bf16* __restrict__ dx, int B, int T, int C) {
+  pdl_grid_sync();
   const long long idx = 1LL * blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= 1LL * B * T * (C / 2)) return;
   const int c2 = static_cast<int>(idx % (C / 2));
@@ -300,6 +306,7 @@ __global__ void mean_pool_bwd_kernel(const bf16* __restrict__ dy, bf16* __restri
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) transpose16_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out,
                                                           long long R, int Cc, long long ld_in, long long ld_out) {
+  pdl_grid_sync();
   __shared__ uint16_t tile[64][66];
   const long long r0 = 64LL * blockIdx.x;
   const int c0 = 64 * blockIdx.y;
@@ -327,6 +334,7 @@ __global__ void __launch_bounds__(256) transpose16_kernel(const uint16_t* __rest
 // fp32 [R, Cc] -> bf16 [R, Cc] (dst) and/or bf16 [Cc, R] (dst_t).  Used for weights (small).
 __global__ void __launch_bounds__(256) cast_transpose_kernel(const float* __restrict__ in, bf16* __restrict__ dst,
                                                              bf16* __restrict__ dst_t, int R, int Cc) {
+  pdl_grid_sync();
   __shared__ float tile[32][33];
   const int r0 = 32 * blockIdx.x, c0 = 32 * blockIdx.y;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -355,6 +363,7 @@ __global__ void __launch_bounds__(256) cast_transpose_kernel(const float* __rest
 template <int TX>
 __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, float* __restrict__ partial, long long M, int N,
                                                      long long ld, long long rows_per_block) {
+  pdl_grid_sync();
   constexpr int TY = 256 / TX;
   __shared__ float red[TY][TX * 8 + 1];
   const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
@@ -394,6 +403,7 @@ constexpr int kChunk = 4096;
 // torch.optim.SGD(momentum, dampening 0, no nesterov): g += wd * p; buf = first ? g : mom * buf + g; p -= lr * buf
 __global__ void __launch_bounds__(256) sgd_kernel(const B200OptTensor* __restrict__ tensors, const int2* __restrict__ chunks,
                                                   float grad_scale) {
+  pdl_grid_sync();
   const int2 ck = chunks[blockIdx.x];
   const B200OptTensor t = tensors[ck.x];
   float* p = reinterpret_cast<float*>(t.param);
@@ -416,6 +426,7 @@ __global__ void __launch_bounds__(256) sgd_kernel(const B200OptTensor* __restric
 // p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
 __global__ void __launch_bounds__(256) adamw_kernel(const B200OptTensor* __restrict__ tensors, const int2* __restrict__ chunks,
                                                     float grad_scale) {
+  pdl_grid_sync();
   const int2 ck = chunks[blockIdx.x];
   const B200OptTensor t = tensors[ck.x];
   float* p = reinterpret_cast<float*>(t.param);
@@ -440,6 +451,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(const B200OptTensor* __restr
 }
 
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, long long n) {
+  pdl_grid_sync();
   const long long i = (1LL * blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n) {
     const float4 v = *reinterpret_cast<const float4*>(in + i);
@@ -465,7 +477,7 @@ int ln_fwd_launch(const bf16* x, const float* g, const float* b, bf16* y, float*
   const int rpw = (32 / LPR) * U;
   const long long warps = (M + rpw - 1) / rpw;
   const int blocks = grid_for(warps * 32, 256, b200_num_sms() * 8);
-  layernorm_fwd_kernel<LPR, MAXIT, U><<<blocks, 256, 0, st>>>(x, g, b, y, mean, rstd, M, C, eps);
+  launch_pdl(layernorm_fwd_kernel<LPR, MAXIT, U>, dim3(blocks), dim3(256), 0, st, x, g, b, y, mean, rstd, M, C, eps);
   B200_LAUNCH_CHECK();
   return B200_OK;
 }
@@ -476,11 +488,11 @@ int ln_bwd_launch(const bf16* dy, const bf16* x, const float* g, const float* me
   if (with_res) {
     if (smem > 48 * 1024)
       B200_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<LPR, MAXIT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    layernorm_bwd_kernel<LPR, MAXIT, true><<<blocks, 256, smem, st>>>(dy, x, g, mean, rstd, dres, dx, partial, M, C);
+    launch_pdl(layernorm_bwd_kernel<LPR, MAXIT, true>, dim3(blocks), dim3(256), smem, st, dy, x, g, mean, rstd, dres, dx, partial, M, C);
   } else {
     if (smem > 48 * 1024)
       B200_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<LPR, MAXIT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    layernorm_bwd_kernel<LPR, MAXIT, false><<<blocks, 256, smem, st>>>(dy, x, g, mean, rstd, dres, dx, partial, M, C);
+    launch_pdl(layernorm_bwd_kernel<LPR, MAXIT, false>, dim3(blocks), dim3(256), smem, st, dy, x, g, mean, rstd, dres, dx, partial, M, C);
   }
   B200_LAUNCH_CHECK();
   return B200_OK;
@@ -549,7 +561,7 @@ extern "C" int b200_patch_gather_image(const float* img, void* out, int B, int C
   B200_REQUIRE(ldo % 4 == 0 && ldo >= Cin * 16, "patch_gather_image: bad ldo");
   const long long total = 1LL * B * (H / 4) * (W / 4) * Cin * 4;
   if (total == 0) return B200_OK;
-  patch_gather_image_kernel<<<grid_for(total, 256, b200_num_sms() * 16), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_pdl(patch_gather_image_kernel, dim3(grid_for(total, 256, b200_num_sms() * 16)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       img, reinterpret_cast<bf16*>(out), B, Cin, H, W, df, static_cast<int>(ldo));
   B200_LAUNCH_CHECK();
   return B200_OK;
@@ -561,8 +573,8 @@ extern "C" int b200_patch_gather_nhwc(void* x, void* cols, int B, int H, int W, 
   if (total == 0) return B200_OK;
   auto st = reinterpret_cast<cudaStream_t>(stream);
   const int blocks = grid_for(total, 256, b200_num_sms() * 16);
-  if (backward) patch_gather_nhwc_kernel<true><<<blocks, 256, 0, st>>>(reinterpret_cast<bf16*>(x), reinterpret_cast<bf16*>(cols), B, H, W, C);
-  else patch_gather_nhwc_kernel<false><<<blocks, 256, 0, st>>>(reinterpret_cast<bf16*>(x), reinterpret_cast<bf16*>(cols), B, H, W, C);
+  if (backward) launch_pdl(patch_gather_nhwc_kernel<true>, dim3(blocks), dim3(256), 0, st, reinterpret_cast<bf16*>(x), reinterpret_cast<bf16*>(cols), B, H, W, C);
+  else launch_pdl(patch_gather_nhwc_kernel<false>, dim3(blocks), dim3(256), 0, st, reinterpret_cast<bf16*>(x), reinterpret_cast<bf16*>(cols), B, H, W, C);
   B200_LAUNCH_CHECK();
   return B200_OK;
 }
@@ -573,10 +585,10 @@ extern "C" int b200_mean_pool(const void* in, void* out, int B, int T, int C, in
   auto st = reinterpret_cast<cudaStream_t>(stream);
   if (!backward) {
     const int n = B * (C / 2);
-    mean_pool_fwd_kernel<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const bf16*>(in), reinterpret_cast<bf16*>(out), B, T, C);
+    launch_pdl(mean_pool_fwd_kernel, dim3((n + 255) / 256), dim3(256), 0, st, reinterpret_cast<const bf16*>(in), reinterpret_cast<bf16*>(out), B, T, C);
   } else {
     const long long n = 1LL * B * T * (C / 2);
-    mean_pool_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const bf16*>(in), reinterpret_cast<bf16*>(out), B, T, C);
+    launch_pdl(mean_pool_bwd_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, reinterpret_cast<const bf16*>(in), reinterpret_cast<bf16*>(out), B, T, C);
   }
   B200_LAUNCH_CHECK();
   return B200_OK;
@@ -586,7 +598,7 @@ extern "C" int b200_transpose16(const void* in, void* out, long long R, int Cc, 
   B200_REQUIRE(Cc % 2 == 0 && ld_in % 2 == 0 && ld_out % 2 == 0, "transpose16: even column count / pitches required");
   if (R == 0 || Cc == 0) return B200_OK;
   dim3 grid(static_cast<unsigned>((R + 63) / 64), (Cc + 63) / 64);
-  transpose16_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const uint16_t*>(in),
+  launch_pdl(transpose16_kernel, dim3(grid), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<const uint16_t*>(in),
                                                                               reinterpret_cast<uint16_t*>(out), R, Cc, ld_in, ld_out);
   B200_LAUNCH_CHECK();
   return B200_OK;
@@ -595,7 +607,7 @@ extern "C" int b200_transpose16(const void* in, void* out, long long R, int Cc, 
 extern "C" int b200_cast_transpose(const float* in, void* dst, void* dst_t, int R, int Cc, void* stream) {
   if (R == 0 || Cc == 0) return B200_OK;
   dim3 grid((R + 31) / 32, (Cc + 31) / 32);
-  cast_transpose_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(in, reinterpret_cast<bf16*>(dst),
+  launch_pdl(cast_transpose_kernel, dim3(grid), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), in, reinterpret_cast<bf16*>(dst),
                                                                                  reinterpret_cast<bf16*>(dst_t), R, Cc);
   B200_LAUNCH_CHECK();
   return B200_OK;
@@ -605,7 +617,7 @@ extern "C" int b200_cast_f32_bf16(const float* in, void* out, long long n, void*
   if (n == 0) return B200_OK;
   B200_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0, "cast: alignment");
   const long long thr = (n + 3) / 4;
-  cast_f32_bf16_kernel<<<(unsigned)((thr + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(in, reinterpret_cast<bf16*>(out), n);
+  launch_pdl(cast_f32_bf16_kernel, dim3((unsigned)((thr + 255) / 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), in, reinterpret_cast<bf16*>(out), n);
   B200_LAUNCH_CHECK();
   return B200_OK;
 }
@@ -625,9 +637,9 @@ extern "C" int b200_colsum(const void* x, long long ld, long long M, int N, floa
   const long long rpb = (M + blocks - 1) / blocks;
   auto st = reinterpret_cast<cudaStream_t>(stream);
   if (N <= 128) {
-    colsum_kernel<16><<<dim3(blocks, (N + 127) / 128), 256, 0, st>>>(reinterpret_cast<const bf16*>(x), partial, M, N, ld, rpb);
+    launch_pdl(colsum_kernel<16>, dim3(dim3(blocks, (N + 127) / 128)), dim3(256), 0, st, reinterpret_cast<const bf16*>(x), partial, M, N, ld, rpb);
   } else {
-    colsum_kernel<32><<<dim3(blocks, (N + 255) / 256), 256, 0, st>>>(reinterpret_cast<const bf16*>(x), partial, M, N, ld, rpb);
+    launch_pdl(colsum_kernel<32>, dim3(dim3(blocks, (N + 255) / 256)), dim3(256), 0, st, reinterpret_cast<const bf16*>(x), partial, M, N, ld, rpb);
   }
   B200_LAUNCH_CHECK();
   return b200_splitk_reduce(partial, out, N, blocks, accumulate, stream);
@@ -641,8 +653,8 @@ extern "C" int b200_optimizer_step(int kind, const void* tensors_dev, const void
   auto st = reinterpret_cast<cudaStream_t>(stream);
   auto T = reinterpret_cast<const B200OptTensor*>(tensors_dev);
   auto Ck = reinterpret_cast<const int2*>(chunks_dev);
-  if (kind == B200_OPT_SGD) sgd_kernel<<<n_chunks, 256, 0, st>>>(T, Ck, grad_scale);
-  else if (kind == B200_OPT_ADAMW) adamw_kernel<<<n_chunks, 256, 0, st>>>(T, Ck, grad_scale);
+  if (kind == B200_OPT_SGD) launch_pdl(sgd_kernel, dim3(n_chunks), dim3(256), 0, st, T, Ck, grad_scale);
+  else if (kind == B200_OPT_ADAMW) launch_pdl(adamw_kernel, dim3(n_chunks), dim3(256), 0, st, T, Ck, grad_scale);
   else return b200_set_error(B200_ERR_INVALID, "optimizer_step: unknown kind %d", kind);
   B200_LAUNCH_CHECK();
   return B200_OK;

@@ -146,6 +146,7 @@ cosine_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_grid_sync();
 
   const int units = p.q_blocks * p.chunks;
   auto tiles_of = [&](int chunk) -> int {
@@ -327,6 +328,7 @@ __global__ void __launch_bounds__(256) rerank_kernel(const float* __restrict__ q
                                                      const int* __restrict__ cand_idx, const float* __restrict__ cand_score,
                                                      const int* __restrict__ cand_cnt, int lists, int cap, int k,
                                                      long long g_index_base, int* __restrict__ out_idx, double* __restrict__ out_score) {
+  pdl_grid_sync();
   extern __shared__ __align__(16) uint8_t sm[];
   Cand* sel = reinterpret_cast<Cand*>(sm);                                                     // [kKP] exact stage
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(sm + kKP * sizeof(Cand));   // [cap] approximate stage
@@ -409,6 +411,7 @@ __global__ void __launch_bounds__(256) rerank_kernel(const float* __restrict__ q
 // merge `lists` pre-scored top lists per query ([lists][nq][k_in]) into one top-k_out
 __global__ void __launch_bounds__(256) merge_kernel(const double* __restrict__ scores, const int* __restrict__ idx, long long nq, int lists,
                                                     int k_in, int n_pow2, int k_out, int* __restrict__ out_idx, double* __restrict__ out_score) {
+  pdl_grid_sync();
   extern __shared__ __align__(16) uint8_t sm[];
   Cand* cands = reinterpret_cast<Cand*>(sm);
   const long long qi = blockIdx.x;
@@ -434,6 +437,7 @@ __global__ void __launch_bounds__(256) merge_kernel(const double* __restrict__ s
 // fp32 rows -> fp16 unit rows + fp64 norms (fixed summation order: lane-strided chains, xor tree)
 __global__ void __launch_bounds__(256) gallery_prepare_kernel(const float* __restrict__ x, __half* __restrict__ out, double* __restrict__ norm,
                                                               long long n, int dim) {
+  pdl_grid_sync();
   const long long row = (1LL * blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= n) return;
@@ -463,6 +467,7 @@ __global__ void __launch_bounds__(256) gallery_prepare_kernel(const float* __res
 __global__ void recall_hits_kernel(const int* __restrict__ top_idx, long long nq, int k_stride, const long long* __restrict__ q_class,
                                    const long long* __restrict__ g_class, const int* __restrict__ ks, int n_ks,
                                    unsigned long long* __restrict__ hits) {
+  pdl_grid_sync();
   const long long qi = 1LL * blockIdx.x * blockDim.x + threadIdx.x;
   if (qi >= nq) return;
   const long long qc = q_class[qi];
@@ -534,7 +539,7 @@ extern "C" int b200_gallery_prepare(const float* emb, void* unit_f16, double* no
   B200_REQUIRE(dim % 4 == 0, "gallery_prepare: dim must be a multiple of 4");
   if (n == 0) return B200_OK;
   const long long blocks = (n * 32 + 255) / 256;
-  gallery_prepare_kernel<<<static_cast<unsigned>(blocks), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_pdl(gallery_prepare_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       emb, reinterpret_cast<__half*>(unit_f16), norm, n, dim);
   B200_LAUNCH_CHECK();
   return B200_OK;
@@ -584,21 +589,21 @@ extern "C" int b200_cosine_topk(const float* q, const void* q_unit_f16, const do
   if (L.pre_rows > 0) {      // threshold passes: one chunk each, exact streaming top-KP of the rows they scan
     p.g_begin = 0; p.ng = L.pre0_rows; p.chunks = 1; p.chunk_rows = L.pre0_rows; p.list_base = 0;
     p.tau_init = nullptr; p.tau_out = tau;
-    cosine_filter_kernel<<<L.ctas_pre, kThreads, kSmem, st>>>(tq, tg, p);
+    launch_pdl(cosine_filter_kernel, dim3(L.ctas_pre), dim3(kThreads), kSmem, st, tq, tg, p);
     B200_LAUNCH_CHECK();
     p.g_begin = L.pre0_rows; p.ng = L.pre_rows; p.chunk_rows = L.pre_rows - L.pre0_rows; p.list_base = 1;
     p.tau_init = tau; p.tau_out = tau;
-    cosine_filter_kernel<<<L.ctas_pre, kThreads, kSmem, st>>>(tq, tg, p);
+    launch_pdl(cosine_filter_kernel, dim3(L.ctas_pre), dim3(kThreads), kSmem, st, tq, tg, p);
     B200_LAUNCH_CHECK();
   }
   p.g_begin = L.pre_rows; p.ng = ng; p.chunks = L.chunks; p.chunk_rows = L.chunk_rows; p.list_base = L.pre_rows ? 2 : 0;
   p.tau_init = L.pre_rows ? tau : nullptr; p.tau_out = nullptr;
-  cosine_filter_kernel<<<L.ctas, kThreads, kSmem, st>>>(tq, tg, p);
+  launch_pdl(cosine_filter_kernel, dim3(L.ctas), dim3(kThreads), kSmem, st, tq, tg, p);
   B200_LAUNCH_CHECK();
   const int n_pow2 = L.lists * kKP;        // candidate capacity per query
   const int smem2 = kKP * static_cast<int>(sizeof(Cand)) + n_pow2 * 8;
   if (smem2 > 48 * 1024) B200_CHECK_CUDA(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
-  rerank_kernel<<<static_cast<unsigned>(nq), 256, smem2, st>>>(q, q_norm, g, g_norm, dim, p.cand_idx, p.cand_score, p.cand_cnt, L.lists, n_pow2, k,
+  launch_pdl(rerank_kernel, dim3(static_cast<unsigned>(nq)), dim3(256), smem2, st, q, q_norm, g, g_norm, dim, p.cand_idx, p.cand_score, p.cand_cnt, L.lists, n_pow2, k,
                                                                g_index_base, out_idx, out_score);
   B200_LAUNCH_CHECK();
   return B200_OK;
@@ -613,7 +618,7 @@ extern "C" int b200_topk_merge(const double* scores, const int* idx, long long n
   const int smem = n_pow2 * static_cast<int>(sizeof(Cand));
   B200_REQUIRE(smem <= 200 * 1024, "topk_merge: lists * k_in too large");
   if (smem > 48 * 1024) B200_CHECK_CUDA(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  merge_kernel<<<static_cast<unsigned>(nq), 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(scores, idx, nq, lists, k_in, n_pow2, k_out,
+  launch_pdl(merge_kernel, dim3(static_cast<unsigned>(nq)), dim3(256), smem, reinterpret_cast<cudaStream_t>(stream), scores, idx, nq, lists, k_in, n_pow2, k_out,
                                                                                               out_idx, out_score);
   B200_LAUNCH_CHECK();
   return B200_OK;
@@ -622,7 +627,7 @@ extern "C" int b200_topk_merge(const double* scores, const int* idx, long long n
 extern "C" int b200_recall_hits(const int* top_idx, long long nq, int k_stride, const long long* q_class, const long long* g_class,
                                 const int* ks, int n_ks, unsigned long long* hits, void* stream) {
   if (nq == 0) return B200_OK;
-  recall_hits_kernel<<<static_cast<unsigned>((nq + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(top_idx, nq, k_stride, q_class,
+  launch_pdl(recall_hits_kernel, dim3(static_cast<unsigned>((nq + 255) / 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), top_idx, nq, k_stride, q_class,
                                                                                                               g_class, ks, n_ks, hits);
   B200_LAUNCH_CHECK();
   return B200_OK;

@@ -264,6 +264,7 @@ struct EpiMargin {
 template <int SL>
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, long long n,
                                                             int splits, int accumulate, long long stride) {
+  pdl_grid_sync();
   constexpr int CG = 256 / SL;                       // column groups (of 4 floats) per block
   __shared__ float4 red[SL][CG];
   const int cx = threadIdx.x % CG, sx = threadIdx.x / CG;
@@ -301,11 +302,11 @@ int splitk_reduce(const float* partial, float* out, long long n, int splits, int
   B200_REQUIRE(n % 4 == 0 && stride % 4 == 0, "splitk_reduce: n %% 4 != 0");
   const long long groups = n / 4;
   if (splits <= 4) {
-    splitk_reduce_kernel<1><<<(unsigned)((groups + 255) / 256), 256, 0, stream>>>(partial, out, n, splits, accumulate, stride);
+    launch_pdl(splitk_reduce_kernel<1>, dim3((unsigned)((groups + 255) / 256)), dim3(256), 0, stream, partial, out, n, splits, accumulate, stride);
   } else if (splits <= 32 || groups >= 65536) {
-    splitk_reduce_kernel<8><<<(unsigned)((groups + 31) / 32), 256, 0, stream>>>(partial, out, n, splits, accumulate, stride);
+    launch_pdl(splitk_reduce_kernel<8>, dim3((unsigned)((groups + 31) / 32)), dim3(256), 0, stream, partial, out, n, splits, accumulate, stride);
   } else {
-    splitk_reduce_kernel<32><<<(unsigned)((groups + 7) / 8), 256, 0, stream>>>(partial, out, n, splits, accumulate, stride);
+    launch_pdl(splitk_reduce_kernel<32>, dim3((unsigned)((groups + 7) / 8)), dim3(256), 0, stream, partial, out, n, splits, accumulate, stride);
   }
   B200_LAUNCH_CHECK();
   return B200_OK;

@@ -122,6 +122,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_grid_sync();      // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
 
   const int num_tiles = p.m_blocks * p.n_blocks * p.splits;
   // K-major: one [128 x 64] A box + one [block_n x 64] B box per stage.  MN-major: the tile is [64 contraction rows x
@@ -434,7 +435,7 @@ int launch(const Operands& o, const Output& out, const typename Epi::Params& ep,
   int ctas = o.max_ctas > 0 ? o.max_ctas : b200_num_sms();
   if (tiles < ctas) ctas = static_cast<int>(tiles);
   const bool prof = b200_prof_gemm_begin(stream, 2.0 * o.M * o.N * o.K);
-  gemm_tn_kernel<Epi, OUT_BYTES, DUAL, AUX><<<ctas, kThreads, kSmemBytes, stream>>>(ta, tb, to, to2, tx, p, ep);
+  launch_pdl(gemm_tn_kernel<Epi, OUT_BYTES, DUAL, AUX>, dim3(ctas), dim3(kThreads), kSmemBytes, stream, ta, tb, to, to2, tx, p, ep);
   if (prof) b200_prof_gemm_end(stream);
   B200_LAUNCH_CHECK();
   return B200_OK;
