@@ -218,7 +218,8 @@ def gpu_arm(args, rank, world, local_rank):
     if rank == 0:
         sampler.start()
     check = abi.check
-    check(L.b200_prof_begin(1), 'prof_begin')
+    # timed region A: K steps, nothing but the step itself on the stream -> `value`
+    check(L.b200_prof_begin(0), 'prof_begin')
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for i in range(args.steps):
@@ -227,7 +228,19 @@ def gpu_arm(args, rank, world, local_rank):
     barrier()
     ms = ev0.elapsed_time(ev1)
     gemm_ms, gemm_fl, gemm_n, total_n = C.c_double(), C.c_double(), C.c_longlong(), C.c_longlong()
-    check(L.b200_prof_end(C.byref(gemm_ms), C.byref(gemm_fl), C.byref(gemm_n), C.byref(total_n)), 'prof_end')
+    check(L.b200_prof_end(None, None, None, C.byref(total_n)), 'prof_end')
+    # timed region B: the same K steps again with a CUDA-event pair around every tcgen05 GEMM launch -> `roofline`.
+    # (Kept apart from region A because an event record between two kernels suspends their programmatic dependent launch
+    # overlap: it would tax the number it is meant to explain.)
+    check(L.b200_prof_begin(1), 'prof_begin')
+    evb0, evb1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    evb0.record()
+    for i in range(args.steps):
+        step(i)
+    evb1.record()
+    barrier()
+    ms_b = evb0.elapsed_time(evb1)
+    check(L.b200_prof_end(C.byref(gemm_ms), C.byref(gemm_fl), C.byref(gemm_n), None), 'prof_end')
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], device=device, dtype=torch.float64)
     if world > 1:
@@ -241,6 +254,16 @@ def gpu_arm(args, rank, world, local_rank):
                     for i in range(2)]
     host_batches = [{k: v.pin_memory() for k, v in b.items()} for b in host_batches]
     h2d = sum(v.numel() * v.element_size() for v in host_batches[0].values())
+
+    hb = host_batches[0]['x']
+    dst = torch.empty_like(hb, device=device)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        dst.copy_(hb, non_blocking=True)
+    torch.cuda.synchronize()
+    h2d_gbps = 3 * hb.numel() * hb.element_size() / (time.perf_counter() - t0) / 1e9
+    del dst
 
     def host_iter(n):
         for i in range(n):
@@ -272,12 +295,13 @@ def gpu_arm(args, rank, world, local_rank):
                                                       'each step streams > 10 GB of activations)',
                    'flops_per_image': train_flops_per_image(), 'final_loss': final_loss},
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
-                'api': 'engine.Trainer.train_batches(module, host_batches, optimizers)'},
+                'api': 'engine.Trainer.train_batches(module, host_batches, optimizers)', 'h2d_pinned_gbps_this_box': h2d_gbps},
         'gpu_launches': int(total_n.value),
         'roofline': {'bound': 'tensor', 'kernel': 'gemm::gemm_tn_kernel (tcgen05, all Linear fwd/dgrad/wgrad + ArcFace cosine)',
                      'achieved': achieved_tf, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved_tf / peak_tf if peak_tf else None,
                      'traffic': None, 'peak_source': peak_src, 'launches_timed': int(gemm_n.value),
-                     'kernel_ms_per_step': gemm_ms.value / args.steps, 'step_share': gemm_ms.value / ms if ms else None,
+                     'kernel_ms_per_step': gemm_ms.value / args.steps, 'step_share': gemm_ms.value / ms_b if ms_b else None,
+                     'timed_region': f'{args.steps} further steps with per-launch events ({ms_b / args.steps:.2f} ms/step)',
                      'whole_step_frac': value / world * train_flops_per_image() / (peak_tf * 1e12) if peak_tf else None},
         'clocks': clocks,
     }

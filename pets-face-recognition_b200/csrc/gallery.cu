@@ -115,6 +115,26 @@ __device__ int prune_list(uint2* list, int n, float* tau_out, int lane) {
   return base;
 }
 
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose box lands at the same smem offset - and signals the mbarrier at the same offset - in every CTA of `mask`
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t smem_dst, const void* tmap, uint32_t bar, int c_inner, int c_outer, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c_inner), "r"(c_outer), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
+}
+
+// CLUSTER CTAs (a thread-block cluster) work on CLUSTER different query blocks against the SAME gallery chunk in lock step:
+// each CTA fetches 1/CLUSTER of every gallery tile and TMA-multicasts it into the smem of all of them, so the L2 -> SM
+// traffic of the gallery stream (the bound of this kernel: 256 KB per 128 x 256 x 512 tile) drops by CLUSTER.
+template <int CLUSTER>
 __global__ void __launch_bounds__(kThreads, 1)
 cosine_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_g, const FilterParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -135,7 +155,7 @@ cosine_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_g);
-    for (int s = 0; s < kBStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < kBStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), CLUSTER); }   // every CTA of the cluster releases a slot
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
     mbar_init(qfull_bar, 1);
     mbar_init(qempty_bar, 1);
@@ -146,9 +166,17 @@ cosine_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  const int crank = CLUSTER > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  if (CLUSTER > 1) cluster_sync_all();      // peers' barriers are initialised before anything is multicast into this CTA
   pdl_grid_sync();
 
-  const int units = p.q_blocks * p.chunks;
+  // work units: (group of CLUSTER consecutive query blocks, gallery chunk); CTA `crank` of a cluster takes query block
+  // group * CLUSTER + crank (a block past the end scores zero-filled queries and writes nothing)
+  const int q_groups = (p.q_blocks + CLUSTER - 1) / CLUSTER;
+  const int units = q_groups * p.chunks;
+  const int cluster_id = static_cast<int>(blockIdx.x) / CLUSTER, n_clusters = static_cast<int>(gridDim.x) / CLUSTER;
+  constexpr uint16_t kMask = static_cast<uint16_t>((1u << CLUSTER) - 1u);
+  constexpr int kSliceRows = kBN / CLUSTER;
   auto tiles_of = [&](int chunk) -> int {
     const long long g0 = p.g_begin + 1LL * chunk * p.chunk_rows;
     const long long g1 = min(p.ng, g0 + p.chunk_rows);
@@ -158,8 +186,8 @@ cosine_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0, qphase = 0;
-      for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
-        const int qb = unit % p.q_blocks, chunk = unit / p.q_blocks;
+      for (int unit = cluster_id; unit < units; unit += n_clusters) {
+        const int qb = (unit % q_groups) * CLUSTER + crank, chunk = unit / q_groups;
         mbar_wait(qempty_bar, qphase ^ 1u);
         mbar_arrive_expect_tx(qfull_bar, static_cast<uint32_t>(p.kb * kQSlab));
         for (int kb = 0; kb < p.kb; ++kb) tma_load_2d(q_base + kb * kQSlab, &tmap_q, qfull_bar, kb * kBK, qb * kBM);
@@ -169,8 +197,12 @@ cosine_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         for (int t = 0; t < nt; ++t)
           for (int kb = 0; kb < p.kb; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
-            mbar_arrive_expect_tx(full_bar(stage), kBStage);
-            tma_load_2d(b_base + stage * kBStage, &tmap_g, full_bar(stage), kb * kBK, static_cast<int>(g0 + 1LL * t * kBN));
+            mbar_arrive_expect_tx(full_bar(stage), kBStage);       // the whole tile: CLUSTER slices, one from each CTA
+            if (CLUSTER == 1)
+              tma_load_2d(b_base + stage * kBStage, &tmap_g, full_bar(stage), kb * kBK, static_cast<int>(g0 + 1LL * t * kBN));
+            else
+              tma_load_2d_mc(b_base + stage * kBStage + crank * (kSliceRows * kBK * 2), &tmap_g, full_bar(stage), kb * kBK,
+                             static_cast<int>(g0 + 1LL * t * kBN) + crank * kSliceRows, kMask);
             if (++stage == kBStages) { stage = 0; phase ^= 1u; }
           }
       }
@@ -179,8 +211,8 @@ cosine_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0, qphase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
-        const int chunk = unit / p.q_blocks;
+      for (int unit = cluster_id; unit < units; unit += n_clusters) {
+        const int chunk = unit / q_groups;
         mbar_wait(qfull_bar, qphase);
         qphase ^= 1u;
         tc_fence_after();
@@ -196,7 +228,8 @@ cosine_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             const uint64_t db = make_sw128_desc(b_base + stage * kBStage, 16, 1024);
 #pragma unroll
             for (int k = 0; k < kBK / 16; ++k) umma_f16(d_tmem, da + 2u * k, db + 2u * k, p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
-            umma_commit(empty_bar(stage));
+            if (CLUSTER == 1) umma_commit(empty_bar(stage));
+            else umma_commit_mc(empty_bar(stage), kMask);       // the slot is refilled by all CTAs: tell every producer
             if (kb == p.kb - 1) umma_commit(tfull_bar(acc));
             if (++stage == kBStages) { stage = 0; phase ^= 1u; }
           }
@@ -211,8 +244,8 @@ cosine_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     const int row = q * 32 + lane;
     uint2* list = p.scratch + (1LL * blockIdx.x * kBM + row) * kCap;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
-      const int qb = unit % p.q_blocks, chunk = unit / p.q_blocks;
+    for (int unit = cluster_id; unit < units; unit += n_clusters) {
+      const int qb = (unit % q_groups) * CLUSTER + crank, chunk = unit / q_groups;
       const long long qrow = 1LL * qb * kBM + row;
       const bool live = qrow < p.nq;
       const long long self_col = p.exclude_self ? (p.self_offset + qrow) : LLONG_MIN;
@@ -277,6 +310,7 @@ cosine_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
           if (lane == src) cnt = m;
         }
         __syncwarp();
+        if (qb < p.q_blocks) {
         const long long li = qrow * p.lists + p.list_base + chunk;
         int* dst = p.cand_idx + li * kKP;
         float* dsc = p.cand_score + li * kKP;
@@ -290,12 +324,14 @@ cosine_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         p.cand_cnt[li] = live ? cnt : 0;
         if (p.tau_out != nullptr && live)      // KP-th best of the rows seen so far: a lower bound of the KP-th best overall
           p.tau_out[qrow] = (cnt >= kKP) ? mn : (p.tau_init != nullptr ? p.tau_init[qrow] : -INFINITY);
+        }
         __syncwarp();
       }
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (CLUSTER > 1) cluster_sync_all();      // no CTA may leave while peers can still multicast into it / arrive on its barriers
   if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
@@ -488,6 +524,8 @@ struct Layout {
   int chunks;                  // gallery chunks of the main pass
   long long chunk_rows;
   int ctas_pre, ctas;
+  long long ng;                // gallery rows
+  float* tau_ptr;              // [q_blocks*128] thresholds handed from pass to pass
 };
 
 // chunks for `rows` gallery rows: enough (q_block, chunk) units to fill the SMs ~6 times, chunks >= 16 tiles, and the unit
@@ -533,6 +571,84 @@ Layout plan_layout(long long nq, long long ng) {
   return L;
 }
 
+constexpr int kCluster = 4;
+
+template <int CLUSTER>
+int launch_one(const CUtensorMap& tq, const CUtensorMap& tg, const FilterParams& p, int ctas, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(cosine_filter_kernel<CLUSTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    attr_done = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(ctas);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  int n = 1;
+  if (CLUSTER > 1) {
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = CLUSTER; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+    n = 2;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  B200_CHECK_CUDA(cudaLaunchKernelEx(&cfg, cosine_filter_kernel<CLUSTER>, tq, tg, p));
+  b200_count_launch();
+  return B200_OK;
+}
+
+// how many clusters of kCluster CTAs can be resident at once (the GPC layout strands a few SMs for clusters of 4)
+int max_clusters() {
+  static int cached = -1;
+  if (cached < 0) {
+    cudaFuncSetAttribute(cosine_filter_kernel<kCluster>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(b200_num_sms() / kCluster * kCluster);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, cosine_filter_kernel<kCluster>, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = 0; }
+    cached = n;
+  }
+  return cached;
+}
+
+// the three passes of one top-k call; clusters when there are enough query blocks to fill them
+int launch_filter(const CUtensorMap& tq, const CUtensorMap& tg, const CUtensorMap& tg_slice, FilterParams p, const Layout& L, cudaStream_t st) {
+  const int sms = b200_num_sms();
+  const int ncl = max_clusters();
+  const bool use_cluster = ncl > 0 && L.q_blocks >= 2 * kCluster;
+  auto run = [&](int units_single) -> int {
+    if (use_cluster) {
+      const int q_groups = (L.q_blocks + kCluster - 1) / kCluster;
+      const int units = q_groups * p.chunks;
+      return launch_one<kCluster>(tq, tg_slice, p, std::min(units, ncl) * kCluster, st);
+    }
+    return launch_one<1>(tq, tg, p, std::min(units_single, sms), st);
+  };
+  int rc;
+  if (L.pre_rows > 0) {      // threshold passes: one chunk each, exact streaming top-KP of the rows they scan
+    p.g_begin = 0; p.ng = L.pre0_rows; p.chunks = 1; p.chunk_rows = L.pre0_rows; p.list_base = 0;
+    p.tau_init = nullptr; p.tau_out = L.tau_ptr;
+    if ((rc = run(L.q_blocks))) return rc;
+    p.g_begin = L.pre0_rows; p.ng = L.pre_rows; p.chunk_rows = L.pre_rows - L.pre0_rows; p.list_base = 1;
+    p.tau_init = L.tau_ptr; p.tau_out = L.tau_ptr;
+    if ((rc = run(L.q_blocks))) return rc;
+  }
+  p.g_begin = L.pre_rows; p.ng = L.ng; p.chunks = L.chunks; p.chunk_rows = L.chunk_rows; p.list_base = L.pre_rows ? 2 : 0;
+  p.tau_init = L.pre_rows ? L.tau_ptr : nullptr; p.tau_out = nullptr;
+  return run(L.q_blocks * L.chunks);
+}
+
 }  // namespace
 
 extern "C" int b200_gallery_prepare(const float* emb, void* unit_f16, double* norm, long long n, int dim, void* stream) {
@@ -564,7 +680,7 @@ extern "C" int b200_cosine_topk(const float* q, const void* q_unit_f16, const do
     B200_CHECK_CUDA(cudaMemsetAsync(out_idx, 0xff, sizeof(int) * nq * k, st));
     return b200_set_error(B200_ERR_INVALID, "cosine_topk: empty gallery");
   }
-  const Layout L = plan_layout(nq, ng);
+  Layout L = plan_layout(nq, ng);
   B200_REQUIRE(L.lists <= 64, "cosine_topk: too many candidate lists");
   if (workspace_bytes < L.total)
     return b200_set_error(B200_ERR_WORKSPACE, "cosine_topk: workspace %lld < required %lld bytes", workspace_bytes, L.total);
@@ -578,28 +694,18 @@ extern "C" int b200_cosine_topk(const float* q, const void* q_unit_f16, const do
   p.cand_idx = reinterpret_cast<int*>(ws + L.cand_idx);
   p.cand_score = reinterpret_cast<float*>(ws + L.cand_score);
   p.cand_cnt = reinterpret_cast<int*>(ws + L.cand_cnt);
-  float* tau = reinterpret_cast<float*>(ws + L.tau);
+  L.ng = ng;
+  L.tau_ptr = reinterpret_cast<float*>(ws + L.tau);
   CUtensorMap tq, tg;
   int rc = gemm::encode_tmap_2d(&tq, false, q_unit_f16, dim, nq, dim, kBK, kBM);
   if (rc) return rc;
   rc = gemm::encode_tmap_2d(&tg, false, g_unit_f16, dim, ng, dim, kBK, kBN);
   if (rc) return rc;
-  static bool attr = false;
-  if (!attr) { B200_CHECK_CUDA(cudaFuncSetAttribute(cosine_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem)); attr = true; }
-  if (L.pre_rows > 0) {      // threshold passes: one chunk each, exact streaming top-KP of the rows they scan
-    p.g_begin = 0; p.ng = L.pre0_rows; p.chunks = 1; p.chunk_rows = L.pre0_rows; p.list_base = 0;
-    p.tau_init = nullptr; p.tau_out = tau;
-    launch_pdl(cosine_filter_kernel, dim3(L.ctas_pre), dim3(kThreads), kSmem, st, tq, tg, p);
-    B200_LAUNCH_CHECK();
-    p.g_begin = L.pre0_rows; p.ng = L.pre_rows; p.chunk_rows = L.pre_rows - L.pre0_rows; p.list_base = 1;
-    p.tau_init = tau; p.tau_out = tau;
-    launch_pdl(cosine_filter_kernel, dim3(L.ctas_pre), dim3(kThreads), kSmem, st, tq, tg, p);
-    B200_LAUNCH_CHECK();
-  }
-  p.g_begin = L.pre_rows; p.ng = ng; p.chunks = L.chunks; p.chunk_rows = L.chunk_rows; p.list_base = L.pre_rows ? 2 : 0;
-  p.tau_init = L.pre_rows ? tau : nullptr; p.tau_out = nullptr;
-  launch_pdl(cosine_filter_kernel, dim3(L.ctas), dim3(kThreads), kSmem, st, tq, tg, p);
-  B200_LAUNCH_CHECK();
+  CUtensorMap tg_slice;      // one cluster CTA's share of a gallery tile
+  rc = gemm::encode_tmap_2d(&tg_slice, false, g_unit_f16, dim, ng, dim, kBK, kBN / kCluster);
+  if (rc) return rc;
+  rc = launch_filter(tq, tg, tg_slice, p, L, st);
+  if (rc) return rc;
   const int n_pow2 = L.lists * kKP;        // candidate capacity per query
   const int smem2 = kKP * static_cast<int>(sizeof(Cand)) + n_pow2 * 8;
   if (smem2 > 48 * 1024) B200_CHECK_CUDA(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
