@@ -82,6 +82,8 @@ int b200_layernorm_bwd(const void* dy, const void* x, const float* gamma, const 
 
 /* ---- patch merging gather == nn.Unfold(k=s=df) + NHWC view (models/swin.py:159,162-165) ---------------------- */
 int b200_patch_gather_image(const float* img_nchw, void* cols, int B, int Cin, int H, int W, int df, long long ldo, void* stream);
+int b200_patch_gather_image_u8(const unsigned char* img_nchw, void* cols, int B, int Cin, int H, int W, int df, long long ldo,
+                              void* stream); /* uint8 pixels, ToTensor's /255 fused */
 int b200_patch_gather_nhwc(void* x_nhwc, void* cols, int B, int H, int W, int C, int backward, void* stream);
 
 /* ---- x.mean(dim=[2,3]) (models/swin.py:224) and its backward -------------------------------------------------- */
@@ -132,8 +134,8 @@ int b200_swin_param_offsets(const void* plan, long long* offsets, long long* num
 long long b200_swin_wcache_bytes(const void* plan);
 long long b200_swin_workspace_bytes(const void* plan);
 int b200_swin_sync_weights(const void* plan, const float* params, void* wcache, void* stream);
-int b200_swin_forward(const void* plan, const float* params, const void* wcache, const float* img_nchw, float* emb,
-                      void* workspace, long long workspace_bytes, void* stream);
+int b200_swin_forward(const void* plan, const float* params, const void* wcache, const void* img_nchw, int img_is_u8, float* emb,
+                      void* workspace, long long workspace_bytes, void* stream); /* img: fp32 in [0,1], or uint8 (x/255 fused) */
 int b200_swin_backward(const void* plan, const float* params, const void* wcache, const float* demb, float* grads,
                        void* workspace, long long workspace_bytes, int stage_hi, int stage_lo, void* stream);
 

@@ -48,6 +48,7 @@ _PROTOS = {
     'b200_layernorm_bwd_blocks': (c_int, [c_ll, c_int]),
     'b200_layernorm_bwd': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, c_int, c_int, c_vp]),
     'b200_patch_gather_image': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_ll, c_vp]),
+    'b200_patch_gather_image_u8': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_ll, c_vp]),
     'b200_patch_gather_nhwc': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
     'b200_mean_pool': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]),
     'b200_transpose16': (c_int, [c_vp, c_vp, c_ll, c_int, c_ll, c_ll, c_vp]),
@@ -76,7 +77,7 @@ _PROTOS = {
     'b200_swin_wcache_bytes': (c_ll, [c_vp]),
     'b200_swin_workspace_bytes': (c_ll, [c_vp]),
     'b200_swin_sync_weights': (c_int, [c_vp, c_vp, c_vp, c_vp]),
-    'b200_swin_forward': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, c_vp]),
+    'b200_swin_forward': (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_ll, c_vp]),
     'b200_swin_backward': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, c_int, c_int, c_vp]),
     'b200_gallery_prepare': (c_int, [c_vp, c_vp, c_vp, c_ll, c_int, c_vp]),
     'b200_cosine_topk_workspace_bytes': (c_ll, [c_ll, c_ll, c_int, c_int]),

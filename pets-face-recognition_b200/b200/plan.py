@@ -116,12 +116,13 @@ class SwinEngine:
         abi.require_device()
         if img.dim() != 4 or img.shape[1] != self.spec['channels'] or img.shape[2] != self.spec['img'] or img.shape[3] != self.spec['img']:
             raise B200Error(f'expected (B, {self.spec["channels"]}, {self.spec["img"]}, {self.spec["img"]}) input, got {tuple(img.shape)}')
-        img = img.contiguous().float()
+        is_u8 = img.dtype == torch.uint8          # raw pixels: ToTensor's /255 is fused into the first gather kernel
+        img = img.contiguous() if is_u8 else img.contiguous().float()
         self._ensure_flat(img.device)
         plan = self._plan(img.shape[0], training, img.device)
         self._sync_weights()
         emb = torch.empty(img.shape[0], self.spec['num_classes'], device=img.device, dtype=torch.float32)
-        check(lib().b200_swin_forward(plan.handle, ptr(self.flat), ptr(self.wcache), ptr(img), ptr(emb), ptr(plan.workspace),
+        check(lib().b200_swin_forward(plan.handle, ptr(self.flat), ptr(self.wcache), ptr(img), int(is_u8), ptr(emb), ptr(plan.workspace),
                                       plan.workspace_bytes, stream_ptr()), 'swin_forward')
         if training:
             self._token += 1

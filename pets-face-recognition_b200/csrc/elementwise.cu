@@ -241,6 +241,29 @@ __global__ void patch_gather_image_kernel(const float* __restrict__ img, bf16* _
   }
 }
 
+// same gather straight from uint8 pixels: the /255 of torchvision's ToTensor (configs/dog_fe/fe_dogs_config.py:25,31) is fused
+// here, so a host batch crosses PCIe at 1 byte per sample instead of 4
+__global__ void patch_gather_image_u8_kernel(const uint8_t* __restrict__ img, bf16* __restrict__ out, int B, int Cin, int H, int W,
+                                             int df, int ldo) {
+  pdl_grid_sync();
+  const int Ho = H / df, Wo = W / df;
+  const int per_row = Cin * df;
+  const long long total = 1LL * B * Ho * Wo * per_row;
+  for (long long idx = 1LL * blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += 1LL * gridDim.x * blockDim.x) {
+    const int j = static_cast<int>(idx % per_row);
+    const long long m = idx / per_row;
+    const int c = j / df, kh = j % df;
+    const int px = static_cast<int>(m % Wo);
+    const int py = static_cast<int>((m / Wo) % Ho);
+    const int b = static_cast<int>(m / (1LL * Wo * Ho));
+    const uchar4 v = __ldg(reinterpret_cast<const uchar4*>(img + ((1LL * b * Cin + c) * H + py * df + kh) * W + px * df));
+    uint2 o;
+    o.x = pack_bf16(v.x / 255.0f, v.y / 255.0f);
+    o.y = pack_bf16(v.z / 255.0f, v.w / 255.0f);
+    *reinterpret_cast<uint2*>(out + m * ldo + j * 4) = o;
+  }
+}
+
 // stages 2-4: bf16 NHWC, df = 2 -> one thread per (output row, channel pair): 4 x bf162 in, 16 B out
 // backward (scatter == exact inverse, every input pixel appears once) uses the same indexing.
 template <bool BACKWARD>
@@ -563,6 +586,18 @@ extern "C" int b200_patch_gather_image(const float* img, void* out, int B, int C
   if (total == 0) return B200_OK;
   launch_pdl(patch_gather_image_kernel, dim3(grid_for(total, 256, b200_num_sms() * 16)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       img, reinterpret_cast<bf16*>(out), B, Cin, H, W, df, static_cast<int>(ldo));
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+extern "C" int b200_patch_gather_image_u8(const unsigned char* img, void* out, int B, int Cin, int H, int W, int df, long long ldo,
+                                          void* stream) {
+  B200_REQUIRE(df == 4 && H % 4 == 0 && W % 4 == 0, "patch_gather_image_u8: downscaling factor 4 only (got %d)", df);
+  B200_REQUIRE(ldo % 4 == 0 && ldo >= Cin * 16, "patch_gather_image_u8: bad ldo");
+  const long long total = 1LL * B * (H / 4) * (W / 4) * Cin * 4;
+  if (total == 0) return B200_OK;
+  launch_pdl(patch_gather_image_u8_kernel, dim3(grid_for(total, 256, b200_num_sms() * 16)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
+             img, reinterpret_cast<bf16*>(out), B, Cin, H, W, df, static_cast<int>(ldo));
   B200_LAUNCH_CHECK();
   return B200_OK;
 }

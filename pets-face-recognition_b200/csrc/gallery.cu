@@ -17,6 +17,7 @@
 //           oracle/rank_oracle.py:topk_spec defines, so indices are bit-exact regardless of fp16 error as long as
 //           the true top-k lie in the approximate top-KP (KP = k + 28 slack, fp16 cosine error ~3e-5).
 #include <climits>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -626,7 +627,8 @@ int max_clusters() {
 int launch_filter(const CUtensorMap& tq, const CUtensorMap& tg, const CUtensorMap& tg_slice, FilterParams p, const Layout& L, cudaStream_t st) {
   const int sms = b200_num_sms();
   const int ncl = max_clusters();
-  const bool use_cluster = ncl > 0 && L.q_blocks >= 2 * kCluster;
+  static const bool env_off = [] { const char* e = getenv("B200_GALLERY_CLUSTER"); return e != nullptr && e[0] == '0'; }();
+  const bool use_cluster = !env_off && ncl > 0 && L.q_blocks >= 2 * kCluster;
   auto run = [&](int units_single) -> int {
     if (use_cluster) {
       const int q_groups = (L.q_blocks + kCluster - 1) / kCluster;

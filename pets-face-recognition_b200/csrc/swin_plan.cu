@@ -214,13 +214,16 @@ int bias_grad(const Ctx& c, const bf16* dy, long long M, int N, float* db) {
   return b200_colsum(dy, N, M, N, db, c.W<float>(c.p.red_partial), 0, c.stv);
 }
 
-int forward(const Ctx& c, const float* img, float* emb) {
+int forward(const Ctx& c, const void* img, int img_u8, float* emb) {
   const Plan& p = c.p;
   const bf16* x = nullptr;
   for (int s = 0; s < 4; ++s) {
     const Stage& S = p.st[s];
     bf16* cols = c.W<bf16>(S.cols);
-    if (s == 0) RC(b200_patch_gather_image(img, cols, p.B, p.channels, p.img, p.img, S.df, S.Kp, c.stv));
+    if (s == 0) {
+      if (img_u8) RC(b200_patch_gather_image_u8(reinterpret_cast<const unsigned char*>(img), cols, p.B, p.channels, p.img, p.img, S.df, S.Kp, c.stv));
+      else RC(b200_patch_gather_image(reinterpret_cast<const float*>(img), cols, p.B, p.channels, p.img, p.img, S.df, S.Kp, c.stv));
+    }
     else RC(b200_patch_gather_nhwc(const_cast<bf16*>(x), cols, p.B, p.st[s - 1].Hs, p.st[s - 1].Hs, p.st[s - 1].C, 0, c.stv));
     bf16* x0 = c.W<bf16>(S.x0);
     RC(linear_fwd(c, cols, S.M, S.Kp, c.wc + S.wp16, S.C, c.P(S.bp), B200_EPI_STORE, x0, nullptr, nullptr));
@@ -397,14 +400,14 @@ extern "C" int b200_swin_sync_weights(const void* plan, const float* params, voi
   return sync_weights(c);
 }
 
-extern "C" int b200_swin_forward(const void* plan, const float* params, const void* wcache, const float* img, float* emb,
+extern "C" int b200_swin_forward(const void* plan, const float* params, const void* wcache, const void* img, int img_is_u8, float* emb,
                                  void* workspace, long long workspace_bytes, void* stream) {
   const Plan* p = reinterpret_cast<const Plan*>(plan);
   if (workspace_bytes < p->ws_bytes)
     return b200_set_error(B200_ERR_WORKSPACE, "swin_forward: workspace %lld < required %lld bytes", workspace_bytes, p->ws_bytes);
   Ctx c{*p, params, nullptr, reinterpret_cast<bf16*>(const_cast<void*>(wcache)), reinterpret_cast<uint8_t*>(workspace),
         reinterpret_cast<cudaStream_t>(stream), stream};
-  return forward(c, img, emb);
+  return forward(c, img, img_is_u8, emb);
 }
 
 extern "C" int b200_swin_backward(const void* plan, const float* params, const void* wcache, const float* demb, float* grads,

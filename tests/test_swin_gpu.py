@@ -158,3 +158,14 @@ def test_batch_odd_sizes_and_repeatability(setup):
         c = wrap(x[:3])
     assert torch.equal(a, b)                                  # deterministic forward
     assert torch.allclose(a[:3], c, rtol=0, atol=0)           # rows independent of batch composition
+
+
+def test_uint8_images_equal_totensor_floats(setup):
+    """Raw uint8 pixels with the /255 fused into the first kernel == the float batch torchvision's ToTensor would hand over."""
+    g, sd, wrap, img, label = setup
+    wrap.eval()
+    u8 = (torch.rand(3, 3, 224, 224, generator=torch.Generator().manual_seed(3)) * 255).to(torch.uint8).cuda()
+    with torch.no_grad():
+        a = wrap(u8)
+        b = wrap(u8.float() / 255)
+    assert torch.equal(a, b)
