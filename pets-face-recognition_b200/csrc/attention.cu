@@ -30,11 +30,9 @@ constexpr int kTileRows = 50;                      // 49 token rows + one all-ze
 constexpr int kTileBytes = kTileRows * kRowB;      // 4000
 constexpr int kStageBytes = 16 * kRowB;            // 1280: one 16-row output tile
 constexpr int kWarps = 4;                          // forward: warps (= tasks in flight) per CTA
-constexpr int kBwdWarps = 5;                       // backward: 2 CTAs x 5 warps per SM (smem- and register-limited)
 constexpr int kBins = 169;
 constexpr int kBiasPitch = 72;                     // floats per row of the 64 x 64 bias table (conflict-free float2 reads)
 constexpr int kBiasBytes = 64 * kBiasPitch * 4;    // 18432
-constexpr int kSlots = 4 * 7 * 4;                  // per-lane dS accumulators: [m-tile][n-tile < 7][fragment element]
 constexpr float kLog2e = 1.4426950408889634f;
 // bit j set <=> window column (j % 7) >= 4, i.e. token j lies in the wrapped part under the left/right mask
 constexpr unsigned long long kColHi = 0x1C3870E1C3870ULL;
@@ -48,7 +46,7 @@ struct AttnArgs {
   const bf16* o;        // bwd: saved attention output
   bf16* dqkv;           // bwd: [B*H*W, 3C]
   float* dpos_partial;  // bwd: [gridDim.x, 169]
-  float* dslots;        // bwd: [gridDim.x * kWarps][kSlots][32] per-lane dS accumulators (L2-resident scratch)
+  float* dslots;        // bwd: [gridDim.x * warps][64][32] per-lane dS accumulators (L2-resident scratch)
   int B, H, W, C, heads, shifted;
   float scale;
 };
@@ -67,6 +65,7 @@ __device__ __forceinline__ void mma16816(float (&d)[4], uint32_t a0, uint32_t a1
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
+__device__ __forceinline__ float fast_exp2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
 
 // byte offset of tile row r inside a slab: rows >= 49 all read the shared zero row (row 49)
@@ -235,8 +234,8 @@ __global__ void __launch_bounds__(kWarps * 32) window_attn_fwd_kernel(const Attn
       uint32_t pf[8][2];
 #pragma unroll
       for (int n = 0; n < 8; ++n) {
-        const float p0 = exp2f(s[n][0] - m0), p1 = exp2f(s[n][1] - m0);
-        const float p2 = exp2f(s[n][2] - m1), p3 = exp2f(s[n][3] - m1);
+        const float p0 = fast_exp2(s[n][0] - m0), p1 = fast_exp2(s[n][1] - m0);
+        const float p2 = fast_exp2(s[n][2] - m1), p3 = fast_exp2(s[n][3] - m1);
         l0 += p0 + p1; l1 += p2 + p3;
         pf[n][0] = pack_bf16(p0, p1);
         pf[n][1] = pack_bf16(p2, p3);
@@ -280,28 +279,47 @@ __global__ void __launch_bounds__(kWarps * 32) window_attn_fwd_kernel(const Attn
 // ---------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------
-constexpr int kBwdWarpBytes = 4 * kTileBytes + kStageBytes;                      // q, k, v, dO, 16-row output staging
-constexpr int kBwdSmem = kBiasBytes + 704 + kBwdWarps * 64 * 8 + kBwdWarps * 2 * 64 * 4 + kBwdWarps * kBwdWarpBytes;
+// Two warps share one (window, head) task; warp w owns keys [32 w, 32 w + 32).  Per 16-query tile each warp forms its
+// 16 x 32 slice of S and dP once (query-major), turns it into P and dS, and uses those fragments three ways:
+//   dQ_part = dS K_w          (A = dS straight from the accumulator registers; the two halves are summed through smem)
+//   dV_w   += P^T dO,  dK_w += dS^T Q      (A = the 8 x 8 blocks transposed in registers by movmatrix)
+// so no score is recomputed in the key-major orientation and dK / dV never leave registers until the task ends.
+constexpr int kPairs = 6;                          // tasks in flight per CTA (one CTA of 12 warps per SM)
+constexpr int kBwdThreads = kPairs * 64;
+constexpr int kSlots = 4 * 4 * 4;                  // per-lane dS accumulators: [m-tile][n-tile of the warp's 32 keys][fragment element]
+constexpr int kXBytes = 16 * 32 * 4;               // one warp's dQ partial of a 16-query tile, fp32
+constexpr int kPairBytes = 4 * kTileBytes + 2 * kXBytes + 2 * kStageBytes + 64 * 8 + 2 * 64 * 4;     // 23680
+constexpr int kBwdSmem = kBiasBytes + 704 + kPairs * kPairBytes;
 
-__global__ void __launch_bounds__(kBwdWarps * 32) window_attn_bwd_kernel(const AttnArgs a) {
+__device__ __forceinline__ uint32_t movm_t(uint32_t x) {
+  uint32_t y;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
+__device__ __forceinline__ void red_add_f32(float* p, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+__device__ __forceinline__ void pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void pair_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+
+__global__ void __launch_bounds__(kBwdThreads, 1) window_attn_bwd_kernel(const AttnArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pair = warp >> 1, w = warp & 1;
   const int g = lane >> 2, tq = lane & 3;
   float* bias_s = reinterpret_cast<float*>(smem);
   float* bins = reinterpret_cast<float*>(smem + kBiasBytes);                                    // [169] (704 B)
-  long long* rows_all = reinterpret_cast<long long*>(smem + kBiasBytes + 704);                  // [kBwdWarps][64]
-  float* stat_all = reinterpret_cast<float*>(smem + kBiasBytes + 704 + kBwdWarps * 64 * 8);        // [kBwdWarps][2][64]: lse (log2), D
-  uint8_t* my = smem + kBiasBytes + 704 + kBwdWarps * 64 * 8 + kBwdWarps * 2 * 64 * 4 + warp * kBwdWarpBytes;
-  const uint32_t qs = smem_u32(my), ks = qs + kTileBytes, vs = ks + kTileBytes, dos = vs + kTileBytes;
-  bf16* stage = reinterpret_cast<bf16*>(my + 4 * kTileBytes);
-  long long* rows_s = rows_all + warp * 64;
-  float* lse_s = stat_all + warp * 128;
+  uint8_t* pb = smem + kBiasBytes + 704 + pair * kPairBytes;
+  const uint32_t qs = smem_u32(pb), ks = qs + kTileBytes, vs = ks + kTileBytes, dos = vs + kTileBytes;
+  float* xbuf = reinterpret_cast<float*>(pb + 4 * kTileBytes);                                  // [2][16][32]
+  bf16* stage = reinterpret_cast<bf16*>(pb + 4 * kTileBytes + 2 * kXBytes + w * kStageBytes);
+  long long* rows_s = reinterpret_cast<long long*>(pb + 4 * kTileBytes + 2 * kXBytes + 2 * kStageBytes);
+  float* lse_s = reinterpret_cast<float*>(rows_s + 64);     // log2 domain
   float* dsum_s = lse_s + 64;
-  float* slots = a.dslots + (1LL * blockIdx.x * kBwdWarps + warp) * (kSlots * 32) + lane;          // [slot * 32]
+  float* slots = a.dslots + (1LL * blockIdx.x * (2 * kPairs) + warp) * (kSlots * 32) + lane;       // [slot * 32]
+  const int bar0 = 1 + 2 * pair;                            // named barriers bar0, bar0 + 1 belong to this pair
 
   build_bias_table(bias_s, a.pos);
   for (int i = threadIdx.x; i < kBins; i += blockDim.x) bins[i] = 0.f;
-  for (int i = lane; i < kBwdWarpBytes / 16; i += 32) reinterpret_cast<uint4*>(my)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = w * 32 + lane; i < kPairBytes / 16; i += 64) reinterpret_cast<uint4*>(pb)[i] = make_uint4(0, 0, 0, 0);
 #pragma unroll 4
   for (int sl = 0; sl < kSlots; ++sl) __stcg(slots + sl * 32, 0.f);
   __syncthreads();
@@ -310,139 +328,69 @@ __global__ void __launch_bounds__(kBwdWarps * 32) window_attn_bwd_kernel(const A
   const long long ntasks = 1LL * a.B * (a.H / kWs) * (a.W / kWs) * a.heads;
   const long long ld_qkv = 3LL * a.C;
   const float sc2 = a.scale * kLog2e;
-  for (long long task = 1LL * blockIdx.x * kBwdWarps + warp; task < ntasks; task += 1LL * gridDim.x * kBwdWarps) {
+  for (long long task = 1LL * blockIdx.x * kPairs + pair; task < ntasks; task += 1LL * gridDim.x * kPairs) {
     const Task t = decode_task(a, task);
     const bool flagged = t.ul || t.lr;
-    for (int i = lane; i < 64; i += 32) {
+    pair_sync(bar0);                    // the partner has finished with the previous task's tiles / rows
+    {
+      const int i = w * 32 + lane;
       if (i < kWt) {
         const long long r = token_row(a, t, i);
         rows_s[i] = r;
         lse_s[i] = a.lse[r * a.heads + t.h] * kLog2e;
       } else {
-        lse_s[i] = INFINITY;          // padded query rows: exp2(x - inf) = 0
+        lse_s[i] = INFINITY;            // padded query rows: exp2(x - inf) = 0
         dsum_s[i] = 0.f;
       }
     }
-    __syncwarp();
-    load_tile_async(qs, a.qkv, ld_qkv, t.h * kHd, rows_s, lane);
-    load_tile_async(ks, a.qkv, ld_qkv, a.C + t.h * kHd, rows_s, lane);
-    load_tile_async(vs, a.qkv, ld_qkv, 2 * a.C + t.h * kHd, rows_s, lane);
-    load_tile_async(dos, a.dout, a.C, t.h * kHd, rows_s, lane);
+    pair_sync(bar0);
+    if (w == 0) {
+      load_tile_async(qs, a.qkv, ld_qkv, t.h * kHd, rows_s, lane);
+      load_tile_async(ks, a.qkv, ld_qkv, a.C + t.h * kHd, rows_s, lane);
+    } else {
+      load_tile_async(vs, a.qkv, ld_qkv, 2 * a.C + t.h * kHd, rows_s, lane);
+      load_tile_async(dos, a.dout, a.C, t.h * kHd, rows_s, lane);
+    }
     // D_i = sum_d dO[i,d] * O[i,d]  (== rowsum(dP o P)); straight from global while the tiles stream in
 #pragma unroll
-    for (int it = 0; it < 7; ++it) {
+    for (int it2 = 0; it2 < 4; ++it2) {
+      const int it = it2 * 2 + w;
       const int row = it * 8 + (lane >> 2);
       float acc = 0.f;
-      if (row < kWt) {
+      if (it < 7 && row < kWt) {
         const long long off = rows_s[row] * a.C + t.h * kHd + (lane & 3) * 8;
         const uint4 u = *reinterpret_cast<const uint4*>(a.dout + off);
-        const uint4 w = *reinterpret_cast<const uint4*>(a.o + off);
+        const uint4 o = *reinterpret_cast<const uint4*>(a.o + off);
         float2 x, y;
-        x = unpack_bf16(u.x); y = unpack_bf16(w.x); acc += x.x * y.x + x.y * y.y;
-        x = unpack_bf16(u.y); y = unpack_bf16(w.y); acc += x.x * y.x + x.y * y.y;
-        x = unpack_bf16(u.z); y = unpack_bf16(w.z); acc += x.x * y.x + x.y * y.y;
-        x = unpack_bf16(u.w); y = unpack_bf16(w.w); acc += x.x * y.x + x.y * y.y;
+        x = unpack_bf16(u.x); y = unpack_bf16(o.x); acc += x.x * y.x + x.y * y.y;
+        x = unpack_bf16(u.y); y = unpack_bf16(o.y); acc += x.x * y.x + x.y * y.y;
+        x = unpack_bf16(u.z); y = unpack_bf16(o.z); acc += x.x * y.x + x.y * y.y;
+        x = unpack_bf16(u.w); y = unpack_bf16(o.w); acc += x.x * y.x + x.y * y.y;
       }
       acc += __shfl_xor_sync(0xffffffffu, acc, 1);
       acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-      if (row < kWt && (lane & 3) == 0) dsum_s[row] = acc;
+      if (it < 7 && row < kWt && (lane & 3) == 0) dsum_s[row] = acc;
     }
     cp_async_wait_all();
-    __syncwarp();
+    pair_sync(bar0);
 
-    // ---- pass A: key-major (rows = keys j): dV = P^T dO, dK = scale * dS^T Q ---------------------------
-#pragma unroll 1
-    for (int jt = 0; jt < 4; ++jt) {
-      float st[8][4], dpt[8][4];
+    float dv[2][4][4], dk[2][4][4];       // this warp's 32 keys x 32 dims, accumulated over the four query tiles
 #pragma unroll
-      for (int n = 0; n < 8; ++n) { st[n][0] = st[n][1] = st[n][2] = st[n][3] = 0.f; dpt[n][0] = dpt[n][1] = dpt[n][2] = dpt[n][3] = 0.f; }
+    for (int jt = 0; jt < 2; ++jt)
 #pragma unroll
-      for (int kk = 0; kk < 2; ++kk) {
-        uint32_t k0, k1, k2, k3, v0, v1, v2, v3;
-        const uint32_t aoff = off_a(jt, kk, lane);
-        ldsm_x4(ks + aoff, k0, k1, k2, k3);     // A = K rows (keys)
-        ldsm_x4(vs + aoff, v0, v1, v2, v3);     // A = V rows (keys)
-#pragma unroll
-        for (int np = 0; np < 4; ++np) {
-          uint32_t b0, b1, b2, b3;
-          const uint32_t boff = off_b(np, kk, lane);
-          ldsm_x4(qs + boff, b0, b1, b2, b3);   // B = Q  (n = query i, k = d)
-          mma16816(st[2 * np], k0, k1, k2, k3, b0, b1);
-          mma16816(st[2 * np + 1], k0, k1, k2, k3, b2, b3);
-          ldsm_x4(dos + boff, b0, b1, b2, b3);  // B = dO (n = query i, k = d)
-          mma16816(dpt[2 * np], v0, v1, v2, v3, b0, b1);
-          mma16816(dpt[2 * np + 1], v0, v1, v2, v3, b2, b3);
-        }
+      for (int n = 0; n < 4; ++n) {
+        dv[jt][n][0] = dv[jt][n][1] = dv[jt][n][2] = dv[jt][n][3] = 0.f;
+        dk[jt][n][0] = dk[jt][n][1] = dk[jt][n][2] = dk[jt][n][3] = 0.f;
       }
-      const int j0 = jt * 16 + g, j1 = j0 + 8;
-      uint32_t pf[8][2], df[8][2];
-#pragma unroll
-      for (int n = 0; n < 8; ++n) {
-        const int i = n * 8 + tq * 2;
-        float p[4], ds[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int ii = i + (e & 1), jj = (e < 2) ? j0 : j1;
-          float sc = fmaf(st[n][e], sc2, bias_s[ii * kBiasPitch + jj] - lse_s[ii]);
-          if (flagged && shift_masked(t, ii, jj)) sc = -INFINITY;
-          p[e] = exp2f(sc);
-          ds[e] = p[e] * (dpt[n][e] - dsum_s[ii]);          // unscaled: `scale` is applied once to the dK accumulators
-        }
-        pf[n][0] = pack_bf16(p[0], p[1]); pf[n][1] = pack_bf16(p[2], p[3]);
-        df[n][0] = pack_bf16(ds[0], ds[1]); df[n][1] = pack_bf16(ds[2], ds[3]);
-      }
-      float dv[4][4], dk[4][4];
-#pragma unroll
-      for (int n = 0; n < 4; ++n) { dv[n][0] = dv[n][1] = dv[n][2] = dv[n][3] = 0.f; dk[n][0] = dk[n][1] = dk[n][2] = dk[n][3] = 0.f; }
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk)      // contraction over queries i, 16 per step
-#pragma unroll
-        for (int np = 0; np < 2; ++np) {
-          uint32_t b0, b1, b2, b3;
-          const uint32_t boff = off_bt(kk, np, lane);
-          ldsm_x4_t(dos + boff, b0, b1, b2, b3);   // B = dO (k = i, n = d)
-          mma16816(dv[2 * np], pf[2 * kk][0], pf[2 * kk][1], pf[2 * kk + 1][0], pf[2 * kk + 1][1], b0, b1);
-          mma16816(dv[2 * np + 1], pf[2 * kk][0], pf[2 * kk][1], pf[2 * kk + 1][0], pf[2 * kk + 1][1], b2, b3);
-          ldsm_x4_t(qs + boff, b0, b1, b2, b3);    // B = Q  (k = i, n = d)
-          mma16816(dk[2 * np], df[2 * kk][0], df[2 * kk][1], df[2 * kk + 1][0], df[2 * kk + 1][1], b0, b1);
-          mma16816(dk[2 * np + 1], df[2 * kk][0], df[2 * kk][1], df[2 * kk + 1][0], df[2 * kk + 1][1], b2, b3);
-        }
-      // stage dK rows then dV rows of this key tile and write them out (64-B row segments)
-#pragma unroll
-      for (int which = 0; which < 2; ++which) {
-        __syncwarp();
-#pragma unroll
-        for (int n = 0; n < 4; ++n) {
-          const float(&src)[4] = which == 0 ? dk[n] : dv[n];
-          const float f = which == 0 ? a.scale : 1.0f;
-          *reinterpret_cast<uint32_t*>(stage + g * kPitch + n * 8 + tq * 2) = pack_bf16(src[0] * f, src[1] * f);
-          *reinterpret_cast<uint32_t*>(stage + (g + 8) * kPitch + n * 8 + tq * 2) = pack_bf16(src[2] * f, src[3] * f);
-        }
-        __syncwarp();
-#pragma unroll
-        for (int it = 0; it < 2; ++it) {
-          const int r = it * 8 + (lane >> 2);
-          const int j = jt * 16 + r;
-          if (j < kWt) {
-            const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(stage) + r * kRowB + (lane & 3) * 16);
-            *reinterpret_cast<uint4*>(a.dqkv + rows_s[j] * ld_qkv + (which == 0 ? 1 : 2) * a.C + t.h * kHd + (lane & 3) * 8) = v;
-          }
-        }
-      }
-    }
 
-    // ---- pass B: query-major (rows = queries i): dQ = scale * dS K; dS summed per lane for the rel-pos gradient ----
 #pragma unroll 1
     for (int mt = 0; mt < 4; ++mt) {
-      float s[8][4], dp[8][4];
+      float s[4][4], dp[4][4];
 #pragma unroll
-      for (int n = 0; n < 8; ++n) { s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f; dp[n][0] = dp[n][1] = dp[n][2] = dp[n][3] = 0.f; }
-      float* sl = slots + mt * (7 * 4 * 32);
-      // the running per-lane dS sums live in an L2-resident scratch: fetch them now so that the round trip overlaps
-      // the 64 MMAs below; add and write back once the scores are known
-      float sv[28];
-#pragma unroll
-      for (int i = 0; i < 28; ++i) sv[i] = __ldcg(sl + i * 32);
+      for (int n = 0; n < 4; ++n) { s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f; dp[n][0] = dp[n][1] = dp[n][2] = dp[n][3] = 0.f; }
+      // the running per-lane dS sums live in an L2-resident scratch and are updated by fire-and-forget reductions:
+      // every address is private to one lane, so the order of the additions - hence the sum - is fixed (deterministic)
+      float* sl = slots + mt * (16 * 32);
 #pragma unroll
       for (int kk = 0; kk < 2; ++kk) {
         uint32_t q0, q1, q2, q3, d0, d1, d2, d3;
@@ -450,9 +398,9 @@ __global__ void __launch_bounds__(kBwdWarps * 32) window_attn_bwd_kernel(const A
         ldsm_x4(qs + aoff, q0, q1, q2, q3);
         ldsm_x4(dos + aoff, d0, d1, d2, d3);
 #pragma unroll
-        for (int np = 0; np < 4; ++np) {
+        for (int np = 0; np < 2; ++np) {
           uint32_t b0, b1, b2, b3;
-          const uint32_t boff = off_b(np, kk, lane);
+          const uint32_t boff = off_b(2 * w + np, kk, lane);
           ldsm_x4(ks + boff, b0, b1, b2, b3);   // B = K (n = key j, k = d)
           mma16816(s[2 * np], q0, q1, q2, q3, b0, b1);
           mma16816(s[2 * np + 1], q0, q1, q2, q3, b2, b3);
@@ -462,70 +410,138 @@ __global__ void __launch_bounds__(kBwdWarps * 32) window_attn_bwd_kernel(const A
         }
       }
       const int i0 = mt * 16 + g, i1 = i0 + 8;
-      const float* b0p = bias_s + i0 * kBiasPitch + tq * 2;
-      const float* b1p = bias_s + i1 * kBiasPitch + tq * 2;
+      const int jw = w * 32 + tq * 2;
+      const float* b0p = bias_s + i0 * kBiasPitch + jw;
+      const float* b1p = bias_s + i1 * kBiasPitch + jw;
       const float l0 = lse_s[i0], l1 = lse_s[i1], D0 = dsum_s[i0], D1 = dsum_s[i1];
-      uint32_t df[8][2];
+      uint32_t pf[4][2], df[4][2];
 #pragma unroll
-      for (int n = 0; n < 8; ++n) {
+      for (int n = 0; n < 4; ++n) {
         const float2 b0 = *reinterpret_cast<const float2*>(b0p + n * 8);
         const float2 b1 = *reinterpret_cast<const float2*>(b1p + n * 8);
         float sc[4];
         sc[0] = fmaf(s[n][0], sc2, b0.x - l0); sc[1] = fmaf(s[n][1], sc2, b0.y - l0);
         sc[2] = fmaf(s[n][2], sc2, b1.x - l1); sc[3] = fmaf(s[n][3], sc2, b1.y - l1);
         if (flagged) {
-          const int j = n * 8 + tq * 2;
+          const int j = jw + n * 8;
           if (shift_masked(t, i0, j)) sc[0] = -INFINITY;
           if (shift_masked(t, i0, j + 1)) sc[1] = -INFINITY;
           if (shift_masked(t, i1, j)) sc[2] = -INFINITY;
           if (shift_masked(t, i1, j + 1)) sc[3] = -INFINITY;
         }
-        float ds[4];
-        ds[0] = exp2f(sc[0]) * (dp[n][0] - D0); ds[1] = exp2f(sc[1]) * (dp[n][1] - D0);
-        ds[2] = exp2f(sc[2]) * (dp[n][2] - D1); ds[3] = exp2f(sc[3]) * (dp[n][3] - D1);
-        if (n < 7) {     // keys 56..63 are padding; per-lane private accumulators, no atomics
+        float p[4], ds[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) __stcg(sl + (n * 4 + e) * 32, sv[n * 4 + e] + ds[e]);
-        }
-        df[n][0] = pack_bf16(ds[0], ds[1]);          // unscaled: `scale` is applied once to the dQ accumulators
-        df[n][1] = pack_bf16(ds[2], ds[3]);
+        for (int e = 0; e < 4; ++e) p[e] = fast_exp2(sc[e]);
+        ds[0] = p[0] * (dp[n][0] - D0); ds[1] = p[1] * (dp[n][1] - D0);       // unscaled: `scale` is applied once to dQ / dK
+        ds[2] = p[2] * (dp[n][2] - D1); ds[3] = p[3] * (dp[n][3] - D1);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) red_add_f32(sl + (n * 4 + e) * 32, ds[e]);
+        pf[n][0] = pack_bf16(p[0], p[1]); pf[n][1] = pack_bf16(p[2], p[3]);
+        df[n][0] = pack_bf16(ds[0], ds[1]); df[n][1] = pack_bf16(ds[2], ds[3]);
       }
+      // dQ (this warp's 32 keys): contraction over keys j
       float dq[4][4];
 #pragma unroll
       for (int n = 0; n < 4; ++n) { dq[n][0] = dq[n][1] = dq[n][2] = dq[n][3] = 0.f; }
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk)      // contraction over keys j
+      for (int kk = 0; kk < 2; ++kk)
 #pragma unroll
         for (int np = 0; np < 2; ++np) {
           uint32_t b0, b1, b2, b3;
-          ldsm_x4_t(ks + off_bt(kk, np, lane), b0, b1, b2, b3);    // B = K (k = j, n = d)
+          ldsm_x4_t(ks + off_bt(2 * w + kk, np, lane), b0, b1, b2, b3);    // B = K (k = j, n = d)
           mma16816(dq[2 * np], df[2 * kk][0], df[2 * kk][1], df[2 * kk + 1][0], df[2 * kk + 1][1], b0, b1);
           mma16816(dq[2 * np + 1], df[2 * kk][0], df[2 * kk][1], df[2 * kk + 1][0], df[2 * kk + 1][1], b2, b3);
         }
-      __syncwarp();
+      // P^T and dS^T as A operands (rows = keys, k = the 16 queries of this tile): transpose the 8 x 8 blocks in registers
+      uint32_t pt[4][2], dt[4][2];
 #pragma unroll
       for (int n = 0; n < 4; ++n) {
-        *reinterpret_cast<uint32_t*>(stage + g * kPitch + n * 8 + tq * 2) = pack_bf16(dq[n][0] * a.scale, dq[n][1] * a.scale);
-        *reinterpret_cast<uint32_t*>(stage + (g + 8) * kPitch + n * 8 + tq * 2) = pack_bf16(dq[n][2] * a.scale, dq[n][3] * a.scale);
+        pt[n][0] = movm_t(pf[n][0]); pt[n][1] = movm_t(pf[n][1]);
+        dt[n][0] = movm_t(df[n][0]); dt[n][1] = movm_t(df[n][1]);
       }
-      __syncwarp();
 #pragma unroll
-      for (int it = 0; it < 2; ++it) {
-        const int r = it * 8 + (lane >> 2);
-        const int i = mt * 16 + r;
-        if (i < kWt) {
-          const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(stage) + r * kRowB + (lane & 3) * 16);
-          *reinterpret_cast<uint4*>(a.dqkv + rows_s[i] * ld_qkv + t.h * kHd + (lane & 3) * 8) = v;
+      for (int np = 0; np < 2; ++np) {
+        uint32_t b0, b1, b2, b3;
+        const uint32_t boff = off_bt(mt, np, lane);
+        ldsm_x4_t(dos + boff, b0, b1, b2, b3);     // B = dO (k = i, n = d)
+#pragma unroll
+        for (int jt = 0; jt < 2; ++jt) {
+          mma16816(dv[jt][2 * np], pt[2 * jt][0], pt[2 * jt + 1][0], pt[2 * jt][1], pt[2 * jt + 1][1], b0, b1);
+          mma16816(dv[jt][2 * np + 1], pt[2 * jt][0], pt[2 * jt + 1][0], pt[2 * jt][1], pt[2 * jt + 1][1], b2, b3);
+        }
+        ldsm_x4_t(qs + boff, b0, b1, b2, b3);      // B = Q (k = i, n = d)
+#pragma unroll
+        for (int jt = 0; jt < 2; ++jt) {
+          mma16816(dk[jt][2 * np], dt[2 * jt][0], dt[2 * jt + 1][0], dt[2 * jt][1], dt[2 * jt + 1][1], b0, b1);
+          mma16816(dk[jt][2 * np + 1], dt[2 * jt][0], dt[2 * jt + 1][0], dt[2 * jt][1], dt[2 * jt + 1][1], b2, b3);
+        }
+      }
+      // sum the two key halves of dQ: the warps alternate as writer / finisher, handing over through a double-buffered slab
+      {
+        const int bid = bar0 + (mt & 1);
+        float* xb = xbuf + (mt & 1) * (16 * 32) + lane;
+        if (w != (mt & 1)) {
+#pragma unroll
+          for (int n = 0; n < 4; ++n)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) xb[(n * 4 + e) * 32] = dq[n][e];
+          __threadfence_block();
+          pair_arrive(bid);
+        } else {
+          pair_sync(bid);
+#pragma unroll
+          for (int n = 0; n < 4; ++n)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) dq[n][e] += xb[(n * 4 + e) * 32];
+#pragma unroll
+          for (int n = 0; n < 4; ++n) {
+            *reinterpret_cast<uint32_t*>(stage + g * kPitch + n * 8 + tq * 2) = pack_bf16(dq[n][0] * a.scale, dq[n][1] * a.scale);
+            *reinterpret_cast<uint32_t*>(stage + (g + 8) * kPitch + n * 8 + tq * 2) = pack_bf16(dq[n][2] * a.scale, dq[n][3] * a.scale);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int it = 0; it < 2; ++it) {
+            const int r = it * 8 + (lane >> 2);
+            const int i = mt * 16 + r;
+            if (i < kWt) {
+              const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(stage) + r * kRowB + (lane & 3) * 16);
+              *reinterpret_cast<uint4*>(a.dqkv + rows_s[i] * ld_qkv + t.h * kHd + (lane & 3) * 8) = v;
+            }
+          }
+          __syncwarp();
         }
       }
     }
-    __syncwarp();
+    // dK (scaled) and dV rows of this warp's keys: stage 16 rows at a time, 64-B row segments out
+#pragma unroll
+    for (int jt = 0; jt < 2; ++jt)
+#pragma unroll
+      for (int which = 0; which < 2; ++which) {
+        __syncwarp();
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+          const float(&src)[4] = which == 0 ? dk[jt][n] : dv[jt][n];
+          const float f = which == 0 ? a.scale : 1.0f;
+          *reinterpret_cast<uint32_t*>(stage + g * kPitch + n * 8 + tq * 2) = pack_bf16(src[0] * f, src[1] * f);
+          *reinterpret_cast<uint32_t*>(stage + (g + 8) * kPitch + n * 8 + tq * 2) = pack_bf16(src[2] * f, src[3] * f);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+          const int r = it * 8 + (lane >> 2);
+          const int j = w * 32 + jt * 16 + r;
+          if (j < kWt) {
+            const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(stage) + r * kRowB + (lane & 3) * 16);
+            *reinterpret_cast<uint4*>(a.dqkv + rows_s[j] * ld_qkv + (which == 0 ? 1 : 2) * a.C + t.h * kHd + (lane & 3) * 8) = v;
+          }
+        }
+      }
   }
   // fold the per-lane accumulators into the 13 x 13 bins (once per warp), then one partial row per CTA
 #pragma unroll 1
   for (int sl = 0; sl < kSlots; ++sl) {
-    const int mt = sl / 28, n = (sl % 28) >> 2, e = sl & 3;
-    const int i = mt * 16 + g + ((e & 2) ? 8 : 0), j = n * 8 + tq * 2 + (e & 1);
+    const int mt = sl >> 4, n = (sl >> 2) & 3, e = sl & 3;
+    const int i = mt * 16 + g + ((e & 2) ? 8 : 0), j = w * 32 + n * 8 + tq * 2 + (e & 1);
     if (i < kWt && j < kWt) {
       const int ri = i / kWs, ci = i - ri * kWs, rj = j / kWs, cj = j - rj * kWs;
       atomicAdd(&bins[(rj - ri + kWs - 1) * (2 * kWs - 1) + (cj - ci + kWs - 1)], __ldcg(slots + sl * 32));
@@ -573,14 +589,14 @@ extern "C" int b200_window_attn_fwd(const void* qkv, const float* pos, void* out
 
 extern "C" int b200_window_attn_bwd_blocks(int B, int H, int W, int heads) {
   const long long ntasks = 1LL * B * (H / kWs) * (W / kWs) * heads;
-  long long blocks = (ntasks + kBwdWarps - 1) / kBwdWarps;
-  const long long cap = 1LL * b200_num_sms() * 2;
+  long long blocks = (ntasks + kPairs - 1) / kPairs;
+  const long long cap = 1LL * b200_num_sms();
   if (blocks > cap) blocks = cap;
   return blocks < 1 ? 1 : static_cast<int>(blocks);
 }
 
 // floats per CTA of the scratch that follows the [blocks, 169] partial rows in `dpos_partial`
-extern "C" long long b200_window_attn_bwd_scratch_floats(int blocks) { return 1LL * blocks * (kBins + kBwdWarps * kSlots * 32); }
+extern "C" long long b200_window_attn_bwd_scratch_floats(int blocks) { return 1LL * blocks * (kBins + 2 * kPairs * kSlots * 32); }
 
 extern "C" int b200_window_attn_bwd(const void* qkv, const float* pos, const void* o, const float* lse, const void* dout,
                                     void* dqkv, float* dpos, float* dpos_partial, int accumulate_dpos, int B, int H, int W,
@@ -598,7 +614,7 @@ extern "C" int b200_window_attn_bwd(const void* qkv, const float* pos, const voi
   static bool attr = false;
   if (!attr) { B200_CHECK_CUDA(cudaFuncSetAttribute(window_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem)); attr = true; }
   auto st = reinterpret_cast<cudaStream_t>(stream);
-  launch_pdl(window_attn_bwd_kernel, dim3(blocks), dim3(kBwdWarps * 32), kBwdSmem, st, a);
+  launch_pdl(window_attn_bwd_kernel, dim3(blocks), dim3(kBwdThreads), kBwdSmem, st, a);
   B200_LAUNCH_CHECK();
   launch_pdl(dpos_reduce_kernel, dim3(1), dim3(192), 0, st, dpos_partial, dpos, blocks, accumulate_dpos);
   B200_LAUNCH_CHECK();

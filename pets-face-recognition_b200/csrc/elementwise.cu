@@ -15,6 +15,13 @@ __device__ __forceinline__ void ld8(const bf16* p, float* x) {
   f = unpack_bf16(u.z); x[4] = f.x; x[5] = f.y;
   f = unpack_bf16(u.w); x[6] = f.x; x[7] = f.y;
 }
+__device__ __forceinline__ void unpack8(const uint4& u, float* x) {
+  float2 f;
+  f = unpack_bf16(u.x); x[0] = f.x; x[1] = f.y;
+  f = unpack_bf16(u.y); x[2] = f.x; x[3] = f.y;
+  f = unpack_bf16(u.z); x[4] = f.x; x[5] = f.y;
+  f = unpack_bf16(u.w); x[6] = f.x; x[7] = f.y;
+}
 __device__ __forceinline__ void st8(bf16* p, const float* x) {
   uint4 u;
   u.x = pack_bf16(x[0], x[1]); u.y = pack_bf16(x[2], x[3]); u.z = pack_bf16(x[4], x[5]); u.w = pack_bf16(x[6], x[7]);
@@ -111,8 +118,12 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restri
 // dres_in, which are the bias gradient of the Linear that produced the residual branch (fc2 / to_out) - are
 // register partials per thread over its rows, CTA-reduced through smem, one [3C] partial row per CTA
 // (reduced by splitk_reduce in a fixed order -> deterministic).
+constexpr int kLnBwdThreads = 128;
+// resident CTAs per SM the register budget is tuned for (two row groups of raw loads + the column partials per thread)
+constexpr int ln_bwd_ctas_per_sm(int maxit) { return maxit == 1 ? 4 : (maxit == 2 ? 3 : (maxit == 3 ? 2 : 1)); }
+
 template <int LPR, int MAXIT, bool WITH_RES>
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+__global__ void __launch_bounds__(kLnBwdThreads, ln_bwd_ctas_per_sm(MAXIT)) layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                                                             const float* __restrict__ gamma, const float* __restrict__ mean,
                                                             const float* __restrict__ rstd, const bf16* dres,
                                                             bf16* dx, float* __restrict__ partial,
@@ -131,10 +142,35 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restri
 #pragma unroll
     for (int i = 0; i < 8; ++i) { dg[it][i] = 0.f; db[it][i] = 0.f; if (WITH_RES) dr[it][i] = 0.f; }
 
-  for (long long row0 = warp_global * RPW; row0 < M; row0 += nwarps * RPW) {
+  // software pipeline: the raw (packed bf16) loads of the warp's next row group are in flight while the current one is
+  // reduced, so every warp keeps two row groups of dy / x / dres outstanding
+  uint4 rd[MAXIT], rx[MAXIT], rr[MAXIT];
+  float mu_n = 0.f, rs_n = 0.f;
+  auto fetch = [&](long long row) {
+    const bool live = row < M;
+    mu_n = live ? mean[row] : 0.f;
+    rs_n = live ? rstd[row] : 0.f;
+#pragma unroll
+    for (int it = 0; it < MAXIT; ++it) {
+      const int ch = l + it * LPR;
+      if (live && ch < chunks) {
+        rd[it] = *reinterpret_cast<const uint4*>(dy + row * C + ch * 8);
+        rx[it] = *reinterpret_cast<const uint4*>(x + row * C + ch * 8);
+        if (dres) rr[it] = *reinterpret_cast<const uint4*>(dres + row * C + ch * 8);
+      }
+    }
+  };
+  const long long stride = nwarps * RPW;
+  long long row0 = warp_global * RPW;
+  if (row0 < M) fetch(row0 + sub);
+  for (; row0 < M; row0 += stride) {
     const long long row = row0 + sub;
     const bool live = row < M;
-    const float mu = live ? mean[row] : 0.f, rs = live ? rstd[row] : 0.f;
+    const float mu = mu_n, rs = rs_n;
+    uint4 cd[MAXIT], cx[MAXIT], cr[MAXIT];
+#pragma unroll
+    for (int it = 0; it < MAXIT; ++it) { cd[it] = rd[it]; cx[it] = rx[it]; cr[it] = rr[it]; }
+    if (row0 + stride < M) fetch(row0 + stride + sub);
     float g[MAXIT][8], xh[MAXIT][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -142,8 +178,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restri
       const int ch = l + it * LPR;
       if (live && ch < chunks) {
         float d[8], xv[8], gm[8];
-        ld8(dy + row * C + ch * 8, d);
-        ld8(x + row * C + ch * 8, xv);
+        unpack8(cd[it], d);
+        unpack8(cx[it], xv);
         ld8f(gamma + ch * 8, gm);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -171,7 +207,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const bf16* __restri
           for (int i = 0; i < 8; ++i) o[i] = rs * (g[it][i] - s1 - xh[it][i] * s2);
           if (dres) {
             float r[8];
-            ld8(dres + row * C + ch * 8, r);
+            unpack8(cr[it], r);
 #pragma unroll
             for (int i = 0; i < 8; ++i) { o[i] += r[i]; if (WITH_RES) dr[it][i] += r[i]; }
           }
@@ -507,15 +543,15 @@ int ln_fwd_launch(const bf16* x, const float* g, const float* b, bf16* y, float*
 template <int LPR, int MAXIT>
 int ln_bwd_launch(const bf16* dy, const bf16* x, const float* g, const float* mean, const float* rstd, const bf16* dres, bf16* dx,
                   float* partial, long long M, int C, int blocks, bool with_res, cudaStream_t st) {
-  const size_t smem = sizeof(float) * 8 * 3 * C;
+  const size_t smem = sizeof(float) * (kLnBwdThreads / 32) * 3 * C;
   if (with_res) {
     if (smem > 48 * 1024)
       B200_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<LPR, MAXIT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    launch_pdl(layernorm_bwd_kernel<LPR, MAXIT, true>, dim3(blocks), dim3(256), smem, st, dy, x, g, mean, rstd, dres, dx, partial, M, C);
+    launch_pdl(layernorm_bwd_kernel<LPR, MAXIT, true>, dim3(blocks), dim3(kLnBwdThreads), smem, st, dy, x, g, mean, rstd, dres, dx, partial, M, C);
   } else {
     if (smem > 48 * 1024)
       B200_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<LPR, MAXIT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    launch_pdl(layernorm_bwd_kernel<LPR, MAXIT, false>, dim3(blocks), dim3(256), smem, st, dy, x, g, mean, rstd, dres, dx, partial, M, C);
+    launch_pdl(layernorm_bwd_kernel<LPR, MAXIT, false>, dim3(blocks), dim3(kLnBwdThreads), smem, st, dy, x, g, mean, rstd, dres, dx, partial, M, C);
   }
   B200_LAUNCH_CHECK();
   return B200_OK;
@@ -540,11 +576,12 @@ extern "C" int b200_layernorm_fwd(const void* x, const float* gamma, const float
   return ln_fwd_launch<32, 6>(X, gamma, beta, Y, mean, rstd, M, C, eps, st);
 }
 
-// 256-thread CTAs; each CTA ends with a cross-warp reduction and one [3C] partial row, so CTAs are kept fat (>= 256
-// rows) and their number at the resident capacity (register-limited: 4 per SM for C <= 256, 2 per SM above)
+// 128-thread CTAs; each CTA ends with a cross-warp reduction and one [3C] partial row, so CTAs are kept fat (>= 64
+// rows) and their number at the resident capacity (register-limited, see ln_bwd_ctas_per_sm)
 extern "C" int b200_layernorm_bwd_blocks(long long M, int C) {
-  long long b = (M + 255) / 256;
-  const int cap = b200_num_sms() * (C <= 256 ? 4 : 2);
+  long long b = (M + 63) / 64;
+  const int maxit = C <= 256 ? 1 : (C <= 512 ? 2 : (C <= 768 ? 3 : 6));
+  const int cap = b200_num_sms() * ln_bwd_ctas_per_sm(maxit);
   if (b > cap) b = cap;
   return b < 1 ? 1 : static_cast<int>(b);
 }

@@ -5,13 +5,14 @@
 //
 //  phase 1  cosine_filter_kernel: fp16 unit rows, Q block (128 queries x dim) resident in smem, gallery tiles of
 //           256 rows streamed by TMA, tcgen05.mma into two 256-column TMEM accumulators; the epilogue never
-//           writes the N x M score matrix: each thread owns one query row, compares its 256 scores per tile
-//           against a running threshold (max-tree over 32 scores, one compare) and appends the rare survivors to a
-//           per-row candidate list, pruned warp-cooperatively by an exact radix select if it fills.
-//           Large galleries run it twice: a first pass over 1/16 of the rows yields, per query, the score of its
-//           KP-th best row there - a threshold that can only be BELOW the KP-th best of the whole gallery, hence safe -
-//           and the second pass over the remaining rows starts from that threshold, so it appends ~16 KP rows per query
-//           instead of flooding and re-pruning its lists in every chunk.
+//           writes the N x M score matrix: eight epilogue warps (a TMEM lane quadrant x a 128-column half each) let every
+//           thread own one query row: it compares its scores against a running threshold (max-tree over 32 scores, one
+//           compare), turns the rare survivors into a bit mask and appends them to a per-(row, half) candidate list,
+//           pruned warp-cooperatively by a radix select when it fills.
+//           Large galleries run it twice.  A first "witness" pass over the first 8192 rows keeps no lists at all: per
+//           query it takes the maximum of each group of 64 scores and the minimum of those 128 maxima - 128 distinct rows
+//           score at least that much, so it can only be BELOW the KP-th best of the whole gallery, hence a safe starting
+//           threshold (it passes ~9 % of the rows).  The second pass over all rows starts from it instead of flooding.
 //  phase 2  rerank_kernel: the <= KP candidates per (query, gallery chunk) are re-scored EXACTLY - fp64 cosine from
 //           the fp32 embeddings - and sorted by (score desc, gallery index asc): the deterministic order that
 //           oracle/rank_oracle.py:topk_spec defines, so indices are bit-exact regardless of fp16 error as long as
@@ -33,17 +34,21 @@ constexpr int kMaxKB = 8;           // dim <= 512
 constexpr int kBStages = 3;
 constexpr int kQSlab = kBM * kBK * 2;        // 16 KB
 constexpr int kBStage = kBN * kBK * 2;       // 32 KB
-constexpr int kCap = 512;           // candidate list capacity per query row (entries of 8 B)
-constexpr int kKP = 128;            // candidates kept per (query, chunk)
-constexpr int kThreads = 192;
+constexpr int kHalf = kBN / 2;       // tile columns per epilogue warp
+constexpr int kCap = 384;           // candidate list capacity per (query row, column half) (entries of 8 B)
+constexpr int kKP = 128;            // candidates kept per (query, chunk, column half)
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + 32 * kEpiWarps;     // TMA warp, MMA warp, epilogue warps
+constexpr int kWitnessRows = 32 * kBN;            // rows of the witness pass: 2 halves x 64 groups of 64 = 128 witnesses
 constexpr int kSmem = kMaxKB * kQSlab + kBStages * kBStage + 256 + 1024;
 
 struct FilterParams {
   long long nq;
   long long g_begin, ng;      // gallery rows [g_begin, ng) are scanned
-  const float* tau_init;      // [nq] starting threshold per query, or null (-inf)
-  float* tau_out;             // [nq] receives the score of the KP-th best row found (chunks == 1 only), or null
-  int list_base, lists;       // this launch fills candidate lists [list_base, list_base + chunks) of `lists` per query
+  const float* tau_init;      // [nq][2] starting threshold per query = min of the pair, or null (-inf)
+  float* tau_out;             // witness pass: [nq][2] receives each column half's minimum of group maxima
+  int witness;                // 1: witness pass (no candidate lists)
+  int lists;                  // candidate lists per query = 2 * chunks; (chunk, half) fills list 2 * chunk + half
   int kb;                     // dim / 64
   int chunks;                 // gallery chunks
   long long chunk_rows;       // multiple of 256
@@ -51,7 +56,7 @@ struct FilterParams {
   long long self_offset;      // gallery row (self_offset + q) is excluded for query q
   int exclude_self;
   uint32_t idesc;
-  uint2* scratch;             // [gridDim.x][128][kCap] (score bits, idx)
+  uint2* scratch;             // [gridDim.x][2][128][kCap] (score bits, idx)
   int* cand_idx;              // [q_blocks*128][lists][kKP]
   float* cand_score;          // [q_blocks*128][lists][kKP] fp16-GEMM scores of the survivors (approximate)
   int* cand_cnt;              // [q_blocks*128][lists]
@@ -66,13 +71,18 @@ __device__ __forceinline__ float fkey_inv(uint32_t k) {
   return __uint_as_float(u);
 }
 
-// Warp-cooperative exact prune of one row's list to its best kKP entries (stable: ties keep list order, which is
-// ascending gallery index).  Returns the new count; *tau_out = score of the kKP-th best (or -inf if fewer).
+// Warp-cooperative prune of one row's list to its best kKP entries (stable: ties keep list order, which is ascending
+// gallery index) by a radix select, two key bits per round.  EXACT = false may stop once the upper 16 key bits are fixed
+// and at most kKP + 64 entries share that prefix or beat it: it keeps all of those (the threshold is the prefix's lower
+// edge, still a true lower bound of the kKP-th best) and saves the dependent rounds that would only split ties.
+// Returns the new count; *tau_out = the threshold below which entries were dropped (-inf if nothing was).
+template <bool EXACT>
 __device__ int prune_list(uint2* list, int n, float* tau_out, int lane) {
-  uint32_t key[kCap / 32];
-  uint32_t idx[kCap / 32];
+  constexpr int R = kCap / 32;
+  uint32_t key[R];
+  uint32_t idx[R];
 #pragma unroll
-  for (int i = 0; i < kCap / 32; ++i) {
+  for (int i = 0; i < R; ++i) {
     const int e = i * 32 + lane;
     if (e < n) { const uint2 v = list[e]; key[i] = fkey(__uint_as_float(v.x)); idx[i] = v.y; }
     else { key[i] = 0u; idx[i] = 0u; }     // key 0 is below every real score's key
@@ -82,27 +92,41 @@ __device__ int prune_list(uint2* list, int n, float* tau_out, int lane) {
     return n;
   }
   uint32_t thr = 0;
+  int cge = n;             // entries with key >= thr
+  bool keep_all_ge = false;
 #pragma unroll 1
-  for (int bit = 31; bit >= 0; --bit) {
-    const uint32_t cand = thr | (1u << bit);
-    int c = 0;
+  for (int bit = 30; bit >= 0; bit -= 2) {
+    const uint32_t c1 = thr | (1u << bit), c2 = thr | (2u << bit), c3 = thr | (3u << bit);
+    int n1 = 0, n2 = 0, n3 = 0;
 #pragma unroll
-    for (int i = 0; i < kCap / 32; ++i) c += (key[i] >= cand) ? 1 : 0;
-    c = __reduce_add_sync(0xffffffffu, c);
-    if (c >= kKP) thr = cand;
+    for (int i = 0; i < R; ++i) {
+      n1 += (key[i] >= c1) ? 1 : 0;
+      n2 += (key[i] >= c2) ? 1 : 0;
+      n3 += (key[i] >= c3) ? 1 : 0;
+    }
+    n1 = __reduce_add_sync(0xffffffffu, n1);
+    n2 = __reduce_add_sync(0xffffffffu, n2);
+    n3 = __reduce_add_sync(0xffffffffu, n3);
+    if (n3 >= kKP) { thr = c3; cge = n3; }
+    else if (n2 >= kKP) { thr = c2; cge = n2; }
+    else if (n1 >= kKP) { thr = c1; cge = n1; }
+    if (!EXACT && bit <= 16 && thr != 0u && cge <= kKP + 64) { keep_all_ge = true; break; }
   }
-  int n_gt = 0;
+  int eq_left = 0;
+  if (!keep_all_ge) {
+    int n_gt = 0;
 #pragma unroll
-  for (int i = 0; i < kCap / 32; ++i) n_gt += (key[i] > thr) ? 1 : 0;
-  n_gt = __reduce_add_sync(0xffffffffu, n_gt);
-  int eq_left = kKP - n_gt;
+    for (int i = 0; i < R; ++i) n_gt += (key[i] > thr) ? 1 : 0;
+    n_gt = __reduce_add_sync(0xffffffffu, n_gt);
+    eq_left = kKP - n_gt;
+  }
   __syncwarp();
   int base = 0;
   const uint32_t lt_mask = (1u << lane) - 1u;
 #pragma unroll
-  for (int i = 0; i < kCap / 32; ++i) {
-    const bool gt = key[i] > thr;
-    const bool eq = key[i] == thr;
+  for (int i = 0; i < R; ++i) {
+    const bool gt = keep_all_ge ? (key[i] >= thr) : (key[i] > thr);
+    const bool eq = !keep_all_ge && key[i] == thr;
     const uint32_t m_eq = __ballot_sync(0xffffffffu, eq);
     const bool eq_keep = eq && (__popc(m_eq & lt_mask) < eq_left);
     const bool keep = gt || eq_keep;
@@ -114,6 +138,20 @@ __device__ int prune_list(uint2* list, int n, float* tau_out, int lane) {
   __syncwarp();
   *tau_out = fkey_inv(thr);
   return base;
+}
+
+// value i of the 32 held in two 16-register arrays, by a 5-level select tree (a dynamic register index would spill)
+__device__ __forceinline__ float pick32(const uint32_t (&a)[16], const uint32_t (&b)[16], int i) {
+  uint32_t t[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) t[j] = (i & 16) ? b[j] : a[j];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) t[j] = (i & 8) ? t[j + 8] : t[j];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) t[j] = (i & 4) ? t[j + 4] : t[j];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) t[j] = (i & 2) ? t[j + 2] : t[j];
+  return __uint_as_float((i & 1) ? t[1] : t[0]);
 }
 
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -157,7 +195,7 @@ cosine_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_g);
     for (int s = 0; s < kBStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), CLUSTER); }   // every CTA of the cluster releases a slot
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kEpiWarps); }
     mbar_init(qfull_bar, 1);
     mbar_init(qempty_bar, 1);
     mbar_fence_init();
@@ -241,43 +279,76 @@ cosine_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       }
     }
   } else {
-    const int q = warp & 3;
+    const int q = warp & 3;                     // TMEM lane quadrant this warp may read
+    const int half = (warp - 2) >> 2;           // column half of every tile
     const int row = q * 32 + lane;
-    uint2* list = p.scratch + (1LL * blockIdx.x * kBM + row) * kCap;
+    uint2* warp_lists = p.scratch + ((1LL * blockIdx.x * 2 + half) * kBM + q * 32) * kCap;
+    uint2* list = warp_lists + 1LL * lane * kCap;
     int acc = 0; uint32_t acc_phase = 0;
     for (int unit = cluster_id; unit < units; unit += n_clusters) {
       const int qb = (unit % q_groups) * CLUSTER + crank, chunk = unit / q_groups;
       const long long qrow = 1LL * qb * kBM + row;
       const bool live = qrow < p.nq;
-      const long long self_col = p.exclude_self ? (p.self_offset + qrow) : LLONG_MIN;
+      const long long self_col = p.exclude_self ? (p.self_offset + qrow) : -(1LL << 62);
       const long long g0 = p.g_begin + 1LL * chunk * p.chunk_rows;
       const long long g1 = min(p.ng, g0 + p.chunk_rows);
       const int nt = tiles_of(chunk);
-      float tau = (live && p.tau_init != nullptr) ? p.tau_init[qrow] : -INFINITY;
+      float tau = -INFINITY;
+      if (live && p.tau_init != nullptr) tau = fminf(p.tau_init[2 * qrow], p.tau_init[2 * qrow + 1]);
       int cnt = 0;
+      float wmin = INFINITY, grp = -INFINITY;        // witness pass: min over 64-column groups of the group maximum
       for (int t = 0; t < nt; ++t) {
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * kBN);
-        const long long col0 = g0 + 1LL * t * kBN;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * kBN + half * kHalf);
+        const long long col0 = g0 + 1LL * t * kBN + half * kHalf;
 #pragma unroll 1
-        for (int c = 0; c < kBN; c += 32) {
+        for (int c = 0; c < kHalf; c += 32) {
           uint32_t r0[16], r1[16];
           tmem_ld16(taddr + c, r0);
           tmem_ld16(taddr + c + 16, r1);
           tmem_ld_wait();
-          // one max-tree + one compare per 32 scores; the element-wise scan runs only for the rare groups with a survivor
           float mx = -INFINITY;
 #pragma unroll
           for (int i = 0; i < 16; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(r0[i]), __uint_as_float(r1[i])));
-          if (live && mx > tau) {
+          const long long cbase = col0 + c;
+          const long long ds = self_col - cbase;
+          if (p.witness) {
+            if (static_cast<unsigned long long>(ds) < 32ULL) {      // the query itself is no witness: maximum of the other 31
+              mx = -INFINITY;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float v = __uint_as_float(i < 16 ? r0[i] : r1[i - 16]);
-              if (v > tau) {
-                const long long col = col0 + c + i;
-                if (col < g1 && col != self_col && cnt < kCap) { list[cnt] = make_uint2(__float_as_uint(v), static_cast<uint32_t>(col)); ++cnt; }
+              for (int i = 0; i < 32; ++i)
+                if (i != static_cast<int>(ds)) mx = fmaxf(mx, __uint_as_float(i < 16 ? r0[i] : r1[i - 16]));
+            }
+            grp = fmaxf(grp, mx);
+            if (c & 32) { wmin = fminf(wmin, grp); grp = -INFINITY; }
+            continue;
+          }
+          // one max-tree + one compare per 32 scores.  Some lane of the warp nearly always has a survivor, so the slow
+          // path is branch-free up to the (usually single) append: a bit mask of the survivors, then one loop over its bits
+          if (live && mx > tau) {
+            uint32_t mask = 0u;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) mask |= (__uint_as_float(i < 16 ? r0[i] : r1[i - 16]) > tau) ? (1u << i) : 0u;
+            const bool single = (mask & (mask - 1u)) == 0u;       // then the survivor is the maximum itself
+            const long long rem = g1 - cbase;
+            if (static_cast<unsigned long long>(ds) < 32ULL) mask &= ~(1u << static_cast<int>(ds));
+            if (rem < 32) mask &= (rem <= 0) ? 0u : ((1u << static_cast<int>(rem)) - 1u);
+            if (__popc(mask) <= 6) {
+              while (mask != 0u && cnt < kCap) {
+                const int i = __ffs(mask) - 1;
+                mask &= mask - 1u;
+                const float v = single ? mx : pick32(r0, r1, i);
+                list[cnt] = make_uint2(__float_as_uint(v), static_cast<uint32_t>(cbase + i));
+                ++cnt;
               }
+            } else {       // a flood (unseeded threshold): walk the registers in order instead of selecting each survivor
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (((mask >> i) & 1u) && cnt < kCap) {
+                  list[cnt] = make_uint2(i < 16 ? r0[i] : r1[i - 16], static_cast<uint32_t>(cbase + i));
+                  ++cnt;
+                }
             }
           }
         }
@@ -286,48 +357,49 @@ cosine_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         if (lane == 0) mbar_arrive(tempty_bar(acc));
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
-        // keep room for a full tile of survivors: prune rows whose list passed half capacity
-        uint32_t need = __ballot_sync(0xffffffffu, cnt > kCap - kBN);
+        // keep room for a full half tile of survivors
+        uint32_t need = __ballot_sync(0xffffffffu, cnt > kCap - kHalf);
         while (need) {
           const int src = __ffs(need) - 1;
           need &= need - 1;
           const int n = __shfl_sync(0xffffffffu, cnt, src);
-          uint2* l = p.scratch + (1LL * blockIdx.x * kBM + q * 32 + src) * kCap;
           float new_tau;
-          const int m = prune_list(l, n, &new_tau, lane);
+          const int m = prune_list<false>(warp_lists + 1LL * src * kCap, n, &new_tau, lane);
           if (lane == src) { cnt = m; tau = fmaxf(tau, new_tau); }
         }
       }
-      // unit done: final prune, then hand the survivors (gallery indices) to phase 2
-      {
-        uint32_t need = __ballot_sync(0xffffffffu, cnt > kKP);
-        while (need) {
-          const int src = __ffs(need) - 1;
-          need &= need - 1;
-          const int n = __shfl_sync(0xffffffffu, cnt, src);
-          uint2* l = p.scratch + (1LL * blockIdx.x * kBM + q * 32 + src) * kCap;
-          float new_tau;
-          const int m = prune_list(l, n, &new_tau, lane);
-          if (lane == src) cnt = m;
-        }
-        __syncwarp();
-        if (qb < p.q_blocks) {
-        const long long li = qrow * p.lists + p.list_base + chunk;
-        int* dst = p.cand_idx + li * kKP;
-        float* dsc = p.cand_score + li * kKP;
-        float mn = INFINITY;
-        for (int i = 0; i < cnt; ++i) {
-          const uint2 e = list[i];
-          dst[i] = static_cast<int>(e.y);
-          dsc[i] = __uint_as_float(e.x);
-          mn = fminf(mn, __uint_as_float(e.x));
-        }
-        p.cand_cnt[li] = live ? cnt : 0;
-        if (p.tau_out != nullptr && live)      // KP-th best of the rows seen so far: a lower bound of the KP-th best overall
-          p.tau_out[qrow] = (cnt >= kKP) ? mn : (p.tau_init != nullptr ? p.tau_init[qrow] : -INFINITY);
-        }
-        __syncwarp();
+      if (p.witness) {
+        // 1e-6 below the weakest witness: the filter compares with >, and a tie with the threshold must survive
+        if (live) p.tau_out[2 * qrow + half] = wmin - 1e-6f;
+        continue;
       }
+      // unit done: exact final prune, then hand the survivors (gallery indices) to phase 2, one row at a time, coalesced
+      __syncwarp();
+      uint32_t need = __ballot_sync(0xffffffffu, cnt > kKP);
+      while (need) {
+        const int src = __ffs(need) - 1;
+        need &= need - 1;
+        const int n = __shfl_sync(0xffffffffu, cnt, src);
+        float new_tau;
+        const int m = prune_list<true>(warp_lists + 1LL * src * kCap, n, &new_tau, lane);
+        if (lane == src) cnt = m;
+      }
+      __syncwarp();
+      if (qb < p.q_blocks) {
+        for (int r = 0; r < 32; ++r) {
+          const int n = __shfl_sync(0xffffffffu, cnt, r);
+          const long long rq = 1LL * qb * kBM + q * 32 + r;
+          const long long li = rq * p.lists + 2 * chunk + half;
+          const uint2* src = warp_lists + 1LL * r * kCap;
+          for (int i = lane; i < n; i += 32) {
+            const uint2 e = src[i];
+            p.cand_idx[li * kKP + i] = static_cast<int>(e.y);
+            p.cand_score[li * kKP + i] = __uint_as_float(e.x);
+          }
+          if (lane == 0) p.cand_cnt[li] = n;
+        }
+      }
+      __syncwarp();
     }
   }
   tc_fence_before();
@@ -360,86 +432,130 @@ __device__ void bitonic_sort(Cand* c, int n_pow2) {
     }
 }
 
+// bitonic sort of a power-of-two array by one warp (stages separated by __syncwarp)
+__device__ void warp_bitonic_sort(Cand* c, int n_pow2, int lane) {
+  for (int k = 2; k <= n_pow2; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = lane; i < n_pow2; i += 32) {
+        const int l = i ^ j;
+        if (l > i) {
+          const bool up = (i & k) == 0;
+          const Cand a = c[i], b = c[l];
+          if (up ? cand_before(b, a) : cand_before(a, b)) { c[i] = b; c[l] = a; }
+        }
+      }
+      __syncwarp();
+    }
+}
+
+// One warp per query (no block-wide barriers): approximate select -> exact fp64 re-score -> sort.
 __global__ void __launch_bounds__(256) rerank_kernel(const float* __restrict__ q, const double* __restrict__ q_norm,
                                                      const float* __restrict__ g, const double* __restrict__ g_norm, int dim,
                                                      const int* __restrict__ cand_idx, const float* __restrict__ cand_score,
-                                                     const int* __restrict__ cand_cnt, int lists, int cap, int k,
+                                                     const int* __restrict__ cand_cnt, int lists, long long nq, int k,
                                                      long long g_index_base, int* __restrict__ out_idx, double* __restrict__ out_score) {
   pdl_grid_sync();
   extern __shared__ __align__(16) uint8_t sm[];
-  Cand* sel = reinterpret_cast<Cand*>(sm);                                                     // [kKP] exact stage
-  unsigned long long* keys = reinterpret_cast<unsigned long long*>(sm + kKP * sizeof(Cand));   // [cap] approximate stage
-  __shared__ int s_off[64];
-  __shared__ int s_total;
-  __shared__ int s_cnt[8];
-  __shared__ int s_slot;
-  const long long qi = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    int t = 0;
-    for (int c = 0; c < lists; ++c) { s_off[c] = t; t += cand_cnt[qi * lists + c]; }
-    s_total = t;
-    s_slot = 0;
-  }
-  for (int i = threadIdx.x; i < kKP; i += blockDim.x) { sel[i].score = -INFINITY; sel[i].idx = INT_MAX; }
-  __syncthreads();
-  int total = s_total;
+  const int cap = lists * kKP;
+  uint8_t* mine = sm + static_cast<size_t>(warp) * (kKP * sizeof(Cand) + static_cast<size_t>(cap) * 8);
+  Cand* sel = reinterpret_cast<Cand*>(mine);                                                     // [kKP] exact stage
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(mine + kKP * sizeof(Cand));   // [cap] approximate stage
+  const long long qi = 1LL * blockIdx.x * (blockDim.x >> 5) + warp;
+  if (qi >= nq) return;
+  for (int i = lane; i < kKP; i += 32) { sel[i].score = -INFINITY; sel[i].idx = INT_MAX; sel[i].pad = 0; }
   // unique order-preserving key: (approximate score desc, gallery index asc)  ==  larger key first
+  int total = 0;
   for (int c = 0; c < lists; ++c) {
     const int n = cand_cnt[qi * lists + c];
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    for (int i = lane; i < n; i += 32) {
       const long long src = (qi * lists + c) * kKP + i;
-      keys[s_off[c] + i] = (static_cast<unsigned long long>(fkey(cand_score[src])) << 32) |
-                           static_cast<unsigned long long>(0xffffffffu - static_cast<uint32_t>(cand_idx[src]));
+      keys[total + i] = (static_cast<unsigned long long>(fkey(cand_score[src])) << 32) |
+                        static_cast<unsigned long long>(0xffffffffu - static_cast<uint32_t>(cand_idx[src]));
     }
+    total += n;
   }
-  __syncthreads();
-  // level 1: of the survivors of all passes / chunks only the best kKP by approximate (fp16 tensor-core) score can contain
-  // the exact top-k (same k + 28 slack argument as inside a chunk): exact 64-bit radix select, O(n) per bit
+  __syncwarp();
+  // level 1: of the survivors of all chunks only the best kKP by approximate (fp16 tensor-core) score can contain
+  // the exact top-k (same k + 28 slack argument as inside a chunk).  64-bit radix select, two bits per round; the keys
+  // are unique, so it can stop as soon as exactly kKP keys reach the threshold
   unsigned long long thr = 0ULL;
-  if (total > kKP) {
+  int cge = total;
 #pragma unroll 1
-    for (int bit = 63; bit >= 0; --bit) {
-      const unsigned long long cand = thr | (1ULL << bit);
-      int c = 0;
-      for (int i = threadIdx.x; i < total; i += blockDim.x) c += (keys[i] >= cand) ? 1 : 0;
-      c = __reduce_add_sync(0xffffffffu, c);
-      if (lane == 0) s_cnt[warp] = c;
-      __syncthreads();
-      int t = 0;
-#pragma unroll
-      for (int w = 0; w < 8; ++w) t += s_cnt[w];
-      if (t >= kKP) thr = cand;
-      __syncthreads();
+  for (int bit = 62; bit >= 0 && cge > kKP; bit -= 2) {
+    const unsigned long long c1 = thr | (1ULL << bit), c2 = thr | (2ULL << bit), c3 = thr | (3ULL << bit);
+    int n1 = 0, n2 = 0, n3 = 0;
+    for (int i = lane; i < total; i += 32) {
+      const unsigned long long key = keys[i];
+      n1 += (key >= c1) ? 1 : 0;
+      n2 += (key >= c2) ? 1 : 0;
+      n3 += (key >= c3) ? 1 : 0;
     }
+    n1 = __reduce_add_sync(0xffffffffu, n1);
+    n2 = __reduce_add_sync(0xffffffffu, n2);
+    n3 = __reduce_add_sync(0xffffffffu, n3);
+    if (n3 >= kKP) { thr = c3; cge = n3; }
+    else if (n2 >= kKP) { thr = c2; cge = n2; }
+    else if (n1 >= kKP) { thr = c1; cge = n1; }
   }
-  for (int i = threadIdx.x; i < total; i += blockDim.x)       // keys are unique: exactly min(total, kKP) pass
-    if (keys[i] >= thr) sel[atomicAdd(&s_slot, 1)].idx = static_cast<int>(0xffffffffu - static_cast<uint32_t>(keys[i] & 0xffffffffULL));
-  __syncthreads();
-  total = min(total, kKP);
-  // level 2: exact fp64 cosine of those <= kKP candidates from the fp32 embeddings
+  int nsel = 0;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  for (int i0 = 0; i0 < total; i0 += 32) {
+    const int i = i0 + lane;
+    const bool keep = i < total && keys[i] >= thr;
+    const uint32_t m = __ballot_sync(0xffffffffu, keep);
+    const int pos = nsel + __popc(m & lt_mask);
+    if (keep && pos < kKP) sel[pos].idx = static_cast<int>(0xffffffffu - static_cast<uint32_t>(keys[i] & 0xffffffffULL));
+    nsel += __popc(m);
+  }
+  nsel = min(nsel, kKP);
+  __syncwarp();
+  // level 2: exact fp64 cosine of those <= kKP candidates from the fp32 embeddings (fixed summation order: lane-strided
+  // chains, xor tree), two candidates in flight
   const float* qr = q + qi * dim;
-  const double nq = fmax(q_norm[qi], 1e-8);
-  for (int i = warp; i < total; i += blockDim.x >> 5) {
-    const int gi = sel[i].idx;
-    const float* gr = g + 1LL * gi * dim;
-    double acc = 0.0;
-    for (int d = lane * 4; d < dim; d += 128) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(qr + d));
-      const float4 b = __ldg(reinterpret_cast<const float4*>(gr + d));
-      acc = fma(static_cast<double>(a.x), static_cast<double>(b.x), acc);
-      acc = fma(static_cast<double>(a.y), static_cast<double>(b.y), acc);
-      acc = fma(static_cast<double>(a.z), static_cast<double>(b.z), acc);
-      acc = fma(static_cast<double>(a.w), static_cast<double>(b.w), acc);
+  const double nqd = fmax(q_norm[qi], 1e-8);
+  float4 qa[kMaxKB * kBK / 128];
+#pragma unroll
+  for (int j = 0; j < kMaxKB * kBK / 128; ++j) {
+    const int d = lane * 4 + j * 128;
+    qa[j] = d < dim ? __ldg(reinterpret_cast<const float4*>(qr + d)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int i = 0; i < nsel; i += 2) {
+    const bool two = i + 1 < nsel;
+    const int g0 = sel[i].idx, g1 = two ? sel[i + 1].idx : g0;
+    const float* r0 = g + 1LL * g0 * dim;
+    const float* r1 = g + 1LL * g1 * dim;
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+    for (int j = 0; j < kMaxKB * kBK / 128; ++j) {
+      const int d = lane * 4 + j * 128;
+      if (d >= dim) break;
+      const float4 a = qa[j];
+      const float4 b = __ldg(reinterpret_cast<const float4*>(r0 + d));
+      const float4 c = __ldg(reinterpret_cast<const float4*>(r1 + d));
+      a0 = fma(static_cast<double>(a.x), static_cast<double>(b.x), a0);
+      a1 = fma(static_cast<double>(a.x), static_cast<double>(c.x), a1);
+      a0 = fma(static_cast<double>(a.y), static_cast<double>(b.y), a0);
+      a1 = fma(static_cast<double>(a.y), static_cast<double>(c.y), a1);
+      a0 = fma(static_cast<double>(a.z), static_cast<double>(b.z), a0);
+      a1 = fma(static_cast<double>(a.z), static_cast<double>(c.z), a1);
+      a0 = fma(static_cast<double>(a.w), static_cast<double>(b.w), a0);
+      a1 = fma(static_cast<double>(a.w), static_cast<double>(c.w), a1);
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) sel[i].score = acc / (nq * fmax(g_norm[gi], 1e-8));
+    for (int o = 16; o > 0; o >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    }
+    if (lane == 0) {
+      sel[i].score = a0 / (nqd * fmax(g_norm[g0], 1e-8));
+      if (two) sel[i + 1].score = a1 / (nqd * fmax(g_norm[g1], 1e-8));
+    }
   }
-  __syncthreads();
-  bitonic_sort(sel, kKP);
-  for (int i = threadIdx.x; i < k; i += blockDim.x) {
-    const bool ok = i < total;
+  __syncwarp();
+  warp_bitonic_sort(sel, kKP, lane);
+  for (int i = lane; i < k; i += 32) {
+    const bool ok = i < nsel;
     out_idx[qi * k + i] = ok ? static_cast<int>(sel[i].idx + g_index_base) : -1;
     out_score[qi * k + i] = ok ? sel[i].score : -INFINITY;
   }
@@ -520,28 +636,31 @@ __global__ void recall_hits_kernel(const int* __restrict__ top_idx, long long nq
 struct Layout {
   long long scratch, cand_idx, cand_score, cand_cnt, tau, total;
   int q_blocks, lists;
-  long long pre0_rows;         // rows [0, pre0_rows): seed pass (floods its lists, tiny)
-  long long pre_rows;          // rows [pre0_rows, pre_rows): threshold pass (0 = single pass over everything)
-  int chunks;                  // gallery chunks of the main pass
+  long long witness_rows;      // rows [0, witness_rows) seed the thresholds (0 = single pass, unseeded)
+  int chunks;                  // gallery chunks of the list pass
   long long chunk_rows;
-  int ctas_pre, ctas;
   long long ng;                // gallery rows
-  float* tau_ptr;              // [q_blocks*128] thresholds handed from pass to pass
+  float* tau_ptr;              // [q_blocks*128][2] thresholds handed from the witness pass to the list pass
 };
 
-// chunks for `rows` gallery rows: enough (q_block, chunk) units to fill the SMs ~6 times, chunks >= 16 tiles, and the unit
-// count close to a multiple of the CTA count (the units are equal-sized: a ragged last wave is pure loss)
+// chunks for `rows` gallery rows.  A chunk starts from the seeded threshold again, so every extra chunk costs ~KP ln(..)
+// more candidate appends per query and one more pair of lists to merge: with at least two query blocks per SM there is
+// one chunk; below that, enough (q_block, chunk) units to fill the SMs ~3 times, chunks >= 16 tiles, and the unit count
+// close to a multiple of the CTA count (the units are equal-sized: a ragged last wave is pure loss)
 void pick_chunks(long long rows, int q_blocks, int sms, int* chunks, long long* chunk_rows) {
   const long long tiles = (rows + kBN - 1) / kBN;
-  long long want = (6LL * sms + q_blocks - 1) / q_blocks;
-  const long long cap = std::max<long long>(1, std::min<long long>(tiles / 16, 31));
-  want = std::max<long long>(1, std::min(want, cap));
-  long long best = want;
-  double best_waste = 1e9;
-  for (long long c = want; c <= std::min(cap, want * 2); ++c) {
-    const long long units = c * q_blocks, ctas = std::min<long long>(units, sms);
-    const double waste = static_cast<double>((units + ctas - 1) / ctas * ctas - units) / units;
-    if (waste < best_waste - 1e-9) { best_waste = waste; best = c; }
+  long long best = 1;
+  if (q_blocks < 2 * sms) {
+    long long want = (3LL * sms + q_blocks - 1) / q_blocks;
+    const long long cap = std::max<long long>(1, std::min<long long>(tiles / 16, 31));
+    want = std::max<long long>(1, std::min(want, cap));
+    best = want;
+    double best_waste = 1e9;
+    for (long long c = want; c <= std::min(cap, want * 2); ++c) {
+      const long long units = c * q_blocks, ctas = std::min<long long>(units, sms);
+      const double waste = static_cast<double>((units + ctas - 1) / ctas * ctas - units) / units;
+      if (waste < best_waste - 1e-9) { best_waste = waste; best = c; }
+    }
   }
   const long long tpc = (tiles + best - 1) / best;
   *chunk_rows = tpc * kBN;
@@ -552,22 +671,16 @@ Layout plan_layout(long long nq, long long ng) {
   Layout L;
   L.q_blocks = static_cast<int>((nq + kBM - 1) / kBM);
   const int sms = b200_num_sms();
-  L.pre_rows = L.pre0_rows = 0;
-  if (ng >= 16LL * 4096) {                                                   // thresholds from the first 1/16 of the rows,
-    L.pre_rows = (ng / 16 + kBN - 1) / kBN * kBN;                            // itself seeded from the first 1024 rows
-    L.pre0_rows = 4 * kBN;
-  }
-  pick_chunks(ng - L.pre_rows, L.q_blocks, sms, &L.chunks, &L.chunk_rows);
-  L.lists = L.chunks + (L.pre_rows ? 2 : 0);
-  L.ctas_pre = std::min(L.q_blocks, sms);
-  L.ctas = static_cast<int>(std::min<long long>(1LL * L.q_blocks * L.chunks, sms));
+  L.witness_rows = (ng >= 4LL * kWitnessRows) ? kWitnessRows : 0;      // small galleries: the unseeded flood is cheaper
+  pick_chunks(ng, L.q_blocks, sms, &L.chunks, &L.chunk_rows);
+  L.lists = 2 * L.chunks;
   long long off = 0;
   auto take = [&](long long bytes) { long long o = off; off = (off + bytes + 255) / 256 * 256; return o; };
-  L.scratch = take(1LL * sms * kBM * kCap * 8);
+  L.scratch = take(1LL * sms * 2 * kBM * kCap * 8);
   L.cand_idx = take(1LL * L.q_blocks * kBM * L.lists * kKP * 4);
   L.cand_score = take(1LL * L.q_blocks * kBM * L.lists * kKP * 4);
   L.cand_cnt = take(1LL * L.q_blocks * kBM * L.lists * 4);
-  L.tau = take(1LL * L.q_blocks * kBM * 4);
+  L.tau = take(1LL * L.q_blocks * kBM * 2 * 4);
   L.total = off;
   return L;
 }
@@ -623,12 +736,12 @@ int max_clusters() {
   return cached;
 }
 
-// the three passes of one top-k call; clusters when there are enough query blocks to fill them
+// the passes of one top-k call; clusters when there are enough query blocks to fill them
 int launch_filter(const CUtensorMap& tq, const CUtensorMap& tg, const CUtensorMap& tg_slice, FilterParams p, const Layout& L, cudaStream_t st) {
   const int sms = b200_num_sms();
   const int ncl = max_clusters();
-  static const bool env_off = [] { const char* e = getenv("B200_GALLERY_CLUSTER"); return e != nullptr && e[0] == '0'; }();
-  const bool use_cluster = !env_off && ncl > 0 && L.q_blocks >= 2 * kCluster;
+  static const bool env_on = [] { const char* e = getenv("B200_GALLERY_CLUSTER"); return e != nullptr && e[0] == '1'; }();
+  const bool use_cluster = env_on && ncl > 0 && L.q_blocks >= 2 * kCluster;
   auto run = [&](int units_single) -> int {
     if (use_cluster) {
       const int q_groups = (L.q_blocks + kCluster - 1) / kCluster;
@@ -638,16 +751,14 @@ int launch_filter(const CUtensorMap& tq, const CUtensorMap& tg, const CUtensorMa
     return launch_one<1>(tq, tg, p, std::min(units_single, sms), st);
   };
   int rc;
-  if (L.pre_rows > 0) {      // threshold passes: one chunk each, exact streaming top-KP of the rows they scan
-    p.g_begin = 0; p.ng = L.pre0_rows; p.chunks = 1; p.chunk_rows = L.pre0_rows; p.list_base = 0;
-    p.tau_init = nullptr; p.tau_out = L.tau_ptr;
-    if ((rc = run(L.q_blocks))) return rc;
-    p.g_begin = L.pre0_rows; p.ng = L.pre_rows; p.chunk_rows = L.pre_rows - L.pre0_rows; p.list_base = 1;
-    p.tau_init = L.tau_ptr; p.tau_out = L.tau_ptr;
+  p.g_begin = 0;
+  if (L.witness_rows > 0) {
+    p.ng = L.witness_rows; p.chunks = 1; p.chunk_rows = L.witness_rows;
+    p.witness = 1; p.tau_init = nullptr; p.tau_out = L.tau_ptr;
     if ((rc = run(L.q_blocks))) return rc;
   }
-  p.g_begin = L.pre_rows; p.ng = L.ng; p.chunks = L.chunks; p.chunk_rows = L.chunk_rows; p.list_base = L.pre_rows ? 2 : 0;
-  p.tau_init = L.pre_rows ? L.tau_ptr : nullptr; p.tau_out = nullptr;
+  p.ng = L.ng; p.chunks = L.chunks; p.chunk_rows = L.chunk_rows;
+  p.witness = 0; p.tau_init = L.witness_rows ? L.tau_ptr : nullptr; p.tau_out = nullptr;
   return run(L.q_blocks * L.chunks);
 }
 
@@ -708,11 +819,13 @@ extern "C" int b200_cosine_topk(const float* q, const void* q_unit_f16, const do
   if (rc) return rc;
   rc = launch_filter(tq, tg, tg_slice, p, L, st);
   if (rc) return rc;
-  const int n_pow2 = L.lists * kKP;        // candidate capacity per query
-  const int smem2 = kKP * static_cast<int>(sizeof(Cand)) + n_pow2 * 8;
+  const int per_warp = kKP * static_cast<int>(sizeof(Cand)) + L.lists * kKP * 8;      // exact stage + candidate keys of one query
+  const int wpc = std::max(1, std::min(8, (200 * 1024) / per_warp));                  // queries (warps) per CTA
+  const int smem2 = wpc * per_warp;
+  B200_REQUIRE(per_warp <= 200 * 1024, "cosine_topk: too many candidate lists");
   if (smem2 > 48 * 1024) B200_CHECK_CUDA(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
-  launch_pdl(rerank_kernel, dim3(static_cast<unsigned>(nq)), dim3(256), smem2, st, q, q_norm, g, g_norm, dim, p.cand_idx, p.cand_score, p.cand_cnt, L.lists, n_pow2, k,
-                                                               g_index_base, out_idx, out_score);
+  launch_pdl(rerank_kernel, dim3(static_cast<unsigned>((nq + wpc - 1) / wpc)), dim3(32 * wpc), smem2, st, q, q_norm, g, g_norm, dim, p.cand_idx,
+             p.cand_score, p.cand_cnt, L.lists, nq, k, g_index_base, out_idx, out_score);
   B200_LAUNCH_CHECK();
   return B200_OK;
 }

@@ -2,7 +2,7 @@
 
     ncu --set full --clock-control none --import-source on -k regex:<kernel> -c 1 -o gpurun_out/<name> python tools/prof_kernels.py <what>
 
-what: attn_bwd | attn_fwd | gemm_fc1 | gemm_qkv | gemm_fc2 | gemm_wgrad | ln | gallery
+what: attn_bwd | attn_fwd | gemm_fc1 | gemm_qkv | gemm_fc2 | gemm_wgrad | ln | gallery | gallery_big
 Each op runs 3 times (the first launches warm the caches / instruction memory); capture with -s to skip warm-ups.
 """
 import sys
@@ -61,6 +61,20 @@ def main(what, stage=0, B=256):
         gal = torch.randn(262144, 512, device='cuda', generator=g)
         for _ in range(2):
             gallery.cosine_topk(q, gal, 100)
+    elif what == 'gallery_big':      # the bench leg's size per GPU, timed with events (not for use under ncu)
+        from b200 import gallery
+        q = torch.randn(50000, 512, device='cuda', generator=g)
+        gal = torch.randn(125000, 512, device='cuda', generator=g)
+        for _ in range(2):
+            gallery.cosine_topk(q, gal, 100)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            gallery.cosine_topk(q, gal, 100)
+        e1.record()
+        torch.cuda.synchronize()
+        print('gallery_big ms/call', e0.elapsed_time(e1) / 5)
     torch.cuda.synchronize()
     print('done', what)
 
