@@ -111,28 +111,32 @@ __device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
-// erf-GELU (nn.GELU() default, models/swin.py:41) and its derivative.  erf by Abramowitz-Stegun 7.1.26
-// (|error| <= 1.5e-7, far below bf16 resolution): one EX2 + one RCP + 5 FMA, and exp(-x^2/2) is shared
-// between erf(x / sqrt 2) and the Gaussian pdf of the derivative.
-__device__ __forceinline__ void gelu_parts(float x, float& erf_v, float& gauss) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));   // MUFU.RCP (an IEEE-rounded reciprocal costs ~40 instructions)
-  gauss = exp2f(-0.72134752044448170f * x * x);          // exp(-x^2 / 2)
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  erf_v = copysignf(fmaf(-poly * t, gauss, 1.0f), x);
+// Exact-erf GELU (nn.GELU() default, models/swin.py:41) from the Abramowitz-Stegun 7.1.26 rational approximation of erfc
+// (|error| <= 1.5e-7, far below bf16 resolution), arranged for the GEMM epilogues, which are ALU-bound:
+//   w(x) = 0.5 erfc(|x| / sqrt 2) = t (a1' + t (a2' + ..)) exp(-x^2 / 2),  t = 1 / (1 + p |x| / sqrt 2),  ai' = ai / 2
+//   gelu(x)  = x Phi(x)          = max(x, 0) - |x| w(x)                                   (12 instructions, 2 MUFU)
+//   gelu'(x) = Phi(x) + x phi(x) = [x >= 0] - copysign(w, x) + x exp(-x^2 / 2) / sqrt(2 pi)
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ void gelu_parts(float x, float& w, float& gauss) {
+  const float t = rcp_approx(fmaf(0.3275911f * 0.70710678118654752f, fabsf(x), 1.0f));
+  gauss = ex2_approx(-0.72134752044448170f * (x * x));          // exp(-x^2 / 2)
+  float poly = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  poly = fmaf(poly, t, 0.5f * 1.421413741f);
+  poly = fmaf(poly, t, 0.5f * -0.284496736f);
+  poly = fmaf(poly, t, 0.5f * 0.254829592f);
+  w = poly * t * gauss;
 }
 __device__ __forceinline__ float gelu_erf(float x) {
-  float e, g;
-  gelu_parts(x, e, g);
-  return 0.5f * x * (1.0f + e);
+  float w, g;
+  gelu_parts(x, w, g);
+  return fmaf(-fabsf(x), w, fmaxf(x, 0.0f));
 }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  float e, g;
-  gelu_parts(x, e, g);
-  return fmaf(x * 0.39894228040143268f, g, 0.5f * (1.0f + e));
+  float w, g;
+  gelu_parts(x, w, g);
+  const float phi_cdf = (x >= 0.0f ? 1.0f : 0.0f) - copysignf(w, x);
+  return fmaf(x * 0.39894228040143268f, g, phi_cdf);
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
