@@ -103,7 +103,9 @@ int b200_window_attn_fwd(const void* qkv, const float* pos_embedding, void* out,
                          int heads, int shifted, void* stream);
 int b200_window_attn_bwd_blocks(int B, int H, int W, int heads);
 long long b200_window_attn_bwd_scratch_floats(int blocks); /* size (floats) of the `dpos_partial` scratch buffer */
-int b200_window_attn_bwd(const void* qkv, const float* pos_embedding, const void* out, const float* lse, const void* dout,
+/* backward from (qkv, lse, dout) alone: P is recomputed from the saved row log-sum-exp and rowsum(P o dP) stands in for
+ * rowsum(dout o out), so the forward output is not an input */
+int b200_window_attn_bwd(const void* qkv, const float* pos_embedding, const float* lse, const void* dout,
                          void* dqkv, float* dpos, float* dpos_partial, int accumulate_dpos, int B, int H, int W, int C,
                          int heads, int shifted, void* stream);
 

@@ -59,7 +59,7 @@ _PROTOS = {
     'b200_window_attn_fwd': (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
     'b200_window_attn_bwd_blocks': (c_int, [c_int, c_int, c_int, c_int]),
     'b200_window_attn_bwd_scratch_floats': (c_ll, [c_int]),
-    'b200_window_attn_bwd': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int,
+    'b200_window_attn_bwd': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int,
                                      c_int, c_vp]),
     'b200_unit_rows': (c_int, [c_vp, c_vp, c_vp, c_ll, c_int, c_ll, c_float, c_int, c_vp]),
     'b200_margin_logits': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_float, c_float, c_int, c_int, c_vp, c_ll, c_vp, c_vp]),

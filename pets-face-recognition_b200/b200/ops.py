@@ -141,12 +141,12 @@ def window_attn_fwd(qkv, pos, B, H, W, Cc, heads, shifted, want_lse=True):
     return out, lse
 
 
-def window_attn_bwd(qkv, pos, out, lse, dout, B, H, W, Cc, heads, shifted):
+def window_attn_bwd(qkv, pos, lse, dout, B, H, W, Cc, heads, shifted):
     dqkv = torch.empty_like(qkv)
     dpos = torch.empty(169, device=qkv.device, dtype=torch.float32)
     blocks = lib().b200_window_attn_bwd_blocks(B, H, W, heads)
     partial = torch.empty(lib().b200_window_attn_bwd_scratch_floats(blocks), device=qkv.device, dtype=torch.float32)
-    check(lib().b200_window_attn_bwd(ptr(qkv), ptr(pos), ptr(out), ptr(lse), ptr(dout), ptr(dqkv), ptr(dpos), ptr(partial), 0,
+    check(lib().b200_window_attn_bwd(ptr(qkv), ptr(pos), ptr(lse), ptr(dout), ptr(dqkv), ptr(dpos), ptr(partial), 0,
                                      B, H, W, Cc, heads, int(shifted), stream_ptr()), 'window_attn_bwd')
     return dqkv, dpos.view(13, 13)
 

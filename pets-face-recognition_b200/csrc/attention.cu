@@ -1,10 +1,10 @@
 // Fused (shifted-)window attention, forward and backward, for the berniwal-variant Swin block
-// (reference models/swin.py:101-135).  One warp owns one (window, head) problem: 49 tokens x 32 dims,
-// padded to 64 x 32, entirely in registers + a private smem slab:
+// (reference models/swin.py:101-135).  One (window, head) problem is 49 tokens x 32 dims, padded to 64 x 32, and lives
+// entirely in registers + a private smem slab of one warp (forward) or one warp pair (backward):
 //
 //   forward : S = Q K^T * scale + relpos + shift masks -> softmax -> O = P V            (P never leaves registers)
 //   backward: recompute P from the saved row log-sum-exp; dV = P^T dO, dP = dO V^T,
-//             dS = P o (dP - rowsum(dO o O)), dQ = scale dS K, dK = scale dS^T Q, dpos[bin] += dS
+//             dS = P o (dP - rowsum(P o dP)), dQ = scale dS K, dK = scale dS^T Q, dpos[bin] += dS
 //
 // The cyclic shift (roll -3 / +3) and the window partition are pure addressing here: token (r, c) of
 // window (wy, wx) lives at pixel ((7 wy + r + off) mod H, (7 wx + c + off) mod W), off = 3 for shifted
@@ -13,8 +13,10 @@
 // GEMM ([q|k|v] chunks, (head, dim) inside a chunk).
 //
 // 49-token problems are far below the 64/128-row tcgen05 atom and carry 3 % of the network's FLOPs, so
-// the matmuls use warp-level mma.sync m16n8k16 (bf16 in, fp32 accumulate); the kernel is HBM-bound:
-// it reads q, k, v once and writes o once (64-B row segments, 16 B per lane).
+// the matmuls use warp-level mma.sync m16n8k16 (bf16 in, fp32 accumulate).  The kernels are bound by the latency of
+// their gathered loads, so both are software-pipelined: the cp.async loads of a warp's NEXT task stream into the second
+// half of a double-buffered slab while the current task is computed.  Tiles are 64-B rows with the 16-B chunk index
+// XOR-swizzled by (row >> 1) & 3, which makes every ldmatrix phase conflict-free without padding.
 #include "common.cuh"
 
 #include "b200_fe.h"
@@ -24,12 +26,13 @@ namespace {
 constexpr int kWs = 7;
 constexpr int kWt = 49;
 constexpr int kHd = 32;
-constexpr int kPitch = 40;                         // bf16 elements per smem row (80 B: conflict-free ldmatrix)
-constexpr int kRowB = kPitch * 2;                  // 80 B
+constexpr int kRowB = 64;                          // bytes per tile row (32 bf16)
 constexpr int kTileRows = 50;                      // 49 token rows + one all-zero row that stands in for rows 49..63
-constexpr int kTileBytes = kTileRows * kRowB;      // 4000
-constexpr int kStageBytes = 16 * kRowB;            // 1280: one 16-row output tile
-constexpr int kWarps = 4;                          // forward: warps (= tasks in flight) per CTA
+constexpr int kTileBytes = kTileRows * kRowB;      // 3200
+constexpr int kPitch = 40;                         // bf16 elements per row of the 16-row output staging tile (80 B)
+constexpr int kStageRowB = kPitch * 2;
+constexpr int kStageBytes = 16 * kStageRowB;       // 1280
+constexpr int kFwdWarps = 10;                      // forward: one CTA of 10 warps per SM, one task in flight + one streaming per warp
 constexpr int kBins = 169;
 constexpr int kBiasPitch = 72;                     // floats per row of the 64 x 64 bias table (conflict-free float2 reads)
 constexpr int kBiasBytes = 64 * kBiasPitch * 4;    // 18432
@@ -43,7 +46,6 @@ struct AttnArgs {
   float* lse;           // [B*H*W, heads] row log-sum-exp (nullable in inference)
   const float* pos;     // [13*13] relative position table of this block
   const bf16* dout;     // bwd: grad wrt attention output [B*H*W, C]
-  const bf16* o;        // bwd: saved attention output
   bf16* dqkv;           // bwd: [B*H*W, 3C]
   float* dpos_partial;  // bwd: [gridDim.x, 169]
   float* dslots;        // bwd: [gridDim.x * warps][64][32] per-lane dS accumulators (L2-resident scratch)
@@ -65,20 +67,28 @@ __device__ __forceinline__ void mma16816(float (&d)[4], uint32_t a0, uint32_t a1
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ float fast_exp2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
 
-// byte offset of tile row r inside a slab: rows >= 49 all read the shared zero row (row 49)
-__device__ __forceinline__ uint32_t trow(int r) { return static_cast<uint32_t>(min(r, kWt) * kRowB); }
+// byte offset of (tile row r, 16-B chunk c) inside a slab: rows >= 49 all read the shared zero row (row 49)
+__device__ __forceinline__ uint32_t sw_off(int r, int c) {
+  r = min(r, kWt);
+  return static_cast<uint32_t>(r * kRowB + ((c ^ ((r >> 1) & 3)) << 4));
+}
 // per-lane ldmatrix offsets.  A-type: 16 rows of m-tile `mt`, k-step kk (16 dims).
-__device__ __forceinline__ uint32_t off_a(int mt, int kk, int lane) { return trow(mt * 16 + (lane & 15)) + (kk * 16 + (lane >> 4) * 8) * 2; }
+__device__ __forceinline__ uint32_t off_a(int mt, int kk, int lane) { return sw_off(mt * 16 + (lane & 15), kk * 2 + (lane >> 4)); }
 // B operand from an [n][k] slab, non-transposed: n-tile pair np (16 rows), k-step kk
 __device__ __forceinline__ uint32_t off_b(int np, int kk, int lane) {
-  return trow(np * 16 + (lane & 7) + (lane >> 4) * 8) + (kk * 16 + ((lane >> 3) & 1) * 8) * 2;
+  return sw_off(np * 16 + (lane & 7) + (lane >> 4) * 8, kk * 2 + ((lane >> 3) & 1));
 }
 // B operand from a [k][n] slab, transposed load: k-step kk (16 rows), n-tile pair np (16 dims)
 __device__ __forceinline__ uint32_t off_bt(int kk, int np, int lane) {
-  return trow(kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) + ((np * 2 + (lane >> 4)) * 8) * 2;
+  return sw_off(kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, np * 2 + (lane >> 4));
 }
 
 struct Task {
@@ -100,15 +110,26 @@ __device__ __forceinline__ Task decode_task(const AttnArgs& a, long long task) {
 }
 
 // global token row of window token i (0..48)
-__device__ __forceinline__ long long token_row(const AttnArgs& a, const Task& t, int i) {
+__device__ __forceinline__ int token_row(const AttnArgs& a, const Task& t, int i) {
   const int off = a.shifted ? kWs / 2 : 0;
   const int r = i / kWs, c = i - r * kWs;
   int y = t.wy * kWs + r + off;
   int x = t.wx * kWs + c + off;
   if (y >= a.H) y -= a.H;
   if (x >= a.W) x -= a.W;
-  return (1LL * t.b * a.H + y) * a.W + x;
+  return (t.b * a.H + y) * a.W + x;
 }
+
+// The 49 token rows of a task, two per lane (tokens lane and lane + 32), handed around by shuffles
+struct Rows {
+  int r0, r1;
+  __device__ __forceinline__ void compute(const AttnArgs& a, const Task& t, int lane) {
+    r0 = token_row(a, t, lane);
+    r1 = lane + 32 < kWt ? token_row(a, t, lane + 32) : 0;
+  }
+  // row of token i; `hi` (i >= 32) must be warp-uniform
+  __device__ __forceinline__ int get(int i, bool hi) const { return __shfl_sync(0xffffffffu, hi ? r1 : r0, i & 31); }
+};
 
 // 64 x 64 additive score table shared by every window and head of the block (models/swin.py:117-118):
 // bias[i][j] = log2(e) * pos[r_j - r_i + 6][c_j - c_i + 6] (scores live in the log2 domain: one FFMA + EX2 per element);
@@ -135,30 +156,30 @@ __device__ __forceinline__ bool shift_masked(const Task& t, int i, int j) {
   return ul || lr;
 }
 
-// load one 49 x 32 bf16 tile (row i of the tile = window token i, 64 B = 4 lanes x 16 B) into a padded slab
-__device__ __forceinline__ void load_tile_async(uint32_t slab, const bf16* base, long long ld, int col0, const long long* rows_s, int lane) {
+// stream one 49 x 32 bf16 tile (row i of the tile = window token i, 64 B = 4 lanes x 16 B) into a swizzled slab
+__device__ __forceinline__ void load_tile_async(uint32_t slab, const bf16* base, long long ld, int col0, const Rows& rows, int lane) {
 #pragma unroll
   for (int it = 0; it < 7; ++it) {
     const int row = it * 8 + (lane >> 2);
-    if (row < kWt) cp_async16(slab + row * kRowB + (lane & 3) * 16, base + rows_s[row] * ld + col0 + (lane & 3) * 8);
+    const int gr = rows.get(row, it >= 4);
+    if (row < kWt) cp_async16(slab + sw_off(row, lane & 3), base + 1LL * gr * ld + col0 + (lane & 3) * 8);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
-constexpr int kFwdWarpBytes = 3 * kTileBytes;                                    // q, k, v (q rows double as the O staging rows)
-constexpr int kFwdSmem = kBiasBytes + kWarps * 64 * 8 + kWarps * kFwdWarpBytes;
+constexpr int kFwdBufBytes = 3 * kTileBytes;                                     // q, k, v (q rows double as the O staging rows)
+constexpr int kFwdWarpBytes = 2 * kFwdBufBytes;
+constexpr int kFwdSmem = kBiasBytes + kFwdWarps * kFwdWarpBytes;
 
-__global__ void __launch_bounds__(kWarps * 32) window_attn_fwd_kernel(const AttnArgs a) {
+__global__ void __launch_bounds__(kFwdWarps * 32, 1) window_attn_fwd_kernel(const AttnArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, tq = lane & 3;
   float* bias_s = reinterpret_cast<float*>(smem);
-  long long* rows_all = reinterpret_cast<long long*>(smem + kBiasBytes);          // [kWarps][64]
-  uint8_t* my = smem + kBiasBytes + kWarps * 64 * 8 + warp * kFwdWarpBytes;
-  const uint32_t qs = smem_u32(my), ks = qs + kTileBytes, vs = ks + kTileBytes;
-  long long* rows_s = rows_all + warp * 64;
+  uint8_t* my = smem + kBiasBytes + warp * kFwdWarpBytes;
+  const uint32_t my_u = smem_u32(my);
 
   build_bias_table(bias_s, a.pos);      // pos is a parameter: not produced by the preceding kernel
   for (int i = lane; i < kFwdWarpBytes / 16; i += 32) reinterpret_cast<uint4*>(my)[i] = make_uint4(0, 0, 0, 0);
@@ -166,18 +187,41 @@ __global__ void __launch_bounds__(kWarps * 32) window_attn_fwd_kernel(const Attn
   pdl_grid_sync();
 
   const long long ntasks = 1LL * a.B * (a.H / kWs) * (a.W / kWs) * a.heads;
+  const long long stride = 1LL * gridDim.x * kFwdWarps;
   const long long ld_qkv = 3LL * a.C;
   const float sc2 = a.scale * kLog2e;               // scores are kept in the log2 domain: one FFMA + EX2 per element
-  for (long long task = 1LL * blockIdx.x * kWarps + warp; task < ntasks; task += 1LL * gridDim.x * kWarps) {
-    const Task t = decode_task(a, task);
+  auto issue = [&](const Task& t, const Rows& rows, int buf) {
+    const uint32_t base = my_u + buf * kFwdBufBytes;
+    load_tile_async(base, a.qkv, ld_qkv, t.h * kHd, rows, lane);
+    load_tile_async(base + kTileBytes, a.qkv, ld_qkv, a.C + t.h * kHd, rows, lane);
+    load_tile_async(base + 2 * kTileBytes, a.qkv, ld_qkv, 2 * a.C + t.h * kHd, rows, lane);
+  };
+
+  long long task = 1LL * blockIdx.x * kFwdWarps + warp;
+  Task t{};
+  Rows rows{};
+  if (task < ntasks) {
+    t = decode_task(a, task);
+    rows.compute(a, t, lane);
+    issue(t, rows, 0);
+  }
+  cp_async_commit();
+  int buf = 0;
+  for (; task < ntasks; task += stride) {
+    // the next task's tiles stream into the other buffer while this one is computed
+    Task tn{};
+    Rows rows_n{};
+    if (task + stride < ntasks) {
+      tn = decode_task(a, task + stride);
+      rows_n.compute(a, tn, lane);
+      issue(tn, rows_n, buf ^ 1);
+    }
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncwarp();
     const bool flagged = t.ul || t.lr;
-    for (int i = lane; i < kWt; i += 32) rows_s[i] = token_row(a, t, i);
-    __syncwarp();
-    load_tile_async(qs, a.qkv, ld_qkv, t.h * kHd, rows_s, lane);
-    load_tile_async(ks, a.qkv, ld_qkv, a.C + t.h * kHd, rows_s, lane);
-    load_tile_async(vs, a.qkv, ld_qkv, 2 * a.C + t.h * kHd, rows_s, lane);
-    cp_async_wait_all();
-    __syncwarp();
+    const uint32_t qs = my_u + buf * kFwdBufBytes, ks = qs + kTileBytes, vs = ks + kTileBytes;
+    uint8_t* qrows = my + buf * kFwdBufBytes;
 
     // K as the B operand of S = Q K^T (n = key j, k = dim d): non-transposed ldmatrix of the [j][d] slab
     uint32_t kf[8][2][2];
@@ -252,28 +296,33 @@ __global__ void __launch_bounds__(kWarps * 32) window_attn_fwd_kernel(const Attn
           mma16816(o[n], pf[2 * kk][0], pf[2 * kk][1], pf[2 * kk + 1][0], pf[2 * kk + 1][1], vf[kk][n][0], vf[kk][n][1]);
       const float r0 = 1.0f / l0, r1 = 1.0f / l1;
       __syncwarp();   // every lane has finished reading this m-tile's Q rows; reuse them as the O staging rows
-      bf16* qrow = reinterpret_cast<bf16*>(my);
 #pragma unroll
       for (int n = 0; n < 4; ++n) {
-        if (i0 < kWt) *reinterpret_cast<uint32_t*>(qrow + i0 * kPitch + n * 8 + tq * 2) = pack_bf16(o[n][0] * r0, o[n][1] * r0);
-        if (i1 < kWt) *reinterpret_cast<uint32_t*>(qrow + i1 * kPitch + n * 8 + tq * 2) = pack_bf16(o[n][2] * r1, o[n][3] * r1);
+        if (i0 < kWt) *reinterpret_cast<uint32_t*>(qrows + sw_off(i0, n) + tq * 4) = pack_bf16(o[n][0] * r0, o[n][1] * r0);
+        if (i1 < kWt) *reinterpret_cast<uint32_t*>(qrows + sw_off(i1, n) + tq * 4) = pack_bf16(o[n][2] * r1, o[n][3] * r1);
       }
+      const int gr0 = rows.get(i0, mt >= 2), gr1 = rows.get(i1, mt >= 2);     // i0, i1 >= 32 <=> mt >= 2 (warp-uniform)
       if (a.lse != nullptr && tq == 0) {            // natural-log LSE of the scaled + biased scores
-        if (i0 < kWt) a.lse[rows_s[i0] * a.heads + t.h] = (m0 + log2f(l0)) * 0.6931471805599453f;
-        if (i1 < kWt) a.lse[rows_s[i1] * a.heads + t.h] = (m1 + log2f(l1)) * 0.6931471805599453f;
+        if (i0 < kWt) a.lse[1LL * gr0 * a.heads + t.h] = (m0 + log2f(l0)) * 0.6931471805599453f;
+        if (i1 < kWt) a.lse[1LL * gr1 * a.heads + t.h] = (m1 + log2f(l1)) * 0.6931471805599453f;
       }
     }
     __syncwarp();
 #pragma unroll
     for (int it = 0; it < 7; ++it) {
       const int row = it * 8 + (lane >> 2);
+      const int gr = rows.get(row, it >= 4);
       if (row < kWt) {
-        const uint4 v = *reinterpret_cast<const uint4*>(my + row * kRowB + (lane & 3) * 16);
-        *reinterpret_cast<uint4*>(a.out + rows_s[row] * a.C + t.h * kHd + (lane & 3) * 8) = v;
+        const uint4 v = *reinterpret_cast<const uint4*>(qrows + sw_off(row, lane & 3));
+        *reinterpret_cast<uint4*>(a.out + 1LL * gr * a.C + t.h * kHd + (lane & 3) * 8) = v;
       }
     }
     __syncwarp();
+    t = tn;
+    rows = rows_n;
+    buf ^= 1;
   }
+  cp_async_wait<0>();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -284,12 +333,17 @@ __global__ void __launch_bounds__(kWarps * 32) window_attn_fwd_kernel(const Attn
 //   dQ_part = dS K_w          (A = dS straight from the accumulator registers; the two halves are summed through smem)
 //   dV_w   += P^T dO,  dK_w += dS^T Q      (A = the 8 x 8 blocks transposed in registers by movmatrix)
 // so no score is recomputed in the key-major orientation and dK / dV never leave registers until the task ends.
+// rowsum(P o dP) is formed from the same fragments (the halves exchange their partial sums through smem), so the saved
+// attention output is not read at all.
 constexpr int kPairs = 6;                          // tasks in flight per CTA (one CTA of 12 warps per SM)
 constexpr int kBwdThreads = kPairs * 64;
 constexpr int kSlots = 4 * 4 * 4;                  // per-lane dS accumulators: [m-tile][n-tile of the warp's 32 keys][fragment element]
 constexpr int kXBytes = 16 * 32 * 4;               // one warp's dQ partial of a 16-query tile, fp32
-constexpr int kPairBytes = 4 * kTileBytes + 2 * kXBytes + 2 * kStageBytes + 64 * 8 + 2 * 64 * 4;     // 23680
+constexpr int kBwdBufBytes = 4 * kTileBytes + 64 * 4;                            // q, k, v, dO tiles + the 64 row LSEs
+// per pair: two buffers, two dQ hand-over slabs, a staging tile per warp, rowsum partials [2][2 warps][16], 2 mbarriers
+constexpr int kPairBytes = 2 * kBwdBufBytes + 2 * kXBytes + 2 * kStageBytes + 2 * 2 * 16 * 4 + 16;
 constexpr int kBwdSmem = kBiasBytes + 704 + kPairs * kPairBytes;
+static_assert(kPairBytes % 16 == 0 && kBwdSmem <= 227 * 1024, "attention backward smem layout");
 
 __device__ __forceinline__ uint32_t movm_t(uint32_t x) {
   uint32_t y;
@@ -298,7 +352,6 @@ __device__ __forceinline__ uint32_t movm_t(uint32_t x) {
 }
 __device__ __forceinline__ void red_add_f32(float* p, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
 __device__ __forceinline__ void pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
-__device__ __forceinline__ void pair_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
 
 __global__ void __launch_bounds__(kBwdThreads, 1) window_attn_bwd_kernel(const AttnArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -308,14 +361,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) window_attn_bwd_kernel(const A
   float* bias_s = reinterpret_cast<float*>(smem);
   float* bins = reinterpret_cast<float*>(smem + kBiasBytes);                                    // [169] (704 B)
   uint8_t* pb = smem + kBiasBytes + 704 + pair * kPairBytes;
-  const uint32_t qs = smem_u32(pb), ks = qs + kTileBytes, vs = ks + kTileBytes, dos = vs + kTileBytes;
-  float* xbuf = reinterpret_cast<float*>(pb + 4 * kTileBytes);                                  // [2][16][32]
-  bf16* stage = reinterpret_cast<bf16*>(pb + 4 * kTileBytes + 2 * kXBytes + w * kStageBytes);
-  long long* rows_s = reinterpret_cast<long long*>(pb + 4 * kTileBytes + 2 * kXBytes + 2 * kStageBytes);
-  float* lse_s = reinterpret_cast<float*>(rows_s + 64);     // log2 domain
-  float* dsum_s = lse_s + 64;
+  const uint32_t pb_u = smem_u32(pb);
+  float* xbuf = reinterpret_cast<float*>(pb + 2 * kBwdBufBytes);                                // [2][16][32]
+  bf16* stage = reinterpret_cast<bf16*>(pb + 2 * kBwdBufBytes + 2 * kXBytes + w * kStageBytes);
+  float* dpart_all = reinterpret_cast<float*>(pb + 2 * kBwdBufBytes + 2 * kXBytes + 2 * kStageBytes);  // [2][2 warps][16]
+  const uint32_t xbar = pb_u + 2 * kBwdBufBytes + 2 * kXBytes + 2 * kStageBytes + 2 * 2 * 16 * 4;      // 2 mbarriers
   float* slots = a.dslots + (1LL * blockIdx.x * (2 * kPairs) + warp) * (kSlots * 32) + lane;       // [slot * 32]
-  const int bar0 = 1 + 2 * pair;                            // named barriers bar0, bar0 + 1 belong to this pair
+  const int bar_id = 1 + pair;                              // named barrier of this pair
 
   build_bias_table(bias_s, a.pos);
   for (int i = threadIdx.x; i < kBins; i += blockDim.x) bins[i] = 0.f;
@@ -323,56 +375,61 @@ __global__ void __launch_bounds__(kBwdThreads, 1) window_attn_bwd_kernel(const A
 #pragma unroll 4
   for (int sl = 0; sl < kSlots; ++sl) __stcg(slots + sl * 32, 0.f);
   __syncthreads();
+  if (w == 0 && lane == 0) {
+    mbar_init(xbar, 1);
+    mbar_init(xbar + 8, 1);
+    mbar_fence_init();
+  }
+  // padded query rows: exp2(x - inf) = 0
+  if (w == 1 && lane >= kWt - 32) {
+    *reinterpret_cast<float*>(pb + 4 * kTileBytes + (32 + lane) * 4) = INFINITY;
+    *reinterpret_cast<float*>(pb + kBwdBufBytes + 4 * kTileBytes + (32 + lane) * 4) = INFINITY;
+  }
+  __syncthreads();
   pdl_grid_sync();
 
   const long long ntasks = 1LL * a.B * (a.H / kWs) * (a.W / kWs) * a.heads;
+  const long long stride = 1LL * gridDim.x * kPairs;
   const long long ld_qkv = 3LL * a.C;
   const float sc2 = a.scale * kLog2e;
-  for (long long task = 1LL * blockIdx.x * kPairs + pair; task < ntasks; task += 1LL * gridDim.x * kPairs) {
-    const Task t = decode_task(a, task);
-    const bool flagged = t.ul || t.lr;
-    pair_sync(bar0);                    // the partner has finished with the previous task's tiles / rows
-    {
-      const int i = w * 32 + lane;
-      if (i < kWt) {
-        const long long r = token_row(a, t, i);
-        rows_s[i] = r;
-        lse_s[i] = a.lse[r * a.heads + t.h] * kLog2e;
-      } else {
-        lse_s[i] = INFINITY;            // padded query rows: exp2(x - inf) = 0
-        dsum_s[i] = 0.f;
-      }
-    }
-    pair_sync(bar0);
+  // warp 0 streams q and k, warp 1 v and dO; each warp the LSE of "its" 32 query rows
+  auto issue = [&](const Task& t, const Rows& rows, int buf) {
+    const uint32_t base = pb_u + buf * kBwdBufBytes;
     if (w == 0) {
-      load_tile_async(qs, a.qkv, ld_qkv, t.h * kHd, rows_s, lane);
-      load_tile_async(ks, a.qkv, ld_qkv, a.C + t.h * kHd, rows_s, lane);
+      load_tile_async(base, a.qkv, ld_qkv, t.h * kHd, rows, lane);
+      load_tile_async(base + kTileBytes, a.qkv, ld_qkv, a.C + t.h * kHd, rows, lane);
     } else {
-      load_tile_async(vs, a.qkv, ld_qkv, 2 * a.C + t.h * kHd, rows_s, lane);
-      load_tile_async(dos, a.dout, a.C, t.h * kHd, rows_s, lane);
+      load_tile_async(base + 2 * kTileBytes, a.qkv, ld_qkv, 2 * a.C + t.h * kHd, rows, lane);
+      load_tile_async(base + 3 * kTileBytes, a.dout, a.C, t.h * kHd, rows, lane);
     }
-    // D_i = sum_d dO[i,d] * O[i,d]  (== rowsum(dP o P)); straight from global while the tiles stream in
-#pragma unroll
-    for (int it2 = 0; it2 < 4; ++it2) {
-      const int it = it2 * 2 + w;
-      const int row = it * 8 + (lane >> 2);
-      float acc = 0.f;
-      if (it < 7 && row < kWt) {
-        const long long off = rows_s[row] * a.C + t.h * kHd + (lane & 3) * 8;
-        const uint4 u = *reinterpret_cast<const uint4*>(a.dout + off);
-        const uint4 o = *reinterpret_cast<const uint4*>(a.o + off);
-        float2 x, y;
-        x = unpack_bf16(u.x); y = unpack_bf16(o.x); acc += x.x * y.x + x.y * y.y;
-        x = unpack_bf16(u.y); y = unpack_bf16(o.y); acc += x.x * y.x + x.y * y.y;
-        x = unpack_bf16(u.z); y = unpack_bf16(o.z); acc += x.x * y.x + x.y * y.y;
-        x = unpack_bf16(u.w); y = unpack_bf16(o.w); acc += x.x * y.x + x.y * y.y;
-      }
-      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-      if (it < 7 && row < kWt && (lane & 3) == 0) dsum_s[row] = acc;
+    const int i = w * 32 + lane;
+    if (i < kWt) cp_async4(base + 4 * kTileBytes + i * 4, a.lse + 1LL * (w ? rows.r1 : rows.r0) * a.heads + t.h);
+  };
+
+  long long task = 1LL * blockIdx.x * kPairs + pair;
+  Task t{};
+  Rows rows{};
+  if (task < ntasks) {
+    t = decode_task(a, task);
+    rows.compute(a, t, lane);
+    issue(t, rows, 0);
+  }
+  cp_async_commit();
+  int buf = 0;
+  for (; task < ntasks; task += stride) {
+    cp_async_wait<0>();
+    pair_sync(bar_id);          // both halves of this task's tiles have landed; the partner is done with the other buffer
+    Task tn{};
+    Rows rows_n{};
+    if (task + stride < ntasks) {
+      tn = decode_task(a, task + stride);
+      rows_n.compute(a, tn, lane);
+      issue(tn, rows_n, buf ^ 1);
     }
-    cp_async_wait_all();
-    pair_sync(bar0);
+    cp_async_commit();
+    const bool flagged = t.ul || t.lr;
+    const uint32_t qs = pb_u + buf * kBwdBufBytes, ks = qs + kTileBytes, vs = ks + kTileBytes, dos = vs + kTileBytes;
+    const float* lse_s = reinterpret_cast<const float*>(pb + buf * kBwdBufBytes + 4 * kTileBytes);
 
     float dv[2][4][4], dk[2][4][4];       // this warp's 32 keys x 32 dims, accumulated over the four query tiles
 #pragma unroll
@@ -388,9 +445,6 @@ __global__ void __launch_bounds__(kBwdThreads, 1) window_attn_bwd_kernel(const A
       float s[4][4], dp[4][4];
 #pragma unroll
       for (int n = 0; n < 4; ++n) { s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f; dp[n][0] = dp[n][1] = dp[n][2] = dp[n][3] = 0.f; }
-      // the running per-lane dS sums live in an L2-resident scratch and are updated by fire-and-forget reductions:
-      // every address is private to one lane, so the order of the additions - hence the sum - is fixed (deterministic)
-      float* sl = slots + mt * (16 * 32);
 #pragma unroll
       for (int kk = 0; kk < 2; ++kk) {
         uint32_t q0, q1, q2, q3, d0, d1, d2, d3;
@@ -413,8 +467,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) window_attn_bwd_kernel(const A
       const int jw = w * 32 + tq * 2;
       const float* b0p = bias_s + i0 * kBiasPitch + jw;
       const float* b1p = bias_s + i1 * kBiasPitch + jw;
-      const float l0 = lse_s[i0], l1 = lse_s[i1], D0 = dsum_s[i0], D1 = dsum_s[i1];
-      uint32_t pf[4][2], df[4][2];
+      const float l0 = lse_s[i0] * kLog2e, l1 = lse_s[i1] * kLog2e;
+      // P (in place of S) and this half's share of D_i = sum_j P_ij dP_ij
+      float D0 = 0.f, D1 = 0.f;
 #pragma unroll
       for (int n = 0; n < 4; ++n) {
         const float2 b0 = *reinterpret_cast<const float2*>(b0p + n * 8);
@@ -429,14 +484,30 @@ __global__ void __launch_bounds__(kBwdThreads, 1) window_attn_bwd_kernel(const A
           if (shift_masked(t, i1, j)) sc[2] = -INFINITY;
           if (shift_masked(t, i1, j + 1)) sc[3] = -INFINITY;
         }
-        float p[4], ds[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) p[e] = fast_exp2(sc[e]);
-        ds[0] = p[0] * (dp[n][0] - D0); ds[1] = p[1] * (dp[n][1] - D0);       // unscaled: `scale` is applied once to dQ / dK
-        ds[2] = p[2] * (dp[n][2] - D1); ds[3] = p[3] * (dp[n][3] - D1);
+        for (int e = 0; e < 4; ++e) s[n][e] = fast_exp2(sc[e]);
+        D0 = fmaf(s[n][0], dp[n][0], fmaf(s[n][1], dp[n][1], D0));
+        D1 = fmaf(s[n][2], dp[n][2], fmaf(s[n][3], dp[n][3], D1));
+      }
+      D0 += __shfl_xor_sync(0xffffffffu, D0, 1); D0 += __shfl_xor_sync(0xffffffffu, D0, 2);
+      D1 += __shfl_xor_sync(0xffffffffu, D1, 1); D1 += __shfl_xor_sync(0xffffffffu, D1, 2);
+      float* dpart = dpart_all + (mt & 1) * 32;        // double-buffered: the partner may still be reading the previous tile's
+      if (tq == 0) { dpart[w * 16 + g] = D0; dpart[w * 16 + g + 8] = D1; }
+      pair_sync(bar_id);
+      D0 += dpart[(w ^ 1) * 16 + g];
+      D1 += dpart[(w ^ 1) * 16 + g + 8];
+      // dS; its per-lane running sums (for the rel-pos gradient) live in an L2-resident scratch and are updated by
+      // fire-and-forget reductions: every address is private to one lane, so the order of the additions is fixed
+      float* sl = slots + mt * (16 * 32);
+      uint32_t pf[4][2], df[4][2];
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        float ds[4];
+        ds[0] = s[n][0] * (dp[n][0] - D0); ds[1] = s[n][1] * (dp[n][1] - D0);       // unscaled: `scale` is applied once to dQ / dK
+        ds[2] = s[n][2] * (dp[n][2] - D1); ds[3] = s[n][3] * (dp[n][3] - D1);
 #pragma unroll
         for (int e = 0; e < 4; ++e) red_add_f32(sl + (n * 4 + e) * 32, ds[e]);
-        pf[n][0] = pack_bf16(p[0], p[1]); pf[n][1] = pack_bf16(p[2], p[3]);
+        pf[n][0] = pack_bf16(s[n][0], s[n][1]); pf[n][1] = pack_bf16(s[n][2], s[n][3]);
         df[n][0] = pack_bf16(ds[0], ds[1]); df[n][1] = pack_bf16(ds[2], ds[3]);
       }
       // dQ (this warp's 32 keys): contraction over keys j
@@ -452,6 +523,17 @@ __global__ void __launch_bounds__(kBwdThreads, 1) window_attn_bwd_kernel(const A
           mma16816(dq[2 * np], df[2 * kk][0], df[2 * kk][1], df[2 * kk + 1][0], df[2 * kk + 1][1], b0, b1);
           mma16816(dq[2 * np + 1], df[2 * kk][0], df[2 * kk][1], df[2 * kk + 1][0], df[2 * kk + 1][1], b2, b3);
         }
+      // the half that does not finish this tile's dQ hands its partial over right away (double-buffered slab + mbarrier)
+      const bool finisher = w == (mt & 1);
+      float* xb = xbuf + (mt & 1) * (16 * 32) + lane;
+      if (!finisher) {
+#pragma unroll
+        for (int n = 0; n < 4; ++n)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) xb[(n * 4 + e) * 32] = dq[n][e];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(xbar + 8 * (mt & 1));
+      }
       // P^T and dS^T as A operands (rows = keys, k = the 16 queries of this tile): transpose the 8 x 8 blocks in registers
       uint32_t pt[4][2], dt[4][2];
 #pragma unroll
@@ -476,45 +558,34 @@ __global__ void __launch_bounds__(kBwdThreads, 1) window_attn_bwd_kernel(const A
           mma16816(dk[jt][2 * np + 1], dt[2 * jt][0], dt[2 * jt + 1][0], dt[2 * jt][1], dt[2 * jt + 1][1], b2, b3);
         }
       }
-      // sum the two key halves of dQ: the warps alternate as writer / finisher, handing over through a double-buffered slab
-      {
-        const int bid = bar0 + (mt & 1);
-        float* xb = xbuf + (mt & 1) * (16 * 32) + lane;
-        if (w != (mt & 1)) {
+      const int gri = rows.get(mt * 16 + (lane >> 2), mt >= 2), gri8 = rows.get(mt * 16 + 8 + (lane >> 2), mt >= 2);
+      if (finisher) {
+        mbar_wait(xbar + 8 * (mt & 1), static_cast<uint32_t>(mt >> 1));     // each barrier completes twice per task
 #pragma unroll
-          for (int n = 0; n < 4; ++n)
+        for (int n = 0; n < 4; ++n)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) xb[(n * 4 + e) * 32] = dq[n][e];
-          __threadfence_block();
-          pair_arrive(bid);
-        } else {
-          pair_sync(bid);
+          for (int e = 0; e < 4; ++e) dq[n][e] += xb[(n * 4 + e) * 32];
 #pragma unroll
-          for (int n = 0; n < 4; ++n)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) dq[n][e] += xb[(n * 4 + e) * 32];
-#pragma unroll
-          for (int n = 0; n < 4; ++n) {
-            *reinterpret_cast<uint32_t*>(stage + g * kPitch + n * 8 + tq * 2) = pack_bf16(dq[n][0] * a.scale, dq[n][1] * a.scale);
-            *reinterpret_cast<uint32_t*>(stage + (g + 8) * kPitch + n * 8 + tq * 2) = pack_bf16(dq[n][2] * a.scale, dq[n][3] * a.scale);
-          }
-          __syncwarp();
-#pragma unroll
-          for (int it = 0; it < 2; ++it) {
-            const int r = it * 8 + (lane >> 2);
-            const int i = mt * 16 + r;
-            if (i < kWt) {
-              const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(stage) + r * kRowB + (lane & 3) * 16);
-              *reinterpret_cast<uint4*>(a.dqkv + rows_s[i] * ld_qkv + t.h * kHd + (lane & 3) * 8) = v;
-            }
-          }
-          __syncwarp();
+        for (int n = 0; n < 4; ++n) {
+          *reinterpret_cast<uint32_t*>(stage + g * kPitch + n * 8 + tq * 2) = pack_bf16(dq[n][0] * a.scale, dq[n][1] * a.scale);
+          *reinterpret_cast<uint32_t*>(stage + (g + 8) * kPitch + n * 8 + tq * 2) = pack_bf16(dq[n][2] * a.scale, dq[n][3] * a.scale);
         }
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+          const int r = it * 8 + (lane >> 2);
+          if (mt * 16 + r < kWt) {
+            const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(stage) + r * kStageRowB + (lane & 3) * 16);
+            *reinterpret_cast<uint4*>(a.dqkv + 1LL * (it ? gri8 : gri) * ld_qkv + t.h * kHd + (lane & 3) * 8) = v;
+          }
+        }
+        __syncwarp();
       }
     }
     // dK (scaled) and dV rows of this warp's keys: stage 16 rows at a time, 64-B row segments out
 #pragma unroll
-    for (int jt = 0; jt < 2; ++jt)
+    for (int jt = 0; jt < 2; ++jt) {
+      const int grj = rows.get(jt * 16 + (lane >> 2), w == 1), grj8 = rows.get(jt * 16 + 8 + (lane >> 2), w == 1);
 #pragma unroll
       for (int which = 0; which < 2; ++which) {
         __syncwarp();
@@ -531,12 +602,17 @@ __global__ void __launch_bounds__(kBwdThreads, 1) window_attn_bwd_kernel(const A
           const int r = it * 8 + (lane >> 2);
           const int j = w * 32 + jt * 16 + r;
           if (j < kWt) {
-            const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(stage) + r * kRowB + (lane & 3) * 16);
-            *reinterpret_cast<uint4*>(a.dqkv + rows_s[j] * ld_qkv + (which == 0 ? 1 : 2) * a.C + t.h * kHd + (lane & 3) * 8) = v;
+            const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(stage) + r * kStageRowB + (lane & 3) * 16);
+            *reinterpret_cast<uint4*>(a.dqkv + 1LL * (it ? grj8 : grj) * ld_qkv + (which == 0 ? 1 : 2) * a.C + t.h * kHd + (lane & 3) * 8) = v;
           }
         }
       }
+    }
+    t = tn;
+    rows = rows_n;
+    buf ^= 1;
   }
+  cp_async_wait<0>();
   // fold the per-lane accumulators into the 13 x 13 bins (once per warp), then one partial row per CTA
 #pragma unroll 1
   for (int sl = 0; sl < kSlots; ++sl) {
@@ -579,10 +655,10 @@ extern "C" int b200_window_attn_fwd(const void* qkv, const float* pos, void* out
   static bool attr = false;
   if (!attr) { B200_CHECK_CUDA(cudaFuncSetAttribute(window_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem)); attr = true; }
   const long long ntasks = 1LL * B * (H / kWs) * (W / kWs) * heads;
-  long long blocks = (ntasks + kWarps - 1) / kWarps;
-  const long long cap = 1LL * b200_num_sms() * 3 * 2;     // 3 resident CTAs per SM, 2 waves (the bias table is built per CTA)
+  long long blocks = (ntasks + kFwdWarps - 1) / kFwdWarps;
+  const long long cap = b200_num_sms();                   // persistent: one CTA per SM
   if (blocks > cap) blocks = cap;
-  launch_pdl(window_attn_fwd_kernel, dim3(static_cast<unsigned>(blocks)), dim3(kWarps * 32), kFwdSmem, reinterpret_cast<cudaStream_t>(stream), a);
+  launch_pdl(window_attn_fwd_kernel, dim3(static_cast<unsigned>(blocks)), dim3(kFwdWarps * 32), kFwdSmem, reinterpret_cast<cudaStream_t>(stream), a);
   B200_LAUNCH_CHECK();
   return B200_OK;
 }
@@ -598,7 +674,7 @@ extern "C" int b200_window_attn_bwd_blocks(int B, int H, int W, int heads) {
 // floats per CTA of the scratch that follows the [blocks, 169] partial rows in `dpos_partial`
 extern "C" long long b200_window_attn_bwd_scratch_floats(int blocks) { return 1LL * blocks * (kBins + 2 * kPairs * kSlots * 32); }
 
-extern "C" int b200_window_attn_bwd(const void* qkv, const float* pos, const void* o, const float* lse, const void* dout,
+extern "C" int b200_window_attn_bwd(const void* qkv, const float* pos, const float* lse, const void* dout,
                                     void* dqkv, float* dpos, float* dpos_partial, int accumulate_dpos, int B, int H, int W,
                                     int C, int heads, int shifted, void* stream) {
   int rc = check_shape(B, H, W, C, heads);
@@ -606,7 +682,7 @@ extern "C" int b200_window_attn_bwd(const void* qkv, const float* pos, const voi
   if (B == 0) return B200_OK;
   const int blocks = b200_window_attn_bwd_blocks(B, H, W, heads);
   AttnArgs a{};
-  a.qkv = reinterpret_cast<const bf16*>(qkv); a.pos = pos; a.o = reinterpret_cast<const bf16*>(o);
+  a.qkv = reinterpret_cast<const bf16*>(qkv); a.pos = pos;
   a.lse = const_cast<float*>(lse); a.dout = reinterpret_cast<const bf16*>(dout); a.dqkv = reinterpret_cast<bf16*>(dqkv);
   a.dpos_partial = dpos_partial;
   a.dslots = dpos_partial + 1LL * blocks * kBins;      // scratch layout: [blocks][169] partial rows, then the per-lane slots

@@ -77,6 +77,9 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 int b200_num_sms();   // cached cudaDevAttrMultiProcessorCount of the current device (148 on B200)
 // out[i] (+)= sum_s partial[s * stride + i], i < n, fixed order (deterministic); stride <= 0 means n
 int splitk_reduce(const float* partial, float* out, long long n, int splits, int accumulate, cudaStream_t stream, long long stride);
+// up to three outputs whose partial rows are adjacent ([splits][ny][n], row pitch `stride`) in one launch
+int splitk_reduce_multi(const float* partial, float* const* outs, int ny, long long n, int splits, int accumulate, cudaStream_t stream,
+                        long long stride);
 // optional per-launch CUDA-event timing of the tcgen05 GEMM kernels (bench.py roofline): no-ops unless enabled
 bool b200_prof_gemm_begin(cudaStream_t stream, double flops);
 void b200_prof_gemm_end(cudaStream_t stream);

@@ -608,11 +608,8 @@ extern "C" int b200_layernorm_bwd(const void* dy, const void* x, const float* ga
   else if (C <= 768) rc = ln_bwd_launch<32, 3>(DY, X, gamma, mean, rstd, DR, DX, partial, M, C, blocks, wr, st);
   else rc = ln_bwd_launch<32, 6>(DY, X, gamma, mean, rstd, DR, DX, partial, M, C, blocks, wr, st);
   if (rc) return rc;
-  rc = splitk_reduce(partial, dgamma, C, blocks, accumulate, st, 3LL * C);
-  if (rc) return rc;
-  rc = splitk_reduce(partial + C, dbeta, C, blocks, accumulate, st, 3LL * C);
-  if (rc || !wr) return rc;
-  return splitk_reduce(partial + 2 * C, dres_colsum, C, blocks, accumulate, st, 3LL * C);
+  float* outs[3] = {dgamma, dbeta, dres_colsum};
+  return splitk_reduce_multi(partial, outs, wr ? 3 : 2, C, blocks, accumulate, st, 3LL * C);
 }
 
 extern "C" int b200_patch_gather_image(const float* img, void* out, int B, int Cin, int H, int W, int df, long long ldo,

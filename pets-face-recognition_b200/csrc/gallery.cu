@@ -47,6 +47,9 @@ struct FilterParams {
   long long g_begin, ng;      // gallery rows [g_begin, ng) are scanned
   const float* tau_init;      // [nq][2] starting threshold per query = min of the pair, or null (-inf)
   float* tau_out;             // witness pass: [nq][2] receives each column half's minimum of group maxima
+  uint32_t* tau_shared;       // [nq] order-preserving keys (0 = unset): best threshold any (chunk, half) list of the query has
+                              // reached - every list's KP-th best is a lower bound of the query's KP-th best overall, so
+                              // the lists of one query, scanned concurrently by different warps / SMs, tighten each other
   int witness;                // 1: witness pass (no candidate lists)
   int lists;                  // candidate lists per query = 2 * chunks; (chunk, half) fills list 2 * chunk + half
   int kb;                     // dim / 64
@@ -295,9 +298,13 @@ cosine_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       const int nt = tiles_of(chunk);
       float tau = -INFINITY;
       if (live && p.tau_init != nullptr) tau = fminf(p.tau_init[2 * qrow], p.tau_init[2 * qrow + 1]);
+      uint32_t* tau_g = (live && !p.witness) ? p.tau_shared + qrow : nullptr;
+      uint32_t shared_key = tau_g != nullptr ? __ldcg(tau_g) : 0u;       // refreshed once per tile, applied one tile later
       int cnt = 0;
       float wmin = INFINITY, grp = -INFINITY;        // witness pass: min over 64-column groups of the group maximum
       for (int t = 0; t < nt; ++t) {
+        if (shared_key != 0u) tau = fmaxf(tau, fkey_inv(shared_key));
+        if (tau_g != nullptr) shared_key = __ldcg(tau_g);
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * kBN + half * kHalf);
@@ -365,7 +372,10 @@ cosine_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
           const int n = __shfl_sync(0xffffffffu, cnt, src);
           float new_tau;
           const int m = prune_list<false>(warp_lists + 1LL * src * kCap, n, &new_tau, lane);
-          if (lane == src) { cnt = m; tau = fmaxf(tau, new_tau); }
+          if (lane == src) {
+            cnt = m;
+            if (new_tau > tau) { tau = new_tau; atomicMax(tau_g, fkey(new_tau)); }
+          }
         }
       }
       if (p.witness) {
@@ -449,7 +459,7 @@ __device__ void warp_bitonic_sort(Cand* c, int n_pow2, int lane) {
 }
 
 // One warp per query (no block-wide barriers): approximate select -> exact fp64 re-score -> sort.
-__global__ void __launch_bounds__(256) rerank_kernel(const float* __restrict__ q, const double* __restrict__ q_norm,
+__global__ void __launch_bounds__(256, 3) rerank_kernel(const float* __restrict__ q, const double* __restrict__ q_norm,
                                                      const float* __restrict__ g, const double* __restrict__ g_norm, int dim,
                                                      const int* __restrict__ cand_idx, const float* __restrict__ cand_score,
                                                      const int* __restrict__ cand_cnt, int lists, long long nq, int k,
@@ -511,45 +521,53 @@ __global__ void __launch_bounds__(256) rerank_kernel(const float* __restrict__ q
   nsel = min(nsel, kKP);
   __syncwarp();
   // level 2: exact fp64 cosine of those <= kKP candidates from the fp32 embeddings (fixed summation order: lane-strided
-  // chains, xor tree), two candidates in flight
+  // chains, xor tree).  The kernel is bound by the latency of the gathered gallery rows: the norms are fetched up front
+  // and four rows (16 x 16 B per lane) are in flight per step
   const float* qr = q + qi * dim;
   const double nqd = fmax(q_norm[qi], 1e-8);
-  float4 qa[kMaxKB * kBK / 128];
+  for (int i = lane; i < nsel; i += 32) sel[i].score = fmax(g_norm[sel[i].idx], 1e-8);     // parked until the dot product lands
+  constexpr int kJ = kMaxKB * kBK / 128;
+  float4 qa[kJ];
 #pragma unroll
-  for (int j = 0; j < kMaxKB * kBK / 128; ++j) {
+  for (int j = 0; j < kJ; ++j) {
     const int d = lane * 4 + j * 128;
     qa[j] = d < dim ? __ldg(reinterpret_cast<const float4*>(qr + d)) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  for (int i = 0; i < nsel; i += 2) {
-    const bool two = i + 1 < nsel;
-    const int g0 = sel[i].idx, g1 = two ? sel[i + 1].idx : g0;
-    const float* r0 = g + 1LL * g0 * dim;
-    const float* r1 = g + 1LL * g1 * dim;
-    double a0 = 0.0, a1 = 0.0;
+  __syncwarp();
+  for (int i = 0; i < nsel; i += 4) {
+    float4 b[4][kJ];
 #pragma unroll
-    for (int j = 0; j < kMaxKB * kBK / 128; ++j) {
-      const int d = lane * 4 + j * 128;
-      if (d >= dim) break;
-      const float4 a = qa[j];
-      const float4 b = __ldg(reinterpret_cast<const float4*>(r0 + d));
-      const float4 c = __ldg(reinterpret_cast<const float4*>(r1 + d));
-      a0 = fma(static_cast<double>(a.x), static_cast<double>(b.x), a0);
-      a1 = fma(static_cast<double>(a.x), static_cast<double>(c.x), a1);
-      a0 = fma(static_cast<double>(a.y), static_cast<double>(b.y), a0);
-      a1 = fma(static_cast<double>(a.y), static_cast<double>(c.y), a1);
-      a0 = fma(static_cast<double>(a.z), static_cast<double>(b.z), a0);
-      a1 = fma(static_cast<double>(a.z), static_cast<double>(c.z), a1);
-      a0 = fma(static_cast<double>(a.w), static_cast<double>(b.w), a0);
-      a1 = fma(static_cast<double>(a.w), static_cast<double>(c.w), a1);
+    for (int c = 0; c < 4; ++c) {
+      const float* r = g + 1LL * sel[min(i + c, nsel - 1)].idx * dim;
+#pragma unroll
+      for (int j = 0; j < kJ; ++j) {
+        const int d = lane * 4 + j * 128;
+        b[c][j] = d < dim ? __ldg(reinterpret_cast<const float4*>(r + d)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    double acc[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      double a0 = 0.0;
+#pragma unroll
+      for (int j = 0; j < kJ; ++j) {
+        if (lane * 4 + j * 128 < dim) {
+          a0 = fma(static_cast<double>(qa[j].x), static_cast<double>(b[c][j].x), a0);
+          a0 = fma(static_cast<double>(qa[j].y), static_cast<double>(b[c][j].y), a0);
+          a0 = fma(static_cast<double>(qa[j].z), static_cast<double>(b[c][j].z), a0);
+          a0 = fma(static_cast<double>(qa[j].w), static_cast<double>(b[c][j].w), a0);
+        }
+      }
+      acc[c] = a0;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
     }
-    if (lane == 0) {
-      sel[i].score = a0 / (nqd * fmax(g_norm[g0], 1e-8));
-      if (two) sel[i + 1].score = a1 / (nqd * fmax(g_norm[g1], 1e-8));
+    if (lane < 4 && i + lane < nsel) {
+      const double a = lane == 0 ? acc[0] : (lane == 1 ? acc[1] : (lane == 2 ? acc[2] : acc[3]));
+      sel[i + lane].score = a / (nqd * sel[i + lane].score);
     }
   }
   __syncwarp();
@@ -634,7 +652,7 @@ __global__ void recall_hits_kernel(const int* __restrict__ top_idx, long long nq
 }
 
 struct Layout {
-  long long scratch, cand_idx, cand_score, cand_cnt, tau, total;
+  long long scratch, cand_idx, cand_score, cand_cnt, tau, tau_shared, total;
   int q_blocks, lists;
   long long witness_rows;      // rows [0, witness_rows) seed the thresholds (0 = single pass, unseeded)
   int chunks;                  // gallery chunks of the list pass
@@ -681,6 +699,7 @@ Layout plan_layout(long long nq, long long ng) {
   L.cand_score = take(1LL * L.q_blocks * kBM * L.lists * kKP * 4);
   L.cand_cnt = take(1LL * L.q_blocks * kBM * L.lists * 4);
   L.tau = take(1LL * L.q_blocks * kBM * 2 * 4);
+  L.tau_shared = take(1LL * L.q_blocks * kBM * 4);
   L.total = off;
   return L;
 }
@@ -809,6 +828,8 @@ extern "C" int b200_cosine_topk(const float* q, const void* q_unit_f16, const do
   p.cand_cnt = reinterpret_cast<int*>(ws + L.cand_cnt);
   L.ng = ng;
   L.tau_ptr = reinterpret_cast<float*>(ws + L.tau);
+  p.tau_shared = reinterpret_cast<uint32_t*>(ws + L.tau_shared);
+  B200_CHECK_CUDA(cudaMemsetAsync(p.tau_shared, 0, sizeof(uint32_t) * L.q_blocks * kBM, st));
   CUtensorMap tq, tg;
   int rc = gemm::encode_tmap_2d(&tq, false, q_unit_f16, dim, nq, dim, kBK, kBM);
   if (rc) return rc;

@@ -261,10 +261,16 @@ struct EpiMargin {
 // ---------------------------------------------------------------------------------------------
 // SL split-lanes cooperate on one float4 column group: lane sx sums splits sx, sx+SL, ... in order, then a fixed
 // smem tree folds the SL partial sums.  The association order depends only on (splits, SL): deterministic.
+// blockIdx.y selects one of up to three outputs whose partials sit side by side ([splits][ny][n]): LayerNorm's dgamma /
+// dbeta / bias-gradient rows are folded by one launch.
+struct ReduceOuts { float* p[3]; };
+
 template <int SL>
-__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, long long n,
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ partial, const ReduceOuts outs, long long n,
                                                             int splits, int accumulate, long long stride) {
   pdl_grid_sync();
+  float* __restrict__ out = outs.p[blockIdx.y];
+  partial += blockIdx.y * n;
   constexpr int CG = 256 / SL;                       // column groups (of 4 floats) per block
   __shared__ float4 red[SL][CG];
   const int cx = threadIdx.x % CG, sx = threadIdx.x / CG;
@@ -297,19 +303,26 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
   }
 }
 
-int splitk_reduce(const float* partial, float* out, long long n, int splits, int accumulate, cudaStream_t stream, long long stride) {
+int splitk_reduce_multi(const float* partial, float* const* outs, int ny, long long n, int splits, int accumulate, cudaStream_t stream,
+                        long long stride) {
   if (stride <= 0) stride = n;
-  B200_REQUIRE(n % 4 == 0 && stride % 4 == 0, "splitk_reduce: n %% 4 != 0");
+  B200_REQUIRE(n % 4 == 0 && stride % 4 == 0 && ny >= 1 && ny <= 3, "splitk_reduce: n %% 4 != 0");
+  ReduceOuts ro{{outs[0], ny > 1 ? outs[1] : nullptr, ny > 2 ? outs[2] : nullptr}};
   const long long groups = n / 4;
+  const unsigned y = static_cast<unsigned>(ny);
   if (splits <= 4) {
-    launch_pdl(splitk_reduce_kernel<1>, dim3((unsigned)((groups + 255) / 256)), dim3(256), 0, stream, partial, out, n, splits, accumulate, stride);
+    launch_pdl(splitk_reduce_kernel<1>, dim3((unsigned)((groups + 255) / 256), y), dim3(256), 0, stream, partial, ro, n, splits, accumulate, stride);
   } else if (splits <= 32 || groups >= 65536) {
-    launch_pdl(splitk_reduce_kernel<8>, dim3((unsigned)((groups + 31) / 32)), dim3(256), 0, stream, partial, out, n, splits, accumulate, stride);
+    launch_pdl(splitk_reduce_kernel<8>, dim3((unsigned)((groups + 31) / 32), y), dim3(256), 0, stream, partial, ro, n, splits, accumulate, stride);
   } else {
-    launch_pdl(splitk_reduce_kernel<32>, dim3((unsigned)((groups + 7) / 8)), dim3(256), 0, stream, partial, out, n, splits, accumulate, stride);
+    launch_pdl(splitk_reduce_kernel<32>, dim3((unsigned)((groups + 7) / 8), y), dim3(256), 0, stream, partial, ro, n, splits, accumulate, stride);
   }
   B200_LAUNCH_CHECK();
   return B200_OK;
+}
+
+int splitk_reduce(const float* partial, float* out, long long n, int splits, int accumulate, cudaStream_t stream, long long stride) {
+  return splitk_reduce_multi(partial, &out, 1, n, splits, accumulate, stream, stride);
 }
 
 // ---------------------------------------------------------------------------------------------

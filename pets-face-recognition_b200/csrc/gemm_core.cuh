@@ -18,7 +18,6 @@
 // serves every layer shape of the network.  Optional split-K (each split writes its own fp32 partial)
 // serves the weight-gradient GEMMs whose contraction runs over all tokens.
 #pragma once
-#include <cstdlib>
 
 #include "common.cuh"
 
@@ -54,10 +53,6 @@ struct CoreParams {
   int out_bytes;             // bytes per output element (2 = bf16, 4 = fp32)
   int box_cols;              // columns per output box (divides block_n; box row = box_cols * out_bytes in {32, 64, 128} B)
   int n_out;                 // 1, or 2 when the epilogue also emits a second tensor (GELU pre-activation)
-  int stg_store;             // 1: boxes leave smem by coalesced 16-B st.global instead of TMA bulk stores
-  uint8_t* out_ptr;          // raw views of the outputs for the st.global path
-  uint8_t* out2_ptr;
-  long long out_pitch, out2_pitch, out_split_pitch;   // bytes
 };
 
 // instruction descriptor, kind::f16: [4,6) D fmt (1=f32), [7,10) A fmt, [10,13) B fmt (0=f16, 1=bf16),
@@ -301,39 +296,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
           }
         }
-        if (p.stg_store) {
-          // the box leaves smem as full 128-B row segments: 32 lanes x 16 B per instruction
-          __syncwarp();
-          const int cpr = static_cast<int>(row_bytes >> 4);                 // 16-B chunks per box row: 2, 4 or 8
-          const int cpr_shift = 31 - __clz(cpr);
-          const int gr0 = m_blk * kBlockM + q * 32, gc = col_tile + c_tile;
-          uint8_t* g1 = p.out_ptr + 1LL * split * p.out_split_pitch + 1LL * gr0 * p.out_pitch + 1LL * gc * OUT_BYTES;
-          uint8_t* g2 = DUAL ? p.out2_ptr + 1LL * gr0 * p.out2_pitch + 1LL * gc * OUT_BYTES : nullptr;
-#pragma unroll 2
-          for (int idx = lane; idx < 32 * cpr; idx += 32) {
-            const int r = idx >> cpr_shift, c16 = idx & (cpr - 1);
-            const uint32_t ro = static_cast<uint32_t>(r) * row_bytes;
-            const uint32_t sa = sbuf + ro + ((static_cast<uint32_t>(c16) << 4) ^ (((ro >> 7) & (cpr - 1)) << 4));
-            if (gr0 + r < p.M && gc + (c16 * 16) / OUT_BYTES < p.N) {
-              uint32_t w0, w1, w2, w3;
-              ld_shared_v4(sa, w0, w1, w2, w3);
-              *reinterpret_cast<uint4*>(g1 + 1LL * r * p.out_pitch + c16 * 16) = make_uint4(w0, w1, w2, w3);
-              if (DUAL) {
-                ld_shared_v4(sa + kBoxBytes, w0, w1, w2, w3);
-                *reinterpret_cast<uint4*>(g2 + 1LL * r * p.out2_pitch + c16 * 16) = make_uint4(w0, w1, w2, w3);
-              }
-            }
-          }
-          if (AUX) fence_proxy_async_smem();   // these generic-proxy reads precede the next aux box the TMA writes here
-        } else {
-          fence_proxy_async_smem();            // generic-proxy smem writes -> visible to the TMA (async proxy)
-          __syncwarp();
-          if (lane == 0) {
-            const int gc = col_tile + c_tile, gr = m_blk * kBlockM + q * 32;
-            tma_store_3d(&tmap_o, sbuf, gc, gr, split);
-            if (DUAL) tma_store_3d(&tmap_o2, sbuf + kBoxBytes, gc, gr, split);
-            bulk_commit();
-          }
+        fence_proxy_async_smem();            // generic-proxy smem writes -> visible to the TMA (async proxy)
+        __syncwarp();
+        if (lane == 0) {
+          const int gc = col_tile + c_tile, gr = m_blk * kBlockM + q * 32;
+          tma_store_3d(&tmap_o, sbuf, gc, gr, split);
+          if (DUAL) tma_store_3d(&tmap_o2, sbuf + kBoxBytes, gc, gr, split);
+          bulk_commit();
         }
         buf ^= 1;
       }
@@ -438,13 +407,6 @@ int launch(const Operands& o, const Output& out, const typename Epi::Params& ep,
   p.box_cols = pick_box_cols(p.block_n, out.elem_bytes);
   p.n_out = out.ptr2 != nullptr ? 2 : 1;
   p.has_aux = out.aux != nullptr ? 1 : 0;
-  static const bool stg_env = [] { const char* e = getenv("B200_GEMM_STG"); return e != nullptr && e[0] == '1'; }();
-  p.stg_store = stg_env ? 1 : 0;
-  p.out_ptr = reinterpret_cast<uint8_t*>(out.ptr);
-  p.out2_ptr = reinterpret_cast<uint8_t*>(out.ptr2);
-  p.out_pitch = 1LL * out.ld * out.elem_bytes;
-  p.out2_pitch = 1LL * out.ld2 * 2;
-  p.out_split_pitch = (p.splits > 1 ? out.split_stride : 1LL * o.M * out.ld) * out.elem_bytes;
   CUtensorMap to, to2, tx;
   rc = encode_tmap_out(&to, out.elem_bytes, out.ptr, o.N, o.M, p.splits, out.ld, p.splits > 1 ? out.split_stride : 1LL * o.M * out.ld,
                        p.box_cols);

@@ -168,7 +168,7 @@ void build(Plan& p) {
     p.partial_bytes = partial;
     p.partial = add_ws(p, partial);
     p.red_partial = add_ws(p, 1LL * 8 * 160 * 3 * 1536 * 4);  // LN (<= 8*SMs rows x 3C) / colsum (<= 2*SMs rows x 4C) partial rows
-    p.dpos_partial = add_ws(p, b200_window_attn_bwd_scratch_floats(2 * 160) * 4);   // <= 2 CTAs per SM
+    p.dpos_partial = add_ws(p, b200_window_attn_bwd_scratch_floats(b200_num_sms()) * 4);   // one CTA per SM
     p.demb16 = add_ws(p, 1LL * p.B * p.num_classes * 2);
     p.dpooled = add_ws(p, 1LL * p.B * C4 * 2);
   }
@@ -306,7 +306,7 @@ int backward(const Ctx& c, const float* demb, int stage_hi, int stage_lo) {
       // ---- attention: x_mid = x_in + Wo attn(LN1(x_in)) + bo
       RC(linear_dgrad(c, g, M, C, c.wc + q.wo16t, C, B200_EPI_STORE, dsmall, nullptr));               // d attn_out
       RC(linear_wgrad(c, g, M, C, c.W<bf16>(a.attn), C, c.G(q.wo)));
-      RC(b200_window_attn_bwd(c.W<bf16>(a.qkv), c.P(q.pos), c.W<bf16>(a.attn), c.W<float>(a.lse), dsmall, dbig, c.G(q.pos),
+      RC(b200_window_attn_bwd(c.W<bf16>(a.qkv), c.P(q.pos), c.W<float>(a.lse), dsmall, dbig, c.G(q.pos),
                               c.W<float>(p.dpos_partial), 0, p.B, S.Hs, S.Hs, C, S.heads, b & 1, c.stv));   // dbig <- d qkv
       RC(linear_dgrad(c, dbig, M, 3 * C, c.wc + q.wqkv16t, C, B200_EPI_STORE, dsmall, nullptr));      // d xn1
       RC(linear_wgrad(c, dbig, M, 3 * C, c.W<bf16>(a.xn1), C, c.G(q.wqkv)));

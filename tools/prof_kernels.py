@@ -33,7 +33,7 @@ def main(what, stage=0, B=256):
         if what == 'attn_bwd':
             dout = rnd(M, C)
             for _ in range(3):
-                ops.window_attn_bwd(qkv, pos, out, lse, dout, B, H, H, C, heads, 1)
+                ops.window_attn_bwd(qkv, pos, lse, dout, B, H, H, C, heads, 1)
     elif what == 'gemm_fc1':
         x, w, b = rnd(M, C), rnd(4 * C, C), torch.randn(4 * C, device='cuda')
         for _ in range(3):
