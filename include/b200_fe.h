@@ -28,9 +28,9 @@ extern "C" {
 
 /* epilogues of b200_gemm_tn */
 #define B200_EPI_STORE 0   /* out = acc (+ bias)                                   nn.Linear                  */
-#define B200_EPI_GELU 1    /* out2 = acc + bias (optional), out = gelu_erf(out2)   models/swin.py:39-41       */
+#define B200_EPI_GELU 1    /* h = acc + bias, out = gelu_erf(h), out2 (optional) = gelu_erf'(h)   models/swin.py:39-41 */
 #define B200_EPI_RESID 2   /* out = acc + bias + aux                               Residual, models/swin.py:22-23 */
-#define B200_EPI_DGELU 3   /* out = acc * gelu_erf'(aux)                           autograd of models/swin.py:41  */
+#define B200_EPI_DGELU 3   /* out = acc * aux, aux = the out2 saved by B200_EPI_GELU          autograd of models/swin.py:41 */
 #define B200_EPI_PARTIAL 4 /* fp32 out[split] = acc   (split-K partial, weight gradients)                     */
 
 /* b200_cosine_topk: pass as exclude_self_offset when no gallery row is to be skipped */

@@ -18,7 +18,7 @@ def _align8(n: int) -> int:
     return (n + 7) // 8 * 8
 
 
-def gemm_tn(a, b, *, mode=abi.EPI_STORE, bias=None, aux=None, out_fp32=False, want_pre=False, splits=1, block_n=0, out=None):
+def gemm_tn(a, b, *, mode=abi.EPI_STORE, bias=None, aux=None, out_fp32=False, want_grad=False, splits=1, block_n=0, out=None):
     """out[M,N] = a[M,K] @ b[N,K]^T with the requested epilogue.  a, b: bf16/fp16 2-D, row pitch = stride(0)."""
     assert a.dim() == 2 and b.dim() == 2 and a.shape[1] == b.shape[1] and a.dtype == b.dtype
     assert a.stride(1) == 1 and b.stride(1) == 1
@@ -34,11 +34,11 @@ def gemm_tn(a, b, *, mode=abi.EPI_STORE, bias=None, aux=None, out_fp32=False, wa
         return out
     if out is None:
         out = torch.empty(M, N, device=dev, dtype=torch.float32 if out_fp32 else bf16)
-    pre = torch.empty(M, N, device=dev, dtype=bf16) if (mode == abi.EPI_GELU and want_pre) else None
+    dact = torch.empty(M, N, device=dev, dtype=bf16) if (mode == abi.EPI_GELU and want_grad) else None
     check(lib().b200_gemm_tn(ptr(a), a.stride(0), ptr(b), b.stride(0), M, N, K, is_bf16, mode, ptr(out), out.stride(0),
-                             1 if out.dtype == torch.float32 else 0, ptr(pre), N, ptr(bias), ptr(aux),
+                             1 if out.dtype == torch.float32 else 0, ptr(dact), N, ptr(bias), ptr(aux),
                              aux.stride(0) if aux is not None else 0, 1, 0, block_n, stream_ptr()), 'gemm_tn')
-    return (out, pre) if mode == abi.EPI_GELU and want_pre else out
+    return (out, dact) if mode == abi.EPI_GELU and want_grad else out
 
 
 def gemm_wgrad(dy, x, splits=1, block_n=0):

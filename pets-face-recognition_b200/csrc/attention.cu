@@ -32,7 +32,6 @@ constexpr int kTileBytes = kTileRows * kRowB;      // 3200
 constexpr int kPitch = 40;                         // bf16 elements per row of the 16-row output staging tile (80 B)
 constexpr int kStageRowB = kPitch * 2;
 constexpr int kStageBytes = 16 * kStageRowB;       // 1280
-constexpr int kFwdWarps = 10;                      // forward: one CTA of 10 warps per SM, one task in flight + one streaming per warp
 constexpr int kBins = 169;
 constexpr int kBiasPitch = 72;                     // floats per row of the 64 x 64 bias table (conflict-free float2 reads)
 constexpr int kBiasBytes = 64 * kBiasPitch * 4;    // 18432
@@ -169,35 +168,53 @@ __device__ __forceinline__ void load_tile_async(uint32_t slab, const bf16* base,
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
+// Two warps share one (window, head) task: its q / k / v tiles are loaded once, warp w computes query tiles 2w and 2w+1.
+// Eight pairs (16 warps) per SM, each with a double-buffered slab.
+constexpr int kFwdPairs = 8;
+constexpr int kFwdThreads = kFwdPairs * 64;
 constexpr int kFwdBufBytes = 3 * kTileBytes;                                     // q, k, v (q rows double as the O staging rows)
-constexpr int kFwdWarpBytes = 2 * kFwdBufBytes;
-constexpr int kFwdSmem = kBiasBytes + kFwdWarps * kFwdWarpBytes;
+constexpr int kFwdPairBytes = 2 * kFwdBufBytes;
+constexpr int kFwdSmem = kBiasBytes + kFwdPairs * kFwdPairBytes;
 
-__global__ void __launch_bounds__(kFwdWarps * 32, 1) window_attn_fwd_kernel(const AttnArgs a) {
+__device__ __forceinline__ void pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+__global__ void __launch_bounds__(kFwdThreads, 1) window_attn_fwd_kernel(const AttnArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pair = warp >> 1, w = warp & 1;
   const int g = lane >> 2, tq = lane & 3;
   float* bias_s = reinterpret_cast<float*>(smem);
-  uint8_t* my = smem + kBiasBytes + warp * kFwdWarpBytes;
-  const uint32_t my_u = smem_u32(my);
+  uint8_t* pb = smem + kBiasBytes + pair * kFwdPairBytes;
+  const uint32_t pb_u = smem_u32(pb);
+  const int bar_id = 1 + pair;
 
   build_bias_table(bias_s, a.pos);      // pos is a parameter: not produced by the preceding kernel
-  for (int i = lane; i < kFwdWarpBytes / 16; i += 32) reinterpret_cast<uint4*>(my)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = w * 32 + lane; i < kFwdPairBytes / 16; i += 64) reinterpret_cast<uint4*>(pb)[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
   pdl_grid_sync();
 
   const long long ntasks = 1LL * a.B * (a.H / kWs) * (a.W / kWs) * a.heads;
-  const long long stride = 1LL * gridDim.x * kFwdWarps;
+  const long long stride = 1LL * gridDim.x * kFwdPairs;
   const long long ld_qkv = 3LL * a.C;
   const float sc2 = a.scale * kLog2e;               // scores are kept in the log2 domain: one FFMA + EX2 per element
+  // the two warps split the rows of each tile (8-row groups alternate)
   auto issue = [&](const Task& t, const Rows& rows, int buf) {
-    const uint32_t base = my_u + buf * kFwdBufBytes;
-    load_tile_async(base, a.qkv, ld_qkv, t.h * kHd, rows, lane);
-    load_tile_async(base + kTileBytes, a.qkv, ld_qkv, a.C + t.h * kHd, rows, lane);
-    load_tile_async(base + 2 * kTileBytes, a.qkv, ld_qkv, 2 * a.C + t.h * kHd, rows, lane);
+    const uint32_t base = pb_u + buf * kFwdBufBytes;
+#pragma unroll
+    for (int it = 0; it < 7; ++it) {
+      const int row = it * 8 + (lane >> 2);
+      const int gr = rows.get(row, it >= 4);
+      if ((it & 1) == w && row < kWt) {
+        const bf16* src = a.qkv + 1LL * gr * ld_qkv + t.h * kHd + (lane & 3) * 8;
+        const uint32_t dst = base + sw_off(row, lane & 3);
+        cp_async16(dst, src);
+        cp_async16(dst + kTileBytes, src + a.C);
+        cp_async16(dst + 2 * kTileBytes, src + 2 * a.C);
+      }
+    }
   };
 
-  long long task = 1LL * blockIdx.x * kFwdWarps + warp;
+  long long task = 1LL * blockIdx.x * kFwdPairs + pair;
   Task t{};
   Rows rows{};
   if (task < ntasks) {
@@ -208,6 +225,8 @@ __global__ void __launch_bounds__(kFwdWarps * 32, 1) window_attn_fwd_kernel(cons
   cp_async_commit();
   int buf = 0;
   for (; task < ntasks; task += stride) {
+    cp_async_wait<0>();
+    pair_sync(bar_id);          // both halves of this task's tiles have landed; the partner is done with the other buffer
     // the next task's tiles stream into the other buffer while this one is computed
     Task tn{};
     Rows rows_n{};
@@ -217,29 +236,13 @@ __global__ void __launch_bounds__(kFwdWarps * 32, 1) window_attn_fwd_kernel(cons
       issue(tn, rows_n, buf ^ 1);
     }
     cp_async_commit();
-    cp_async_wait<1>();
-    __syncwarp();
     const bool flagged = t.ul || t.lr;
-    const uint32_t qs = my_u + buf * kFwdBufBytes, ks = qs + kTileBytes, vs = ks + kTileBytes;
-    uint8_t* qrows = my + buf * kFwdBufBytes;
-
-    // K as the B operand of S = Q K^T (n = key j, k = dim d): non-transposed ldmatrix of the [j][d] slab
-    uint32_t kf[8][2][2];
-#pragma unroll
-    for (int np = 0; np < 4; ++np)
-#pragma unroll
-      for (int kk = 0; kk < 2; ++kk)
-        ldsm_x4(ks + off_b(np, kk, lane), kf[2 * np][kk][0], kf[2 * np][kk][1], kf[2 * np + 1][kk][0], kf[2 * np + 1][kk][1]);
-    // V as the B operand of O = P V (k = key j, n = dim d): transposed ldmatrix of the [j][d] slab
-    uint32_t vf[4][4][2];
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk)
-#pragma unroll
-      for (int np = 0; np < 2; ++np)
-        ldsm_x4_t(vs + off_bt(kk, np, lane), vf[kk][2 * np][0], vf[kk][2 * np][1], vf[kk][2 * np + 1][0], vf[kk][2 * np + 1][1]);
+    const uint32_t qs = pb_u + buf * kFwdBufBytes, ks = qs + kTileBytes, vs = ks + kTileBytes;
+    uint8_t* qrows = pb + buf * kFwdBufBytes;
 
 #pragma unroll 1
-    for (int mt = 0; mt < 4; ++mt) {
+    for (int mi = 0; mi < 2; ++mi) {
+      const int mt = 2 * w + mi;
       float s[8][4];
 #pragma unroll
       for (int n = 0; n < 8; ++n) { s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f; }
@@ -248,7 +251,12 @@ __global__ void __launch_bounds__(kFwdWarps * 32, 1) window_attn_fwd_kernel(cons
         uint32_t a0, a1, a2, a3;
         ldsm_x4(qs + off_a(mt, kk, lane), a0, a1, a2, a3);
 #pragma unroll
-        for (int n = 0; n < 8; ++n) mma16816(s[n], a0, a1, a2, a3, kf[n][kk][0], kf[n][kk][1]);
+        for (int np = 0; np < 4; ++np) {
+          uint32_t b0, b1, b2, b3;      // K as the B operand of S = Q K^T (n = key j, k = dim d)
+          ldsm_x4(ks + off_b(np, kk, lane), b0, b1, b2, b3);
+          mma16816(s[2 * np], a0, a1, a2, a3, b0, b1);
+          mma16816(s[2 * np + 1], a0, a1, a2, a3, b2, b3);
+        }
       }
       const int i0 = mt * 16 + g, i1 = i0 + 8;
       const float* b0p = bias_s + i0 * kBiasPitch + tq * 2;
@@ -292,8 +300,12 @@ __global__ void __launch_bounds__(kFwdWarps * 32, 1) window_attn_fwd_kernel(cons
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk)
 #pragma unroll
-        for (int n = 0; n < 4; ++n)
-          mma16816(o[n], pf[2 * kk][0], pf[2 * kk][1], pf[2 * kk + 1][0], pf[2 * kk + 1][1], vf[kk][n][0], vf[kk][n][1]);
+        for (int np = 0; np < 2; ++np) {
+          uint32_t b0, b1, b2, b3;        // V as the B operand of O = P V (k = key j, n = dim d): transposed ldmatrix
+          ldsm_x4_t(vs + off_bt(kk, np, lane), b0, b1, b2, b3);
+          mma16816(o[2 * np], pf[2 * kk][0], pf[2 * kk][1], pf[2 * kk + 1][0], pf[2 * kk + 1][1], b0, b1);
+          mma16816(o[2 * np + 1], pf[2 * kk][0], pf[2 * kk][1], pf[2 * kk + 1][0], pf[2 * kk + 1][1], b2, b3);
+        }
       const float r0 = 1.0f / l0, r1 = 1.0f / l1;
       __syncwarp();   // every lane has finished reading this m-tile's Q rows; reuse them as the O staging rows
 #pragma unroll
@@ -301,7 +313,7 @@ __global__ void __launch_bounds__(kFwdWarps * 32, 1) window_attn_fwd_kernel(cons
         if (i0 < kWt) *reinterpret_cast<uint32_t*>(qrows + sw_off(i0, n) + tq * 4) = pack_bf16(o[n][0] * r0, o[n][1] * r0);
         if (i1 < kWt) *reinterpret_cast<uint32_t*>(qrows + sw_off(i1, n) + tq * 4) = pack_bf16(o[n][2] * r1, o[n][3] * r1);
       }
-      const int gr0 = rows.get(i0, mt >= 2), gr1 = rows.get(i1, mt >= 2);     // i0, i1 >= 32 <=> mt >= 2 (warp-uniform)
+      const int gr0 = rows.get(i0, w == 1), gr1 = rows.get(i1, w == 1);     // tokens >= 32 <=> the second warp's tiles
       if (a.lse != nullptr && tq == 0) {            // natural-log LSE of the scaled + biased scores
         if (i0 < kWt) a.lse[1LL * gr0 * a.heads + t.h] = (m0 + log2f(l0)) * 0.6931471805599453f;
         if (i1 < kWt) a.lse[1LL * gr1 * a.heads + t.h] = (m1 + log2f(l1)) * 0.6931471805599453f;
@@ -309,15 +321,14 @@ __global__ void __launch_bounds__(kFwdWarps * 32, 1) window_attn_fwd_kernel(cons
     }
     __syncwarp();
 #pragma unroll
-    for (int it = 0; it < 7; ++it) {
-      const int row = it * 8 + (lane >> 2);
-      const int gr = rows.get(row, it >= 4);
+    for (int it2 = 0; it2 < 4; ++it2) {       // this warp's 32 token rows
+      const int row = (4 * w + it2) * 8 + (lane >> 2);
+      const int gr = rows.get(row, w == 1);
       if (row < kWt) {
         const uint4 v = *reinterpret_cast<const uint4*>(qrows + sw_off(row, lane & 3));
         *reinterpret_cast<uint4*>(a.out + 1LL * gr * a.C + t.h * kHd + (lane & 3) * 8) = v;
       }
     }
-    __syncwarp();
     t = tn;
     rows = rows_n;
     buf ^= 1;
@@ -351,7 +362,6 @@ __device__ __forceinline__ uint32_t movm_t(uint32_t x) {
   return y;
 }
 __device__ __forceinline__ void red_add_f32(float* p, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
-__device__ __forceinline__ void pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 
 __global__ void __launch_bounds__(kBwdThreads, 1) window_attn_bwd_kernel(const AttnArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -655,10 +665,10 @@ extern "C" int b200_window_attn_fwd(const void* qkv, const float* pos, void* out
   static bool attr = false;
   if (!attr) { B200_CHECK_CUDA(cudaFuncSetAttribute(window_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem)); attr = true; }
   const long long ntasks = 1LL * B * (H / kWs) * (W / kWs) * heads;
-  long long blocks = (ntasks + kFwdWarps - 1) / kFwdWarps;
+  long long blocks = (ntasks + kFwdPairs - 1) / kFwdPairs;
   const long long cap = b200_num_sms();                   // persistent: one CTA per SM
   if (blocks > cap) blocks = cap;
-  launch_pdl(window_attn_fwd_kernel, dim3(static_cast<unsigned>(blocks)), dim3(kFwdWarps * 32), kFwdSmem, reinterpret_cast<cudaStream_t>(stream), a);
+  launch_pdl(window_attn_fwd_kernel, dim3(static_cast<unsigned>(blocks)), dim3(kFwdThreads), kFwdSmem, reinterpret_cast<cudaStream_t>(stream), a);
   B200_LAUNCH_CHECK();
   return B200_OK;
 }

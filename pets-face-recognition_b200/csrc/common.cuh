@@ -76,6 +76,10 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 
 int b200_num_sms();   // cached cudaDevAttrMultiProcessorCount of the current device (148 on B200)
 // out[i] (+)= sum_s partial[s * stride + i], i < n, fixed order (deterministic); stride <= 0 means n
+// one launch for a table of fp32 [R, Cc] -> bf16 (+ transposed bf16) casts; offsets are elements from in_base / out_base
+struct CastJob { long long in_off, dst_off, dst_t_off; int R, Cc, tile0, tiles_c; };
+struct CastJobs { CastJob job[64]; int n; };
+int cast_transpose_multi(const float* in_base, void* out_base, const CastJobs& jobs, int total_tiles, cudaStream_t stream);
 int splitk_reduce(const float* partial, float* out, long long n, int splits, int accumulate, cudaStream_t stream, long long stride);
 // up to three outputs whose partial rows are adjacent ([splits][ny][n], row pitch `stride`) in one launch
 int splitk_reduce_multi(const float* partial, float* const* outs, int ny, long long n, int splits, int accumulate, cudaStream_t stream,
@@ -141,6 +145,13 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   const float phi_cdf = (x >= 0.0f ? 1.0f : 0.0f) - copysignf(w, x);
   return fmaf(x * 0.39894228040143268f, g, phi_cdf);
 }
+// both at once (the forward GELU epilogue saves the derivative for the backward pass instead of the pre-activation)
+__device__ __forceinline__ void gelu_erf_both(float x, float& y, float& dy) {
+  float w, g;
+  gelu_parts(x, w, g);
+  y = fmaf(-fabsf(x), w, fmaxf(x, 0.0f));
+  dy = fmaf(x * 0.39894228040143268f, g, (x >= 0.0f ? 1.0f : 0.0f) - copysignf(w, x));
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
@@ -166,6 +177,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "@p bra DONE_%=;\n\t"
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+
+// The same wait for the single-thread producer / MMA-issuer roles: a failed probe backs off with nanosleep, so the waiting
+// warp does not compete for the issue slots of the epilogue warps that share its scheduler (try_wait alone returns after
+// ~10 cycles: a tight probe loop costs a quarter of a scheduler's slots, and the small-K GEMM epilogues are issue-bound).
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAITB_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONEB_%=;\n\t"
+      "nanosleep.u32 32;\n\t"
+      "bra WAITB_%=;\n\t"
+      "DONEB_%=:\n\t"
       "}" ::"r"(bar),
       "r"(parity)
       : "memory");

@@ -415,6 +415,39 @@ __global__ void __launch_bounds__(256) cast_transpose_kernel(const float* __rest
   }
 }
 
+// the same for a whole table of matrices in one launch (the per-step fp32 -> bf16 weight refresh): block -> (job, tile)
+__global__ void __launch_bounds__(256) cast_transpose_multi_kernel(const float* __restrict__ in_base, bf16* __restrict__ out_base,
+                                                                   const CastJobs jobs) {
+  pdl_grid_sync();
+  __shared__ float tile[32][33];
+  int j = 0;
+  while (j + 1 < jobs.n && static_cast<int>(blockIdx.x) >= jobs.job[j + 1].tile0) ++j;
+  const CastJob job = jobs.job[j];
+  const int t = blockIdx.x - job.tile0;
+  const int r0 = 32 * (t / job.tiles_c), c0 = 32 * (t % job.tiles_c);
+  const float* in = in_base + job.in_off;
+  bf16* dst = out_base + job.dst_off;
+  bf16* dst_t = job.dst_t_off >= 0 ? out_base + job.dst_t_off : nullptr;
+  const int R = job.R, Cc = job.Cc;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    float v = 0.f;
+    if (r < R && c < Cc) {
+      v = in[1LL * r * Cc + c];
+      dst[1LL * r * Cc + c] = __float2bfloat16_rn(v);
+    }
+    tile[i][tx] = v;
+  }
+  __syncthreads();
+  if (dst_t) {
+    for (int i = ty; i < 32; i += 8) {
+      const int c = c0 + i, r = r0 + tx;
+      if (c < Cc && r < R) dst_t[1LL * c * R + r] = __float2bfloat16_rn(tile[tx][i]);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // column sums of a bf16 [M, N] matrix (bias gradients): 256 threads = TX column lanes (16 B = 8 columns each) x
 // 256/TX row lanes; each CTA reduces a slab of rows -> partial[blk][N] (fixed order: deterministic)
@@ -678,6 +711,13 @@ extern "C" int b200_cast_transpose(const float* in, void* dst, void* dst_t, int 
   dim3 grid((R + 31) / 32, (Cc + 31) / 32);
   launch_pdl(cast_transpose_kernel, dim3(grid), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), in, reinterpret_cast<bf16*>(dst),
                                                                                  reinterpret_cast<bf16*>(dst_t), R, Cc);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+int cast_transpose_multi(const float* in_base, void* out_base, const CastJobs& jobs, int total_tiles, cudaStream_t stream) {
+  if (jobs.n == 0 || total_tiles == 0) return B200_OK;
+  launch_pdl(cast_transpose_multi_kernel, dim3(static_cast<unsigned>(total_tiles)), dim3(256), 0, stream, in_base, reinterpret_cast<bf16*>(out_base), jobs);
   B200_LAUNCH_CHECK();
   return B200_OK;
 }

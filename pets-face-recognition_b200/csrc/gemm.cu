@@ -190,7 +190,8 @@ struct EpiLinear {
   };
 
   // v: 16 consecutive accumulator columns of one output row; ax: the matching 16 values of the aux input (RESID: residual,
-  // DGELU: saved pre-activation) -> o (and o2 = pre-activation in GELU mode).  Rows >= M / columns >= N are computed on
+  // DGELU: the GELU derivative saved by the forward) -> o (and o2 = gelu'(pre-activation) in GELU mode: the backward
+  // epilogue is then one multiply instead of a second erf evaluation).  Rows >= M / columns >= N are computed on
   // zero-filled inputs and clipped by the TMA store.
   __device__ static __forceinline__ void compute(const Params& ep, const CoreParams& p, int /*row*/, int col, const float (&v)[16],
                                                  const float (&ax)[16], float (&o)[16], float (&o2)[16]) {
@@ -208,13 +209,16 @@ struct EpiLinear {
     }
     if (MODE == B200_EPI_GELU) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) { o2[i] = o[i]; o[i] = gelu_erf(o[i]); }
+      for (int i = 0; i < 16; ++i) {
+        if (p.n_out == 2) gelu_erf_both(o[i], o[i], o2[i]);
+        else o[i] = gelu_erf(o[i]);
+      }
     } else if (MODE == B200_EPI_RESID) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) o[i] += ax[i];
     } else if (MODE == B200_EPI_DGELU) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) o[i] *= gelu_erf_grad(ax[i]);
+      for (int i = 0; i < 16; ++i) o[i] *= ax[i];
     }
   }
 };

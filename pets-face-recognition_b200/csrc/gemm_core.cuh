@@ -5,7 +5,7 @@
 //                                sized at run time from block_n)
 //   warp 1      MMA issuer     : one thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=block_n, K=16)
 //   warps 2..9  epilogue       : two warps per TMEM lane quarter, each taking a share of the tile's column boxes:
-//                                [TMA-prefetched aux box (residual / saved pre-activation) ->] tcgen05.ld -> registers ->
+//                                [TMA-prefetched aux box (residual / saved GELU') ->]       tcgen05.ld -> registers ->
 //                                Epi::compute (bias / GELU / residual / GELU' / margin ...) -> swizzled smem box
 //                                (32 rows x <=128 B) -> TMA bulk tensor STORE (coalesced, asynchronous, clipped at the
 //                                matrix edge); two boxes per warp, so loads / math / stores of consecutive boxes overlap
@@ -52,7 +52,7 @@ struct CoreParams {
   int has_aux;               // epilogue consumes a bf16 [M, N] side input, streamed by TMA into the staging boxes
   int out_bytes;             // bytes per output element (2 = bf16, 4 = fp32)
   int box_cols;              // columns per output box (divides block_n; box row = box_cols * out_bytes in {32, 64, 128} B)
-  int n_out;                 // 1, or 2 when the epilogue also emits a second tensor (GELU pre-activation)
+  int n_out;                 // 1, or 2 when the epilogue also emits a second tensor (GELU derivative)
 };
 
 // instruction descriptor, kind::f16: [4,6) D fmt (1=f32), [7,10) A fmt, [10,13) B fmt (0=f16, 1=bf16),
@@ -74,7 +74,7 @@ __device__ __forceinline__ float bf16hi(uint32_t v) { return __uint_as_float(v &
 
 // Compile-time specialisation of the epilogue (the small-K layers are bound by the epilogue's instruction issue rate):
 //   Epi       what to compute per element          OUT_BYTES  2 = bf16 output, 4 = fp32 output
-//   DUAL      second bf16 output (GELU pre-activation)   AUX   bf16 side input streamed by TMA into the staging boxes
+//   DUAL      second bf16 output (GELU derivative)       AUX   bf16 side input streamed by TMA into the staging boxes
 template <class Epi, int OUT_BYTES, bool DUAL, bool AUX>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -142,7 +142,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int kb0 = split * p.k_blocks_per_split;
         const int kb1 = min(p.k_blocks, kb0 + p.k_blocks_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_wait_backoff(empty_bar(stage), phase ^ 1u);
           mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
           const uint32_t sa = smem_base + stage * p.stage_bytes;
           if (!p.mn_major) {
@@ -167,11 +167,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int split = tile / (p.n_blocks * p.m_blocks);
         const int kb0 = split * p.k_blocks_per_split;
         const int kb1 = min(p.k_blocks, kb0 + p.k_blocks_per_split);
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        mbar_wait_backoff(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kMaxBlockN);
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(full_bar(stage), phase);
+          mbar_wait_backoff(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * p.stage_bytes;
           // K-major : SBO = 1024 B between 8-row groups; a K=16 slice is +32 B inside the 128-B swizzle row (+2 in addr>>4)
@@ -347,9 +347,9 @@ struct Operands {
 
 struct Output {
   void* ptr; long long ld; int elem_bytes;          // primary output [M, N] (per split: + split_stride elements)
-  void* ptr2; long long ld2;                         // optional second bf16 output (GELU pre-activation), or nullptr
+  void* ptr2; long long ld2;                         // optional second bf16 output (GELU derivative), or nullptr
   long long split_stride;                            // elements between split partials (0 when splits == 1)
-  const void* aux; long long ldaux;                 // optional bf16 [M, N] epilogue input (residual / pre-activation)
+  const void* aux; long long ldaux;                 // optional bf16 [M, N] epilogue input (residual / saved GELU derivative)
 };
 
 inline int pick_box_cols(int block_n, int elem_bytes) {

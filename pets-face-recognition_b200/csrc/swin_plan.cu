@@ -30,7 +30,7 @@ struct BlockParams {
   long long wqkv16 = 0, wqkv16t = 0, wo16 = 0, wo16t = 0, w116 = 0, w116t = 0, w216 = 0, w216t = 0;   // wcache element offsets
 };
 struct BlockActs {   // byte offsets into the workspace
-  long long mean1, rstd1, xn1, qkv, attn, lse, xmid, mean2, rstd2, xn2, hpre, hact, xout;
+  long long mean1, rstd1, xn1, qkv, attn, lse, xmid, mean2, rstd2, xn2, hgrad, hact, xout;
 };
 struct Stage {
   int C, Hs, heads, df, nblocks, Kp;   // Kp = patch feature count (C_in * df^2)
@@ -140,7 +140,7 @@ void build(Plan& p) {
         a.xmid = add_ws(p, mc * 2);
         a.mean2 = add_ws(p, Mx * 4); a.rstd2 = add_ws(p, Mx * 4);
         a.xn2 = add_ws(p, mc * 2);
-        a.hpre = add_ws(p, p.training ? mc * 4 * 2 : 256);
+        a.hgrad = add_ws(p, p.training ? mc * 4 * 2 : 256);
         a.hact = add_ws(p, mc * 4 * 2);
         a.xout = add_ws(p, mc * 2);
       } else {
@@ -243,8 +243,8 @@ int forward(const Ctx& c, const void* img, int img_u8, float* emb) {
       bf16* xn2 = c.W<bf16>(a.xn2);
       RC(b200_layernorm_fwd(xmid, c.P(q.ln2_w), c.P(q.ln2_b), xn2, c.W<float>(a.mean2), c.W<float>(a.rstd2), S.M, C, 1e-5f, c.stv));
       bf16* hact = c.W<bf16>(a.hact);
-      // training also keeps the pre-activation (out2) for GELU' in backward
-      RC(linear_fwd(c, xn2, S.M, C, c.wc + q.w116, 4 * C, c.P(q.b1), B200_EPI_GELU, hact, p.training ? c.W<bf16>(a.hpre) : nullptr, nullptr));
+      // training also keeps GELU'(pre-activation) (out2): backward multiplies by it
+      RC(linear_fwd(c, xn2, S.M, C, c.wc + q.w116, 4 * C, c.P(q.b1), B200_EPI_GELU, hact, p.training ? c.W<bf16>(a.hgrad) : nullptr, nullptr));
       // inference shares one block's buffers: the block input may live in xout, so alternate with x0
       bf16* xout = c.W<bf16>(a.xout);
       if (!p.training && x == xout) xout = c.W<bf16>(p.st[0].x0);
@@ -295,7 +295,7 @@ int backward(const Ctx& c, const float* demb, int stage_hi, int stage_lo) {
       bf16* dbig = c.W<bf16>(p.d_big);
       bf16* dsmall = c.W<bf16>(p.d_small);
       // ---- MLP: x_out = x_mid + W2 gelu(W1 LN2(x_mid) + b1) + b2
-      RC(linear_dgrad(c, g, M, C, c.wc + q.w216t, 4 * C, B200_EPI_DGELU, dbig, c.W<bf16>(a.hpre)));   // d h_pre
+      RC(linear_dgrad(c, g, M, C, c.wc + q.w216t, 4 * C, B200_EPI_DGELU, dbig, c.W<bf16>(a.hgrad)));   // d h_pre = (dy W2) o gelu'(h_pre)
       RC(linear_wgrad(c, g, M, C, c.W<bf16>(a.hact), 4 * C, c.G(q.w2)));
       RC(linear_dgrad(c, dbig, M, 4 * C, c.wc + q.w116t, C, B200_EPI_STORE, dsmall, nullptr));        // d xn2
       RC(linear_wgrad(c, dbig, M, 4 * C, c.W<bf16>(a.xn2), C, c.G(q.w1)));
@@ -326,20 +326,33 @@ int backward(const Ctx& c, const float* demb, int stage_hi, int stage_lo) {
   return B200_OK;
 }
 
+// fp32 master weights -> the bf16 (and transposed bf16) copies the GEMMs read: one launch over a table of all matrices
 int sync_weights(const Ctx& c) {
   const Plan& p = c.p;
+  CastJobs jobs{};
+  int tiles = 0;
+  bool ok = true;
+  auto add = [&](long long in_off, long long dst_off, long long dst_t_off, int R, int Cc) {
+    if (jobs.n >= 64) { ok = false; return; }
+    CastJob& j = jobs.job[jobs.n++];
+    j.in_off = in_off; j.dst_off = dst_off; j.dst_t_off = dst_t_off; j.R = R; j.Cc = Cc;
+    j.tile0 = tiles; j.tiles_c = (Cc + 31) / 32;
+    tiles += ((R + 31) / 32) * j.tiles_c;
+  };
   for (int s = 0; s < 4; ++s) {
     const Stage& S = p.st[s];
-    RC(b200_cast_transpose(c.P(S.wp), c.wc + S.wp16, s > 0 ? c.wc + S.wp16t : nullptr, S.C, S.Kp, c.stv));
+    add(S.wp.off, S.wp16, s > 0 ? S.wp16t : -1, S.C, S.Kp);
     const int C = S.C;
     for (const BlockParams& q : S.bp_) {
-      RC(b200_cast_transpose(c.P(q.wqkv), c.wc + q.wqkv16, c.wc + q.wqkv16t, 3 * C, C, c.stv));
-      RC(b200_cast_transpose(c.P(q.wo), c.wc + q.wo16, c.wc + q.wo16t, C, C, c.stv));
-      RC(b200_cast_transpose(c.P(q.w1), c.wc + q.w116, c.wc + q.w116t, 4 * C, C, c.stv));
-      RC(b200_cast_transpose(c.P(q.w2), c.wc + q.w216, c.wc + q.w216t, C, 4 * C, c.stv));
+      add(q.wqkv.off, q.wqkv16, q.wqkv16t, 3 * C, C);
+      add(q.wo.off, q.wo16, q.wo16t, C, C);
+      add(q.w1.off, q.w116, q.w116t, 4 * C, C);
+      add(q.w2.off, q.w216, q.w216t, C, 4 * C);
     }
   }
-  return b200_cast_transpose(c.P(p.head_w), c.wc + p.head_w16, c.wc + p.head_w16t, p.num_classes, p.st[3].C, c.stv);
+  add(p.head_w.off, p.head_w16, p.head_w16t, p.num_classes, p.st[3].C);
+  B200_REQUIRE(ok, "sync_weights: more than 64 weight matrices");
+  return cast_transpose_multi(c.params, c.wc, jobs, tiles, c.st);
 }
 
 }  // namespace

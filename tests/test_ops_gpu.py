@@ -60,17 +60,18 @@ def test_gemm_epilogues():
     a, b = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=0.2)
     bias = rnd(N, seed=3, dtype=torch.float32)
     pre_ref = a.float() @ b.float().t() + bias
-    act, pre = ops.gemm_tn(a, b, bias=bias, mode=abi.EPI_GELU, want_pre=True)
-    assert rel_err(pre, pre_ref) < 6e-3
+    act, dact = ops.gemm_tn(a, b, bias=bias, mode=abi.EPI_GELU, want_grad=True)     # second output: gelu'(pre-activation)
+    pr = pre_ref.clone().requires_grad_(True)
+    torch.nn.functional.gelu(pr).sum().backward()
+    assert rel_err(dact, pr.grad) < 6e-3
     assert rel_err(act, torch.nn.functional.gelu(pre_ref)) < 6e-3
+    assert rel_err(ops.gemm_tn(a, b, bias=bias, mode=abi.EPI_GELU), torch.nn.functional.gelu(pre_ref)) < 6e-3
     res = rnd(M, N, seed=7)
     out = ops.gemm_tn(a, b, bias=bias, mode=abi.EPI_RESID, aux=res)
     assert rel_err(out, pre_ref + res.float()) < 6e-3
     x = rnd(M, N, seed=8)
-    xr = x.float().requires_grad_(True)
-    torch.nn.functional.gelu(xr).sum().backward()
-    out = ops.gemm_tn(a, b, mode=abi.EPI_DGELU, aux=x)
-    assert rel_err(out, (a.float() @ b.float().t()) * xr.grad) < 6e-3
+    out = ops.gemm_tn(a, b, mode=abi.EPI_DGELU, aux=x)          # aux = the derivative saved by the GELU epilogue
+    assert rel_err(out, (a.float() @ b.float().t()) * x.float()) < 6e-3
 
 
 @pytest.mark.parametrize('M,N,K,splits', [(384, 96, 50000, 37), (96, 48, 6272, 148), (768, 256, 1000, 3), (512, 768, 2, 4)])

@@ -37,7 +37,7 @@ def main(what, stage=0, B=256):
     elif what == 'gemm_fc1':
         x, w, b = rnd(M, C), rnd(4 * C, C), torch.randn(4 * C, device='cuda')
         for _ in range(3):
-            ops.gemm_tn(x, w, bias=b, mode=abi.EPI_GELU, want_pre=True)
+            ops.gemm_tn(x, w, bias=b, mode=abi.EPI_GELU, want_grad=True)
     elif what == 'gemm_qkv':
         x, w = rnd(M, C), rnd(3 * C, C)
         for _ in range(3):
