@@ -193,6 +193,7 @@ struct EpiLinear {
   // DGELU: the GELU derivative saved by the forward) -> o (and o2 = gelu'(pre-activation) in GELU mode: the backward
   // epilogue is then one multiply instead of a second erf evaluation).  Rows >= M / columns >= N are computed on
   // zero-filled inputs and clipped by the TMA store.
+  template <bool DUAL>
   __device__ static __forceinline__ void compute(const Params& ep, const CoreParams& p, int /*row*/, int col, const float (&v)[16],
                                                  const float (&ax)[16], float (&o)[16], float (&o2)[16]) {
 #pragma unroll
@@ -210,7 +211,7 @@ struct EpiLinear {
     if (MODE == B200_EPI_GELU) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        if (p.n_out == 2) gelu_erf_both(o[i], o[i], o2[i]);
+        if (DUAL) gelu_erf_both(o[i], o[i], o2[i]);
         else o[i] = gelu_erf(o[i]);
       }
     } else if (MODE == B200_EPI_RESID) {
@@ -235,6 +236,7 @@ struct EpiMargin {
     int kind;                             // 0 = ArcFace, 1 = CosFace (AddMarginProduct)
     int easy_margin;
   };
+  template <bool DUAL>
   __device__ static __forceinline__ void compute(const Params& ep, const CoreParams& p, int row, int col, const float (&v)[16],
                                                  const float (&)[16], float (&o)[16], float (&)[16]) {
     const bool live = row < p.M && col < p.N;

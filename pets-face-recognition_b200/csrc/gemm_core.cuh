@@ -18,6 +18,7 @@
 // serves every layer shape of the network.  Optional split-K (each split writes its own fp32 partial)
 // serves the weight-gradient GEMMs whose contraction runs over all tokens.
 #pragma once
+#include <algorithm>
 
 #include "common.cuh"
 
@@ -45,6 +46,8 @@ struct CoreParams {
   int splits;                // split-K factor (>= 1)
   int k_blocks_per_split;
   uint32_t idesc;            // tcgen05 instruction descriptor (formats, majors, M=128, N=block_n)
+  uint32_t idesc_last;       // the same for the last (ragged) column block: N = columns left, rounded up to 16
+  int k_last_steps;          // K=16 MMA steps of the last 64-wide K block (1..4): padding is not multiplied
   int mn_major;              // 1: operands are [K, M] / [K, N] row-major (contraction index = row): weight gradients
   int b_chunks;              // mn_major: 64-column chunks of the B tile = ceil(block_n / 64)
   int stages;                // operand ring depth
@@ -167,6 +170,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int split = tile / (p.n_blocks * p.m_blocks);
         const int kb0 = split * p.k_blocks_per_split;
         const int kb1 = min(p.k_blocks, kb0 + p.k_blocks_per_split);
+        const uint32_t idesc = (tile % p.n_blocks == p.n_blocks - 1) ? p.idesc_last : p.idesc;
         mbar_wait_backoff(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kMaxBlockN);
@@ -180,8 +184,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const uint64_t da = p.mn_major ? make_sw128_desc(sa, kChunk, 1024) : make_sw128_desc(sa, 16, 1024);
           const uint64_t db = p.mn_major ? make_sw128_desc(sa + kABytes, kChunk, 1024) : make_sw128_desc(sa + kABytes, 16, 1024);
           const uint32_t kstep = p.mn_major ? 128u : 2u;
+          const int ksteps = (kb == p.k_blocks - 1) ? p.k_last_steps : kBlockK / 16;
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) umma_f16(d_tmem, da + kstep * k, db + kstep * k, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < kBlockK / 16; ++k)
+            if (k < ksteps) umma_f16(d_tmem, da + kstep * k, db + kstep * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           umma_commit(empty_bar(stage));                 // smem slot reusable once these MMAs retire
           if (kb == kb1 - 1) umma_commit(tfull_bar(acc)); // accumulator complete
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -277,7 +283,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               for (int i = 0; i < 16; ++i) r[i] = 0u;
             }
             float o[16], o2[16];
-            Epi::compute(ep, p, row, col_tile + c_tile + ci * 16, reinterpret_cast<const float(&)[16]>(r), ax, o, o2);
+            Epi::template compute<DUAL>(ep, p, row, col_tile + c_tile + ci * 16, reinterpret_cast<const float(&)[16]>(r), ax, o, o2);
             if (OUT_BYTES == 2) {
 #pragma unroll
               for (int k = 0; k < 2; ++k) {
@@ -381,6 +387,9 @@ int launch(const Operands& o, const Output& out, const typename Epi::Params& ep,
   p.k_blocks_per_split = (p.k_blocks + p.splits - 1) / p.splits;
   p.splits = (p.k_blocks + p.k_blocks_per_split - 1) / p.k_blocks_per_split;   // no empty splits
   p.idesc = make_idesc(o.is_bf16, p.block_n, o.mn_major);
+  const int n_last = o.N - (p.n_blocks - 1) * p.block_n;
+  p.idesc_last = make_idesc(o.is_bf16, std::min(p.block_n, (n_last + 15) / 16 * 16), o.mn_major);
+  p.k_last_steps = (o.K - (p.k_blocks - 1) * kBlockK + 15) / 16;
   p.mn_major = o.mn_major ? 1 : 0;
   p.b_chunks = (p.block_n + 63) / 64;
   const int b_bytes = o.mn_major ? p.b_chunks * 8192 : p.block_n * kBlockK * 2;
