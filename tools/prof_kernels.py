@@ -2,7 +2,7 @@
 
     ncu --set full --clock-control none --import-source on -k regex:<kernel> -c 1 -o gpurun_out/<name> python tools/prof_kernels.py <what>
 
-what: attn_bwd | attn_fwd | gemm_fc1 | gemm_qkv | gemm_fc2 | gemm_wgrad | ln | gallery | gallery_big
+what: attn_bwd | attn_fwd | gemm_fc1 | gemm_qkv | gemm_fc2 | gemm_outproj | gemm_wgrad | gemm_wgrad_small | ln | gallery | gallery_big
 Each op runs 3 times (the first launches warm the caches / instruction memory); capture with -s to skip warm-ups.
 """
 import sys
@@ -46,6 +46,14 @@ def main(what, stage=0, B=256):
         x, w, b, r = rnd(M, 4 * C), rnd(C, 4 * C), torch.randn(C, device='cuda'), rnd(M, C)
         for _ in range(3):
             ops.gemm_tn(x, w, bias=b, mode=abi.EPI_RESID, aux=r)
+    elif what == 'gemm_outproj':       # K = N = C with the residual aux: the smallest-K layer shape
+        x, w, b, r = rnd(M, C), rnd(C, C), torch.randn(C, device='cuda'), rnd(M, C)
+        for _ in range(3):
+            ops.gemm_tn(x, w, bias=b, mode=abi.EPI_RESID, aux=r)
+    elif what == 'gemm_wgrad_small':   # out-projection weight gradient: one 128 x C output tile, split over the tokens
+        dy, x = rnd(M, C), rnd(M, C)
+        for _ in range(3):
+            ops.splitk_reduce(ops.gemm_wgrad(dy, x, splits=147))
     elif what == 'gemm_wgrad':
         dy, x = rnd(M, 4 * C), rnd(M, C)
         for _ in range(3):
