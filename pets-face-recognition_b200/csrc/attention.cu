@@ -361,7 +361,9 @@ __device__ __forceinline__ uint32_t movm_t(uint32_t x) {
   asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(y) : "r"(x));
   return y;
 }
-__device__ __forceinline__ void red_add_f32(float* p, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+__device__ __forceinline__ void red_add_f32x4(float* p, float v0, float v1, float v2, float v3) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v0), "f"(v1), "f"(v2), "f"(v3) : "memory");
+}
 
 __global__ void __launch_bounds__(kBwdThreads, 1) window_attn_bwd_kernel(const AttnArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -369,21 +371,19 @@ __global__ void __launch_bounds__(kBwdThreads, 1) window_attn_bwd_kernel(const A
   const int pair = warp >> 1, w = warp & 1;
   const int g = lane >> 2, tq = lane & 3;
   float* bias_s = reinterpret_cast<float*>(smem);
-  float* bins = reinterpret_cast<float*>(smem + kBiasBytes);                                    // [169] (704 B)
   uint8_t* pb = smem + kBiasBytes + 704 + pair * kPairBytes;
   const uint32_t pb_u = smem_u32(pb);
   float* xbuf = reinterpret_cast<float*>(pb + 2 * kBwdBufBytes);                                // [2][16][32]
   bf16* stage = reinterpret_cast<bf16*>(pb + 2 * kBwdBufBytes + 2 * kXBytes + w * kStageBytes);
   float* dpart_all = reinterpret_cast<float*>(pb + 2 * kBwdBufBytes + 2 * kXBytes + 2 * kStageBytes);  // [2][2 warps][16]
   const uint32_t xbar = pb_u + 2 * kBwdBufBytes + 2 * kXBytes + 2 * kStageBytes + 2 * 2 * 16 * 4;      // 2 mbarriers
-  float* slots = a.dslots + (1LL * blockIdx.x * (2 * kPairs) + warp) * (kSlots * 32) + lane;       // [slot * 32]
+  float* slots = a.dslots + (1LL * blockIdx.x * (2 * kPairs) + warp) * (kSlots * 32) + lane * 4;   // [slot / 4][lane][4]
   const int bar_id = 1 + pair;                              // named barrier of this pair
 
   build_bias_table(bias_s, a.pos);
-  for (int i = threadIdx.x; i < kBins; i += blockDim.x) bins[i] = 0.f;
   for (int i = w * 32 + lane; i < kPairBytes / 16; i += 64) reinterpret_cast<uint4*>(pb)[i] = make_uint4(0, 0, 0, 0);
 #pragma unroll 4
-  for (int sl = 0; sl < kSlots; ++sl) __stcg(slots + sl * 32, 0.f);
+  for (int s4 = 0; s4 < kSlots / 4; ++s4) __stcg(reinterpret_cast<float4*>(slots + s4 * 128), make_float4(0.f, 0.f, 0.f, 0.f));
   __syncthreads();
   if (w == 0 && lane == 0) {
     mbar_init(xbar, 1);
@@ -508,15 +508,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) window_attn_bwd_kernel(const A
       D1 += dpart[(w ^ 1) * 16 + g + 8];
       // dS; its per-lane running sums (for the rel-pos gradient) live in an L2-resident scratch and are updated by
       // fire-and-forget reductions: every address is private to one lane, so the order of the additions is fixed
-      float* sl = slots + mt * (16 * 32);
+      float* sl = slots + mt * (4 * 128);
       uint32_t pf[4][2], df[4][2];
 #pragma unroll
       for (int n = 0; n < 4; ++n) {
         float ds[4];
         ds[0] = s[n][0] * (dp[n][0] - D0); ds[1] = s[n][1] * (dp[n][1] - D0);       // unscaled: `scale` is applied once to dQ / dK
         ds[2] = s[n][2] * (dp[n][2] - D1); ds[3] = s[n][3] * (dp[n][3] - D1);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) red_add_f32(sl + (n * 4 + e) * 32, ds[e]);
+        red_add_f32x4(sl + n * 128, ds[0], ds[1], ds[2], ds[3]);
         pf[n][0] = pack_bf16(s[n][0], s[n][1]); pf[n][1] = pack_bf16(s[n][2], s[n][3]);
         df[n][0] = pack_bf16(ds[0], ds[1]); df[n][1] = pack_bf16(ds[2], ds[3]);
       }
@@ -623,18 +622,26 @@ __global__ void __launch_bounds__(kBwdThreads, 1) window_attn_bwd_kernel(const A
     buf ^= 1;
   }
   cp_async_wait<0>();
-  // fold the per-lane accumulators into the 13 x 13 bins (once per warp), then one partial row per CTA
-#pragma unroll 1
-  for (int sl = 0; sl < kSlots; ++sl) {
-    const int mt = sl >> 4, n = (sl >> 2) & 3, e = sl & 3;
-    const int i = mt * 16 + g + ((e & 2) ? 8 : 0), j = w * 32 + n * 8 + tq * 2 + (e & 1);
-    if (i < kWt && j < kWt) {
-      const int ri = i / kWs, ci = i - ri * kWs, rj = j / kWs, cj = j - rj * kWs;
-      atomicAdd(&bins[(rj - ri + kWs - 1) * (2 * kWs - 1) + (cj - ci + kWs - 1)], __ldcg(slots + sl * 32));
-    }
-  }
+  // Fold the per-lane accumulators into the 13 x 13 bins: one partial row per CTA.  Thread b gathers bin b straight from
+  // the L2-resident slots of the CTA's 12 warps in a fixed order (no atomics): bin (dr, dc) collects every (query i, key j)
+  // with j's window row / column = i's + (dr, dc), and (i, j) lives in warp-half w = j / 32, slot group (i / 16) * 4 +
+  // (j % 32) / 8, lane (i % 8) * 4 + (j % 8) / 2, element ((i % 16) / 8) * 2 + (j % 2) of the mma accumulator layout.
+  __threadfence();
   __syncthreads();
-  for (int i = threadIdx.x; i < kBins; i += blockDim.x) a.dpos_partial[1LL * blockIdx.x * kBins + i] = bins[i];
+  if (threadIdx.x < kBins) {
+    const int dr = static_cast<int>(threadIdx.x) / (2 * kWs - 1) - (kWs - 1), dc = static_cast<int>(threadIdx.x) % (2 * kWs - 1) - (kWs - 1);
+    const float* cta_slots = a.dslots + 1LL * blockIdx.x * (2 * kPairs) * (kSlots * 32);
+    float acc = 0.f;
+    for (int ri = max(0, -dr); ri < min(kWs, kWs - dr); ++ri)
+      for (int ci = max(0, -dc); ci < min(kWs, kWs - dc); ++ci) {
+        const int i = ri * kWs + ci, j = (ri + dr) * kWs + ci + dc;
+        const int off = (j >> 5) * (kSlots * 32) + (((i >> 4) * 4 + ((j & 31) >> 3)) * 32 + (i & 7) * 4 + ((j & 7) >> 1)) * 4 +
+                        ((i & 15) >> 3) * 2 + (j & 1);
+#pragma unroll
+        for (int pr = 0; pr < kPairs; ++pr) acc += __ldcg(cta_slots + pr * (2 * kSlots * 32) + off);
+      }
+    a.dpos_partial[1LL * blockIdx.x * kBins + threadIdx.x] = acc;
+  }
 }
 
 __global__ void dpos_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, int blocks, int accumulate) {

@@ -145,12 +145,47 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   const float phi_cdf = (x >= 0.0f ? 1.0f : 0.0f) - copysignf(w, x);
   return fmaf(x * 0.39894228040143268f, g, phi_cdf);
 }
-// both at once (the forward GELU epilogue saves the derivative for the backward pass instead of the pre-activation)
-__device__ __forceinline__ void gelu_erf_both(float x, float& y, float& dy) {
-  float w, g;
-  gelu_parts(x, w, g);
-  y = fmaf(-fabsf(x), w, fmaxf(x, 0.0f));
-  dy = fmaf(x * 0.39894228040143268f, g, (x >= 0.0f ? 1.0f : 0.0f) - copysignf(w, x));
+
+// Packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2: one instruction for two lanes of a 64-bit register pair).  The GEMM
+// epilogues are bound by instruction issue, not by the FP32 pipe, so halving the instruction count of the element-wise
+// math is what buys time there.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 dup2(float v) { return pk2(v, v); }
+
+// GELU and its derivative for two pre-activations at once (the forward GELU epilogue saves the derivative for the backward
+// pass instead of the pre-activation).  Same rational erfc as gelu_parts, rearranged so that everything but the two MUFU
+// pairs and the sign handling is a packed instruction:
+//   g' = exp(-x^2 / 2) / sqrt(2 pi) = 2^(x * (-k x) + log2(1 / sqrt(2 pi)))        w = t poly'(t) g'   (ai' = ai sqrt(2 pi) / 2)
+//   Phi = 1/2 + copysign(1/2 - w, x)        gelu = x Phi        gelu' = Phi + x g'
+// 12 instructions per element for both outputs (the scalar form above needs 21).
+__device__ __forceinline__ void gelu_erf_both2(f32x2 x, f32x2& y, f32x2& dy) {
+  constexpr float kS = 1.2533141373155001f;                                  // sqrt(2 pi) / 2
+  float x0, x1;
+  upk2(x, x0, x1);
+  const f32x2 targ = fma2(dup2(0.3275911f * 0.70710678118654752f), pk2(fabsf(x0), fabsf(x1)), dup2(1.0f));
+  float a0, a1;
+  upk2(targ, a0, a1);
+  const f32x2 t = pk2(rcp_approx(a0), rcp_approx(a1));
+  const f32x2 e = fma2(x, mul2(x, dup2(-0.72134752044448170f)), dup2(-1.3257480647361593f));   // log2(1 / sqrt(2 pi))
+  float e0, e1;
+  upk2(e, e0, e1);
+  const f32x2 g = pk2(ex2_approx(e0), ex2_approx(e1));
+  f32x2 poly = fma2(dup2(kS * 1.061405429f), t, dup2(kS * -1.453152027f));
+  poly = fma2(poly, t, dup2(kS * 1.421413741f));
+  poly = fma2(poly, t, dup2(kS * -0.284496736f));
+  poly = fma2(poly, t, dup2(kS * 0.254829592f));
+  const f32x2 w = mul2(mul2(poly, t), g);
+  const f32x2 s = fma2(w, dup2(-1.0f), dup2(0.5f));
+  float s0, s1;
+  upk2(s, s0, s1);
+  const f32x2 phi = add2(pk2(copysignf(s0, x0), copysignf(s1, x1)), dup2(0.5f));
+  y = mul2(x, phi);
+  dy = fma2(x, g, phi);
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -182,23 +217,30 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       : "memory");
 }
 
-// The same wait for the single-thread producer / MMA-issuer roles: a failed probe backs off with nanosleep, so the waiting
-// warp does not compete for the issue slots of the epilogue warps that share its scheduler (try_wait alone returns after
-// ~10 cycles: a tight probe loop costs a quarter of a scheduler's slots, and the small-K GEMM epilogues are issue-bound).
-__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+// The same wait for the single-thread producer / MMA-issuer roles.  These roles share their warp scheduler with epilogue
+// warps whose instruction issue bounds the small-K GEMMs, so a waiting role must not burn issue slots: try_wait with a
+// suspend-time hint compiles to SYNCS.TRYWAIT + NANOSLEEP.SYNCS <ns> (a sleep the barrier's completion ends early) instead
+// of a probe / branch loop (ncu, r01e: the probe loop with a 32 ns nanosleep was 19 % of all instructions of the fc1 GEMM,
+// all of them on two of the four schedulers).  ns == 0 selects the plain probe loop.
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity, uint32_t ns) {
+  if (ns == 0) {
+    mbar_wait(bar, parity);
+    return;
+  }
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "WAITB_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra DONEB_%=;\n\t"
-      "nanosleep.u32 32;\n\t"
       "bra WAITB_%=;\n\t"
       "DONEB_%=:\n\t"
       "}" ::"r"(bar),
-      "r"(parity)
+      "r"(parity), "r"(ns)
       : "memory");
 }
+// suspend-time hint of the single-thread roles (ns); B200_WAIT_NS overrides it for experiments
+int b200_wait_ns();
 
 // ---------------------------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor) 2-D tile load, completion on an mbarrier

@@ -15,6 +15,11 @@ __device__ __forceinline__ void ld8(const bf16* p, float* x) {
   f = unpack_bf16(u.z); x[4] = f.x; x[5] = f.y;
   f = unpack_bf16(u.w); x[6] = f.x; x[7] = f.y;
 }
+__device__ __forceinline__ uint4 ld_nc_v4(const bf16* p) {     // streaming 16-B load: read once, do not keep in L1
+  uint4 u;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(p));
+  return u;
+}
 __device__ __forceinline__ void unpack8(const uint4& u, float* x) {
   float2 f;
   f = unpack_bf16(u.x); x[0] = f.x; x[1] = f.y;
@@ -57,29 +62,28 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restri
   const int chunks = C >> 3;
   // U row groups per iteration: all their loads are issued before any arithmetic (memory-level parallelism)
   for (long long row0 = warp_global * (RPW * U); row0 < M; row0 += nwarps * (RPW * U)) {
-    float v[U][MAXIT][8];
+    uint4 raw[U][MAXIT];                 // kept packed until used: U * MAXIT 16-B loads in flight per lane
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long row = row0 + u * RPW + sub;
 #pragma unroll
       for (int it = 0; it < MAXIT; ++it) {
         const int ch = l + it * LPR;
-        if (row < M && ch < chunks) ld8(x + row * C + ch * 8, v[u][it]);
-        else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[u][it][i] = 0.f;
-        }
+        raw[u][it] = (row < M && ch < chunks) ? ld_nc_v4(x + row * C + ch * 8) : make_uint4(0u, 0u, 0u, 0u);
       }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long row = row0 + u * RPW + sub;
       const bool live = row < M;
+      float v[MAXIT][8];
       float s = 0.f;
 #pragma unroll
-      for (int it = 0; it < MAXIT; ++it)
+      for (int it = 0; it < MAXIT; ++it) {
+        unpack8(raw[u][it], v[it]);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s += v[u][it][i];
+        for (int i = 0; i < 8; ++i) s += v[it][i];
+      }
       const float mu = group_sum<LPR>(s) / C;
       float q = 0.f;
 #pragma unroll
@@ -87,7 +91,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restri
         const int ch = l + it * LPR;
         if (ch < chunks) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) { const float d = v[u][it][i] - mu; q += d * d; }
+          for (int i = 0; i < 8; ++i) { const float d = v[it][i] - mu; q += d * d; }
         }
       }
       const float rs = rsqrtf(group_sum<LPR>(q) / C + eps);
@@ -100,7 +104,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restri
             ld8f(gamma + ch * 8, g);
             ld8f(beta + ch * 8, b);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = (v[u][it][i] - mu) * rs * g[i] + b[i];
+            for (int i = 0; i < 8; ++i) o[i] = (v[it][i] - mu) * rs * g[i] + b[i];
             st8(y + row * C + ch * 8, o);
           }
         }
@@ -142,76 +146,82 @@ __global__ void __launch_bounds__(kLnBwdThreads, ln_bwd_ctas_per_sm(MAXIT)) laye
 #pragma unroll
     for (int i = 0; i < 8; ++i) { dg[it][i] = 0.f; db[it][i] = 0.f; if (WITH_RES) dr[it][i] = 0.f; }
 
-  // software pipeline: the raw (packed bf16) loads of the warp's next row group are in flight while the current one is
-  // reduced, so every warp keeps two row groups of dy / x / dres outstanding
-  uint4 rd[MAXIT], rx[MAXIT], rr[MAXIT];
-  float mu_n = 0.f, rs_n = 0.f;
-  auto fetch = [&](long long row) {
+  // software pipeline: the raw (packed bf16) loads of the warp's next D row groups are in flight while the current one is
+  // reduced (D slots, each refilled as soon as it has been consumed), so every lane keeps D * MAXIT * 3 16-B loads
+  // outstanding - the narrow layers (C = 96 / 192: one chunk per lane) need the depth to cover the HBM latency
+  constexpr int D = MAXIT == 1 ? 4 : 1;
+  uint4 rd[D][MAXIT], rx[D][MAXIT], rr[D][MAXIT];
+  float mu_r[D], rs_r[D];
+  auto fetch = [&](int slot, long long row) {
     const bool live = row < M;
-    mu_n = live ? mean[row] : 0.f;
-    rs_n = live ? rstd[row] : 0.f;
+    mu_r[slot] = live ? mean[row] : 0.f;
+    rs_r[slot] = live ? rstd[row] : 0.f;
 #pragma unroll
     for (int it = 0; it < MAXIT; ++it) {
       const int ch = l + it * LPR;
       if (live && ch < chunks) {
-        rd[it] = *reinterpret_cast<const uint4*>(dy + row * C + ch * 8);
-        rx[it] = *reinterpret_cast<const uint4*>(x + row * C + ch * 8);
-        if (dres) rr[it] = *reinterpret_cast<const uint4*>(dres + row * C + ch * 8);
+        rd[slot][it] = ld_nc_v4(dy + row * C + ch * 8);
+        rx[slot][it] = ld_nc_v4(x + row * C + ch * 8);
+        if (dres) rr[slot][it] = ld_nc_v4(dres + row * C + ch * 8);
       }
     }
   };
   const long long stride = nwarps * RPW;
   long long row0 = warp_global * RPW;
-  if (row0 < M) fetch(row0 + sub);
-  for (; row0 < M; row0 += stride) {
-    const long long row = row0 + sub;
-    const bool live = row < M;
-    const float mu = mu_n, rs = rs_n;
-    uint4 cd[MAXIT], cx[MAXIT], cr[MAXIT];
 #pragma unroll
-    for (int it = 0; it < MAXIT; ++it) { cd[it] = rd[it]; cx[it] = rx[it]; cr[it] = rr[it]; }
-    if (row0 + stride < M) fetch(row0 + stride + sub);
-    float g[MAXIT][8], xh[MAXIT][8];
-    float s1 = 0.f, s2 = 0.f;
+  for (int d = 0; d < D; ++d) fetch(d, row0 + d * stride + sub);
+  for (; row0 < M; row0 += D * stride) {
 #pragma unroll
-    for (int it = 0; it < MAXIT; ++it) {
-      const int ch = l + it * LPR;
-      if (live && ch < chunks) {
-        float d[8], xv[8], gm[8];
-        unpack8(cd[it], d);
-        unpack8(cx[it], xv);
-        ld8f(gamma + ch * 8, gm);
+    for (int d = 0; d < D; ++d) {
+      const long long row = row0 + d * stride + sub;
+      const bool live = row < M;
+      const float mu = mu_r[d], rs = rs_r[d];
+      uint4 cd[MAXIT], cx[MAXIT], cr[MAXIT];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          xh[it][i] = (xv[i] - mu) * rs;
-          g[it][i] = d[i] * gm[i];
-          s1 += g[it][i];
-          s2 += g[it][i] * xh[it][i];
-          dg[it][i] += d[i] * xh[it][i];
-          db[it][i] += d[i];
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { g[it][i] = 0.f; xh[it][i] = 0.f; }
-      }
-    }
-    s1 = group_sum<LPR>(s1) / C;
-    s2 = group_sum<LPR>(s2) / C;
-    if (live) {
+      for (int it = 0; it < MAXIT; ++it) { cd[it] = rd[d][it]; cx[it] = rx[d][it]; cr[it] = rr[d][it]; }
+      fetch(d, row0 + (d + D) * stride + sub);
+      float g[MAXIT][8], xh[MAXIT][8];
+      float s1 = 0.f, s2 = 0.f;
 #pragma unroll
       for (int it = 0; it < MAXIT; ++it) {
         const int ch = l + it * LPR;
-        if (ch < chunks) {
-          float o[8];
+        if (live && ch < chunks) {
+          float dv[8], xv[8], gm[8];
+          unpack8(cd[it], dv);
+          unpack8(cx[it], xv);
+          ld8f(gamma + ch * 8, gm);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] = rs * (g[it][i] - s1 - xh[it][i] * s2);
-          if (dres) {
-            float r[8];
-            unpack8(cr[it], r);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { o[i] += r[i]; if (WITH_RES) dr[it][i] += r[i]; }
+          for (int i = 0; i < 8; ++i) {
+            xh[it][i] = (xv[i] - mu) * rs;
+            g[it][i] = dv[i] * gm[i];
+            s1 += g[it][i];
+            s2 += g[it][i] * xh[it][i];
+            dg[it][i] += dv[i] * xh[it][i];
+            db[it][i] += dv[i];
           }
-          st8(dx + row * C + ch * 8, o);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { g[it][i] = 0.f; xh[it][i] = 0.f; }
+        }
+      }
+      s1 = group_sum<LPR>(s1) / C;
+      s2 = group_sum<LPR>(s2) / C;
+      if (live) {
+#pragma unroll
+        for (int it = 0; it < MAXIT; ++it) {
+          const int ch = l + it * LPR;
+          if (ch < chunks) {
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = rs * (g[it][i] - s1 - xh[it][i] * s2);
+            if (dres) {
+              float r[8];
+              unpack8(cr[it], r);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) { o[i] += r[i]; if (WITH_RES) dr[it][i] += r[i]; }
+            }
+            st8(dx + row * C + ch * 8, o);
+          }
         }
       }
     }
@@ -562,10 +572,9 @@ int grid_for(long long work_items, int threads, int max_blocks) {
   return static_cast<int>(b);
 }
 
-template <int LPR, int MAXIT>
+template <int LPR, int MAXIT, int U = (MAXIT == 1 ? 4 : (MAXIT <= 3 ? 2 : 1))>
 int ln_fwd_launch(const bf16* x, const float* g, const float* b, bf16* y, float* mean, float* rstd, long long M, int C, float eps,
                   cudaStream_t st) {
-  constexpr int U = MAXIT == 1 ? 4 : (MAXIT <= 3 ? 2 : 1);
   const int rpw = (32 / LPR) * U;
   const long long warps = (M + rpw - 1) / rpw;
   const int blocks = grid_for(warps * 32, 256, b200_num_sms() * 8);
@@ -602,6 +611,11 @@ extern "C" int b200_layernorm_fwd(const void* x, const float* gamma, const float
   auto st = reinterpret_cast<cudaStream_t>(stream);
   auto X = reinterpret_cast<const bf16*>(x);
   auto Y = reinterpret_cast<bf16*>(y);
+  // widths of the form 24 * 2^k (Swin: 96 / 192 / 384 / 768): C / 24 lanes per row hold exactly three 16-B chunks each -
+  // no idle lanes, short shuffle trees, and 12 loads in flight per lane
+  if (C == 96) return ln_fwd_launch<4, 3, 4>(X, gamma, beta, Y, mean, rstd, M, C, eps, st);
+  if (C == 192) return ln_fwd_launch<8, 3, 4>(X, gamma, beta, Y, mean, rstd, M, C, eps, st);
+  if (C == 384) return ln_fwd_launch<16, 3, 4>(X, gamma, beta, Y, mean, rstd, M, C, eps, st);
   if (C <= 128) return ln_fwd_launch<16, 1>(X, gamma, beta, Y, mean, rstd, M, C, eps, st);
   if (C <= 256) return ln_fwd_launch<32, 1>(X, gamma, beta, Y, mean, rstd, M, C, eps, st);
   if (C <= 512) return ln_fwd_launch<32, 2>(X, gamma, beta, Y, mean, rstd, M, C, eps, st);

@@ -59,6 +59,7 @@ struct FilterParams {
   long long self_offset;      // gallery row (self_offset + q) is excluded for query q
   int exclude_self;
   uint32_t idesc;
+  uint32_t wait_ns;           // suspend-time hint of the producer / MMA-issuer barrier waits
   uint2* scratch;             // [gridDim.x][2][128][kCap] (score bits, idx)
   int* cand_idx;              // [q_blocks*128][lists][kKP]
   float* cand_score;          // [q_blocks*128][lists][kKP] fp16-GEMM scores of the survivors (approximate)
@@ -230,7 +231,7 @@ cosine_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       int stage = 0; uint32_t phase = 0, qphase = 0;
       for (int unit = cluster_id; unit < units; unit += n_clusters) {
         const int qb = (unit % q_groups) * CLUSTER + crank, chunk = unit / q_groups;
-        mbar_wait(qempty_bar, qphase ^ 1u);
+        mbar_wait_backoff(qempty_bar, qphase ^ 1u, p.wait_ns);
         mbar_arrive_expect_tx(qfull_bar, static_cast<uint32_t>(p.kb * kQSlab));
         for (int kb = 0; kb < p.kb; ++kb) tma_load_2d(q_base + kb * kQSlab, &tmap_q, qfull_bar, kb * kBK, qb * kBM);
         qphase ^= 1u;
@@ -238,7 +239,7 @@ cosine_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         const long long g0 = p.g_begin + 1LL * chunk * p.chunk_rows;
         for (int t = 0; t < nt; ++t)
           for (int kb = 0; kb < p.kb; ++kb) {
-            mbar_wait(empty_bar(stage), phase ^ 1u);
+            mbar_wait_backoff(empty_bar(stage), phase ^ 1u, p.wait_ns);
             mbar_arrive_expect_tx(full_bar(stage), kBStage);       // the whole tile: CLUSTER slices, one from each CTA
             if (CLUSTER == 1)
               tma_load_2d(b_base + stage * kBStage, &tmap_g, full_bar(stage), kb * kBK, static_cast<int>(g0 + 1LL * t * kBN));
@@ -255,16 +256,16 @@ cosine_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       int acc = 0; uint32_t acc_phase = 0;
       for (int unit = cluster_id; unit < units; unit += n_clusters) {
         const int chunk = unit / q_groups;
-        mbar_wait(qfull_bar, qphase);
+        mbar_wait_backoff(qfull_bar, qphase, p.wait_ns);
         qphase ^= 1u;
         tc_fence_after();
         const int nt = tiles_of(chunk);
         for (int t = 0; t < nt; ++t) {
-          mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+          mbar_wait_backoff(tempty_bar(acc), acc_phase ^ 1u, p.wait_ns);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kBN);
           for (int kb = 0; kb < p.kb; ++kb) {
-            mbar_wait(full_bar(stage), phase);
+            mbar_wait_backoff(full_bar(stage), phase, p.wait_ns);
             tc_fence_after();
             const uint64_t da = make_sw128_desc(q_base + kb * kQSlab, 16, 1024);
             const uint64_t db = make_sw128_desc(b_base + stage * kBStage, 16, 1024);
@@ -822,6 +823,7 @@ extern "C" int b200_cosine_topk(const float* q, const void* q_unit_f16, const do
   p.exclude_self = exclude_self_offset != B200_NO_EXCLUDE;
   p.self_offset = p.exclude_self ? exclude_self_offset : 0;
   p.idesc = gemm::make_idesc(false, kBN);
+  p.wait_ns = static_cast<uint32_t>(b200_wait_ns());
   p.scratch = reinterpret_cast<uint2*>(ws + L.scratch);
   p.cand_idx = reinterpret_cast<int*>(ws + L.cand_idx);
   p.cand_score = reinterpret_cast<float*>(ws + L.cand_score);

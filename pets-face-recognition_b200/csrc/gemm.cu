@@ -4,6 +4,7 @@
 #include "gemm_core.cuh"
 
 #include <cmath>
+#include <cstdlib>
 #include <mutex>
 
 #include "b200_fe.h"
@@ -21,6 +22,15 @@ int b200_set_error(int code, const char* fmt, ...) {
   return code;
 }
 extern "C" const char* b200_last_error(void) { return g_err; }
+
+int b200_wait_ns() {
+  static const int ns = [] {
+    const char* e = getenv("B200_WAIT_NS");
+    const int v = e != nullptr ? atoi(e) : 256;
+    return v < 0 ? 0 : v;
+  }();
+  return ns;
+}
 
 int b200_num_sms() {
   static int sms[64] = {0};
@@ -193,34 +203,54 @@ struct EpiLinear {
   // DGELU: the GELU derivative saved by the forward) -> o (and o2 = gelu'(pre-activation) in GELU mode: the backward
   // epilogue is then one multiply instead of a second erf evaluation).  Rows >= M / columns >= N are computed on
   // zero-filled inputs and clipped by the TMA store.
+  static bool wants_columns(const Params& ep) { return ep.bias != nullptr; }
+  // smem copy of the bias, zero-padded to the tile grid
+  __device__ static __forceinline__ void stage_columns(const Params& ep, const CoreParams& p, float* dst, int tid, int nthreads) {
+    const int n_pad = p.n_blocks * p.block_n;
+    for (int c = tid; c < n_pad; c += nthreads) dst[c] = c < p.N ? __ldg(ep.bias + c) : 0.0f;
+  }
+
   template <bool DUAL>
-  __device__ static __forceinline__ void compute(const Params& ep, const CoreParams& p, int /*row*/, int col, const float (&v)[16],
-                                                 const float (&ax)[16], float (&o)[16], float (&o2)[16]) {
+  __device__ static __forceinline__ void compute(const Params& ep, const CoreParams& p, const float* bias_s, int /*row*/, int col,
+                                                 const float (&v)[16], const float (&ax)[16], float (&o)[16], float (&o2)[16]) {
+    // packed fp32 pairs throughout: the epilogue is bound by instruction issue
+    f32x2 a[8];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) o[i] = v[i];
-    if (ep.bias != nullptr) {
+    for (int i = 0; i < 8; ++i) a[i] = pk2(v[2 * i], v[2 * i + 1]);
+    if (p.bias_smem) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {                                  // broadcast reads: every lane wants the same 16 floats
+        const float4 b = *reinterpret_cast<const float4*>(bias_s + col + g * 4);
+        a[g * 2 + 0] = add2(a[g * 2 + 0], pk2(b.x, b.y));
+        a[g * 2 + 1] = add2(a[g * 2 + 1], pk2(b.z, b.w));
+      }
+    } else if (ep.bias != nullptr) {
 #pragma unroll
       for (int g = 0; g < 2; ++g)
         if (col + g * 8 < p.N) {                                   // N % 8 == 0 is required by the launcher
           const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + col + g * 8));
           const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + col + g * 8 + 4));
-          o[g * 8 + 0] += b0.x; o[g * 8 + 1] += b0.y; o[g * 8 + 2] += b0.z; o[g * 8 + 3] += b0.w;
-          o[g * 8 + 4] += b1.x; o[g * 8 + 5] += b1.y; o[g * 8 + 6] += b1.z; o[g * 8 + 7] += b1.w;
+          a[g * 4 + 0] = add2(a[g * 4 + 0], pk2(b0.x, b0.y)); a[g * 4 + 1] = add2(a[g * 4 + 1], pk2(b0.z, b0.w));
+          a[g * 4 + 2] = add2(a[g * 4 + 2], pk2(b1.x, b1.y)); a[g * 4 + 3] = add2(a[g * 4 + 3], pk2(b1.z, b1.w));
         }
     }
     if (MODE == B200_EPI_GELU) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        if (DUAL) gelu_erf_both(o[i], o[i], o2[i]);
-        else o[i] = gelu_erf(o[i]);
+      for (int i = 0; i < 8; ++i) {
+        f32x2 y, dy;
+        gelu_erf_both2(a[i], y, dy);
+        a[i] = y;
+        if (DUAL) upk2(dy, o2[2 * i], o2[2 * i + 1]);
       }
     } else if (MODE == B200_EPI_RESID) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) o[i] += ax[i];
+      for (int i = 0; i < 8; ++i) a[i] = add2(a[i], pk2(ax[2 * i], ax[2 * i + 1]));
     } else if (MODE == B200_EPI_DGELU) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) o[i] *= ax[i];
+      for (int i = 0; i < 8; ++i) a[i] = mul2(a[i], pk2(ax[2 * i], ax[2 * i + 1]));
     }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) upk2(a[i], o[2 * i], o[2 * i + 1]);
   }
 };
 
@@ -236,9 +266,11 @@ struct EpiMargin {
     int kind;                             // 0 = ArcFace, 1 = CosFace (AddMarginProduct)
     int easy_margin;
   };
+  static bool wants_columns(const Params&) { return false; }
+  __device__ static __forceinline__ void stage_columns(const Params&, const CoreParams&, float*, int, int) {}
   template <bool DUAL>
-  __device__ static __forceinline__ void compute(const Params& ep, const CoreParams& p, int row, int col, const float (&v)[16],
-                                                 const float (&)[16], float (&o)[16], float (&)[16]) {
+  __device__ static __forceinline__ void compute(const Params& ep, const CoreParams& p, const float*, int row, int col,
+                                                 const float (&v)[16], const float (&)[16], float (&o)[16], float (&)[16]) {
     const bool live = row < p.M && col < p.N;
     const int lab = live ? static_cast<int>(ep.label[row]) : -1;
 #pragma unroll

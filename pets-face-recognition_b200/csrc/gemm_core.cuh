@@ -36,7 +36,26 @@ constexpr int kThreads = 64 + kEpiWarps * 32;     // 320
 constexpr int kBoxBytes = 32 * 128;               // one output box: 32 rows x (at most) 128 B
 constexpr int kStagingPerWarp = 2 * kBoxBytes;    // double buffer (or the two outputs of the GELU epilogue)
 constexpr int kBarBytes = 512;
-constexpr int kSmemBytes = kPipeBytes + kEpiWarps * kStagingPerWarp + kBarBytes + 1024 /*alignment slack*/;
+constexpr int kBiasFloats = 4096;                 // the (zero-padded) bias vector is staged in smem once per CTA when it fits
+constexpr int kSmemBytes = kPipeBytes + kEpiWarps * kStagingPerWarp + kBarBytes + kBiasFloats * 4 + 1024 /*alignment slack*/;
+
+// Division by a run-time constant as multiply-high + shift (the per-tile index arithmetic of every role sits on the critical
+// path of the small-K layers: ncu showed the three hardware-emulated divisions per tile at 17 % of the out-projection's
+// stall samples).  Exact for 0 <= n < 2^31.
+struct FastDiv {
+  uint32_t d, mul, shift;
+  __device__ __forceinline__ uint32_t div(uint32_t n) const { return d == 1u ? n : (__umulhi(n, mul) >> shift); }
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f{d, 0u, 0u};
+  if (d <= 1u) { f.d = 1u; return f; }
+  uint32_t l = 0;
+  while ((1ull << l) < d) ++l;                    // ceil(log2 d) >= 1
+  const uint32_t p = 31u + l;
+  f.mul = static_cast<uint32_t>(((1ull << p) + d - 1) / d);
+  f.shift = p - 32u;
+  return f;
+}
 
 struct CoreParams {
   int M, N;                  // output rows (rows of A) / columns (rows of B)
@@ -56,6 +75,9 @@ struct CoreParams {
   int out_bytes;             // bytes per output element (2 = bf16, 4 = fp32)
   int box_cols;              // columns per output box (divides block_n; box row = box_cols * out_bytes in {32, 64, 128} B)
   int n_out;                 // 1, or 2 when the epilogue also emits a second tensor (GELU derivative)
+  FastDiv div_n, div_m;      // tile -> (n block, m block, split)
+  int bias_smem;             // 1: the epilogue reads the bias from its smem copy (padded N <= kBiasFloats)
+  uint32_t wait_ns;          // suspend-time hint of the producer / MMA-issuer barrier waits
 };
 
 // instruction descriptor, kind::f16: [4,6) D fmt (1=f32), [7,10) A fmt, [10,13) B fmt (0=f16, 1=bf16),
@@ -93,6 +115,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kMaxStages + 2 + a); };
   auto aux_bar = [&](int w, int b) { return bar_base + 8u * (2 * kMaxStages + 4 + 2 * w + b); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 4 + 2 * kEpiWarps);
+  const uint32_t bias_base = bar_base + kBarBytes;
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -128,6 +151,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   pdl_grid_sync();      // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
 
   const int num_tiles = p.m_blocks * p.n_blocks * p.splits;
+  auto decode = [&](int tile, int& n_blk, int& m_blk, int& split) {
+    const uint32_t t1 = p.div_n.div(static_cast<uint32_t>(tile));            // tile / n_blocks
+    n_blk = tile - static_cast<int>(t1) * p.n_blocks;
+    const uint32_t t2 = p.div_m.div(t1);                                     // tile / (n_blocks * m_blocks)
+    m_blk = static_cast<int>(t1) - static_cast<int>(t2) * p.m_blocks;
+    split = static_cast<int>(t2);
+  };
   // K-major: one [128 x 64] A box + one [block_n x 64] B box per stage.  MN-major: the tile is [64 contraction rows x
   // 128 / block_n columns], loaded as [64 x 64] boxes (one 128-B swizzle row = 64 columns) 8 KB apart.
   constexpr uint32_t kChunk = 64 * 64 * 2;
@@ -139,13 +169,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n_blk = tile % p.n_blocks;
-        const int m_blk = (tile / p.n_blocks) % p.m_blocks;
-        const int split = tile / (p.n_blocks * p.m_blocks);
+        int n_blk, m_blk, split;
+        decode(tile, n_blk, m_blk, split);
         const int kb0 = split * p.k_blocks_per_split;
         const int kb1 = min(p.k_blocks, kb0 + p.k_blocks_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait_backoff(empty_bar(stage), phase ^ 1u);
+          mbar_wait_backoff(empty_bar(stage), phase ^ 1u, p.wait_ns);
           mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
           const uint32_t sa = smem_base + stage * p.stage_bytes;
           if (!p.mn_major) {
@@ -167,15 +196,16 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int split = tile / (p.n_blocks * p.m_blocks);
+        int n_blk, m_blk, split;
+        decode(tile, n_blk, m_blk, split);
         const int kb0 = split * p.k_blocks_per_split;
         const int kb1 = min(p.k_blocks, kb0 + p.k_blocks_per_split);
-        const uint32_t idesc = (tile % p.n_blocks == p.n_blocks - 1) ? p.idesc_last : p.idesc;
-        mbar_wait_backoff(tempty_bar(acc), acc_phase ^ 1u);
+        const uint32_t idesc = (n_blk == p.n_blocks - 1) ? p.idesc_last : p.idesc;
+        mbar_wait_backoff(tempty_bar(acc), acc_phase ^ 1u, p.wait_ns);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kMaxBlockN);
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait_backoff(full_bar(stage), phase);
+          mbar_wait_backoff(full_bar(stage), phase, p.wait_ns);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * p.stage_bytes;
           // K-major : SBO = 1024 B between 8-row groups; a K=16 slice is +32 B inside the 128-B swizzle row (+2 in addr>>4)
@@ -219,17 +249,23 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint32_t acc_phase = 0;
     // stream the aux box of (tile, box) into staging buffer b (same geometry / swizzle as the output box)
     auto issue_aux = [&](int tile, int box, int b) {
-      const int n_blk = tile % p.n_blocks;
-      const int m_blk = (tile / p.n_blocks) % p.m_blocks;
+      int n_blk, m_blk, split_unused;
+      decode(tile, n_blk, m_blk, split_unused);
       mbar_arrive_expect_tx(aux_bar(ew, b), box_bytes);
       tma_load_3d(stg + static_cast<uint32_t>(b) * kBoxBytes, &tmap_aux, aux_bar(ew, b), n_blk * p.block_n + box * p.box_cols,
                   m_blk * kBlockM + q * 32, 0);
     };
     if (aux && lane == 0 && static_cast<int>(blockIdx.x) < num_tiles) issue_aux(blockIdx.x, box_lo, 0);
+    // the epilogue's per-column vector (bias), zero-padded to the tile grid, once per CTA: the epilogue then reads it with
+    // broadcast shared loads and needs no column guard
+    const float* bias_s = reinterpret_cast<const float*>(smem_raw + (bias_base - smem_u32(smem_raw)));
+    if (p.bias_smem) {
+      Epi::stage_columns(ep, p, const_cast<float*>(bias_s), static_cast<int>(threadIdx.x) - 64, kEpiWarps * 32);
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+    }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int n_blk = tile % p.n_blocks;
-      const int m_blk = (tile / p.n_blocks) % p.m_blocks;
-      const int split = tile / (p.n_blocks * p.m_blocks);
+      int n_blk, m_blk, split;
+      decode(tile, n_blk, m_blk, split);
       const int kb0 = split * p.k_blocks_per_split;
       const bool has_k = min(p.k_blocks, kb0 + p.k_blocks_per_split) > kb0;
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -283,7 +319,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               for (int i = 0; i < 16; ++i) r[i] = 0u;
             }
             float o[16], o2[16];
-            Epi::template compute<DUAL>(ep, p, row, col_tile + c_tile + ci * 16, reinterpret_cast<const float(&)[16]>(r), ax, o, o2);
+            Epi::template compute<DUAL>(ep, p, bias_s, row, col_tile + c_tile + ci * 16, reinterpret_cast<const float(&)[16]>(r), ax, o, o2);
             if (OUT_BYTES == 2) {
 #pragma unroll
               for (int k = 0; k < 2; ++k) {
@@ -416,6 +452,10 @@ int launch(const Operands& o, const Output& out, const typename Epi::Params& ep,
   p.box_cols = pick_box_cols(p.block_n, out.elem_bytes);
   p.n_out = out.ptr2 != nullptr ? 2 : 1;
   p.has_aux = out.aux != nullptr ? 1 : 0;
+  p.div_n = make_fastdiv(static_cast<uint32_t>(p.n_blocks));
+  p.div_m = make_fastdiv(static_cast<uint32_t>(p.m_blocks));
+  p.bias_smem = (Epi::wants_columns(ep) && 1LL * p.n_blocks * p.block_n <= kBiasFloats) ? 1 : 0;
+  p.wait_ns = static_cast<uint32_t>(b200_wait_ns());
   CUtensorMap to, to2, tx;
   rc = encode_tmap_out(&to, out.elem_bytes, out.ptr, o.N, o.M, p.splits, out.ld, p.splits > 1 ? out.split_stride : 1LL * o.M * out.ld,
                        p.box_cols);
