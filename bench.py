@@ -11,8 +11,9 @@ A "step" = forward + backward + (all-reduce) + optimizer step over one batch.
   value  : whole-job images/s with the batch already resident in HBM (CUDA events, max over ranks).
   e2e    : the same step through the public API (engine.Trainer.train_batches on HOST batches: pinned staging,
            H2D of the images every step, D2H read of the loss every step).
-  roofline: the tcgen05 GEMM kernel (all Linear fwd/dgrad/wgrad + the ArcFace cosine GEMM): algorithmic FLOPs of
-           its launches / their CUDA-event durations, against MEASURED_PEAKS.json's sustained bf16 figure.
+  roofline: the tcgen05 GEMM kernel (all Linear fwd/dgrad/wgrad + the ArcFace cosine GEMM): algorithmic bytes and FLOPs
+           of its launches / their CUDA-event durations, against MEASURED_PEAKS.json's HBM and sustained bf16 figures; the
+           larger fraction names the bound.
   cpu_baseline: the oracle port (oracle/, plain PyTorch fp32) of the same step timed on this box's host cores.
 
 --impl reference times that CPU port alone (the reference itself needs pytorch-lightning and its datasets, neither
@@ -52,6 +53,20 @@ def peaks():
         d = json.loads(p.read_text())
         return d.get('bf16_tflops_sustained', d.get('bf16_tflops')), d.get('hbm_gbs'), 'measured (MEASURED_PEAKS.json, sustained)'
     return 1400.0, 6650.0, 'fallback (B200_PROFILING.md: ~1.4 PFLOP/s sustained, 6.65 TB/s)'
+
+
+def ncu_traffic():
+    """DRAM bytes of one launch of the dominant kernel from the committed `ncu --set full` capture (profiles/*_ncu_full.json,
+    written by tools/ncu_suite.sh + tools/ncu_read.py on the GPU box): the largest single GEMM launch of the step (stage-1 fc1)."""
+    files = sorted((ROOT / 'profiles').glob('*_ncu_full.json'))
+    if not files:
+        return None
+    try:
+        k = json.loads(files[-1].read_text())['kernels']['gemm_fc1']
+        return {'source': f'profiles/{files[-1].name}', 'launch': k['what'], 'dram_bytes': k['dram_bytes'],
+                'algorithmic_bytes': k['algorithmic_bytes'], 'duration_us': k['duration_us']}
+    except Exception:
+        return None
 
 
 # ------------------------------------------------------------------------------------------------------ CPU side
@@ -241,6 +256,8 @@ def gpu_arm(args, rank, world, local_rank):
     barrier()
     ms_b = evb0.elapsed_time(evb1)
     check(L.b200_prof_end(C.byref(gemm_ms), C.byref(gemm_fl), C.byref(gemm_n), None), 'prof_end')
+    gemm_by = C.c_double()
+    check(L.b200_prof_gemm_bytes(C.byref(gemm_by)), 'prof_gemm_bytes')
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], device=device, dtype=torch.float64)
     if world > 1:
@@ -285,6 +302,11 @@ def gpu_arm(args, rank, world, local_rank):
         return
     peak_tf, peak_hbm, peak_src = peaks()
     achieved_tf = gemm_fl.value / (gemm_ms.value * 1e-3) / 1e12 if gemm_ms.value > 0 else 0.0
+    achieved_gbs = gemm_by.value / (gemm_ms.value * 1e-3) / 1e9 if gemm_ms.value > 0 else 0.0
+    # the GEMM launches of this network are mostly small-K (96..768): in aggregate their algorithmic HBM time exceeds their
+    # tensor-core time, so the binding roofline is whichever fraction is larger; both are reported
+    hbm_bound = peak_hbm and peak_tf and achieved_gbs / peak_hbm >= achieved_tf / peak_tf
+    traffic = ncu_traffic()
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
@@ -297,9 +319,17 @@ def gpu_arm(args, rank, world, local_rank):
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
                 'api': 'engine.Trainer.train_batches(module, host_batches, optimizers)', 'h2d_pinned_gbps_this_box': h2d_gbps},
         'gpu_launches': int(total_n.value),
-        'roofline': {'bound': 'tensor', 'kernel': 'gemm::gemm_tn_kernel (tcgen05, all Linear fwd/dgrad/wgrad + ArcFace cosine)',
-                     'achieved': achieved_tf, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved_tf / peak_tf if peak_tf else None,
-                     'traffic': None, 'peak_source': peak_src, 'launches_timed': int(gemm_n.value),
+        'roofline': {'bound': 'hbm' if hbm_bound else 'tensor',
+                     'kernel': 'gemm::gemm_tn_kernel (tcgen05, all Linear fwd/dgrad/wgrad + ArcFace cosine)',
+                     'achieved': achieved_gbs if hbm_bound else achieved_tf, 'peak': peak_hbm if hbm_bound else peak_tf,
+                     'unit': 'GB/s' if hbm_bound else 'TFLOP/s',
+                     'frac': (achieved_gbs / peak_hbm if hbm_bound else achieved_tf / peak_tf) if peak_tf and peak_hbm else None,
+                     'traffic': traffic.get('dram_bytes') if traffic else None, 'traffic_launch': traffic,
+                     'hbm': {'achieved_gbs': achieved_gbs, 'peak_gbs': peak_hbm, 'frac': achieved_gbs / peak_hbm if peak_hbm else None,
+                             'algorithmic_bytes_per_step': gemm_by.value / args.steps},
+                     'tensor': {'achieved_tflops': achieved_tf, 'peak_tflops': peak_tf, 'frac': achieved_tf / peak_tf if peak_tf else None,
+                                'algorithmic_flops_per_step': gemm_fl.value / args.steps},
+                     'peak_source': peak_src, 'launches_timed': int(gemm_n.value),
                      'kernel_ms_per_step': gemm_ms.value / args.steps, 'step_share': gemm_ms.value / ms_b if ms_b else None,
                      'timed_region': f'{args.steps} further steps with per-launch events ({ms_b / args.steps:.2f} ms/step)',
                      'whole_step_frac': value / world * train_flops_per_image() / (peak_tf * 1e12) if peak_tf else None},

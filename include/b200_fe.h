@@ -58,6 +58,7 @@ int b200_device_check(void); /* B200_ERR_ARCH unless the current device is sm_10
  *      with CUDA events on its stream.  b200_prof_end synchronises the device. ------------------------------------ */
 int b200_prof_begin(int time_gemm_launches);
 int b200_prof_end(double* gemm_ms, double* gemm_flops, long long* gemm_launches, long long* total_launches);
+int b200_prof_gemm_bytes(double* bytes); /* algorithmic HBM bytes of the launches the last b200_prof_end summed */
 
 /* ---- linear layers: D[M,N] = A[M,K] * B[N,K]^T on tcgen05 tensor cores (TMA-fed, TMEM accumulators) ---------
  * replaces nn.Linear forward and the two GEMMs autograd runs for its backward (models/swin.py:39-43,91,98,

@@ -39,6 +39,7 @@ _PROTOS = {
     'b200_device_check': (c_int, []),
     'b200_prof_begin': (c_int, [c_int]),
     'b200_prof_end': (c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(c_ll), C.POINTER(c_ll)]),
+    'b200_prof_gemm_bytes': (c_int, [C.POINTER(C.c_double)]),
     'b200_gemm_tn': (c_int, [c_vp, c_ll, c_vp, c_ll, c_int, c_int, c_int, c_int, c_int, c_vp, c_ll, c_int, c_vp, c_ll, c_vp,
                              c_vp, c_ll, c_int, c_ll, c_int, c_vp]),
     'b200_gemm_wgrad': (c_int, [c_vp, c_ll, c_vp, c_ll, c_ll, c_int, c_int, c_vp, c_int, c_int, c_vp]),

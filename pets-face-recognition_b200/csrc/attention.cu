@@ -50,6 +50,7 @@ struct AttnArgs {
   float* dslots;        // bwd: [gridDim.x * warps][64][32] per-lane dS accumulators (L2-resident scratch)
   int B, H, W, C, heads, shifted;
   float scale;
+  FastDiv div_heads, div_nww, div_nwh;   // task -> (head, window column, window row, image)
 };
 
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
@@ -98,11 +99,14 @@ struct Task {
 __device__ __forceinline__ Task decode_task(const AttnArgs& a, long long task) {
   const int nww = a.W / kWs, nwh = a.H / kWs;
   Task t;
-  t.h = static_cast<int>(task % a.heads);
-  long long win = task / a.heads;
-  t.wx = static_cast<int>(win % nww);
-  t.wy = static_cast<int>((win / nww) % nwh);
-  t.b = static_cast<int>(win / (1LL * nww * nwh));
+  const uint32_t tk = static_cast<uint32_t>(task);                 // the launcher checks that the task count fits 31 bits
+  const uint32_t win = a.div_heads.div(tk);
+  t.h = static_cast<int>(tk - win * static_cast<uint32_t>(a.heads));
+  const uint32_t wrow = a.div_nww.div(win);
+  t.wx = static_cast<int>(win - wrow * static_cast<uint32_t>(nww));
+  const uint32_t img = a.div_nwh.div(wrow);
+  t.wy = static_cast<int>(wrow - img * static_cast<uint32_t>(nwh));
+  t.b = static_cast<int>(img);
   t.ul = a.shifted && (t.wy == nwh - 1);
   t.lr = a.shifted && (t.wx == nww - 1);
   return t;
@@ -149,10 +153,23 @@ __device__ __forceinline__ void build_bias_table(float* bias_s, const float* __r
 
 // shift masks (models/swin.py:49-62, 122-124) in closed form: -inf where query and key fall on different sides of
 // the wrap boundary (window row >= 4 <=> token >= 28; window column >= 4 <=> bit of kColHi).
-__device__ __forceinline__ bool shift_masked(const Task& t, int i, int j) {
-  const bool ul = t.ul && ((i >= 28) != (j >= 28));
-  const bool lr = t.lr && ((((kColHi >> i) ^ (kColHi >> j)) & 1ULL) != 0ULL);
-  return ul || lr;
+
+// Evaluated as bit vectors over a lane's accumulator columns (bit 2 n + e <-> key j = jbase + 8 n + e): the column
+// sides are lane constants, a row's mask is one select per mask kind, and the per-element test is a constant-bit probe.
+__device__ __forceinline__ void shift_col_bits(int jbase, int ntiles, uint32_t& col_ul, uint32_t& col_lr) {
+  col_ul = 0u; col_lr = 0u;
+  for (int n = 0; n < ntiles; ++n)
+    for (int e = 0; e < 2; ++e) {
+      const int j = jbase + n * 8 + e;
+      col_ul |= (j >= 28 ? 1u : 0u) << (2 * n + e);
+      col_lr |= static_cast<uint32_t>((kColHi >> j) & 1ULL) << (2 * n + e);
+    }
+}
+__device__ __forceinline__ uint32_t shift_row_mask(const Task& t, int i, uint32_t col_ul, uint32_t col_lr) {
+  uint32_t m = 0u;
+  if (t.ul) m |= (i >= 28) ? ~col_ul : col_ul;
+  if (t.lr) m |= ((kColHi >> i) & 1ULL) ? ~col_lr : col_lr;
+  return m;
 }
 
 // stream one 49 x 32 bf16 tile (row i of the tile = window token i, 64 B = 4 lanes x 16 B) into a swizzled slab
@@ -194,6 +211,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) window_attn_fwd_kernel(const A
   pdl_grid_sync();
 
   const long long ntasks = 1LL * a.B * (a.H / kWs) * (a.W / kWs) * a.heads;
+  uint32_t col_ul, col_lr;                 // this lane's key columns on the far side of the shift boundaries
+  shift_col_bits((lane & 3) * 2, 8, col_ul, col_lr);
   const long long stride = 1LL * gridDim.x * kFwdPairs;
   const long long ld_qkv = 3LL * a.C;
   const float sc2 = a.scale * kLog2e;               // scores are kept in the log2 domain: one FFMA + EX2 per element
@@ -262,6 +281,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) window_attn_fwd_kernel(const A
       const float* b0p = bias_s + i0 * kBiasPitch + tq * 2;
       const float* b1p = bias_s + i1 * kBiasPitch + tq * 2;
       float m0 = -INFINITY, m1 = -INFINITY;
+      const uint32_t mk0 = flagged ? shift_row_mask(t, i0, col_ul, col_lr) : 0u;
+      const uint32_t mk1 = flagged ? shift_row_mask(t, i1, col_ul, col_lr) : 0u;
 #pragma unroll
       for (int n = 0; n < 8; ++n) {
         const float2 b0 = *reinterpret_cast<const float2*>(b0p + n * 8);
@@ -271,11 +292,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) window_attn_fwd_kernel(const A
         s[n][2] = fmaf(s[n][2], sc2, b1.x);
         s[n][3] = fmaf(s[n][3], sc2, b1.y);
         if (flagged) {
-          const int j = n * 8 + tq * 2;
-          if (shift_masked(t, i0, j)) s[n][0] = -INFINITY;
-          if (shift_masked(t, i0, j + 1)) s[n][1] = -INFINITY;
-          if (shift_masked(t, i1, j)) s[n][2] = -INFINITY;
-          if (shift_masked(t, i1, j + 1)) s[n][3] = -INFINITY;
+          if (mk0 & (1u << (2 * n))) s[n][0] = -INFINITY;
+          if (mk0 & (2u << (2 * n))) s[n][1] = -INFINITY;
+          if (mk1 & (1u << (2 * n))) s[n][2] = -INFINITY;
+          if (mk1 & (2u << (2 * n))) s[n][3] = -INFINITY;
         }
         m0 = fmaxf(m0, fmaxf(s[n][0], s[n][1]));
         m1 = fmaxf(m1, fmaxf(s[n][2], s[n][3]));
@@ -399,6 +419,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) window_attn_bwd_kernel(const A
   pdl_grid_sync();
 
   const long long ntasks = 1LL * a.B * (a.H / kWs) * (a.W / kWs) * a.heads;
+  uint32_t col_ul, col_lr;                 // this lane's key columns on the far side of the shift boundaries
+  shift_col_bits(w * 32 + tq * 2, 4, col_ul, col_lr);
   const long long stride = 1LL * gridDim.x * kPairs;
   const long long ld_qkv = 3LL * a.C;
   const float sc2 = a.scale * kLog2e;
@@ -480,6 +502,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) window_attn_bwd_kernel(const A
       const float l0 = lse_s[i0] * kLog2e, l1 = lse_s[i1] * kLog2e;
       // P (in place of S) and this half's share of D_i = sum_j P_ij dP_ij
       float D0 = 0.f, D1 = 0.f;
+      const uint32_t mk0 = flagged ? shift_row_mask(t, i0, col_ul, col_lr) : 0u;
+      const uint32_t mk1 = flagged ? shift_row_mask(t, i1, col_ul, col_lr) : 0u;
 #pragma unroll
       for (int n = 0; n < 4; ++n) {
         const float2 b0 = *reinterpret_cast<const float2*>(b0p + n * 8);
@@ -488,11 +512,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) window_attn_bwd_kernel(const A
         sc[0] = fmaf(s[n][0], sc2, b0.x - l0); sc[1] = fmaf(s[n][1], sc2, b0.y - l0);
         sc[2] = fmaf(s[n][2], sc2, b1.x - l1); sc[3] = fmaf(s[n][3], sc2, b1.y - l1);
         if (flagged) {
-          const int j = jw + n * 8;
-          if (shift_masked(t, i0, j)) sc[0] = -INFINITY;
-          if (shift_masked(t, i0, j + 1)) sc[1] = -INFINITY;
-          if (shift_masked(t, i1, j)) sc[2] = -INFINITY;
-          if (shift_masked(t, i1, j + 1)) sc[3] = -INFINITY;
+          if (mk0 & (1u << (2 * n))) sc[0] = -INFINITY;
+          if (mk0 & (2u << (2 * n))) sc[1] = -INFINITY;
+          if (mk1 & (1u << (2 * n))) sc[2] = -INFINITY;
+          if (mk1 & (2u << (2 * n))) sc[3] = -INFINITY;
         }
 #pragma unroll
         for (int e = 0; e < 4; ++e) s[n][e] = fast_exp2(sc[e]);
@@ -669,9 +692,11 @@ extern "C" int b200_window_attn_fwd(const void* qkv, const float* pos, void* out
   AttnArgs a{};
   a.qkv = reinterpret_cast<const bf16*>(qkv); a.out = reinterpret_cast<bf16*>(out); a.lse = lse; a.pos = pos;
   a.B = B; a.H = H; a.W = W; a.C = C; a.heads = heads; a.shifted = shifted; a.scale = 0.17677669529663687f;  // 32^-0.5
+  a.div_heads = make_fastdiv(static_cast<uint32_t>(heads)); a.div_nww = make_fastdiv(static_cast<uint32_t>(W / kWs)); a.div_nwh = make_fastdiv(static_cast<uint32_t>(H / kWs));
   static bool attr = false;
   if (!attr) { B200_CHECK_CUDA(cudaFuncSetAttribute(window_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem)); attr = true; }
   const long long ntasks = 1LL * B * (H / kWs) * (W / kWs) * heads;
+  B200_REQUIRE(ntasks < (1LL << 31), "window_attn: %lld (window, head) tasks exceed 31 bits", ntasks);
   long long blocks = (ntasks + kFwdPairs - 1) / kFwdPairs;
   const long long cap = b200_num_sms();                   // persistent: one CTA per SM
   if (blocks > cap) blocks = cap;
@@ -689,7 +714,9 @@ extern "C" int b200_window_attn_bwd_blocks(int B, int H, int W, int heads) {
 }
 
 // floats per CTA of the scratch that follows the [blocks, 169] partial rows in `dpos_partial`
-extern "C" long long b200_window_attn_bwd_scratch_floats(int blocks) { return 1LL * blocks * (kBins + 2 * kPairs * kSlots * 32); }
+// [blocks][169] partial rows (padded to a 16-B multiple: the slots are updated with 16-B vector reductions), then the slots
+static long long dpos_rows_floats(int blocks) { return (1LL * blocks * kBins + 3) / 4 * 4; }
+extern "C" long long b200_window_attn_bwd_scratch_floats(int blocks) { return dpos_rows_floats(blocks) + 1LL * blocks * (2 * kPairs * kSlots * 32); }
 
 extern "C" int b200_window_attn_bwd(const void* qkv, const float* pos, const float* lse, const void* dout,
                                     void* dqkv, float* dpos, float* dpos_partial, int accumulate_dpos, int B, int H, int W,
@@ -702,8 +729,9 @@ extern "C" int b200_window_attn_bwd(const void* qkv, const float* pos, const flo
   a.qkv = reinterpret_cast<const bf16*>(qkv); a.pos = pos;
   a.lse = const_cast<float*>(lse); a.dout = reinterpret_cast<const bf16*>(dout); a.dqkv = reinterpret_cast<bf16*>(dqkv);
   a.dpos_partial = dpos_partial;
-  a.dslots = dpos_partial + 1LL * blocks * kBins;      // scratch layout: [blocks][169] partial rows, then the per-lane slots
-  a.B = B; a.H = H; a.W = W; a.C = C; a.heads = heads; a.shifted = shifted; a.scale = 0.17677669529663687f;
+  a.dslots = dpos_partial + dpos_rows_floats(blocks);  // scratch layout: [blocks][169] partial rows, then the per-lane slots
+  a.B = B; a.H = H; a.W = W; a.C = C; a.heads = heads; a.shifted = shifted; a.scale = 0.17677669529663687f;  // 32^-0.5
+  a.div_heads = make_fastdiv(static_cast<uint32_t>(heads)); a.div_nww = make_fastdiv(static_cast<uint32_t>(W / kWs)); a.div_nwh = make_fastdiv(static_cast<uint32_t>(H / kWs));
   static bool attr = false;
   if (!attr) { B200_CHECK_CUDA(cudaFuncSetAttribute(window_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem)); attr = true; }
   auto st = reinterpret_cast<cudaStream_t>(stream);

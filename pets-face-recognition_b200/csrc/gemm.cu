@@ -51,9 +51,10 @@ int b200_num_sms() {
 #include <vector>
 static std::atomic<long long> g_launches{0};
 static bool g_prof_gemm = false;
-struct GemmEv { cudaEvent_t a, b; double flops; };
+struct GemmEv { cudaEvent_t a, b; double flops, bytes; };
 static std::vector<GemmEv> g_gemm_events;
 static std::vector<cudaEvent_t> g_event_pool;
+static double g_last_gemm_bytes = 0.0;
 
 void b200_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
@@ -63,9 +64,9 @@ static cudaEvent_t take_event() {
   cudaEventCreate(&e);
   return e;
 }
-bool b200_prof_gemm_begin(cudaStream_t stream, double flops) {
+bool b200_prof_gemm_begin(cudaStream_t stream, double flops, double bytes) {
   if (!g_prof_gemm) return false;
-  GemmEv ev{take_event(), take_event(), flops};
+  GemmEv ev{take_event(), take_event(), flops, bytes};
   cudaEventRecord(ev.a, stream);
   g_gemm_events.push_back(ev);
   return true;
@@ -84,16 +85,24 @@ extern "C" int b200_prof_begin(int time_gemm_launches) {
 extern "C" int b200_prof_end(double* gemm_ms, double* gemm_flops, long long* gemm_launches, long long* total_launches) {
   g_prof_gemm = false;
   B200_CHECK_CUDA(cudaDeviceSynchronize());
-  double ms = 0.0, fl = 0.0;
+  double ms = 0.0, fl = 0.0, by = 0.0;
   for (auto& e : g_gemm_events) {
     float t = 0.f;
     B200_CHECK_CUDA(cudaEventElapsedTime(&t, e.a, e.b));
-    ms += t; fl += e.flops;
+    ms += t; fl += e.flops; by += e.bytes;
   }
   if (gemm_ms) *gemm_ms = ms;
   if (gemm_flops) *gemm_flops = fl;
+  g_last_gemm_bytes = by;
   if (gemm_launches) *gemm_launches = static_cast<long long>(g_gemm_events.size());
   if (total_launches) *total_launches = g_launches.load();
+  return B200_OK;
+}
+
+// Algorithmic HBM bytes (operands + outputs, each once) of the GEMM launches timed by the last b200_prof_begin(1) ..
+// b200_prof_end pair; call it after b200_prof_end.
+extern "C" int b200_prof_gemm_bytes(double* bytes) {
+  if (bytes) *bytes = g_last_gemm_bytes;
   return B200_OK;
 }
 

@@ -39,24 +39,6 @@ constexpr int kBarBytes = 512;
 constexpr int kBiasFloats = 4096;                 // the (zero-padded) bias vector is staged in smem once per CTA when it fits
 constexpr int kSmemBytes = kPipeBytes + kEpiWarps * kStagingPerWarp + kBarBytes + kBiasFloats * 4 + 1024 /*alignment slack*/;
 
-// Division by a run-time constant as multiply-high + shift (the per-tile index arithmetic of every role sits on the critical
-// path of the small-K layers: ncu showed the three hardware-emulated divisions per tile at 17 % of the out-projection's
-// stall samples).  Exact for 0 <= n < 2^31.
-struct FastDiv {
-  uint32_t d, mul, shift;
-  __device__ __forceinline__ uint32_t div(uint32_t n) const { return d == 1u ? n : (__umulhi(n, mul) >> shift); }
-};
-inline FastDiv make_fastdiv(uint32_t d) {
-  FastDiv f{d, 0u, 0u};
-  if (d <= 1u) { f.d = 1u; return f; }
-  uint32_t l = 0;
-  while ((1ull << l) < d) ++l;                    // ceil(log2 d) >= 1
-  const uint32_t p = 31u + l;
-  f.mul = static_cast<uint32_t>(((1ull << p) + d - 1) / d);
-  f.shift = p - 32u;
-  return f;
-}
-
 struct CoreParams {
   int M, N;                  // output rows (rows of A) / columns (rows of B)
   int block_n;               // multiple of 16, <= 256
@@ -483,7 +465,17 @@ int launch(const Operands& o, const Output& out, const typename Epi::Params& ep,
   const long long tiles = 1LL * p.m_blocks * p.n_blocks * p.splits;
   int ctas = o.max_ctas > 0 ? o.max_ctas : b200_num_sms();
   if (tiles < ctas) ctas = static_cast<int>(tiles);
-  const bool prof = b200_prof_gemm_begin(stream, 2.0 * o.M * o.N * o.K);
+  // A ragged last column block makes the tiles of one row block unequal (qkv of stage 1: 192 + 96 columns).  With the static
+  // tile sequence (tile = cta + i * ctas, n fastest) a CTA count sharing a factor with n_blocks would hand some CTAs only
+  // wide tiles and others only narrow ones; a coprime count rotates every CTA through all column blocks.
+  if (p.n_blocks > 1 && o.N % p.block_n != 0 && tiles > ctas) {
+    auto gcd = [](int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; };
+    while (ctas > 1 && gcd(ctas, p.n_blocks) != 1) --ctas;
+  }
+  // algorithmic HBM bytes of the launch: both operands once, every output (and the aux input) once
+  const double io_bytes = 2.0 * (1.0 * o.M + o.N) * o.K + 1.0 * o.M * o.N * p.splits * out.elem_bytes +
+                          (out.ptr2 != nullptr ? 2.0 * o.M * o.N : 0.0) + (out.aux != nullptr ? 2.0 * o.M * o.N : 0.0);
+  const bool prof = b200_prof_gemm_begin(stream, 2.0 * o.M * o.N * o.K, io_bytes);
   launch_pdl(gemm_tn_kernel<Epi, OUT_BYTES, DUAL, AUX>, dim3(ctas), dim3(kThreads), kSmemBytes, stream, ta, tb, to, to2, tx, p, ep);
   if (prof) b200_prof_gemm_end(stream);
   B200_LAUNCH_CHECK();

@@ -191,10 +191,33 @@ class Trainer:
         """Run optimizer steps over an iterable of HOST batches (dicts of CPU tensors): pinned staging + async H2D one
         step ahead, and a device->host read of the loss every `read_loss_every` steps."""
         losses = []
+        if self.device.type != 'cuda':
+            for i, batch in enumerate(_Prefetcher(host_batches, self.device)):
+                loss = self.run_training_batch(module, batch, optimizers)
+                if read_loss_every and (i + 1) % read_loss_every == 0:
+                    losses.append(float(loss.item()))
+            return losses
+        # The loss of step i crosses to the host through a pinned buffer and is read after step i + 1 has been enqueued,
+        # so the read never leaves the GPU without queued work (a blocking .item() per step would idle it for the whole
+        # launch time of the next step).
+        bufs = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+        pending = None
+        n_read = 0
         for i, batch in enumerate(_Prefetcher(host_batches, self.device)):
             loss = self.run_training_batch(module, batch, optimizers)
             if read_loss_every and (i + 1) % read_loss_every == 0:
-                losses.append(float(loss.item()))
+                buf = bufs[n_read % 2]
+                n_read += 1
+                buf.copy_(loss.detach().reshape(1).float(), non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                if pending is not None:
+                    pending[0].synchronize()
+                    losses.append(float(pending[1][0]))
+                pending = (ev, buf)
+        if pending is not None:
+            pending[0].synchronize()
+            losses.append(float(pending[1][0]))
         return losses
 
     # ------------------------------------------------------------------ loops

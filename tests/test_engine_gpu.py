@@ -72,3 +72,43 @@ def test_eval_entry_sequence_and_recall_parity(run):
     ref = rank_oracle.recall_at_k_loop(emb, classes, (10, 100))
     assert metrics['Recall@K=10'] == pytest.approx(ref['Recall@K=10'], abs=1e-12)
     assert metrics['Recall@K=100'] == pytest.approx(ref['Recall@K=100'], abs=1e-12)
+
+
+def test_train_batches_host_path_matches_device_steps():
+    """engine.Trainer.train_batches (the e2e leg of bench.py: pinned staging, H2D one step ahead, deferred loss read) must
+    report, step for step, the losses of the same steps run on device-resident batches."""
+    from b200 import abi, synth
+    from engine.trainer import Trainer
+    from losses import SoftmaxBasedMetricLearning
+    from models import swin_t
+    abi.require_device()
+
+    def build():
+        model = swin_t(num_classes=512)
+        sd = synth.synth_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, seed=123)
+        model.load_state_dict(sd)
+        wrap = SoftmaxBasedMetricLearning(model, num_class=64, embedding_size=512, is_focal=True, arc_margin=True)
+        wrap.add_margin.weight.data.copy_(synth.synth_tensor('add_margin.weight', (64, 512), seed=123))
+        wrap = wrap.cuda()
+
+        class M(torch.nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.model_loss = wrap
+
+            def training_step(self, batch, batch_idx):
+                return self.model_loss(batch['x'], batch['label'])['loss']
+        m = M()
+        opt = torch.optim.SGD([p for p in wrap.parameters() if p.requires_grad], 5e-3, momentum=0.9)
+        return m, opt
+
+    host = [{'x': synth.synth_images(4, seed=10 + i), 'label': synth.synth_labels(4, 64, seed=10 + i)} for i in range(4)]
+    m1, o1 = build()
+    t1 = Trainer(gpus=[0], max_epochs=1)
+    ref = [float(t1.run_training_batch(m1, {k: v.cuda() for k, v in b.items()}, [o1]).item()) for b in host]
+    m2, o2 = build()
+    t2 = Trainer(gpus=[0], max_epochs=1)
+    got = t2.train_batches(m2, iter(host), [o2], read_loss_every=1)
+    assert len(got) == 4 and all(abs(a - b) <= 1e-5 * max(1.0, abs(b)) for a, b in zip(got, ref)), (got, ref)
+    got2 = t2.train_batches(m2, iter(host), [o2], read_loss_every=2)
+    assert len(got2) == 2
