@@ -72,6 +72,14 @@ int b200_gemm_wgrad(const void* dy, long long ldy, const void* x, long long ldx,
                     int splits, int block_n, void* stream);
 int b200_gemm_splits(int K, int splits); /* split count b200_gemm_tn will really use (sizes the partial buffer) */
 int b200_splitk_reduce(const float* partial, float* out, long long n, int splits, int accumulate, void* stream);
+/* Batched reductions.  Between b200_reduce_defer_begin() and b200_reduce_flush() (same host thread) every fixed-order
+ * reduction the library would launch - b200_splitk_reduce and the ones inside b200_layernorm_bwd, b200_colsum and
+ * b200_window_attn_bwd - is recorded instead; the flush folds all of them in ONE launch on `stream` (keep_deferring != 0
+ * re-opens a batch).  Every recorded reduction needs its own partial buffer, alive until the flush; the outputs are
+ * defined only after it.  The summation order of an output never depends on the rest of the batch. */
+int b200_reduce_defer_begin(void);
+int b200_reduce_pending(void);
+int b200_reduce_flush(void* stream, int keep_deferring);
 
 /* ---- LayerNorm, nn.LayerNorm(C) eps 1e-5 (models/swin.py:29,215) -------------------------------------------- */
 int b200_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, long long M,

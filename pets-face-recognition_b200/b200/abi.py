@@ -45,6 +45,9 @@ _PROTOS = {
     'b200_gemm_wgrad': (c_int, [c_vp, c_ll, c_vp, c_ll, c_ll, c_int, c_int, c_vp, c_int, c_int, c_vp]),
     'b200_gemm_splits': (c_int, [c_int, c_int]),
     'b200_splitk_reduce': (c_int, [c_vp, c_vp, c_ll, c_int, c_int, c_vp]),
+    'b200_reduce_defer_begin': (c_int, []),
+    'b200_reduce_pending': (c_int, []),
+    'b200_reduce_flush': (c_int, [c_vp, c_int]),
     'b200_layernorm_fwd': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, c_int, c_float, c_vp]),
     'b200_layernorm_bwd_blocks': (c_int, [c_ll, c_int]),
     'b200_layernorm_bwd': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, c_int, c_int, c_vp]),

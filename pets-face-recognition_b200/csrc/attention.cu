@@ -667,14 +667,6 @@ __global__ void __launch_bounds__(kBwdThreads, 1) window_attn_bwd_kernel(const A
   }
 }
 
-__global__ void dpos_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out, int blocks, int accumulate) {
-  pdl_grid_sync();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= kBins) return;
-  float acc = accumulate ? out[i] : 0.f;
-  for (int b = 0; b < blocks; ++b) acc += partial[1LL * b * kBins + i];
-  out[i] = acc;
-}
 
 int check_shape(int B, int H, int W, int C, int heads) {
   B200_REQUIRE(B >= 0 && H > 0 && W > 0 && H % kWs == 0 && W % kWs == 0, "window_attn: H=%d W=%d must be multiples of 7", H, W);
@@ -737,7 +729,6 @@ extern "C" int b200_window_attn_bwd(const void* qkv, const float* pos, const flo
   auto st = reinterpret_cast<cudaStream_t>(stream);
   launch_pdl(window_attn_bwd_kernel, dim3(blocks), dim3(kBwdThreads), kBwdSmem, st, a);
   B200_LAUNCH_CHECK();
-  launch_pdl(dpos_reduce_kernel, dim3(1), dim3(192), 0, st, dpos_partial, dpos, blocks, accumulate_dpos);
-  B200_LAUNCH_CHECK();
-  return B200_OK;
+  // [blocks][169] partial rows -> the 13 x 13 table gradient, fixed order (recorded, not launched, inside a reduce batch)
+  return reduce_or_defer(dpos_partial, &dpos, 1, kBins, blocks, accumulate_dpos, st, kBins);
 }

@@ -81,6 +81,9 @@ struct CastJob { long long in_off, dst_off, dst_t_off; int R, Cc, tile0, tiles_c
 struct CastJobs { CastJob job[64]; int n; };
 int cast_transpose_multi(const float* in_base, void* out_base, const CastJobs& jobs, int total_tiles, cudaStream_t stream);
 int splitk_reduce(const float* partial, float* out, long long n, int splits, int accumulate, cudaStream_t stream, long long stride);
+// the same reduction without alignment requirements; recorded instead of launched while a reduce batch is open (gemm.cu)
+int reduce_or_defer(const float* partial, float* const* outs, int ny, long long n, int splits, int accumulate, cudaStream_t stream,
+                    long long stride);
 // up to three outputs whose partial rows are adjacent ([splits][ny][n], row pitch `stride`) in one launch
 int splitk_reduce_multi(const float* partial, float* const* outs, int ny, long long n, int splits, int accumulate, cudaStream_t stream,
                         long long stride);

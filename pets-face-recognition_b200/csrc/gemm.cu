@@ -350,9 +350,111 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Batched reduce: between b200_reduce_defer_begin() and b200_reduce_flush() every fixed-order reduction the library would
+// launch (split-K weight gradients, LayerNorm / bias-gradient partial rows, the rel-pos table rows) is only RECORDED; the
+// flush folds all of them in ONE launch.  A Swin block's backward has eight such reductions of 4-12 us each, latency-bound
+// single-wave launches; batched they are one launch per block that fills the machine.  The caller must give every
+// recorded reduction its own partial buffer and keep it alive until the flush.
+// Summation order per output element: 8 split-lanes (lane s takes splits s, s + 8, ...) then a fixed smem tree - it
+// depends only on the split count, so results are deterministic (and independent of what else is in the batch).
+// ---------------------------------------------------------------------------------------------
+struct ReduceJob {
+  const float* partial;
+  float* out[3];
+  long long n, stride;          // floats per output / between consecutive splits
+  int splits, ny, accumulate, block0, vec, pad;
+};
+constexpr int kMaxReduceJobs = 56;
+struct ReduceBatch {
+  ReduceJob job[kMaxReduceJobs];
+  int n_jobs, n_blocks;
+};
+static thread_local ReduceBatch g_batch;
+static thread_local bool g_batch_on = false;
+
+__global__ void __launch_bounds__(256) reduce_batch_kernel(const __grid_constant__ ReduceBatch b) {
+  pdl_grid_sync();
+  __shared__ float4 red[8][32];
+  int j = 0;
+  while (j + 1 < b.n_jobs && static_cast<int>(blockIdx.x) >= b.job[j + 1].block0) ++j;
+  const ReduceJob& q = b.job[j];
+  const int per_y = static_cast<int>((q.n + 127) / 128);
+  const int rel = static_cast<int>(blockIdx.x) - q.block0;
+  const int y = rel / per_y;
+  const int cx = threadIdx.x & 31, sx = threadIdx.x >> 5;
+  const long long col = (1LL * (rel - y * per_y) * 32 + cx) * 4;
+  const float* __restrict__ partial = q.partial + y * q.n;
+  float* __restrict__ out = q.out[y];
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (q.vec) {
+    if (col < q.n)
+      for (int s = sx; s < q.splits; s += 8) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(partial + 1LL * s * q.stride + col));
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+  } else {
+    for (int s = sx; s < q.splits; s += 8) {
+      const float* row = partial + 1LL * s * q.stride + col;
+      if (col + 0 < q.n) acc.x += __ldg(row + 0);
+      if (col + 1 < q.n) acc.y += __ldg(row + 1);
+      if (col + 2 < q.n) acc.z += __ldg(row + 2);
+      if (col + 3 < q.n) acc.w += __ldg(row + 3);
+    }
+  }
+  red[sx][cx] = acc;
+  __syncthreads();
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) {
+    if (sx < o) {
+      const float4 a = red[sx][cx], c = red[sx + o][cx];
+      red[sx][cx] = make_float4(a.x + c.x, a.y + c.y, a.z + c.z, a.w + c.w);
+    }
+    __syncthreads();
+  }
+  if (sx == 0 && col < q.n) {
+    acc = red[0][cx];
+    if (q.vec) {
+      if (q.accumulate) {
+        const float4 c = *reinterpret_cast<const float4*>(out + col);
+        acc.x += c.x; acc.y += c.y; acc.z += c.z; acc.w += c.w;
+      }
+      *reinterpret_cast<float4*>(out + col) = acc;
+    } else {
+      const float v[4] = {acc.x, acc.y, acc.z, acc.w};
+      for (int i = 0; i < 4; ++i)
+        if (col + i < q.n) out[col + i] = q.accumulate ? out[col + i] + v[i] : v[i];
+    }
+  }
+}
+
+extern "C" int b200_reduce_defer_begin(void) {
+  g_batch.n_jobs = 0;
+  g_batch.n_blocks = 0;
+  g_batch_on = true;
+  return B200_OK;
+}
+extern "C" int b200_reduce_pending(void) { return g_batch_on ? g_batch.n_jobs : 0; }
+// launches the recorded reductions (one kernel) and leaves deferred mode; keep_deferring != 0 re-enters it right away
+extern "C" int b200_reduce_flush(void* stream, int keep_deferring) {
+  if (g_batch_on && g_batch.n_jobs > 0) {
+    launch_pdl(reduce_batch_kernel, dim3(static_cast<unsigned>(g_batch.n_blocks)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), g_batch);
+    B200_LAUNCH_CHECK();
+  }
+  g_batch.n_jobs = 0;
+  g_batch.n_blocks = 0;
+  g_batch_on = keep_deferring != 0;
+  return B200_OK;
+}
+
+// general (also unaligned / n % 4 != 0) recording entry: the rel-pos table rows are 169 floats
+int reduce_or_defer(const float* partial, float* const* outs, int ny, long long n, int splits, int accumulate, cudaStream_t stream,
+                    long long stride);
+
 int splitk_reduce_multi(const float* partial, float* const* outs, int ny, long long n, int splits, int accumulate, cudaStream_t stream,
                         long long stride) {
   if (stride <= 0) stride = n;
+  if (g_batch_on) return reduce_or_defer(partial, outs, ny, n, splits, accumulate, stream, stride);
   B200_REQUIRE(n % 4 == 0 && stride % 4 == 0 && ny >= 1 && ny <= 3, "splitk_reduce: n %% 4 != 0");
   ReduceOuts ro{{outs[0], ny > 1 ? outs[1] : nullptr, ny > 2 ? outs[2] : nullptr}};
   const long long groups = n / 4;
@@ -370,6 +472,37 @@ int splitk_reduce_multi(const float* partial, float* const* outs, int ny, long l
 
 int splitk_reduce(const float* partial, float* out, long long n, int splits, int accumulate, cudaStream_t stream, long long stride) {
   return splitk_reduce_multi(partial, &out, 1, n, splits, accumulate, stream, stride);
+}
+
+int reduce_or_defer(const float* partial, float* const* outs, int ny, long long n, int splits, int accumulate, cudaStream_t stream,
+                    long long stride) {
+  if (stride <= 0) stride = n;
+  B200_REQUIRE(ny >= 1 && ny <= 3 && n > 0 && splits >= 1, "reduce: bad job (ny=%d n=%lld splits=%d)", ny, n, splits);
+  const bool deferred = g_batch_on;
+  if (deferred && g_batch.n_jobs == kMaxReduceJobs) {          // table full: fold what is recorded, keep recording
+    int rc = b200_reduce_flush(stream, 1);
+    if (rc) return rc;
+  }
+  if (!deferred) {
+    g_batch.n_jobs = 0;
+    g_batch.n_blocks = 0;
+  }
+  ReduceJob& q = g_batch.job[g_batch.n_jobs];
+  q.partial = partial;
+  bool aligned = (reinterpret_cast<uintptr_t>(partial) & 15) == 0 && n % 4 == 0 && stride % 4 == 0;
+  for (int y = 0; y < 3; ++y) {
+    q.out[y] = y < ny ? outs[y] : nullptr;
+    if (y < ny) aligned = aligned && (reinterpret_cast<uintptr_t>(outs[y]) & 15) == 0;
+  }
+  q.n = n; q.stride = stride; q.splits = splits; q.ny = ny; q.accumulate = accumulate; q.vec = aligned ? 1 : 0; q.pad = 0;
+  q.block0 = g_batch.n_blocks;
+  g_batch.n_blocks += ny * static_cast<int>((n + 127) / 128);
+  ++g_batch.n_jobs;
+  if (!deferred) {                                              // immediate mode: a batch of one
+    g_batch_on = true;
+    return b200_reduce_flush(stream, 0);
+  }
+  return B200_OK;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -19,6 +19,7 @@
 // serves the weight-gradient GEMMs whose contraction runs over all tokens.
 #pragma once
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -378,6 +379,8 @@ struct Output {
 
 inline int pick_box_cols(int block_n, int elem_bytes) {
   const int widest = 128 / elem_bytes;               // 64 bf16 / 32 fp32 columns = one 128-B row
+  static const int forced = [] { const char* e = getenv("B200_BOX_COLS"); return e != nullptr ? atoi(e) : 0; }();   // experiments
+  if (forced > 0 && forced <= widest && block_n % forced == 0 && forced * elem_bytes >= 32) return forced;
   for (int w = widest; w >= 32; w >>= 1)             // prefer an even box count: the two warps of a quarter split it evenly
     if (block_n % w == 0 && ((block_n / w) & 1) == 0) return w;
   for (int w = widest; w >= 16; w >>= 1)

@@ -55,8 +55,8 @@ struct Plan {
   // head / tail activations
   long long pooled, pool_mean, pool_rstd, pooled_n;
   // backward transients
-  long long g_a, g_b, d_big, d_small, partial, red_partial, dpos_partial, demb16, dpooled;
-  long long partial_bytes;
+  long long g_a, g_b, d_big, d_small, arena, demb16, dpooled;
+  long long arena_bytes;               // partial-sum arena of the batched reductions (one batch per Swin block)
 };
 
 ParamRef add_param(Plan& p, long long numel) {
@@ -154,7 +154,7 @@ void build(Plan& p) {
   p.pooled_n = add_ws(p, 1LL * p.B * C4 * 2);
   if (p.training) {
     // the widest operand of any GEMM in a stage has 4C columns (stage 1 patch: Kp=48 < 4C)
-    long long big = 0, partial = 0;
+    long long big = 0;
     for (int s = 0; s < 4; ++s) {
       const Stage& S = p.st[s];
       const long long wide = std::max<long long>(4LL * S.C, S.Kp);
@@ -163,12 +163,12 @@ void build(Plan& p) {
     p.g_a = add_ws(p, maxMC * 2); p.g_b = add_ws(p, maxMC * 2);
     p.d_big = add_ws(p, big * 2);
     p.d_small = add_ws(p, maxMC * 2);
-    // split-K partials: worst case is ~#SMs tiles of 128 x 256 fp32 (each CTA writes at most a few tiles)
-    partial = 1LL * 4 * 160 * 128 * 256 * 4;
-    p.partial_bytes = partial;
-    p.partial = add_ws(p, partial);
-    p.red_partial = add_ws(p, 1LL * 8 * 160 * 3 * 1536 * 4);  // LN (<= 8*SMs rows x 3C) / colsum (<= 2*SMs rows x 4C) partial rows
-    p.dpos_partial = add_ws(p, b200_window_attn_bwd_scratch_floats(b200_num_sms()) * 4);   // one CTA per SM
+    // Partial sums of every fixed-order reduction of one Swin block's backward (4 split-K weight gradients of at most
+    // ~#SMs tiles of 128 x 256 fp32 each, the LayerNorm / bias-gradient partial rows, the attention scratch): each gets its
+    // own slice, the block's reductions are folded by ONE batched launch, then the arena is reused.
+    p.arena_bytes = 4 * (1LL * 160 * 128 * 256 * 4) + 2 * (1LL * 8 * 160 * 3 * 1536 * 4) + 1LL * 2 * 160 * 4 * 1536 * 4 +
+                    b200_window_attn_bwd_scratch_floats(b200_num_sms()) * 4 + (1 << 20);
+    p.arena = add_ws(p, p.arena_bytes);
     p.demb16 = add_ws(p, 1LL * p.B * p.num_classes * 2);
     p.dpooled = add_ws(p, 1LL * p.B * C4 * 2);
   }
@@ -178,6 +178,22 @@ void build(Plan& p) {
 struct Ctx {
   const Plan& p;
   const float* params; float* grads; bf16* wc; uint8_t* ws; cudaStream_t st; void* stv;
+  mutable long long arena_used = 0;
+  // a slice of the partial-sum arena; when it runs out the recorded reductions are folded and the arena starts over
+  float* take(long long bytes, int* rc) const {
+    bytes = align_up(bytes, 256);
+    if (arena_used + bytes > p.arena_bytes) {
+      *rc = bytes > p.arena_bytes ? B200_ERR_INVALID : flush(true);
+      if (*rc) return nullptr;
+    }
+    float* ptr = reinterpret_cast<float*>(ws + p.arena + arena_used);
+    arena_used += bytes;
+    return ptr;
+  }
+  int flush(bool keep) const {
+    arena_used = 0;
+    return b200_reduce_flush(stv, keep ? 1 : 0);
+  }
   template <class T> T* W(long long off) const { return reinterpret_cast<T*>(ws + off); }
   const float* P(const ParamRef& r) const { return params + r.off; }
   float* G(const ParamRef& r) const { return grads + r.off; }
@@ -203,15 +219,29 @@ int linear_wgrad(const Ctx& c, const bf16* dy, long long M, int N, const bf16* x
   const long long tiles = ((N + 127) / 128) * ((K + bn_eff - 1) / bn_eff);
   int splits = static_cast<int>(std::max<long long>(1, b200_num_sms() / tiles));
   splits = b200_gemm_splits(static_cast<int>(M), splits);
-  while (splits > 1 && 1LL * splits * N * K * 4 > c.p.partial_bytes) --splits;
+  while (splits > 1 && 1LL * splits * N * K * 4 > c.p.arena_bytes / 4) --splits;
   splits = b200_gemm_splits(static_cast<int>(M), splits);
-  float* partial = c.W<float>(c.p.partial);
+  int rc = 0;
+  float* partial = c.take(1LL * splits * N * K * 4, &rc);
+  RC(rc);
   RC(b200_gemm_wgrad(dy, N, x, K, M, N, K, partial, splits, bn, c.stv));
   return b200_splitk_reduce(partial, dw, 1LL * N * K, splits, 0, c.stv);
 }
 
 int bias_grad(const Ctx& c, const bf16* dy, long long M, int N, float* db) {
-  return b200_colsum(dy, N, M, N, db, c.W<float>(c.p.red_partial), 0, c.stv);
+  int rc = 0;
+  float* partial = c.take(1LL * b200_colsum_blocks(M) * N * 4, &rc);
+  RC(rc);
+  return b200_colsum(dy, N, M, N, db, partial, 0, c.stv);
+}
+
+// LayerNorm backward with its partial rows in the arena
+int ln_bwd(const Ctx& c, const bf16* dy, const bf16* x, const float* gamma, const float* mean, const float* rstd, const bf16* dres,
+           bf16* dx, float* dgamma, float* dbeta, float* dres_colsum, long long M, int C) {
+  int rc = 0;
+  float* partial = c.take(1LL * b200_layernorm_bwd_blocks(M, C) * 3 * C * 4, &rc);
+  RC(rc);
+  return b200_layernorm_bwd(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, dres_colsum, partial, M, C, 0, c.stv);
 }
 
 int forward(const Ctx& c, const void* img, int img_u8, float* emb) {
@@ -278,8 +308,8 @@ int backward(const Ctx& c, const float* demb, int stage_hi, int stage_lo) {
     bf16* dpn = c.W<bf16>(p.dpooled);
     RC(linear_dgrad(c, d16, p.B, p.num_classes, c.wc + p.head_w16t, L.C, B200_EPI_STORE, dpn, nullptr));
     bf16* dpool = c.W<bf16>(p.d_small);
-    RC(b200_layernorm_bwd(dpn, c.W<bf16>(p.pooled), c.P(p.head_ln_w), c.W<float>(p.pool_mean), c.W<float>(p.pool_rstd), nullptr, dpool,
-                          c.G(p.head_ln_w), c.G(p.head_ln_b), nullptr, c.W<float>(p.red_partial), p.B, L.C, 0, c.stv));
+    RC(ln_bwd(c, dpn, c.W<bf16>(p.pooled), c.P(p.head_ln_w), c.W<float>(p.pool_mean), c.W<float>(p.pool_rstd), nullptr, dpool,
+              c.G(p.head_ln_w), c.G(p.head_ln_b), nullptr, p.B, L.C));
     RC(b200_mean_pool(dpool, g, p.B, L.Hs * L.Hs, L.C, 1, c.stv));
     stage_hi = 3;
   }
@@ -301,18 +331,23 @@ int backward(const Ctx& c, const float* demb, int stage_hi, int stage_lo) {
       RC(linear_wgrad(c, dbig, M, 4 * C, c.W<bf16>(a.xn2), C, c.G(q.w1)));
       RC(bias_grad(c, dbig, M, 4 * C, c.G(q.b1)));
       // g <- d x_mid; the same pass yields d b2 = colsum(g): g is dL/d(fc2 output)
-      RC(b200_layernorm_bwd(dsmall, c.W<bf16>(a.xmid), c.P(q.ln2_w), c.W<float>(a.mean2), c.W<float>(a.rstd2), g, g,
-                            c.G(q.ln2_w), c.G(q.ln2_b), c.G(q.b2), c.W<float>(p.red_partial), M, C, 0, c.stv));
+      RC(ln_bwd(c, dsmall, c.W<bf16>(a.xmid), c.P(q.ln2_w), c.W<float>(a.mean2), c.W<float>(a.rstd2), g, g,
+                c.G(q.ln2_w), c.G(q.ln2_b), c.G(q.b2), M, C));
       // ---- attention: x_mid = x_in + Wo attn(LN1(x_in)) + bo
       RC(linear_dgrad(c, g, M, C, c.wc + q.wo16t, C, B200_EPI_STORE, dsmall, nullptr));               // d attn_out
       RC(linear_wgrad(c, g, M, C, c.W<bf16>(a.attn), C, c.G(q.wo)));
-      RC(b200_window_attn_bwd(c.W<bf16>(a.qkv), c.P(q.pos), c.W<float>(a.lse), dsmall, dbig, c.G(q.pos),
-                              c.W<float>(p.dpos_partial), 0, p.B, S.Hs, S.Hs, C, S.heads, b & 1, c.stv));   // dbig <- d qkv
+      {
+        int rc = 0;
+        float* scratch = c.take(b200_window_attn_bwd_scratch_floats(b200_window_attn_bwd_blocks(p.B, S.Hs, S.Hs, S.heads)) * 4, &rc);
+        RC(rc);
+        RC(b200_window_attn_bwd(c.W<bf16>(a.qkv), c.P(q.pos), c.W<float>(a.lse), dsmall, dbig, c.G(q.pos), scratch, 0, p.B, S.Hs, S.Hs, C,
+                                S.heads, b & 1, c.stv));                                                // dbig <- d qkv
+      }
       RC(linear_dgrad(c, dbig, M, 3 * C, c.wc + q.wqkv16t, C, B200_EPI_STORE, dsmall, nullptr));      // d xn1
       RC(linear_wgrad(c, dbig, M, 3 * C, c.W<bf16>(a.xn1), C, c.G(q.wqkv)));
       // g <- d x_in; d bo = colsum(g before the update): g is dL/d(to_out output)
-      RC(b200_layernorm_bwd(dsmall, x_in, c.P(q.ln1_w), c.W<float>(a.mean1), c.W<float>(a.rstd1), g, g, c.G(q.ln1_w), c.G(q.ln1_b),
-                            c.G(q.bo), c.W<float>(p.red_partial), M, C, 0, c.stv));
+      RC(ln_bwd(c, dsmall, x_in, c.P(q.ln1_w), c.W<float>(a.mean1), c.W<float>(a.rstd1), g, g, c.G(q.ln1_w), c.G(q.ln1_b), c.G(q.bo), M, C));
+      RC(c.flush(true));                                     // the block's eight reductions: one launch
     }
     // ---- patch merging linear (models/swin.py:162-167)
     RC(linear_wgrad(c, g, M, C, c.W<bf16>(S.cols), S.Kp, c.G(S.wp)));
@@ -432,5 +467,10 @@ extern "C" int b200_swin_backward(const void* plan, const float* params, const v
     return b200_set_error(B200_ERR_WORKSPACE, "swin_backward: workspace %lld < required %lld bytes", workspace_bytes, p->ws_bytes);
   Ctx c{*p, params, grads, reinterpret_cast<bf16*>(const_cast<void*>(wcache)), reinterpret_cast<uint8_t*>(workspace),
         reinterpret_cast<cudaStream_t>(stream), stream};
-  return backward(c, demb, stage_hi, stage_lo);
+  // every fixed-order reduction of the pass is recorded and folded one batch per block (see Ctx::take / flush); whatever
+  // happens, deferred mode ends with this call
+  int rc = b200_reduce_defer_begin();
+  if (rc == B200_OK) rc = backward(c, demb, stage_hi, stage_lo);
+  const int rc_flush = b200_reduce_flush(stream, 0);
+  return rc ? rc : rc_flush;
 }

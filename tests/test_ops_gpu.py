@@ -222,3 +222,33 @@ def test_cpu_tensors_are_rejected():
     from b200 import abi, ops
     with pytest.raises(abi.B200Error):
         ops.layernorm_fwd(torch.zeros(4, 96, dtype=bf16), torch.ones(96), torch.zeros(96))
+
+
+def test_batched_reduce_matches_fp64_and_is_deterministic():
+    """b200_reduce_defer_begin / b200_reduce_flush: several recorded reductions (aligned and not, 1..3 splits to 300) are
+    folded by one launch; results match an fp64 sum and repeat bit for bit."""
+    from b200 import abi, ops
+    L = abi.lib()
+    g = torch.Generator(device='cuda').manual_seed(5)
+    shapes = [(7, 1000), (300, 4096), (1, 128), (148, 169), (33, 12)]
+    parts = [torch.randn(s, n, device='cuda', generator=g) for s, n in shapes]
+
+    def run():
+        outs = [torch.full((n,), float('nan'), device='cuda') for _, n in shapes]
+        abi.check(L.b200_reduce_defer_begin(), 'defer_begin')
+        for p, o in zip(parts, outs):
+            ops.splitk_reduce(p, out=o)
+        assert L.b200_reduce_pending() == len(shapes)
+        abi.check(L.b200_reduce_flush(abi.stream_ptr(), 0), 'flush')
+        assert L.b200_reduce_pending() == 0
+        torch.cuda.synchronize()
+        return outs
+    a, b = run(), run()
+    for p, x, y in zip(parts, a, b):
+        ref = p.double().sum(0)
+        assert torch.equal(x, y)
+        assert (x.double() - ref).abs().max().item() <= 1e-5 * max(1.0, ref.abs().max().item()) * p.shape[0] ** 0.5
+    # outside a batch the call is immediate again
+    o = ops.splitk_reduce(parts[0])
+    torch.cuda.synchronize()
+    assert torch.isfinite(o).all()

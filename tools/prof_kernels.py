@@ -83,6 +83,32 @@ def main(what, stage=0, B=256):
         e1.record()
         torch.cuda.synchronize()
         print('gallery_big ms/call', e0.elapsed_time(e1) / 5)
+    elif what == 'time_gemms':       # event-timed GEMM shapes of stages 1-2 (for A/B runs with B200_BOX_COLS / B200_WAIT_NS)
+        def timed(name, fn, reps=10):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            print(f'{name:28s} {e0.elapsed_time(e1) / reps * 1e3:8.1f} us')
+        for st in (0, 1):
+            Cs, Ms = 96 << st, B * (56 >> st) ** 2
+            x, x4, r = rnd(Ms, Cs), rnd(Ms, 4 * Cs), rnd(Ms, Cs)
+            wq, wo, w1, w2 = rnd(3 * Cs, Cs), rnd(Cs, Cs), rnd(4 * Cs, Cs), rnd(Cs, 4 * Cs)
+            b1, bo = torch.randn(4 * Cs, device='cuda'), torch.randn(Cs, device='cuda')
+            dq = rnd(Ms, 3 * Cs)
+            wqt = rnd(Cs, 3 * Cs)
+            timed(f's{st + 1} qkv fwd   N={3 * Cs} K={Cs}', lambda: ops.gemm_tn(x, wq))
+            timed(f's{st + 1} out-proj  N={Cs} K={Cs}', lambda: ops.gemm_tn(x, wo, bias=bo, mode=abi.EPI_RESID, aux=r))
+            timed(f's{st + 1} out dgrad N={Cs} K={Cs}', lambda: ops.gemm_tn(x, wo))
+            timed(f's{st + 1} fc1 dual  N={4 * Cs} K={Cs}', lambda: ops.gemm_tn(x, w1, bias=b1, mode=abi.EPI_GELU, want_grad=True))
+            timed(f's{st + 1} fc2       N={Cs} K={4 * Cs}', lambda: ops.gemm_tn(x4, w2, bias=bo, mode=abi.EPI_RESID, aux=r))
+            timed(f's{st + 1} qkv dgrad N={Cs} K={3 * Cs}', lambda: ops.gemm_tn(dq, wqt))
+            del x, x4, r, dq
     torch.cuda.synchronize()
     print('done', what)
 
