@@ -356,14 +356,14 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
 // flush folds all of them in ONE launch.  A Swin block's backward has eight such reductions of 4-12 us each, latency-bound
 // single-wave launches; batched they are one launch per block that fills the machine.  The caller must give every
 // recorded reduction its own partial buffer and keep it alive until the flush.
-// Summation order per output element: 8 split-lanes (lane s takes splits s, s + 8, ...) then a fixed smem tree - it
-// depends only on the split count, so results are deterministic (and independent of what else is in the batch).
+// Summation order per output element: SL split-lanes (lane s takes splits s, s + SL, ...; SL = 8 or 32 from the job's own
+// shape) then a fixed smem tree: deterministic, and independent of what else is in the batch.
 // ---------------------------------------------------------------------------------------------
 struct ReduceJob {
   const float* partial;
   float* out[3];
   long long n, stride;          // floats per output / between consecutive splits
-  int splits, ny, accumulate, block0, vec, pad;
+  int splits, ny, accumulate, block0, vec, sl;   // sl: split-lanes per column group (8 or 32)
 };
 constexpr int kMaxReduceJobs = 56;
 struct ReduceBatch {
@@ -375,26 +375,28 @@ static thread_local bool g_batch_on = false;
 
 __global__ void __launch_bounds__(256) reduce_batch_kernel(const __grid_constant__ ReduceBatch b) {
   pdl_grid_sync();
-  __shared__ float4 red[8][32];
+  __shared__ float4 red[256];
   int j = 0;
   while (j + 1 < b.n_jobs && static_cast<int>(blockIdx.x) >= b.job[j + 1].block0) ++j;
   const ReduceJob& q = b.job[j];
-  const int per_y = static_cast<int>((q.n + 127) / 128);
+  const int SL = q.sl, CG = 256 / SL;                 // split-lanes x column groups (of 4 floats) of this CTA
+  const int per_y = static_cast<int>((q.n + 4 * CG - 1) / (4 * CG));
   const int rel = static_cast<int>(blockIdx.x) - q.block0;
   const int y = rel / per_y;
-  const int cx = threadIdx.x & 31, sx = threadIdx.x >> 5;
-  const long long col = (1LL * (rel - y * per_y) * 32 + cx) * 4;
+  const int cx = threadIdx.x % CG, sx = threadIdx.x / CG;
+  const long long col = (1LL * (rel - y * per_y) * CG + cx) * 4;
   const float* __restrict__ partial = q.partial + y * q.n;
   float* __restrict__ out = q.out[y];
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (q.vec) {
     if (col < q.n)
-      for (int s = sx; s < q.splits; s += 8) {
+#pragma unroll 4
+      for (int s = sx; s < q.splits; s += SL) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(partial + 1LL * s * q.stride + col));
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
       }
   } else {
-    for (int s = sx; s < q.splits; s += 8) {
+    for (int s = sx; s < q.splits; s += SL) {
       const float* row = partial + 1LL * s * q.stride + col;
       if (col + 0 < q.n) acc.x += __ldg(row + 0);
       if (col + 1 < q.n) acc.y += __ldg(row + 1);
@@ -402,18 +404,17 @@ __global__ void __launch_bounds__(256) reduce_batch_kernel(const __grid_constant
       if (col + 3 < q.n) acc.w += __ldg(row + 3);
     }
   }
-  red[sx][cx] = acc;
+  red[sx * CG + cx] = acc;
   __syncthreads();
-#pragma unroll
-  for (int o = 4; o > 0; o >>= 1) {
+  for (int o = SL / 2; o > 0; o >>= 1) {
     if (sx < o) {
-      const float4 a = red[sx][cx], c = red[sx + o][cx];
-      red[sx][cx] = make_float4(a.x + c.x, a.y + c.y, a.z + c.z, a.w + c.w);
+      const float4 a = red[sx * CG + cx], c = red[(sx + o) * CG + cx];
+      red[sx * CG + cx] = make_float4(a.x + c.x, a.y + c.y, a.z + c.z, a.w + c.w);
     }
     __syncthreads();
   }
   if (sx == 0 && col < q.n) {
-    acc = red[0][cx];
+    acc = red[cx];
     if (q.vec) {
       if (q.accumulate) {
         const float4 c = *reinterpret_cast<const float4*>(out + col);
@@ -494,9 +495,12 @@ int reduce_or_defer(const float* partial, float* const* outs, int ny, long long 
     q.out[y] = y < ny ? outs[y] : nullptr;
     if (y < ny) aligned = aligned && (reinterpret_cast<uintptr_t>(outs[y]) & 15) == 0;
   }
-  q.n = n; q.stride = stride; q.splits = splits; q.ny = ny; q.accumulate = accumulate; q.vec = aligned ? 1 : 0; q.pad = 0;
+  q.n = n; q.stride = stride; q.splits = splits; q.ny = ny; q.accumulate = accumulate; q.vec = aligned ? 1 : 0;
+  // many splits of a narrow output (LayerNorm / bias partial rows: hundreds of rows x a few hundred columns): 32 split-lanes
+  // keep the serial chain per thread short; wide weight-gradient outputs have few splits and enough column groups
+  q.sl = (splits > 32 && n < 65536 * 4) ? 32 : 8;
   q.block0 = g_batch.n_blocks;
-  g_batch.n_blocks += ny * static_cast<int>((n + 127) / 128);
+  g_batch.n_blocks += ny * static_cast<int>((n + 4 * (256 / q.sl) - 1) / (4 * (256 / q.sl)));
   ++g_batch.n_jobs;
   if (!deferred) {                                              // immediate mode: a batch of one
     g_batch_on = true;
