@@ -125,7 +125,7 @@ def reference_arm(args, rank):
             'cpu_baseline': {'value': ips, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                              'sample': f'{args.steps} steps of batch {batch} after {args.warmup} warm-up, oracle/ port on {cores} threads'},
             'e2e': {'value': ips, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------ GPU side
@@ -344,7 +344,7 @@ def gpu_arm(args, rank, world, local_rank):
         line['cpu_baseline'] = {'value': ips, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
                                 'sample': f'{steps_cb} steps of batch {cb} after 1 warm-up: same step (Swin-T + ArcFace(C={NUM_CLASS}) + SGD), '
                                           f'oracle/ port, fp32, {torch.get_num_threads()} threads'}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def gallery_leg(args, rank, world, device):
@@ -391,7 +391,25 @@ def gallery_leg(args, rank, world, device):
             'tflops': flops / (ms * 1e-3) / 1e12}
 
 
+_RESULT_FD = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the process's original stdout; everything else any library prints (NCCL's version banner
+    arrives on fd 1) has been diverted to stderr by main()."""
+    data = (json.dumps(line) + '\n').encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
@@ -414,7 +432,7 @@ def main():
         import torch.distributed as dist
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         torch.cuda.set_device(local_rank)
-        dist.init_process_group('nccl')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     try:
         gpu_arm(args, rank, world, local_rank)
     finally:

@@ -70,6 +70,10 @@ int b200_gemm_tn(const void* a, long long lda, const void* b, long long ldb, int
  * operands are consumed in place through MN-major UMMA descriptors (no transposed copies) */
 int b200_gemm_wgrad(const void* dy, long long ldy, const void* x, long long ldx, long long tokens, int N, int K, float* partial,
                     int splits, int block_n, void* stream);
+/* b200_gemm_wgrad + the bias gradient colsum(dy) as [splits][N] fp32 partial rows (all-ones MMA inside the same kernel);
+ * *fused = 0 when the tile shape has no room for it (then colsum_partial is untouched: use b200_colsum). */
+int b200_gemm_wgrad_bias(const void* dy, long long ldy, const void* x, long long ldx, long long tokens, int N, int K, float* partial,
+                         float* colsum_partial, int splits, int block_n, int* fused, void* stream);
 int b200_gemm_splits(int K, int splits); /* split count b200_gemm_tn will really use (sizes the partial buffer) */
 int b200_splitk_reduce(const float* partial, float* out, long long n, int splits, int accumulate, void* stream);
 /* Batched reductions.  Between b200_reduce_defer_begin() and b200_reduce_flush() (same host thread) every fixed-order

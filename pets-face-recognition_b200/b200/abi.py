@@ -43,6 +43,7 @@ _PROTOS = {
     'b200_gemm_tn': (c_int, [c_vp, c_ll, c_vp, c_ll, c_int, c_int, c_int, c_int, c_int, c_vp, c_ll, c_int, c_vp, c_ll, c_vp,
                              c_vp, c_ll, c_int, c_ll, c_int, c_vp]),
     'b200_gemm_wgrad': (c_int, [c_vp, c_ll, c_vp, c_ll, c_ll, c_int, c_int, c_vp, c_int, c_int, c_vp]),
+    'b200_gemm_wgrad_bias': (c_int, [c_vp, c_ll, c_vp, c_ll, c_ll, c_int, c_int, c_vp, c_vp, c_int, c_int, C.POINTER(c_int), c_vp]),
     'b200_gemm_splits': (c_int, [c_int, c_int]),
     'b200_splitk_reduce': (c_int, [c_vp, c_vp, c_ll, c_int, c_int, c_vp]),
     'b200_reduce_defer_begin': (c_int, []),

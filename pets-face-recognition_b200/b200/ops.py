@@ -51,6 +51,21 @@ def gemm_wgrad(dy, x, splits=1, block_n=0):
     return out
 
 
+def gemm_wgrad_bias(dy, x, splits=1, block_n=0):
+    """gemm_wgrad that also returns the bias-gradient partial rows [splits, N] (column sums of dy from an all-ones MMA in the
+    same kernel), or None for them when the tile shape cannot host the extra accumulator columns."""
+    import ctypes
+    tokens, N = dy.shape
+    K = x.shape[1]
+    splits = lib().b200_gemm_splits(tokens, max(1, splits))
+    out = torch.empty(splits, N, K, device=dy.device, dtype=torch.float32)
+    cs = torch.empty(splits, N, device=dy.device, dtype=torch.float32)
+    fused = ctypes.c_int(0)
+    check(lib().b200_gemm_wgrad_bias(ptr(dy), dy.stride(0), ptr(x), x.stride(0), tokens, N, K, ptr(out), ptr(cs), splits, block_n,
+                                     ctypes.byref(fused), stream_ptr()), 'gemm_wgrad_bias')
+    return out, (cs if fused.value else None)
+
+
 def splitk_reduce(partial, out=None, accumulate=False):
     splits, n = partial.shape[0], partial[0].numel()
     if out is None:

@@ -549,6 +549,21 @@ extern "C" int b200_gemm_wgrad(const void* dy, long long ldy, const void* x, lon
   return gemm::launch<gemm::EpiLinear<B200_EPI_PARTIAL>, 4, false, false>(o, od, {nullptr}, reinterpret_cast<cudaStream_t>(stream));
 }
 
+// The same launch also producing the bias gradient db[N] = colsum(dY) as [splits][N] fp32 partial rows in `colsum_partial`
+// (an all-ones MMA inside the kernel: no second pass over dY).  *fused = 0 (and colsum_partial untouched) when the tile
+// shape leaves no spare TMEM columns for it (K > 240 with a 256-wide tile): the caller then runs b200_colsum.
+extern "C" int b200_gemm_wgrad_bias(const void* dy, long long ldy, const void* x, long long ldx, long long tokens, int N, int K,
+                                    float* partial, float* colsum_partial, int splits, int block_n, int* fused, void* stream) {
+  B200_REQUIRE(K % 8 == 0 && N > 0 && tokens > 0 && tokens < (1LL << 31), "gemm_wgrad: bad shape tokens=%lld N=%d K=%d", tokens, N, K);
+  const int bn = block_n > 0 ? block_n : gemm::pick_block_n(K, static_cast<int>(tokens));
+  const bool can = colsum_partial != nullptr && bn <= gemm::kOnesCol;
+  if (fused) *fused = can ? 1 : 0;
+  gemm::Operands o{dy, (int)ldy, x, (int)ldx, N, K, static_cast<int>(tokens), true, block_n, splits, 0, true};
+  gemm::Output od{partial, K, 4, nullptr, 0, 1LL * N * K, nullptr, 0};
+  if (can) od.colsum = colsum_partial;
+  return gemm::launch<gemm::EpiLinear<B200_EPI_PARTIAL>, 4, false, false>(o, od, {nullptr}, reinterpret_cast<cudaStream_t>(stream));
+}
+
 extern "C" int b200_gemm_splits(int K, int splits) { return gemm::effective_splits(K, splits); }
 
 extern "C" int b200_splitk_reduce(const float* partial, float* out, long long n, int splits, int accumulate, void* stream) {

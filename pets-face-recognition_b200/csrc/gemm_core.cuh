@@ -37,6 +37,8 @@ constexpr int kThreads = 64 + kEpiWarps * 32;     // 320
 constexpr int kBoxBytes = 32 * 128;               // one output box: 32 rows x (at most) 128 B
 constexpr int kStagingPerWarp = 2 * kBoxBytes;    // double buffer (or the two outputs of the GELU epilogue)
 constexpr int kBarBytes = 512;
+constexpr int kOnesBytes = 64 * 128;                // the all-ones operand tile of the fused bias gradient (shares the bias staging area)
+constexpr int kOnesCol = 240;                     // TMEM columns [240, 256) of an accumulator stage hold its product
 constexpr int kBiasFloats = 4096;                 // the (zero-padded) bias vector is staged in smem once per CTA when it fits
 constexpr int kSmemBytes = kPipeBytes + kEpiWarps * kStagingPerWarp + kBarBytes + kBiasFloats * 4 + 1024 /*alignment slack*/;
 
@@ -59,6 +61,8 @@ struct CoreParams {
   int box_cols;              // columns per output box (divides block_n; box row = box_cols * out_bytes in {32, 64, 128} B)
   int n_out;                 // 1, or 2 when the epilogue also emits a second tensor (GELU derivative)
   FastDiv div_n, div_m;      // tile -> (n block, m block, split)
+  float* colsum_out;         // weight gradients only: [splits][M] column sums of the A operand (= the bias gradient), or null
+  uint32_t idesc_ones;       // N = 16 instruction descriptor of the all-ones MMA that produces them
   int bias_smem;             // 1: the epilogue reads the bias from its smem copy (padded N <= kBiasFloats)
   uint32_t wait_ns;          // suspend-time hint of the producer / MMA-issuer barrier waits
 };
@@ -126,6 +130,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 2) {
     tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
+  }
+  if (p.colsum_out != nullptr) {
+    // Bias gradient for free: db[m] = sum_t dY[t, m] is the weight-gradient GEMM with an all-ones second operand.  One
+    // 8-KB tile of bf16 1.0 (layout and swizzle are irrelevant: every element is equal) sits where the bias staging would
+    // be, and each K block gets four extra N = 16 MMAs into 16 spare TMEM columns of the accumulator stage.
+    for (int i = threadIdx.x; i < kOnesBytes / 16; i += kThreads) st_shared_v4(bias_base + 16u * i, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    fence_proxy_async_smem();
   }
   tc_fence_before();
   __syncthreads();
@@ -201,6 +212,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k)
             if (k < ksteps) umma_f16(d_tmem, da + kstep * k, db + kstep * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          if (p.colsum_out != nullptr && n_blk == 0) {
+            const uint64_t d1 = make_sw128_desc(bias_base, kChunk, 1024);
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k)
+              if (k < ksteps) umma_f16(d_tmem + kOnesCol, da + kstep * k, d1 + 128u * k, p.idesc_ones, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
           umma_commit(empty_bar(stage));                 // smem slot reusable once these MMAs retire
           if (kb == kb1 - 1) umma_commit(tfull_bar(acc)); // accumulator complete
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -331,6 +348,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
         buf ^= 1;
       }
+      if (p.colsum_out != nullptr && n_blk == 0 && ew < 4) {       // one warp per lane quarter: column 0 of the ones product
+        uint32_t r[16];
+        tmem_ld16(taddr + kOnesCol, r);
+        tmem_ld_wait();
+        if (row < p.M) p.colsum_out[1LL * split * p.M + row] = has_k ? __uint_as_float(r[0]) : 0.0f;
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -375,6 +398,7 @@ struct Output {
   void* ptr2; long long ld2;                         // optional second bf16 output (GELU derivative), or nullptr
   long long split_stride;                            // elements between split partials (0 when splits == 1)
   const void* aux; long long ldaux;                 // optional bf16 [M, N] epilogue input (residual / saved GELU derivative)
+  float* colsum = nullptr;                           // weight gradients: [splits][M] column sums of A (fused bias gradient)
 };
 
 inline int pick_box_cols(int block_n, int elem_bytes) {
@@ -437,6 +461,11 @@ int launch(const Operands& o, const Output& out, const typename Epi::Params& ep,
   p.box_cols = pick_box_cols(p.block_n, out.elem_bytes);
   p.n_out = out.ptr2 != nullptr ? 2 : 1;
   p.has_aux = out.aux != nullptr ? 1 : 0;
+  p.colsum_out = out.colsum;
+  p.idesc_ones = make_idesc(o.is_bf16, 16, o.mn_major);
+  if (out.colsum != nullptr)
+    B200_REQUIRE(o.mn_major && o.is_bf16 && OUT_BYTES == 4 && p.block_n <= kOnesCol && !Epi::wants_columns(ep),
+                 "gemm: fused column sums need a bf16 weight-gradient launch with block_n <= %d (got %d)", kOnesCol, p.block_n);
   p.div_n = make_fastdiv(static_cast<uint32_t>(p.n_blocks));
   p.div_m = make_fastdiv(static_cast<uint32_t>(p.m_blocks));
   p.bias_smem = (Epi::wants_columns(ep) && 1LL * p.n_blocks * p.block_n <= kBiasFloats) ? 1 : 0;

@@ -213,7 +213,9 @@ int linear_dgrad(const Ctx& c, const bf16* dy, long long M, int N, const bf16* w
 
 // dW[N,K] = dY[M,N]^T * X[M,K]: operands read in place (MN-major tcgen05 descriptors), split-K over the tokens,
 // fp32 partials reduced in a fixed order.
-int linear_wgrad(const Ctx& c, const bf16* dy, long long M, int N, const bf16* x, int K, float* dw) {
+int bias_grad(const Ctx& c, const bf16* dy, long long M, int N, float* db);
+// db (optional): the bias gradient colsum(dy), produced by the same kernel when the tile shape allows it
+int linear_wgrad(const Ctx& c, const bf16* dy, long long M, int N, const bf16* x, int K, float* dw, float* db = nullptr) {
   const int bn = (K <= 256) ? static_cast<int>(align_up(K, 16)) : 0;
   const int bn_eff = bn ? bn : 256;
   const long long tiles = ((N + 127) / 128) * ((K + bn_eff - 1) / bn_eff);
@@ -224,8 +226,17 @@ int linear_wgrad(const Ctx& c, const bf16* dy, long long M, int N, const bf16* x
   int rc = 0;
   float* partial = c.take(1LL * splits * N * K * 4, &rc);
   RC(rc);
-  RC(b200_gemm_wgrad(dy, N, x, K, M, N, K, partial, splits, bn, c.stv));
-  return b200_splitk_reduce(partial, dw, 1LL * N * K, splits, 0, c.stv);
+  if (db == nullptr) {
+    RC(b200_gemm_wgrad(dy, N, x, K, M, N, K, partial, splits, bn, c.stv));
+    return b200_splitk_reduce(partial, dw, 1LL * N * K, splits, 0, c.stv);
+  }
+  float* cs = c.take(1LL * splits * N * 4, &rc);
+  RC(rc);
+  int fused = 0;
+  RC(b200_gemm_wgrad_bias(dy, N, x, K, M, N, K, partial, cs, splits, bn, &fused, c.stv));
+  RC(b200_splitk_reduce(partial, dw, 1LL * N * K, splits, 0, c.stv));
+  if (fused) return b200_splitk_reduce(cs, db, N, splits, 0, c.stv);
+  return bias_grad(c, dy, M, N, db);
 }
 
 int bias_grad(const Ctx& c, const bf16* dy, long long M, int N, float* db) {
@@ -328,8 +339,7 @@ int backward(const Ctx& c, const float* demb, int stage_hi, int stage_lo) {
       RC(linear_dgrad(c, g, M, C, c.wc + q.w216t, 4 * C, B200_EPI_DGELU, dbig, c.W<bf16>(a.hgrad)));   // d h_pre = (dy W2) o gelu'(h_pre)
       RC(linear_wgrad(c, g, M, C, c.W<bf16>(a.hact), 4 * C, c.G(q.w2)));
       RC(linear_dgrad(c, dbig, M, 4 * C, c.wc + q.w116t, C, B200_EPI_STORE, dsmall, nullptr));        // d xn2
-      RC(linear_wgrad(c, dbig, M, 4 * C, c.W<bf16>(a.xn2), C, c.G(q.w1)));
-      RC(bias_grad(c, dbig, M, 4 * C, c.G(q.b1)));
+      RC(linear_wgrad(c, dbig, M, 4 * C, c.W<bf16>(a.xn2), C, c.G(q.w1), c.G(q.b1)));            // + d b1 = colsum(d h_pre)
       // g <- d x_mid; the same pass yields d b2 = colsum(g): g is dL/d(fc2 output)
       RC(ln_bwd(c, dsmall, c.W<bf16>(a.xmid), c.P(q.ln2_w), c.W<float>(a.mean2), c.W<float>(a.rstd2), g, g,
                 c.G(q.ln2_w), c.G(q.ln2_b), c.G(q.b2), M, C));
@@ -350,8 +360,7 @@ int backward(const Ctx& c, const float* demb, int stage_hi, int stage_lo) {
       RC(c.flush(true));                                     // the block's eight reductions: one launch
     }
     // ---- patch merging linear (models/swin.py:162-167)
-    RC(linear_wgrad(c, g, M, C, c.W<bf16>(S.cols), S.Kp, c.G(S.wp)));
-    RC(bias_grad(c, g, M, C, c.G(S.bp)));
+    RC(linear_wgrad(c, g, M, C, c.W<bf16>(S.cols), S.Kp, c.G(S.wp), c.G(S.bp)));
     if (s > 0) {
       bf16* dcols = c.W<bf16>(p.d_big);
       RC(linear_dgrad(c, g, M, C, c.wc + S.wp16t, S.Kp, B200_EPI_STORE, dcols, nullptr));

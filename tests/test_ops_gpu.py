@@ -99,6 +99,24 @@ def test_gemm_wgrad_mn_major(tokens, N, K, splits):
     assert rel_err(out, ref) < 2e-5 * math.sqrt(tokens) + 1e-6
 
 
+@pytest.mark.parametrize('tokens,N,K,splits', [(3136, 384, 96, 7), (1000, 200, 192, 3), (50, 1536, 384, 1), (777, 96, 48, 148), (640, 3072, 768, 4)])
+def test_gemm_wgrad_fused_bias_gradient(tokens, N, K, splits):
+    """The weight-gradient kernel's all-ones MMA: column sums of dY (= the bias gradient) from the same launch; shapes whose
+    tile leaves no spare TMEM columns (K = 768 -> 256-wide tiles) must report `not fused` and leave the weight gradient intact."""
+    from b200 import ops
+    dy, x = rnd(tokens, N, seed=1, scale=0.1), rnd(tokens, K, seed=2, scale=0.1)
+    part, cs = ops.gemm_wgrad_bias(dy, x, splits=splits)
+    out = ops.splitk_reduce(part)
+    assert rel_err(out, dy.float().t() @ x.float()) < 2e-5 * math.sqrt(tokens) + 1e-6
+    if K == 768:
+        assert cs is None
+        return
+    assert cs is not None and cs.shape == (part.shape[0], N)
+    db = cs.sum(0)
+    ref = dy.float().sum(0)
+    assert (db - ref).abs().max().item() < 1e-5 * math.sqrt(tokens) * max(1.0, ref.abs().max().item())
+
+
 @pytest.mark.parametrize('C', [96, 192, 384, 768])
 @pytest.mark.parametrize('M', [1, 49, 1000])
 def test_layernorm(C, M):
