@@ -356,14 +356,14 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
 // flush folds all of them in ONE launch.  A Swin block's backward has eight such reductions of 4-12 us each, latency-bound
 // single-wave launches; batched they are one launch per block that fills the machine.  The caller must give every
 // recorded reduction its own partial buffer and keep it alive until the flush.
-// Summation order per output element: SL split-lanes (lane s takes splits s, s + SL, ...; SL = 8 or 32 from the job's own
+// Summation order per output element: SL split-lanes (lane s takes splits s, s + SL, ...; SL = 1, 8 or 32 from the job's own
 // shape) then a fixed smem tree: deterministic, and independent of what else is in the batch.
 // ---------------------------------------------------------------------------------------------
 struct ReduceJob {
   const float* partial;
   float* out[3];
   long long n, stride;          // floats per output / between consecutive splits
-  int splits, ny, accumulate, block0, vec, sl;   // sl: split-lanes per column group (8 or 32)
+  int splits, ny, accumulate, block0, vec, sl;   // sl: split-lanes per column group (1, 8 or 32)
 };
 constexpr int kMaxReduceJobs = 56;
 struct ReduceBatch {
@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(256) reduce_batch_kernel(const __grid_constant
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (q.vec) {
     if (col < q.n)
-#pragma unroll 4
+#pragma unroll 8
       for (int s = sx; s < q.splits; s += SL) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(partial + 1LL * s * q.stride + col));
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
@@ -404,17 +404,19 @@ __global__ void __launch_bounds__(256) reduce_batch_kernel(const __grid_constant
       if (col + 3 < q.n) acc.w += __ldg(row + 3);
     }
   }
-  red[sx * CG + cx] = acc;
-  __syncthreads();
-  for (int o = SL / 2; o > 0; o >>= 1) {
-    if (sx < o) {
-      const float4 a = red[sx * CG + cx], c = red[(sx + o) * CG + cx];
-      red[sx * CG + cx] = make_float4(a.x + c.x, a.y + c.y, a.z + c.z, a.w + c.w);
-    }
+  if (SL > 1) {                                        // CTA-uniform: the job is a property of the CTA
+    red[sx * CG + cx] = acc;
     __syncthreads();
+    for (int o = SL / 2; o > 0; o >>= 1) {
+      if (sx < o) {
+        const float4 a = red[sx * CG + cx], c = red[(sx + o) * CG + cx];
+        red[sx * CG + cx] = make_float4(a.x + c.x, a.y + c.y, a.z + c.z, a.w + c.w);
+      }
+      __syncthreads();
+    }
+    acc = red[cx];
   }
   if (sx == 0 && col < q.n) {
-    acc = red[cx];
     if (q.vec) {
       if (q.accumulate) {
         const float4 c = *reinterpret_cast<const float4*>(out + col);
@@ -496,9 +498,10 @@ int reduce_or_defer(const float* partial, float* const* outs, int ny, long long 
     if (y < ny) aligned = aligned && (reinterpret_cast<uintptr_t>(outs[y]) & 15) == 0;
   }
   q.n = n; q.stride = stride; q.splits = splits; q.ny = ny; q.accumulate = accumulate; q.vec = aligned ? 1 : 0;
-  // many splits of a narrow output (LayerNorm / bias partial rows: hundreds of rows x a few hundred columns): 32 split-lanes
-  // keep the serial chain per thread short; wide weight-gradient outputs have few splits and enough column groups
-  q.sl = (splits > 32 && n < 65536 * 4) ? 32 : 8;
+  // Split-lanes per column group, from the job's own shape: few splits (the wide weight gradients of stages 3-4) -> one
+  // thread sums all splits of its float4 (independent loads, no smem, 1024 columns per CTA); hundreds of partial rows of a
+  // narrow output (LayerNorm / bias rows) -> 32 lanes keep the serial chain short.
+  q.sl = splits <= 16 ? 1 : (splits <= 64 ? 8 : 32);
   q.block0 = g_batch.n_blocks;
   g_batch.n_blocks += ny * static_cast<int>((n + 4 * (256 / q.sl) - 1) / (4 * (256 / q.sl)));
   ++g_batch.n_jobs;
