@@ -51,6 +51,8 @@ struct AttnArgs {
   int B, H, W, C, heads, shifted;
   float scale;
   FastDiv div_heads, div_nww, div_nwh;   // task -> (head, window column, window row, image)
+  long long ntasks;
+  int rev_tasks;
 };
 
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
@@ -99,7 +101,8 @@ struct Task {
 __device__ __forceinline__ Task decode_task(const AttnArgs& a, long long task) {
   const int nww = a.W / kWs, nwh = a.H / kWs;
   Task t;
-  const uint32_t tk = static_cast<uint32_t>(task);                 // the launcher checks that the task count fits 31 bits
+  // rev_tasks: tasks are walked from the last image / window to the first (see b200_reverse_rows)
+  const uint32_t tk = a.rev_tasks ? static_cast<uint32_t>(a.ntasks - 1 - task) : static_cast<uint32_t>(task);   // launcher: count fits 31 bits
   const uint32_t win = a.div_heads.div(tk);
   t.h = static_cast<int>(tk - win * static_cast<uint32_t>(a.heads));
   const uint32_t wrow = a.div_nww.div(win);
@@ -685,6 +688,7 @@ extern "C" int b200_window_attn_fwd(const void* qkv, const float* pos, void* out
   a.qkv = reinterpret_cast<const bf16*>(qkv); a.out = reinterpret_cast<bf16*>(out); a.lse = lse; a.pos = pos;
   a.B = B; a.H = H; a.W = W; a.C = C; a.heads = heads; a.shifted = shifted; a.scale = 0.17677669529663687f;  // 32^-0.5
   a.div_heads = make_fastdiv(static_cast<uint32_t>(heads)); a.div_nww = make_fastdiv(static_cast<uint32_t>(W / kWs)); a.div_nwh = make_fastdiv(static_cast<uint32_t>(H / kWs));
+  a.ntasks = 1LL * B * (H / kWs) * (W / kWs) * heads; a.rev_tasks = b200_reverse_rows();
   static bool attr = false;
   if (!attr) { B200_CHECK_CUDA(cudaFuncSetAttribute(window_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem)); attr = true; }
   const long long ntasks = 1LL * B * (H / kWs) * (W / kWs) * heads;
@@ -724,6 +728,7 @@ extern "C" int b200_window_attn_bwd(const void* qkv, const float* pos, const flo
   a.dslots = dpos_partial + dpos_rows_floats(blocks);  // scratch layout: [blocks][169] partial rows, then the per-lane slots
   a.B = B; a.H = H; a.W = W; a.C = C; a.heads = heads; a.shifted = shifted; a.scale = 0.17677669529663687f;  // 32^-0.5
   a.div_heads = make_fastdiv(static_cast<uint32_t>(heads)); a.div_nww = make_fastdiv(static_cast<uint32_t>(W / kWs)); a.div_nwh = make_fastdiv(static_cast<uint32_t>(H / kWs));
+  a.ntasks = 1LL * B * (H / kWs) * (W / kWs) * heads; a.rev_tasks = b200_reverse_rows();
   static bool attr = false;
   if (!attr) { B200_CHECK_CUDA(cudaFuncSetAttribute(window_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem)); attr = true; }
   auto st = reinterpret_cast<cudaStream_t>(stream);

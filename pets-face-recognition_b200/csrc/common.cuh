@@ -262,6 +262,9 @@ __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity,
 }
 // suspend-time hint of the single-thread roles (ns); B200_WAIT_NS overrides it for experiments
 int b200_wait_ns();
+// 1: the streaming kernels between two GEMMs (LayerNorm, window attention) walk their rows / tasks in descending order so
+// that producer -> consumer hand-overs of tensors larger than L2 hit the most recently written part; B200_REVERSE=0 disables
+int b200_reverse_rows();
 
 // ---------------------------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor) 2-D tile load, completion on an mbarrier

@@ -52,8 +52,12 @@ template <int LPR, int MAXIT, int U>
 __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, bf16* __restrict__ y,
                                                             float* __restrict__ mean, float* __restrict__ rstd,
-                                                            long long M, int C, float eps) {
+                                                            long long M, int C, float eps, int rev) {
   pdl_grid_sync();
+  // rev: walk the rows from the last to the first.  The producer of x (a GEMM, tiles in ascending row order) has just
+  // left its last ~100 MB in L2 and the consumer of y (the next GEMM) starts at row 0: running this kernel backwards turns
+  // both hand-overs into L2 hits when the tensor is larger than L2 (stages 1-2).
+  auto phys = [&](long long row) { return rev ? M - 1 - row : row; };
   constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & 31;
   const int sub = lane / LPR, l = lane % LPR;
@@ -69,7 +73,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restri
 #pragma unroll
       for (int it = 0; it < MAXIT; ++it) {
         const int ch = l + it * LPR;
-        raw[u][it] = (row < M && ch < chunks) ? ld_nc_v4(x + row * C + ch * 8) : make_uint4(0u, 0u, 0u, 0u);
+        raw[u][it] = (row < M && ch < chunks) ? ld_nc_v4(x + phys(row) * C + ch * 8) : make_uint4(0u, 0u, 0u, 0u);
       }
     }
 #pragma unroll
@@ -105,12 +109,12 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restri
             ld8f(beta + ch * 8, b);
 #pragma unroll
             for (int i = 0; i < 8; ++i) o[i] = (v[it][i] - mu) * rs * g[i] + b[i];
-            st8(y + row * C + ch * 8, o);
+            st8(y + phys(row) * C + ch * 8, o);
           }
         }
         if (l == 0) {
-          if (mean) mean[row] = mu;
-          if (rstd) rstd[row] = rs;
+          if (mean) mean[phys(row)] = mu;
+          if (rstd) rstd[phys(row)] = rs;
         }
       }
     }
@@ -131,10 +135,11 @@ __global__ void __launch_bounds__(kLnBwdThreads, ln_bwd_ctas_per_sm(MAXIT)) laye
                                                             const float* __restrict__ gamma, const float* __restrict__ mean,
                                                             const float* __restrict__ rstd, const bf16* dres,
                                                             bf16* dx, float* __restrict__ partial,
-                                                            long long M, int C) {
+                                                            long long M, int C, int rev) {
   pdl_grid_sync();
   constexpr int RPW = 32 / LPR;
   extern __shared__ float red[];   // [warps][3][C]
+  auto phys = [&](long long row) { return rev ? M - 1 - row : row; };     // see layernorm_fwd_kernel
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane / LPR, l = lane % LPR;
   const long long warp_global = (1LL * blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -154,15 +159,16 @@ __global__ void __launch_bounds__(kLnBwdThreads, ln_bwd_ctas_per_sm(MAXIT)) laye
   float mu_r[D], rs_r[D];
   auto fetch = [&](int slot, long long row) {
     const bool live = row < M;
-    mu_r[slot] = live ? mean[row] : 0.f;
-    rs_r[slot] = live ? rstd[row] : 0.f;
+    const long long prow = phys(row);
+    mu_r[slot] = live ? mean[prow] : 0.f;
+    rs_r[slot] = live ? rstd[prow] : 0.f;
 #pragma unroll
     for (int it = 0; it < MAXIT; ++it) {
       const int ch = l + it * LPR;
       if (live && ch < chunks) {
-        rd[slot][it] = ld_nc_v4(dy + row * C + ch * 8);
-        rx[slot][it] = ld_nc_v4(x + row * C + ch * 8);
-        if (dres) rr[slot][it] = ld_nc_v4(dres + row * C + ch * 8);
+        rd[slot][it] = ld_nc_v4(dy + prow * C + ch * 8);
+        rx[slot][it] = ld_nc_v4(x + prow * C + ch * 8);
+        if (dres) rr[slot][it] = ld_nc_v4(dres + prow * C + ch * 8);
       }
     }
   };
@@ -220,7 +226,7 @@ __global__ void __launch_bounds__(kLnBwdThreads, ln_bwd_ctas_per_sm(MAXIT)) laye
 #pragma unroll
               for (int i = 0; i < 8; ++i) { o[i] += r[i]; if (WITH_RES) dr[it][i] += r[i]; }
             }
-            st8(dx + row * C + ch * 8, o);
+            st8(dx + phys(row) * C + ch * 8, o);
           }
         }
       }
@@ -251,137 +257,6 @@ __global__ void __launch_bounds__(kLnBwdThreads, ln_bwd_ctas_per_sm(MAXIT)) laye
           red[(warp * 3 + 2) * C + ch * 8 + i] = WITH_RES ? dr[it][i] : 0.f;
         }
       }
-    }
-  }
-  __syncthreads();
-  for (int c = threadIdx.x; c < 3 * C; c += blockDim.x) {
-    const int which = c / C, col = c % C;
-    float a = 0.f;
-    for (int w = 0; w < warps; ++w) a += red[(w * 3 + which) * C + col];
-    partial[1LL * blockIdx.x * 3 * C + c] = a;
-  }
-}
-
-// The same backward for the narrow layers (C <= 256: one 8-channel chunk per lane), where the kernel is bound by
-// instruction issue rather than by HBM (ncu, C = 96: 44 instructions per element, 16 of them integer / address work):
-// running element offsets instead of per-row 64-bit index arithmetic, gamma held in registers, and the element-wise math
-// on packed fp32 pairs (FFMA2 / FADD2 / FMUL2).  Same partial-row layout and fold as layernorm_bwd_kernel.
-template <int LPR, bool WITH_RES>
-__global__ void __launch_bounds__(kLnBwdThreads, 4) layernorm_bwd_narrow_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
-                                                            const float* __restrict__ gamma, const float* __restrict__ mean,
-                                                            const float* __restrict__ rstd, const bf16* dres,
-                                                            bf16* dx, float* __restrict__ partial,
-                                                            long long M, int C) {
-  pdl_grid_sync();
-  constexpr int RPW = 32 / LPR;
-  constexpr int D = 3;                       // row groups in flight per warp
-  extern __shared__ float red[];             // [warps][3][C]
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int sub = lane / LPR, l = lane % LPR;
-  const long long warp_global = (1LL * blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long nwarps = (1LL * gridDim.x * blockDim.x) >> 5;
-  const bool has_chunk = l < (C >> 3);
-  const float inv_c = 1.0f / static_cast<float>(C);
-  f32x2 gm[4], dg[4], db[4], dr[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) { gm[i] = 0ull; dg[i] = 0ull; db[i] = 0ull; dr[i] = 0ull; }
-  if (has_chunk) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(gamma + l * 8)), b = __ldg(reinterpret_cast<const float4*>(gamma + l * 8 + 4));
-    gm[0] = pk2(a.x, a.y); gm[1] = pk2(a.z, a.w); gm[2] = pk2(b.x, b.y); gm[3] = pk2(b.z, b.w);
-  }
-  auto unpack2 = [](uint32_t w) { return pk2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); };
-
-  const long long stride = nwarps * RPW;               // rows between consecutive row groups of this warp
-  const long long step = stride * C;                   // the same in elements
-  long long frow = warp_global * RPW + sub;            // next row to fetch / its element offset
-  long long foff = frow * C + l * 8;
-  long long crow = frow, coff = foff;                  // next row to compute
-  uint4 rd[D], rx[D], rr[D];
-  float mu_r[D], rs_r[D];
-  auto fetch = [&](int slot) {
-    const bool live = frow < M;
-    mu_r[slot] = live ? __ldg(mean + frow) : 0.f;
-    rs_r[slot] = live ? __ldg(rstd + frow) : 0.f;
-    if (live && has_chunk) {
-      rd[slot] = ld_nc_v4(dy + foff);
-      rx[slot] = ld_nc_v4(x + foff);
-      if (dres) rr[slot] = ld_nc_v4(dres + foff);
-    }
-    frow += stride;
-    foff += step;
-  };
-#pragma unroll
-  for (int d = 0; d < D; ++d) fetch(d);
-  for (long long row0 = warp_global * RPW; row0 < M; row0 += D * stride) {
-#pragma unroll
-    for (int d = 0; d < D; ++d) {
-      const bool live = crow < M && has_chunk;
-      const float mu = mu_r[d], rs = rs_r[d];
-      const uint4 cd = rd[d], cx = rx[d], cr = rr[d];
-      fetch(d);
-      const uint32_t wd[4] = {cd.x, cd.y, cd.z, cd.w}, wx[4] = {cx.x, cx.y, cx.z, cx.w}, wr[4] = {cr.x, cr.y, cr.z, cr.w};
-      const f32x2 rs2 = dup2(rs), nmr = dup2(-mu * rs);
-      f32x2 g[4], xh[4], s1 = 0ull, s2 = 0ull;
-      if (live) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const f32x2 dv = unpack2(wd[i]);
-          xh[i] = fma2(unpack2(wx[i]), rs2, nmr);
-          g[i] = mul2(dv, gm[i]);
-          s1 = add2(s1, g[i]);
-          s2 = fma2(g[i], xh[i], s2);
-          dg[i] = fma2(dv, xh[i], dg[i]);
-          db[i] = add2(db[i], dv);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { g[i] = 0ull; xh[i] = 0ull; }
-      }
-      float a0, a1, b0, b1;
-      upk2(s1, a0, a1);
-      upk2(s2, b0, b1);
-      const float m1 = group_sum<LPR>(a0 + a1) * inv_c, m2 = group_sum<LPR>(b0 + b1) * inv_c;
-      if (live) {
-        const f32x2 c1 = dup2(-rs * m1), c2 = dup2(-rs * m2);
-        uint32_t ow[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          f32x2 o = fma2(xh[i], c2, fma2(g[i], rs2, c1));           // rs * (g - m1 - xh * m2)
-          if (dres) {
-            const f32x2 r = unpack2(wr[i]);
-            o = add2(o, r);
-            if (WITH_RES) dr[i] = add2(dr[i], r);
-          }
-          float o0, o1;
-          upk2(o, o0, o1);
-          ow[i] = pack_bf16(o0, o1);
-        }
-        *reinterpret_cast<uint4*>(dx + coff) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-      }
-      crow += stride;
-      coff += step;
-    }
-  }
-  // fold the RPW sub-rows of a warp, then the warps of the CTA (as layernorm_bwd_kernel)
-  float fg[8], fb[8], fr[8];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) { upk2(dg[i], fg[2 * i], fg[2 * i + 1]); upk2(db[i], fb[2 * i], fb[2 * i + 1]); upk2(dr[i], fr[2 * i], fr[2 * i + 1]); }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-#pragma unroll
-    for (int o = 16; o >= LPR; o >>= 1) {
-      fg[i] += __shfl_xor_sync(0xffffffffu, fg[i], o);
-      fb[i] += __shfl_xor_sync(0xffffffffu, fb[i], o);
-      if (WITH_RES) fr[i] += __shfl_xor_sync(0xffffffffu, fr[i], o);
-    }
-  }
-  const int warps = blockDim.x >> 5;
-  if (sub == 0 && has_chunk) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      red[(warp * 3 + 0) * C + l * 8 + i] = fg[i];
-      red[(warp * 3 + 1) * C + l * 8 + i] = fb[i];
-      red[(warp * 3 + 2) * C + l * 8 + i] = WITH_RES ? fr[i] : 0.f;
     }
   }
   __syncthreads();
@@ -709,7 +584,7 @@ int ln_fwd_launch(const bf16* x, const float* g, const float* b, bf16* y, float*
   const int rpw = (32 / LPR) * U;
   const long long warps = (M + rpw - 1) / rpw;
   const int blocks = grid_for(warps * 32, 256, b200_num_sms() * 8);
-  launch_pdl(layernorm_fwd_kernel<LPR, MAXIT, U>, dim3(blocks), dim3(256), 0, st, x, g, b, y, mean, rstd, M, C, eps);
+  launch_pdl(layernorm_fwd_kernel<LPR, MAXIT, U>, dim3(blocks), dim3(256), 0, st, x, g, b, y, mean, rstd, M, C, eps, b200_reverse_rows());
   B200_LAUNCH_CHECK();
   return B200_OK;
 }
@@ -717,20 +592,14 @@ template <int LPR, int MAXIT>
 int ln_bwd_launch(const bf16* dy, const bf16* x, const float* g, const float* mean, const float* rstd, const bf16* dres, bf16* dx,
                   float* partial, long long M, int C, int blocks, bool with_res, cudaStream_t st) {
   const size_t smem = sizeof(float) * (kLnBwdThreads / 32) * 3 * C;
-  if (MAXIT == 1) {                                   // narrow layers: the lean packed-math kernel
-    if (with_res) launch_pdl(layernorm_bwd_narrow_kernel<LPR, true>, dim3(blocks), dim3(kLnBwdThreads), smem, st, dy, x, g, mean, rstd, dres, dx, partial, M, C);
-    else launch_pdl(layernorm_bwd_narrow_kernel<LPR, false>, dim3(blocks), dim3(kLnBwdThreads), smem, st, dy, x, g, mean, rstd, dres, dx, partial, M, C);
-    B200_LAUNCH_CHECK();
-    return B200_OK;
-  }
   if (with_res) {
     if (smem > 48 * 1024)
       B200_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<LPR, MAXIT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    launch_pdl(layernorm_bwd_kernel<LPR, MAXIT, true>, dim3(blocks), dim3(kLnBwdThreads), smem, st, dy, x, g, mean, rstd, dres, dx, partial, M, C);
+    launch_pdl(layernorm_bwd_kernel<LPR, MAXIT, true>, dim3(blocks), dim3(kLnBwdThreads), smem, st, dy, x, g, mean, rstd, dres, dx, partial, M, C, b200_reverse_rows());
   } else {
     if (smem > 48 * 1024)
       B200_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<LPR, MAXIT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    launch_pdl(layernorm_bwd_kernel<LPR, MAXIT, false>, dim3(blocks), dim3(kLnBwdThreads), smem, st, dy, x, g, mean, rstd, dres, dx, partial, M, C);
+    launch_pdl(layernorm_bwd_kernel<LPR, MAXIT, false>, dim3(blocks), dim3(kLnBwdThreads), smem, st, dy, x, g, mean, rstd, dres, dx, partial, M, C, b200_reverse_rows());
   }
   B200_LAUNCH_CHECK();
   return B200_OK;

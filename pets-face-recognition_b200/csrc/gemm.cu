@@ -32,6 +32,14 @@ int b200_wait_ns() {
   return ns;
 }
 
+int b200_reverse_rows() {
+  static const int on = [] {
+    const char* e = getenv("B200_REVERSE");
+    return (e != nullptr && e[0] == '0') ? 0 : 1;
+  }();
+  return on;
+}
+
 int b200_num_sms() {
   static int sms[64] = {0};
   int dev = 0;
