@@ -285,7 +285,7 @@ def gpu_arm(args, rank, world, local_rank):
     def host_iter(n):
         for i in range(n):
             yield host_batches[i % 2]
-    trainer.train_batches(module, host_iter(max(2, args.warmup // 2)), [opt])
+    trainer.train_batches(module, host_iter(max(3, args.warmup)), [opt])
     barrier()
     t0 = time.perf_counter()
     losses = trainer.train_batches(module, host_iter(args.steps), [opt], read_loss_every=1)

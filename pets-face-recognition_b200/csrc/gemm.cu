@@ -35,7 +35,7 @@ int b200_wait_ns() {
 int b200_reverse_rows() {
   static const int on = [] {
     const char* e = getenv("B200_REVERSE");
-    return (e != nullptr && e[0] == '0') ? 0 : 1;
+    return (e != nullptr && e[0] == '1') ? 1 : 0;
   }();
   return on;
 }

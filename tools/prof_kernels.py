@@ -109,6 +109,38 @@ def main(what, stage=0, B=256):
             timed(f's{st + 1} fc2       N={Cs} K={4 * Cs}', lambda: ops.gemm_tn(x4, w2, bias=bo, mode=abi.EPI_RESID, aux=r))
             timed(f's{st + 1} qkv dgrad N={Cs} K={3 * Cs}', lambda: ops.gemm_tn(dq, wqt))
             del x, x4, r, dq
+    elif what == 'time_bn':          # tile-width sweep for the small-K layers (more, narrower tiles = deeper A ring)
+        def timed(fn, reps=10):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps * 1e3
+        for st in (0, 1):
+            Cs, Ms = 96 << st, B * (56 >> st) ** 2
+            x, x4, r = rnd(Ms, Cs), rnd(Ms, 4 * Cs), rnd(Ms, Cs)
+            wq, wo, w1, w2 = rnd(3 * Cs, Cs), rnd(Cs, Cs), rnd(4 * Cs, Cs), rnd(Cs, 4 * Cs)
+            b1, bo = torch.randn(4 * Cs, device='cuda'), torch.randn(Cs, device='cuda')
+            dq, wqt, w1t = rnd(Ms, 3 * Cs), rnd(Cs, 3 * Cs), rnd(Cs, 4 * Cs)
+            for bn in (0, 48, 64, 96, 128, 192, 256):
+                row = [f's{st + 1} bn={bn:3d}']
+                for name, fn in (('qkv', lambda: ops.gemm_tn(x, wq, block_n=bn)),
+                                 ('fc1', lambda: ops.gemm_tn(x, w1, bias=b1, mode=abi.EPI_GELU, want_grad=True, block_n=bn)),
+                                 ('outp', lambda: ops.gemm_tn(x, wo, bias=bo, mode=abi.EPI_RESID, aux=r, block_n=bn)),
+                                 ('fc2', lambda: ops.gemm_tn(x4, w2, bias=bo, mode=abi.EPI_RESID, aux=r, block_n=bn)),
+                                 ('fc1dg', lambda: ops.gemm_tn(x4, w1t, block_n=bn)),
+                                 ('qkvdg', lambda: ops.gemm_tn(dq, wqt, block_n=bn))):
+                    try:
+                        row.append(f'{name} {timed(fn):7.1f}')
+                    except Exception as e:           # tile width not valid for this shape
+                        row.append(f'{name}     n/a')
+                print('  '.join(row), flush=True)
+            del x, x4, r, dq
     torch.cuda.synchronize()
     print('done', what)
 
