@@ -298,11 +298,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           else { mbar_wait(aux_bar(ew, 1), aux_phase1); aux_phase1 ^= 1u; }
         }
         const uint32_t srow = sbuf + row_off;
+        // all TMEM loads of the box are issued before the first wait: their latencies overlap instead of adding up
+        uint32_t r[kMaxChunks][16];
+#pragma unroll
+        for (int ci = 0; ci < kMaxChunks; ++ci)
+          if (ci * 16 < p.box_cols) tmem_ld16(taddr + c_tile + ci * 16, r[ci]);
+        tmem_ld_wait();
 #pragma unroll
         for (int ci = 0; ci < kMaxChunks; ++ci) {
           if (ci * 16 < p.box_cols) {
-            uint32_t r[16];
-            tmem_ld16(taddr + c_tile + ci * 16, r);
             float ax[16];
             if (AUX) {      // the bf16 side input sits exactly where the result will be written
 #pragma unroll
@@ -313,13 +317,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 ax[8 * k + 4] = bf16lo(w2); ax[8 * k + 5] = bf16hi(w2); ax[8 * k + 6] = bf16lo(w3); ax[8 * k + 7] = bf16hi(w3);
               }
             }
-            tmem_ld_wait();
             if (!has_k) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) r[i] = 0u;
+              for (int i = 0; i < 16; ++i) r[ci][i] = 0u;
             }
             float o[16], o2[16];
-            Epi::template compute<DUAL>(ep, p, bias_s, row, col_tile + c_tile + ci * 16, reinterpret_cast<const float(&)[16]>(r), ax, o, o2);
+            Epi::template compute<DUAL>(ep, p, bias_s, row, col_tile + c_tile + ci * 16, reinterpret_cast<const float(&)[16]>(r[ci]), ax, o, o2);
             if (OUT_BYTES == 2) {
 #pragma unroll
               for (int k = 0; k < 2; ++k) {
