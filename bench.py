@@ -297,6 +297,7 @@ def gpu_arm(args, rank, world, local_rank):
     e2e_value = world * B * args.steps / t.item()
 
     gallery = gallery_leg(args, rank, world, device) if not args.no_gallery else None
+    extract = extract_leg(args, wrap, dev_batches, world, device) if not args.no_gallery else None
 
     if rank != 0:
         return
@@ -335,6 +336,9 @@ def gpu_arm(args, rank, world, local_rank):
                      'whole_step_frac': value / world * train_flops_per_image() / (peak_tf * 1e12) if peak_tf else None},
         'clocks': clocks,
     }
+    if extract is not None:
+        extract['frac_of_peak'] = extract['tflops'] / peak_tf if peak_tf else None
+        line['extract'] = extract
     if gallery is not None:
         gallery['frac_of_peak'] = gallery['tflops'] / peak_tf if peak_tf else None
         line['gallery'] = gallery
@@ -345,6 +349,35 @@ def gpu_arm(args, rank, world, local_rank):
                                 'sample': f'{steps_cb} steps of batch {cb} after 1 warm-up: same step (Swin-T + ArcFace(C={NUM_CLASS}) + SGD), '
                                           f'oracle/ port, fp32, {torch.get_num_threads()} threads'}
     emit(line)
+
+
+def extract_leg(args, wrap, dev_batches, world, device):
+    """Embedding extraction (BASELINE.json configs[4], first half): forward only, eval mode, the same per-GPU batch, images
+    resident in HBM; value = whole-job images/s (every rank extracts its own shard, no collective)."""
+    import torch.distributed as dist
+    was_training = wrap.training
+    wrap.eval()
+    B = dev_batches[0]['x'].shape[0]
+    reps = max(5, args.steps // 2)
+    with torch.no_grad():
+        for i in range(3):
+            wrap(dev_batches[i % 2]['x'])
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for i in range(reps):
+            emb = wrap(dev_batches[i % 2]['x'])
+        ev1.record()
+        torch.cuda.synchronize()
+    wrap.train(was_training)
+    t = torch.tensor([ev0.elapsed_time(ev1) / reps], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    return {'metric': 'FE extract images/sec (Swin-T forward, eval, bf16)', 'value': world * B / (ms * 1e-3), 'unit': 'images/s',
+            'ms_per_batch': ms, 'batch_per_gpu': B, 'tflops': B * FWD_GFLOP * 1e9 / (ms * 1e-3) / 1e12, 'finite': bool(torch.isfinite(emb).all().item())}
 
 
 def gallery_leg(args, rank, world, device):

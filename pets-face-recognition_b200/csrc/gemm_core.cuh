@@ -285,14 +285,16 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               const int ntile = more_here ? tile : tile + static_cast<int>(gridDim.x);
               if (ntile < num_tiles) issue_aux(ntile, more_here ? box + 1 : box_lo, buf ^ 1);
             }
+          } else if (DUAL) {
+            bulk_wait_read<0>();               // both buffers are rewritten for every box
           } else {
             bulk_wait_read<1>();               // the buffer about to be rewritten was read by the store before last
           }
         }
         __syncwarp();
-        // DUAL: boxes are at most 64 B wide (2 KB), so each 4-KB buffer holds the box of both outputs - double-buffered like
-        // the single-output path (the stores of box i are still being read while box i + 1 is computed and written)
-        const uint32_t sbuf = stg + static_cast<uint32_t>(buf) * kBoxBytes;
+        // DUAL: one 128-B-wide box per output, no double buffering (measured, r01p: halving the boxes to double-buffer them
+        // costs more in per-box overhead than the exposed store latency it hides: fc1 305 -> 343 us)
+        const uint32_t sbuf = stg + (DUAL ? 0u : static_cast<uint32_t>(buf) * kBoxBytes);
         if (AUX) {
           if (buf == 0) { mbar_wait(aux_bar(ew, 0), aux_phase0); aux_phase0 ^= 1u; }
           else { mbar_wait(aux_bar(ew, 1), aux_phase1); aux_phase1 ^= 1u; }
@@ -330,7 +332,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 st_shared_v4(sw, pack_bf16(o[8 * k], o[8 * k + 1]), pack_bf16(o[8 * k + 2], o[8 * k + 3]),
                              pack_bf16(o[8 * k + 4], o[8 * k + 5]), pack_bf16(o[8 * k + 6], o[8 * k + 7]));
                 if (DUAL)
-                  st_shared_v4(sw + kBoxBytes / 2, pack_bf16(o2[8 * k], o2[8 * k + 1]), pack_bf16(o2[8 * k + 2], o2[8 * k + 3]),
+                  st_shared_v4(sw + kBoxBytes, pack_bf16(o2[8 * k], o2[8 * k + 1]), pack_bf16(o2[8 * k + 2], o2[8 * k + 3]),
                                pack_bf16(o2[8 * k + 4], o2[8 * k + 5]), pack_bf16(o2[8 * k + 6], o2[8 * k + 7]));
               }
             } else {
@@ -346,7 +348,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (lane == 0) {
           const int gc = col_tile + c_tile, gr = m_blk * kBlockM + q * 32;
           tma_store_3d(&tmap_o, sbuf, gc, gr, split);
-          if (DUAL) tma_store_3d(&tmap_o2, sbuf + kBoxBytes / 2, gc, gr, split);
+          if (DUAL) tma_store_3d(&tmap_o2, sbuf + kBoxBytes, gc, gr, split);
           bulk_commit();
         }
         buf ^= 1;
@@ -462,7 +464,6 @@ int launch(const Operands& o, const Output& out, const typename Epi::Params& ep,
   B200_REQUIRE((out.ld * out.elem_bytes) % 16 == 0 && (out.split_stride * out.elem_bytes) % 16 == 0, "gemm: output pitch must be a multiple of 16 B");
   p.out_bytes = out.elem_bytes;
   p.box_cols = pick_box_cols(p.block_n, out.elem_bytes);
-  if (DUAL && p.box_cols > 32) p.box_cols = (p.block_n % 32 == 0) ? 32 : 16;     // two outputs share one 4-KB staging buffer
   p.n_out = out.ptr2 != nullptr ? 2 : 1;
   p.has_aux = out.aux != nullptr ? 1 : 0;
   p.colsum_out = out.colsum;
