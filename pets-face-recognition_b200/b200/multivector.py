@@ -93,12 +93,15 @@ def calc_scores(init_db: Dict[Any, Any], extra_db: Dict[Any, Any], strategy: str
             score = ((dot + 1.0) / 2.0).clamp_min(0.0)
         else:
             idx, score = _max_strategy_topk(init_db, extra_db, qn, gn, qsel, gsel, layout, k, device)
-        # Scores that agree to 1e-9 are ties (set means of sign vectors take few distinct values, and the reference's fp32
-        # arithmetic keeps them exactly equal): order them as the reference's stable sort does, by verify order.
+        # Ties: set means of sign vectors take few distinct values and the reference's fp32 arithmetic keeps equal scores
+        # exactly equal, ordering them by verify position (stable sort); here equal scores differ by float noise (~1e-10).
+        # Consecutive scores closer than 1e-8 are chained into one tie group, groups keep their order, members go by index.
         ng = int(gsel.numel())
-        key = torch.round(score * 1e9).to(torch.int64) * (ng + 1) + (ng - idx.long())
-        key = torch.where(idx >= 0, key, torch.full_like(key, torch.iinfo(torch.int64).min))
-        order = torch.argsort(key, dim=1, descending=True)
+        new_group = torch.zeros_like(idx, dtype=torch.int64)
+        new_group[:, 1:] = ((score[:, :-1] - score[:, 1:]) > 1e-8).to(torch.int64)
+        key = torch.cumsum(new_group, dim=1) * (ng + 1) + idx.long().clamp_min(0)
+        key = torch.where(idx >= 0, key, torch.full_like(key, torch.iinfo(torch.int64).max))
+        order = torch.argsort(key, dim=1)
         idx, score = torch.gather(idx, 1, order).cpu(), torch.gather(score, 1, order).cpu()
         gsel_l = gsel.tolist()
         for r, qi in enumerate(qsel.tolist()):
