@@ -164,6 +164,10 @@ int b200_cosine_topk(const float* q, const void* q_unit_f16, const double* q_nor
                      void* stream);
 int b200_topk_merge(const double* scores, const int* idx, long long nq, int lists, int k_in, int k_out, int* out_idx,
                     double* out_score, void* stream);
+/* Pair verification scores, engine/controller.py:60-68 + similarity_f (configs/dog_fe/fe_dogs_config.py:89-93):
+ * out[p] = (cosine(emb[i1[p]], emb[i2[p]]) + 1) / 2 in fp32.  emb [n, dim] fp32, i1 / i2 int64 [n_pairs] (row numbers < n). */
+int b200_pair_similarity(const float* emb, long long n, int dim, const long long* i1, const long long* i2, long long n_pairs,
+                         float* out, void* stream);
 int b200_recall_hits(const int* top_idx, long long nq, int k_stride, const long long* q_class, const long long* g_class,
                      const int* ks, int n_ks, unsigned long long* hits, void* stream);
 

@@ -89,6 +89,7 @@ _PROTOS = {
     'b200_cosine_topk': (c_int, [c_vp, c_vp, c_vp, c_ll, c_vp, c_vp, c_vp, c_ll, c_int, c_int, c_ll, c_ll, c_vp, c_vp, c_vp, c_ll,
                                  c_vp]),
     'b200_topk_merge': (c_int, [c_vp, c_vp, c_ll, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
+    'b200_pair_similarity': (c_int, [c_vp, c_ll, c_int, c_vp, c_vp, c_ll, c_vp, c_vp]),
     'b200_recall_hits': (c_int, [c_vp, c_ll, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp]),
 }
 

@@ -57,6 +57,21 @@ def topk_merge(scores: torch.Tensor, idx: torch.Tensor, k_out: int) -> Tuple[tor
     return out_idx, out_score
 
 
+def pair_similarity(emb: torch.Tensor, idx1: torch.Tensor, idx2: torch.Tensor) -> torch.Tensor:
+    """(cos(emb[idx1[p]], emb[idx2[p]]) + 1) / 2 for every pair, fp32 [n_pairs] on the device: the pair-verification scores of
+    engine/controller.py:60-68 without building 2 x n_pairs Python tensors."""
+    abi.require_device()
+    emb = emb.contiguous().float()
+    idx1 = idx1.to(device=emb.device, dtype=torch.int64).contiguous()
+    idx2 = idx2.to(device=emb.device, dtype=torch.int64).contiguous()
+    if idx1.numel() and (int(torch.max(torch.maximum(idx1, idx2))) >= emb.shape[0] or int(torch.min(torch.minimum(idx1, idx2))) < 0):
+        raise abi.B200Error('pair_similarity: pair index out of range')
+    out = torch.empty(idx1.numel(), device=emb.device, dtype=torch.float32)
+    check(lib().b200_pair_similarity(ptr(emb), emb.shape[0], emb.shape[1], ptr(idx1), ptr(idx2), idx1.numel(), ptr(out), stream_ptr()),
+          'pair_similarity')
+    return out
+
+
 def recall_hits(top_idx: torch.Tensor, q_class: torch.Tensor, g_class: torch.Tensor, ks: Iterable[int]) -> torch.Tensor:
     """hits[i] = #queries with a same-class gallery row among their first ks[i] candidates (engine/controller.py:86-87)."""
     ks = list(ks)

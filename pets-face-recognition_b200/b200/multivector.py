@@ -131,10 +131,14 @@ def _max_strategy_topk(init_db, extra_db, qn, gn, qsel, gsel, layout, k, device)
         return x / x.norm(dim=1, keepdim=True).clamp_min(1e-8), torch.tensor(owner, device=device)
     qa, qo = members(init_db, qn, qsel)
     ga, go = members(extra_db, gn, gsel)
-    cos = ops.gemm_tn(qa.to(torch.float16).contiguous(), ga.to(torch.float16).contiguous(), out_fp32=True)   # [members_q, members_g]
     nq, ng = int(qsel.numel()), int(gsel.numel())
+    pad = (-ga.shape[0]) % 8                    # the GEMM wants its N (gallery member count) in multiples of 8: zero rows,
+    if pad:                                     # owned by a dummy folder that is dropped afterwards
+        ga = torch.cat([ga, torch.zeros(pad, ga.shape[1], device=device)])
+        go = torch.cat([go, torch.full((pad,), ng, device=device, dtype=go.dtype)])
+    cos = ops.gemm_tn(qa.to(torch.float16).contiguous(), ga.to(torch.float16).contiguous(), out_fp32=True)   # [members_q, members_g]
     best = torch.full((nq, cos.shape[1]), -2.0, device=device).scatter_reduce_(0, qo.unsqueeze(1).expand_as(cos), cos, 'amax')
-    best = torch.full((nq, ng), -2.0, device=device).scatter_reduce_(1, go.unsqueeze(0).expand_as(best), best, 'amax')
+    best = torch.full((nq, ng + 1), -2.0, device=device).scatter_reduce_(1, go.unsqueeze(0).expand_as(best), best, 'amax')[:, :ng]
     score, idx = torch.sort((best.double() + 1.0) / 2.0, dim=1, descending=True, stable=True)
     return idx[:, :k].to(torch.int32), score[:, :k]
 

@@ -53,6 +53,9 @@ def similarity_f(pairs):
     return (F.cosine_similarity(t1, t2) + 1) / 2
 
 
+similarity_f.b200_kind = 'cosine01'      # lets the Controller score the verification pairs on the device (b200_pair_similarity)
+
+
 def model():
     return swin_t(num_classes=512)
 

@@ -652,6 +652,34 @@ __global__ void recall_hits_kernel(const int* __restrict__ top_idx, long long nq
     if (first < ks[i]) atomicAdd(&hits[i], 1ULL);
 }
 
+// Pair verification scores (engine/controller.py:60-68 with similarity_f of configs/dog_fe/fe_dogs_config.py:89-93):
+// out[p] = (cos(emb[i1[p]], emb[i2[p]]) + 1) / 2, fp32 like the reference (cosine_similarity's eps on each norm), one warp
+// per pair, fixed summation order (lane-strided chains, xor tree).
+__global__ void __launch_bounds__(256) pair_similarity_kernel(const float* __restrict__ emb, const long long* __restrict__ i1,
+                                                              const long long* __restrict__ i2, long long n_pairs, int dim, float eps,
+                                                              float* __restrict__ out) {
+  pdl_grid_sync();
+  const long long p = (1LL * blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (p >= n_pairs) return;
+  const float* a = emb + i1[p] * dim;
+  const float* b = emb + i2[p] * dim;
+  float ab = 0.f, aa = 0.f, bb = 0.f;
+  for (int d = lane * 4; d < dim; d += 128) {
+    const float4 x = __ldg(reinterpret_cast<const float4*>(a + d)), y = __ldg(reinterpret_cast<const float4*>(b + d));
+    ab = fmaf(x.x, y.x, fmaf(x.y, y.y, fmaf(x.z, y.z, fmaf(x.w, y.w, ab))));
+    aa = fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, fmaf(x.w, x.w, aa))));
+    bb = fmaf(y.x, y.x, fmaf(y.y, y.y, fmaf(y.z, y.z, fmaf(y.w, y.w, bb))));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ab += __shfl_xor_sync(0xffffffffu, ab, o);
+    aa += __shfl_xor_sync(0xffffffffu, aa, o);
+    bb += __shfl_xor_sync(0xffffffffu, bb, o);
+  }
+  if (lane == 0) out[p] = (ab / (fmaxf(sqrtf(aa), eps) * fmaxf(sqrtf(bb), eps)) + 1.0f) * 0.5f;
+}
+
 struct Layout {
   long long scratch, cand_idx, cand_score, cand_cnt, tau, tau_shared, total;
   int q_blocks, lists;
@@ -864,6 +892,16 @@ extern "C" int b200_topk_merge(const double* scores, const int* idx, long long n
   if (smem > 48 * 1024) B200_CHECK_CUDA(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   launch_pdl(merge_kernel, dim3(static_cast<unsigned>(nq)), dim3(256), smem, reinterpret_cast<cudaStream_t>(stream), scores, idx, nq, lists, k_in, n_pow2, k_out,
                                                                                               out_idx, out_score);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+extern "C" int b200_pair_similarity(const float* emb, long long n, int dim, const long long* i1, const long long* i2, long long n_pairs,
+                                    float* out, void* stream) {
+  B200_REQUIRE(dim % 4 == 0 && dim > 0 && n >= 0, "pair_similarity: dim must be a positive multiple of 4 (got %d)", dim);
+  if (n_pairs == 0) return B200_OK;
+  launch_pdl(pair_similarity_kernel, dim3(static_cast<unsigned>((n_pairs * 32 + 255) / 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
+             emb, i1, i2, n_pairs, dim, 1e-8f, out);
   B200_LAUNCH_CHECK();
   return B200_OK;
 }

@@ -5,8 +5,9 @@ names; the two hot pieces run on the B200 kernels:
   training_step / validation_step / test_step  -> model_loss(...)  (models/swin.py + losses/*: native plan)
   the O(N^2) Recall@K loop of test_epoch_end / _evaluate (:77-91, :143-160) -> b200.gallery.recall_at_k
 
-Pair scoring (similarity_f over pair_generator.corrected_indices, :60-68) and the ROC-type metrics stay
-host-side PyTorch, as SURVEY.md 8(a14) scopes them.
+Pair scoring (similarity_f over pair_generator.corrected_indices, :60-68): when the config marks its similarity_f as the
+reference's (cos + 1) / 2, one b200_pair_similarity launch over the index list, and the ROC-type metrics (engine/metrics.py)
+run on the device the scores live on; otherwise the hook is called as in the reference.
 """
 from pathlib import Path
 from typing import Any, Optional
@@ -61,9 +62,16 @@ class Controller(torch.nn.Module):
         return emb[s], classes[s]
 
     def _pair_scores(self, emb, i):
+        """:60-68.  A config whose similarity_f is the reference's (cos + 1) / 2 says so with the function attribute
+        `b200_kind = 'cosine01'`; then the pairs are scored by one kernel over an index list and the scores (and every metric
+        computed from them) stay on the device.  Any other similarity_f is called as the reference calls it."""
         name, pair_generator = self.config.pair_generator(i)
-        scores = self.config.similarity_f([(emb[id1], emb[id2]) for id1, id2 in pair_generator.corrected_indices])
         labels = torch.as_tensor(pair_generator.labels)
+        if emb.is_cuda and getattr(self.config.similarity_f, 'b200_kind', None) == 'cosine01':
+            idx = torch.as_tensor(pair_generator.corrected_indices, dtype=torch.int64).reshape(-1, 2)
+            scores = gallery.pair_similarity(emb.float(), idx[:, 0], idx[:, 1])
+            return name, scores, labels.to(emb.device)
+        scores = self.config.similarity_f([(emb[id1], emb[id2]) for id1, id2 in pair_generator.corrected_indices])
         return name, scores.detach().float().cpu(), labels
 
     def _recall_at_k(self, emb, classes, ks):

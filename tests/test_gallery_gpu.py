@@ -90,3 +90,37 @@ def test_large_scale_properties():
     assert torch.equal(m_idx, idx) and torch.equal(m_score, score)
     r = gallery.recall_at_k(emb[::6].contiguous(), classes[::6].contiguous(), (10, 100))   # stride 6 keeps both images of an identity
     assert 0.0 <= r['Recall@K=10'] <= r['Recall@K=100'] <= 1.0
+
+
+def test_pair_similarity_and_device_metrics_match_host():
+    """Row 8f-2: verification-pair scores from one kernel over an index list == the config's similarity_f on the gathered
+    tensors (engine/controller.py:60-68), and the ROC-type metrics computed on the device == the same functions on the host
+    == scikit-learn's reference implementations."""
+    from sklearn.metrics import average_precision_score, roc_auc_score
+    from b200 import gallery
+    from engine import metrics as M
+    from oracle import rank_oracle
+    g = torch.Generator().manual_seed(3)
+    n, dim, n_pairs = 3000, 512, 20000
+    cls = torch.randint(0, 300, (n,), generator=g)
+    centres = torch.randn(300, dim, generator=g)
+    emb = centres[cls] + 0.9 * torch.randn(n, dim, generator=g)
+    i1, i2 = torch.randint(0, n, (n_pairs,), generator=g), torch.randint(0, n, (n_pairs,), generator=g)
+    i2[: n_pairs // 2] = i1[: n_pairs // 2].roll(1)                       # some structure: many same-class pairs
+    labels = (cls[i1] == cls[i2]).long()
+    scores = gallery.pair_similarity(emb.cuda(), i1, i2)
+    assert scores.is_cuda and scores.dtype == torch.float32
+    ref = rank_oracle.similarity_f([(emb[a], emb[b]) for a, b in zip(i1[:2000].tolist(), i2[:2000].tolist())])
+    assert (scores[:2000].cpu() - ref).abs().max().item() < 2e-6
+    full_ref = (torch.nn.functional.cosine_similarity(emb[i1], emb[i2]) + 1) / 2
+    assert (scores.cpu() - full_ref).abs().max().item() < 2e-6
+    # metrics on the device vs the host path vs scikit-learn
+    auc_d, ap_d = M.auroc(scores, labels.cuda()), M.average_precision(scores, labels.cuda())
+    auc_h, ap_h = M.auroc(scores.cpu(), labels), M.average_precision(scores.cpu(), labels)
+    assert auc_d == pytest.approx(auc_h, abs=1e-12) and ap_d == pytest.approx(ap_h, abs=1e-12)
+    assert auc_d == pytest.approx(roc_auc_score(labels.numpy(), scores.cpu().numpy()), abs=1e-9)
+    assert ap_d == pytest.approx(average_precision_score(labels.numpy(), scores.cpu().numpy()), abs=1e-9)
+    fpr, tpr, thr = M.roc(scores, labels.cuda())
+    assert fpr.is_cuda and M.stat_scores(scores, labels.cuda(), 0.6) == M.stat_scores(scores.cpu(), labels, 0.6)
+    with pytest.raises(Exception):
+        gallery.pair_similarity(emb.cuda(), torch.tensor([0, n]), torch.tensor([1, 2]))
