@@ -375,9 +375,15 @@ int sync_weights(const Ctx& c) {
   const Plan& p = c.p;
   CastJobs jobs{};
   int tiles = 0;
-  bool ok = true;
+  int rc = B200_OK;
+  // one launch per table of 64 matrices: Swin-T (49) takes one, the 24-block variants (Swin-S / B / L: 101) two
   auto add = [&](long long in_off, long long dst_off, long long dst_t_off, int R, int Cc) {
-    if (jobs.n >= 64) { ok = false; return; }
+    if (rc) return;
+    if (jobs.n == 64) {
+      rc = cast_transpose_multi(c.params, c.wc, jobs, tiles, c.st);
+      jobs.n = 0;
+      tiles = 0;
+    }
     CastJob& j = jobs.job[jobs.n++];
     j.in_off = in_off; j.dst_off = dst_off; j.dst_t_off = dst_t_off; j.R = R; j.Cc = Cc;
     j.tile0 = tiles; j.tiles_c = (Cc + 31) / 32;
@@ -395,7 +401,7 @@ int sync_weights(const Ctx& c) {
     }
   }
   add(p.head_w.off, p.head_w16, p.head_w16t, p.num_classes, p.st[3].C);
-  B200_REQUIRE(ok, "sync_weights: more than 64 weight matrices");
+  RC(rc);
   return cast_transpose_multi(c.params, c.wc, jobs, tiles, c.st);
 }
 

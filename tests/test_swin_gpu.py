@@ -169,3 +169,36 @@ def test_uint8_images_equal_totensor_floats(setup):
         a = wrap(u8)
         b = wrap(u8.float() / 255)
     assert torch.equal(a, b)
+
+
+def test_swin_b_variant_forward_backward_matches_oracle():
+    """the other Swin variants of models/swin.py:232-241 run through the same native plan.  Swin-B
+    (hidden 128, 24 blocks, 101 weight matrices -> two weight-cache launches, C up to 1024): embeddings and a sample of
+    gradient tensors against the fp32 oracle on the same seeded weights."""
+    from b200 import abi, synth
+    abi.require_device()
+    from models import swin_b
+    from oracle.swin_oracle import SwinSpec, param_shapes, swin_forward
+    spec = SwinSpec(hidden_dim=128, layers=(2, 2, 18, 2), heads=(4, 8, 16, 32))
+    sd = synth.synth_state_dict(param_shapes(spec), seed=7)
+    model = swin_b(num_classes=512)
+    assert {k: tuple(v.shape) for k, v in model.state_dict().items()} == {k: tuple(v) for k, v in param_shapes(spec).items()}
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().train()
+    img = synth.synth_images(2, seed=7)
+    emb = model(img.cuda())
+    w = torch.randn(2, 512, generator=torch.Generator().manual_seed(1))
+    (emb * w.cuda()).sum().backward()
+    osd = {k: v.clone().requires_grad_(not k.endswith('_mask')) for k, v in sd.items()}
+    ref = swin_forward(osd, img, spec)
+    (ref * w).sum().backward()
+    cos = torch.nn.functional.cosine_similarity(emb.detach().cpu(), ref.detach())
+    assert (1 - cos).max().item() < 1e-3, cos
+    errs = {}
+    for name, p in model.named_parameters():
+        if name.endswith('_mask') or 'pos_embedding' in name:
+            continue
+        assert p.grad is not None and torch.isfinite(p.grad).all(), name
+        errs[name] = rel(p.grad, osd[name].grad)
+    vals = sorted(errs.values())
+    assert vals[len(vals) // 2] < 2e-2 and vals[-1] < 1e-1, sorted(errs.items(), key=lambda kv: -kv[1])[:6]
