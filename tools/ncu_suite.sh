@@ -10,6 +10,7 @@ cap() {   # cap <name> <kernel regex> <skip> <what> [stage]
 }
 cap gemm_fc1 gemm_tn_kernel 2 gemm_fc1
 cap gemm_outproj gemm_tn_kernel 2 gemm_outproj
+cap gemm_qkv gemm_tn_kernel 2 gemm_qkv
 cap gemm_wgrad_small gemm_tn_kernel 2 gemm_wgrad_small
 cap attn_bwd window_attn_bwd 2 attn_bwd
 cap attn_fwd window_attn_fwd 2 attn_fwd
