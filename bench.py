@@ -298,6 +298,7 @@ def gpu_arm(args, rank, world, local_rank):
 
     gallery = gallery_leg(args, rank, world, device) if not args.no_gallery else None
     extract = extract_leg(args, wrap, dev_batches, world, device) if not args.no_gallery else None
+    rows_f = rows_f_leg(device) if (world == 1 and not args.no_gallery) else None
 
     if rank != 0:
         return
@@ -339,6 +340,8 @@ def gpu_arm(args, rank, world, local_rank):
     if extract is not None:
         extract['frac_of_peak'] = extract['tflops'] / peak_tf if peak_tf else None
         line['extract'] = extract
+    if rows_f is not None:
+        line['tsv_scoring'], line['pair_scoring'] = rows_f
     if gallery is not None:
         gallery['frac_of_peak'] = gallery['tflops'] / peak_tf if peak_tf else None
         line['gallery'] = gallery
@@ -348,6 +351,8 @@ def gpu_arm(args, rank, world, local_rank):
         line['cpu_baseline'] = {'value': ips, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
                                 'sample': f'{steps_cb} steps of batch {cb} after 1 warm-up: same step (Swin-T + ArcFace(C={NUM_CLASS}) + SGD), '
                                           f'oracle/ port, fp32, {torch.get_num_threads()} threads'}
+        if rows_f is not None:
+            line['cpu_baseline'].update(rows_f_cpu())
     emit(line)
 
 
@@ -378,6 +383,70 @@ def extract_leg(args, wrap, dev_batches, world, device):
     ms = t.item()
     return {'metric': 'FE extract images/sec (Swin-T forward, eval, bf16)', 'value': world * B / (ms * 1e-3), 'unit': 'images/s',
             'ms_per_batch': ms, 'batch_per_gpu': B, 'tflops': B * FWD_GFLOP * 1e9 / (ms * 1e-3) / 1e12, 'finite': bool(torch.isfinite(emb).all().item())}
+
+
+def _folder_db(n_sets, seed, n_ids, prefix, dim=512):
+    """Synthetic folder database in the reference's layout (generate_tsv_to_reproduce2.py:31-52): 1..4 (1, dim) head vectors."""
+    g = torch.Generator().manual_seed(seed)
+    centres = torch.randn(n_ids, dim, generator=torch.Generator().manual_seed(4321))
+    db = {}
+    for s in range(n_sets):
+        ident = s % n_ids
+        nvec = int(torch.randint(1, 5, (1,), generator=g).item())
+        db[f'{prefix}{s:06d}'] = {'head_vectors': [(centres[ident] + 0.6 * torch.randn(dim, generator=g)).reshape(1, dim) for _ in range(nvec)],
+                                  'type': 1 + ident % 2}
+    return db
+
+
+def rows_f_leg(device):
+    """SURVEY.md 8f-1 / 8f-2 through their public calls: the submission table for 2,000 enroll x 20,000 verify folders
+    (b200.multivector.calc_scores, host dicts in, rows out) and the 20,000 verification-pair scores + AUROC of one
+    Controller evaluation (b200.gallery.pair_similarity + engine.metrics on the device)."""
+    from b200 import gallery, multivector
+    from engine import metrics as M
+    n_q, n_g = 2000, 20000
+    dq, dg = _folder_db(n_q, 1, 5000, 'q'), _folder_db(n_g, 2, 5000, 'g')
+    multivector.calc_scores(dq, dg)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    rows = multivector.calc_scores(dq, dg)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    tsv = {'metric': 'folder pairs scored/sec (multi-vector mean strategy + top-100 + TSV rows, host dicts in)', 'value': n_q * (n_g / 2) / dt,
+           'unit': 'folder pairs/s', 'enroll': n_q, 'verify': n_g, 'seconds': dt, 'rows': len(rows)}
+    g = torch.Generator().manual_seed(5)
+    n, n_pairs = 20000, 20000
+    emb = torch.randn(n, 512, generator=g).to(device)
+    i1, i2 = torch.randint(0, n, (n_pairs,), generator=g), torch.randint(0, n, (n_pairs,), generator=g)
+    labels = torch.randint(0, 2, (n_pairs,), generator=g).to(device)
+    gallery.pair_similarity(emb, i1, i2)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    sc = gallery.pair_similarity(emb, i1, i2)
+    auc = M.auroc(sc, labels)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    pair = {'metric': 'verification pairs/sec (scores + AUROC, device)', 'value': n_pairs / dt, 'unit': 'pairs/s', 'pairs': n_pairs,
+            'seconds': dt, 'auroc': auc}
+    return tsv, pair
+
+
+def rows_f_cpu():
+    """The same two pieces as the reference runs them, on a bounded sample: its per-folder-pair Python loop
+    (oracle.tsv_oracle.calc_scores: 4 enroll x 2,000 verify folders) and similarity_f over a list of 20,000 tensor pairs."""
+    from oracle import rank_oracle, tsv_oracle
+    dq, dg = _folder_db(4, 1, 5000, 'q'), _folder_db(2000, 2, 5000, 'g')
+    t0 = time.perf_counter()
+    tsv_oracle.calc_scores(dq, dg)
+    dt = time.perf_counter() - t0
+    g = torch.Generator().manual_seed(5)
+    emb = torch.randn(20000, 512, generator=g)
+    i1, i2 = torch.randint(0, 20000, (20000,), generator=g), torch.randint(0, 20000, (20000,), generator=g)
+    t1 = time.perf_counter()
+    rank_oracle.similarity_f([(emb[a], emb[b]) for a, b in zip(i1.tolist(), i2.tolist())])
+    dt2 = time.perf_counter() - t1
+    return {'tsv_scoring': {'value': 4 * 1000 / dt, 'unit': 'folder pairs/s', 'sample': '4 enroll x 2,000 verify folders, reference loop (oracle port)'},
+            'pair_scoring': {'value': 20000 / dt2, 'unit': 'pairs/s', 'sample': 'similarity_f over 20,000 gathered tensor pairs (oracle port)'}}
 
 
 def gallery_leg(args, rank, world, device):

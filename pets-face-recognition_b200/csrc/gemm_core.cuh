@@ -30,7 +30,7 @@ constexpr int kBlockK = 64;                       // 64 x 2 B = one 128-B swizzl
 constexpr int kMaxStages = 8;
 constexpr int kMaxBlockN = 256;
 constexpr int kABytes = kBlockM * kBlockK * 2;    // 16 KB
-constexpr int kPipeBytes = 3 * (kABytes + kMaxBlockN * kBlockK * 2);   // 144 KB operand ring: 3 stages at block_n = 256, more below
+constexpr int kMinPipeBytes = 3 * (kABytes + kMaxBlockN * kBlockK * 2);   // the operand ring always holds 3 stages at block_n = 256 (144 KB)
 constexpr int kTmemCols = 512;                    // 2 accumulator stages x 256 fp32 columns
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 64 + kEpiWarps * 32;     // 320
@@ -40,7 +40,14 @@ constexpr int kBarBytes = 512;
 constexpr int kOnesBytes = 64 * 128;                // the all-ones operand tile of the fused bias gradient (shares the bias staging area)
 constexpr int kOnesCol = 240;                     // TMEM columns [240, 256) of an accumulator stage hold its product
 constexpr int kBiasFloats = 4096;                 // the (zero-padded) bias vector is staged in smem once per CTA when it fits
-constexpr int kSmemBytes = kPipeBytes + kEpiWarps * kStagingPerWarp + kBarBytes + kBiasFloats * 4 + 1024 /*alignment slack*/;
+// Every launch asks for the SM's whole 227 KB.  What the epilogue does not need - staging boxes, barriers and the ACTUAL
+// size of the staged bias vector (or the all-ones tile) - goes to the operand ring, whose depth decides how many tiles of A
+// are in flight: with 1.5 tiles (3 stages of a 192-wide tile at K = 96) the issue of a tile's last K block waits for the
+// previous tile's MMA, the tile period equals the HBM latency and the epilogue warps starve on the accumulator barrier
+// (ncu r01t, qkv of stage 1: 16 % of all samples); the fourth stage halves that period.
+constexpr int kSmemBytes = 232448;
+constexpr int kFixedSmem = kEpiWarps * kStagingPerWarp + kBarBytes + 1024 /*alignment slack*/;
+static_assert(kMinPipeBytes + kFixedSmem + kBiasFloats * 4 <= kSmemBytes, "shared memory budget");
 
 struct CoreParams {
   int M, N;                  // output rows (rows of A) / columns (rows of B)
@@ -64,6 +71,7 @@ struct CoreParams {
   float* colsum_out;         // weight gradients only: [splits][M] column sums of the A operand (= the bias gradient), or null
   uint32_t idesc_ones;       // N = 16 instruction descriptor of the all-ones MMA that produces them
   int bias_smem;             // 1: the epilogue reads the bias from its smem copy (padded N <= kBiasFloats)
+  int pipe_bytes;            // operand ring size = stages * stage_bytes (a multiple of 1024)
   uint32_t wait_ns;          // suspend-time hint of the producer / MMA-issuer barrier waits
 };
 
@@ -94,7 +102,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                const __grid_constant__ CUtensorMap tmap_aux, const CoreParams p, const typename Epi::Params ep) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B wants 1024-B alignment
-  const uint32_t staging_base = smem_base + kPipeBytes;
+  const uint32_t staging_base = smem_base + static_cast<uint32_t>(p.pipe_bytes);
   const uint32_t bar_base = staging_base + kEpiWarps * kStagingPerWarp;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
@@ -444,8 +452,6 @@ int launch(const Operands& o, const Output& out, const typename Epi::Params& ep,
   p.b_chunks = (p.block_n + 63) / 64;
   const int b_bytes = o.mn_major ? p.b_chunks * 8192 : p.block_n * kBlockK * 2;
   p.stage_bytes = (kABytes + b_bytes + 1023) / 1024 * 1024;
-  p.stages = kPipeBytes / p.stage_bytes;
-  if (p.stages > kMaxStages) p.stages = kMaxStages;
 
   CUtensorMap ta, tb;
   int rc;
@@ -474,6 +480,10 @@ int launch(const Operands& o, const Output& out, const typename Epi::Params& ep,
   p.div_n = make_fastdiv(static_cast<uint32_t>(p.n_blocks));
   p.div_m = make_fastdiv(static_cast<uint32_t>(p.m_blocks));
   p.bias_smem = (Epi::wants_columns(ep) && 1LL * p.n_blocks * p.block_n <= kBiasFloats) ? 1 : 0;
+  const int extra_bytes = p.bias_smem ? p.n_blocks * p.block_n * 4 : (out.colsum != nullptr ? kOnesBytes : 0);
+  p.stages = (kSmemBytes - kFixedSmem - (extra_bytes + 1023) / 1024 * 1024) / p.stage_bytes;
+  if (p.stages > kMaxStages) p.stages = kMaxStages;
+  p.pipe_bytes = p.stages * p.stage_bytes;
   p.wait_ns = static_cast<uint32_t>(b200_wait_ns());
   CUtensorMap to, to2, tx;
   rc = encode_tmap_out(&to, out.elem_bytes, out.ptr, o.N, o.M, p.splits, out.ld, p.splits > 1 ? out.split_stride : 1LL * o.M * out.ld,

@@ -121,7 +121,7 @@ def main(what, stage=0, B=256):
             e1.record()
             torch.cuda.synchronize()
             return e0.elapsed_time(e1) / reps * 1e3
-        for st in (0, 1):
+        for st in ((0, 1) if stage == 0 else (stage,)):      # `time_bn 2` / `time_bn 3`: stage 3 / 4 shapes only
             Cs, Ms = 96 << st, B * (56 >> st) ** 2
             x, x4, r = rnd(Ms, Cs), rnd(Ms, 4 * Cs), rnd(Ms, Cs)
             wq, wo, w1, w2 = rnd(3 * Cs, Cs), rnd(Cs, Cs), rnd(4 * Cs, Cs), rnd(Cs, 4 * Cs)
