@@ -32,6 +32,8 @@ extern "C" {
 #define B200_EPI_RESID 2   /* out = acc + bias + aux                               Residual, models/swin.py:22-23 */
 #define B200_EPI_DGELU 3   /* out = acc * aux, aux = the out2 saved by B200_EPI_GELU          autograd of models/swin.py:41 */
 #define B200_EPI_PARTIAL 4 /* fp32 out[split] = acc   (split-K partial, weight gradients)                     */
+#define B200_EPI_GELU_Q8 5  /* B200_EPI_GELU with out2 stored as 8-bit codes: uint8 [M, N], q = rint((g + 0.13) * 255 / 1.26) */
+#define B200_EPI_DGELU_Q8 6 /* B200_EPI_DGELU with aux = those uint8 codes                                     */
 
 /* b200_cosine_topk: pass as exclude_self_offset when no gallery row is to be skipped */
 #define B200_NO_EXCLUDE (-(1LL << 62))

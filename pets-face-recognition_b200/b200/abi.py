@@ -17,7 +17,7 @@ import torch
 _LIB_PATH = Path(__file__).resolve().parent / 'libb200fe.so'
 _lib = None
 
-EPI_STORE, EPI_GELU, EPI_RESID, EPI_DGELU, EPI_PARTIAL = range(5)
+EPI_STORE, EPI_GELU, EPI_RESID, EPI_DGELU, EPI_PARTIAL, EPI_GELU_Q8, EPI_DGELU_Q8 = range(7)
 OPT_SGD, OPT_ADAMW = 0, 1
 
 c_ll, c_int, c_float, c_vp = C.c_longlong, C.c_int, C.c_float, C.c_void_p

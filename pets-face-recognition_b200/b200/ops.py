@@ -34,11 +34,20 @@ def gemm_tn(a, b, *, mode=abi.EPI_STORE, bias=None, aux=None, out_fp32=False, wa
         return out
     if out is None:
         out = torch.empty(M, N, device=dev, dtype=torch.float32 if out_fp32 else bf16)
-    dact = torch.empty(M, N, device=dev, dtype=bf16) if (mode == abi.EPI_GELU and want_grad) else None
+    # EPI_GELU_Q8: the derivative comes back as 8-bit codes (see include/b200_fe.h); EPI_DGELU_Q8 takes them as `aux`
+    if mode == abi.EPI_GELU_Q8:
+        dact = torch.empty(M, N, device=dev, dtype=torch.uint8)
+    else:
+        dact = torch.empty(M, N, device=dev, dtype=bf16) if (mode == abi.EPI_GELU and want_grad) else None
     check(lib().b200_gemm_tn(ptr(a), a.stride(0), ptr(b), b.stride(0), M, N, K, is_bf16, mode, ptr(out), out.stride(0),
                              1 if out.dtype == torch.float32 else 0, ptr(dact), N, ptr(bias), ptr(aux),
                              aux.stride(0) if aux is not None else 0, 1, 0, block_n, stream_ptr()), 'gemm_tn')
-    return (out, dact) if mode == abi.EPI_GELU and want_grad else out
+    return (out, dact) if dact is not None else out
+
+
+def gelu_q8_decode(codes):
+    """uint8 codes of B200_EPI_GELU_Q8 -> the GELU derivative they stand for (fp32)."""
+    return codes.float() * (1.26 / 255.0) - 0.13
 
 
 def gemm_wgrad(dy, x, splits=1, block_n=0):

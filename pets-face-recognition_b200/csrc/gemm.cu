@@ -176,7 +176,7 @@ int encode_tmap_out(CUtensorMap* map, int elem_bytes, const void* ptr, uint64_t 
   const CUtensorMapSwizzle swz = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
   if (row_bytes != 128 && row_bytes != 64 && row_bytes != 32)
     return b200_set_error(B200_ERR_INVALID, "output box row of %u B unsupported", row_bytes);
-  CUresult r = fn(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims,
+  CUresult r = fn(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : (elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32), 3, const_cast<void*>(ptr), dims,
                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return b200_set_error(B200_ERR_CUDA, "cuTensorMapEncodeTiled(out) failed (%d) cols=%llu rows=%llu splits=%llu pitch=%llu box=%u", (int)r,
@@ -528,8 +528,11 @@ extern "C" int b200_gemm_tn(const void* a, long long lda, const void* b, long lo
                             int mode, void* out, long long ldo, int out_fp32, void* out2, long long ldo2, const float* bias,
                             const void* aux, long long ldaux, int splits, long long split_stride, int block_n, void* stream) {
   B200_REQUIRE(N % 8 == 0, "gemm_tn: N must be a multiple of 8 (got %d)", N);
-  B200_REQUIRE(mode >= B200_EPI_STORE && mode <= B200_EPI_PARTIAL, "gemm_tn: bad epilogue mode %d", mode);
-  if (mode == B200_EPI_RESID || mode == B200_EPI_DGELU) B200_REQUIRE(aux != nullptr && ldaux % 8 == 0, "gemm_tn: mode needs aux");
+  B200_REQUIRE(mode >= B200_EPI_STORE && mode <= B200_EPI_DGELU_Q8, "gemm_tn: bad epilogue mode %d", mode);
+  const bool q8 = mode == B200_EPI_GELU_Q8 || mode == B200_EPI_DGELU_Q8;      // the GELU derivative travels as 8-bit codes
+  if (mode == B200_EPI_GELU_Q8) { mode = B200_EPI_GELU; B200_REQUIRE(out2 != nullptr, "gemm_tn: GELU_Q8 needs out2"); }
+  if (mode == B200_EPI_DGELU_Q8) mode = B200_EPI_DGELU;
+  if (mode == B200_EPI_RESID || mode == B200_EPI_DGELU) B200_REQUIRE(aux != nullptr && ldaux % (q8 ? 16 : 8) == 0, "gemm_tn: mode needs aux");
   if (mode != B200_EPI_PARTIAL) B200_REQUIRE(splits <= 1, "gemm_tn: split-K only with the PARTIAL epilogue");
   if (mode != B200_EPI_GELU) out2 = nullptr;
   const int eb = (out_fp32 || mode == B200_EPI_PARTIAL) ? 4 : 2;
@@ -544,10 +547,13 @@ extern "C" int b200_gemm_tn(const void* a, long long lda, const void* b, long lo
       if (eb == 2) return gemm::launch<gemm::EpiLinear<B200_EPI_STORE>, 2, false, false>(o, od, {bias}, st);
       return gemm::launch<gemm::EpiLinear<B200_EPI_STORE>, 4, false, false>(o, od, {bias}, st);
     case B200_EPI_GELU:
+      if (out2 != nullptr && q8) return gemm::launch<gemm::EpiLinear<B200_EPI_GELU>, 2, true, false, true>(o, od, {bias}, st);
       if (out2 != nullptr) return gemm::launch<gemm::EpiLinear<B200_EPI_GELU>, 2, true, false>(o, od, {bias}, st);
       return gemm::launch<gemm::EpiLinear<B200_EPI_GELU>, 2, false, false>(o, od, {bias}, st);
     case B200_EPI_RESID: return gemm::launch<gemm::EpiLinear<B200_EPI_RESID>, 2, false, true>(o, od, {bias}, st);
-    case B200_EPI_DGELU: return gemm::launch<gemm::EpiLinear<B200_EPI_DGELU>, 2, false, true>(o, od, {bias}, st);
+    case B200_EPI_DGELU:
+      if (q8) return gemm::launch<gemm::EpiLinear<B200_EPI_DGELU>, 2, false, true, true>(o, od, {bias}, st);
+      return gemm::launch<gemm::EpiLinear<B200_EPI_DGELU>, 2, false, true>(o, od, {bias}, st);
     default: return gemm::launch<gemm::EpiLinear<B200_EPI_PARTIAL>, 4, false, false>(o, od, {bias}, st);
   }
 }

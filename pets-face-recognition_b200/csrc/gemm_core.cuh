@@ -92,10 +92,34 @@ inline uint32_t make_idesc(bool is_bf16, int block_n, bool mn_major = false) {
 __device__ __forceinline__ float bf16lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
+// 8-bit storage of the GELU derivative: gelu'(x) lies in [-0.1290, 1.1290]; q = rint((g - kQ8Lo) * kQ8Scale) in 0..255 has an
+// absolute error <= 0.0025 everywhere - the size of the bf16 rounding error for g near 1, where most of the mass is.
+constexpr float kQ8Lo = -0.13f;
+constexpr float kQ8Scale = 255.0f / 1.26f;
+constexpr float kQ8Step = 1.26f / 255.0f;
+__device__ __forceinline__ uint32_t q8_quant(float g) {
+  uint32_t q;
+  asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(q) : "f"(fmaf(g, kQ8Scale, -kQ8Lo * kQ8Scale)));
+  return q;
+}
+__device__ __forceinline__ uint32_t q8_pack4(float a, float b, float c, float d) {
+  const uint32_t lo = __byte_perm(q8_quant(a), q8_quant(b), 0x3340), hi = __byte_perm(q8_quant(c), q8_quant(d), 0x3340);
+  return __byte_perm(lo, hi, 0x5410);
+}
+// byte k of w -> the float it encodes: 0x4B000000 | q is the float 2^23 + q; subtract, scale, shift
+template <int K>
+__device__ __forceinline__ float q8_dequant(uint32_t w) {
+  const float m = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540 + K));
+  return fmaf(m - 8388608.0f, kQ8Step, kQ8Lo);
+}
+
 // Compile-time specialisation of the epilogue (the small-K layers are bound by the epilogue's instruction issue rate):
 //   Epi       what to compute per element          OUT_BYTES  2 = bf16 output, 4 = fp32 output
 //   DUAL      second bf16 output (GELU derivative)       AUX   bf16 side input streamed by TMA into the staging boxes
-template <class Epi, int OUT_BYTES, bool DUAL, bool AUX>
+//   Q8        the second output (DUAL) / the side input (AUX) is the GELU derivative quantised to 8 bits (see q8_*): the fc1
+//             epilogue is bound by HBM WRITE bandwidth (8 of its 9 tensor units are stores), so a 1-byte derivative cuts its
+//             traffic by a quarter, and the fc2 data-gradient kernel that reads it back by 2 of 9
+template <class Epi, int OUT_BYTES, bool DUAL, bool AUX, bool Q8 = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_o2,
@@ -248,6 +272,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // the row (Swizzle<3|2|1,4,3> of the 128 / 64 / 32-B TMA modes); both are loop invariants
     const uint32_t row_off = static_cast<uint32_t>(lane) * row_bytes;
     const uint32_t swz = ((row_off >> 7) & ((row_bytes >> 4) - 1u)) << 4;
+    // the 8-bit tensor (Q8): one byte per element, so its box rows are box_cols bytes with their own swizzle term
+    const uint32_t row_off8 = static_cast<uint32_t>(lane * p.box_cols);
+    const uint32_t swz8 = ((row_off8 >> 7) & ((static_cast<uint32_t>(p.box_cols) >> 4) - 1u)) << 4;
     constexpr int kChunkBytes = 16 * OUT_BYTES;                   // bytes one 16-column chunk occupies in a box row
     constexpr int kMaxChunks = 128 / kChunkBytes;                 // 4 (bf16) / 2 (fp32)
     const bool aux = AUX && box_hi > box_lo;
@@ -259,7 +286,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     auto issue_aux = [&](int tile, int box, int b) {
       int n_blk, m_blk, split_unused;
       decode(tile, n_blk, m_blk, split_unused);
-      mbar_arrive_expect_tx(aux_bar(ew, b), box_bytes);
+      mbar_arrive_expect_tx(aux_bar(ew, b), Q8 ? 32u * static_cast<uint32_t>(p.box_cols) : box_bytes);
       tma_load_3d(stg + static_cast<uint32_t>(b) * kBoxBytes, &tmap_aux, aux_bar(ew, b), n_blk * p.block_n + box * p.box_cols,
                   m_blk * kBlockM + q * 32, 0);
     };
@@ -308,6 +335,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           else { mbar_wait(aux_bar(ew, 1), aux_phase1); aux_phase1 ^= 1u; }
         }
         const uint32_t srow = sbuf + row_off;
+        uint32_t aux8[kMaxChunks][4];
+        if (AUX && Q8) {
+          // the 1-byte side input shares the buffer the 2-byte result is about to overwrite, with a different row pitch:
+          // every lane pulls its whole row into registers before anybody writes
+#pragma unroll
+          for (int ci = 0; ci < kMaxChunks; ++ci)
+            if (ci * 16 < p.box_cols) ld_shared_v4(sbuf + row_off8 + ((ci * 16) ^ swz8), aux8[ci][0], aux8[ci][1], aux8[ci][2], aux8[ci][3]);
+          __syncwarp();
+        }
         // all TMEM loads of the box are issued before the first wait: their latencies overlap instead of adding up
         uint32_t r[kMaxChunks][16];
 #pragma unroll
@@ -318,7 +354,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int ci = 0; ci < kMaxChunks; ++ci) {
           if (ci * 16 < p.box_cols) {
             float ax[16];
-            if (AUX) {      // the bf16 side input sits exactly where the result will be written
+            if (AUX && Q8) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                ax[4 * k + 0] = q8_dequant<0>(aux8[ci][k]); ax[4 * k + 1] = q8_dequant<1>(aux8[ci][k]);
+                ax[4 * k + 2] = q8_dequant<2>(aux8[ci][k]); ax[4 * k + 3] = q8_dequant<3>(aux8[ci][k]);
+              }
+            } else if (AUX) {      // the bf16 side input sits exactly where the result will be written
 #pragma unroll
               for (int k = 0; k < 2; ++k) {
                 uint32_t w0, w1, w2, w3;
@@ -339,10 +381,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 const uint32_t sw = srow + ((ci * kChunkBytes + 16 * k) ^ swz);
                 st_shared_v4(sw, pack_bf16(o[8 * k], o[8 * k + 1]), pack_bf16(o[8 * k + 2], o[8 * k + 3]),
                              pack_bf16(o[8 * k + 4], o[8 * k + 5]), pack_bf16(o[8 * k + 6], o[8 * k + 7]));
-                if (DUAL)
+                if (DUAL && !Q8)
                   st_shared_v4(sw + kBoxBytes, pack_bf16(o2[8 * k], o2[8 * k + 1]), pack_bf16(o2[8 * k + 2], o2[8 * k + 3]),
                                pack_bf16(o2[8 * k + 4], o2[8 * k + 5]), pack_bf16(o2[8 * k + 6], o2[8 * k + 7]));
               }
+              if (DUAL && Q8)
+                st_shared_v4(sbuf + kBoxBytes + row_off8 + ((ci * 16) ^ swz8), q8_pack4(o2[0], o2[1], o2[2], o2[3]), q8_pack4(o2[4], o2[5], o2[6], o2[7]),
+                             q8_pack4(o2[8], o2[9], o2[10], o2[11]), q8_pack4(o2[12], o2[13], o2[14], o2[15]));
             } else {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
@@ -425,8 +470,9 @@ inline int pick_box_cols(int block_n, int elem_bytes) {
   return 16;
 }
 
-template <class Epi, int OUT_BYTES, bool DUAL, bool AUX>
+template <class Epi, int OUT_BYTES, bool DUAL, bool AUX, bool Q8 = false>
 int launch(const Operands& o, const Output& out, const typename Epi::Params& ep, cudaStream_t stream) {
+  static_assert(!Q8 || ((DUAL || AUX) && OUT_BYTES == 2), "Q8 qualifies the second output / the side input of a bf16 epilogue");
   B200_REQUIRE(out.elem_bytes == OUT_BYTES && (out.ptr2 != nullptr) == DUAL && (out.aux != nullptr) == AUX, "gemm: epilogue specialisation mismatch");
   B200_REQUIRE(o.M > 0 && o.N > 0 && o.K > 0, "gemm: empty problem M=%d N=%d K=%d", o.M, o.N, o.K);
   B200_REQUIRE(o.lda % 8 == 0 && o.ldb % 8 == 0, "gemm: row pitch must be a multiple of 8 elements (16 B)");
@@ -470,6 +516,7 @@ int launch(const Operands& o, const Output& out, const typename Epi::Params& ep,
   B200_REQUIRE((out.ld * out.elem_bytes) % 16 == 0 && (out.split_stride * out.elem_bytes) % 16 == 0, "gemm: output pitch must be a multiple of 16 B");
   p.out_bytes = out.elem_bytes;
   p.box_cols = pick_box_cols(p.block_n, out.elem_bytes);
+  if (Q8) B200_REQUIRE(p.box_cols >= 32, "gemm: the 8-bit GELU-derivative tensor needs boxes of >= 32 columns (block_n %d)", p.block_n);
   p.n_out = out.ptr2 != nullptr ? 2 : 1;
   p.has_aux = out.aux != nullptr ? 1 : 0;
   p.colsum_out = out.colsum;
@@ -490,8 +537,8 @@ int launch(const Operands& o, const Output& out, const typename Epi::Params& ep,
                        p.box_cols);
   if (rc) return rc;
   if (out.ptr2 != nullptr) {
-    B200_REQUIRE(out.elem_bytes == 2 && (out.ld2 * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(out.ptr2) & 15) == 0, "gemm: second output must be bf16, 16-B aligned");
-    rc = encode_tmap_out(&to2, 2, out.ptr2, o.N, o.M, 1, out.ld2, 1LL * o.M * out.ld2, p.box_cols);
+    B200_REQUIRE(out.elem_bytes == 2 && (out.ld2 * (Q8 ? 1 : 2)) % 16 == 0 && (reinterpret_cast<uintptr_t>(out.ptr2) & 15) == 0, "gemm: second output must be 16-B aligned");
+    rc = encode_tmap_out(&to2, Q8 ? 1 : 2, out.ptr2, o.N, o.M, 1, out.ld2, 1LL * o.M * out.ld2, p.box_cols);
     if (rc) return rc;
   } else {
     to2 = to;
@@ -499,14 +546,14 @@ int launch(const Operands& o, const Output& out, const typename Epi::Params& ep,
   tx = to;
   if (out.aux != nullptr) {
     B200_REQUIRE(out.elem_bytes == 2 && out.ptr2 == nullptr && p.splits == 1, "gemm: an aux input needs a single bf16 output");
-    B200_REQUIRE((out.ldaux * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(out.aux) & 15) == 0, "gemm: aux must be 16-B aligned");
-    rc = encode_tmap_out(&tx, 2, out.aux, o.N, o.M, 1, out.ldaux, 1LL * o.M * out.ldaux, p.box_cols);
+    B200_REQUIRE((out.ldaux * (Q8 ? 1 : 2)) % 16 == 0 && (reinterpret_cast<uintptr_t>(out.aux) & 15) == 0, "gemm: aux must be 16-B aligned");
+    rc = encode_tmap_out(&tx, Q8 ? 1 : 2, out.aux, o.N, o.M, 1, out.ldaux, 1LL * o.M * out.ldaux, p.box_cols);
     if (rc) return rc;
   }
 
   static bool attr_done = false;   // per instantiation
   if (!attr_done) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<Epi, OUT_BYTES, DUAL, AUX>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<Epi, OUT_BYTES, DUAL, AUX, Q8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_done = true;
   }
   const long long tiles = 1LL * p.m_blocks * p.n_blocks * p.splits;
@@ -521,9 +568,9 @@ int launch(const Operands& o, const Output& out, const typename Epi::Params& ep,
   }
   // algorithmic HBM bytes of the launch: both operands once, every output (and the aux input) once
   const double io_bytes = 2.0 * (1.0 * o.M + o.N) * o.K + 1.0 * o.M * o.N * p.splits * out.elem_bytes +
-                          (out.ptr2 != nullptr ? 2.0 * o.M * o.N : 0.0) + (out.aux != nullptr ? 2.0 * o.M * o.N : 0.0);
+                          (out.ptr2 != nullptr ? (Q8 ? 1.0 : 2.0) * o.M * o.N : 0.0) + (out.aux != nullptr ? (Q8 ? 1.0 : 2.0) * o.M * o.N : 0.0);
   const bool prof = b200_prof_gemm_begin(stream, 2.0 * o.M * o.N * o.K, io_bytes);
-  launch_pdl(gemm_tn_kernel<Epi, OUT_BYTES, DUAL, AUX>, dim3(ctas), dim3(kThreads), kSmemBytes, stream, ta, tb, to, to2, tx, p, ep);
+  launch_pdl(gemm_tn_kernel<Epi, OUT_BYTES, DUAL, AUX, Q8>, dim3(ctas), dim3(kThreads), kSmemBytes, stream, ta, tb, to, to2, tx, p, ep);
   if (prof) b200_prof_gemm_end(stream);
   B200_LAUNCH_CHECK();
   return B200_OK;

@@ -74,6 +74,28 @@ def test_gemm_epilogues():
     assert rel_err(out, (a.float() @ b.float().t()) * x.float()) < 6e-3
 
 
+@pytest.mark.parametrize('M,N,K', [(1024, 384, 96), (777, 768, 192), (130, 1536, 384), (50, 3072, 768)])
+def test_gemm_gelu_derivative_as_8bit_codes(M, N, K):
+    """B200_EPI_GELU_Q8 / B200_EPI_DGELU_Q8: the saved GELU derivative travels as uint8 codes (step 1.26 / 255): decoded it is
+    within half a step (+ the bf16 rounding of the pre-activation path) of torch's derivative, and the data-gradient epilogue
+    that consumes the codes equals acc * decode(codes)."""
+    from b200 import abi, ops
+    a, b = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=0.2)
+    bias = rnd(N, seed=3, dtype=torch.float32)
+    pre_ref = a.float() @ b.float().t() + bias
+    act, codes = ops.gemm_tn(a, b, bias=bias, mode=abi.EPI_GELU_Q8)
+    assert codes.dtype == torch.uint8 and codes.shape == (M, N)
+    pr = pre_ref.clone().requires_grad_(True)
+    torch.nn.functional.gelu(pr).sum().backward()
+    assert rel_err(act, torch.nn.functional.gelu(pre_ref)) < 6e-3
+    dec = ops.gelu_q8_decode(codes)
+    assert (dec - pr.grad).abs().max().item() < 0.5 * 1.26 / 255 + 2e-3
+    assert rel_err(dec, pr.grad) < 6e-3
+    g, wt = rnd(M, K, seed=5), rnd(N, K, seed=6, scale=0.2)
+    out = ops.gemm_tn(g, wt, mode=abi.EPI_DGELU_Q8, aux=codes)
+    assert rel_err(out, (g.float() @ wt.float().t()) * dec) < 6e-3
+
+
 @pytest.mark.parametrize('M,N,K,splits', [(384, 96, 50000, 37), (96, 48, 6272, 148), (768, 256, 1000, 3), (512, 768, 2, 4)])
 def test_gemm_splitk_partial(M, N, K, splits):
     from b200 import abi, ops
