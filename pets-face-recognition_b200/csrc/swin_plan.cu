@@ -140,7 +140,7 @@ void build(Plan& p) {
         a.xmid = add_ws(p, mc * 2);
         a.mean2 = add_ws(p, Mx * 4); a.rstd2 = add_ws(p, Mx * 4);
         a.xn2 = add_ws(p, mc * 2);
-        a.hgrad = add_ws(p, p.training ? mc * 4 : 256);      // GELU'(pre-activation) as 8-bit codes
+        a.hgrad = add_ws(p, p.training ? mc * 4 * 2 : 256);
         a.hact = add_ws(p, mc * 4 * 2);
         a.xout = add_ws(p, mc * 2);
       } else {
@@ -285,7 +285,7 @@ int forward(const Ctx& c, const void* img, int img_u8, float* emb) {
       RC(b200_layernorm_fwd(xmid, c.P(q.ln2_w), c.P(q.ln2_b), xn2, c.W<float>(a.mean2), c.W<float>(a.rstd2), S.M, C, 1e-5f, c.stv));
       bf16* hact = c.W<bf16>(a.hact);
       // training also keeps GELU'(pre-activation) (out2): backward multiplies by it
-      RC(linear_fwd(c, xn2, S.M, C, c.wc + q.w116, 4 * C, c.P(q.b1), p.training ? B200_EPI_GELU_Q8 : B200_EPI_GELU, hact, p.training ? c.W<bf16>(a.hgrad) : nullptr, nullptr));
+      RC(linear_fwd(c, xn2, S.M, C, c.wc + q.w116, 4 * C, c.P(q.b1), B200_EPI_GELU, hact, p.training ? c.W<bf16>(a.hgrad) : nullptr, nullptr));
       // inference shares one block's buffers: the block input may live in xout, so alternate with x0
       bf16* xout = c.W<bf16>(a.xout);
       if (!p.training && x == xout) xout = c.W<bf16>(p.st[0].x0);
@@ -336,7 +336,7 @@ int backward(const Ctx& c, const float* demb, int stage_hi, int stage_lo) {
       bf16* dbig = c.W<bf16>(p.d_big);
       bf16* dsmall = c.W<bf16>(p.d_small);
       // ---- MLP: x_out = x_mid + W2 gelu(W1 LN2(x_mid) + b1) + b2
-      RC(linear_dgrad(c, g, M, C, c.wc + q.w216t, 4 * C, B200_EPI_DGELU_Q8, dbig, c.W<bf16>(a.hgrad)));   // d h_pre = (dy W2) o gelu'(h_pre)
+      RC(linear_dgrad(c, g, M, C, c.wc + q.w216t, 4 * C, B200_EPI_DGELU, dbig, c.W<bf16>(a.hgrad)));   // d h_pre = (dy W2) o gelu'(h_pre)
       RC(linear_wgrad(c, g, M, C, c.W<bf16>(a.hact), 4 * C, c.G(q.w2)));
       RC(linear_dgrad(c, dbig, M, 4 * C, c.wc + q.w116t, C, B200_EPI_STORE, dsmall, nullptr));        // d xn2
       RC(linear_wgrad(c, dbig, M, 4 * C, c.W<bf16>(a.xn2), C, c.G(q.w1), c.G(q.b1)));            // + d b1 = colsum(d h_pre)
