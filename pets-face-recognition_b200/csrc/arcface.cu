@@ -100,19 +100,34 @@ __global__ void __launch_bounds__(256) margin_ce_kernel(const float* __restrict_
   if (threadIdx.x == 0) rdot[b] = dot;
 }
 
-// cdot[c] = sum_b G[b,c] * cos[b,c]; thread per column
-__global__ void margin_coldot_kernel(const bf16* __restrict__ G, long long ldg, const float* __restrict__ logits, long long ldl,
-                                     const long long* __restrict__ label, const float* __restrict__ cos_label, int B, int C, float s,
-                                     float* __restrict__ cdot) {
+// cdot[c] = sum_b G[b,c] * cos[b,c].  32 columns x 8 row lanes per CTA: row lane r sums b = r, r + 8, ... in order, a fixed
+// smem tree folds the 8 partial sums (deterministic; a thread per column walking all B rows was latency-bound: 115 us at
+// B = 256, C = 10,000 with 40 CTAs on 148 SMs)
+__global__ void __launch_bounds__(256) margin_coldot_kernel(const bf16* __restrict__ G, long long ldg, const float* __restrict__ logits,
+                                                            long long ldl, const long long* __restrict__ label,
+                                                            const float* __restrict__ cos_label, int B, int C, float s,
+                                                            float* __restrict__ cdot) {
   pdl_grid_sync();
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+  __shared__ float red[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
   float acc = 0.f;
-  for (int b = 0; b < B; ++b) {
-    const float cosv = (c == static_cast<int>(label[b])) ? cos_label[b] : logits[1LL * b * ldl + c] / s;
-    acc += __bfloat162float(G[1LL * b * ldg + c]) * cosv;
+  if (c < C) {
+    const float inv_s = 1.0f / s;
+#pragma unroll 4
+    for (int b = ry; b < B; b += 8) {
+      const float cosv = (c == static_cast<int>(label[b])) ? cos_label[b] : logits[1LL * b * ldl + c] * inv_s;
+      acc = fmaf(__bfloat162float(G[1LL * b * ldg + c]), cosv, acc);
+    }
   }
-  cdot[c] = acc;
+  red[ry][cx] = acc;
+  __syncthreads();
+  if (ry == 0 && c < C) {
+    float a = red[0][cx];
+#pragma unroll
+    for (int r = 1; r < 8; ++r) a += red[r][cx];
+    cdot[c] = a;
+  }
 }
 
 __global__ void mean_kernel(const float* __restrict__ x, int n, float* __restrict__ out) {
@@ -180,7 +195,7 @@ extern "C" int b200_margin_ce(const float* logits, long long ldl, const long lon
     B200_LAUNCH_CHECK();
   }
   if (G != nullptr && cdot != nullptr) {
-    launch_pdl(margin_coldot_kernel, dim3((C + 255) / 256), dim3(256), 0, st, reinterpret_cast<const bf16*>(G), ldg, logits, ldl, label, cos_label, B, C, s, cdot);
+    launch_pdl(margin_coldot_kernel, dim3((C + 31) / 32), dim3(256), 0, st, reinterpret_cast<const bf16*>(G), ldg, logits, ldl, label, cos_label, B, C, s, cdot);
     B200_LAUNCH_CHECK();
   }
   return B200_OK;
