@@ -262,6 +262,7 @@ __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity,
 }
 // suspend-time hint of the single-thread roles (ns); B200_WAIT_NS overrides it for experiments
 int b200_wait_ns();
+int b200_epi16();   // 1 (default): small-K plain GEMM epilogues run with 16 epilogue warps; B200_EPI16=0 -> 8
 // B200_REVERSE=1 (experiment, default off): the streaming kernels between two GEMMs (LayerNorm, window attention) walk their
 // rows / tasks in descending order so that producer -> consumer hand-overs of tensors larger than L2 would hit the most
 // recently written part.  Measured on B200 (r01m, 2 x 2 runs): no gain (20.1 / 20.4 ms vs 19.9 / 20.1 ms per step).

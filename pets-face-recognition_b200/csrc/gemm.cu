@@ -32,6 +32,14 @@ int b200_wait_ns() {
   return ns;
 }
 
+int b200_epi16() {
+  static const int on = [] {
+    const char* e = getenv("B200_EPI16");
+    return (e != nullptr && e[0] == '0') ? 0 : 1;
+  }();
+  return on;
+}
+
 int b200_reverse_rows() {
   static const int on = [] {
     const char* e = getenv("B200_REVERSE");
@@ -544,6 +552,8 @@ extern "C" int b200_gemm_tn(const void* a, long long lda, const void* b, long lo
   auto st = reinterpret_cast<cudaStream_t>(stream);
   switch (mode) {
     case B200_EPI_STORE:
+      // small-K bf16 layers (K <= 5 blocks of 64): epilogue-latency bound -> sixteen epilogue warps (B200_EPI16=0 disables)
+      if (eb == 2 && K <= 320 && b200_epi16()) return gemm::launch<gemm::EpiLinear<B200_EPI_STORE>, 2, false, false, false, 16>(o, od, {bias}, st);
       if (eb == 2) return gemm::launch<gemm::EpiLinear<B200_EPI_STORE>, 2, false, false>(o, od, {bias}, st);
       return gemm::launch<gemm::EpiLinear<B200_EPI_STORE>, 4, false, false>(o, od, {bias}, st);
     case B200_EPI_GELU:

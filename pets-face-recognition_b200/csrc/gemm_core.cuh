@@ -120,8 +120,11 @@ __device__ __forceinline__ float q8_dequant(uint32_t w) {
 //             less traffic for the fc1 epilogue and 1.2 GB less saved activations at batch 256.  Measured (r01v): NOT faster -
 //             fc1 1.69 -> 1.79 ms per step, the epilogue is bound by instruction issue / latency, not by the stores - so the
 //             training plan keeps the bf16 derivative; the modes stay available (B200_EPI_GELU_Q8 / B200_EPI_DGELU_Q8)
-template <class Epi, int OUT_BYTES, bool DUAL, bool AUX, bool Q8 = false>
-__global__ void __launch_bounds__(kThreads, 1)
+//   EW        epilogue warps: 8 (two per scheduler, double-buffered staging boxes) or 16 (four per scheduler, one staging box
+//             each, plain epilogues only).  The small-K layers are bound by the latency chain of a box (barrier -> tcgen05.ld
+//             -> convert -> st.shared -> fence -> TMA store), and two warps per scheduler do not cover it.
+template <class Epi, int OUT_BYTES, bool DUAL, bool AUX, bool Q8 = false, int EW = kEpiWarps>
+__global__ void __launch_bounds__(64 + EW * 32, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_o2,
                const __grid_constant__ CUtensorMap tmap_aux, const CoreParams p, const typename Epi::Params ep) {
@@ -134,7 +137,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kMaxStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kMaxStages + 2 + a); };
   auto aux_bar = [&](int w, int b) { return bar_base + 8u * (2 * kMaxStages + 4 + 2 * w + b); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 4 + 2 * kEpiWarps);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 4 + 2 * EW);
+  constexpr int kStg = kEpiWarps * kStagingPerWarp / EW;      // staging bytes per epilogue warp: 8 KB (two boxes) or 4 KB (one)
+  static_assert(EW == 8 || (EW == 16 && !DUAL && !AUX), "16 epilogue warps: plain epilogues only");
   const uint32_t bias_base = bar_base + kBarBytes;
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
@@ -150,13 +155,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    for (int w = 0; w < kEpiWarps; ++w) {
+    for (int w = 0; w < EW; ++w) {
       mbar_init(aux_bar(w, 0), 1);
       mbar_init(aux_bar(w, 1), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), kEpiWarps);   // one arrival per epilogue warp
+      mbar_init(tempty_bar(a), EW);          // one arrival per epilogue warp
     }
     mbar_fence_init();
   }
@@ -168,7 +173,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // Bias gradient for free: db[m] = sum_t dY[t, m] is the weight-gradient GEMM with an all-ones second operand.  One
     // 8-KB tile of bf16 1.0 (layout and swizzle are irrelevant: every element is equal) sits where the bias staging would
     // be, and each K block gets four extra N = 16 MMAs into 16 spare TMEM columns of the accumulator stage.
-    for (int i = threadIdx.x; i < kOnesBytes / 16; i += kThreads) st_shared_v4(bias_base + 16u * i, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    for (int i = threadIdx.x; i < kOnesBytes / 16; i += 64 + EW * 32) st_shared_v4(bias_base + 16u * i, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
     fence_proxy_async_smem();
   }
   tc_fence_before();
@@ -264,9 +269,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int ew = warp - 2;                // epilogue warp 0..7
     const int q = warp & 3;                 // TMEM lane quarter this warp may access (hardware rule: warp_id % 4)
     const int nboxes = p.block_n / p.box_cols;
-    const int box_lo = (ew < 4) ? 0 : (nboxes + 1) / 2;          // the two warps of a quarter split the column boxes
-    const int box_hi = (ew < 4) ? (nboxes + 1) / 2 : nboxes;
-    const uint32_t stg = staging_base + ew * kStagingPerWarp;
+    constexpr int kWpq = EW / 4;                                  // the warps of a lane quarter split the column boxes
+    const int wq = ew >> 2;
+    const int box_lo = (nboxes * wq + kWpq - 1) / kWpq;
+    const int box_hi = (nboxes * (wq + 1) + kWpq - 1) / kWpq;
+    const uint32_t stg = staging_base + ew * kStg;
     const uint32_t row_bytes = static_cast<uint32_t>(p.box_cols * OUT_BYTES);
     const uint32_t box_bytes = 32u * row_bytes;
     // this lane's row inside a staging box, and its swizzle term: the 16-B chunk index is XORed with address bits 7.. of
@@ -296,8 +303,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     // broadcast shared loads and needs no column guard
     const float* bias_s = reinterpret_cast<const float*>(smem_raw + (bias_base - smem_u32(smem_raw)));
     if (p.bias_smem) {
-      Epi::stage_columns(ep, p, const_cast<float*>(bias_s), static_cast<int>(threadIdx.x) - 64, kEpiWarps * 32);
-      asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+      Epi::stage_columns(ep, p, const_cast<float*>(bias_s), static_cast<int>(threadIdx.x) - 64, EW * 32);
+      asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
     }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int n_blk, m_blk, split;
@@ -323,6 +330,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
           } else if (DUAL) {
             bulk_wait_read<0>();               // both buffers are rewritten for every box
+          } else if (EW == 16) {
+            bulk_wait_read<0>();               // one staging box per warp: the other warps of the scheduler cover the wait
           } else {
             bulk_wait_read<1>();               // the buffer about to be rewritten was read by the store before last
           }
@@ -330,7 +339,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         __syncwarp();
         // DUAL: one 128-B-wide box per output, no double buffering (measured, r01p: halving the boxes to double-buffer them
         // costs more in per-box overhead than the exposed store latency it hides: fc1 305 -> 343 us)
-        const uint32_t sbuf = stg + (DUAL ? 0u : static_cast<uint32_t>(buf) * kBoxBytes);
+        const uint32_t sbuf = stg + ((DUAL || EW == 16) ? 0u : static_cast<uint32_t>(buf) * kBoxBytes);
         if (AUX) {
           if (buf == 0) { mbar_wait(aux_bar(ew, 0), aux_phase0); aux_phase0 ^= 1u; }
           else { mbar_wait(aux_bar(ew, 1), aux_phase1); aux_phase1 ^= 1u; }
@@ -346,14 +355,21 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           __syncwarp();
         }
         // all TMEM loads of the box are issued before the first wait: their latencies overlap instead of adding up
+        // (with 16 epilogue warps the register budget is 112 per thread: one chunk at a time, the other warps overlap)
         uint32_t r[kMaxChunks][16];
+        if (EW != 16) {
 #pragma unroll
-        for (int ci = 0; ci < kMaxChunks; ++ci)
-          if (ci * 16 < p.box_cols) tmem_ld16(taddr + c_tile + ci * 16, r[ci]);
-        tmem_ld_wait();
+          for (int ci = 0; ci < kMaxChunks; ++ci)
+            if (ci * 16 < p.box_cols) tmem_ld16(taddr + c_tile + ci * 16, r[ci]);
+          tmem_ld_wait();
+        }
 #pragma unroll
         for (int ci = 0; ci < kMaxChunks; ++ci) {
           if (ci * 16 < p.box_cols) {
+            if (EW == 16) {
+              tmem_ld16(taddr + c_tile + ci * 16, r[ci]);
+              tmem_ld_wait();
+            }
             float ax[16];
             if (AUX && Q8) {
 #pragma unroll
@@ -471,7 +487,7 @@ inline int pick_box_cols(int block_n, int elem_bytes) {
   return 16;
 }
 
-template <class Epi, int OUT_BYTES, bool DUAL, bool AUX, bool Q8 = false>
+template <class Epi, int OUT_BYTES, bool DUAL, bool AUX, bool Q8 = false, int EW = kEpiWarps>
 int launch(const Operands& o, const Output& out, const typename Epi::Params& ep, cudaStream_t stream) {
   static_assert(!Q8 || ((DUAL || AUX) && OUT_BYTES == 2), "Q8 qualifies the second output / the side input of a bf16 epilogue");
   B200_REQUIRE(out.elem_bytes == OUT_BYTES && (out.ptr2 != nullptr) == DUAL && (out.aux != nullptr) == AUX, "gemm: epilogue specialisation mismatch");
@@ -554,7 +570,7 @@ int launch(const Operands& o, const Output& out, const typename Epi::Params& ep,
 
   static bool attr_done = false;   // per instantiation
   if (!attr_done) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<Epi, OUT_BYTES, DUAL, AUX, Q8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<Epi, OUT_BYTES, DUAL, AUX, Q8, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_done = true;
   }
   const long long tiles = 1LL * p.m_blocks * p.n_blocks * p.splits;
@@ -571,7 +587,7 @@ int launch(const Operands& o, const Output& out, const typename Epi::Params& ep,
   const double io_bytes = 2.0 * (1.0 * o.M + o.N) * o.K + 1.0 * o.M * o.N * p.splits * out.elem_bytes +
                           (out.ptr2 != nullptr ? (Q8 ? 1.0 : 2.0) * o.M * o.N : 0.0) + (out.aux != nullptr ? (Q8 ? 1.0 : 2.0) * o.M * o.N : 0.0);
   const bool prof = b200_prof_gemm_begin(stream, 2.0 * o.M * o.N * o.K, io_bytes);
-  launch_pdl(gemm_tn_kernel<Epi, OUT_BYTES, DUAL, AUX, Q8>, dim3(ctas), dim3(kThreads), kSmemBytes, stream, ta, tb, to, to2, tx, p, ep);
+  launch_pdl(gemm_tn_kernel<Epi, OUT_BYTES, DUAL, AUX, Q8, EW>, dim3(ctas), dim3(64 + EW * 32), kSmemBytes, stream, ta, tb, to, to2, tx, p, ep);
   if (prof) b200_prof_gemm_end(stream);
   B200_LAUNCH_CHECK();
   return B200_OK;
