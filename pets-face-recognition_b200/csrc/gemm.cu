@@ -552,8 +552,9 @@ extern "C" int b200_gemm_tn(const void* a, long long lda, const void* b, long lo
   auto st = reinterpret_cast<cudaStream_t>(stream);
   switch (mode) {
     case B200_EPI_STORE:
-      // small-K bf16 layers (K <= 5 blocks of 64): epilogue-latency bound -> sixteen epilogue warps (B200_EPI16=0 disables)
-      if (eb == 2 && K <= 320 && b200_epi16()) return gemm::launch<gemm::EpiLinear<B200_EPI_STORE>, 2, false, false, false, 16>(o, od, {bias}, st);
+      // small-K bf16 layers (K <= 4 blocks of 64): sixteen epilogue warps (B200_EPI16=0 -> eight).  Measured (r01y): qkv of stage 1
+      // 143.5 -> 134.8 us, out-projection data gradient 60.1 -> 57.7 us, nothing elsewhere: the warp count is not what starves these layers
+      if (eb == 2 && K <= 256 && b200_epi16()) return gemm::launch<gemm::EpiLinear<B200_EPI_STORE>, 2, false, false, false, 16>(o, od, {bias}, st);
       if (eb == 2) return gemm::launch<gemm::EpiLinear<B200_EPI_STORE>, 2, false, false>(o, od, {bias}, st);
       return gemm::launch<gemm::EpiLinear<B200_EPI_STORE>, 4, false, false>(o, od, {bias}, st);
     case B200_EPI_GELU:
