@@ -27,7 +27,7 @@ IMAGE_SUFFIXES = ('.jpg', '.png', '.JPG', 'jpeg')      # compared with the last 
 
 def uint8_chw(img: np.ndarray) -> torch.Tensor:
     """HWC uint8 image -> CHW uint8 tensor (the fast input layout of the B200 path; the model divides by 255)."""
-    return torch.from_numpy(np.ascontiguousarray(img)).permute(2, 0, 1).contiguous()
+    return torch.from_numpy(np.array(img, dtype=np.uint8, copy=True)).permute(2, 0, 1).contiguous()     # PIL's buffer is read-only
 
 
 def check_dir(path, type_, min_number) -> bool:

@@ -67,3 +67,30 @@ def test_pair_cache_subset_and_uint8_path(trees, tmp_path):
             [bad[i] for i in range(len(bad))]
     finally:
         stray.unlink()
+
+
+def test_real_data_config_loads_on_a_folder_tree(tmp_path, monkeypatch):
+    """configs/dog_fe/swin_t_dog_head.py (the reference's fe_dogs_config.py on models.swin_t): split by users, pair
+    generator over the validation users, loaders yielding the reference's item format through its torchvision augmentations."""
+    from PIL import Image
+    from utils import get_config
+    root = tmp_path / 'dogs'
+    rng = np.random.RandomState(0)
+    for u in range(8):
+        d = root / f'dog_{u:02d}'
+        d.mkdir(parents=True)
+        for j in range(3):
+            Image.fromarray(rng.randint(0, 256, (230, 240, 3)).astype(np.uint8)).save(d / f'{j}.jpg')
+    monkeypatch.setenv('PETS_DOGS_ROOT', str(root))
+    monkeypatch.setenv('PETS_PAIRS', '12')
+    monkeypatch.chdir(tmp_path)
+    cfg = get_config(Path(__file__).resolve().parents[1] / 'pets-face-recognition_b200' / 'configs/dog_fe/swin_t_dog_head.py')
+    assert len(cfg.train_users) == 4 and len(cfg.val_users) == 4 and cfg.n_train_classes == 4
+    name, pg = cfg.pair_generator(0)
+    assert name == 'Val' and len(pg) == 24 and pg.labels.sum() == 12
+    assert max(max(p) for p in pg.corrected_indices) < len(cfg.val)
+    item = cfg.train[0]
+    assert item['x'].shape == (3, 224, 224) and item['x'].dtype == torch.float32 and 0 <= item['label'] < 4
+    batch = next(iter(cfg.val_dataloader()))
+    assert batch['x'].shape == (12, 3, 230, 240) and set(batch) == {'x', 'label', 'index'}
+    assert getattr(cfg.similarity_f, 'b200_kind', None) == 'cosine01'
