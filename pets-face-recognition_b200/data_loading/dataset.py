@@ -30,51 +30,51 @@ def uint8_chw(img: np.ndarray) -> torch.Tensor:
     return torch.from_numpy(np.array(img, dtype=np.uint8, copy=True)).permute(2, 0, 1).contiguous()     # PIL's buffer is read-only
 
 
+def _card_type(folder: Path) -> int:
+    with open(folder / CARD, 'r', encoding='utf-8') as fp:
+        return int(json.load(fp)['pet']['animal'])
+
+
+def _content(folder: Path):
+    return [f for f in folder.iterdir() if f.name != CARD]
+
+
 def check_dir(path, type_, min_number) -> bool:
     """An identity folder qualifies when its card says `type_` and it holds at least `min_number` files besides the card."""
-    path = Path(path)
-    if not path.is_dir():
+    folder = Path(path)
+    return folder.is_dir() and _card_type(folder) == type_ and len(_content(folder)) >= min_number
+
+
+def _opens(path, preprocessor) -> bool:
+    try:
+        pixels = np.asarray(Image.open(path))
+        if preprocessor:
+            preprocessor(pixels)
+        return True
+    except Exception:
         return False
-    with open(path / CARD, 'r', encoding='utf-8') as fp:
-        card = json.load(fp)
-    n_files = sum(1 for f in path.iterdir() if f.name != CARD)
-    return n_files >= min_number and int(card['pet']['animal']) == type_
 
 
 def check(paths, preprocessor=None):
     """The paths that open as images (and survive the preprocessor, if any)."""
-    good = []
-    for p in paths:
-        try:
-            img = np.asarray(Image.open(p))
-            if preprocessor:
-                preprocessor(img)
-        except Exception:
-            continue
-        good.append(p)
-    return good
+    return [p for p in paths if _opens(p, preprocessor)]
 
 
 def init_dataset(path, type_=1, min_number=3, preprocessor=None, paths_to_exclude=None):
-    excluded = {Path(p).resolve() for p in paths_to_exclude} if paths_to_exclude is not None else set()
-    user_to_paths = {}
-    for folder in Path(path).iterdir():
-        if not check_dir(folder, type_, min_number):
-            continue
-        files = [f for f in folder.iterdir() if f.name != CARD and f.resolve() not in excluded]
-        files = check(files, preprocessor)
-        if len(files) >= min_number:
-            user_to_paths[folder] = files
-    return user_to_paths
+    """Folders of pet type `type_` (card.json) with at least `min_number` readable, non-excluded images."""
+    skip = {Path(p).resolve() for p in (paths_to_exclude or ())}
+    found = {}
+    for folder in (f for f in Path(path).iterdir() if check_dir(f, type_, min_number)):
+        images = check([f for f in _content(folder) if f.resolve() not in skip], preprocessor)
+        if len(images) >= min_number:
+            found[folder] = images
+    return found
 
 
 def simple_init_dataset(path, type_, min_number, *_, **__):
-    user_to_paths = {}
-    for folder in Path(path).iterdir():
-        files = list(folder.iterdir())
-        if len(files) >= min_number:
-            user_to_paths[folder] = files
-    return user_to_paths
+    """Every folder with at least `min_number` files, whatever they are (no card, no decoding check)."""
+    listing = {folder: list(folder.iterdir()) for folder in Path(path).iterdir()}
+    return {folder: files for folder, files in listing.items() if len(files) >= min_number}
 
 
 class RecDataset(Dataset):

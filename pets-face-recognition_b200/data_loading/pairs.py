@@ -10,6 +10,7 @@ identities to their rank among them: the position of the image in an embedding m
 """
 from __future__ import annotations
 
+import itertools
 import pickle
 from pathlib import Path
 
@@ -35,60 +36,47 @@ class PairGenerator(Dataset):
 
     def generate_pairs(self, gen_number, gen_ratio, path, random_seed, usr_list):
         rng = np.random.RandomState(random_seed)
+        wanted = set(usr_list)
+        members = {u: idx for u, idx in self.dataset.uid_to_indices.items() if u in wanted}     # dataset order kept
         n_total = len(self.dataset)
-        users = set(usr_list)
-        members = {u: idx for u, idx in self.dataset.uid_to_indices.items() if u in users}     # dataset order kept
-
-        def genuine_capacity(idx):
-            return len(idx) * len(idx) - len(idx)
-
-        def impostor_capacity(idx):
-            return n_total * len(idx) - min(n_total, len(idx))
-
-        max_gen = sum(genuine_capacity(idx) for idx in members.values())
-        max_imp = sum(impostor_capacity(idx) for idx in members.values())
+        gen_cap = {u: len(idx) * (len(idx) - 1) for u, idx in members.items()}                  # ordered pairs (i, j), i != j
+        imp_cap = {u: n_total * len(idx) - min(n_total, len(idx)) for u, idx in members.items()}
+        max_gen, max_imp = sum(gen_cap.values()), sum(imp_cap.values())
         if gen_number is None:
             gen_number = max_gen
-        else:
-            assert gen_number <= max_gen, f'{gen_number} greater than {max_gen}'
+        assert gen_number <= max_gen, f'{gen_number} greater than {max_gen}'
         imp_number = int(gen_number * gen_ratio)
         assert imp_number <= max_imp, f'{imp_number} greater than {max_imp}'
 
-        genuine = []
-        for u, idx in members.items():
-            if len(idx) < 2:
-                continue
-            cap = genuine_capacity(idx)
-            quota = min(round(cap / max_gen * gen_number), cap)
-            candidates = [(a, b) for a in idx for b in idx if a != b]
-            genuine.extend(candidates[k] for k in rng.choice(len(candidates), quota, replace=False))
+        def sample(candidates, quota):
+            picked = rng.choice(len(candidates), quota, replace=False)      # one draw per identity, in dataset order
+            return [candidates[k] for k in picked]
 
         listed = {i for idx in members.values() for i in idx}
-        impostor = []
-        for u, idx in members.items():
-            cap = impostor_capacity(idx)
-            quota = min(round(cap * imp_number / max_imp), cap)
-            others = listed - set(idx)
-            candidates = [(a, b) for a in idx for b in others]
-            impostor.extend(candidates[k] for k in rng.choice(len(candidates), quota, replace=False))
+        pairs = []
+        for u, idx in members.items():                                      # genuine pairs first (label 1) ...
+            if len(idx) > 1:
+                quota = min(round(gen_cap[u] / max_gen * gen_number), gen_cap[u])
+                pairs += [(a, b, 1) for a, b in sample(list(itertools.permutations(idx, 2)), quota)]
+        for u, idx in members.items():                                      # ... then the impostors (label 0)
+            quota = min(round(imp_cap[u] * imp_number / max_imp), imp_cap[u])
+            pairs += [(a, b, 0) for a, b in sample(list(itertools.product(idx, listed - set(idx))), quota)]
 
-        # dataset index -> rank among the listed images.  (As in the reference, the smallest listed index maps to 0 and every
-        # later one to its index minus the number of unlisted indices below it.)
-        correction = {i: 0 for i in listed}
-        skipped, previous = 0, None
-        for i in sorted(correction):
-            if previous is None:
-                skipped = i
-            else:
-                skipped += i - previous - 1
-                correction[i] = i - skipped
-            previous = i
-
-        pairs = [(a, b, 1) for a, b in genuine] + [(a, b, 0) for a, b in impostor]
+        self.pairs, self.correction = pairs, self._rank_among(listed)
         if path is not None:
             with open(path, 'wb') as f:
-                pickle.dump([pairs, correction], f)
-        self.pairs, self.correction = pairs, correction
+                pickle.dump([self.pairs, self.correction], f)
+
+    @staticmethod
+    def _rank_among(listed):
+        """dataset index -> position among the listed images.  As in the reference the smallest listed index maps to 0 and
+        every later one to its index minus the number of unlisted indices below it."""
+        ranks, skipped, previous = {}, 0, None
+        for i in sorted(listed):
+            skipped = i if previous is None else skipped + (i - previous - 1)
+            ranks[i] = 0 if previous is None else i - skipped
+            previous = i
+        return ranks
 
     @property
     def labels(self):

@@ -1,24 +1,6 @@
-"""Eval entry point - same call sequence as the reference's eval_fe_dog_head_sgd.py:15-25
-(get_config -> Controller -> load_state_dict(strict=False) -> configure_trainer -> trainer.test)."""
-import os
-import warnings
-from pathlib import Path
-
-import torch
-
-from engine import Controller
-from utils import configure_trainer, get_config
+"""Evaluate the dog-head feature extractor (pair metrics + Recall@K=10/100): drop-in for the reference's
+eval_fe_dog_head_sgd.py.  Paths come from FE_CONFIG / FE_CKPT / FE_LOG_DIR (see engine/evaluate.py)."""
+from engine.evaluate import run_fe_eval
 
 if __name__ == '__main__':
-    warnings.simplefilter('ignore')
-    lightning_logger = False
-    checkpoint_path = Path('results')
-    cfg_path = Path(os.environ.get('FE_CONFIG', 'configs/dog_fe/swin_t_dog_head_synth.py'))
-    config = get_config(cfg_path)
-    controller = Controller(config=config)
-    ckpt = os.environ.get('FE_CKPT')
-    if ckpt:
-        controller.load_state_dict(torch.load(Path(ckpt)), strict=False)
-    trainer = configure_trainer(config, lightning_logger, checkpoint_path)
-    trainer.test(controller)
-    print('Completed!')
+    run_fe_eval('configs/dog_fe/swin_t_dog_head_synth.py')

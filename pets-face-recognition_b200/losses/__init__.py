@@ -1,51 +1,55 @@
-"""Drop-in for the reference's losses/__init__.py: SoftmaxBasedMetricLearning = backbone -> margin head -> loss."""
+"""The metric-learning wrapper of the FE path: backbone -> large-margin head -> loss, with the reference's class name,
+constructor keywords and attributes (losses/__init__.py:8-46 there), so configs and `Controller.load_state_dict` keys
+(`model_loss.module.*`, `model_loss.add_margin.weight`) carry over.  Head and loss run as one fused native op."""
 import torch
-import torch.nn as nn
+from torch import nn
 
 from b200 import ops
 from b200.abi import B200Error
 
-from .large_margin import ArcMarginProduct, AddMarginProduct
+from .large_margin import AddMarginProduct, ArcMarginProduct
 from .losses import FocalLoss
 
 
 class SoftmaxBasedMetricLearning(nn.Module):
-    """Same constructor and attributes (.module, .add_margin, .focal_loss) as the reference
-    (losses/__init__.py:8-35); forward(img, label=None) returns the embeddings without a label and
-    {'loss', 'emb', 'logits'} with one (:37-46)."""
+    """`module` is the backbone, `add_margin` the ArcFace (arc_margin=True) or CosFace head, `focal_loss` the criterion
+    (FocalLoss when is_focal, else plain cross entropy).  forward(img) -> embeddings; forward(img, label) ->
+    {'loss', 'emb', 'logits'}; `img` may be a list of image batches (their embeddings are concatenated)."""
 
     def __init__(self, model: nn.Module, num_class, embedding_size=512, s=64.0, m=0.5, is_focal=False, loss_kwargs=None,
                  arc_margin=False, easy_margin=False):
         super().__init__()
-        if arc_margin:
-            self.add_margin = ArcMarginProduct(embedding_size, num_class, s=s, m=m, easy_margin=easy_margin)
-        else:
-            self.add_margin = AddMarginProduct(embedding_size, num_class, s=s, m=m)
-        loss_kwargs = loss_kwargs or {}
+        head_cls, head_kw = (ArcMarginProduct, {'easy_margin': easy_margin}) if arc_margin else (AddMarginProduct, {})
+        self.add_margin = head_cls(embedding_size, num_class, s=s, m=m, **head_kw)
+        options = dict(loss_kwargs or {})
         if is_focal:
-            self.focal_loss = FocalLoss(num_class=num_class, **loss_kwargs)
-            self._gamma = float(self.focal_loss.gamma)
+            self.focal_loss = FocalLoss(num_class=num_class, **options)
+            gamma = float(self.focal_loss.gamma)
+        elif options:
+            raise B200Error(f'CrossEntropyLoss options {sorted(options)} are not built on the fused path')
         else:
-            if loss_kwargs:
-                raise B200Error(f'CrossEntropyLoss options {sorted(loss_kwargs)} are not built on the fused path')
-            self.focal_loss = nn.CrossEntropyLoss()
-            self._gamma = 0.0
+            self.focal_loss, gamma = nn.CrossEntropyLoss(), 0.0
+        self._gamma = gamma
         self.module = model
         self.softmax = nn.Softmax(dim=1)
 
-    def forward(self, img, label=None, **__):
+    def _embed(self, img):
         if isinstance(img, (list, tuple)):
-            tensor = torch.cat([self.module(i) for i in img], dim=0)
-        else:
-            tensor = self.module(img)
+            return torch.cat([self.module(part) for part in img], dim=0)
+        return self.module(img)
+
+    def forward(self, img, label=None, **__):
+        emb = self._embed(img)
         if label is None:
-            return tensor
-        h = self.add_margin
-        loss, logits = ops.margin_head(tensor, h.weight, label, h.s, h.m, h.kind, h.easy_margin, self._gamma)
-        return {'loss': loss, 'emb': tensor, 'logits': logits}
+            return emb
+        head = self.add_margin
+        loss, logits = ops.margin_head(emb, head.weight, label, head.s, head.m, head.kind, head.easy_margin, self._gamma)
+        return {'loss': loss, 'emb': emb, 'logits': logits}
 
 
 class DummyWrapper(nn.Module):
+    """Pass-through wrapper with the `.module` attribute the configs expect."""
+
     def __init__(self, model, *_, **__):
         super().__init__()
         self.module = model

@@ -1,8 +1,15 @@
-"""Config loader and trainer factory - drop-in for the reference's utils/__init__.py:13-134 (same names, same config
-keys), without pytorch-lightning: get_strategy returns the string 'ddp' instead of a DDPPlugin object."""
-import inspect
+"""Config loading and trainer construction with the reference's names and config keys (utils/__init__.py:13-134 there),
+re-implemented without pytorch-lightning.
+
+A config is a Python module; `get_config(path)` executes it and exposes its public, non-module globals both as attributes
+and as mapping items (`cfg.n_epochs`, `cfg['n_epochs']`, `cfg.get('callbacks')`, iteration over the names).  `Config` is a
+process-wide singleton as in the reference (a second `get_config` replaces it); `get_dict_wrapper` gives an independent
+`DictWrapper` (the TSV scripts load two configs side by side).  `configure_trainer` maps `config.device` / `world_size`
+to the GPU list and passes the reference's keyword set to `engine.Trainer`; `get_strategy` answers with the string 'ddp'
+where the reference builds a DDPPlugin.
+"""
 import os
-from contextlib import suppress
+import types
 from importlib.util import module_from_spec, spec_from_file_location
 from typing import List, Optional, Union
 
@@ -12,116 +19,129 @@ from engine import Trainer
 
 
 class DictWrapper:
+    """Attribute + mapping view of a config namespace.  Unknown attributes fall through to the underlying dict, which is
+    what makes `cfg.get(...)`, `cfg.items()` and `cfg.keys()` work."""
+
     def __init__(self, d=None):
-        if d:
-            for k in d:
-                if not inspect.ismodule(d[k]):
-                    self.__setattr__(k, d[k])
+        for name, value in (d or {}).items():
+            if not isinstance(value, types.ModuleType):
+                setattr(self, name, value)
 
-    def __getitem__(self, index):
-        return self.__getattribute__(index)
+    # mapping protocol over the instance dict
+    def __getitem__(self, name):
+        return self.__dict__[name] if name in self.__dict__ else getattr(self, name)
 
-    def __setitem__(self, key, value):
-        return self.__setattr__(key, value)
+    def __setitem__(self, name, value):
+        setattr(self, name, value)
 
     def __iter__(self):
-        return iter(self.__dict__)
+        return iter(vars(self))
 
     def __len__(self):
-        return len(self.__dict__)
+        return len(vars(self))
+
+    def __getattr__(self, name):          # only reached when normal lookup fails
+        return getattr(vars(self), name)
 
     def __repr__(self):
-        return 'DictWrapper: ' + repr(self.__dict__)
-
-    def __getattr__(self, item):
-        return getattr(self.__dict__, item)      # .get / .items / .keys fall through to the dict
+        return f'{type(self).__name__}: {vars(self)!r}'
 
 
-class _SingletonBase(type):
-    _instances = {}
+class Config(DictWrapper):
+    """The one live configuration of the process: constructing it again without arguments hands back the same object."""
+    _live = None
 
-    def __call__(cls, *args, **kwargs):
-        if cls not in cls._instances:
-            cls._instances[cls] = super().__call__(*args, **kwargs)
-        return cls._instances[cls]
+    def __new__(cls, *args, **kwargs):
+        if cls._live is None:
+            cls._live = super().__new__(cls)
+            cls._live._filled = False
+        return cls._live
 
+    def __init__(self, d=None):
+        if not self.__dict__.get('_filled'):
+            super().__init__(d)
+            self.__dict__['_filled'] = True
 
-class Config(DictWrapper, metaclass=_SingletonBase):
+    def __iter__(self):
+        return (k for k in vars(self) if k != '_filled')
+
+    def __len__(self):
+        return len(vars(self)) - 1
+
     def __repr__(self):
-        return 'Config: ' + repr(self.__dict__)
+        return 'Config: ' + repr({k: self[k] for k in self})
+
+    @classmethod
+    def _forget(cls):
+        cls._live = None
 
 
-def _exec_config(path):
-    assert os.path.exists(path), path
+def _public_globals(path) -> dict:
+    if not os.path.exists(path):
+        raise AssertionError(path)
     spec = spec_from_file_location('config', path)
-    config = module_from_spec(spec)
-    spec.loader.exec_module(config)
-    return {k: getattr(config, k) for k in dir(config) if not k.startswith('_')}
+    module = module_from_spec(spec)
+    spec.loader.exec_module(module)
+    return {name: getattr(module, name) for name in dir(module) if not name.startswith('_')}
 
 
 def get_dict_wrapper(path) -> DictWrapper:
-    return DictWrapper(_exec_config(path))
+    return DictWrapper(_public_globals(path))
 
 
 def get_config(path) -> Config:
-    config = _exec_config(path)
-    if Config in _SingletonBase._instances:
-        del _SingletonBase._instances[Config]
-    return Config(config)
+    values = _public_globals(path)
+    Config._forget()
+    return Config(values)
 
 
 def get_gpus(world_size=1) -> Union[int, List[int]]:
-    assert world_size <= torch.cuda.device_count(), f'Only {torch.cuda.device_count()} are visible'
+    """The first `world_size` devices a tensor can actually be created on."""
+    visible = torch.cuda.device_count()
+    assert world_size <= visible, f'Only {visible} are visible'
     assert world_size >= 0
+    usable: List[int] = []
+    for index in range(visible if world_size else 0):
+        try:
+            torch.zeros(5, 5, device=f'cuda:{index}')
+        except RuntimeError:
+            continue
+        usable.append(index)
+        if len(usable) == world_size:
+            return usable
     if world_size == 0:
         return 0
-    gpus = []
-    for i in range(torch.cuda.device_count()):
-        with suppress(RuntimeError):
-            torch.zeros(5, 5, device=f'cuda:{i}')
-            gpus.append(i)
-        if len(gpus) >= world_size:
-            return gpus
     raise Exception(f'Cannot access {world_size} gpus')
 
 
 def parse_gpus(cfg) -> Union[int, List[int]]:
+    """config.device: 'cpu' -> 0, 'cuda' -> first usable GPU, 'cuda:N' -> [N] (0 / [0] if that index does not exist),
+    a list -> those GPUs (distributed_train, world_size must match); an int world_size -> that many GPUs."""
     if cfg.get('distributed_train'):
         if isinstance(cfg.device, list):
-            gpus = cfg.device
-            assert cfg.world_size == len(gpus), 'Not enough GPUs'
-        else:
-            gpus = cfg.world_size
-    elif cfg.device == 'cpu':
-        gpus = 0
-    elif cfg.device == 'cuda':
-        gpus = get_gpus()
-    else:
-        gpus = [int(cfg.device.split(':')[-1])]
-        gpus = list({i for i in gpus if i < torch.cuda.device_count()})
-        if len(gpus) == 0:
-            gpus = 0 if not torch.cuda.is_available() else [0]
-    return gpus
+            assert cfg.world_size == len(cfg.device), 'Not enough GPUs'
+            return cfg.device
+        return cfg.world_size
+    if cfg.device == 'cpu':
+        return 0
+    if cfg.device == 'cuda':
+        return get_gpus()
+    index = int(cfg.device.split(':')[-1])
+    if index < torch.cuda.device_count():
+        return [index]
+    return [0] if torch.cuda.is_available() else 0
 
 
 def is_main_process() -> bool:
-    return all(os.environ.get(i, 0) == 0 for i in ('NODE_RANK', 'LOCAL_RANK'))
+    return not any(name in os.environ and os.environ[name] != 0 for name in ('NODE_RANK', 'LOCAL_RANK'))
 
 
 def get_strategy(config) -> Optional[str]:
-    if config.get('distributed_train', False):
-        return 'ddp'
-    return None
+    return 'ddp' if config.get('distributed_train', False) else None
 
 
 def configure_trainer(config, lightning_logger, lightning_log_dir=None) -> Trainer:
-    return Trainer(
-        gpus=parse_gpus(config),
-        default_root_dir=lightning_log_dir,
-        strategy=get_strategy(config),
-        max_epochs=config.n_epochs,
-        logger=lightning_logger if lightning_logger is not None else False,
-        enable_checkpointing=True,
-        callbacks=config.get('callbacks'),
-        **config.get('trainer_kwargs', {})
-    )
+    kwargs = dict(config.get('trainer_kwargs', {}))
+    return Trainer(gpus=parse_gpus(config), default_root_dir=lightning_log_dir, strategy=get_strategy(config),
+                   max_epochs=config.n_epochs, logger=False if lightning_logger is None else lightning_logger,
+                   enable_checkpointing=True, callbacks=config.get('callbacks'), **kwargs)
