@@ -112,6 +112,29 @@ def time_oracle(batch, warmup, steps):
     return batch * steps / dt, dt / steps
 
 
+def time_oracle_gpu_eager(device, batch=64, steps=3):
+    """SURVEY.md 8(d) 'GPU-side bar': the same oracle port (plain PyTorch ops: cuBLAS / ATen kernels) on the B200 under
+    torch.autocast(bfloat16) - what the reference's own modules would do on this GPU.  Part of the baseline leg; never on
+    the product path."""
+    spec, sd, w, img, label = oracle_train_setup(batch)
+    sd = {k: v.detach().to(device).requires_grad_(v.requires_grad) for k, v in sd.items()}
+    w = w.detach().to(device).requires_grad_(True)
+    img, label = img.to(device), label.to(device)
+    bufs = [None] * (sum(1 for p in sd.values() if p.requires_grad) + 1)
+
+    def step(b):
+        with torch.autocast('cuda', dtype=torch.bfloat16):
+            return oracle_train_step(spec, sd, w, img, label, b)[1]
+    bufs = step(bufs)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        bufs = step(bufs)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return {'value': batch * steps / dt, 'unit': UNIT, 'sample': f'{steps} steps of batch {batch}, oracle/ port on the GPU (PyTorch eager, autocast bf16)'}
+
+
 def reference_arm(args, rank):
     if rank != 0:
         return
@@ -353,6 +376,10 @@ def gpu_arm(args, rank, world, local_rank):
                                           f'oracle/ port, fp32, {torch.get_num_threads()} threads'}
         if rows_f is not None:
             line['cpu_baseline'].update(rows_f_cpu())
+        try:
+            line['cpu_baseline']['gpu_eager'] = time_oracle_gpu_eager(torch.device('cuda', 0))
+        except Exception as e:          # a baseline, not the product: report why it is missing and go on
+            line['cpu_baseline']['gpu_eager'] = {'unavailable': f'{type(e).__name__}: {str(e)[:160]}'}
     emit(line)
 
 
