@@ -112,7 +112,7 @@ def time_oracle(batch, warmup, steps):
     return batch * steps / dt, dt / steps
 
 
-def time_oracle_gpu_eager(device, batch=64, steps=3):
+def time_oracle_gpu_eager(device, batch=256, steps=3):
     """SURVEY.md 8(d) 'GPU-side bar': the same oracle port (plain PyTorch ops: cuBLAS / ATen kernels) on the B200 under
     torch.autocast(bfloat16) - what the reference's own modules would do on this GPU.  Part of the baseline leg; never on
     the product path."""
