@@ -30,6 +30,20 @@ def test_config_loader_and_trainer_factory(tmp_path, monkeypatch):
     tr = configure_trainer(cfg, None, None)
     assert tr.max_epochs == 3 and tr.device.type == 'cpu' and tr.enable_checkpointing
     assert isinstance(DictWrapper({'a': 1}), DictWrapper)
+    # singleton as in the reference: Config() anywhere in the process is the configuration get_config loaded last
+    live = get_config(cfg_file)
+    assert Config() is live and Config().n_epochs == 3
+    assert set(live) >= {'n_epochs', 'device', 'k', 'model'} and '_filled' not in set(live) and len(live) == len(list(live))
+    assert {i: repr(live[i]) for i in live}['n_epochs'] == '3'                # Controller builds its hparams this way
+    from utils import get_dict_wrapper, is_main_process
+    side = get_dict_wrapper(cfg_file)                                         # independent of the singleton (TSV scripts)
+    side.n_epochs = 9
+    assert Config().n_epochs == 3 and side['n_epochs'] == 9 and side.get('nope', 1) == 1
+    for var in ('NODE_RANK', 'LOCAL_RANK'):
+        monkeypatch.delenv(var, raising=False)
+    assert is_main_process()
+    monkeypatch.setenv('LOCAL_RANK', '0')                                     # set at all (even to 0) = a DDP child process
+    assert not is_main_process()
 
 
 def test_shipped_configs_keep_the_reference_keys(monkeypatch):
