@@ -133,13 +133,20 @@ int b200_margin_logits(const void* emb_unit, const void* w_unit, int B, int C, i
 int b200_margin_ce(const float* logits, long long ldl, const long long* label, const float* cos_label, int B, int C, float s,
                    float m, int kind, int easy_margin, float gamma, float* loss_rows, float* loss_mean, void* G, long long ldg,
                    float* rdot, float* cdot, void* stream);
+/* stand-alone FocalLoss.forward(input, target) (losses/losses.py:22-28): loss_rows[b] = (1 - p_b)^gamma * nll_b, loss_mean = their
+ * mean; dlogits (optional, fp32 [B, ldd]) = d loss_mean / d logits.  A label outside [0, C) yields a NaN row (no device sync). */
+int b200_focal_loss(const float* logits, long long ldl, const long long* label, int B, int C, float gamma, float* loss_rows,
+                    float* loss_mean, float* dlogits, long long ldd, void* stream);
 int b200_unit_rows_bwd(const float* T, const float* x, const float* inv_norm, const float* dot, const float* scale_dev,
                        float* out_f32, void* out_bf16, long long R, int E, int accumulate, void* stream);
 
 /* ---- fused multi-tensor optimizer step: torch.optim.SGD(momentum) as built at
  *      configs/dog_fe/fe_dogs_config.py:123-133, torch.optim.AdamW of configs/dog_fe/body_dog_fe.py:123-131 -------- */
 int b200_opt_chunk_elems(void);
-int b200_optimizer_step(int kind, const void* tensors_dev, const void* chunks_dev, int n_chunks, float grad_scale, void* stream);
+/* step_offset: optimizer steps taken since the device table was written (added to every B200OptTensor.step), so the table
+ * is uploaded once and not once per step */
+int b200_optimizer_step(int kind, const void* tensors_dev, const void* chunks_dev, int n_chunks, float grad_scale, int step_offset,
+                        void* stream);
 
 /* ---- whole Swin backbone (models/swin.py:196-225): plan = shapes + buffer layout, no memory of its own --------- */
 void* b200_swin_create(int batch, int img, int channels, int hidden_dim, const int* layers, const int* heads,

@@ -70,9 +70,10 @@ _PROTOS = {
     'b200_margin_logits': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_float, c_float, c_int, c_int, c_vp, c_ll, c_vp, c_vp]),
     'b200_margin_ce': (c_int, [c_vp, c_ll, c_vp, c_vp, c_int, c_int, c_float, c_float, c_int, c_int, c_float, c_vp, c_vp, c_vp,
                                c_ll, c_vp, c_vp, c_vp]),
+    'b200_focal_loss': (c_int, [c_vp, c_ll, c_vp, c_int, c_int, c_float, c_vp, c_vp, c_vp, c_ll, c_vp]),
     'b200_unit_rows_bwd': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, c_int, c_int, c_vp]),
     'b200_opt_chunk_elems': (c_int, []),
-    'b200_optimizer_step': (c_int, [c_int, c_vp, c_vp, c_int, c_float, c_vp]),
+    'b200_optimizer_step': (c_int, [c_int, c_vp, c_vp, c_int, c_float, c_int, c_vp]),
     'b200_swin_create': (c_vp, [c_int, c_int, c_int, c_int, C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_int), c_int, c_int,
                                 c_int, c_int]),
     'b200_swin_destroy': (None, [c_vp]),

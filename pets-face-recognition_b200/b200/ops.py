@@ -244,3 +244,30 @@ class MarginHeadFunction(torch.autograd.Function):
 
 def margin_head(emb, weight, label, s=64.0, m=0.5, kind=0, easy_margin=False, gamma=0.0):
     return MarginHeadFunction.apply(emb, weight, label, float(s), float(m), int(kind), bool(easy_margin), float(gamma))
+
+
+class FocalLossFunction(torch.autograd.Function):
+    """Stand-alone focal / cross-entropy loss of given logits (csrc/arcface.cu: focal_rows_kernel): the criterion object of
+    the reference (losses/losses.py:22-28) called on its own, outside the fused head."""
+
+    @staticmethod
+    def forward(ctx, logits, target, gamma):
+        B, Cn = logits.shape
+        x = logits.contiguous().float()
+        t = target.contiguous().long()
+        rows = torch.empty(B, device=x.device, dtype=torch.float32)
+        loss = torch.empty(1, device=x.device, dtype=torch.float32)
+        d = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        check(lib().b200_focal_loss(ptr(x), x.stride(0), ptr(t), B, Cn, float(gamma), ptr(rows), ptr(loss), ptr(d), Cn, stream_ptr()),
+              'focal_loss')
+        ctx.save_for_backward(d)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, dloss):
+        (d,) = ctx.saved_tensors
+        return (d * dloss if d is not None else None), None, None
+
+
+def focal_loss(logits, target, gamma=0.0):
+    return FocalLossFunction.apply(logits, target, float(gamma))

@@ -33,6 +33,8 @@ class FusedStep:
         self._key = None
         self._tensors_dev = self._chunks_dev = None
         self._n_chunks = 0
+        self._since_build = 0
+        self._base_steps = []
         self._chunk = lib().b200_opt_chunk_elems()
 
     def _entries(self):
@@ -67,8 +69,19 @@ class FusedStep:
         if not ents:
             return
         dev = ents[0][0].device
-        key = tuple((e[0].data_ptr(), e[1].data_ptr(), e[2].data_ptr(), e[4], e[5], e[6], e[7], e[8], e[9]) for e in ents)
-        if key != self._key:
+        # The device table is rebuilt only when a pointer or a hyper-parameter changes.  The step counters are NOT part of the
+        # key: the kernel adds `offset` (steps since the table was written) to the stored ones, so AdamW's per-step counter
+        # and SGD's first-step flag do not force a rebuild + pageable H2D copy every step.
+        key = tuple((e[0].data_ptr(), e[1].data_ptr(), e[2].data_ptr(), e[4], e[5], e[6], e[7], e[8]) for e in ents)
+        offset = self._since_build
+        if key == self._key:
+            if self.kind == abi.OPT_ADAMW:
+                uniform = all(e[9] == b + offset for e, b in zip(ents, self._base_steps))
+            else:
+                uniform = all((e[9] == 0) == (b + offset == 0) for e, b in zip(ents, self._base_steps))
+        if key != self._key or not uniform:
+            offset = self._since_build = 0
+            self._base_steps = [e[9] for e in ents]
             arr = (abi.OptTensor * len(ents))()
             chunks = []
             for i, (p, g, s1, s2, lr, wd, b1, b2, eps, step) in enumerate(ents):
@@ -84,7 +97,9 @@ class FusedStep:
             self._n_chunks = len(chunks)
             self._key = key
         check(lib().b200_optimizer_step(self.kind, self._tensors_dev.data_ptr(), self._chunks_dev.data_ptr(), self._n_chunks,
-                                        float(grad_scale), stream_ptr()), 'optimizer_step')
+                                        float(grad_scale), int(offset), stream_ptr()), 'optimizer_step')
+        self._since_build += 1
+        self.opt._opt_called = True          # what optimizer.step() would set: lr_scheduler.step() checks it (order warning)
         if self.kind == abi.OPT_ADAMW:
             for g in self.opt.param_groups:
                 for p in g['params']:

@@ -65,7 +65,11 @@ __global__ void __launch_bounds__(256) margin_ce_kernel(const float* __restrict_
   for (int c = threadIdx.x; c < C; c += blockDim.x) se += __expf(lr[c] - mx);
   se = block_reduce(se, red, false);
   const float lse = mx + logf(se);
-  const float nll = lse - lr[lab];
+  // a label outside [0, C) (mis-numbered start_class / label_map in a config): the reference's scatter_ / CrossEntropyLoss
+  // raise; here the row's loss - and with it the batch mean the trainer reads back - becomes NaN instead of a silent
+  // out-of-bounds read (no device synchronisation on the hot path)
+  const bool bad_label = lab < 0 || lab >= C;
+  const float nll = bad_label ? __int_as_float(0x7fc00000) : lse - lr[lab];
   const float p = __expf(-nll);
   float lossv, f;
   if (gamma == 0.f) { lossv = nll; f = 1.f; }
@@ -77,7 +81,7 @@ __global__ void __launch_bounds__(256) margin_ce_kernel(const float* __restrict_
   if (threadIdx.x == 0) loss_rows[b] = lossv;
   if (G == nullptr) return;
   // d logits -> d cos
-  const float cl = cos_label[b];
+  const float cl = bad_label ? 0.f : cos_label[b];
   float dphi = 1.f;
   if (kind == 0) {
     const float sine = sqrtf(fmaxf(1.f - cl * cl, 0.f));
@@ -128,6 +132,39 @@ __global__ void __launch_bounds__(256) margin_coldot_kernel(const bf16* __restri
     for (int r = 1; r < 8; ++r) a += red[r][cx];
     cdot[c] = a;
   }
+}
+
+// Stand-alone FocalLoss.forward (losses/losses.py:22-28): per-row focal / cross-entropy loss of arbitrary logits and,
+// optionally, its gradient wrt the logits (d mean-loss / d logit).  One CTA per row.
+__global__ void __launch_bounds__(256) focal_rows_kernel(const float* __restrict__ logits, long long ldl, const long long* __restrict__ label,
+                                                         int B, int C, float gamma, float* __restrict__ loss_rows,
+                                                         float* __restrict__ dlogits, long long ldd) {
+  pdl_grid_sync();
+  __shared__ float red[8];
+  const int b = blockIdx.x;
+  const float* lr = logits + 1LL * b * ldl;
+  const int lab = static_cast<int>(label[b]);
+  float mx = -INFINITY;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) mx = fmaxf(mx, lr[c]);
+  mx = block_reduce(mx, red, true);
+  float se = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) se += __expf(lr[c] - mx);
+  se = block_reduce(se, red, false);
+  const float lse = mx + logf(se);
+  const bool bad_label = lab < 0 || lab >= C;
+  const float nll = bad_label ? __int_as_float(0x7fc00000) : lse - lr[lab];
+  const float p = __expf(-nll);
+  float lossv, f;
+  if (gamma == 0.f) { lossv = nll; f = 1.f; }
+  else {
+    const float omp = fmaxf(1.f - p, 0.f);
+    lossv = powf(omp, gamma) * nll;
+    f = powf(omp, gamma) + gamma * nll * p * powf(omp, gamma - 1.f);
+  }
+  if (threadIdx.x == 0) loss_rows[b] = lossv;
+  if (dlogits == nullptr) return;
+  const float k = f / B;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) dlogits[1LL * b * ldd + c] = k * (__expf(lr[c] - lse) - (c == lab ? 1.f : 0.f));
 }
 
 __global__ void mean_kernel(const float* __restrict__ x, int n, float* __restrict__ out) {
@@ -196,6 +233,20 @@ extern "C" int b200_margin_ce(const float* logits, long long ldl, const long lon
   }
   if (G != nullptr && cdot != nullptr) {
     launch_pdl(margin_coldot_kernel, dim3((C + 31) / 32), dim3(256), 0, st, reinterpret_cast<const bf16*>(G), ldg, logits, ldl, label, cos_label, B, C, s, cdot);
+    B200_LAUNCH_CHECK();
+  }
+  return B200_OK;
+}
+
+extern "C" int b200_focal_loss(const float* logits, long long ldl, const long long* label, int B, int C, float gamma,
+                               float* loss_rows, float* loss_mean, float* dlogits, long long ldd, void* stream) {
+  B200_REQUIRE(C > 0 && ldl >= C && (dlogits == nullptr || ldd >= C), "focal_loss: bad shape C=%d ldl=%lld ldd=%lld", C, ldl, ldd);
+  if (B == 0) return B200_OK;
+  auto st = reinterpret_cast<cudaStream_t>(stream);
+  launch_pdl(focal_rows_kernel, dim3(B), dim3(256), 0, st, logits, ldl, label, B, C, gamma, loss_rows, dlogits, ldd);
+  B200_LAUNCH_CHECK();
+  if (loss_mean) {
+    launch_pdl(mean_kernel, dim3(1), dim3(256), 0, st, loss_rows, B, loss_mean);
     B200_LAUNCH_CHECK();
   }
   return B200_OK;

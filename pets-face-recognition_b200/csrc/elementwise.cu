@@ -510,7 +510,7 @@ constexpr int kChunk = 4096;
 
 // torch.optim.SGD(momentum, dampening 0, no nesterov): g += wd * p; buf = first ? g : mom * buf + g; p -= lr * buf
 __global__ void __launch_bounds__(256) sgd_kernel(const B200OptTensor* __restrict__ tensors, const int2* __restrict__ chunks,
-                                                  float grad_scale) {
+                                                  float grad_scale, int step_offset) {
   pdl_grid_sync();
   const int2 ck = chunks[blockIdx.x];
   const B200OptTensor t = tensors[ck.x];
@@ -522,7 +522,7 @@ __global__ void __launch_bounds__(256) sgd_kernel(const B200OptTensor* __restric
   for (long long i = ck.y + threadIdx.x; i < end; i += blockDim.x) {
     float pv = p[i];
     float gv = g[i] * grad_scale + t.weight_decay * pv;
-    const float bv = t.step == 0 ? gv : t.beta1 * buf[i] + gv;
+    const float bv = (t.step + step_offset) == 0 ? gv : t.beta1 * buf[i] + gv;
     buf[i] = bv;
     pv -= t.lr * bv;
     p[i] = pv;
@@ -533,7 +533,7 @@ __global__ void __launch_bounds__(256) sgd_kernel(const B200OptTensor* __restric
 // torch.optim.AdamW: p *= 1 - lr*wd; m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
 // p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
 __global__ void __launch_bounds__(256) adamw_kernel(const B200OptTensor* __restrict__ tensors, const int2* __restrict__ chunks,
-                                                    float grad_scale) {
+                                                    float grad_scale, int step_offset) {
   pdl_grid_sync();
   const int2 ck = chunks[blockIdx.x];
   const B200OptTensor t = tensors[ck.x];
@@ -542,7 +542,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(const B200OptTensor* __restr
   float* m = reinterpret_cast<float*>(t.state1);
   float* v = reinterpret_cast<float*>(t.state2);
   bf16* p16 = reinterpret_cast<bf16*>(t.param_bf16);
-  const float stepf = static_cast<float>(t.step + 1);
+  const float stepf = static_cast<float>(t.step + step_offset + 1);
   const float bc1 = 1.0f - powf(t.beta1, stepf);
   const float bc2s = sqrtf(1.0f - powf(t.beta2, stepf));
   const long long end = min(t.numel, 1LL * ck.y + kChunk);
@@ -777,13 +777,13 @@ extern "C" int b200_colsum(const void* x, long long ld, long long M, int N, floa
 extern "C" int b200_opt_chunk_elems(void) { return kChunk; }
 
 extern "C" int b200_optimizer_step(int kind, const void* tensors_dev, const void* chunks_dev, int n_chunks, float grad_scale,
-                                   void* stream) {
+                                   int step_offset, void* stream) {
   if (n_chunks == 0) return B200_OK;
   auto st = reinterpret_cast<cudaStream_t>(stream);
   auto T = reinterpret_cast<const B200OptTensor*>(tensors_dev);
   auto Ck = reinterpret_cast<const int2*>(chunks_dev);
-  if (kind == B200_OPT_SGD) launch_pdl(sgd_kernel, dim3(n_chunks), dim3(256), 0, st, T, Ck, grad_scale);
-  else if (kind == B200_OPT_ADAMW) launch_pdl(adamw_kernel, dim3(n_chunks), dim3(256), 0, st, T, Ck, grad_scale);
+  if (kind == B200_OPT_SGD) launch_pdl(sgd_kernel, dim3(n_chunks), dim3(256), 0, st, T, Ck, grad_scale, step_offset);
+  else if (kind == B200_OPT_ADAMW) launch_pdl(adamw_kernel, dim3(n_chunks), dim3(256), 0, st, T, Ck, grad_scale, step_offset);
   else return b200_set_error(B200_ERR_INVALID, "optimizer_step: unknown kind %d", kind);
   B200_LAUNCH_CHECK();
   return B200_OK;

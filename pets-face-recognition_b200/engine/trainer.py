@@ -304,6 +304,32 @@ class Trainer:
         module.train(was_training)
         return outputs
 
+    def _shard_loader(self, loader, epoch: int):
+        """PL's replace_sampler_ddp: under DDP every rank must see its own shard of the training set.
+        A DataLoader without a distributed sampler is rebuilt around DistributedSampler(shuffle = the loader's own shuffle);
+        set_epoch(epoch) reseeds the shuffle every epoch.  Anything that is not a DataLoader is used as it is."""
+        if self.world_size == 1:
+            return loader
+        from torch.utils.data import DataLoader, RandomSampler
+        from torch.utils.data.distributed import DistributedSampler
+        if not isinstance(loader, DataLoader):
+            return loader
+        sampler = getattr(loader, 'sampler', None)
+        if isinstance(sampler, DistributedSampler):
+            sampler.set_epoch(epoch)
+            return loader
+        if loader.batch_sampler is not None and loader.batch_size is None:
+            raise RuntimeError("strategy='ddp': a train DataLoader with a custom batch_sampler must shard itself by rank")
+        dist_sampler = DistributedSampler(loader.dataset, num_replicas=self.world_size, rank=self.rank,
+                                          shuffle=isinstance(sampler, RandomSampler), drop_last=loader.drop_last)
+        dist_sampler.set_epoch(epoch)
+        kw = dict(batch_size=loader.batch_size, sampler=dist_sampler, num_workers=loader.num_workers, collate_fn=loader.collate_fn,
+                  pin_memory=loader.pin_memory, drop_last=loader.drop_last, timeout=loader.timeout,
+                  worker_init_fn=loader.worker_init_fn)
+        if loader.num_workers > 0:
+            kw.update(prefetch_factor=loader.prefetch_factor, persistent_workers=loader.persistent_workers)
+        return DataLoader(loader.dataset, **kw)
+
     def fit(self, module) -> None:
         module.to(self.device)
         module.logger = self.logger
@@ -313,7 +339,7 @@ class Trainer:
         for epoch in range(self.current_epoch, self.max_epochs):
             self.current_epoch = module.current_epoch = epoch
             t0, n_img, last = time.time(), 0, None
-            for b_idx, batch in enumerate(_Prefetcher(module.train_dataloader(), self.device, reuse=True)):
+            for b_idx, batch in enumerate(_Prefetcher(self._shard_loader(module.train_dataloader(), epoch), self.device, reuse=True)):
                 if self.limit_train_batches is not None and b_idx >= self.limit_train_batches:
                     break
                 last = self.run_training_batch(module, batch, optimizers)

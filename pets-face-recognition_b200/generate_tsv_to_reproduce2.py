@@ -43,7 +43,7 @@ def main():
     ap.add_argument('--preds', default=None, help='preds.tsv whose rows fill the queries that got no prediction')
     ap.add_argument('--strategy', default='mean', choices=['mean', 'max'])
     args = ap.parse_args()
-    db = synthetic_db(args.synthetic) if args.synthetic else torch.load(args.db)
+    db = synthetic_db(args.synthetic) if args.synthetic else torch.load(args.db, weights_only=False)   # trusted input: keys are pathlib.Path objects
     df = create_table(db, strategy=args.strategy)
     write_tsv(df, args.out)
     if args.preds:

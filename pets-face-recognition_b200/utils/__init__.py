@@ -133,7 +133,16 @@ def parse_gpus(cfg) -> Union[int, List[int]]:
 
 
 def is_main_process() -> bool:
-    return not any(name in os.environ and os.environ[name] != 0 for name in ('NODE_RANK', 'LOCAL_RANK'))
+    """Global rank 0.  The reference (utils/__init__.py:105-111) compares the env STRING with the int 0 and so answers False
+    whenever LOCAL_RANK is set; that only worked because Lightning spawned the workers after the check.  Here every rank is
+    launched torchrun-style with RANK / LOCAL_RANK already set, so main-ness is decided from the rank itself."""
+    for name in ('RANK', 'NODE_RANK', 'LOCAL_RANK'):
+        if name in os.environ:
+            try:
+                return int(os.environ[name]) == 0
+            except ValueError:
+                return False
+    return True
 
 
 def get_strategy(config) -> Optional[str]:

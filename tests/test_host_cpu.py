@@ -39,10 +39,12 @@ def test_config_loader_and_trainer_factory(tmp_path, monkeypatch):
     side = get_dict_wrapper(cfg_file)                                         # independent of the singleton (TSV scripts)
     side.n_epochs = 9
     assert Config().n_epochs == 3 and side['n_epochs'] == 9 and side.get('nope', 1) == 1
-    for var in ('NODE_RANK', 'LOCAL_RANK'):
+    for var in ('RANK', 'NODE_RANK', 'LOCAL_RANK'):
         monkeypatch.delenv(var, raising=False)
     assert is_main_process()
-    monkeypatch.setenv('LOCAL_RANK', '0')                                     # set at all (even to 0) = a DDP child process
+    monkeypatch.setenv('LOCAL_RANK', '0')                                     # torchrun rank 0 IS the main process (it writes the checkpoints)
+    assert is_main_process()
+    monkeypatch.setenv('RANK', '1')
     assert not is_main_process()
 
 
@@ -220,3 +222,39 @@ def test_sharded_gallery_plumbing_world2_gloo(tmp_path):
     got = torch.cat([outs[0]['idx'], outs[1]['idx']]).numpy()
     assert np.array_equal(got, ref_idx)
     np.testing.assert_allclose(torch.cat([outs[0]['score'], outs[1]['score']]).numpy(), ref_score, atol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def _shard_worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path[:0] = [str(ROOT), str(PKG)]
+    import torch.distributed as dist
+    from torch.utils.data import DataLoader, TensorDataset
+    from engine import Trainer
+    from utils import is_main_process
+    tr = Trainer(gpus=0, strategy='ddp')                       # CPU + gloo: the host-side DDP plumbing only
+    assert (tr.world_size, tr.rank) == (world, rank) and is_main_process() == (rank == 0)
+    ds = TensorDataset(torch.arange(22))
+    torch.manual_seed(123)                                     # what the shipped configs do on every rank alike
+    seen = {}
+    for shuffle in (True, False):
+        base = DataLoader(ds, batch_size=4, shuffle=shuffle, drop_last=True)
+        seen[shuffle] = [[int(v) for b in tr._shard_loader(base, epoch) for v in b[0]] for epoch in (0, 1)]
+    torch.save(seen, Path(tmp) / f'seen{rank}.pt')
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_ddp_train_loader_is_sharded_by_rank_world2_gloo(tmp_path):
+    """PL injected a DistributedSampler (replace_sampler_ddp); the Lightning-free Trainer has to do it itself,
+    or every rank trains on the same batches."""
+    import torch.multiprocessing as mp
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_shard_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a, b = (torch.load(tmp_path / f'seen{r}.pt', weights_only=False) for r in range(2))
+    for shuffle in (True, False):
+        for epoch in (0, 1):
+            ra, rb = a[shuffle][epoch], b[shuffle][epoch]
+            assert len(ra) == len(rb) == 8 and not set(ra) & set(rb)          # 11 per rank -> 2 full batches of 4, disjoint shards
+        assert (a[shuffle][0] != a[shuffle][1]) == shuffle                      # set_epoch reshuffles; sequential order is fixed
+    assert a[False][0] == [0, 2, 4, 6, 8, 10, 12, 14]

@@ -258,6 +258,37 @@ def test_margin_head_against_oracle_and_golden(golden_dir):
         assert rel_err(w2.grad.cpu(), wc.grad) < 3e-2
 
 
+@pytest.mark.parametrize('gamma', [0.0, 2.0])
+def test_standalone_focal_loss_and_bad_labels(gamma):
+    """losses.FocalLoss.forward(logits, target) on its own (losses/losses.py:22-28): value and gradient vs the oracle; a label
+    outside [0, C) must poison the loss (NaN), in the stand-alone kernel and in the fused head alike."""
+    from b200 import ops
+    from losses import FocalLoss
+    from oracle import head_oracle
+    B, Cn = 37, 1000
+    x = rnd(B, Cn, seed=1, dtype=torch.float32, scale=3.0).requires_grad_(True)
+    lab = torch.randint(0, Cn, (B,), generator=torch.Generator().manual_seed(3)).to(DEV)
+    crit = FocalLoss(num_class=Cn, gamma=gamma)
+    loss = crit(x, lab)
+    xc = x.detach().cpu().requires_grad_(True)
+    ref = head_oracle.focal_loss(xc, lab.cpu(), gamma)
+    assert abs(loss.item() - ref.item()) < 1e-4 * max(1.0, abs(ref.item()))
+    (2 * loss).backward()
+    (2 * ref).backward()
+    assert rel_err(x.grad.cpu(), xc.grad) < 1e-4
+    bad = lab.clone(); bad[5] = Cn
+    assert math.isnan(crit(x.detach(), bad).item())
+    e = rnd(B, 512, seed=4, dtype=torch.float32)
+    w = rnd(Cn, 512, seed=5, dtype=torch.float32, scale=0.05)
+    loss_bad, _ = ops.margin_head(e, w, bad, 64.0, 0.5, 0, False, gamma)
+    assert math.isnan(loss_bad.item())
+    bad[5] = -1
+    loss_bad, _ = ops.margin_head(e, w, bad, 64.0, 0.5, 0, False, gamma)
+    assert math.isnan(loss_bad.item())
+    loss_ok, _ = ops.margin_head(e, w, lab, 64.0, 0.5, 0, False, gamma)
+    assert math.isfinite(loss_ok.item())
+
+
 def test_cpu_tensors_are_rejected():
     from b200 import abi, ops
     with pytest.raises(abi.B200Error):
