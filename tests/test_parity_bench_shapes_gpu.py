@@ -1,0 +1,175 @@
+"""Parity at the BENCHMARK shapes: everything the B = 2 tests cannot reach - GEMM grids of more
+than one wave on 148 SMs, persistent multi-tile loops with TMEM double-buffer phase flips, aux-box prefetch across tile
+boundaries, 100+-way split-K over the tokens, the ones-MMA bias gradients - is compared with the oracle here.
+
+  * B = 32 and B = 64: one full train step against the CPU fp32 oracle (all 157 gradients; same thresholds as B = 2).
+  * B = 256, C = 10,000 (BASELINE.json configs[1] exactly): against the SAME oracle functions run in fp32 on the GPU as the
+    checker (TF32 off): loss, embeddings, every gradient tensor, and a 3-step SGD loss trajectory.
+  * gallery: 4,096 queries x 1,000,000 rows, top-100 indices bit-exact against a chunked fp64 evaluation of
+    oracle.rank_oracle's specification (score = fp64 cosine, order = score desc, index asc).
+The product path never imports the oracle; the oracle is the checker only.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(1800)]
+
+
+def rel(got, ref):
+    got, ref = got.detach().double().cpu(), ref.detach().double().cpu()
+    return ((got - ref).norm() / ref.norm().clamp_min(1e-30)).item()
+
+
+def _build(num_class, seed=123):
+    from b200 import abi, synth
+    abi.require_device()
+    from losses import SoftmaxBasedMetricLearning
+    from models import swin_t
+    from oracle.swin_oracle import SwinSpec, param_shapes
+    sd = synth.synth_state_dict(param_shapes(SwinSpec()), seed=seed)
+    model = swin_t(num_classes=512)
+    model.load_state_dict(sd, strict=True)
+    wrap = SoftmaxBasedMetricLearning(model, num_class=num_class, embedding_size=512, is_focal=True, arc_margin=True)
+    w_arc = synth.synth_tensor('add_margin.weight', (num_class, 512), seed=seed)
+    wrap.add_margin.weight.data.copy_(w_arc)
+    return sd, w_arc, wrap.cuda().train()
+
+
+def _oracle_step(sd, w_arc, img, label, device):
+    """fp32 oracle forward + autograd on `device` (CPU, or the GPU as checker with TF32 disabled)."""
+    from oracle import head_oracle
+    from oracle.swin_oracle import SwinSpec, swin_forward
+    osd = {k: v.clone().to(device).requires_grad_(not k.endswith('_mask')) for k, v in sd.items()}
+    w = w_arc.clone().to(device).requires_grad_(True)
+    o = head_oracle.metric_learning_forward(lambda x: swin_forward(osd, x, SwinSpec()), w, img.to(device), label.to(device),
+                                            clamp_sine=True)
+    o['loss'].backward()
+    return osd, w, o
+
+
+def _compare_grads(wrap, osd, w, pos_tol):
+    errs = {}
+    for name, p in wrap.named_parameters():
+        if name.endswith('_mask'):
+            continue
+        ref = w.grad if name == 'add_margin.weight' else osd[name[len('module.'):]].grad
+        assert p.grad is not None and torch.isfinite(p.grad).all(), name
+        errs[name] = rel(p.grad, ref)
+    med = float(np.median(list(errs.values())))
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:6]
+    worst_pos = max(v for k, v in errs.items() if k.endswith('pos_embedding'))
+    worst_other = max(v for k, v in errs.items() if not k.endswith('pos_embedding'))
+    print(f'{len(errs)} gradient tensors: median rel-L2 {med:.3e}, worst non-pos {worst_other:.3e}, worst pos {worst_pos:.3e}', worst)
+    assert len(errs) == 158                      # 157 backbone tensors + the ArcFace weight
+    assert med < 2e-2, med
+    assert worst_other < 5e-2, worst
+    assert worst_pos < pos_tol, worst
+    return errs
+
+
+@pytest.mark.parametrize('B', [32, 64])
+def test_train_step_vs_cpu_oracle_multi_wave(B):
+    """More than 148 tiles in every layer (B = 32: 784 row blocks at stage 1): loss, embeddings and ALL gradients vs the CPU
+    fp32 oracle, thresholds as in tests/test_swin_gpu.py (B = 2)."""
+    from b200 import synth
+    sd, w_arc, wrap = _build(1000)
+    img, label = synth.synth_images(B, seed=B), synth.synth_labels(B, 1000, seed=B)
+    wrap.zero_grad(set_to_none=True)
+    out = wrap(img.cuda(), label.cuda())
+    out['loss'].backward()
+    torch.cuda.synchronize()
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    osd, w, o = _oracle_step(sd, w_arc, img, label, 'cpu')
+    cos = torch.nn.functional.cosine_similarity(out['emb'].detach().cpu(), o['emb'].detach())
+    assert (1 - cos).max().item() < 1e-3, cos.min()
+    assert abs(out['loss'].item() - o['loss'].item()) < 1e-2 * abs(o['loss'].item())
+    _compare_grads(wrap, osd, w, pos_tol=0.2)
+
+
+def test_train_step_b256_vs_fp32_oracle_on_gpu_and_trajectory():
+    """BASELINE.json configs[1] exactly (B = 256, 10,000 classes): the oracle functions run in fp32 on the GPU as the checker."""
+    from b200 import synth
+    from b200.optim import FusedStep
+    from oracle import head_oracle
+    from oracle.swin_oracle import SwinSpec, swin_forward
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    B, C = 256, 10000
+    sd, w_arc, wrap = _build(C)
+    img, label = synth.synth_images(B, seed=256), synth.synth_labels(B, C, seed=256)
+    img_d, label_d = img.cuda(), label.cuda()
+    wrap.zero_grad(set_to_none=True)
+    out = wrap(img_d, label_d)
+    out['loss'].backward()
+    torch.cuda.synchronize()
+    osd, w, o = _oracle_step(sd, w_arc, img, label, 'cuda')
+    cos = torch.nn.functional.cosine_similarity(out['emb'].detach(), o['emb'].detach())
+    print('B=256: min cosine', cos.min().item(), 'loss', out['loss'].item(), 'oracle', o['loss'].item())
+    assert (1 - cos).max().item() < 1e-3
+    assert abs(out['loss'].item() - o['loss'].item()) < 1e-2 * abs(o['loss'].item())
+    # 256 images average the rel-pos table gradients over 128x more windows than the B = 2 test: the tolerance tightens
+    _compare_grads(wrap, osd, w, pos_tol=0.1)
+    del o
+
+    # 3-step loss trajectory: the config's optimizer (fe_dogs_config.py:123-133: SGD momentum 0.9, backbone lr 5e-3, ArcFace
+    # W lr 1e-2 wd 1e-4) through the fused step vs torch.optim.SGD on the oracle tensors
+    def groups(backbone, head):
+        return [{'lr': 5e-3, 'params': backbone}, {'lr': 1e-2, 'params': head, 'weight_decay': 1e-4}]
+    opt = torch.optim.SGD(groups([p for n, p in wrap.module.named_parameters() if p.requires_grad], list(wrap.add_margin.parameters())),
+                          0.01, momentum=0.9)
+    fused = FusedStep(opt)
+    oparams = [v for k, v in osd.items() if v.requires_grad]
+    oopt = torch.optim.SGD(groups(oparams, [w]), 0.01, momentum=0.9)
+    ours, theirs = [out['loss'].item()], []
+    fused.step()                                               # step 1 from the gradients computed above
+    theirs.append(float(head_oracle.focal_loss(head_oracle.arcface_logits(swin_forward(osd, img_d, SwinSpec()).detach(), w.detach(), label_d,
+                                                                             clamp_sine=True), label_d).item()))
+    oopt.step()
+    for step in range(2):
+        wrap.zero_grad(set_to_none=True)
+        l = wrap(img_d, label_d)['loss']
+        l.backward()
+        fused.step()
+        ours.append(l.item())
+        oopt.zero_grad(set_to_none=True)
+        lo = head_oracle.metric_learning_forward(lambda x: swin_forward(osd, x, SwinSpec()), w, img_d, label_d, clamp_sine=True)['loss']
+        lo.backward()
+        oopt.step()
+        theirs.append(lo.item())
+    print('loss trajectory (B200 path / fp32 oracle):', ours, theirs)
+    for a, b in zip(ours, theirs):
+        assert abs(a - b) < 1e-2 * abs(b), (ours, theirs)
+    assert ours[2] < ours[0]                                   # and it trains
+
+
+def _topk_spec_fp64_gpu(q, g, k, chunk=65536):
+    """oracle.rank_oracle.topk_spec evaluated on the GPU in fp64, gallery in chunks: score = <q, g> / (max(|q|, 1e-8) *
+    max(|g|, 1e-8)); ranked by (score desc, index asc) - a stable descending sort of index-ordered candidates."""
+    qd = q.double()
+    qn = qd.norm(dim=1).clamp_min(1e-8)
+    best_s = torch.full((q.shape[0], 0), 0.0, dtype=torch.float64, device=q.device)
+    best_i = torch.zeros((q.shape[0], 0), dtype=torch.int64, device=q.device)
+    for lo in range(0, g.shape[0], chunk):
+        gd = g[lo:lo + chunk].double()
+        s = (qd @ gd.t()) / (qn[:, None] * gd.norm(dim=1).clamp_min(1e-8)[None, :])
+        idx = torch.arange(lo, lo + gd.shape[0], device=q.device).expand(q.shape[0], -1)
+        s = torch.cat([best_s, s], dim=1)                      # earlier (lower) indices first: stability = index asc on ties
+        idx = torch.cat([best_i, idx], dim=1)
+        s, order = torch.sort(s, dim=1, descending=True, stable=True)
+        best_s, best_i = s[:, :k].contiguous(), torch.gather(idx, 1, order[:, :k]).contiguous()
+    return best_i, best_s
+
+
+def test_gallery_top100_bit_exact_at_one_million_rows():
+    from b200 import gallery, synth
+    nq, k = 4096, 100
+    emb, _ = synth.synth_embeddings(62500, 16, sigma=1.0, seed=41)            # 1,000,000 rows, 16 per identity
+    assert emb.shape[0] == 1_000_000
+    g = emb.cuda()
+    q = g[torch.randperm(g.shape[0], generator=torch.Generator().manual_seed(1))[:nq].cuda()] \
+        + 0.02 * torch.randn(nq, 512, generator=torch.Generator().manual_seed(2)).cuda()
+    idx, score = gallery.cosine_topk(q, g, k)
+    ref_i, ref_s = _topk_spec_fp64_gpu(q, g, k)
+    assert torch.equal(idx.long(), ref_i), f'{(idx.long() != ref_i).any(dim=1).sum().item()} of {nq} queries differ'
+    assert (score - ref_s).abs().max().item() < 1e-12

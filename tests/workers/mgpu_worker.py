@@ -1,0 +1,148 @@
+"""Worker of tests/test_multigpu_gpu.py - one process per GPU under torchrun (NCCL).  Real kernels on every rank:
+
+  1. data-parallel training step: averaged gradients / updated parameters of N ranks == one GPU over the whole batch;
+  2. Trainer.fit under strategy='ddp': rank-sharded loader, rank 0 writes the checkpoint;
+  3. gallery-sharded cosine top-k (BASELINE config 4 layout) == single-GPU pass, bit for bit;
+  4. leave-one-out Recall@K with row-sharded embeddings == single-GPU value.
+Rank 0 prints 'MGPU CHECK OK' when everything holds."""
+import os
+import sys
+import tempfile
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path[:0] = [str(ROOT), str(ROOT / 'pets-face-recognition_b200')]
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+
+def build(device, num_class=1000):
+    from b200 import synth
+    from losses import SoftmaxBasedMetricLearning
+    from models import swin_t
+    model = swin_t(num_classes=512)
+    sd = synth.synth_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, seed=123)
+    model.load_state_dict(sd)
+    wrap = SoftmaxBasedMetricLearning(model, num_class=num_class, embedding_size=512, is_focal=True, arc_margin=True)
+    wrap.add_margin.weight.data.copy_(synth.synth_tensor('add_margin.weight', (num_class, 512), seed=123))
+    return wrap.to(device)
+
+
+class Mod(torch.nn.Module):
+    """The slice of engine.Controller the Trainer drives (training_step / dataloaders / optimizers)."""
+
+    def __init__(self, wrap, dataset=None):
+        super().__init__()
+        self.model_loss = wrap
+        self.dataset = dataset
+
+    def training_step(self, batch, idx):
+        return self.model_loss(batch['x'], batch['label'])['loss']
+
+    def train_dataloader(self):
+        torch.manual_seed(123)                   # as the shipped configs: the same seed on every rank
+        return torch.utils.data.DataLoader(self.dataset, batch_size=4, shuffle=True, drop_last=True)
+
+    def val_dataloader(self):
+        return []
+
+    def validation_step(self, *a):
+        return None
+
+    def validation_epoch_end(self, outputs):
+        pass
+
+    def configure_optimizers(self):
+        return [torch.optim.SGD([p for p in self.parameters() if p.requires_grad], 5e-3, momentum=0.9)], []
+
+
+class Items(torch.utils.data.Dataset):
+    def __init__(self, n):
+        from b200 import synth
+        self.x, self.y = synth.synth_images(n, seed=9), synth.synth_labels(n, 1000, seed=9)
+
+    def __len__(self):
+        return self.x.shape[0]
+
+    def __getitem__(self, i):
+        return {'x': self.x[i], 'label': self.y[i], 'index': i}
+
+
+def main():
+    rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
+    torch.cuda.set_device(local)
+    dist.init_process_group('nccl')
+    from b200 import gallery, synth
+    from engine.trainer import Trainer
+    dev = torch.device('cuda', local)
+
+    # ---- 1. DDP step == single GPU
+    per = 16
+    img = synth.synth_images(per * world, seed=5).to(dev)
+    lab = synth.synth_labels(per * world, 1000, seed=5).to(dev)
+    mod = Mod(build(dev))
+    opt = torch.optim.SGD([p for p in mod.parameters() if p.requires_grad], 5e-3, momentum=0.9)
+    tr = Trainer(gpus=[local], strategy='ddp', max_epochs=1)
+    tr._allreduce_hooks(mod)
+    sl = slice(rank * per, (rank + 1) * per)
+    tr.run_training_batch(mod, {'x': img[sl], 'label': lab[sl]}, [opt])
+    torch.cuda.synchronize()
+    after = torch.cat([p.detach().flatten() for p in mod.parameters() if p.requires_grad])
+    grads = torch.cat([p.grad.flatten() / world for p in mod.parameters() if p.grad is not None])
+    ref_after = after.clone()
+    dist.broadcast(ref_after, 0)
+    flags = torch.tensor([int(torch.equal(ref_after, after))], device=dev)
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        single = Mod(build(dev))
+        opt1 = torch.optim.SGD([p for p in single.parameters() if p.requires_grad], 5e-3, momentum=0.9)
+        Trainer(gpus=[local], max_epochs=1).run_training_batch(single, {'x': img, 'label': lab}, [opt1])
+        g1 = torch.cat([p.grad.flatten() for p in single.parameters() if p.grad is not None])
+        a1 = torch.cat([p.detach().flatten() for p in single.parameters() if p.requires_grad])
+        rel_g = ((grads - g1).norm() / g1.norm()).item()
+        rel_p = ((after - a1).norm() / a1.norm()).item()
+        print(f'world {world}: ranks identical {bool(flags.item())}; grad rel-L2 vs 1 GPU {rel_g:.3e}; params rel-L2 {rel_p:.3e}')
+        assert flags.item() == 1 and rel_g < 1e-3 and rel_p < 1e-6, (rel_g, rel_p)
+        del single
+
+    # ---- 2. fit(): sharded loader + rank-0 checkpoint
+    root = Path(os.environ.get('MGPU_TMP', tempfile.gettempdir())) / 'mgpu_ckpt'
+    fit_mod = Mod(build(dev), Items(8 * world))
+    tr2 = Trainer(gpus=[local], strategy='ddp', max_epochs=1, default_root_dir=str(root), enable_checkpointing=True,
+                  log_every_n_steps=0)
+    seen = [int(i) for b in tr2._shard_loader(fit_mod.train_dataloader(), 0) for i in b['index']]
+    all_seen = [None] * world
+    dist.all_gather_object(all_seen, seen)
+    flat = [i for s in all_seen for i in s]
+    assert len(flat) == len(set(flat)) == 8 * world, all_seen            # disjoint shards covering the set
+    tr2.fit(fit_mod)
+    dist.barrier()
+    if rank == 0:
+        assert list(root.glob('epoch=0-step=*.ckpt')) and (root / 'trainer_state.pt').exists(), list(root.iterdir())
+
+    # ---- 3. gallery-sharded top-k == single pass; 4. sharded leave-one-out Recall@K == single value
+    emb, classes = synth.synth_embeddings(4000, 5, sigma=1.0, seed=31)      # 20,000 rows
+    emb, classes = emb.to(dev), classes.to(dev)
+    q, _ = synth.synth_embeddings(700, 3, sigma=1.0, seed=32)               # 2,100 queries
+    q = q.to(dev)
+    gb = [emb.shape[0] * r // world for r in range(world + 1)]
+    gb[1] += 37 if world > 1 else 0                                          # ragged shards
+    qb = [q.shape[0] * r // world for r in range(world + 1)]
+    idx, score = gallery.cosine_topk_gallery_sharded(q[qb[rank]:qb[rank + 1]], emb[gb[rank]:gb[rank + 1]], 100)
+    ref_idx, ref_score = gallery.cosine_topk(q, emb, 100)
+    assert torch.equal(idx, ref_idx[qb[rank]:qb[rank + 1]]) and torch.equal(score, ref_score[qb[rank]:qb[rank + 1]])
+    r_sh = gallery.recall_at_k_sharded(emb[gb[rank]:gb[rank + 1]], classes[gb[rank]:gb[rank + 1]], (10, 100))
+    r_one = gallery.recall_at_k(emb, classes, (10, 100))
+    assert r_sh == r_one, (r_sh, r_one)
+    ok = torch.ones(1, device=dev)
+    dist.all_reduce(ok)
+    if rank == 0:
+        print(f'sharded gallery == single pass on {world} ranks; Recall@K {r_sh}')
+        print('MGPU CHECK OK')
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()
