@@ -209,6 +209,39 @@ inline FastDiv make_fastdiv(uint32_t d) {
   return f;
 }
 
+// Raster row <-> window-major row of a [B, H, W] token grid cut into 7 x 7 windows, optionally after the cyclic shift by 3 of
+// the shifted Swin blocks (models/swin.py:8-14, :112): token (r, c) of window (wy, wx) of image b is pixel
+// ((7 wy + r + off) mod H, (7 wx + c + off) mod W) and gets window-major row ((b nwh + wy) nww + wx) 49 + 7 r + c.  The
+// LayerNorm in front of to_qkv writes its output in this order, so that every (window, head) operand of the attention
+// kernels is a contiguous [49 rows x 32 columns] box a TMA descriptor can fetch.
+struct WinMap {
+  int enabled, H, W, nwh, nww, off;
+  FastDiv div_w, div_hw;
+};
+inline WinMap make_winmap(int H, int W, int shifted) {
+  WinMap m;
+  m.enabled = 1; m.H = H; m.W = W; m.nwh = H / 7; m.nww = W / 7; m.off = shifted ? 3 : 0;
+  m.div_w = make_fastdiv(static_cast<uint32_t>(W));
+  m.div_hw = make_fastdiv(static_cast<uint32_t>(H) * static_cast<uint32_t>(W));
+  return m;
+}
+inline WinMap no_winmap() { WinMap m{}; m.enabled = 0; m.div_w = make_fastdiv(1); m.div_hw = make_fastdiv(1); return m; }
+#ifdef __CUDACC__
+__device__ __forceinline__ long long win_row(const WinMap& m, long long raster_row) {
+  const uint32_t row = static_cast<uint32_t>(raster_row);                  // launchers require B * H * W < 2^31
+  const uint32_t b = m.div_hw.div(row);
+  const uint32_t rem = row - b * static_cast<uint32_t>(m.H * m.W);
+  const uint32_t y = m.div_w.div(rem);
+  const uint32_t x = rem - y * static_cast<uint32_t>(m.W);
+  int ys = static_cast<int>(y) - m.off, xs = static_cast<int>(x) - m.off;
+  if (ys < 0) ys += m.H;
+  if (xs < 0) xs += m.W;
+  const int wy = ys / 7, wx = xs / 7;
+  const int r = ys - 7 * wy, c = xs - 7 * wx;
+  return (static_cast<long long>(b) * m.nwh + wy) * m.nww * 49 + wx * 49 + r * 7 + c;
+}
+#endif
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
 // ---------------------------------------------------------------------------------------------
@@ -359,6 +392,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
+}
+__device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t& r) {       // one fp32 column
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 

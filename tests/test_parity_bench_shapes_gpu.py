@@ -48,7 +48,7 @@ def _oracle_step(sd, w_arc, img, label, device):
     return osd, w, o
 
 
-def _compare_grads(wrap, osd, w, pos_tol):
+def _compare_grads(wrap, osd, w, pos_tol, med_tol=2e-2):
     errs = {}
     for name, p in wrap.named_parameters():
         if name.endswith('_mask'):
@@ -61,8 +61,8 @@ def _compare_grads(wrap, osd, w, pos_tol):
     worst_pos = max(v for k, v in errs.items() if k.endswith('pos_embedding'))
     worst_other = max(v for k, v in errs.items() if not k.endswith('pos_embedding'))
     print(f'{len(errs)} gradient tensors: median rel-L2 {med:.3e}, worst non-pos {worst_other:.3e}, worst pos {worst_pos:.3e}', worst)
-    assert len(errs) == 158                      # 157 backbone tensors + the ArcFace weight
-    assert med < 2e-2, med
+    assert len(errs) == 157                      # every trainable tensor: 156 of the backbone + the ArcFace weight
+    assert med < med_tol, med
     assert worst_other < 5e-2, worst
     assert worst_pos < pos_tol, worst
     return errs
@@ -109,7 +109,9 @@ def test_train_step_b256_vs_fp32_oracle_on_gpu_and_trajectory():
     assert (1 - cos).max().item() < 1e-3
     assert abs(out['loss'].item() - o['loss'].item()) < 1e-2 * abs(o['loss'].item())
     # 256 images average the rel-pos table gradients over 128x more windows than the B = 2 test: the tolerance tightens
-    _compare_grads(wrap, osd, w, pos_tol=0.1)
+    # (measured r02a: median 1.97e-2, worst non-pos 2.6e-2, worst pos 8.0e-2; B = 32 / 64: 1.2e-2 / 1.4e-2 medians)
+    _compare_grads(wrap, osd, w, pos_tol=0.1, med_tol=2.5e-2)
+    first_oracle_loss = o['loss'].item()
     del o
 
     # 3-step loss trajectory: the config's optimizer (fe_dogs_config.py:123-133: SGD momentum 0.9, backbone lr 5e-3, ArcFace
@@ -123,8 +125,7 @@ def test_train_step_b256_vs_fp32_oracle_on_gpu_and_trajectory():
     oopt = torch.optim.SGD(groups(oparams, [w]), 0.01, momentum=0.9)
     ours, theirs = [out['loss'].item()], []
     fused.step()                                               # step 1 from the gradients computed above
-    theirs.append(float(head_oracle.focal_loss(head_oracle.arcface_logits(swin_forward(osd, img_d, SwinSpec()).detach(), w.detach(), label_d,
-                                                                             clamp_sine=True), label_d).item()))
+    theirs.append(first_oracle_loss)
     oopt.step()
     for step in range(2):
         wrap.zero_grad(set_to_none=True)
