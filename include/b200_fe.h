@@ -95,6 +95,18 @@ int b200_layernorm_bwd(const void* dy, const void* x, const float* gamma, const 
                        const void* dres_in, void* dx_out, float* dgamma, float* dbeta, float* dres_colsum, float* partial,
                        long long M, int C, int accumulate, void* stream);
 
+/* Window-major variants for the LayerNorm in front of to_qkv (models/swin.py:160 PreNorm -> WindowAttention :101-135): the
+ * token grid [B, H, W] is cut into 7 x 7 windows (after the cyclic shift by 3 when shifted != 0, models/swin.py:8-14) and
+ * window-major row = ((b * H/7 + wy) * W/7 + wx) * 49 + 7 r + c.  fwd writes y in that order; bwd reads dy in that order. */
+int b200_layernorm_fwd_windows(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int B, int H,
+                               int W, int C, int shifted, float eps, void* stream);
+int b200_layernorm_bwd_windows(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                               const void* dres_in, void* dx_out, float* dgamma, float* dbeta, float* dres_colsum, float* partial,
+                               int B, int H, int W, int C, int shifted, int accumulate, void* stream);
+/* rows of `row_bytes` bytes (a multiple of 4) permuted between raster and window-major order: to_window != 0 writes
+ * out[window_major(r)] = in[r], else out[r] = in[window_major(r)] */
+int b200_window_rows(const void* in, void* out, int B, int H, int W, int row_bytes, int shifted, int to_window, void* stream);
+
 /* ---- patch merging gather == nn.Unfold(k=s=df) + NHWC view (models/swin.py:159,162-165) ---------------------- */
 int b200_patch_gather_image(const float* img_nchw, void* cols, int B, int Cin, int H, int W, int df, long long ldo, void* stream);
 int b200_patch_gather_image_u8(const unsigned char* img_nchw, void* cols, int B, int Cin, int H, int W, int df, long long ldo,
@@ -112,14 +124,16 @@ int b200_colsum_blocks(long long M);
 int b200_colsum(const void* x, long long ld, long long M, int N, float* out, float* partial, int accumulate, void* stream);
 
 /* ---- (shifted-)window attention (models/swin.py:101-135, CyclicShift :8-14, create_mask :49-62,
- *      get_relative_distances :65-68).  qkv: [B*H*W, 3C] bf16 = output of to_qkv; out: [B*H*W, C] bf16 = input of
- *      to_out; the cyclic shift and window partition are folded into the addressing. ------------------------------ */
+ *      get_relative_distances :65-68) on tcgen05 tensor cores, q / k / v tiles fetched by TMA.
+ *      qkv: [B*H*W, 3C] bf16 = output of to_qkv with its rows in WINDOW-MAJOR order (b200_layernorm_fwd_windows /
+ *      b200_window_rows); the cyclic shift and the window partition are that row order.  out: [B*H*W, C] bf16 = input of
+ *      to_out, RASTER order.  lse: [B*H*W, heads] fp32 row log-sum-exp, window-major (nullable in inference). ------------- */
 int b200_window_attn_fwd(const void* qkv, const float* pos_embedding, void* out, float* lse, int B, int H, int W, int C,
                          int heads, int shifted, void* stream);
 int b200_window_attn_bwd_blocks(int B, int H, int W, int heads);
 long long b200_window_attn_bwd_scratch_floats(int blocks); /* size (floats) of the `dpos_partial` scratch buffer */
 /* backward from (qkv, lse, dout) alone: P is recomputed from the saved row log-sum-exp and rowsum(P o dP) stands in for
- * rowsum(dout o out), so the forward output is not an input */
+ * rowsum(dout o out), so the forward output is not an input.  dout: raster order; dqkv: window-major like qkv */
 int b200_window_attn_bwd(const void* qkv, const float* pos_embedding, const float* lse, const void* dout,
                          void* dqkv, float* dpos, float* dpos_partial, int accumulate_dpos, int B, int H, int W, int C,
                          int heads, int shifted, void* stream);

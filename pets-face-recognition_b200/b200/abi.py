@@ -52,6 +52,9 @@ _PROTOS = {
     'b200_layernorm_fwd': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, c_int, c_float, c_vp]),
     'b200_layernorm_bwd_blocks': (c_int, [c_ll, c_int]),
     'b200_layernorm_bwd': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, c_int, c_int, c_vp]),
+    'b200_layernorm_fwd_windows': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_float, c_vp]),
+    'b200_layernorm_bwd_windows': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    'b200_window_rows': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
     'b200_patch_gather_image': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_ll, c_vp]),
     'b200_patch_gather_image_u8': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_ll, c_vp]),
     'b200_patch_gather_nhwc': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),

@@ -92,6 +92,29 @@ def layernorm_fwd(x, gamma, beta, eps=1e-5):
     return y, mean, rstd
 
 
+def layernorm_fwd_windows(x, gamma, beta, B, H, W, shifted, eps=1e-5):
+    """LayerNorm whose output rows leave in window-major order (mean / rstd stay per raster row)."""
+    M, Cc = x.shape
+    y = torch.empty_like(x)
+    mean = torch.empty(M, device=x.device, dtype=torch.float32)
+    rstd = torch.empty_like(mean)
+    check(lib().b200_layernorm_fwd_windows(ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(mean), ptr(rstd), B, H, W, Cc, int(shifted), eps,
+                                           stream_ptr()), 'layernorm_fwd_windows')
+    return y, mean, rstd
+
+
+def layernorm_bwd_windows(dy, x, gamma, mean, rstd, B, H, W, shifted, dres=None):
+    """LayerNorm backward whose dy rows arrive in window-major order."""
+    M, Cc = x.shape
+    dx = torch.empty_like(x)
+    dgb = torch.empty(3, Cc, device=x.device, dtype=torch.float32)
+    blocks = lib().b200_layernorm_bwd_blocks(M, Cc)
+    partial = torch.empty(blocks, 3 * Cc, device=x.device, dtype=torch.float32)
+    check(lib().b200_layernorm_bwd_windows(ptr(dy), ptr(x), ptr(gamma), ptr(mean), ptr(rstd), ptr(dres), ptr(dx), ptr(dgb[0]), ptr(dgb[1]),
+                                           0, ptr(partial), B, H, W, Cc, int(shifted), 0, stream_ptr()), 'layernorm_bwd_windows')
+    return dx, dgb[0], dgb[1]
+
+
 def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None, want_dres_colsum=False):
     M, Cc = x.shape
     dx = torch.empty_like(x)
@@ -158,20 +181,39 @@ def colsum(x):
     return out
 
 
-def window_attn_fwd(qkv, pos, B, H, W, Cc, heads, shifted, want_lse=True):
+def window_rows(x, B, H, W, shifted, to_window=True):
+    """Rows of a [B*H*W, n] tensor permuted raster -> window-major order (to_window) or back: the row order the attention
+    kernels take their q / k / v in (include/b200_fe.h: b200_window_rows)."""
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    check(lib().b200_window_rows(ptr(x), ptr(out), B, H, W, x.shape[1] * x.element_size(), int(shifted), int(to_window), stream_ptr()),
+          'window_rows')
+    return out
+
+
+def window_attn_fwd(qkv, pos, B, H, W, Cc, heads, shifted, want_lse=True, window_major=False):
+    """qkv [B*H*W, 3C] in raster order (window_major=False: permuted here) or already window-major.  Returns the attention output
+    in raster order and the row log-sum-exp in WINDOW-MAJOR order (what window_attn_bwd takes back)."""
+    if not window_major:
+        qkv = window_rows(qkv, B, H, W, shifted, True)
     out = torch.empty(B * H * W, Cc, device=qkv.device, dtype=bf16)
     lse = torch.empty(B * H * W, heads, device=qkv.device, dtype=torch.float32) if want_lse else None
     check(lib().b200_window_attn_fwd(ptr(qkv), ptr(pos), ptr(out), ptr(lse), B, H, W, Cc, heads, int(shifted), stream_ptr()), 'window_attn_fwd')
     return out, lse
 
 
-def window_attn_bwd(qkv, pos, lse, dout, B, H, W, Cc, heads, shifted):
+def window_attn_bwd(qkv, pos, lse, dout, B, H, W, Cc, heads, shifted, window_major=False):
+    """qkv / the returned dqkv in raster order (window_major=False) or window-major; lse as returned by window_attn_fwd."""
+    if not window_major:
+        qkv = window_rows(qkv, B, H, W, shifted, True)
     dqkv = torch.empty_like(qkv)
     dpos = torch.empty(169, device=qkv.device, dtype=torch.float32)
     blocks = lib().b200_window_attn_bwd_blocks(B, H, W, heads)
     partial = torch.empty(lib().b200_window_attn_bwd_scratch_floats(blocks), device=qkv.device, dtype=torch.float32)
     check(lib().b200_window_attn_bwd(ptr(qkv), ptr(pos), ptr(lse), ptr(dout), ptr(dqkv), ptr(dpos), ptr(partial), 0,
                                      B, H, W, Cc, heads, int(shifted), stream_ptr()), 'window_attn_bwd')
+    if not window_major:
+        dqkv = window_rows(dqkv, B, H, W, shifted, False)
     return dqkv, dpos.view(13, 13)
 
 

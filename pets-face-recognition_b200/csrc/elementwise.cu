@@ -52,7 +52,7 @@ template <int LPR, int MAXIT, int U>
 __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, bf16* __restrict__ y,
                                                             float* __restrict__ mean, float* __restrict__ rstd,
-                                                            long long M, int C, float eps, int rev) {
+                                                            long long M, int C, float eps, int rev, const WinMap wm) {
   pdl_grid_sync();
   // rev: walk the rows from the last to the first.  The producer of x (a GEMM, tiles in ascending row order) has just
   // left its last ~100 MB in L2 and the consumer of y (the next GEMM) starts at row 0: running this kernel backwards turns
@@ -100,6 +100,8 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restri
       }
       const float rs = rsqrtf(group_sum<LPR>(q) / C + eps);
       if (live) {
+        // wm: the normalised rows leave in window-major order (the attention kernels' operand layout, see WinMap)
+        const long long orow = wm.enabled ? win_row(wm, phys(row)) : phys(row);
 #pragma unroll
         for (int it = 0; it < MAXIT; ++it) {
           const int ch = l + it * LPR;
@@ -109,7 +111,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const bf16* __restri
             ld8f(beta + ch * 8, b);
 #pragma unroll
             for (int i = 0; i < 8; ++i) o[i] = (v[it][i] - mu) * rs * g[i] + b[i];
-            st8(y + phys(row) * C + ch * 8, o);
+            st8(y + orow * C + ch * 8, o);
           }
         }
         if (l == 0) {
@@ -135,7 +137,7 @@ __global__ void __launch_bounds__(kLnBwdThreads, ln_bwd_ctas_per_sm(MAXIT)) laye
                                                             const float* __restrict__ gamma, const float* __restrict__ mean,
                                                             const float* __restrict__ rstd, const bf16* dres,
                                                             bf16* dx, float* __restrict__ partial,
-                                                            long long M, int C, int rev) {
+                                                            long long M, int C, int rev, const WinMap wm) {
   pdl_grid_sync();
   constexpr int RPW = 32 / LPR;
   extern __shared__ float red[];   // [warps][3][C]
@@ -162,11 +164,12 @@ __global__ void __launch_bounds__(kLnBwdThreads, ln_bwd_ctas_per_sm(MAXIT)) laye
     const long long prow = phys(row);
     mu_r[slot] = live ? mean[prow] : 0.f;
     rs_r[slot] = live ? rstd[prow] : 0.f;
+    const long long drow = (live && wm.enabled) ? win_row(wm, prow) : prow;      // wm: dy arrives in window-major order
 #pragma unroll
     for (int it = 0; it < MAXIT; ++it) {
       const int ch = l + it * LPR;
       if (live && ch < chunks) {
-        rd[slot][it] = ld_nc_v4(dy + prow * C + ch * 8);
+        rd[slot][it] = ld_nc_v4(dy + drow * C + ch * 8);
         rx[slot][it] = ld_nc_v4(x + prow * C + ch * 8);
         if (dres) rr[slot][it] = ld_nc_v4(dres + prow * C + ch * 8);
       }
@@ -580,26 +583,26 @@ int grid_for(long long work_items, int threads, int max_blocks) {
 
 template <int LPR, int MAXIT, int U = (MAXIT == 1 ? 4 : (MAXIT <= 3 ? 2 : 1))>
 int ln_fwd_launch(const bf16* x, const float* g, const float* b, bf16* y, float* mean, float* rstd, long long M, int C, float eps,
-                  cudaStream_t st) {
+                  cudaStream_t st, const WinMap& wm) {
   const int rpw = (32 / LPR) * U;
   const long long warps = (M + rpw - 1) / rpw;
   const int blocks = grid_for(warps * 32, 256, b200_num_sms() * 8);
-  launch_pdl(layernorm_fwd_kernel<LPR, MAXIT, U>, dim3(blocks), dim3(256), 0, st, x, g, b, y, mean, rstd, M, C, eps, b200_reverse_rows());
+  launch_pdl(layernorm_fwd_kernel<LPR, MAXIT, U>, dim3(blocks), dim3(256), 0, st, x, g, b, y, mean, rstd, M, C, eps, b200_reverse_rows(), wm);
   B200_LAUNCH_CHECK();
   return B200_OK;
 }
 template <int LPR, int MAXIT>
 int ln_bwd_launch(const bf16* dy, const bf16* x, const float* g, const float* mean, const float* rstd, const bf16* dres, bf16* dx,
-                  float* partial, long long M, int C, int blocks, bool with_res, cudaStream_t st) {
+                  float* partial, long long M, int C, int blocks, bool with_res, cudaStream_t st, const WinMap& wm) {
   const size_t smem = sizeof(float) * (kLnBwdThreads / 32) * 3 * C;
   if (with_res) {
     if (smem > 48 * 1024)
       B200_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<LPR, MAXIT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    launch_pdl(layernorm_bwd_kernel<LPR, MAXIT, true>, dim3(blocks), dim3(kLnBwdThreads), smem, st, dy, x, g, mean, rstd, dres, dx, partial, M, C, b200_reverse_rows());
+    launch_pdl(layernorm_bwd_kernel<LPR, MAXIT, true>, dim3(blocks), dim3(kLnBwdThreads), smem, st, dy, x, g, mean, rstd, dres, dx, partial, M, C, b200_reverse_rows(), wm);
   } else {
     if (smem > 48 * 1024)
       B200_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<LPR, MAXIT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    launch_pdl(layernorm_bwd_kernel<LPR, MAXIT, false>, dim3(blocks), dim3(kLnBwdThreads), smem, st, dy, x, g, mean, rstd, dres, dx, partial, M, C, b200_reverse_rows());
+    launch_pdl(layernorm_bwd_kernel<LPR, MAXIT, false>, dim3(blocks), dim3(kLnBwdThreads), smem, st, dy, x, g, mean, rstd, dres, dx, partial, M, C, b200_reverse_rows(), wm);
   }
   B200_LAUNCH_CHECK();
   return B200_OK;
@@ -610,8 +613,8 @@ int ln_bwd_launch(const bf16* dy, const bf16* x, const float* g, const float* me
 // ---------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------
-extern "C" int b200_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
-                                  long long M, int C, float eps, void* stream) {
+static int layernorm_fwd_impl(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                              long long M, int C, float eps, const WinMap& wm, void* stream) {
   B200_REQUIRE(C % 8 == 0 && C >= 8 && C <= 1536, "layernorm: C=%d unsupported (multiple of 8, <= 1536)", C);
   if (M == 0) return B200_OK;
   auto st = reinterpret_cast<cudaStream_t>(stream);
@@ -619,14 +622,33 @@ extern "C" int b200_layernorm_fwd(const void* x, const float* gamma, const float
   auto Y = reinterpret_cast<bf16*>(y);
   // widths of the form 24 * 2^k (Swin: 96 / 192 / 384 / 768): C / 24 lanes per row hold exactly three 16-B chunks each -
   // no idle lanes, short shuffle trees, and 12 loads in flight per lane
-  if (C == 96) return ln_fwd_launch<4, 3, 4>(X, gamma, beta, Y, mean, rstd, M, C, eps, st);
-  if (C == 192) return ln_fwd_launch<8, 3, 4>(X, gamma, beta, Y, mean, rstd, M, C, eps, st);
-  if (C == 384) return ln_fwd_launch<16, 3, 4>(X, gamma, beta, Y, mean, rstd, M, C, eps, st);
-  if (C <= 128) return ln_fwd_launch<16, 1>(X, gamma, beta, Y, mean, rstd, M, C, eps, st);
-  if (C <= 256) return ln_fwd_launch<32, 1>(X, gamma, beta, Y, mean, rstd, M, C, eps, st);
-  if (C <= 512) return ln_fwd_launch<32, 2>(X, gamma, beta, Y, mean, rstd, M, C, eps, st);
-  if (C <= 768) return ln_fwd_launch<32, 3>(X, gamma, beta, Y, mean, rstd, M, C, eps, st);
-  return ln_fwd_launch<32, 6>(X, gamma, beta, Y, mean, rstd, M, C, eps, st);
+  if (C == 96) return ln_fwd_launch<4, 3, 4>(X, gamma, beta, Y, mean, rstd, M, C, eps, st, wm);
+  if (C == 192) return ln_fwd_launch<8, 3, 4>(X, gamma, beta, Y, mean, rstd, M, C, eps, st, wm);
+  if (C == 384) return ln_fwd_launch<16, 3, 4>(X, gamma, beta, Y, mean, rstd, M, C, eps, st, wm);
+  if (C <= 128) return ln_fwd_launch<16, 1>(X, gamma, beta, Y, mean, rstd, M, C, eps, st, wm);
+  if (C <= 256) return ln_fwd_launch<32, 1>(X, gamma, beta, Y, mean, rstd, M, C, eps, st, wm);
+  if (C <= 512) return ln_fwd_launch<32, 2>(X, gamma, beta, Y, mean, rstd, M, C, eps, st, wm);
+  if (C <= 768) return ln_fwd_launch<32, 3>(X, gamma, beta, Y, mean, rstd, M, C, eps, st, wm);
+  return ln_fwd_launch<32, 6>(X, gamma, beta, Y, mean, rstd, M, C, eps, st, wm);
+}
+
+extern "C" int b200_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                                  long long M, int C, float eps, void* stream) {
+  return layernorm_fwd_impl(x, gamma, beta, y, mean, rstd, M, C, eps, no_winmap(), stream);
+}
+
+static int check_window_grid(int B, int H, int W) {
+  B200_REQUIRE(B >= 0 && H > 0 && W > 0 && H % 7 == 0 && W % 7 == 0 && 1LL * B * H * W < (1LL << 31),
+               "window order: H=%d W=%d must be multiples of 7 and B*H*W < 2^31", H, W);
+  return B200_OK;
+}
+
+// y rows are written in WINDOW-MAJOR order (x, mean, rstd stay in raster order)
+extern "C" int b200_layernorm_fwd_windows(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                                          int B, int H, int W, int C, int shifted, float eps, void* stream) {
+  int rc = check_window_grid(B, H, W);
+  if (rc) return rc;
+  return layernorm_fwd_impl(x, gamma, beta, y, mean, rstd, 1LL * B * H * W, C, eps, make_winmap(H, W, shifted), stream);
 }
 
 // 128-thread CTAs; each CTA ends with a cross-warp reduction and one [3C] partial row, so CTAs are kept fat (>= 64
@@ -641,9 +663,9 @@ extern "C" int b200_layernorm_bwd_blocks(long long M, int C) {
 
 // partial: fp32 scratch of b200_layernorm_bwd_blocks(M, C) x 3C.  dres_colsum (optional, needs dres_in) receives the column
 // sums of dres_in: the bias gradient of the Linear whose output was added to the residual stream.
-extern "C" int b200_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
-                                  const void* dres_in, void* dx_out, float* dgamma, float* dbeta, float* dres_colsum, float* partial,
-                                  long long M, int C, int accumulate, void* stream) {
+static int layernorm_bwd_impl(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                              const void* dres_in, void* dx_out, float* dgamma, float* dbeta, float* dres_colsum, float* partial,
+                              long long M, int C, int accumulate, const WinMap& wm, void* stream) {
   B200_REQUIRE(C % 8 == 0 && C >= 8 && C <= 1536, "layernorm_bwd: C=%d unsupported", C);
   B200_REQUIRE(dres_colsum == nullptr || dres_in != nullptr, "layernorm_bwd: dres_colsum needs dres_in");
   if (M == 0) return B200_OK;
@@ -655,14 +677,60 @@ extern "C" int b200_layernorm_bwd(const void* dy, const void* x, const float* ga
   auto DX = reinterpret_cast<bf16*>(dx_out);
   const bool wr = dres_colsum != nullptr;
   int rc;
-  if (C <= 128) rc = ln_bwd_launch<16, 1>(DY, X, gamma, mean, rstd, DR, DX, partial, M, C, blocks, wr, st);
-  else if (C <= 256) rc = ln_bwd_launch<32, 1>(DY, X, gamma, mean, rstd, DR, DX, partial, M, C, blocks, wr, st);
-  else if (C <= 512) rc = ln_bwd_launch<32, 2>(DY, X, gamma, mean, rstd, DR, DX, partial, M, C, blocks, wr, st);
-  else if (C <= 768) rc = ln_bwd_launch<32, 3>(DY, X, gamma, mean, rstd, DR, DX, partial, M, C, blocks, wr, st);
-  else rc = ln_bwd_launch<32, 6>(DY, X, gamma, mean, rstd, DR, DX, partial, M, C, blocks, wr, st);
+  if (C <= 128) rc = ln_bwd_launch<16, 1>(DY, X, gamma, mean, rstd, DR, DX, partial, M, C, blocks, wr, st, wm);
+  else if (C <= 256) rc = ln_bwd_launch<32, 1>(DY, X, gamma, mean, rstd, DR, DX, partial, M, C, blocks, wr, st, wm);
+  else if (C <= 512) rc = ln_bwd_launch<32, 2>(DY, X, gamma, mean, rstd, DR, DX, partial, M, C, blocks, wr, st, wm);
+  else if (C <= 768) rc = ln_bwd_launch<32, 3>(DY, X, gamma, mean, rstd, DR, DX, partial, M, C, blocks, wr, st, wm);
+  else rc = ln_bwd_launch<32, 6>(DY, X, gamma, mean, rstd, DR, DX, partial, M, C, blocks, wr, st, wm);
   if (rc) return rc;
   float* outs[3] = {dgamma, dbeta, dres_colsum};
   return splitk_reduce_multi(partial, outs, wr ? 3 : 2, C, blocks, accumulate, st, 3LL * C);
+}
+
+// partial: fp32 scratch of b200_layernorm_bwd_blocks(M, C) x 3C.  dres_colsum (optional, needs dres_in) receives the column
+// sums of dres_in: the bias gradient of the Linear whose output was added to the residual stream.
+extern "C" int b200_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                                  const void* dres_in, void* dx_out, float* dgamma, float* dbeta, float* dres_colsum, float* partial,
+                                  long long M, int C, int accumulate, void* stream) {
+  return layernorm_bwd_impl(dy, x, gamma, mean, rstd, dres_in, dx_out, dgamma, dbeta, dres_colsum, partial, M, C, accumulate, no_winmap(), stream);
+}
+
+// dy rows are READ in window-major order (everything else in raster order): the backward of b200_layernorm_fwd_windows
+extern "C" int b200_layernorm_bwd_windows(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                                          const void* dres_in, void* dx_out, float* dgamma, float* dbeta, float* dres_colsum,
+                                          float* partial, int B, int H, int W, int C, int shifted, int accumulate, void* stream) {
+  int rc = check_window_grid(B, H, W);
+  if (rc) return rc;
+  return layernorm_bwd_impl(dy, x, gamma, mean, rstd, dres_in, dx_out, dgamma, dbeta, dres_colsum, partial, 1LL * B * H * W, C, accumulate,
+                            make_winmap(H, W, shifted), stream);
+}
+
+// out rows = in rows permuted between raster and window-major order (row = n_words 32-bit words): to_window != 0 writes
+// out[window_major(r)] = in[r], otherwise out[r] = in[window_major(r)].  A layout helper for callers that hold raster-order
+// tensors (tests, stand-alone use of the attention entry points); the Swin plan never needs it.
+__global__ void __launch_bounds__(256) window_rows_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, long long M, int n_words,
+                                                          int to_window, const WinMap wm) {
+  pdl_grid_sync();
+  const long long total = M * n_words;
+  for (long long idx = 1LL * blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += 1LL * gridDim.x * blockDim.x) {
+    const long long row = idx / n_words;
+    const int wd = static_cast<int>(idx - row * n_words);
+    const long long w = win_row(wm, row);
+    if (to_window) out[w * n_words + wd] = in[idx];
+    else out[idx] = in[w * n_words + wd];
+  }
+}
+
+extern "C" int b200_window_rows(const void* in, void* out, int B, int H, int W, int row_bytes, int shifted, int to_window, void* stream) {
+  int rc = check_window_grid(B, H, W);
+  if (rc) return rc;
+  B200_REQUIRE(row_bytes > 0 && row_bytes % 4 == 0, "window_rows: row_bytes must be a positive multiple of 4");
+  const long long M = 1LL * B * H * W;
+  if (M == 0) return B200_OK;
+  launch_pdl(window_rows_kernel, dim3(grid_for(M * (row_bytes / 4), 256, b200_num_sms() * 16)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
+             reinterpret_cast<const uint32_t*>(in), reinterpret_cast<uint32_t*>(out), M, row_bytes / 4, to_window, make_winmap(H, W, shifted));
+  B200_LAUNCH_CHECK();
+  return B200_OK;
 }
 
 extern "C" int b200_patch_gather_image(const float* img, void* out, int B, int Cin, int H, int W, int df, long long ldo,

@@ -246,7 +246,15 @@ int bias_grad(const Ctx& c, const bf16* dy, long long M, int N, float* db) {
   return b200_colsum(dy, N, M, N, db, partial, 0, c.stv);
 }
 
-// LayerNorm backward with its partial rows in the arena
+// LayerNorm backward with its partial rows in the arena.  win_shift >= 0: dy is in window-major order (LN1 of a block whose
+// shift flag is win_shift)
+int ln_bwd_win(const Ctx& c, const bf16* dy, const bf16* x, const float* gamma, const float* mean, const float* rstd, const bf16* dres,
+               bf16* dx, float* dgamma, float* dbeta, float* dres_colsum, int B, int Hs, int C, int shifted) {
+  int rc = 0;
+  float* partial = c.take(1LL * b200_layernorm_bwd_blocks(1LL * B * Hs * Hs, C) * 3 * C * 4, &rc);
+  RC(rc);
+  return b200_layernorm_bwd_windows(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, dres_colsum, partial, B, Hs, Hs, C, shifted, 0, c.stv);
+}
 int ln_bwd(const Ctx& c, const bf16* dy, const bf16* x, const float* gamma, const float* mean, const float* rstd, const bf16* dres,
            bf16* dx, float* dgamma, float* dbeta, float* dres_colsum, long long M, int C) {
   int rc = 0;
@@ -274,7 +282,10 @@ int forward(const Ctx& c, const void* img, int img_u8, float* emb) {
       const BlockParams& q = S.bp_[b];
       const BlockActs& a = S.ba_[b];
       bf16* xn1 = c.W<bf16>(a.xn1);
-      RC(b200_layernorm_fwd(x, c.P(q.ln1_w), c.P(q.ln1_b), xn1, c.W<float>(a.mean1), c.W<float>(a.rstd1), S.M, C, 1e-5f, c.stv));
+      // LN1 writes its rows in window-major order of this block's (shifted) partition: xn1, qkv, lse, dqkv and d xn1 all live
+      // in that order (the GEMMs between them are row-wise); the attention output comes back in raster order
+      RC(b200_layernorm_fwd_windows(x, c.P(q.ln1_w), c.P(q.ln1_b), xn1, c.W<float>(a.mean1), c.W<float>(a.rstd1), p.B, S.Hs, S.Hs, C, b & 1,
+                                    1e-5f, c.stv));
       bf16* qkv = c.W<bf16>(a.qkv);
       RC(linear_fwd(c, xn1, S.M, C, c.wc + q.wqkv16, 3 * C, nullptr, B200_EPI_STORE, qkv, nullptr, nullptr));
       bf16* attn = c.W<bf16>(a.attn);
@@ -356,7 +367,8 @@ int backward(const Ctx& c, const float* demb, int stage_hi, int stage_lo) {
       RC(linear_dgrad(c, dbig, M, 3 * C, c.wc + q.wqkv16t, C, B200_EPI_STORE, dsmall, nullptr));      // d xn1
       RC(linear_wgrad(c, dbig, M, 3 * C, c.W<bf16>(a.xn1), C, c.G(q.wqkv)));
       // g <- d x_in; d bo = colsum(g before the update): g is dL/d(to_out output)
-      RC(ln_bwd(c, dsmall, x_in, c.P(q.ln1_w), c.W<float>(a.mean1), c.W<float>(a.rstd1), g, g, c.G(q.ln1_w), c.G(q.ln1_b), c.G(q.bo), M, C));
+      RC(ln_bwd_win(c, dsmall, x_in, c.P(q.ln1_w), c.W<float>(a.mean1), c.W<float>(a.rstd1), g, g, c.G(q.ln1_w), c.G(q.ln1_b), c.G(q.bo),
+                    p.B, S.Hs, C, b & 1));
       RC(c.flush(true));                                     // the block's eight reductions: one launch
     }
     // ---- patch merging linear (models/swin.py:162-167)

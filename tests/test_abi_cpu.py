@@ -52,6 +52,23 @@ def test_sass_is_blackwell_native(built_lib):
         pytest.skip('cuobjdump unavailable')
     for mnemonic in ('UTCHMMA', 'LDTM', 'UTMALDG'):
         assert mnemonic in out.stdout, mnemonic
+    # no legacy tensor path anywhere in the library (mma.sync / wmma -> HMMA; UTCHMMA is the tcgen05 one), and the
+    # window-attention kernels themselves are tcgen05 + TMA (north_star kernel mandate)
+    import re
+    assert not re.search(r'(?<!UTC)HMMA', out.stdout)
+    sect = {}
+    name = None
+    for line in out.stdout.splitlines():
+        m = re.search(r'Function : (\S+)', line)
+        if m:
+            name = m.group(1)
+            sect[name] = []
+        elif name is not None:
+            sect[name].append(line)
+    attn = {k: '\n'.join(v) for k, v in sect.items() if 'window_attn' in k}
+    assert len(attn) == 2, list(attn)
+    for k, text in attn.items():
+        assert 'UTCHMMA' in text and 'LDTM' in text and 'UTMALDG' in text, k
 
 
 def test_no_cpu_fallback(built_lib):

@@ -163,6 +163,32 @@ def test_layernorm(C, M):
     assert rel_err(dcol, dres.float().sum(0)) < 1e-4          # fused bias gradient of the residual branch's Linear
 
 
+@pytest.mark.parametrize('B,H,W,C,shifted', [(2, 14, 14, 96, 0), (3, 14, 21, 192, 1), (1, 7, 7, 768, 1), (5, 28, 28, 96, 1)])
+def test_window_major_rows_and_layernorm_variants(B, H, W, C, shifted):
+    """b200_window_rows == the reference's roll(-3) + window rearrange (models/swin.py:8-14, :112); the window-major LayerNorm
+    forward / backward equal the raster kernels composed with that permutation, bit for bit."""
+    from b200 import ops
+    M = B * H * W
+    x = rnd(M, C, seed=1, scale=2.0)
+    wm = ops.window_rows(x, B, H, W, shifted, True)
+    ref = x.view(B, H, W, C)
+    if shifted:
+        ref = torch.roll(ref, shifts=(-3, -3), dims=(1, 2))
+    ref = ref.view(B, H // 7, 7, W // 7, 7, C).permute(0, 1, 3, 2, 4, 5).reshape(M, C)       # b (nw_h nw_w) (w_h w_w)
+    assert torch.equal(wm, ref)
+    assert torch.equal(ops.window_rows(wm, B, H, W, shifted, False), x)
+    g = 1 + 0.1 * rnd(C, seed=2, dtype=torch.float32)
+    b = 0.1 * rnd(C, seed=3, dtype=torch.float32)
+    y, mean, rstd = ops.layernorm_fwd(x, g, b)
+    yw, mean_w, rstd_w = ops.layernorm_fwd_windows(x, g, b, B, H, W, shifted)
+    assert torch.equal(yw, ops.window_rows(y, B, H, W, shifted, True)) and torch.equal(mean, mean_w) and torch.equal(rstd, rstd_w)
+    dy = rnd(M, C, seed=4)
+    dres = rnd(M, C, seed=5)
+    dx, dgam, dbet = ops.layernorm_bwd(dy, x, g, mean, rstd, dres=dres)
+    dxw, dgam_w, dbet_w = ops.layernorm_bwd_windows(ops.window_rows(dy, B, H, W, shifted, True), x, g, mean, rstd, B, H, W, shifted, dres=dres)
+    assert torch.equal(dx, dxw) and torch.equal(dgam, dgam_w) and torch.equal(dbet, dbet_w)
+
+
 def test_patch_gather_matches_unfold():
     from b200 import ops
     from oracle.swin_oracle import patch_merge
@@ -202,11 +228,14 @@ def test_mean_pool_transpose_colsum_cast():
     assert rel_err(ops.colsum(m), m.float().sum(0)) < 1e-5
 
 
-@pytest.mark.parametrize('heads,H,W,shifted', [(3, 14, 14, 0), (3, 14, 14, 1), (6, 7, 7, 1), (2, 21, 14, 1), (24, 7, 7, 0), (1, 28, 28, 1)])
-def test_window_attention_fwd_bwd(heads, H, W, shifted):
+@pytest.mark.parametrize('heads,H,W,shifted,B', [(3, 14, 14, 0, 2), (3, 14, 14, 1, 2), (6, 7, 7, 1, 2), (2, 21, 14, 1, 2), (24, 7, 7, 0, 2),
+                                                  (1, 28, 28, 1, 2), (3, 7, 7, 1, 1), (4, 14, 7, 1, 3), (3, 56, 56, 1, 4), (6, 28, 28, 0, 7)])
+def test_window_attention_fwd_bwd(heads, H, W, shifted, B):
+    """tcgen05 window attention vs the oracle: odd / even head counts (a lone head in the last head pair), odd window counts
+    (a lone window in the last window pair), more work units than SMs (persistent loops, barrier phase flips)."""
     from b200 import ops
     from oracle.swin_oracle import attention_core
-    B, C = 2, heads * 32
+    C = heads * 32
     qkv = rnd(B * H * W, 3 * C, seed=1)
     pos = rnd(13, 13, seed=2, dtype=torch.float32)
     out, lse = ops.window_attn_fwd(qkv, pos, B, H, W, C, heads, shifted)
