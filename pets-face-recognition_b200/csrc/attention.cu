@@ -20,10 +20,13 @@
 //             dQ = dS K             (A = dS K-major,  B = K MN-major)        dK = dS^T Q,  dV = P^T dO
 //             (A = the dS / P tile read MN-major: its two 64-row halves are exactly the two M chunks of an M = 128 operand)
 //
-// Warp roles: warp 0 = TMA producer, warp 1 = the single MMA-issuing thread, (backward: warps 2-3 gather the dO rows, which
-// arrive in raster order, with cp.async), then two groups of four warps (one warp per TMEM lane quarter).  The heads of the
-// stream of work units are dealt alternately to the two groups, each with its own TMEM accumulators and P / dS tiles, so one
-// group's softmax overlaps the other's MMAs and global stores.
+// Warp roles (20 warps, one CTA per SM), a pipeline over the stream of (window pair, head) tasks:
+//   TMA producer | issuer of the score MMAs | issuer of the second-stage MMAs (two threads, so neither waits behind the
+//   other's barrier) | backward: two warps that gather the dO rows (raster order) with cp.async |
+//   12 softmax warps - three per TMEM lane quarter, each thread owning one token row and 16 / 16 / 17 of its 49 key columns;
+//   the parts of the row maximum / rowsum(P o dP) meet through smem - | 4 epilogue warps (TMEM -> bf16 -> global).
+// Task n uses buffer n & 1 of everything that is double-buffered (P / dS tiles; forward: S and O accumulators), so the
+// tensor core works on task n + 1 while the softmax warps are on task n and the epilogue warps on task n - 1.
 //
 // The forward output and the backward's dO are in RASTER order (they meet the residual stream through to_out); dqkv and the
 // row log-sum-exp are window-major like qkv.
@@ -140,89 +143,191 @@ __device__ __forceinline__ void row_unit(RowCtx& rc, const AttnArgs& a, int pair
   rc.mask = m;
 }
 
-// 16 consecutive accumulator columns -> scores in the log2 domain (scale * acc + bias), masked
-template <int J0, int N>
-__device__ __forceinline__ void scores_chunk(const uint32_t* r, const float* bias_row, float sc2, float sub, unsigned long long mask,
-                                             float* s) {
+// Three softmax warps share a TMEM lane quarter (the same 32 token rows); warp part T owns key columns [16 T, 16 T + 16)
+// (+ column 48 for T = 2) of every row: 16 / 16 / 17 of the 49 keys
+constexpr int kParts = 3;
+constexpr int kPC = 17;                            // columns a thread holds at most
+template <int T> struct Part { static constexpr int J0 = 16 * T; static constexpr int NC = T == 2 ? 17 : 16; };
+
+// this thread's key columns [J0, J0 + NC) of its row: `taddr` = the row's first column
+template <int T>
+__device__ __forceinline__ void load_cols(uint32_t taddr, uint32_t (&v)[kPC]) {
+  tmem_ld16(taddr + Part<T>::J0, reinterpret_cast<uint32_t(&)[16]>(v[0]));
+  if (T == 2) tmem_ld1(taddr + 48, v[16]);
+}
+
+// accumulator columns -> scores in the log2 domain (scale * acc + bias - sub), shift-masked
+template <int T>
+__device__ __forceinline__ void scores(const uint32_t (&v)[kPC], const float* bias_row, float sc2, float sub, unsigned long long mask,
+                                       float (&s)[kPC]) {
+  constexpr int J0 = Part<T>::J0, NC = Part<T>::NC;
 #pragma unroll
-  for (int j4 = 0; j4 < (N + 3) / 4; ++j4) {
+  for (int j4 = 0; j4 < (NC + 3) / 4; ++j4) {
     const float4 b = *reinterpret_cast<const float4*>(bias_row + J0 + 4 * j4);
     const float bb[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e)
-      if (4 * j4 + e < N) s[4 * j4 + e] = fmaf(__uint_as_float(r[4 * j4 + e]), sc2, bb[e] - sub);
+      if (4 * j4 + e < NC) s[4 * j4 + e] = fmaf(__uint_as_float(v[4 * j4 + e]), sc2, bb[e] - sub);
   }
   if (mask != 0ULL) {                    // warp-uniform: a warp's 32 rows belong to one window
 #pragma unroll
-    for (int j = 0; j < N; ++j)
+    for (int j = 0; j < NC; ++j)
       if ((mask >> (J0 + j)) & 1ULL) s[j] = -INFINITY;
   }
 }
 
-// one row of a P / dS tile: 49 values -> bf16, chunks 0..6 of the 128-B swizzled row (chunk 7 and keys 49..55 stay zero)
-__device__ __forceinline__ void store_row_bf16(uint32_t tile_row_addr, int row, const float* v) {
+// the same with this thread's slice of its bias row held in registers for the whole kernel (a thread always serves the same
+// token index, so the slice never changes)
+template <int T>
+__device__ __forceinline__ void scores_reg(const uint32_t (&v)[kPC], const float (&bias)[kPC], float sc2, unsigned long long mask, float (&s)[kPC]) {
+  constexpr int J0 = Part<T>::J0, NC = Part<T>::NC;
 #pragma unroll
-  for (int c = 0; c < 6; ++c)
-    st_shared_v4(tile_row_addr + ((c ^ (row & 7)) << 4), pack_bf16(v[8 * c], v[8 * c + 1]), pack_bf16(v[8 * c + 2], v[8 * c + 3]),
-                 pack_bf16(v[8 * c + 4], v[8 * c + 5]), pack_bf16(v[8 * c + 6], v[8 * c + 7]));
-  st_shared_v4(tile_row_addr + ((6 ^ (row & 7)) << 4), pack_bf16(v[48], 0.f), 0u, 0u, 0u);
+  for (int j = 0; j < NC; ++j) s[j] = fmaf(__uint_as_float(v[j]), sc2, bias[j]);
+  if (mask != 0ULL) {
+#pragma unroll
+    for (int j = 0; j < NC; ++j)
+      if ((mask >> (J0 + j)) & 1ULL) s[j] = -INFINITY;
+  }
 }
 
-// 32 fp32 accumulator columns of this lane -> bf16 * f -> 64 B of global memory
-__device__ __forceinline__ void store_row32(bf16* dst, uint32_t taddr, float f, bool live) {
-  uint32_t r0[16], r1[16];
+// this thread's part of one row of a P / dS tile: bf16, 16-B chunks 2 T, 2 T + 1 (and chunk 6 = key 48 + zeros for T = 2) of the
+// 128-B swizzled row; chunk 7 and keys 49..55 stay zero
+template <int T>
+__device__ __forceinline__ void store_part_row(uint32_t tile_row_addr, int row, const float (&v)[kPC]) {
+#pragma unroll
+  for (int c = 0; c < 2; ++c)
+    st_shared_v4(tile_row_addr + (((c + 2 * T) ^ (row & 7)) << 4), pack_bf16(v[8 * c], v[8 * c + 1]), pack_bf16(v[8 * c + 2], v[8 * c + 3]),
+                 pack_bf16(v[8 * c + 4], v[8 * c + 5]), pack_bf16(v[8 * c + 6], v[8 * c + 7]));
+  if (T == 2) st_shared_v4(tile_row_addr + ((6 ^ (row & 7)) << 4), pack_bf16(v[16], 0.f), 0u, 0u, 0u);
+}
+
+// 32 fp32 accumulator columns of this lane -> * f -> bf16 -> 64 B of global memory
+__device__ __forceinline__ void load_row32(uint32_t taddr, uint32_t (&r0)[16], uint32_t (&r1)[16]) {
   tmem_ld16(taddr, r0);
   tmem_ld16(taddr + 16, r1);
-  tmem_ld_wait();
-  if (live) {
-    st_global_v4(dst, pack_bf16(__uint_as_float(r0[0]) * f, __uint_as_float(r0[1]) * f), pack_bf16(__uint_as_float(r0[2]) * f, __uint_as_float(r0[3]) * f),
-                 pack_bf16(__uint_as_float(r0[4]) * f, __uint_as_float(r0[5]) * f), pack_bf16(__uint_as_float(r0[6]) * f, __uint_as_float(r0[7]) * f));
-    st_global_v4(dst + 8, pack_bf16(__uint_as_float(r0[8]) * f, __uint_as_float(r0[9]) * f), pack_bf16(__uint_as_float(r0[10]) * f, __uint_as_float(r0[11]) * f),
-                 pack_bf16(__uint_as_float(r0[12]) * f, __uint_as_float(r0[13]) * f), pack_bf16(__uint_as_float(r0[14]) * f, __uint_as_float(r0[15]) * f));
-    st_global_v4(dst + 16, pack_bf16(__uint_as_float(r1[0]) * f, __uint_as_float(r1[1]) * f), pack_bf16(__uint_as_float(r1[2]) * f, __uint_as_float(r1[3]) * f),
-                 pack_bf16(__uint_as_float(r1[4]) * f, __uint_as_float(r1[5]) * f), pack_bf16(__uint_as_float(r1[6]) * f, __uint_as_float(r1[7]) * f));
-    st_global_v4(dst + 24, pack_bf16(__uint_as_float(r1[8]) * f, __uint_as_float(r1[9]) * f), pack_bf16(__uint_as_float(r1[10]) * f, __uint_as_float(r1[11]) * f),
-                 pack_bf16(__uint_as_float(r1[12]) * f, __uint_as_float(r1[13]) * f), pack_bf16(__uint_as_float(r1[14]) * f, __uint_as_float(r1[15]) * f));
-  }
+}
+__device__ __forceinline__ void store_row32(bf16* dst, const uint32_t (&r0)[16], const uint32_t (&r1)[16], float f) {
+#pragma unroll
+  for (int c = 0; c < 2; ++c)
+    st_global_v4(dst + 8 * c, pack_bf16(__uint_as_float(r0[8 * c]) * f, __uint_as_float(r0[8 * c + 1]) * f),
+                 pack_bf16(__uint_as_float(r0[8 * c + 2]) * f, __uint_as_float(r0[8 * c + 3]) * f),
+                 pack_bf16(__uint_as_float(r0[8 * c + 4]) * f, __uint_as_float(r0[8 * c + 5]) * f),
+                 pack_bf16(__uint_as_float(r0[8 * c + 6]) * f, __uint_as_float(r0[8 * c + 7]) * f));
+#pragma unroll
+  for (int c = 0; c < 2; ++c)
+    st_global_v4(dst + 16 + 8 * c, pack_bf16(__uint_as_float(r1[8 * c]) * f, __uint_as_float(r1[8 * c + 1]) * f),
+                 pack_bf16(__uint_as_float(r1[8 * c + 2]) * f, __uint_as_float(r1[8 * c + 3]) * f),
+                 pack_bf16(__uint_as_float(r1[8 * c + 4]) * f, __uint_as_float(r1[8 * c + 5]) * f),
+                 pack_bf16(__uint_as_float(r1[8 * c + 6]) * f, __uint_as_float(r1[8 * c + 7]) * f));
+}
+
+constexpr int kThreads = 640;                      // 20 warps
+constexpr int kSmWarp0 = 4;                        // softmax warps 4..15, epilogue warps 16..19
+constexpr int kEpWarp0 = kSmWarp0 + 4 * kParts;
+constexpr int kSmWarps = 4 * kParts;
+// the softmax warps that share a TMEM lane quarter (and so the same 32 rows) meet on named barrier 1 + quarter
+__device__ __forceinline__ void part_sync(int q) { asm volatile("bar.sync %0, 96;" ::"r"(1 + q) : "memory"); }
+// one warp's arrival on a barrier that counts warps: every lane's prior work (smem writes + proxy fence, TMEM loads) first
+__device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) {
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
 }
 
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
-constexpr int kFwdStages = 3;
+constexpr int kFwdStages = 4;
 constexpr int kFwdStageBytes = 3 * kTile;                                  // q, k, v tiles
-constexpr int kFwdThreads = 64 + 2 * 128;
-constexpr int kFwdTileBytes = kFwdStages * kFwdStageBytes + 2 * kTile;      // operand ring + one P tile per group
-constexpr int kFwdSmem = kFwdTileBytes + kBiasBytes + kBarBytes + 1024;
-// TMEM columns of group g: S at 256 g (128 columns), O of window A / B at 256 g + 128 / + 160
-constexpr int kFwdTmemO = 128;
+constexpr int kFwdTileBytes = kFwdStages * kFwdStageBytes;                 // the operand ring (P lives in tensor memory)
+constexpr int kXchBytes = 9216;                                             // row-statistics exchange: xM, xL [2][128][4], xRowM [2][128]
+constexpr int kFwdSmem = kFwdTileBytes + kBiasBytes + kXchBytes + kBarBytes + 1024;
+// TMEM columns: S of buffer b at 128 b (128 columns); O of buffer b at 256 + 64 b (window A: +0, window B: +32); P of buffer
+// b at 384 + 32 b: the A operand of O = P V read straight from tensor memory (bf16 pairs, key 2 c and 2 c + 1 in column c), so
+// the probabilities never touch shared memory - the kernel is bound by shared-memory bandwidth (operand reads of the MMAs)
+constexpr int kFwdTmemP = 384;
 
-__global__ void __launch_bounds__(kFwdThreads, 1) window_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs a) {
+template <int T>
+__device__ __forceinline__ void fwd_softmax_task(const RowCtx& rc, const float (&bias)[kPC], float sc2, uint32_t t_s, uint32_t t_p, int q, int lane,
+                                                 int b, uint32_t par, float* xM, float* xL, float* xRowM, uint32_t sfull, uint32_t sfree,
+                                                 uint32_t ofree, uint32_t pfull) {
+  constexpr int NC = Part<T>::NC;
+  mbar_wait(sfull, par);
+  tc_fence_after();
+  uint32_t v[kPC];
+  load_cols<T>(t_s, v);
+  tmem_ld_wait();
+  tc_fence_before();
+  warp_arrive(sfree, lane);                      // the S buffer may be overwritten by the task after next
+  float s[kPC];
+  scores_reg<T>(v, bias, sc2, rc.mask, s);
+  float m0 = s[0], m1 = s[1];
+#pragma unroll
+  for (int j = 2; j < NC; ++j) { if (j & 1) m1 = fmaxf(m1, s[j]); else m0 = fmaxf(m0, s[j]); }
+  float m = fmaxf(m0, m1);
+  float* xm = xM + (b * 128 + rc.row) * 4;
+  xm[T] = m;
+  part_sync(q);
+  m = fmaxf(fmaxf(xm[0], xm[1]), xm[2]);
+  float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < NC; ++j) {
+    s[j] = fast_exp2(s[j] - m);
+    if (j & 1) l1 += s[j]; else l0 += s[j];
+  }
+  // the epilogue warps have read O, xL and xRowM of the task before last (same buffers); its PV MMAs are done with the P columns
+  mbar_wait(ofree, par ^ 1u);
+  tc_fence_after();
+  xL[(b * 128 + rc.row) * 4 + T] = l0 + l1;
+  if (T == 0) xRowM[b * 128 + rc.row] = m;
+  // un-normalised probabilities (1 / l is applied to O) -> bf16 pairs -> this row's P columns: keys 16 T .. 16 T + 15 are
+  // columns 8 T .. 8 T + 7; part 2 also writes columns 24 .. 31 = key 48 and the zeros of the padded keys
+  uint32_t pk[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) pk[c] = pack_bf16(s[2 * c], s[2 * c + 1]);
+  tmem_st8(t_p + 8 * T, pk);
+  if (T == 2) {
+    uint32_t pz[8] = {pack_bf16(s[16], 0.f), 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    tmem_st8(t_p + 24, pz);
+  }
+  tmem_st_wait();
+  tc_fence_before();
+  warp_arrive(pfull, lane);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) window_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t p_base = base + kFwdStages * kFwdStageBytes;
   float* bias_s = reinterpret_cast<float*>(base_ptr + kFwdTileBytes);
-  const uint32_t bar_base = base + kFwdTileBytes + kBiasBytes;
+  float* xM = reinterpret_cast<float*>(base_ptr + kFwdTileBytes + kBiasBytes);
+  float* xL = xM + 2 * 128 * 4;
+  float* xRowM = xL + 2 * 128 * 4;
+  const uint32_t bar_base = base + kFwdTileBytes + kBiasBytes + kXchBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kFwdStages + s); };
-  auto sfull_bar = [&](int g) { return bar_base + 8u * (2 * kFwdStages + g); };
-  auto pfull_bar = [&](int g) { return bar_base + 8u * (2 * kFwdStages + 2 + g); };
-  auto ofull_bar = [&](int g) { return bar_base + 8u * (2 * kFwdStages + 4 + g); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kFwdStages + 6);
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + kFwdTileBytes + kBiasBytes + 8 * (2 * kFwdStages + 6));
+  auto sfull_bar = [&](int b) { return bar_base + 8u * (2 * kFwdStages + b); };
+  auto sfree_bar = [&](int b) { return bar_base + 8u * (2 * kFwdStages + 2 + b); };
+  auto pfull_bar = [&](int b) { return bar_base + 8u * (2 * kFwdStages + 4 + b); };
+  auto ofull_bar = [&](int b) { return bar_base + 8u * (2 * kFwdStages + 6 + b); };
+  auto ofree_bar = [&](int b) { return bar_base + 8u * (2 * kFwdStages + 8 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kFwdStages + 10);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(base_ptr + kFwdTileBytes + kBiasBytes + kXchBytes + 8 * (2 * kFwdStages + 10));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // rows 49..63 / 113..127 of every tile (and key columns 49..63 of the P tiles) are never written again: they must be zero
-  for (int i = threadIdx.x; i < kFwdTileBytes / 16; i += kFwdThreads) st_shared_v4(base + 16u * i, 0u, 0u, 0u, 0u);
+  // rows 49..63 / 113..127 of every tile are never written again: they must be zero
+  for (int i = threadIdx.x; i < kFwdTileBytes / 16; i += kThreads) st_shared_v4(base + 16u * i, 0u, 0u, 0u, 0u);
   build_bias_table(bias_s, a.pos);      // pos is a parameter: not produced by the preceding kernel
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_qkv);
     for (int s = 0; s < kFwdStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int g = 0; g < 2; ++g) { mbar_init(sfull_bar(g), 1); mbar_init(pfull_bar(g), 1); mbar_init(ofull_bar(g), 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(sfull_bar(b), 1); mbar_init(sfree_bar(b), kSmWarps); mbar_init(pfull_bar(b), kSmWarps);
+      mbar_init(ofull_bar(b), 1); mbar_init(ofree_bar(b), 4);
+    }
     mbar_fence_init();
   }
-  if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (warp == 3) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   fence_proxy_async_smem();             // the zero fill is visible to TMA writes and UMMA reads
   tc_fence_before();
   __syncthreads();
@@ -249,111 +354,123 @@ __global__ void __launch_bounds__(kFwdThreads, 1) window_attn_fwd_kernel(const _
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      struct Pend { int valid, stage, slot, last; } pend[2] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
-      uint32_t np[2] = {0u, 0u};                 // P tiles consumed per group (parity of p_full)
-      auto issue_pv = [&](int g) {
-        const Pend pd = pend[g];
-        mbar_wait_backoff(pfull_bar(g), np[g] & 1u, a.wait_ns);
-        ++np[g];
-        tc_fence_after();
-        const uint32_t vs = base + pd.stage * kFwdStageBytes + 2 * kTile;
-        const uint64_t da = make_sw128_desc(p_base + g * kTile, 16, 1024);
-#pragma unroll
-        for (int w = 0; w < 2; ++w) {
-          // B = V of window w, MN-major: contraction over its 64 key rows (8-row groups 1024 B apart, 16 rows per MMA),
-          // N = the head's 32 columns inside the 64-column row
-          const uint64_t db = make_sw128_desc(vs + w * kWinOff + 64 * pd.slot, 8192, 1024);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_f16(tmem_base + g * 256 + kFwdTmemO + 32 * w, da + 2u * k, db + 128u * k, a.idesc_kmn, k > 0 ? 1u : 0u);
-        }
-        umma_commit(ofull_bar(g));
-        if (pd.last) umma_commit(empty_bar(pd.stage));       // every MMA that reads this unit's tiles has been issued
-        pend[g].valid = 0;
-      };
-      int k = 0;
+    if (lane == 0) {                             // S = Q K^T of task n into S buffer n & 1
+      int stage = 0; uint32_t phase = 0, n = 0;
       for (int unit = blockIdx.x; unit < a.units; unit += gridDim.x) {
         const int pair = static_cast<int>(a.div_nhp.div(static_cast<uint32_t>(unit)));
-        const int hp = unit - pair * nhp;
-        const int nslots = min(2, a.heads - 2 * hp);
-        for (int slot = 0; slot < nslots; ++slot, ++k) {
-          const int g = k & 1;
-          if (pend[g].valid) issue_pv(g);        // O of this group's previous head first: it frees S, and (last slot) the stage
-          if (slot == 0) {
-            mbar_wait_backoff(full_bar(stage), phase, a.wait_ns);
-            tc_fence_after();
-          }
+        const int nslots = min(2, a.heads - 2 * (unit - pair * nhp));
+        mbar_wait_backoff(full_bar(stage), phase, a.wait_ns);
+        for (int slot = 0; slot < nslots; ++slot, ++n) {
+          const int b = n & 1;
+          mbar_wait_backoff(sfree_bar(b), ((n >> 1) & 1u) ^ 1u, a.wait_ns);
+          tc_fence_after();
           const uint32_t qs = base + stage * kFwdStageBytes, ks = qs + kTile;
           const uint64_t da = make_sw128_desc(qs + 64 * slot, 16, 1024);
           const uint64_t db = make_sw128_desc(ks + 64 * slot, 16, 1024);
 #pragma unroll
-          for (int kk = 0; kk < 2; ++kk) umma_f16(tmem_base + g * 256, da + 2u * kk, db + 2u * kk, a.idesc_s, kk > 0 ? 1u : 0u);
-          umma_commit(sfull_bar(g));
-          pend[g].valid = 1; pend[g].stage = stage; pend[g].slot = slot; pend[g].last = slot == nslots - 1;
+          for (int kk = 0; kk < 2; ++kk) umma_f16(tmem_base + b * 128, da + 2u * kk, db + 2u * kk, a.idesc_s, kk > 0 ? 1u : 0u);
+          umma_commit(sfull_bar(b));
         }
         if (++stage == kFwdStages) { stage = 0; phase ^= 1u; }
       }
-      if (pend[k & 1].valid) issue_pv(k & 1);                // the older of the two pending heads first
-      if (pend[(k + 1) & 1].valid) issue_pv((k + 1) & 1);
     }
-  } else {
-    const int g = (warp - 2) >> 2;
-    const int q = warp & 3;                     // TMEM lane quarter this warp may access
+  } else if (warp == 2) {
+    if (lane == 0) {                             // O = P V of task n into O buffer n & 1
+      int stage = 0; uint32_t phase = 0, n = 0;
+      for (int unit = blockIdx.x; unit < a.units; unit += gridDim.x) {
+        const int pair = static_cast<int>(a.div_nhp.div(static_cast<uint32_t>(unit)));
+        const int nslots = min(2, a.heads - 2 * (unit - pair * nhp));
+        mbar_wait_backoff(full_bar(stage), phase, a.wait_ns);
+        for (int slot = 0; slot < nslots; ++slot, ++n) {
+          const int b = n & 1;
+          const uint32_t par = (n >> 1) & 1u;
+          mbar_wait_backoff(pfull_bar(b), par, a.wait_ns);
+          mbar_wait_backoff(ofree_bar(b), par ^ 1u, a.wait_ns);
+          tc_fence_after();
+          const uint32_t vs = base + stage * kFwdStageBytes + 2 * kTile;
+#pragma unroll
+          for (int w = 0; w < 2; ++w) {
+            // A = P from tensor memory (8 columns per 16 keys); B = V of window w, MN-major: contraction over its 64 key rows
+            // (8-row groups 1024 B apart, 16 rows per MMA), N = the head's 32 columns inside the 64-column row
+            const uint64_t db = make_sw128_desc(vs + w * kWinOff + 64 * slot, 8192, 1024);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16_ts(tmem_base + 256 + 64 * b + 32 * w, tmem_base + kFwdTmemP + 32 * b + 8 * k, db + 128u * k, a.idesc_kmn, k > 0 ? 1u : 0u);
+          }
+          umma_commit(ofull_bar(b));
+          if (slot == nslots - 1) umma_commit(empty_bar(stage));     // every MMA that reads this unit's tiles has been issued
+        }
+        if (++stage == kFwdStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp >= kSmWarp0 && warp < kEpWarp0) {
+    const int q = warp & 3, part = (warp - kSmWarp0) >> 2;
     RowCtx rc;
     rc.row = q * 32 + lane; rc.ws = rc.row >> 6; rc.i = rc.row & 63;
     rc.row_hi = rc.i >= 28; rc.col_hi = (kColHi >> min(rc.i, 63)) & 1ULL;
-    const float* bias_row = bias_s + min(rc.i, kWt - 1) * kBiasPitch;
     const float sc2 = a.scale * kLog2e;
-    const uint32_t t_s = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * 256 + 64 * rc.ws;
-    const uint32_t t_o = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * 256 + kFwdTmemO + 32 * rc.ws;
-    const uint32_t p_row = p_base + g * kTile + rc.row * 128;
+    float bias[kPC];
+#pragma unroll
+    for (int j = 0; j < kPC; ++j) bias[j] = bias_s[min(rc.i, kWt - 1) * kBiasPitch + min(16 * part + j, kBiasPitch - 1)];
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t lane_addr = lane_base + 64 * rc.ws;
     uint32_t n = 0;
-    int k = 0;
+    for (int unit = blockIdx.x; unit < a.units; unit += gridDim.x) {
+      const int pair = static_cast<int>(a.div_nhp.div(static_cast<uint32_t>(unit)));
+      const int nslots = min(2, a.heads - 2 * (unit - pair * nhp));
+      row_unit(rc, a, pair);
+      for (int slot = 0; slot < nslots; ++slot, ++n) {
+        const int b = n & 1;
+        const uint32_t par = (n >> 1) & 1u;
+        const uint32_t t_p = lane_base + kFwdTmemP + 32 * b;
+        if (part == 0)
+          fwd_softmax_task<0>(rc, bias, sc2, lane_addr + b * 128, t_p, q, lane, b, par, xM, xL, xRowM, sfull_bar(b), sfree_bar(b),
+                              ofree_bar(b), pfull_bar(b));
+        else if (part == 1)
+          fwd_softmax_task<1>(rc, bias, sc2, lane_addr + b * 128, t_p, q, lane, b, par, xM, xL, xRowM, sfull_bar(b), sfree_bar(b),
+                              ofree_bar(b), pfull_bar(b));
+        else
+          fwd_softmax_task<2>(rc, bias, sc2, lane_addr + b * 128, t_p, q, lane, b, par, xM, xL, xRowM, sfull_bar(b), sfree_bar(b),
+                              ofree_bar(b), pfull_bar(b));
+      }
+    }
+  } else if (warp >= kEpWarp0) {
+    const int q = warp & 3;
+    RowCtx rc;
+    rc.row = q * 32 + lane; rc.ws = rc.row >> 6; rc.i = rc.row & 63;
+    rc.row_hi = false; rc.col_hi = false;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + 256 + 32 * rc.ws;
+    uint32_t n = 0;
     for (int unit = blockIdx.x; unit < a.units; unit += gridDim.x) {
       const int pair = static_cast<int>(a.div_nhp.div(static_cast<uint32_t>(unit)));
       const int hp = unit - pair * nhp;
       const int nslots = min(2, a.heads - 2 * hp);
       row_unit(rc, a, pair);
-      for (int slot = 0; slot < nslots; ++slot, ++k) {
-        if ((k & 1) != g) continue;
+      for (int slot = 0; slot < nslots; ++slot, ++n) {
+        const int b = n & 1;
+        const uint32_t par = (n >> 1) & 1u;
         const int h = 2 * hp + slot;
-        mbar_wait(sfull_bar(g), n & 1u);
+        mbar_wait(pfull_bar(b), par);            // the softmax warps' xL / xRowM of this task are visible
+        mbar_wait(ofull_bar(b), par);
         tc_fence_after();
-        uint32_t r0[16], r1[16], r2[16], r3;
-        tmem_ld16(t_s, r0);
-        tmem_ld16(t_s + 16, r1);
-        tmem_ld16(t_s + 32, r2);
-        tmem_ld1(t_s + 48, r3);
+        uint32_t r0[16], r1[16];
+        load_row32(lane_addr + 64 * b, r0, r1);
+        const float* xl = xL + (b * 128 + rc.row) * 4;
+        const float l = (xl[0] + xl[1]) + xl[2];
+        const float m = xRowM[b * 128 + rc.row];
         tmem_ld_wait();
-        float s[kWt];
-        scores_chunk<0, 16>(r0, bias_row, sc2, 0.f, rc.mask, s);
-        scores_chunk<16, 16>(r1, bias_row, sc2, 0.f, rc.mask, s + 16);
-        scores_chunk<32, 16>(r2, bias_row, sc2, 0.f, rc.mask, s + 32);
-        scores_chunk<48, 1>(&r3, bias_row, sc2, 0.f, rc.mask, s + 48);
-        float m = s[0];
-#pragma unroll
-        for (int j = 1; j < kWt; ++j) m = fmaxf(m, s[j]);
-        float l = 0.f;
-#pragma unroll
-        for (int j = 0; j < kWt; ++j) { s[j] = fast_exp2(s[j] - m); l += s[j]; }
-        store_row_bf16(p_row, rc.row, s);            // un-normalised: 1 / l is applied to O
-        fence_proxy_async_smem();                    // generic-proxy smem writes -> visible to the UMMA (async proxy)
         tc_fence_before();
-        group_sync(g);
-        if ((threadIdx.x & 127) == 64) mbar_arrive(pfull_bar(g));      // first thread of the group (threads 64.. / 192..)
-        if (a.lse != nullptr && rc.valid) a.lse[rc.wm_row * a.heads + h] = (m + log2f(l)) * kLn2;
-        mbar_wait(ofull_bar(g), n & 1u);
-        tc_fence_after();
-        store_row32(a.out + rc.gr * a.C + h * kHd, t_o, 1.0f / l, rc.valid);
-        ++n;
+        warp_arrive(ofree_bar(b), lane);
+        if (rc.valid) {
+          store_row32(a.out + rc.gr * a.C + h * kHd, r0, r1, 1.0f / l);
+          if (a.lse != nullptr) a.lse[rc.wm_row * a.heads + h] = (m + log2f(l)) * kLn2;      // natural-log LSE
+        }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+  if (warp == 3) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -361,38 +478,81 @@ __global__ void __launch_bounds__(kFwdThreads, 1) window_attn_fwd_kernel(const _
 // ---------------------------------------------------------------------------------------------
 constexpr int kBwdStages = 2;
 constexpr int kBwdStageBytes = 4 * kTile;                                  // q, k, v, dO tiles
-constexpr int kBwdThreads = 128 + 2 * 128;                                 // producer, MMA, two dO loader warps, two groups
-constexpr int kBwdTileBytes = kBwdStages * kBwdStageBytes + 4 * kTile;      // operand ring + (P, dS) tiles of each group
-constexpr int kBwdSmem = kBwdTileBytes + kBiasBytes + kBarBytes + 1024;
+constexpr int kBwdTileBytes = kBwdStages * kBwdStageBytes + 4 * kTile;      // operand ring + two (P, dS) tile pairs
+constexpr int kBwdXchBytes = 4096;                                          // xD [2][128][4]
+constexpr int kBwdSmem = kBwdTileBytes + kBiasBytes + kBwdXchBytes + kBarBytes + 1024;
 static_assert(kBwdSmem <= 232448 && kFwdSmem <= 232448, "attention smem budget");
-static_assert(2 * 128 * kWt * 4 <= kBwdStages * kBwdStageBytes, "rel-pos fold scratch fits in the operand ring");
-// TMEM columns of group g (base 256 g): S at +0 and dP at +128 (128 columns each); once both have been read they are reused
-// for dQ at +0 / +32 (window A / B), dK at +64 / +96, dV at +128 / +160
+static_assert(128 * kWt * 4 <= kBwdStages * kBwdStageBytes, "rel-pos fold scratch fits in the operand ring");
+// TMEM columns: S at 0, dP at 128 (128 columns each, single-buffered: the softmax warps pull them into registers at once);
+// dQ at 256 / 288 (window A / B), dK at 320 / 352, dV at 384 / 416
 
-__global__ void __launch_bounds__(kBwdThreads, 1) window_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs a) {
+template <int T>
+__device__ __forceinline__ void bwd_softmax_task(const RowCtx& rc, const float* bias_row, float sc2, float lse2, uint32_t t_row, int q, int lane,
+                                                 int b, uint32_t n, float* xD, uint32_t p_row, float (&acc)[kPC], uint32_t sdp, uint32_t sfree,
+                                                 uint32_t gfull, uint32_t pds) {
+  constexpr int NC = Part<T>::NC;
+  mbar_wait(sdp, n & 1u);
+  tc_fence_after();
+  uint32_t v[kPC], d[kPC];
+  load_cols<T>(t_row, v);
+  load_cols<T>(t_row + 128, d);
+  tmem_ld_wait();
+  tc_fence_before();
+  warp_arrive(sfree, lane);                      // S and dP are in registers: the next task's may be computed
+  float p[kPC];
+  scores<T>(v, bias_row, sc2, lse2, rc.mask, p);
+  float D0 = 0.f, D1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < NC; ++j) {
+    p[j] = fast_exp2(p[j]);
+    if (j & 1) D1 = fmaf(p[j], __uint_as_float(d[j]), D1); else D0 = fmaf(p[j], __uint_as_float(d[j]), D0);
+  }
+  float* xd = xD + (b * 128 + rc.row) * 4;
+  xd[T] = D0 + D1;
+  // the dK / dV MMAs of the task before last are done with this buffer's P / dS tiles
+  mbar_wait(gfull, ((n >> 1) & 1u) ^ 1u);
+  store_part_row<T>(p_row, rc.row, p);
+  part_sync(q);
+  const float D = (xd[0] + xd[1]) + xd[2];
+  // dS = P o (dP - D), in place of P; its running sum is the rel-pos gradient of this row
+#pragma unroll
+  for (int j = 0; j < NC; ++j) {
+    p[j] *= __uint_as_float(d[j]) - D;
+    acc[j] += p[j];
+  }
+  store_part_row<T>(p_row + kTile, rc.row, p);
+  fence_proxy_async_smem();
+  warp_arrive(pds, lane);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) window_attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t pds_base = base + kBwdStages * kBwdStageBytes;          // group g: P tile at + 2 g kTile, dS tile after it
+  const uint32_t pds_base = base + kBwdStages * kBwdStageBytes;          // buffer b: P tile at + 2 b kTile, dS tile after it
   float* bias_s = reinterpret_cast<float*>(base_ptr + kBwdTileBytes);
-  const uint32_t bar_base = base + kBwdTileBytes + kBiasBytes;
+  float* xD = reinterpret_cast<float*>(base_ptr + kBwdTileBytes + kBiasBytes);
+  const uint32_t bar_base = base + kBwdTileBytes + kBiasBytes + kBwdXchBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto dofull_bar = [&](int s) { return bar_base + 8u * (kBwdStages + s); };
   auto empty_bar = [&](int s) { return bar_base + 8u * (2 * kBwdStages + s); };
-  auto sdp_bar = [&](int g) { return bar_base + 8u * (3 * kBwdStages + g); };           // S and dP complete
-  auto pds_bar = [&](int g) { return bar_base + 8u * (3 * kBwdStages + 2 + g); };       // P and dS tiles written
-  auto grads_bar = [&](int g) { return bar_base + 8u * (3 * kBwdStages + 4 + g); };     // dQ, dK, dV complete
-  auto free_bar = [&](int g) { return bar_base + 8u * (3 * kBwdStages + 6 + g); };      // dQ, dK, dV read: the columns may be overwritten
-  const uint32_t tmem_slot = bar_base + 8u * (3 * kBwdStages + 8);
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + kBwdTileBytes + kBiasBytes + 8 * (3 * kBwdStages + 8));
+  const uint32_t sdp_bar = bar_base + 8u * (3 * kBwdStages);                            // S and dP complete
+  const uint32_t sfree_bar = bar_base + 8u * (3 * kBwdStages + 1);                      // ... and read
+  auto pds_bar = [&](int b) { return bar_base + 8u * (3 * kBwdStages + 2 + b); };       // P and dS tiles of buffer b written
+  auto gfull_bar = [&](int b) { return bar_base + 8u * (3 * kBwdStages + 4 + b); };     // dQ, dK, dV from buffer b complete
+  const uint32_t gfree_bar = bar_base + 8u * (3 * kBwdStages + 6);                      // ... and read
+  const uint32_t tmem_slot = bar_base + 8u * (3 * kBwdStages + 7);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(base_ptr + kBwdTileBytes + kBiasBytes + kBwdXchBytes + 8 * (3 * kBwdStages + 7));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < kBwdTileBytes / 16; i += kBwdThreads) st_shared_v4(base + 16u * i, 0u, 0u, 0u, 0u);
+  for (int i = threadIdx.x; i < kBwdTileBytes / 16; i += kThreads) st_shared_v4(base + 16u * i, 0u, 0u, 0u, 0u);
   build_bias_table(bias_s, a.pos);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_qkv);
     for (int s = 0; s < kBwdStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(dofull_bar(s), 2); mbar_init(empty_bar(s), 1); }
-    for (int g = 0; g < 2; ++g) { mbar_init(sdp_bar(g), 1); mbar_init(pds_bar(g), 1); mbar_init(grads_bar(g), 1); mbar_init(free_bar(g), 1); }
+    mbar_init(sdp_bar, 1); mbar_init(sfree_bar, kSmWarps); mbar_init(gfree_bar, 4);
+    for (int b = 0; b < 2; ++b) { mbar_init(pds_bar(b), kSmWarps); mbar_init(gfull_bar(b), 1); }
     mbar_fence_init();
   }
   if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -404,96 +564,75 @@ __global__ void __launch_bounds__(kBwdThreads, 1) window_attn_bwd_kernel(const _
   pdl_grid_sync();
 
   const int nhp = a.nhp;
-  float acc[kWt];                              // groups: running sum of this row's dS over every task (rel-pos gradient)
+  float acc[kPC];                              // softmax warps: running sum of this row's dS over every task (rel-pos gradient)
 #pragma unroll
-  for (int j = 0; j < kWt; ++j) acc[j] = 0.f;
+  for (int j = 0; j < kPC; ++j) acc[j] = 0.f;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
+    if (lane == 0) {                             // S = Q K^T and dP = dO V^T of every task
+      int stage = 0; uint32_t phase = 0, n = 0;
       for (int unit = blockIdx.x; unit < a.units; unit += gridDim.x) {
         const int pair = static_cast<int>(a.div_nhp.div(static_cast<uint32_t>(unit)));
-        const int hp = unit - pair * nhp;
-        mbar_wait_backoff(empty_bar(stage), phase ^ 1u, a.wait_ns);
-        mbar_arrive_expect_tx(full_bar(stage), 6u * kBoxBytes);
-        const uint32_t sb = base + stage * kBwdStageBytes;
-#pragma unroll
-        for (int t = 0; t < 3; ++t)
-#pragma unroll
-          for (int w = 0; w < 2; ++w)
-            tma_load_2d(sb + t * kTile + w * kWinOff, &tmap_qkv, full_bar(stage), t * a.C + hp * 64, (2 * pair + w) * kWt);
-        if (++stage == kBwdStages) { stage = 0; phase ^= 1u; }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      struct Pend { int valid, stage, slot, last; } pend[2] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
-      uint32_t ng[2] = {0u, 0u};                 // gradient rounds issued per group (parity of pds)
-      uint32_t ns[2] = {0u, 0u};                 // score rounds issued per group (parity of free)
-      auto issue_grads = [&](int g) {
-        const Pend pd = pend[g];
-        mbar_wait_backoff(pds_bar(g), ng[g] & 1u, a.wait_ns);
-        ++ng[g];
-        tc_fence_after();
-        const uint32_t sb = base + pd.stage * kBwdStageBytes;
-        const uint32_t qs = sb, ks = sb + kTile, dos = sb + 3 * kTile;
-        const uint32_t pt = pds_base + g * 2 * kTile, dt = pt + kTile;
-        const uint32_t tg = tmem_base + g * 256;
-        const uint64_t ds_k = make_sw128_desc(dt, 16, 1024);            // dS as the K-major A operand (contraction over keys)
-        const uint64_t ds_mn = make_sw128_desc(dt, 8192, 1024);         // dS^T: MN-major, its two 64-row halves = two M chunks
-        const uint64_t p_mn = make_sw128_desc(pt, 8192, 1024);
-#pragma unroll
-        for (int w = 0; w < 2; ++w) {
-          const uint32_t col = 64 * pd.slot;
-          const uint64_t k_mn = make_sw128_desc(ks + w * kWinOff + col, 8192, 1024);
-          const uint64_t q_mn = make_sw128_desc(qs + w * kWinOff + col, 8192, 1024);
-          const uint64_t do_mn = make_sw128_desc(dos + w * kWinOff + col, 8192, 1024);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16(tg + 32 * w, ds_k + 2u * k, k_mn + 128u * k, a.idesc_kmn, k > 0 ? 1u : 0u);          // dQ
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16(tg + 64 + 32 * w, ds_mn + 128u * k, q_mn + 128u * k, a.idesc_mnmn, k > 0 ? 1u : 0u);  // dK
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16(tg + 128 + 32 * w, p_mn + 128u * k, do_mn + 128u * k, a.idesc_mnmn, k > 0 ? 1u : 0u);  // dV
-        }
-        umma_commit(grads_bar(g));
-        if (pd.last) umma_commit(empty_bar(pd.stage));
-        pend[g].valid = 0;
-      };
-      int k = 0;
-      for (int unit = blockIdx.x; unit < a.units; unit += gridDim.x) {
-        const int pair = static_cast<int>(a.div_nhp.div(static_cast<uint32_t>(unit)));
-        const int hp = unit - pair * nhp;
-        const int nslots = min(2, a.heads - 2 * hp);
-        for (int slot = 0; slot < nslots; ++slot, ++k) {
-          const int g = k & 1;
-          if (pend[g ^ 1].valid) issue_grads(g ^ 1);       // the previous head (other group): its P / dS are ready by now
-          if (slot == 0) {
-            mbar_wait_backoff(full_bar(stage), phase, a.wait_ns);
-            mbar_wait_backoff(dofull_bar(stage), phase, a.wait_ns);
-            tc_fence_after();
-          }
-          mbar_wait_backoff(free_bar(g), (ns[g] & 1u) ^ 1u, a.wait_ns);   // the group has read its previous dQ / dK / dV
-          ++ns[g];
+        const int nslots = min(2, a.heads - 2 * (unit - pair * nhp));
+        mbar_wait_backoff(full_bar(stage), phase, a.wait_ns);
+        mbar_wait_backoff(dofull_bar(stage), phase, a.wait_ns);
+        for (int slot = 0; slot < nslots; ++slot, ++n) {
+          mbar_wait_backoff(sfree_bar, (n & 1u) ^ 1u, a.wait_ns);
           tc_fence_after();
           const uint32_t sb = base + stage * kBwdStageBytes;
           const uint32_t col = 64 * slot;
           const uint64_t dq = make_sw128_desc(sb + col, 16, 1024), dk = make_sw128_desc(sb + kTile + col, 16, 1024);
           const uint64_t dv = make_sw128_desc(sb + 2 * kTile + col, 16, 1024), dd = make_sw128_desc(sb + 3 * kTile + col, 16, 1024);
 #pragma unroll
-          for (int kk = 0; kk < 2; ++kk) umma_f16(tmem_base + g * 256, dq + 2u * kk, dk + 2u * kk, a.idesc_s, kk > 0 ? 1u : 0u);         // S = Q K^T
+          for (int kk = 0; kk < 2; ++kk) umma_f16(tmem_base, dq + 2u * kk, dk + 2u * kk, a.idesc_s, kk > 0 ? 1u : 0u);         // S = Q K^T
 #pragma unroll
-          for (int kk = 0; kk < 2; ++kk) umma_f16(tmem_base + g * 256 + 128, dd + 2u * kk, dv + 2u * kk, a.idesc_s, kk > 0 ? 1u : 0u);   // dP = dO V^T
-          umma_commit(sdp_bar(g));
-          pend[g].valid = 1; pend[g].stage = stage; pend[g].slot = slot; pend[g].last = slot == nslots - 1;
+          for (int kk = 0; kk < 2; ++kk) umma_f16(tmem_base + 128, dd + 2u * kk, dv + 2u * kk, a.idesc_s, kk > 0 ? 1u : 0u);   // dP = dO V^T
+          umma_commit(sdp_bar);
         }
         if (++stage == kBwdStages) { stage = 0; phase ^= 1u; }
       }
-      if (pend[k & 1].valid) issue_grads(k & 1);
-      if (pend[(k + 1) & 1].valid) issue_grads((k + 1) & 1);
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {                             // dQ = dS K, dK = dS^T Q, dV = P^T dO of every task
+      int stage = 0; uint32_t phase = 0, n = 0;
+      for (int unit = blockIdx.x; unit < a.units; unit += gridDim.x) {
+        const int pair = static_cast<int>(a.div_nhp.div(static_cast<uint32_t>(unit)));
+        const int nslots = min(2, a.heads - 2 * (unit - pair * nhp));
+        mbar_wait_backoff(full_bar(stage), phase, a.wait_ns);
+        mbar_wait_backoff(dofull_bar(stage), phase, a.wait_ns);
+        for (int slot = 0; slot < nslots; ++slot, ++n) {
+          const int b = n & 1;
+          mbar_wait_backoff(pds_bar(b), (n >> 1) & 1u, a.wait_ns);
+          mbar_wait_backoff(gfree_bar, (n & 1u) ^ 1u, a.wait_ns);      // the epilogue warps have read the previous dQ / dK / dV
+          tc_fence_after();
+          const uint32_t sb = base + stage * kBwdStageBytes;
+          const uint32_t qs = sb, ks = sb + kTile, dos = sb + 3 * kTile;
+          const uint32_t pt = pds_base + b * 2 * kTile, dt = pt + kTile;
+          const uint64_t ds_k = make_sw128_desc(dt, 16, 1024);            // dS as the K-major A operand (contraction over keys)
+          const uint64_t ds_mn = make_sw128_desc(dt, 8192, 1024);         // dS^T: MN-major, its two 64-row halves = two M chunks
+          const uint64_t p_mn = make_sw128_desc(pt, 8192, 1024);
+#pragma unroll
+          for (int w = 0; w < 2; ++w) {
+            const uint32_t col = 64 * slot;
+            const uint64_t k_mn = make_sw128_desc(ks + w * kWinOff + col, 8192, 1024);
+            const uint64_t q_mn = make_sw128_desc(qs + w * kWinOff + col, 8192, 1024);
+            const uint64_t do_mn = make_sw128_desc(dos + w * kWinOff + col, 8192, 1024);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16(tmem_base + 256 + 32 * w, ds_k + 2u * k, k_mn + 128u * k, a.idesc_kmn, k > 0 ? 1u : 0u);      // dQ
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16(tmem_base + 320 + 32 * w, ds_mn + 128u * k, q_mn + 128u * k, a.idesc_mnmn, k > 0 ? 1u : 0u);  // dK
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16(tmem_base + 384 + 32 * w, p_mn + 128u * k, do_mn + 128u * k, a.idesc_mnmn, k > 0 ? 1u : 0u);  // dV
+          }
+          umma_commit(gfull_bar(b));
+          if (slot == nslots - 1) umma_commit(empty_bar(stage));
+        }
+        if (++stage == kBwdStages) { stage = 0; phase ^= 1u; }
+      }
     }
   } else if (warp < 4) {
-    // dO rows arrive in raster order: gather them into the swizzled tile with 16-B cp.async (8 lanes per 128-B row)
+    // q / k / v boxes by TMA (lane 0 of warp 2); the dO rows arrive in raster order: both warps gather them into the swizzled
+    // tile with 16-B cp.async (8 lanes per 128-B row)
     const int lt = (warp - 2) * 32 + lane;
     const int chunk = lt & 7, rsub = lt >> 3;
     const int nww = a.W / kWs, nwh = a.H / kWs;
@@ -503,8 +642,25 @@ __global__ void __launch_bounds__(kBwdThreads, 1) window_attn_bwd_kernel(const _
     for (int unit = blockIdx.x; unit < a.units; unit += gridDim.x) {
       const int pair = static_cast<int>(a.div_nhp.div(static_cast<uint32_t>(unit)));
       const int hp = unit - pair * nhp;
+      // the previous unit's rows are announced BEFORE this unit's slot is waited for: with two stages that wait ends only
+      // when the unit before the previous one has been fully consumed, and the score MMAs of the previous unit must not
+      // queue behind it
+      if (prev_stage >= 0) {
+        cp_async_wait<0>();
+        fence_proxy_async_smem();
+        warp_arrive(dofull_bar(prev_stage), lane);
+      }
       mbar_wait_backoff(empty_bar(stage), phase ^ 1u, a.wait_ns);
-      const uint32_t dos = base + stage * kBwdStageBytes + 3 * kTile;
+      const uint32_t sb = base + stage * kBwdStageBytes;
+      if (lt == 0) {
+        mbar_arrive_expect_tx(full_bar(stage), 6u * kBoxBytes);
+#pragma unroll
+        for (int t = 0; t < 3; ++t)
+#pragma unroll
+          for (int w = 0; w < 2; ++w)
+            tma_load_2d(sb + t * kTile + w * kWinOff, &tmap_qkv, full_bar(stage), t * a.C + hp * 64, (2 * pair + w) * kWt);
+      }
+      const uint32_t dos = sb + 3 * kTile;
       const int col0 = hp * 64 + chunk * 8;
       if (col0 < a.C) {
 #pragma unroll
@@ -533,116 +689,94 @@ __global__ void __launch_bounds__(kBwdThreads, 1) window_attn_bwd_kernel(const _
         }
       }
       cp_async_commit();
-      if (prev_stage >= 0) {                     // the previous unit's rows have landed while this unit's were being issued
-        cp_async_wait<1>();
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(dofull_bar(prev_stage));
-      }
       prev_stage = stage;
       if (++stage == kBwdStages) { stage = 0; phase ^= 1u; }
     }
     if (prev_stage >= 0) {
       cp_async_wait<0>();
       fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(dofull_bar(prev_stage));
+      warp_arrive(dofull_bar(prev_stage), lane);
     }
-  } else {
-    const int g = (warp - 4) >> 2;
-    const int q = warp & 3;
+  } else if (warp < kEpWarp0) {
+    const int q = warp & 3, part = (warp - kSmWarp0) >> 2;
     RowCtx rc;
     rc.row = q * 32 + lane; rc.ws = rc.row >> 6; rc.i = rc.row & 63;
     rc.row_hi = rc.i >= 28; rc.col_hi = (kColHi >> min(rc.i, 63)) & 1ULL;
     const float* bias_row = bias_s + min(rc.i, kWt - 1) * kBiasPitch;
     const float sc2 = a.scale * kLog2e;
-    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * 256;
-    const uint32_t t_s = lane_addr + 64 * rc.ws, t_dp = lane_addr + 128 + 64 * rc.ws;
-    const uint32_t p_row = pds_base + g * 2 * kTile + rc.row * 128, ds_row = p_row + kTile;
-    const long long ld = 3LL * a.C;
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + 64 * rc.ws;
     uint32_t n = 0;
-    int k = 0;
+    // the row log-sum-exp of the NEXT task is fetched while the current one is computed (padded rows: +inf makes every
+    // probability exp2(-inf) = 0)
+    auto fetch_lse = [&](int unit, int slot) -> float {
+      if (unit >= a.units) return INFINITY;
+      const int pair = static_cast<int>(a.div_nhp.div(static_cast<uint32_t>(unit)));
+      const int hp = unit - pair * nhp;
+      const int win = 2 * pair + rc.ws;
+      if (win >= a.nwin || rc.i >= kWt) return INFINITY;
+      return __ldg(a.lse + (static_cast<long long>(win) * kWt + rc.i) * a.heads + 2 * hp + slot) * kLog2e;
+    };
+    float lse_next = fetch_lse(blockIdx.x, 0);
     for (int unit = blockIdx.x; unit < a.units; unit += gridDim.x) {
       const int pair = static_cast<int>(a.div_nhp.div(static_cast<uint32_t>(unit)));
       const int hp = unit - pair * nhp;
       const int nslots = min(2, a.heads - 2 * hp);
       row_unit(rc, a, pair);
-      for (int slot = 0; slot < nslots; ++slot, ++k) {
-        if ((k & 1) != g) continue;
+      for (int slot = 0; slot < nslots; ++slot, ++n) {
+        const int b = n & 1;
+        const float lse2 = lse_next;
+        lse_next = slot + 1 < nslots ? fetch_lse(unit, slot + 1) : fetch_lse(unit + static_cast<int>(gridDim.x), 0);
+        const uint32_t p_row = pds_base + b * 2 * kTile + rc.row * 128;
+        if (part == 0) bwd_softmax_task<0>(rc, bias_row, sc2, lse2, t_row, q, lane, b, n, xD, p_row, acc, sdp_bar, sfree_bar, gfull_bar(b), pds_bar(b));
+        else if (part == 1) bwd_softmax_task<1>(rc, bias_row, sc2, lse2, t_row, q, lane, b, n, xD, p_row, acc, sdp_bar, sfree_bar, gfull_bar(b), pds_bar(b));
+        else bwd_softmax_task<2>(rc, bias_row, sc2, lse2, t_row, q, lane, b, n, xD, p_row, acc, sdp_bar, sfree_bar, gfull_bar(b), pds_bar(b));
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    RowCtx rc;
+    rc.row = q * 32 + lane; rc.ws = rc.row >> 6; rc.i = rc.row & 63;
+    rc.row_hi = false; rc.col_hi = false;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + 256 + 32 * rc.ws;
+    const long long ld = 3LL * a.C;
+    uint32_t n = 0;
+    for (int unit = blockIdx.x; unit < a.units; unit += gridDim.x) {
+      const int pair = static_cast<int>(a.div_nhp.div(static_cast<uint32_t>(unit)));
+      const int hp = unit - pair * nhp;
+      const int nslots = min(2, a.heads - 2 * hp);
+      row_unit(rc, a, pair);
+      for (int slot = 0; slot < nslots; ++slot, ++n) {
+        const int b = n & 1;
         const int h = 2 * hp + slot;
-        // padded rows: lse = +inf makes every probability exp2(-inf) = 0
-        const float lse2 = rc.valid ? __ldg(a.lse + rc.wm_row * a.heads + h) * kLog2e : INFINITY;
-        mbar_wait(sdp_bar(g), n & 1u);
-        tc_fence_after();
-        float p[kWt];
-        float D = 0.f;
-        {
-          uint32_t r0[16], r1[16], r2[16], r3;
-          tmem_ld16(t_s, r0);
-          tmem_ld16(t_s + 16, r1);
-          tmem_ld16(t_s + 32, r2);
-          tmem_ld1(t_s + 48, r3);
-          tmem_ld_wait();
-          scores_chunk<0, 16>(r0, bias_row, sc2, lse2, rc.mask, p);
-          scores_chunk<16, 16>(r1, bias_row, sc2, lse2, rc.mask, p + 16);
-          scores_chunk<32, 16>(r2, bias_row, sc2, lse2, rc.mask, p + 32);
-          scores_chunk<48, 1>(&r3, bias_row, sc2, lse2, rc.mask, p + 48);
-#pragma unroll
-          for (int j = 0; j < kWt; ++j) p[j] = fast_exp2(p[j]);
-          store_row_bf16(p_row, rc.row, p);
-        }
-        {
-          uint32_t d0[16], d1[16], d2[16], d3;
-          tmem_ld16(t_dp, d0);
-          tmem_ld16(t_dp + 16, d1);
-          tmem_ld16(t_dp + 32, d2);
-          tmem_ld1(t_dp + 48, d3);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            D = fmaf(p[j], __uint_as_float(d0[j]), D);
-            D = fmaf(p[16 + j], __uint_as_float(d1[j]), D);
-            D = fmaf(p[32 + j], __uint_as_float(d2[j]), D);
-          }
-          D = fmaf(p[48], __uint_as_float(d3), D);
-          // dS = P o (dP - D), in place of P; its running sum is the rel-pos gradient of this row
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            p[j] *= __uint_as_float(d0[j]) - D;
-            p[16 + j] *= __uint_as_float(d1[j]) - D;
-            p[32 + j] *= __uint_as_float(d2[j]) - D;
-          }
-          p[48] *= __uint_as_float(d3) - D;
-#pragma unroll
-          for (int j = 0; j < kWt; ++j) acc[j] += p[j];
-          store_row_bf16(ds_row, rc.row, p);
-        }
-        fence_proxy_async_smem();
-        tc_fence_before();
-        group_sync(g);
-        if ((threadIdx.x & 127) == 0) mbar_arrive(pds_bar(g));
-        mbar_wait(grads_bar(g), n & 1u);
+        mbar_wait(gfull_bar(b), (n >> 1) & 1u);
         tc_fence_after();
         bf16* dst = a.dqkv + rc.wm_row * ld + h * kHd;
-        store_row32(dst, lane_addr + 32 * rc.ws, a.scale, rc.valid);                  // dQ (scaled: S = scale Q K^T + bias)
-        store_row32(dst + a.C, lane_addr + 64 + 32 * rc.ws, a.scale, rc.valid);       // dK
-        store_row32(dst + 2 * a.C, lane_addr + 128 + 32 * rc.ws, 1.0f, rc.valid);     // dV
+        uint32_t r0[16], r1[16], r2[16], r3[16];
+        load_row32(lane_addr, r0, r1);                  // dQ
+        load_row32(lane_addr + 64, r2, r3);             // dK
+        tmem_ld_wait();
+        if (rc.valid) {
+          store_row32(dst, r0, r1, a.scale);            // scaled: S = scale Q K^T + bias
+          store_row32(dst + a.C, r2, r3, a.scale);
+        }
+        load_row32(lane_addr + 128, r0, r1);            // dV
+        tmem_ld_wait();
         tc_fence_before();
-        group_sync(g);
-        if ((threadIdx.x & 127) == 0) mbar_arrive(free_bar(g));
-        ++n;
+        warp_arrive(gfree_bar, lane);
+        if (rc.valid) store_row32(dst + 2 * a.C, r0, r1, 1.0f);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
   // Fold the per-row dS sums into the 13 x 13 bins, one partial row per CTA, fixed order (no atomics): bin (dr, dc) collects
-  // every (query i, key j) with j's window row / column = i's + (dr, dc), over both groups and both window slots.
-  float* fold = reinterpret_cast<float*>(base_ptr);                 // [2 groups][128 rows][49]: the operand ring is idle now
-  if (warp >= 4) {
-    const int g = (warp - 4) >> 2, row = (warp & 3) * 32 + lane;
+  // every (query i, key j) with j's window row / column = i's + (dr, dc), over both window slots.
+  float* fold = reinterpret_cast<float*>(base_ptr);                 // [128 rows][49]: the operand ring is idle now
+  if (warp >= kSmWarp0 && warp < kEpWarp0) {
+    const int part = (warp - kSmWarp0) >> 2, row = (warp & 3) * 32 + lane;
 #pragma unroll
-    for (int j = 0; j < kWt; ++j) fold[(g * 128 + row) * kWt + j] = acc[j];
+    for (int j = 0; j < kPC; ++j)
+      if (part == 2 || j < 16) fold[row * kWt + 16 * part + j] = acc[j];
   }
   __syncthreads();
   if (threadIdx.x < kBins) {
@@ -651,8 +785,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) window_attn_bwd_kernel(const _
     for (int ri = max(0, -dr); ri < min(kWs, kWs - dr); ++ri)
       for (int ci = max(0, -dc); ci < min(kWs, kWs - dc); ++ci) {
         const int i = ri * kWs + ci, j = (ri + dr) * kWs + ci + dc;
-#pragma unroll
-        for (int src = 0; src < 4; ++src) sum += fold[((src >> 1) * 128 + (src & 1) * 64 + i) * kWt + j];
+        sum += fold[i * kWt + j] + fold[(64 + i) * kWt + j];
       }
     a.dpos_partial[1LL * blockIdx.x * kBins + threadIdx.x] = sum;
   }
@@ -700,7 +833,7 @@ extern "C" int b200_window_attn_fwd(const void* qkv, const float* pos, void* out
   static bool attr = false;
   if (!attr) { B200_CHECK_CUDA(cudaFuncSetAttribute(window_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem)); attr = true; }
   const int blocks = std::min(a.units, b200_num_sms());                 // persistent: one CTA per SM
-  launch_pdl(window_attn_fwd_kernel, dim3(blocks), dim3(kFwdThreads), kFwdSmem, reinterpret_cast<cudaStream_t>(stream), tm, a);
+  launch_pdl(window_attn_fwd_kernel, dim3(blocks), dim3(kThreads), kFwdSmem, reinterpret_cast<cudaStream_t>(stream), tm, a);
   B200_LAUNCH_CHECK();
   return B200_OK;
 }
@@ -731,7 +864,7 @@ extern "C" int b200_window_attn_bwd(const void* qkv, const float* pos, const flo
   if (!attr) { B200_CHECK_CUDA(cudaFuncSetAttribute(window_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem)); attr = true; }
   const int blocks = b200_window_attn_bwd_blocks(B, H, W, heads);
   auto st = reinterpret_cast<cudaStream_t>(stream);
-  launch_pdl(window_attn_bwd_kernel, dim3(blocks), dim3(kBwdThreads), kBwdSmem, st, tm, a);
+  launch_pdl(window_attn_bwd_kernel, dim3(blocks), dim3(kThreads), kBwdSmem, st, tm, a);
   B200_LAUNCH_CHECK();
   // [blocks][169] partial rows -> the 13 x 13 table gradient, fixed order (recorded, not launched, inside a reduce batch)
   return reduce_or_defer(dpos_partial, &dpos, 1, kBins, blocks, accumulate_dpos, st, kBins);
