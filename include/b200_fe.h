@@ -61,6 +61,17 @@ int b200_device_check(void); /* B200_ERR_ARCH unless the current device is sm_10
 int b200_prof_begin(int time_gemm_launches);
 int b200_prof_end(double* gemm_ms, double* gemm_flops, long long* gemm_launches, long long* total_launches);
 int b200_prof_gemm_bytes(double* bytes); /* algorithmic HBM bytes of the launches the last b200_prof_end summed */
+/* kinds of timed kernels: the tcgen05 GEMM, window attention forward / backward, LayerNorm forward / backward, the batched
+ * fixed-order reductions */
+#define B200_PROF_GEMM 0
+#define B200_PROF_ATTN_FWD 1
+#define B200_PROF_ATTN_BWD 2
+#define B200_PROF_LN_FWD 3
+#define B200_PROF_LN_BWD 4
+#define B200_PROF_REDUCE 5
+#define B200_PROF_KINDS 6
+/* per-kind totals (CUDA-event ms, algorithmic FLOPs and HBM bytes, launches) of the last timed region; call after b200_prof_end */
+int b200_prof_kernels(int n_kinds, double* ms, double* flops, double* bytes, long long* launches);
 
 /* ---- linear layers: D[M,N] = A[M,K] * B[N,K]^T on tcgen05 tensor cores (TMA-fed, TMEM accumulators) ---------
  * replaces nn.Linear forward and the two GEMMs autograd runs for its backward (models/swin.py:39-43,91,98,
@@ -180,11 +191,30 @@ int b200_swin_backward(const void* plan, const float* params, const void* wcache
 /* ---- gallery matching: cosine scores + top-k (engine/controller.py:77-91, similarity_f of
  *      configs/dog_fe/fe_dogs_config.py:89-93; query != gallery form: generate_tsv_to_reproduce2.py:63-119) ---------- */
 int b200_gallery_prepare(const float* emb, void* unit_f16, double* norm, long long n, int dim, void* stream);
+/* Rows for the tensor-core pass in a frame fitted to a (concentrated) gallery, with error accounting for the certificate.
+ * frame = [mu (dim) | w (dim) | |mu|] from b200_gallery_frame(mean unit gallery row): H = I - 2 w w^T maps mu / |mu| onto the
+ * first axis and   gallery (role 1): row = scale * H (g^ - mu)      query (role 0): row = H q^,
+ * so row_q . row_g / scale = cos(q, g) - q^ . mu: the ranking of the cosine, with operands of the size of the embeddings'
+ * spread.  frame null: plain unit rows.  err (nullable, [n][4]) = {|d_1|, |d_rest|, |row_1|, |row_rest|} (d = fp16 rounding
+ * residual, unscaled); stats (nullable, 4 floats the caller zeroes): maxima over the rows of {|row_1|, |row_rest|, |d_1|, |d_rest|}. */
+int b200_gallery_prepare_ex(const float* emb, const float* frame, int role, float scale, void* f16_rows, double* norm, float* err,
+                            float* stats, long long n, int dim, void* stream);
+int b200_gallery_frame(const float* mean_unit_row, int dim, float* frame /* [2 * dim + 1] */, void* stream);
+int b200_unit_row_mean_blocks(long long n);
+int b200_unit_row_mean(const float* emb, long long n, int dim, float* mean, float* partial, void* stream); /* mean unit row */
 long long b200_cosine_topk_workspace_bytes(long long nq, long long ng, int dim, int k);
 int b200_cosine_topk(const float* q, const void* q_unit_f16, const double* q_norm, long long nq, const float* g,
                      const void* g_unit_f16, const double* g_norm, long long ng, int dim, int k, long long exclude_self_offset,
                      long long g_index_base, int* out_idx, double* out_score, void* workspace, long long workspace_bytes,
                      void* stream);
+/* b200_cosine_topk + exactness certificate: a query whose kept candidates cannot be PROVEN to contain the true top-k (bound on
+ * |fp16 score - exact score| from the measured rounding residuals vs the margin between the pruning thresholds and the exact
+ * k-th score) is re-done by an exact fp64 scan of the gallery.  uncertified: int [1 + nq] = count, then those queries. */
+int b200_cosine_topk_certified(const float* q, const void* q_f16, const double* q_norm, const float* q_err, long long nq,
+                               const float* g, const void* g_f16, const double* g_norm, const float* frame, float g_scale,
+                               const float* g_stats, long long ng, int dim, int k, long long exclude_self_offset, long long g_index_base,
+                               int* out_idx, double* out_score, int* uncertified, void* workspace, long long workspace_bytes,
+                               void* stream);
 int b200_topk_merge(const double* scores, const int* idx, long long nq, int lists, int k_in, int k_out, int* out_idx,
                     double* out_score, void* stream);
 /* Pair verification scores, engine/controller.py:60-68 + similarity_f (configs/dog_fe/fe_dogs_config.py:89-93):

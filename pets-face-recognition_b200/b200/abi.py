@@ -40,6 +40,7 @@ _PROTOS = {
     'b200_prof_begin': (c_int, [c_int]),
     'b200_prof_end': (c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(c_ll), C.POINTER(c_ll)]),
     'b200_prof_gemm_bytes': (c_int, [C.POINTER(C.c_double)]),
+    'b200_prof_kernels': (c_int, [c_int, c_vp, c_vp, c_vp, c_vp]),
     'b200_gemm_tn': (c_int, [c_vp, c_ll, c_vp, c_ll, c_int, c_int, c_int, c_int, c_int, c_vp, c_ll, c_int, c_vp, c_ll, c_vp,
                              c_vp, c_ll, c_int, c_ll, c_int, c_vp]),
     'b200_gemm_wgrad': (c_int, [c_vp, c_ll, c_vp, c_ll, c_ll, c_int, c_int, c_vp, c_int, c_int, c_vp]),
@@ -89,9 +90,15 @@ _PROTOS = {
     'b200_swin_forward': (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_ll, c_vp]),
     'b200_swin_backward': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, c_int, c_int, c_vp]),
     'b200_gallery_prepare': (c_int, [c_vp, c_vp, c_vp, c_ll, c_int, c_vp]),
+    'b200_gallery_prepare_ex': (c_int, [c_vp, c_vp, c_int, c_float, c_vp, c_vp, c_vp, c_vp, c_ll, c_int, c_vp]),
+    'b200_gallery_frame': (c_int, [c_vp, c_int, c_vp, c_vp]),
+    'b200_unit_row_mean_blocks': (c_int, [c_ll]),
+    'b200_unit_row_mean': (c_int, [c_vp, c_ll, c_int, c_vp, c_vp, c_vp]),
     'b200_cosine_topk_workspace_bytes': (c_ll, [c_ll, c_ll, c_int, c_int]),
     'b200_cosine_topk': (c_int, [c_vp, c_vp, c_vp, c_ll, c_vp, c_vp, c_vp, c_ll, c_int, c_int, c_ll, c_ll, c_vp, c_vp, c_vp, c_ll,
                                  c_vp]),
+    'b200_cosine_topk_certified': (c_int, [c_vp, c_vp, c_vp, c_vp, c_ll, c_vp, c_vp, c_vp, c_vp, c_float, c_vp, c_ll, c_int, c_int, c_ll, c_ll,
+                                           c_vp, c_vp, c_vp, c_vp, c_ll, c_vp]),
     'b200_topk_merge': (c_int, [c_vp, c_vp, c_ll, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
     'b200_pair_similarity': (c_int, [c_vp, c_ll, c_int, c_vp, c_vp, c_ll, c_vp, c_vp]),
     'b200_recall_hits': (c_int, [c_vp, c_ll, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp]),

@@ -25,26 +25,69 @@ def prepare(emb: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     return unit, norm
 
 
+_G_SCALE = 64.0      # power of two: lifts the centred gallery rows well into the fp16 normal range; ranking is scale-invariant
+
+
+class Prepared:
+    """fp16 rows of one embedding set for the tensor-core pass + what the exactness certificate needs (csrc/gallery.cu).
+    A gallery defines the frame (its mean unit row mu and the reflection that puts mu on the first axis) and is stored as
+    scale * H (g^ - mu); queries matched against it are stored as H q^ in the SAME frame (`frame_of=` the gallery's Prepared)."""
+
+    def __init__(self, emb: torch.Tensor, as_gallery: bool, frame_of: 'Prepared' = None):
+        emb = emb.contiguous().float()
+        n, dim = emb.shape
+        dev = emb.device
+        L = lib()
+        self.rows = torch.empty(n, dim, device=dev, dtype=torch.float16)
+        self.norm = torch.empty(n, device=dev, dtype=torch.float64)
+        self.err = torch.empty(n, 4, device=dev, dtype=torch.float32)
+        self.stats = torch.zeros(4, device=dev, dtype=torch.float32)
+        self.frame, self.scale = None, 1.0
+        if as_gallery and n > 0:
+            mean = torch.empty(dim, device=dev, dtype=torch.float32)
+            partial = torch.empty(L.b200_unit_row_mean_blocks(n), dim, device=dev, dtype=torch.float32)
+            check(L.b200_unit_row_mean(ptr(emb), n, dim, ptr(mean), ptr(partial), stream_ptr()), 'unit_row_mean')
+            self.frame = torch.empty(2 * dim + 1, device=dev, dtype=torch.float32)
+            check(L.b200_gallery_frame(ptr(mean), dim, ptr(self.frame), stream_ptr()), 'gallery_frame')
+            self.scale = _G_SCALE
+        elif frame_of is not None:
+            self.frame = frame_of.frame
+        check(L.b200_gallery_prepare_ex(ptr(emb), ptr(self.frame), int(as_gallery), self.scale, ptr(self.rows), ptr(self.norm),
+                                        ptr(self.err), ptr(self.stats), n, dim, stream_ptr()), 'gallery_prepare_ex')
+
+
 def cosine_topk(q: torch.Tensor, g: torch.Tensor, k: int, exclude_self_offset: Optional[int] = None, g_index_base: int = 0,
-                q_prepared=None, g_prepared=None) -> Tuple[torch.Tensor, torch.Tensor]:
+                q_prepared=None, g_prepared=None, return_uncertified: bool = False):
     """Top-k gallery rows per query: (idx int32 [nq, k] (+ g_index_base, -1 = none), score fp64 [nq, k]).
-    exclude_self_offset = o skips gallery row (o + i) for query i (leave-one-out, engine/controller.py:80)."""
+    exclude_self_offset = o skips gallery row (o + i) for query i (leave-one-out, engine/controller.py:80).
+
+    Default path: centred fp16 gallery rows + the exactness certificate (queries it cannot prove are re-done by an exact
+    scan on the device; return_uncertified=True also returns how many that were).  Passing legacy (rows, norm) tuples as
+    q_prepared / g_prepared runs the uncertified kernel pair (the dot-mode scoring of b200/multivector.py)."""
     abi.require_device()
     q = q.contiguous().float()
     g = g.contiguous().float()
     nq, dim = q.shape
     ng = g.shape[0]
-    qu, qn = q_prepared if q_prepared is not None else prepare(q)
-    gu, gn = g_prepared if g_prepared is not None else (
-        (qu, qn) if (g.data_ptr() == q.data_ptr() and ng == nq) else prepare(g))
     idx = torch.empty(nq, k, device=q.device, dtype=torch.int32)
     score = torch.empty(nq, k, device=q.device, dtype=torch.float64)
     wsb = lib().b200_cosine_topk_workspace_bytes(nq, ng, dim, k)
     ws = torch.empty(wsb, device=q.device, dtype=torch.uint8)
     off = abi.NO_EXCLUDE if exclude_self_offset is None else int(exclude_self_offset)
-    check(lib().b200_cosine_topk(ptr(q), ptr(qu), ptr(qn), nq, ptr(g), ptr(gu), ptr(gn), ng, dim, k, off, g_index_base,
-                                 ptr(idx), ptr(score), ptr(ws), wsb, stream_ptr()), 'cosine_topk')
-    return idx, score
+    legacy = isinstance(q_prepared, tuple) or isinstance(g_prepared, tuple)
+    if legacy:
+        qu, qn = q_prepared if q_prepared is not None else prepare(q)
+        gu, gn = g_prepared if g_prepared is not None else prepare(g)
+        check(lib().b200_cosine_topk(ptr(q), ptr(qu), ptr(qn), nq, ptr(g), ptr(gu), ptr(gn), ng, dim, k, off, g_index_base,
+                                     ptr(idx), ptr(score), ptr(ws), wsb, stream_ptr()), 'cosine_topk')
+        return (idx, score, 0) if return_uncertified else (idx, score)
+    gp = g_prepared if g_prepared is not None else Prepared(g, as_gallery=True)
+    qp = q_prepared if q_prepared is not None else Prepared(q, as_gallery=False, frame_of=gp)
+    unc = torch.empty(1 + nq, device=q.device, dtype=torch.int32)
+    check(lib().b200_cosine_topk_certified(ptr(q), ptr(qp.rows), ptr(qp.norm), ptr(qp.err), nq, ptr(g), ptr(gp.rows), ptr(gp.norm),
+                                           ptr(gp.frame), gp.scale, ptr(gp.stats), ng, dim, k, off, g_index_base, ptr(idx), ptr(score),
+                                           ptr(unc), ptr(ws), wsb, stream_ptr()), 'cosine_topk_certified')
+    return (idx, score, unc[0]) if return_uncertified else (idx, score)
 
 
 def topk_merge(scores: torch.Tensor, idx: torch.Tensor, k_out: int) -> Tuple[torch.Tensor, torch.Tensor]:

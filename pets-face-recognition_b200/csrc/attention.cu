@@ -833,7 +833,12 @@ extern "C" int b200_window_attn_fwd(const void* qkv, const float* pos, void* out
   static bool attr = false;
   if (!attr) { B200_CHECK_CUDA(cudaFuncSetAttribute(window_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem)); attr = true; }
   const int blocks = std::min(a.units, b200_num_sms());                 // persistent: one CTA per SM
-  launch_pdl(window_attn_fwd_kernel, dim3(blocks), dim3(kThreads), kFwdSmem, reinterpret_cast<cudaStream_t>(stream), tm, a);
+  auto st = reinterpret_cast<cudaStream_t>(stream);
+  // algorithmic work: q, k, v in, the output (and one LSE per row and head) out; 4 x 49 x 32 MACs per (token, head)
+  const double tokens = 1.0 * B * H * W;
+  const bool prof = b200_prof_kind_begin(st, B200_PROF_ATTN_FWD, tokens * heads * 4.0 * kWt * kHd * 2.0, tokens * C * 2.0 * 4.0 + (lse ? tokens * heads * 4.0 : 0.0));
+  launch_pdl(window_attn_fwd_kernel, dim3(blocks), dim3(kThreads), kFwdSmem, st, tm, a);
+  if (prof) b200_prof_kind_end(st);
   B200_LAUNCH_CHECK();
   return B200_OK;
 }
@@ -864,7 +869,11 @@ extern "C" int b200_window_attn_bwd(const void* qkv, const float* pos, const flo
   if (!attr) { B200_CHECK_CUDA(cudaFuncSetAttribute(window_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem)); attr = true; }
   const int blocks = b200_window_attn_bwd_blocks(B, H, W, heads);
   auto st = reinterpret_cast<cudaStream_t>(stream);
+  // algorithmic work: q, k, v, dO (and the LSE) in, dq, dk, dv out; five 49 x 49 x 32 products per (window, head)
+  const double tokens = 1.0 * B * H * W;
+  const bool prof = b200_prof_kind_begin(st, B200_PROF_ATTN_BWD, tokens * heads * 10.0 * kWt * kHd * 2.0, tokens * C * 2.0 * 7.0 + tokens * heads * 4.0);
   launch_pdl(window_attn_bwd_kernel, dim3(blocks), dim3(kThreads), kBwdSmem, st, tm, a);
+  if (prof) b200_prof_kind_end(st);
   B200_LAUNCH_CHECK();
   // [blocks][169] partial rows -> the 13 x 13 table gradient, fixed order (recorded, not launched, inside a reduce batch)
   return reduce_or_defer(dpos_partial, &dpos, 1, kBins, blocks, accumulate_dpos, st, kBins);

@@ -587,7 +587,9 @@ int ln_fwd_launch(const bf16* x, const float* g, const float* b, bf16* y, float*
   const int rpw = (32 / LPR) * U;
   const long long warps = (M + rpw - 1) / rpw;
   const int blocks = grid_for(warps * 32, 256, b200_num_sms() * 8);
+  const bool prof = b200_prof_kind_begin(st, B200_PROF_LN_FWD, 0.0, 1.0 * M * C * 2.0 * 2.0 + 1.0 * M * 8.0);
   launch_pdl(layernorm_fwd_kernel<LPR, MAXIT, U>, dim3(blocks), dim3(256), 0, st, x, g, b, y, mean, rstd, M, C, eps, b200_reverse_rows(), wm);
+  if (prof) b200_prof_kind_end(st);
   B200_LAUNCH_CHECK();
   return B200_OK;
 }
@@ -595,6 +597,7 @@ template <int LPR, int MAXIT>
 int ln_bwd_launch(const bf16* dy, const bf16* x, const float* g, const float* mean, const float* rstd, const bf16* dres, bf16* dx,
                   float* partial, long long M, int C, int blocks, bool with_res, cudaStream_t st, const WinMap& wm) {
   const size_t smem = sizeof(float) * (kLnBwdThreads / 32) * 3 * C;
+  const bool prof = b200_prof_kind_begin(st, B200_PROF_LN_BWD, 0.0, 1.0 * M * C * 2.0 * (dres ? 4.0 : 3.0) + 1.0 * M * 8.0);
   if (with_res) {
     if (smem > 48 * 1024)
       B200_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<LPR, MAXIT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -604,6 +607,7 @@ int ln_bwd_launch(const bf16* dy, const bf16* x, const float* g, const float* me
       B200_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<LPR, MAXIT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     launch_pdl(layernorm_bwd_kernel<LPR, MAXIT, false>, dim3(blocks), dim3(kLnBwdThreads), smem, st, dy, x, g, mean, rstd, dres, dx, partial, M, C, b200_reverse_rows(), wm);
   }
+  if (prof) b200_prof_kind_end(st);
   B200_LAUNCH_CHECK();
   return B200_OK;
 }

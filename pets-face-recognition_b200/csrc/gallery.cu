@@ -17,6 +17,19 @@
 //           the fp32 embeddings - and sorted by (score desc, gallery index asc): the deterministic order that
 //           oracle/rank_oracle.py:topk_spec defines, so indices are bit-exact regardless of fp16 error as long as
 //           the true top-k lie in the approximate top-KP (KP = k + 28 slack, fp16 cosine error ~3e-5).
+//  frame    Embeddings of one domain are concentrated (cosines of 0.99+ between unrelated images for an untrained / early
+//           backbone): plain fp16 unit rows have no resolution left there.  The tensor-core pass therefore runs in a frame
+//           fitted to the gallery: mu = mean unit gallery row, H = the Householder reflection that maps mu / |mu| onto the
+//           first axis (orthogonal: dot products are unchanged), and
+//               gallery row  G = scale * [ (H g^)_1 - |mu| , (H g^)_2.. ]   ( = H (g^ - mu) )        query  Q = H q^
+//           so that Q . G / scale = q^ . (g^ - mu) = cos(q, g) - q^ . mu: the cosine up to a per-query constant - the ranking
+//           is untouched - while every large number has left the fp16 operands: all of the gallery vector and all but one
+//           coordinate of the query are of the size of the embeddings' SPREAD, and so are their rounding errors.
+//  phase 3  CERTIFICATE: every candidate ever dropped had an approximate score <= a_cut (the largest threshold any of the
+//           query's lists pruned with / the level-1 cut).  With E = the rigorous bound of |approximate - exact| from the
+//           measured fp16 residual norms, a_cut + E < (exact k-th score) proves that no dropped row belongs to the top-k.
+//           Queries that cannot be certified (near-duplicate galleries: hundreds of rows closer than fp16 resolution) are
+//           re-done by exact_topk_kernel, an exact fp64 scan of the whole gallery - slow, rare, never wrong.
 #include <climits>
 #include <cstdlib>
 
@@ -64,6 +77,7 @@ struct FilterParams {
   int* cand_idx;              // [q_blocks*128][lists][kKP]
   float* cand_score;          // [q_blocks*128][lists][kKP] fp16-GEMM scores of the survivors (approximate)
   int* cand_cnt;              // [q_blocks*128][lists]
+  float* list_tau;            // [q_blocks*128][lists] final threshold of every list: nothing it dropped scored above it
 };
 
 __device__ __forceinline__ uint32_t fkey(float f) {   // order-preserving float -> uint
@@ -393,7 +407,7 @@ cosine_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         const int n = __shfl_sync(0xffffffffu, cnt, src);
         float new_tau;
         const int m = prune_list<true>(warp_lists + 1LL * src * kCap, n, &new_tau, lane);
-        if (lane == src) cnt = m;
+        if (lane == src) { cnt = m; tau = fmaxf(tau, new_tau); }
       }
       __syncwarp();
       if (qb < p.q_blocks) {
@@ -409,6 +423,7 @@ cosine_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
           }
           if (lane == 0) p.cand_cnt[li] = n;
         }
+        if (live) p.list_tau[qrow * p.lists + 2 * chunk + half] = tau;
       }
       __syncwarp();
     }
@@ -460,11 +475,21 @@ __device__ void warp_bitonic_sort(Cand* c, int n_pow2, int lane) {
 }
 
 // One warp per query (no block-wide barriers): approximate select -> exact fp64 re-score -> sort.
+struct CertParams {             // all null / zero: no certificate
+  const float* list_tau;        // [nq][lists]
+  const float* center;          // [dim] mu of the gallery frame (null: plain unit rows)
+  const float* q_err;           // [nq][4]: |dQ_1|, |dQ_rest|, |Q_1|, |Q_rest| of the fp16 query row (d = rounding residual)
+  const float* g_stats;         // [4] maxima over the gallery rows of |G_1|, |G_rest|, |dG_1|, |dG_rest| (unscaled)
+  float inv_scale;              // approximate scores are in units of `scale`
+  int* uncert;                  // [1 + nq]: count, then the queries that could not be certified
+};
+
 __global__ void __launch_bounds__(256, 3) rerank_kernel(const float* __restrict__ q, const double* __restrict__ q_norm,
                                                      const float* __restrict__ g, const double* __restrict__ g_norm, int dim,
                                                      const int* __restrict__ cand_idx, const float* __restrict__ cand_score,
                                                      const int* __restrict__ cand_cnt, int lists, long long nq, int k,
-                                                     long long g_index_base, int* __restrict__ out_idx, double* __restrict__ out_score) {
+                                                     long long g_index_base, int* __restrict__ out_idx, double* __restrict__ out_score,
+                                                     const CertParams cert) {
   pdl_grid_sync();
   extern __shared__ __align__(16) uint8_t sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -578,6 +603,113 @@ __global__ void __launch_bounds__(256, 3) rerank_kernel(const float* __restrict_
     out_idx[qi * k + i] = ok ? static_cast<int>(sel[i].idx + g_index_base) : -1;
     out_score[qi * k + i] = ok ? sel[i].score : -INFINITY;
   }
+  if (cert.uncert != nullptr) {
+    // a_cut: no dropped candidate had an approximate score above it
+    float a_cut = -INFINITY;
+    for (int c = lane; c < lists; c += 32) a_cut = fmaxf(a_cut, cert.list_tau[qi * lists + c]);
+    a_cut = warp_max(a_cut);
+    if (total > kKP) a_cut = fmaxf(a_cut, fkey_inv(static_cast<uint32_t>(thr >> 32)));
+    // q^ . mu: the constant the centring removed from every score of this query
+    double qmu = 0.0;
+    if (cert.center != nullptr) {
+#pragma unroll
+      for (int j = 0; j < kJ; ++j) {
+        const int d = lane * 4 + j * 128;
+        if (d < dim) {
+          const float4 m = __ldg(reinterpret_cast<const float4*>(cert.center + d));
+          qmu = fma(static_cast<double>(qa[j].x), static_cast<double>(m.x), qmu);
+          qmu = fma(static_cast<double>(qa[j].y), static_cast<double>(m.y), qmu);
+          qmu = fma(static_cast<double>(qa[j].z), static_cast<double>(m.z), qmu);
+          qmu = fma(static_cast<double>(qa[j].w), static_cast<double>(m.w), qmu);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) qmu += __shfl_xor_sync(0xffffffffu, qmu, o);
+      qmu /= nqd;
+    }
+    if (lane == 0 && a_cut > -INFINITY) {
+      // |Q~ . G~ - Q . G| <= |dQ_1||G_1| + |dQ_r||G_r| + |Q~_1||dG_1| + |Q~_r||dG_r| (first coordinate and the rest bounded
+      // separately: the query's first coordinate is O(1), everything else is of the size of the spread), plus the fp32
+      // accumulation of 512 products and the fp32 arithmetic that built the rows
+      const float* qe = cert.q_err + 4 * qi;
+      const double G1 = cert.g_stats[0], Gr = cert.g_stats[1], dG1 = cert.g_stats[2], dGr = cert.g_stats[3];
+      const double E = qe[0] * G1 + qe[1] * Gr + qe[2] * dG1 + qe[3] * dGr + 4e-5 * (qe[2] * G1 + qe[3] * Gr);
+      const bool proven = nsel >= k && static_cast<double>(a_cut) * cert.inv_scale + E < sel[k - 1].score - qmu;
+      if (!proven) cert.uncert[1 + atomicAdd(cert.uncert, 1)] = static_cast<int>(qi);
+    }
+  }
+}
+
+// Exact top-k of the queries the certificate could not prove: one CTA per such query scans the whole gallery with the re-rank's
+// own fp64 cosine (same summation order, so a row scores identically on both paths), keeping a pruned candidate buffer.
+constexpr int kExBlock = 1024;                    // gallery rows per round
+constexpr int kExCap = 2048;                      // candidate buffer (a round's survivors always fit behind the kept k)
+__global__ void __launch_bounds__(256) exact_topk_kernel(const float* __restrict__ q, const double* __restrict__ q_norm, const float* __restrict__ g,
+                                                         const double* __restrict__ g_norm, long long ng, int dim, int k, long long self_offset,
+                                                         int exclude_self, long long g_index_base, const int* __restrict__ uncert,
+                                                         int* __restrict__ out_idx, double* __restrict__ out_score) {
+  pdl_grid_sync();
+  __shared__ Cand buf[kExCap];
+  __shared__ int s_cnt;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_flag = uncert[0];
+  constexpr int kJ = kMaxKB * kBK / 128;
+  for (int f = blockIdx.x; f < n_flag; f += gridDim.x) {
+    const long long qi = uncert[1 + f];
+    const float* qr = q + qi * dim;
+    const double nqd = fmax(q_norm[qi], 1e-8);
+    float4 qa[kJ];
+#pragma unroll
+    for (int j = 0; j < kJ; ++j) {
+      const int d = lane * 4 + j * 128;
+      qa[j] = d < dim ? __ldg(reinterpret_cast<const float4*>(qr + d)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const long long self_row = exclude_self ? self_offset + qi : -1;
+    if (threadIdx.x == 0) s_cnt = 0;
+    Cand cut; cut.score = -INFINITY; cut.idx = INT_MAX; cut.pad = 0;       // keep only rows ranking ahead of `cut` once k are held
+    __syncthreads();
+    for (long long r0 = 0; r0 < ng; r0 += kExBlock) {
+      for (int rr = warp; rr < kExBlock; rr += 8) {
+        const long long row = r0 + rr;
+        if (row >= ng) break;
+        const float* gr = g + row * dim;
+        double a0 = 0.0;
+#pragma unroll
+        for (int j = 0; j < kJ; ++j) {
+          const int d = lane * 4 + j * 128;
+          if (d < dim) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(gr + d));
+            a0 = fma(static_cast<double>(qa[j].x), static_cast<double>(b.x), a0);
+            a0 = fma(static_cast<double>(qa[j].y), static_cast<double>(b.y), a0);
+            a0 = fma(static_cast<double>(qa[j].z), static_cast<double>(b.z), a0);
+            a0 = fma(static_cast<double>(qa[j].w), static_cast<double>(b.w), a0);
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+        if (lane == 0 && row != self_row) {
+          Cand c; c.score = a0 / (nqd * fmax(g_norm[row], 1e-8)); c.idx = static_cast<int>(row); c.pad = 0;
+          if (cand_before(c, cut)) buf[atomicAdd(&s_cnt, 1)] = c;
+        }
+      }
+      __syncthreads();
+      const int n = s_cnt;
+      if (n > kExCap - kExBlock || r0 + kExBlock >= ng) {          // CTA-uniform: sort, keep the best k, tighten the cut
+        for (int i = n + threadIdx.x; i < kExCap; i += blockDim.x) { buf[i].score = -INFINITY; buf[i].idx = INT_MAX; buf[i].pad = 0; }
+        __syncthreads();
+        bitonic_sort(buf, kExCap);
+        if (threadIdx.x == 0) s_cnt = min(n, k);
+        if (n >= k) cut = buf[k - 1];
+        __syncthreads();
+      }
+    }
+    const int n = s_cnt;
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+      out_idx[qi * k + i] = i < n ? static_cast<int>(buf[i].idx + g_index_base) : -1;
+      out_score[qi * k + i] = i < n ? buf[i].score : -INFINITY;
+    }
+    __syncthreads();
+  }
 }
 
 // merge `lists` pre-scored top lists per query ([lists][nq][k_in]) into one top-k_out
@@ -606,34 +738,156 @@ __global__ void __launch_bounds__(256) merge_kernel(const double* __restrict__ s
   }
 }
 
-// fp32 rows -> fp16 unit rows + fp64 norms (fixed summation order: lane-strided chains, xor tree)
-__global__ void __launch_bounds__(256) gallery_prepare_kernel(const float* __restrict__ x, __half* __restrict__ out, double* __restrict__ norm,
-                                                              long long n, int dim) {
+// fp32 rows -> fp16 rows + fp64 norms (fixed summation order: lane-strided chains, xor tree).  frame == null: plain unit
+// rows.  Otherwise frame = [mu (dim) | w (dim) | |mu|] (b200_gallery_frame) and y = H x^ = x^ - 2 w (w . x^):
+//   role 1 (gallery): row = scale * [y_1 - |mu|, y_2 ..]            role 0 (query): row = y
+// err[row] (nullable) = {|d_1|, |d_rest|, |row_1|, |row_rest|} of the fp16 row (d = fp16 - exact, unscaled); stats (nullable, 4
+// floats the caller zeroes): running maxima over the rows of {|row_1|, |row_rest|, |d_1|, |d_rest|}.
+__global__ void __launch_bounds__(256) gallery_prepare_kernel(const float* __restrict__ x, const float* __restrict__ frame, int role, float scale,
+                                                              __half* __restrict__ out, double* __restrict__ norm, float* __restrict__ err,
+                                                              float* __restrict__ stats, long long n, int dim) {
   pdl_grid_sync();
   const long long row = (1LL * blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= n) return;
   const float* xr = x + row * dim;
-  double ss = 0.0;
+  const float* mu = frame;
+  const float* w = frame != nullptr ? frame + dim : nullptr;
+  double ss = 0.0, wx = 0.0;
   for (int d = lane * 4; d < dim; d += 128) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(xr + d));
     ss = fma(static_cast<double>(v.x), static_cast<double>(v.x), ss);
     ss = fma(static_cast<double>(v.y), static_cast<double>(v.y), ss);
     ss = fma(static_cast<double>(v.z), static_cast<double>(v.z), ss);
     ss = fma(static_cast<double>(v.w), static_cast<double>(v.w), ss);
+    if (w != nullptr) {
+      const float4 ww = __ldg(reinterpret_cast<const float4*>(w + d));
+      wx = fma(static_cast<double>(v.x), static_cast<double>(ww.x), wx);
+      wx = fma(static_cast<double>(v.y), static_cast<double>(ww.y), wx);
+      wx = fma(static_cast<double>(v.z), static_cast<double>(ww.z), wx);
+      wx = fma(static_cast<double>(v.w), static_cast<double>(ww.w), wx);
+    }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  for (int o = 16; o > 0; o >>= 1) { ss += __shfl_xor_sync(0xffffffffu, ss, o); wx += __shfl_xor_sync(0xffffffffu, wx, o); }
   const double nr = sqrt(ss);
   if (lane == 0) norm[row] = nr;
-  const float inv = static_cast<float>(1.0 / fmax(nr, 1e-8));
+  const double invd = 1.0 / fmax(nr, 1e-8);
+  const float inv = static_cast<float>(invd);
+  const float two_wx = static_cast<float>(2.0 * wx * invd);                   // 2 (w . x^)
+  const double mu_norm = (frame != nullptr && role == 1) ? static_cast<double>(frame[2 * dim]) : 0.0;
+  float r1 = 0.f, r2 = 0.f, c1 = 0.f, c2 = 0.f;     // first coordinate: |d|, |value|; the rest: squared norms
   for (int d = lane * 4; d < dim; d += 128) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(xr + d));
+    float e[4] = {v.x * inv, v.y * inv, v.z * inv, v.w * inv};
+    if (w != nullptr) {
+      const float4 ww = __ldg(reinterpret_cast<const float4*>(w + d));
+      e[0] -= ww.x * two_wx; e[1] -= ww.y * two_wx; e[2] -= ww.z * two_wx; e[3] -= ww.w * two_wx;
+      if (d == 0) {       // the first coordinate carries the large numbers: y_1 = x^_1 - 2 w_1 (w . x^) and y_1 - |mu| in fp64
+        const double y1 = static_cast<double>(v.x) * invd - 2.0 * static_cast<double>(ww.x) * wx * invd;
+        e[0] = static_cast<float>(y1 - mu_norm);
+      }
+    }
+    const __half2 h0 = __floats2half2_rn(e[0] * scale, e[1] * scale), h1 = __floats2half2_rn(e[2] * scale, e[3] * scale);
     uint2 o;
-    o.x = pack_f16(v.x * inv, v.y * inv);
-    o.y = pack_f16(v.z * inv, v.w * inv);
+    o.x = *reinterpret_cast<const uint32_t*>(&h0);
+    o.y = *reinterpret_cast<const uint32_t*>(&h1);
     *reinterpret_cast<uint2*>(out + row * dim + d) = o;
+    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+    const float back[4] = {f0.x, f0.y, f1.x, f1.y};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float dlt = back[i] - e[i] * scale;
+      if (d == 0 && i == 0) { r1 = fabsf(dlt); c1 = fabsf(back[i]); }
+      else { r2 = fmaf(dlt, dlt, r2); c2 = fmaf(back[i], back[i], c2); }
+    }
   }
+  if (err != nullptr || stats != nullptr) {
+    r2 = warp_sum(r2);
+    c2 = warp_sum(c2);
+    r1 = __shfl_sync(0xffffffffu, r1, 0);
+    c1 = __shfl_sync(0xffffffffu, c1, 0);
+    // a little head-room for the fp32 evaluation of these norms themselves
+    const float is = 1.0f / scale;
+    const float d1 = r1 * is * 1.01f + 1e-12f, dr = sqrtf(r2) * is * 1.01f + 1e-12f;
+    const float v1 = c1 * is * 1.001f + 1e-12f, vr = sqrtf(c2) * is * 1.001f + 1e-12f;
+    if (lane == 0) {
+      if (err != nullptr) *reinterpret_cast<float4*>(err + 4 * row) = make_float4(d1, dr, v1, vr);
+      if (stats != nullptr) {                      // positive floats order like their bit patterns
+        unsigned int* st = reinterpret_cast<unsigned int*>(stats);
+        atomicMax(st + 0, __float_as_uint(v1)); atomicMax(st + 1, __float_as_uint(vr));
+        atomicMax(st + 2, __float_as_uint(d1)); atomicMax(st + 3, __float_as_uint(dr));
+      }
+    }
+  }
+}
+
+// frame of a gallery from its mean unit row: [mu | w | |mu|], w = (u - e_1) / |u - e_1| with u = mu / |mu| (H = I - 2 w w^T maps
+// u onto the first axis); one CTA, fp64 reductions
+__global__ void __launch_bounds__(256) gallery_frame_kernel(const float* __restrict__ mean, int dim, float* __restrict__ frame) {
+  pdl_grid_sync();
+  __shared__ double red[256];
+  double ss = 0.0;
+  for (int d = threadIdx.x; d < dim; d += blockDim.x) ss += static_cast<double>(mean[d]) * mean[d];
+  red[threadIdx.x] = ss;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o]; __syncthreads(); }
+  const double mn = sqrt(red[0]);
+  __syncthreads();
+  // v = u - e_1;  |v|^2 = 2 - 2 u_1
+  const double u1 = mn > 1e-12 ? mean[0] / mn : 1.0;
+  const double vn = sqrt(fmax(2.0 - 2.0 * u1, 0.0));
+  for (int d = threadIdx.x; d < dim; d += blockDim.x) {
+    frame[d] = mean[d];
+    double v = (mn > 1e-12 ? mean[d] / mn : (d == 0 ? 1.0 : 0.0)) - (d == 0 ? 1.0 : 0.0);
+    frame[dim + d] = vn > 1e-9 ? static_cast<float>(v / vn) : 0.f;
+  }
+  if (threadIdx.x == 0) frame[2 * dim] = static_cast<float>(mn);
+}
+
+// sum of the unit rows (for the centre mu = mean unit gallery row): one partial row per CTA, fixed order
+__global__ void __launch_bounds__(256) unit_row_sum_kernel(const float* __restrict__ x, float* __restrict__ partial, long long n, int dim,
+                                                           long long rows_per_block) {
+  pdl_grid_sync();
+  __shared__ float red[8][kMaxKB * kBK];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kJ = kMaxKB * kBK / 128;
+  float4 acc[kJ];
+#pragma unroll
+  for (int j = 0; j < kJ; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const long long r0 = rows_per_block * blockIdx.x, r1 = min(n, r0 + rows_per_block);
+  for (long long row = r0 + warp; row < r1; row += 8) {
+    const float* xr = x + row * dim;
+    float4 v[kJ];
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < kJ; ++j) {
+      const int d = lane * 4 + j * 128;
+      v[j] = d < dim ? __ldg(reinterpret_cast<const float4*>(xr + d)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      ss += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w;
+    }
+    ss = warp_sum(ss);
+    const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-8f);
+#pragma unroll
+    for (int j = 0; j < kJ; ++j) { acc[j].x += v[j].x * inv; acc[j].y += v[j].y * inv; acc[j].z += v[j].z * inv; acc[j].w += v[j].w * inv; }
+  }
+#pragma unroll
+  for (int j = 0; j < kJ; ++j) {
+    const int d = lane * 4 + j * 128;
+    if (d < dim) *reinterpret_cast<float4*>(&red[warp][d]) = acc[j];
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < dim; d += blockDim.x) {
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) a += red[w][d];
+    partial[1LL * blockIdx.x * dim + d] = a;
+  }
+}
+__global__ void scale_vec_kernel(float* v, int n, float f) {
+  pdl_grid_sync();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] *= f;
 }
 
 __global__ void recall_hits_kernel(const int* __restrict__ top_idx, long long nq, int k_stride, const long long* __restrict__ q_class,
@@ -681,7 +935,7 @@ __global__ void __launch_bounds__(256) pair_similarity_kernel(const float* __res
 }
 
 struct Layout {
-  long long scratch, cand_idx, cand_score, cand_cnt, tau, tau_shared, total;
+  long long scratch, cand_idx, cand_score, cand_cnt, list_tau, tau, tau_shared, total;
   int q_blocks, lists;
   long long witness_rows;      // rows [0, witness_rows) seed the thresholds (0 = single pass, unseeded)
   int chunks;                  // gallery chunks of the list pass
@@ -727,6 +981,7 @@ Layout plan_layout(long long nq, long long ng) {
   L.cand_idx = take(1LL * L.q_blocks * kBM * L.lists * kKP * 4);
   L.cand_score = take(1LL * L.q_blocks * kBM * L.lists * kKP * 4);
   L.cand_cnt = take(1LL * L.q_blocks * kBM * L.lists * 4);
+  L.list_tau = take(1LL * L.q_blocks * kBM * L.lists * 4);
   L.tau = take(1LL * L.q_blocks * kBM * 2 * 4);
   L.tau_shared = take(1LL * L.q_blocks * kBM * 4);
   L.total = off;
@@ -812,12 +1067,47 @@ int launch_filter(const CUtensorMap& tq, const CUtensorMap& tg, const CUtensorMa
 
 }  // namespace
 
-extern "C" int b200_gallery_prepare(const float* emb, void* unit_f16, double* norm, long long n, int dim, void* stream) {
+extern "C" int b200_gallery_prepare_ex(const float* emb, const float* frame, int role, float scale, void* f16_rows, double* norm, float* err,
+                                       float* stats, long long n, int dim, void* stream) {
   B200_REQUIRE(dim % 4 == 0, "gallery_prepare: dim must be a multiple of 4");
+  B200_REQUIRE(scale > 0.f && (role == 0 || role == 1), "gallery_prepare: scale must be positive, role 0 (query) or 1 (gallery)");
   if (n == 0) return B200_OK;
   const long long blocks = (n * 32 + 255) / 256;
-  launch_pdl(gallery_prepare_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
-      emb, reinterpret_cast<__half*>(unit_f16), norm, n, dim);
+  launch_pdl(gallery_prepare_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
+             emb, frame, role, scale, reinterpret_cast<__half*>(f16_rows), norm, err, stats, n, dim);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+extern "C" int b200_gallery_prepare(const float* emb, void* unit_f16, double* norm, long long n, int dim, void* stream) {
+  return b200_gallery_prepare_ex(emb, nullptr, 0, 1.0f, unit_f16, norm, nullptr, nullptr, n, dim, stream);
+}
+
+// frame [2 * dim + 1] floats from the mean unit gallery row (b200_unit_row_mean)
+extern "C" int b200_gallery_frame(const float* mean, int dim, float* frame, void* stream) {
+  B200_REQUIRE(dim % 4 == 0 && dim > 0, "gallery_frame: dim must be a positive multiple of 4");
+  launch_pdl(gallery_frame_kernel, dim3(1), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), mean, dim, frame);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+extern "C" int b200_unit_row_mean_blocks(long long n) {
+  const long long b = (n + 2047) / 2048;
+  return static_cast<int>(std::max<long long>(1, std::min<long long>(b, 4LL * b200_num_sms())));
+}
+
+// mean[d] = (1 / n) sum_rows x[row][d] / |x[row]|: the centre b200_gallery_prepare_ex subtracts.  partial: fp32
+// [b200_unit_row_mean_blocks(n)][dim] scratch.
+extern "C" int b200_unit_row_mean(const float* emb, long long n, int dim, float* mean, float* partial, void* stream) {
+  B200_REQUIRE(dim % 4 == 0 && dim <= kMaxKB * kBK && n > 0, "unit_row_mean: dim must be a multiple of 4, <= 512, n > 0");
+  auto st = reinterpret_cast<cudaStream_t>(stream);
+  const int blocks = b200_unit_row_mean_blocks(n);
+  const long long rpb = (n + blocks - 1) / blocks;
+  launch_pdl(unit_row_sum_kernel, dim3(blocks), dim3(256), 0, st, emb, partial, n, dim, rpb);
+  B200_LAUNCH_CHECK();
+  int rc = splitk_reduce(partial, mean, dim, blocks, 0, st, dim);
+  if (rc) return rc;
+  launch_pdl(scale_vec_kernel, dim3((dim + 255) / 256), dim3(256), 0, st, mean, dim, static_cast<float>(1.0 / static_cast<double>(n)));
   B200_LAUNCH_CHECK();
   return B200_OK;
 }
@@ -828,10 +1118,10 @@ extern "C" long long b200_cosine_topk_workspace_bytes(long long nq, long long ng
   return plan_layout(nq, ng).total;
 }
 
-extern "C" int b200_cosine_topk(const float* q, const void* q_unit_f16, const double* q_norm, long long nq, const float* g,
-                                const void* g_unit_f16, const double* g_norm, long long ng, int dim, int k,
-                                long long exclude_self_offset, long long g_index_base, int* out_idx, double* out_score,
-                                void* workspace, long long workspace_bytes, void* stream) {
+static int cosine_topk_impl(const float* q, const void* q_unit_f16, const double* q_norm, long long nq, const float* g,
+                            const void* g_unit_f16, const double* g_norm, long long ng, int dim, int k,
+                            long long exclude_self_offset, long long g_index_base, int* out_idx, double* out_score,
+                            void* workspace, long long workspace_bytes, CertParams cert, void* stream) {
   B200_REQUIRE(dim % 64 == 0 && dim >= 64 && dim <= 64 * kMaxKB, "cosine_topk: dim=%d must be a multiple of 64, <= 512", dim);
   B200_REQUIRE(k >= 1 && k <= kKP - 28, "cosine_topk: k=%d must be in [1, %d] (KP=%d candidates with 28 slack)", k, kKP - 28, kKP);
   B200_REQUIRE(ng < (1LL << 31) && nq < (1LL << 31), "cosine_topk: more than 2^31 rows");
@@ -856,6 +1146,8 @@ extern "C" int b200_cosine_topk(const float* q, const void* q_unit_f16, const do
   p.cand_idx = reinterpret_cast<int*>(ws + L.cand_idx);
   p.cand_score = reinterpret_cast<float*>(ws + L.cand_score);
   p.cand_cnt = reinterpret_cast<int*>(ws + L.cand_cnt);
+  p.list_tau = reinterpret_cast<float*>(ws + L.list_tau);
+  cert.list_tau = p.list_tau;
   L.ng = ng;
   L.tau_ptr = reinterpret_cast<float*>(ws + L.tau);
   p.tau_shared = reinterpret_cast<uint32_t*>(ws + L.tau_shared);
@@ -875,10 +1167,40 @@ extern "C" int b200_cosine_topk(const float* q, const void* q_unit_f16, const do
   const int smem2 = wpc * per_warp;
   B200_REQUIRE(per_warp <= 200 * 1024, "cosine_topk: too many candidate lists");
   if (smem2 > 48 * 1024) B200_CHECK_CUDA(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+  if (cert.uncert != nullptr) B200_CHECK_CUDA(cudaMemsetAsync(cert.uncert, 0, sizeof(int), st));
   launch_pdl(rerank_kernel, dim3(static_cast<unsigned>((nq + wpc - 1) / wpc)), dim3(32 * wpc), smem2, st, q, q_norm, g, g_norm, dim, p.cand_idx,
-             p.cand_score, p.cand_cnt, L.lists, nq, k, g_index_base, out_idx, out_score);
+             p.cand_score, p.cand_cnt, L.lists, nq, k, g_index_base, out_idx, out_score, cert);
   B200_LAUNCH_CHECK();
+  if (cert.uncert != nullptr) {
+    // the queries the certificate could not prove (normally none): exact scan; every CTA leaves at once when the list is empty
+    launch_pdl(exact_topk_kernel, dim3(static_cast<unsigned>(std::min<long long>(nq, 4LL * b200_num_sms()))), dim3(256), 0, st, q, q_norm, g, g_norm,
+               ng, dim, k, p.self_offset, p.exclude_self, g_index_base, cert.uncert, out_idx, out_score);
+    B200_LAUNCH_CHECK();
+  }
   return B200_OK;
+}
+
+extern "C" int b200_cosine_topk(const float* q, const void* q_unit_f16, const double* q_norm, long long nq, const float* g,
+                                const void* g_unit_f16, const double* g_norm, long long ng, int dim, int k,
+                                long long exclude_self_offset, long long g_index_base, int* out_idx, double* out_score,
+                                void* workspace, long long workspace_bytes, void* stream) {
+  return cosine_topk_impl(q, q_unit_f16, q_norm, nq, g, g_unit_f16, g_norm, ng, dim, k, exclude_self_offset, g_index_base, out_idx, out_score,
+                          workspace, workspace_bytes, CertParams{}, stream);
+}
+
+// b200_cosine_topk with the exactness certificate.  q_f16 / g_f16 = rows of b200_gallery_prepare_ex in the SAME frame (roles 0 /
+// 1; frame may be null for both = plain unit rows), q_err = the queries' err rows, g_stats = the maxima the gallery call
+// accumulated.  uncertified: int [1 + nq], receives the number of queries re-done by the exact scan and their indices.
+extern "C" int b200_cosine_topk_certified(const float* q, const void* q_f16, const double* q_norm, const float* q_err, long long nq,
+                                          const float* g, const void* g_f16, const double* g_norm, const float* frame, float g_scale,
+                                          const float* g_stats, long long ng, int dim, int k, long long exclude_self_offset,
+                                          long long g_index_base, int* out_idx, double* out_score, int* uncertified, void* workspace,
+                                          long long workspace_bytes, void* stream) {
+  B200_REQUIRE(q_err != nullptr && g_stats != nullptr && uncertified != nullptr && g_scale > 0.f, "cosine_topk_certified: missing certificate inputs");
+  CertParams cert{};
+  cert.center = frame; cert.q_err = q_err; cert.g_stats = g_stats; cert.inv_scale = 1.0f / g_scale; cert.uncert = uncertified;
+  return cosine_topk_impl(q, q_f16, q_norm, nq, g, g_f16, g_norm, ng, dim, k, exclude_self_offset, g_index_base, out_idx, out_score,
+                          workspace, workspace_bytes, cert, stream);
 }
 
 extern "C" int b200_topk_merge(const double* scores, const int* idx, long long nq, int lists, int k_in, int k_out, int* out_idx,

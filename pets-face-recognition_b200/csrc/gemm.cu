@@ -67,7 +67,10 @@ int b200_num_sms() {
 #include <vector>
 static std::atomic<long long> g_launches{0};
 static bool g_prof_gemm = false;
-struct GemmEv { cudaEvent_t a, b; double flops, bytes; };
+struct GemmEv { cudaEvent_t a, b; double flops, bytes; int kind; };
+constexpr int kProfKinds = 8;
+static double g_kind_ms[kProfKinds], g_kind_flops[kProfKinds], g_kind_bytes[kProfKinds];
+static long long g_kind_launches[kProfKinds];
 static std::vector<GemmEv> g_gemm_events;
 static std::vector<cudaEvent_t> g_event_pool;
 static double g_last_gemm_bytes = 0.0;
@@ -80,14 +83,14 @@ static cudaEvent_t take_event() {
   cudaEventCreate(&e);
   return e;
 }
-bool b200_prof_gemm_begin(cudaStream_t stream, double flops, double bytes) {
-  if (!g_prof_gemm) return false;
-  GemmEv ev{take_event(), take_event(), flops, bytes};
+bool b200_prof_kind_begin(cudaStream_t stream, int kind, double flops, double bytes) {
+  if (!g_prof_gemm || kind < 0 || kind >= kProfKinds) return false;
+  GemmEv ev{take_event(), take_event(), flops, bytes, kind};
   cudaEventRecord(ev.a, stream);
   g_gemm_events.push_back(ev);
   return true;
 }
-void b200_prof_gemm_end(cudaStream_t stream) { cudaEventRecord(g_gemm_events.back().b, stream); }
+void b200_prof_kind_end(cudaStream_t stream) { cudaEventRecord(g_gemm_events.back().b, stream); }
 
 extern "C" int b200_prof_begin(int time_gemm_launches) {
   g_launches.store(0);
@@ -101,16 +104,16 @@ extern "C" int b200_prof_begin(int time_gemm_launches) {
 extern "C" int b200_prof_end(double* gemm_ms, double* gemm_flops, long long* gemm_launches, long long* total_launches) {
   g_prof_gemm = false;
   B200_CHECK_CUDA(cudaDeviceSynchronize());
-  double ms = 0.0, fl = 0.0, by = 0.0;
+  for (int k = 0; k < kProfKinds; ++k) { g_kind_ms[k] = g_kind_flops[k] = g_kind_bytes[k] = 0.0; g_kind_launches[k] = 0; }
   for (auto& e : g_gemm_events) {
     float t = 0.f;
     B200_CHECK_CUDA(cudaEventElapsedTime(&t, e.a, e.b));
-    ms += t; fl += e.flops; by += e.bytes;
+    g_kind_ms[e.kind] += t; g_kind_flops[e.kind] += e.flops; g_kind_bytes[e.kind] += e.bytes; ++g_kind_launches[e.kind];
   }
-  if (gemm_ms) *gemm_ms = ms;
-  if (gemm_flops) *gemm_flops = fl;
-  g_last_gemm_bytes = by;
-  if (gemm_launches) *gemm_launches = static_cast<long long>(g_gemm_events.size());
+  if (gemm_ms) *gemm_ms = g_kind_ms[0];
+  if (gemm_flops) *gemm_flops = g_kind_flops[0];
+  g_last_gemm_bytes = g_kind_bytes[0];
+  if (gemm_launches) *gemm_launches = g_kind_launches[0];
   if (total_launches) *total_launches = g_launches.load();
   return B200_OK;
 }
@@ -119,6 +122,19 @@ extern "C" int b200_prof_end(double* gemm_ms, double* gemm_flops, long long* gem
 // b200_prof_end pair; call it after b200_prof_end.
 extern "C" int b200_prof_gemm_bytes(double* bytes) {
   if (bytes) *bytes = g_last_gemm_bytes;
+  return B200_OK;
+}
+
+// Per-kind totals of the launches timed by the last b200_prof_begin(1) .. b200_prof_end pair (call after b200_prof_end):
+// arrays of n_kinds entries indexed by B200_PROF_*.
+extern "C" int b200_prof_kernels(int n_kinds, double* ms, double* flops, double* bytes, long long* launches) {
+  B200_REQUIRE(n_kinds >= 1 && n_kinds <= kProfKinds, "prof_kernels: n_kinds must be in [1, %d]", kProfKinds);
+  for (int k = 0; k < n_kinds; ++k) {
+    if (ms) ms[k] = g_kind_ms[k];
+    if (flops) flops[k] = g_kind_flops[k];
+    if (bytes) bytes[k] = g_kind_bytes[k];
+    if (launches) launches[k] = g_kind_launches[k];
+  }
   return B200_OK;
 }
 
@@ -458,7 +474,11 @@ extern "C" int b200_reduce_pending(void) { return g_batch_on ? g_batch.n_jobs : 
 // launches the recorded reductions (one kernel) and leaves deferred mode; keep_deferring != 0 re-enters it right away
 extern "C" int b200_reduce_flush(void* stream, int keep_deferring) {
   if (g_batch_on && g_batch.n_jobs > 0) {
+    double by = 0.0;
+    for (int j = 0; j < g_batch.n_jobs; ++j) by += 4.0 * g_batch.job[j].ny * g_batch.job[j].n * (g_batch.job[j].splits + 1 + (g_batch.job[j].accumulate ? 1 : 0));
+    const bool prof = b200_prof_kind_begin(reinterpret_cast<cudaStream_t>(stream), B200_PROF_REDUCE, 0.0, by);
     launch_pdl(reduce_batch_kernel, dim3(static_cast<unsigned>(g_batch.n_blocks)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), g_batch);
+    if (prof) b200_prof_kind_end(reinterpret_cast<cudaStream_t>(stream));
     B200_LAUNCH_CHECK();
   }
   g_batch.n_jobs = 0;

@@ -124,3 +124,64 @@ def test_pair_similarity_and_device_metrics_match_host():
     assert fpr.is_cuda and M.stat_scores(scores, labels.cuda(), 0.6) == M.stat_scores(scores.cpu(), labels, 0.6)
     with pytest.raises(Exception):
         gallery.pair_similarity(emb.cuda(), torch.tensor([0, n]), torch.tensor([1, 2]))
+
+
+def _spec_fp64_gpu(q, g, k, excl=None, chunk=32768):
+    """oracle.rank_oracle.topk_spec on the GPU in fp64 (checker, not product): score = <q, g> / (max(|q|, 1e-8) max(|g|, 1e-8)),
+    order = (score desc, index asc) through a stable sort of index-ordered candidates."""
+    qd = q.double()
+    qn = qd.norm(dim=1).clamp_min(1e-8)
+    best_s = torch.zeros((q.shape[0], 0), dtype=torch.float64, device=q.device)
+    best_i = torch.zeros((q.shape[0], 0), dtype=torch.int64, device=q.device)
+    for lo in range(0, g.shape[0], chunk):
+        gd = g[lo:lo + chunk].double()
+        sc = (qd @ gd.t()) / (qn[:, None] * gd.norm(dim=1).clamp_min(1e-8)[None, :])
+        idx = torch.arange(lo, lo + gd.shape[0], device=q.device).expand(q.shape[0], -1)
+        if excl is not None:
+            sc = sc.masked_fill(idx == (torch.arange(q.shape[0], device=q.device) + excl)[:, None], float('-inf'))
+        sc, idx = torch.cat([best_s, sc], 1), torch.cat([best_i, idx], 1)
+        sc, order = torch.sort(sc, dim=1, descending=True, stable=True)
+        best_s, best_i = sc[:, :k].contiguous(), torch.gather(idx, 1, order[:, :k]).contiguous()
+    return best_i, best_s
+
+
+def test_near_duplicate_gallery_is_caught_by_the_certificate():
+    """300 gallery rows within 1e-6 of one another (augmented copies of one pet) sit far inside fp16
+    resolution, so the approximate pass cannot know which 100 of them are the true top-100.  The certificate must flag those
+    queries and the exact scan must return the specification's answer - bit-exact indices, not a silent near-miss."""
+    from b200 import gallery
+    gen = torch.Generator().manual_seed(5)
+    base = torch.nn.functional.normalize(torch.randn(4000, 512, generator=gen))
+    pet = torch.nn.functional.normalize(torch.randn(1, 512, generator=gen))
+    dup = pet + 1e-6 * torch.randn(300, 512, generator=gen)                  # 300 near-duplicates
+    g = torch.cat([base[:2000], dup, base[2000:]], 0).cuda()
+    q = torch.cat([pet + 1e-3 * torch.randn(8, 512, generator=gen), base[:56] + 0.05 * torch.randn(56, 512, generator=gen)], 0).cuda()
+    idx, score, unc = gallery.cosine_topk(q, g, 100, return_uncertified=True)
+    ref_i, ref_s = _spec_fp64_gpu(q, g, 100)
+    assert int(unc) >= 8                                                      # the 8 queries next to the duplicated pet
+    assert torch.equal(idx.long(), ref_i)
+    assert (score - ref_s).abs().max().item() < 1e-12
+    # the legacy, uncertified kernel pair on plain unit rows really does miss here (what the certificate is for)
+    legacy, _ = gallery.cosine_topk(q, g, 100, q_prepared=gallery.prepare(q), g_prepared=gallery.prepare(g))
+    assert not torch.equal(legacy.long()[:8], ref_i[:8])
+
+
+@pytest.mark.parametrize('spread,excl', [(0.02, None), (0.02, 0), (0.3, None)])
+def test_concentrated_embeddings_bit_exact_with_few_exact_scans(spread, excl):
+    """Embeddings of one domain are concentrated (random-init / early-training Swin outputs: cosines of 0.99 between
+    unrelated images).  Centring the fp16 gallery rows keeps the tensor-core pass discriminative there: indices stay
+    bit-exact and (almost) every query is certified without the exact scan."""
+    from b200 import gallery
+    gen = torch.Generator().manual_seed(11)
+    common = torch.nn.functional.normalize(torch.randn(1, 512, generator=gen))
+    g = torch.nn.functional.normalize(common + spread * torch.randn(60000, 512, generator=gen) / 512 ** 0.5).cuda()
+    q = (g[:3000].clone() if excl == 0 else torch.nn.functional.normalize(common + spread * torch.randn(3000, 512, generator=gen) / 512 ** 0.5).cuda())
+    if excl == 0:
+        g = torch.cat([q, g[3000:]], 0)
+    cos = (g[:1000] @ g[1000:2000].t())
+    assert cos.mean().item() > (0.999 if spread < 0.1 else 0.9)
+    idx, score, unc = gallery.cosine_topk(q, g, 100, exclude_self_offset=excl, return_uncertified=True)
+    ref_i, ref_s = _spec_fp64_gpu(q, g, 100, excl)
+    assert torch.equal(idx.long(), ref_i), f'{(idx.long() != ref_i).any(dim=1).sum().item()} queries differ'
+    print(f'spread {spread}: {int(unc)} of {q.shape[0]} queries took the exact scan')
+    assert int(unc) <= 0.02 * q.shape[0]
