@@ -135,18 +135,69 @@ def time_oracle_gpu_eager(device, batch=256, steps=3):
     return {'value': batch * steps / dt, 'unit': UNIT, 'sample': f'{steps} steps of batch {batch}, oracle/ port on the GPU (PyTorch eager, autocast bf16)'}
 
 
+def time_reference_modules(batch, warmup, steps):
+    """The UNMODIFIED reference modules (baseline/_ref: models/swin.py, losses/* copied from the reference by
+    __graft_entry__.install_reference) through the reference's own public API on the host cores: swin_t ->
+    SoftmaxBasedMetricLearning(arc_margin=True) forward, autograd backward, torch.optim.SGD with the groups of
+    configs/dog_fe/fe_dogs_config.py:123-133.  Raises ImportError if the copy is not there."""
+    ref = ROOT / 'baseline' / '_ref'
+    if not (ref / 'models' / 'swin.py').exists():
+        raise ImportError('baseline/_ref not installed (run __graft_entry__.build() where /root/reference exists)')
+    for name in [m for m in sys.modules if m == 'models' or m.startswith('models.') or m == 'losses' or m.startswith('losses.')]:
+        del sys.modules[name]
+    sys.path.insert(0, str(ref))
+    try:
+        import losses as ref_losses
+        import models as ref_models
+        assert str(ref) in ref_models.__file__ and str(ref) in ref_losses.__file__, 'reference modules shadowed'
+    finally:
+        sys.path.remove(str(ref))
+    from b200 import synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    model = ref_models.swin_t(num_classes=512)
+    sd = synth.synth_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, seed=123)
+    model.load_state_dict(sd, strict=True)
+    wrap = ref_losses.SoftmaxBasedMetricLearning(model, num_class=NUM_CLASS, embedding_size=512, is_focal=True, arc_margin=True)
+    wrap.add_margin.weight.data.copy_(synth.synth_tensor('add_margin.weight', (NUM_CLASS, 512), seed=123))
+    wrap.train()
+    params1 = [p for i, p in wrap.module.named_parameters() if 'fc' not in i]
+    params2 = [p for i, p in wrap.module.named_parameters() if 'fc' in i]
+    optim = torch.optim.SGD([{'lr': 10 ** -2 / 2, 'params': params1}, {'lr': 10 ** -2, 'params': params2},
+                             {'lr': 10 ** -2, 'params': wrap.add_margin.parameters(), 'weight_decay': 1 * (10 ** -4)}], 0.01, momentum=0.9)
+    img, label = synth.synth_images(batch, seed=123), synth.synth_labels(batch, NUM_CLASS, seed=123)
+
+    def step():
+        optim.zero_grad()
+        loss = wrap(img, label)['loss']
+        loss.backward()
+        optim.step()
+        return loss.item()
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        last = step()
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps, last
+
+
 def reference_arm(args, rank):
     if rank != 0:
         return
     batch = 8
-    ips, sec = time_oracle(batch, args.warmup, args.steps)
+    try:
+        ips, sec, _ = time_reference_modules(batch, args.warmup, args.steps)
+        kind, what = 'reference', 'the reference\'s own models/swin.py + losses/* (unmodified copy in baseline/_ref) + torch.optim.SGD'
+    except Exception as e:          # no copy of the reference on this box: the oracle port (pinned to it by tests/golden) stands in
+        ips, sec = time_oracle(batch, args.warmup, args.steps)
+        kind, what = 'port', f'oracle/ port (baseline/_ref unavailable: {type(e).__name__}: {str(e)[:80]})'
     cores = torch.get_num_threads()
     line = {'impl': 'reference', 'metric': METRIC, 'value': ips, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': f'dog-head FE train step, Swin-T + ArcFace(C={NUM_CLASS}) + SGD, CPU fp32, bounded sample: batch {batch} per step'},
-            'cpu_baseline': {'value': ips, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                             'sample': f'{args.steps} steps of batch {batch} after {args.warmup} warm-up, oracle/ port on {cores} threads'},
+            'cpu_baseline': {'value': ips, 'unit': UNIT, 'cores': cores, 'kind': kind,
+                             'sample': f'{args.steps} steps of batch {batch} after {args.warmup} warm-up, {what}, {cores} threads'},
             'e2e': {'value': ips, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     emit(line)
 
@@ -300,7 +351,9 @@ def gpu_arm(args, rank, world, local_rank):
     final_loss = float(loss.item())
 
     # ---- end to end through the public API: host batches, pinned staging + H2D every step, loss D2H every step
-    host_batches = [{'x': synth.synth_images(B, seed=2000 * rank + i), 'label': synth.synth_labels(B, NUM_CLASS, seed=2000 * rank + i)}
+    # the host batch is what a decoder hands over: uint8 pixels (38.5 MB per 256 images instead of 154 MB of floats);
+    # ToTensor's / 255 is fused into the first gather kernel (models/swin.py takes either dtype)
+    host_batches = [{'x': (synth.synth_images(B, seed=2000 * rank + i) * 255).to(torch.uint8), 'label': synth.synth_labels(B, NUM_CLASS, seed=2000 * rank + i)}
                     for i in range(2)]
     host_batches = [{k: v.pin_memory() for k, v in b.items()} for b in host_batches]
     h2d = sum(v.numel() * v.element_size() for v in host_batches[0].values())
@@ -332,6 +385,7 @@ def gpu_arm(args, rank, world, local_rank):
     gallery = gallery_leg(args, rank, world, device) if not args.no_gallery else None
     extract = extract_leg(args, wrap, dev_batches, world, device) if not args.no_gallery else None
     rows_f = rows_f_leg(device) if (world == 1 and not args.no_gallery) else None
+    pipeline = pipeline_leg(args, wrap, rank, world, device) if not args.no_gallery else None
 
     if rank != 0:
         return
@@ -352,7 +406,8 @@ def gpu_arm(args, rank, world, local_rank):
                                                       'each step streams > 10 GB of activations)',
                    'flops_per_image': train_flops_per_image(), 'final_loss': final_loss},
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
-                'api': 'engine.Trainer.train_batches(module, host_batches, optimizers)', 'h2d_pinned_gbps_this_box': h2d_gbps},
+                'api': 'engine.Trainer.train_batches(module, host_batches, optimizers)', 'h2d_pinned_gbps_this_box': h2d_gbps,
+                'host_batch': 'uint8 pixels [B, 3, 224, 224] + int64 labels in pinned memory (ToTensor / 255 fused into the first kernel)'},
         'gpu_launches': int(total_n.value),
         'roofline': {'bound': 'hbm' if hbm_bound else 'tensor',
                      'kernel': 'gemm::gemm_tn_kernel (tcgen05, all Linear fwd/dgrad/wgrad + ArcFace cosine)',
@@ -386,6 +441,8 @@ def gpu_arm(args, rank, world, local_rank):
     if gallery is not None:
         gallery['frac_of_peak'] = gallery['tflops'] / peak_tf if peak_tf else None
         line['gallery'] = gallery
+    if pipeline is not None:
+        line['pipeline'] = pipeline
     if world == 1 and not args.no_cpu_baseline:
         cb, steps_cb = 32, 2
         ips, _ = time_oracle(cb, 1, steps_cb)
@@ -428,6 +485,115 @@ def extract_leg(args, wrap, dev_batches, world, device):
     ms = t.item()
     return {'metric': 'FE extract images/sec (Swin-T forward, eval, bf16)', 'value': world * B / (ms * 1e-3), 'unit': 'images/s',
             'ms_per_batch': ms, 'batch_per_gpu': B, 'tflops': B * FWD_GFLOP * 1e9 / (ms * 1e-3) / 1e12, 'finite': bool(torch.isfinite(emb).all().item())}
+
+
+def _topk_spec_fp64_gpu(q, g, k, self_rows=None, chunk=32768):
+    """CHECKER (not product): oracle/rank_oracle.py:topk_spec evaluated in fp64 with torch on the GPU, gallery in chunks -
+    score = <q, g> / (max(|q|, 1e-8) max(|g|, 1e-8)), order = (score desc, index asc); self_rows[i] is excluded for query i."""
+    qd = q.double()
+    qn = qd.norm(dim=1).clamp_min(1e-8)
+    best_s = torch.zeros((q.shape[0], 0), dtype=torch.float64, device=q.device)
+    best_i = torch.zeros((q.shape[0], 0), dtype=torch.int64, device=q.device)
+    for lo in range(0, g.shape[0], chunk):
+        gd = g[lo:lo + chunk].double()
+        sc = (qd @ gd.t()) / (qn[:, None] * gd.norm(dim=1).clamp_min(1e-8)[None, :])
+        idx = torch.arange(lo, lo + gd.shape[0], device=q.device).expand(q.shape[0], -1)
+        if self_rows is not None:
+            sc = sc.masked_fill(idx == self_rows[:, None], float('-inf'))
+        sc, idx = torch.cat([best_s, sc], 1), torch.cat([best_i, idx], 1)
+        sc, order = torch.sort(sc, dim=1, descending=True, stable=True)
+        best_s, best_i = sc[:, :k].contiguous(), torch.gather(idx, 1, order[:, :k]).contiguous()
+    return best_i
+
+
+def pipeline_leg(args, wrap, rank, world, device):
+    """BASELINE.json configs[4]: the eval_fe pipeline end to end on all GPUs - Swin-T embedding extraction of every rank's
+    image shard, NCCL all-gather of the embeddings, leave-one-out candR@10 / candR@100 (engine/controller.py:77-91) with every
+    rank ranking its own queries against the whole set, counts all-reduced - plus parity: the top-100 lists of a 2,000-query
+    subsample bit-exact against an fp64 evaluation of the specification, and candR on that subsample equal.
+    Synthetic identities: two images per identity = one low-frequency pattern + pixel noise (uint8, resident in HBM)."""
+    import torch.distributed as dist
+    from b200 import gallery
+    n_img, B = args.pipeline_images, 256
+    n_img -= n_img % B
+    # seeded random-init weights, as BASELINE.json's configs ask (the `wrap` of the training legs has taken SGD steps on random
+    # labels by now, which collapses its embeddings onto one point: cos 0.9999995 between any two images)
+    wrap = build_model(NUM_CLASS, device)
+    g = torch.Generator(device=device).manual_seed(500 + rank)
+    n_id = n_img // 2
+    imgs = torch.empty(n_img, 3, 224, 224, device=device, dtype=torch.uint8)
+    for lo in range(0, n_id, 128):
+        m = min(128, n_id - lo)
+        base = torch.nn.functional.interpolate(torch.rand(m, 3, 7, 7, device=device, generator=g), size=224, mode='bilinear')
+        both = (base.repeat_interleave(2, 0) * 0.8 + 0.2 * torch.rand(2 * m, 3, 224, 224, device=device, generator=g)).clamp_(0, 1)
+        imgs[2 * lo:2 * (lo + m)] = (both * 255).to(torch.uint8)
+    classes_local = (torch.arange(n_img, device=device) // 2) + rank * n_id
+    was_training = wrap.training
+    wrap.eval()
+
+    def run():
+        emb = torch.empty(n_img, 512, device=device, dtype=torch.float32)
+        with torch.no_grad():
+            for lo in range(0, n_img, B):
+                emb[lo:lo + B] = wrap(imgs[lo:lo + B])
+        ev_x.record()
+        if world > 1:
+            emb_all, sizes = gallery._all_gather_rows(emb)
+            cls_all, _ = gallery._all_gather_rows(classes_local)
+            start = sum(sizes[:rank])
+        else:
+            emb_all, cls_all, start = emb, classes_local, 0
+        rows = torch.arange(start, start + n_img, device=device)
+        recall = gallery.recall_at_k_rows(emb_all, cls_all, rows, (10, 100))
+        return emb_all, cls_all, rows, recall
+    ev0, ev_x, ev1 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    run()                                                    # warm-up (plans, workspaces)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ev0.record()
+    emb_all, cls_all, rows, recall = run()
+    ev1.record()
+    torch.cuda.synchronize()
+    wrap.train(was_training)
+    t = torch.tensor([ev0.elapsed_time(ev_x), ev0.elapsed_time(ev1)], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_extract, ms_total = t.tolist()
+    # parity on a subsample of this rank's queries (checker: fp64 torch on the GPU; top-100 = integer work -> bit-exact)
+    sub = rows[torch.randperm(n_img, device=device, generator=g)[:2000]]
+    mask = torch.ones(emb_all.shape[0], dtype=torch.bool, device=device)
+    # same leave-one-out as the pipeline: the query's own row is excluded (here by score masking in the checker and by
+    # dropping it from the kernel's 101-candidate answer would change k, so the kernel is asked for the offset form)
+    order = torch.cat([sub, (mask.index_fill(0, sub, False)).nonzero().flatten()])
+    g_re = emb_all[order].contiguous()
+    idx_k, _, unc = gallery.cosine_topk(g_re[:sub.numel()], g_re, 100, exclude_self_offset=0, return_uncertified=True)
+    ref = _topk_spec_fp64_gpu(g_re[:sub.numel()], g_re, 100, self_rows=torch.arange(sub.numel(), device=device))
+    exact = bool(torch.equal(idx_k.long(), ref))
+    # where the lists differ: is it more than a tie at fp64 rounding level (two rows whose cosines agree to 1e-13 - their order
+    # depends on the summation order of the fp64 dot product, which the specification does not fix)?
+    diff = (idx_k.long() != ref)
+    beyond = 0
+    if diff.any():
+        qi, pos = diff.nonzero(as_tuple=True)
+        qd = g_re[qi].double()
+
+        def cos64(rows):
+            gd = g_re[rows].double()
+            return (qd * gd).sum(1) / (qd.norm(dim=1) * gd.norm(dim=1))
+        beyond = int(((cos64(idx_k.long()[qi, pos]) - cos64(ref[qi, pos])).abs() > 1e-13).sum().item())
+    c_re = cls_all[order]
+    hit_k = [(c_re[idx_k.long()[:, :k]] == c_re[:sub.numel(), None]).any(1).float().mean().item() for k in (10, 100)]
+    hit_r = [(c_re[ref[:, :k]] == c_re[:sub.numel(), None]).any(1).float().mean().item() for k in (10, 100)]
+    n_all = emb_all.shape[0]
+    cosm = (torch.nn.functional.normalize(emb_all[:2000]) @ torch.nn.functional.normalize(emb_all[2000:4000]).t()).mean().item() if n_all >= 4000 else None
+    return {'metric': 'eval_fe pipeline: Swin-T extract + all-gather + leave-one-out candR@10/100', 'images': n_all, 'images_per_gpu': n_img,
+            'identities': n_all // 2, 'seconds': ms_total * 1e-3, 'extract_images_per_s': n_all / (ms_extract * 1e-3),
+            'match_queries_per_s': n_all / ((ms_total - ms_extract) * 1e-3), 'images_per_s_end_to_end': n_all / (ms_total * 1e-3),
+            'candR@10': recall['Recall@K=10'], 'candR@100': recall['Recall@K=100'], 'mean_cosine_between_images': cosm,
+            'parity': {'checker': 'fp64 evaluation of oracle/rank_oracle.py:topk_spec on the GPU, 2,000 sampled queries x all rows',
+                       'top100_indices_bit_exact': exact, 'differences_beyond_fp64_rounding_ties': beyond, 'candR@10_kernel_vs_checker': [hit_k[0], hit_r[0]],
+                       'candR@100_kernel_vs_checker': [hit_k[1], hit_r[1]], 'queries_re_done_by_exact_scan': int(unc)}}
 
 
 def _folder_db(n_sets, seed, n_ids, prefix, dim=512):
@@ -570,6 +736,7 @@ def main():
     ap.add_argument('--no-gallery', action='store_true')
     ap.add_argument('--gallery-queries', type=int, default=50000)
     ap.add_argument('--gallery-rows', type=int, default=125000)
+    ap.add_argument('--pipeline-images', type=int, default=25600, help='images per GPU of the config-5 leg (extract + candR@10/100)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     rank = int(os.environ.get('RANK', 0))

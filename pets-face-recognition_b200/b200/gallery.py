@@ -149,6 +149,38 @@ def recall_at_k(emb: torch.Tensor, classes: torch.Tensor, ks: Iterable[int] = (1
     return {f'Recall@K={k}': (h / valid if valid else float('nan')) for k, h in zip(ks, hits)}
 
 
+def recall_at_k_rows(emb_all: torch.Tensor, classes_all: torch.Tensor, rows: torch.Tensor, ks: Iterable[int] = (10, 100), group=None):
+    """Leave-one-out Recall@K of the WHOLE set `emb_all` (present on every rank) with the queries split over the ranks: this
+    rank ranks emb_all[rows] against everything (each query skipping its own row), hit / valid counts are all-reduced.  The
+    queries are gathered into a contiguous block in front of the gallery so that leave-one-out is the kernel's offset form."""
+    import torch.distributed as dist
+    ks = list(ks)
+    n = emb_all.shape[0]
+    kmax = max(1, min(max(ks), 100, n - 1))
+    if max(ks) > 100:
+        raise abi.B200Error('Recall@K is built for K <= 100 (the reference uses 5, 10, 100)')
+    dev = emb_all.device
+    rows = rows.to(dev).long()
+    if rows.numel() > 0:
+        # gallery = [this rank's rows first, everything else after]: query i excludes gallery row i
+        mask = torch.ones(n, dtype=torch.bool, device=dev)
+        mask[rows] = False
+        order = torch.cat([rows, mask.nonzero().flatten()])
+        g, gc = emb_all[order].contiguous(), classes_all[order].contiguous()
+        idx = cosine_topk(g[:rows.numel()], g, kmax, exclude_self_offset=0)[0]
+        hits = recall_hits(idx, gc[:rows.numel()], gc, ks).to(torch.int64)
+        uniq, counts = torch.unique(classes_all, return_counts=True)
+        valid = ((counts[torch.searchsorted(uniq, gc[:rows.numel()])] - 1) > 0).sum().to(torch.int64)
+    else:
+        hits = torch.zeros(len(ks), dtype=torch.int64, device=dev)
+        valid = torch.zeros((), dtype=torch.int64, device=dev)
+    tot = torch.cat([hits, valid.reshape(1)])
+    if dist.is_available() and dist.is_initialized():
+        dist.all_reduce(tot, group=group)
+    tot = tot.tolist()
+    return {f'Recall@K={k}': (h / tot[-1] if tot[-1] else float('nan')) for k, h in zip(ks, tot[:-1])}
+
+
 # ---------------------------------------------------------------------------------------------------------
 # multi-GPU: one process per GPU, torch.distributed for the plumbing (NCCL on GPUs; gloo in the CPU tests)
 # ---------------------------------------------------------------------------------------------------------

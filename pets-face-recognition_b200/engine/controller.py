@@ -53,13 +53,32 @@ class Controller(torch.nn.Module):
 
     # ---- shared pieces
     @staticmethod
-    def _gather(outputs_i):
-        """:51-56 - concatenate the per-batch dicts and undo the loader order."""
+    def _world():
+        import torch.distributed as dist
+        return (dist.get_world_size(), dist.get_rank()) if (dist.is_available() and dist.is_initialized()) else (1, 0)
+
+    @classmethod
+    def _gather(cls, outputs_i):
+        """:51-56 - concatenate the per-batch dicts and undo the loader order.  Under DDP every rank holds the shard of the set
+        its Trainer extracted (engine/trainer.py:_shard_eval_loader): the shards are all-gathered over NCCL and put back into
+        dataset order, so everything below sees the whole set on every rank.  Returns (emb, classes, local) with `local` = the
+        positions of this rank's own rows in the whole set (None on one process)."""
         emb = torch.cat([j['emb'] for j in outputs_i], dim=0)
         classes = torch.cat([j['label'] for j in outputs_i], dim=0)
         indices = torch.cat([j['index'] for j in outputs_i], dim=0)
-        s = torch.argsort(indices)
-        return emb[s], classes[s]
+        world, rank = cls._world()
+        if world == 1:
+            s = torch.argsort(indices)
+            return emb[s], classes[s], None
+        dev = emb.device
+        emb_all, sizes = gallery._all_gather_rows(emb.float().contiguous())
+        cls_all, _ = gallery._all_gather_rows(classes.to(dev).long().contiguous())
+        idx_all, _ = gallery._all_gather_rows(indices.to(dev).long().contiguous())
+        s = torch.argsort(idx_all)
+        inv = torch.empty_like(s)
+        inv[s] = torch.arange(s.numel(), device=dev)
+        start = sum(sizes[:rank])
+        return emb_all[s], cls_all[s], inv[start:start + sizes[rank]]
 
     def _pair_scores(self, emb, i):
         """:60-68.  A config whose similarity_f is the reference's (cos + 1) / 2 says so with the function attribute
@@ -74,36 +93,44 @@ class Controller(torch.nn.Module):
         scores = self.config.similarity_f([(emb[id1], emb[id2]) for id1, id2 in pair_generator.corrected_indices])
         return name, scores.detach().float().cpu(), labels
 
-    def _recall_at_k(self, emb, classes, ks):
+    def _recall_at_k(self, emb, classes, ks, local=None):
         """engine/controller.py:77-91: leave-one-out ranking of every embedding against all others.  similarity_f in
-        every reference config is (cosine + 1) / 2, monotone in the cosine, so the fused cosine top-k ranks identically."""
+        every reference config is (cosine + 1) / 2, monotone in the cosine, so the fused cosine top-k ranks identically.
+        Under DDP (`local` = this rank's rows of the gathered set) every rank ranks only ITS queries against the whole set and
+        the hit / valid counts are all-reduced: BASELINE.json config 5."""
         ks = list(ks)
         if not ks:
             return {}
         dev = emb.device if emb.is_cuda else torch.device('cuda')
-        return gallery.recall_at_k(emb.to(dev).float(), classes.to(dev).long(), ks)
+        emb, classes = emb.to(dev).float(), classes.to(dev).long()
+        if local is None:
+            return gallery.recall_at_k(emb, classes, ks)
+        return gallery.recall_at_k_rows(emb, classes, local.to(dev), ks)
 
     # ---- test (engine/controller.py:48-93)
     def test_epoch_end(self, outputs) -> None:
         for i in range(len(outputs)):
-            emb, classes = self._gather(outputs[i])
+            emb, classes, local = self._gather(outputs[i])
             name, scores, labels = self._pair_scores(emb, i)
             fpr, tpr, thresholds = M.roc(scores, labels)
             metrics = {'ROC AUC': M.auroc(scores, labels),
                        'Accuracy': self.compute_accuracy(scores, labels, thresholds, fpr, 1 - tpr)}
-            metrics.update(self._recall_at_k(emb, classes, [10, 100]))
+            metrics.update(self._recall_at_k(emb, classes, [10, 100], local))
             self.last_metrics = metrics
-            print('', *[f'{name} {k}\t{v}' for k, v in metrics.items()], sep='\n')
+            if self._world()[1] == 0:
+                print('', *[f'{name} {k}\t{v}' for k, v in metrics.items()], sep='\n')
 
     # ---- validation (engine/controller.py:95-203)
     def _evaluate(self, outputs) -> None:
+        main = self._world()[1] == 0
         for i in range(len(outputs)):
-            emb, classes = self._gather(outputs[i])
+            emb, classes, local = self._gather(outputs[i])
             name, scores, labels = self._pair_scores(emb, i)
             fpr, tpr, thresholds = M.roc(scores, labels)
             opt_thr = thresholds[torch.argmin(fpr + 1 - tpr)].item()
             tp, fp, tn, fn = M.stat_scores(scores, labels, opt_thr)
-            print(name, f'\nConf Mat thr = {opt_thr}', torch.tensor([[tn, fp], [fn, tp]]))
+            if main:
+                print(name, f'\nConf Mat thr = {opt_thr}', torch.tensor([[tn, fp], [fn, tp]]))
             metrics = {'ROC AUC': M.auroc(scores, labels), 'AveragePrecision': M.average_precision(scores, labels),
                        'Accuracy': self.compute_accuracy(scores, labels, thresholds, fpr, 1 - tpr), 'Opt thr': opt_thr}
             for thr in self.config.thrs:
@@ -111,7 +138,7 @@ class Controller(torch.nn.Module):
                 metrics[f'Accuracy thr={thr}'] = (tp + tn) / max(1, tp + fp + tn + fn)
                 metrics[f'Precision thr={thr}'] = tp / max(1, tp + fp)
                 metrics[f'Recall thr={thr}'] = tp / max(1, tp + fn)
-            metrics.update(self._recall_at_k(emb, classes, self.config.k))
+            metrics.update(self._recall_at_k(emb, classes, self.config.k, local))
             sorted_scores, perm = torch.sort(scores)
             sorted_labels = labels[perm]
             neg_scores, pos_scores = sorted_scores[sorted_labels == 0], sorted_scores[sorted_labels == 1]
@@ -126,8 +153,9 @@ class Controller(torch.nn.Module):
                     metrics[f'TRR@FRR={frr_thr}'] = M.stat_scores(scores, labels, thr.item())[2] / max(1, len(neg_scores))
                     metrics[f'TH@FRR={frr_thr}'] = thr.item()
             self.last_metrics = metrics
-            print(*[f'{name} {k}\t{v}' for k, v in metrics.items()], sep='\n')
-            if self.logger is not None:
+            if main:
+                print(*[f'{name} {k}\t{v}' for k, v in metrics.items()], sep='\n')
+            if self.logger is not None and main:
                 self.logger.log_metrics({f'{name} {k}': v for k, v in metrics.items()}, self.current_epoch)
 
     @staticmethod

@@ -212,6 +212,29 @@ class Trainer:
                     self._comm_stream.wait_event(ev)
                     dist.all_reduce(flat_grad[begin:end])
             eng.grad_hook = hook
+        # parameters outside the native engines (the ArcFace / CosFace weight, 20 MB at C = 10,000): their gradient is the
+        # FIRST thing backward produces, so its all-reduce is launched from a post-accumulate hook and runs under the whole
+        # backbone backward instead of after it
+        covered = set()
+        for eng in engines:
+            covered.update(id(p) for p in eng.params)
+        self._early_reduced = set()
+        for prm in module.parameters():
+            if prm.requires_grad and id(prm) not in covered and not getattr(prm, '_b200_ddp_hook', False):
+                def early(param):
+                    if param.grad is None:
+                        return
+                    if self._comm_stream is None:
+                        dist.all_reduce(param.grad)
+                    else:
+                        ev = torch.cuda.Event()
+                        ev.record()
+                        with torch.cuda.stream(self._comm_stream):
+                            self._comm_stream.wait_event(ev)
+                            dist.all_reduce(param.grad)
+                    self._early_reduced.add(id(param))
+                prm.register_post_accumulate_grad_hook(early)
+                prm._b200_ddp_hook = True
         return engines
 
     def run_training_batch(self, module, batch, optimizers) -> torch.Tensor:
@@ -226,7 +249,9 @@ class Trainer:
             for m in module.modules():
                 if hasattr(m, '_engine') and m._engine is not None and m._engine.last_flat_grad is not None:
                     covered.update(id(p) for p in m._engine.params)
-            rest = [p.grad for p in module.parameters() if p.grad is not None and id(p) not in covered]
+            early = getattr(self, '_early_reduced', set())
+            rest = [p.grad for p in module.parameters() if p.grad is not None and id(p) not in covered and id(p) not in early]
+            self._early_reduced = set()
             if self._comm_stream is not None:
                 ev = torch.cuda.Event(); ev.record()
                 with torch.cuda.stream(self._comm_stream):
@@ -287,9 +312,35 @@ class Trainer:
             return list(cfg), []
         return [cfg], []
 
+    def _shard_eval_loader(self, loader):
+        """Evaluation under DDP: rank r takes samples r, r + world, ... of the loader's dataset (no padding, no duplicates -
+        a repeated sample would count twice in Recall@K); Controller.*_epoch_end gathers the shards again."""
+        if self.world_size == 1:
+            return loader
+        from torch.utils.data import DataLoader, Sampler
+
+        class _Strided(Sampler):
+            def __init__(self, n, rank, world):
+                self.idx = list(range(rank, n, world))
+
+            def __iter__(self):
+                return iter(self.idx)
+
+            def __len__(self):
+                return len(self.idx)
+        if not isinstance(loader, DataLoader) or loader.batch_size is None:
+            return loader
+        kw = dict(batch_size=loader.batch_size, sampler=_Strided(len(loader.dataset), self.rank, self.world_size),
+                  num_workers=loader.num_workers, collate_fn=loader.collate_fn, pin_memory=loader.pin_memory, drop_last=False,
+                  timeout=loader.timeout, worker_init_fn=loader.worker_init_fn)
+        if loader.num_workers > 0:
+            kw.update(prefetch_factor=loader.prefetch_factor, persistent_workers=loader.persistent_workers)
+        return DataLoader(loader.dataset, **kw)
+
     def _run_eval(self, module, dataloaders, step_name: str, limit=None):
         if not isinstance(dataloaders, (list, tuple)):
             dataloaders = [dataloaders]
+        dataloaders = [self._shard_eval_loader(dl) for dl in dataloaders]
         was_training = module.training
         module.eval()
         outputs = []
@@ -353,7 +404,8 @@ class Trainer:
                 print(f'epoch {epoch}: loss {last.item():.4f}  {n_img / max(dt, 1e-9):.1f} img/s')
                 if self.logger is not None and hasattr(self.logger, 'log_metrics'):
                     self.logger.log_metrics({'train_loss': last.item()}, epoch)
-            if (epoch + 1) % self.check_val_every_n_epoch == 0 and self.rank == 0:
+            if (epoch + 1) % self.check_val_every_n_epoch == 0:
+                # every rank extracts its shard of the validation set; the Controller gathers and ranks (rank 0 prints)
                 outputs = self._run_eval(module, module.val_dataloader(), 'validation_step', self.limit_val_batches)
                 module.validation_epoch_end(outputs)
             if self.world_size > 1:

@@ -138,8 +138,8 @@ def test_controller_gather_restores_dataset_order():
     emb = torch.arange(12.).reshape(6, 2)
     perm = torch.tensor([4, 1, 5, 0, 3, 2])
     outs = [{'emb': emb[perm[:3]], 'label': perm[:3] * 10, 'index': perm[:3]}, {'emb': emb[perm[3:]], 'label': perm[3:] * 10, 'index': perm[3:]}]
-    e, c = Controller._gather(outs)
-    assert torch.equal(e, emb) and torch.equal(c, torch.arange(6) * 10)
+    e, c, local = Controller._gather(outs)
+    assert torch.equal(e, emb) and torch.equal(c, torch.arange(6) * 10) and local is None       # one process: no shard bookkeeping
     sc, lab = torch.tensor([0.9, 0.8, 0.3, 0.2]), torch.tensor([1, 1, 0, 0])
     from engine import metrics as M
     fpr, tpr, thr = M.roc(sc, lab)
@@ -258,3 +258,58 @@ def test_ddp_train_loader_is_sharded_by_rank_world2_gloo(tmp_path):
             assert len(ra) == len(rb) == 8 and not set(ra) & set(rb)          # 11 per rank -> 2 full batches of 4, disjoint shards
         assert (a[shuffle][0] != a[shuffle][1]) == shuffle                      # set_epoch reshuffles; sequential order is fixed
     assert a[False][0] == [0, 2, 4, 6, 8, 10, 12, 14]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def _eval_worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path[:0] = [str(ROOT), str(PKG)]
+    import torch.distributed as dist
+    from torch.utils.data import DataLoader, Dataset
+    from b200 import gallery, synth
+    from engine import Controller, Trainer
+    from oracle import rank_oracle
+    tr = Trainer(gpus=0, strategy='ddp')
+    emb, classes = synth.synth_embeddings(9, 3, sigma=3.0, seed=21)           # 27 rows: ragged over 2 ranks (14 / 13)
+
+    class DS(Dataset):
+        def __len__(self):
+            return emb.shape[0]
+
+        def __getitem__(self, i):
+            return {'emb': emb[i], 'label': classes[i], 'index': i}
+    dl = tr._shard_eval_loader(DataLoader(DS(), batch_size=4, shuffle=False))
+    outs = [b for b in dl]
+    mine = torch.cat([b['index'] for b in outs])
+    assert mine.tolist() == list(range(rank, 27, world))                       # strided shard, no padding / duplicates
+    e_all, c_all, local = Controller._gather(outs)
+    assert torch.equal(e_all, emb) and torch.equal(c_all, classes) and torch.equal(local, mine)     # whole set, dataset order, own rows
+
+    # recall_at_k_rows with the oracle standing in for the kernels (host logic: reorder / offsets / all-reduce)
+    def topk(q, g, k, exclude_self_offset=None, **_):
+        return torch.from_numpy(rank_oracle.topk_spec(q.numpy(), g.numpy(), k, exclude_self_offset=exclude_self_offset)[0]), None
+
+    def hits(idx, qc, gc, ks):
+        first = [next((j for j, i in enumerate(row.tolist()) if i >= 0 and gc[i] == c), 10 ** 9) for row, c in zip(idx, qc.tolist())]
+        return torch.tensor([sum(f < k for f in first) for k in ks])
+    gallery.cosine_topk, gallery.recall_hits = topk, hits
+    r = gallery.recall_at_k_rows(e_all, c_all, local, (2, 5))
+    torch.save(r, Path(tmp) / f'r{rank}.pt')
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_eval_gather_and_recall_world2_gloo(tmp_path):
+    """BASELINE.json config 5 host logic: strided evaluation shards, all-gather back into dataset order, every rank ranks its own
+    queries, counts all-reduced == the reference loop over the whole set."""
+    import torch.multiprocessing as mp
+    from b200 import synth
+    from oracle import rank_oracle
+    port = 33500 + (os.getpid() % 2000)
+    mp.spawn(_eval_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a, b = (torch.load(tmp_path / f'r{r}.pt', weights_only=False) for r in range(2))
+    emb, classes = synth.synth_embeddings(9, 3, sigma=3.0, seed=21)
+    full = rank_oracle.recall_at_k_loop(emb, classes, (2, 5))
+    assert a == b
+    for k in (2, 5):
+        assert a[f'Recall@K={k}'] == pytest.approx(full[f'Recall@K={k}'], abs=1e-12)
