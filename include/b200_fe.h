@@ -124,6 +124,20 @@ int b200_patch_gather_image_u8(const unsigned char* img_nchw, void* cols, int B,
                               void* stream); /* uint8 pixels, ToTensor's /255 fused */
 int b200_patch_gather_nhwc(void* x_nhwc, void* cols, int B, int H, int W, int C, int backward, void* stream);
 
+/* ---- training augmentation of configs/dog_fe/fe_dogs_config.py:17-26 on a uint8 batch in HBM: sharpness 0 (ImageFilter.SMOOTH),
+ *      autocontrast, crop, PIL's two-pass fixed-point bilinear resize, nearest-neighbour rotation (fill 0) - PIL's own integer /
+ *      float32 arithmetic, so equal random draws give equal bytes.  params_dev: one B200AugParams per image (device memory);
+ *      coef_dev: int [S][4] = first source index + three 22-bit fixed-point bilinear weights of the crop -> S resize (16-B aligned);
+ *      minmax_scratch: B * 6 bytes.  The result stays uint8: b200_swin_forward takes it as it is (x / 255 fused). ----------------- */
+typedef struct B200AugParams {
+  int sharpen;       /* RandomAdjustSharpness(0, p) fired  */
+  int autocontrast;  /* RandomAutocontrast(p) fired        */
+  int crop_y, crop_x;
+  int rot[6];        /* PIL's affine walk of the rotation in 16.16 fixed point: x step, y step, origin for xin (0..2) and yin (3..5) */
+} B200AugParams;
+int b200_augment_train(const unsigned char* in_nchw, unsigned char* out_nchw, const B200AugParams* params_dev, const int* coef_dev, int B,
+                       int H, int W, int crop, int S, unsigned char* minmax_scratch, void* stream);
+
 /* ---- x.mean(dim=[2,3]) (models/swin.py:224) and its backward -------------------------------------------------- */
 int b200_mean_pool(const void* in, void* out, int B, int T, int C, int backward, void* stream);
 

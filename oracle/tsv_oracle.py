@@ -79,3 +79,55 @@ def synth_db(n_sets: int, dim: int, seed: int, n_ids: int, prefix: str, max_vec:
         vecs = [(centres[ident] + noise * torch.randn(dim, generator=g)).reshape((dim,) if flat else (1, dim)) for _ in range(nvec)]
         db[f'{prefix}{s:04d}'] = {'head_vectors': vecs, 'type': 1 + ident % 2}
     return db
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Head + body ensemble (generate_tsv_to_reproduce1.py of the reference)
+# ---------------------------------------------------------------------------------------------------------------------
+ENSEMBLE_THRESHOLDS = (0.9069641, 0.985643)          # generate_tsv_to_reproduce1.py:106, indexed by type - 1 (dog, cat)
+
+
+def calc_scores_ensemble(init_db: Dict[str, Any], extra_db: Dict[str, Any], top: int = 100) -> List[tuple]:
+    """generate_tsv_to_reproduce1.py:88-120.  Every folder carries 'head_vectors' AND 'body_vectors'.  Per (enroll, verify)
+    pair of the same type: s0 = mean-strategy score of the head sets (0 if either is empty), s1 = the same for the body sets;
+    pairs with s0 + s1 == 0 are skipped; the pair's score is s1 if the enroll folder has no head vector, or if s0 == 0 and s1
+    exceeds the type's threshold - else s0 (:106-107).  Then as calc_scores: stable descending sort, first 100 names,
+    matched_1 / 3 / 10."""
+    rows = []
+    for name, enroll in init_db.items():
+        v1, v1_body = enroll['head_vectors'], enroll['body_vectors']
+        ranked = []
+        for name2, verify in extra_db.items():
+            if verify['type'] != enroll['type']:
+                continue
+            s0 = mean_strategy(v1, verify['head_vectors']) if (len(v1) != 0 and len(verify['head_vectors']) != 0) else 0
+            s1 = mean_strategy(v1_body, verify['body_vectors']) if (len(v1_body) != 0 and len(verify['body_vectors']) != 0) else 0
+            if s0 + s1 == 0:
+                continue
+            score = s1 if len(v1) == 0 or (s0 == 0 and s1 > ENSEMBLE_THRESHOLDS[enroll['type'] - 1]) else s0
+            ranked.append((name2, score))
+        ranked = sorted(ranked, key=lambda x: x[1], reverse=True)
+        if ranked:
+            answer = [ranked[i][0] for i in range(min(top, len(ranked)))]
+            rows.append((str(name), ranked[0][1], float(np.mean([ranked[i][1] for i in range(3)])),
+                         float(np.mean([ranked[i][1] for i in range(10)])), ','.join(answer)))
+    return rows
+
+
+def synth_db_ensemble(n_sets: int, dim: int, seed: int, n_ids: int, prefix: str, max_vec: int = 3, noise: float = 0.15, flat: bool = True):
+    """synth_db with a second, independent 'body_vectors' set per folder.  Low noise: body scores of matching identities clear
+    the ensemble thresholds (0.907 / 0.986), so every branch of the rule is taken; some folders have no head, some no body."""
+    g = torch.Generator().manual_seed(seed)
+    head_c = torch.randn(n_ids, dim, generator=torch.Generator().manual_seed(12345))
+    body_c = torch.randn(n_ids, dim, generator=torch.Generator().manual_seed(54321))
+    db = {}
+    for s in range(n_sets):
+        ident = s % n_ids
+        nh = int(torch.randint(0, max_vec + 1, (1,), generator=g).item())
+        nb = int(torch.randint(0, max_vec + 1, (1,), generator=g).item())
+        shape = (dim,) if flat else (1, dim)
+        db[f'{prefix}{s:04d}'] = {
+            'head_vectors': [(head_c[ident] + noise * torch.randn(dim, generator=g)).reshape(shape) for _ in range(nh)],
+            'body_vectors': [(body_c[ident] + (0.05 if s % 3 else noise) * torch.randn(dim, generator=g)).reshape(shape) for _ in range(nb)],
+            'type': 1 + ident % 2}
+    return db

@@ -33,6 +33,10 @@ class OptTensor(C.Structure):
                 ('eps', c_float), ('step', c_int)]
 
 
+class AugParams(C.Structure):
+    _fields_ = [('sharpen', c_int), ('autocontrast', c_int), ('crop_y', c_int), ('crop_x', c_int), ('rot', c_int * 6)]
+
+
 # name -> (restype, argtypes); mirrors include/b200_fe.h line by line
 _PROTOS = {
     'b200_last_error': (C.c_char_p, []),
@@ -59,6 +63,7 @@ _PROTOS = {
     'b200_patch_gather_image': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_ll, c_vp]),
     'b200_patch_gather_image_u8': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_ll, c_vp]),
     'b200_patch_gather_nhwc': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    'b200_augment_train': (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     'b200_mean_pool': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]),
     'b200_transpose16': (c_int, [c_vp, c_vp, c_ll, c_int, c_ll, c_ll, c_vp]),
     'b200_cast_transpose': (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_vp]),

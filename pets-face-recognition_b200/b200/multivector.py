@@ -36,12 +36,12 @@ def _layout_of(db_list: Sequence[Dict[Any, Any]]) -> str:
     return 'flat'
 
 
-def set_means(db: Dict[Any, Any], layout: str, device) -> Tuple[List[Any], torch.Tensor, torch.Tensor, torch.Tensor]:
+def set_means(db: Dict[Any, Any], layout: str, device, field: str = 'head_vectors') -> Tuple[List[Any], torch.Tensor, torch.Tensor, torch.Tensor]:
     """names, types [n] (int64), counts [n] (int64), mean of u(v) per folder [n, D] fp32 on `device` (zeros for empty sets)."""
     names = list(db.keys())
     types = torch.tensor([int(db[n]['type']) for n in names], dtype=torch.int64, device=device)
-    counts = torch.tensor([len(db[n]['head_vectors']) for n in names], dtype=torch.int64, device=device)
-    vecs = [v.reshape(-1) for n in names for v in db[n]['head_vectors']]
+    counts = torch.tensor([len(db[n][field]) for n in names], dtype=torch.int64, device=device)
+    vecs = [v.reshape(-1) for n in names for v in db[n][field]]
     if not vecs:
         return names, types, counts, torch.zeros(len(names), 0, device=device)
     x = torch.stack(vecs).to(device=device, dtype=torch.float32)
@@ -115,6 +115,81 @@ def calc_scores(init_db: Dict[Any, Any], extra_db: Dict[Any, Any], strategy: str
     return [rows[i] for i in sorted(rows)]
 
 
+def _dense_dot(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """a [n, D] . b [m, D]^T to ~fp32 accuracy on the fp16 tensor-core GEMM: x = hi + lo with hi = fp16(x), lo = fp16(2^11 (x - hi));
+    a . b = hi.hi + 2^-11 (hi.lo + lo.hi) (the lo.lo term is below 2^-22).  Two launches of the tcgen05 GEMM with fp32 output;
+    the second contracts over the concatenation [a_hi | a_lo] x [b_lo | b_hi]."""
+    n, m = a.shape[0], b.shape[0]
+    pad_n, pad_m = (-n) % 8, (-m) % 8
+
+    def split(x, pad):
+        if pad:
+            x = torch.cat([x, torch.zeros(pad, x.shape[1], device=x.device, dtype=x.dtype)])
+        hi = x.to(torch.float16)
+        lo = ((x - hi.float()) * 2048.0).to(torch.float16)
+        return hi.contiguous(), lo.contiguous()
+    ah, al = split(a, pad_n)
+    bh, bl = split(b, pad_m)
+    main = ops.gemm_tn(ah, bh, out_fp32=True)
+    corr = ops.gemm_tn(torch.cat([ah, al], 1).contiguous(), torch.cat([bl, bh], 1).contiguous(), out_fp32=True)
+    return (main + corr * (1.0 / 2048.0))[:n, :m]
+
+
+ENSEMBLE_THRESHOLDS = (0.9069641, 0.985643)      # generate_tsv_to_reproduce1.py:106, by pet type (1 = dog, 2 = cat)
+
+
+def calc_scores_ensemble(init_db: Dict[Any, Any], extra_db: Dict[Any, Any], top: int = 100, layout: Optional[str] = None,
+                         strict: bool = True, thresholds=ENSEMBLE_THRESHOLDS, device='cuda') -> List[tuple]:
+    """Head + body ensemble of generate_tsv_to_reproduce1.py:88-120 for a whole table at once.  Per (enroll, verify) pair of one
+    pet type: s0 / s1 = the mean-strategy scores of the head / body sets (0 when either set is empty); pairs with s0 + s1 == 0 are
+    skipped; the score is s1 when the enroll folder has no head vector or (s0 == 0 and s1 > thresholds[type - 1]), else s0.
+    The rule is not separable, so both [enroll x verify] score tables are formed densely - two set-mean products on the tcgen05
+    GEMM at split precision (_dense_dot) - combined element-wise on the device and ranked with a stable sort (ties keep the
+    verify order, as the reference's sorted() does)."""
+    abi.require_device()
+    layout = layout or _layout_of([init_db, extra_db])
+    device = torch.device(device)
+    qn, qt, qh, qhm = set_means(init_db, layout, device, 'head_vectors')
+    _, _, qb, qbm = set_means(init_db, layout, device, 'body_vectors')
+    gn, gt, gh, ghm = set_means(extra_db, layout, device, 'head_vectors')
+    _, _, gb, gbm = set_means(extra_db, layout, device, 'body_vectors')
+    rows: Dict[int, tuple] = {}
+    for t in sorted(set(qt.tolist()) & set(gt.tolist())):
+        qsel = torch.nonzero(qt == t).flatten()
+        gsel = torch.nonzero(gt == t).flatten()
+        if qsel.numel() == 0 or gsel.numel() == 0:
+            continue
+
+        def table(qm, qc, gm, gc):
+            if qm.shape[1] == 0 or gm.shape[1] == 0:
+                return torch.zeros(qsel.numel(), gsel.numel(), device=device)
+            sc = ((_dense_dot(qm[qsel].contiguous(), gm[gsel].contiguous()) + 1.0) / 2.0).clamp_min(0.0)
+            have = (qc[qsel] > 0).unsqueeze(1) & (gc[gsel] > 0).unsqueeze(0)
+            return torch.where(have, sc, torch.zeros_like(sc))
+        s0, s1 = table(qhm, qh, ghm, gh), table(qbm, qb, gbm, gb)
+        thr = float(thresholds[int(t) - 1])
+        use_body = (qh[qsel] == 0).unsqueeze(1) | ((s0 == 0) & (s1 > thr))
+        score = torch.where(use_body, s1, s0)
+        listed = (s0 + s1) != 0
+        score = torch.where(listed, score, torch.full_like(score, -1.0))
+        sc_sorted, order = torch.sort(score, dim=1, descending=True, stable=True)
+        n_listed = listed.sum(1)
+        if strict and bool(((n_listed > 0) & (n_listed < 10)).any()):
+            raise IndexError('list index out of range')      # the reference's np.mean([l[i][1] for i in range(10)])
+        k = min(max(top, 10), int(gsel.numel()))
+        sc_sorted, order, n_listed = sc_sorted[:, :k].cpu(), order[:, :k].cpu(), n_listed.cpu()
+        gsel_l = gsel.tolist()
+        for r, qi in enumerate(qsel.tolist()):
+            n = min(int(n_listed[r]), k)
+            if n == 0:
+                continue
+            sc = sc_sorted[r, :n].tolist()
+            names = [gn[gsel_l[j]] for j in order[r, :n].tolist()]
+            rows[qi] = (str(getattr(qn[qi], 'name', qn[qi])), sc[0], sum(sc[:3]) / len(sc[:3]), sum(sc[:10]) / len(sc[:10]),
+                        ','.join(str(getattr(nm, 'name', nm)) for nm in names[:top]))
+    return [rows[i] for i in sorted(rows)]
+
+
 def _max_strategy_topk(init_db, extra_db, qn, gn, qsel, gsel, layout, k, device):
     """max_strategy_cal_scores (:80-87): best pair of every (enroll, verify) folder pair.  Not bilinear, so the all-pairs
     score matrix of the member vectors is formed (tcgen05 GEMM on unit rows) and folded by a segmented max."""
@@ -143,12 +218,13 @@ def _max_strategy_topk(init_db, extra_db, qn, gn, qsel, gsel, layout, k, device)
     return idx[:, :k].to(torch.int32), score[:, :k]
 
 
-def create_table(db: Dict[Any, Tuple[Dict[Any, Any], Dict[Any, Any]]], **kw):
-    """:123-136: one calc_scores per big folder, rows concatenated into a DataFrame with the submission's columns."""
+def create_table(db: Dict[Any, Tuple[Dict[Any, Any], Dict[Any, Any]]], ensemble: bool = False, **kw):
+    """:123-136: one calc_scores per big folder, rows concatenated into a DataFrame with the submission's columns.
+    ensemble: the head + body rule of generate_tsv_to_reproduce1.py instead of the head-only scoring of script 2."""
     import pandas as pd
     rows: List[tuple] = []
     for big_folder in db:
-        rows.extend(calc_scores(*db[big_folder], **kw))
+        rows.extend((calc_scores_ensemble if ensemble else calc_scores)(*db[big_folder], **kw))
     return pd.DataFrame(data=rows, columns=COLUMNS)
 
 

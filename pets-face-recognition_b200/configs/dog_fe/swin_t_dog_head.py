@@ -5,6 +5,7 @@ ArcFace weight, MultiStepLR [35, 45], 50 epochs, batch 64 / 20).  Data roots com
     PETS_DOGS_ROOT        identity folders (>= 2 images each)                         [required]
     PETS_DOGS_EXTRA_ROOT  extra training identities (>= 3 images each)                [optional]
     PETS_PAIRS            genuine pairs to draw (default 10000; as many impostors)
+    PETS_GPU_AUGMENT      1: the train augmentation runs on the GPU over the uint8 batch (data_loading/gpu_augment.py)
 """
 import os
 from pathlib import Path
@@ -24,7 +25,8 @@ np.random.seed(seed)
 
 if 'PETS_DOGS_ROOT' not in os.environ:
     raise Exception('set PETS_DOGS_ROOT to the folder of identity folders (see the docstring of this config)')
-globals().update(build(os.environ['PETS_DOGS_ROOT'], os.environ.get('PETS_DOGS_EXTRA_ROOT'), seed, int(os.environ.get('PETS_PAIRS', 10000))))
+globals().update(build(os.environ['PETS_DOGS_ROOT'], os.environ.get('PETS_DOGS_EXTRA_ROOT'), seed, int(os.environ.get('PETS_PAIRS', 10000)),
+                       gpu_augment=os.environ.get('PETS_GPU_AUGMENT', '0') == '1'))
 
 n_epochs, train_batch_size, test_batch_size = 50, 64, 20
 thrs = np.linspace(0.5, 0.99, 6)

@@ -22,8 +22,18 @@ def augmentations():
     return train, val
 
 
-def build(root, extra_root=None, seed=123, n_pairs=10000, train_fraction=0.5, min_images=2, extra_min_images=3):
+def uint8_chw(img):
+    """Dataset item -> uint8 CHW tensor, untouched (the GPU augmentation and the backbone's first kernel take raw pixels)."""
+    import torch
+    return img if torch.is_tensor(img) else torch.as_tensor(np.asarray(img)).permute(2, 0, 1).contiguous()
+
+
+def build(root, extra_root=None, seed=123, n_pairs=10000, train_fraction=0.5, min_images=2, extra_min_images=3, gpu_augment=False):
+    """gpu_augment: the training items stay uint8 and un-augmented in the DataLoader; the returned dict carries
+    `gpu_train_augmentation`, which engine.Controller.training_step applies to the whole batch on the device."""
     train_aug, val_aug = augmentations()
+    if gpu_augment:
+        train_aug = uint8_chw
     base = RecDataset(Path(root), None, min_images, init_dataset_method=simple_init_dataset)
     order = np.random.RandomState(seed).permutation(base.get_users())
     cut = int(len(order) * train_fraction)
@@ -48,4 +58,10 @@ def build(root, extra_root=None, seed=123, n_pairs=10000, train_fraction=0.5, mi
 
     return dict(dataset=base, train=parts[0] if len(parts) == 1 else ConcatDataset(parts), val=RecSubset(base, val_idx, val_aug),
                 train_users=train_users, val_users=val_users, n_train_classes=n_classes, pair_generator=pair_generator,
-                train_augmentation=train_aug, val_augmentation=val_aug)
+                train_augmentation=train_aug, val_augmentation=val_aug,
+                **({'gpu_train_augmentation': _gpu_aug()} if gpu_augment else {}))
+
+
+def _gpu_aug():
+    from data_loading.gpu_augment import GpuTrainAugmentation
+    return GpuTrainAugmentation(size=224, crop=220, p_sharp=0.1, p_autocontrast=0.3, degrees=5.0)

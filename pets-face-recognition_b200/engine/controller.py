@@ -35,7 +35,14 @@ class Controller(torch.nn.Module):
 
     # ---- steps (engine/controller.py:27-46)
     def training_step(self, batch, batch_idx):
-        loss = self.model_loss(batch['x'], batch['label'])
+        x = batch['x']
+        # config key `gpu_train_augmentation` (data_loading/gpu_augment.py): the reference's torchvision Compose
+        # (configs/dog_fe/fe_dogs_config.py:17-26) applied to the uint8 batch on the device instead of per image in the
+        # DataLoader workers; the backbone takes the uint8 result directly
+        aug = self.config.get('gpu_train_augmentation') if hasattr(self.config, 'get') else None
+        if aug is not None and torch.is_tensor(x) and x.is_cuda and x.dtype == torch.uint8:
+            x = aug(x)
+        loss = self.model_loss(x, batch['label'])
         return loss['loss']
 
     def validation_step(self, batch, batch_idx, dataset_idx=0) -> Optional[dict]:

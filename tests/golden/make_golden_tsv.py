@@ -34,6 +34,32 @@ def reference_functions():
     return ns
 
 
+REF1 = Path('/root/reference/generate_tsv_to_reproduce1.py')
+
+
+def reference_functions_ensemble():
+    """The head + body ensemble: the same four function names, taken from generate_tsv_to_reproduce1.py (:63-120)."""
+    tree = ast.parse(REF1.read_text())
+    body = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in WANT]
+    assert len(body) == len(WANT)
+    ns = {'torch': torch, 'F': F, 'np': np, 'List': List, 'Dict': Dict, 'Any': Any, 'Path': Path, 'tqdm': lambda it, **kw: it}
+    exec(compile(ast.Module(body=body, type_ignores=[]), str(REF1), 'exec'), ns)
+    return ns
+
+
+def main_ensemble():
+    from oracle.tsv_oracle import synth_db_ensemble
+    ns = reference_functions_ensemble()
+    cases = {}
+    for case, (n_q, n_g, n_ids, seed) in {'small': (14, 70, 16, 5), 'medium': (40, 300, 50, 6)}.items():
+        init = {Path(k): v for k, v in synth_db_ensemble(n_q, 512, seed, n_ids, 'q').items()}
+        extra = {Path(k): v for k, v in synth_db_ensemble(n_g, 512, seed + 100, n_ids, 'g').items()}
+        rows = ns['calc_scores'](init, extra)
+        cases[case] = {'args': [n_q, n_g, n_ids, seed], 'rows': [[r[0], float(r[1]), float(r[2]), float(r[3]), r[4]] for r in rows]}
+        print('ensemble', case, len(rows), 'rows')
+    (Path(__file__).resolve().parent / 'tsv_scores_ensemble.json').write_text(json.dumps(cases, indent=0))
+
+
 def main():
     ns = reference_functions()
     cases = {}
@@ -54,3 +80,4 @@ def main():
 
 if __name__ == '__main__':
     main()
+    main_ensemble()

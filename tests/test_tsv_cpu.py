@@ -50,3 +50,18 @@ def test_tsv_write_and_backfill(tmp_path):
     df = pd.read_csv(out, sep='\t')
     assert df['query'].tolist() == ['q1', 'q2', 'q3']        # preds.tsv order; q2 back-filled
     assert df['answer'].tolist() == ['g3,g1', 'y', 'g2'] and df['matched_1'].tolist() == [0.9, 0.2, 0.6]
+
+
+def test_ensemble_oracle_equals_reference_outputs(golden_dir):
+    """oracle.tsv_oracle.calc_scores_ensemble == the reference's own calc_scores of generate_tsv_to_reproduce1.py (:88-120),
+    run by tests/golden/make_golden_tsv.py on the same seeded folder databases."""
+    import json
+    from oracle import tsv_oracle as T
+    cases = json.loads((golden_dir / 'tsv_scores_ensemble.json').read_text())
+    for case, c in cases.items():
+        n_q, n_g, n_ids, seed = c['args']
+        rows = T.calc_scores_ensemble(T.synth_db_ensemble(n_q, 512, seed, n_ids, 'q'), T.synth_db_ensemble(n_g, 512, seed + 100, n_ids, 'g'))
+        assert len(rows) == len(c['rows'])
+        for a, b in zip(rows, c['rows']):
+            assert a[0] == b[0] and a[4] == b[4]
+            assert abs(a[1] - b[1]) < 1e-7 and abs(a[2] - b[2]) < 1e-7 and abs(a[3] - b[3]) < 1e-7

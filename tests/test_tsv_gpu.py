@@ -76,3 +76,25 @@ def test_strict_mirrors_reference_index_error():
     with pytest.raises(IndexError):
         multivector.calc_scores(dq, dg)
     assert len(multivector.calc_scores(dq, dg, strict=False)) > 0
+
+
+@pytest.mark.parametrize('case', ['small', 'medium'])
+def test_ensemble_matches_reference_outputs(golden_dir, case):
+    """SURVEY 8f-1, second half: the head + body ensemble rule against the outputs of the reference's own calc_scores of
+    generate_tsv_to_reproduce1.py (tests/golden/tsv_scores_ensemble.json, made by tests/golden/make_golden_tsv.py)."""
+    from b200 import multivector
+    c = json.loads((golden_dir / 'tsv_scores_ensemble.json').read_text())[case]
+    n_q, n_g, n_ids, seed = c['args']
+    rows = multivector.calc_scores_ensemble(T.synth_db_ensemble(n_q, 512, seed, n_ids, 'q'), T.synth_db_ensemble(n_g, 512, seed + 100, n_ids, 'g'))
+    _check(rows, c['rows'], 2e-6)
+    assert any(r[1] > 0.99 for r in c['rows'])          # body scores above the thresholds take part in the fixture
+
+
+def test_dense_dot_split_precision():
+    from b200 import multivector
+    g = torch.Generator().manual_seed(3)
+    a = torch.nn.functional.normalize(torch.randn(130, 512, generator=g)).cuda()
+    b = torch.nn.functional.normalize(torch.randn(1001, 512, generator=g)).cuda()
+    got = multivector._dense_dot(a, b)
+    ref = a.double() @ b.double().t()
+    assert (got.double() - ref).abs().max().item() < 1e-6        # plain fp16 operands: ~3e-4
