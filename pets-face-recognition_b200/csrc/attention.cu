@@ -239,16 +239,20 @@ __device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) {
 constexpr int kFwdStages = 4;
 constexpr int kFwdStageBytes = 3 * kTile;                                  // q, k, v tiles
 constexpr int kFwdTileBytes = kFwdStages * kFwdStageBytes;                 // the operand ring (P lives in tensor memory)
-constexpr int kXchBytes = 9216;                                             // row-statistics exchange: xM, xL [2][128][4], xRowM [2][128]
+constexpr int kXchBytes = 4096;                                             // row-maximum exchange between the column parts: xM [2][128][4]
 constexpr int kFwdSmem = kFwdTileBytes + kBiasBytes + kXchBytes + kBarBytes + 1024;
 // TMEM columns: S of buffer b at 128 b (128 columns); O of buffer b at 256 + 64 b (window A: +0, window B: +32); P of buffer
 // b at 384 + 32 b: the A operand of O = P V read straight from tensor memory (bf16 pairs, key 2 c and 2 c + 1 in column c), so
 // the probabilities never touch shared memory - the kernel is bound by shared-memory bandwidth (operand reads of the MMAs)
 constexpr int kFwdTmemP = 384;
+// row statistics for the epilogue warps, also in tensor memory: buffer b, columns 448 + 4 b .. + 3 = the three partial row
+// sums (one per column part) and the row maximum - the softmax warps tcgen05.st them next to P, the epilogue tcgen05.ld's them
+// next to O: no shared-memory hand-over
+constexpr int kFwdTmemStat = 448;
 
 template <int T>
 __device__ __forceinline__ void fwd_softmax_task(const RowCtx& rc, const float (&bias)[kPC], float sc2, uint32_t t_s, uint32_t t_p, int q, int lane,
-                                                 int b, uint32_t par, float* xM, float* xL, float* xRowM, uint32_t sfull, uint32_t sfree,
+                                                 int b, uint32_t par, float* xM, uint32_t t_stat, uint32_t sfull, uint32_t sfree,
                                                  uint32_t ofree, uint32_t pfull) {
   constexpr int NC = Part<T>::NC;
   mbar_wait(sfull, par);
@@ -274,11 +278,12 @@ __device__ __forceinline__ void fwd_softmax_task(const RowCtx& rc, const float (
     s[j] = fast_exp2(s[j] - m);
     if (j & 1) l1 += s[j]; else l0 += s[j];
   }
-  // the epilogue warps have read O, xL and xRowM of the task before last (same buffers); its PV MMAs are done with the P columns
+  // the epilogue warps have read O and the row statistics of the task before last (same buffers); its PV MMAs are done with
+  // the P columns
   mbar_wait(ofree, par ^ 1u);
   tc_fence_after();
-  xL[(b * 128 + rc.row) * 4 + T] = l0 + l1;
-  if (T == 0) xRowM[b * 128 + rc.row] = m;
+  tmem_st1(t_stat + T, __float_as_uint(l0 + l1));
+  if (T == 0) tmem_st1(t_stat + 3, __float_as_uint(m));
   // un-normalised probabilities (1 / l is applied to O) -> bf16 pairs -> this row's P columns: keys 16 T .. 16 T + 15 are
   // columns 8 T .. 8 T + 7; part 2 also writes columns 24 .. 31 = key 48 and the zeros of the padded keys
   uint32_t pk[8];
@@ -300,8 +305,6 @@ __global__ void __launch_bounds__(kThreads, 1) window_attn_fwd_kernel(const __gr
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
   float* bias_s = reinterpret_cast<float*>(base_ptr + kFwdTileBytes);
   float* xM = reinterpret_cast<float*>(base_ptr + kFwdTileBytes + kBiasBytes);
-  float* xL = xM + 2 * 128 * 4;
-  float* xRowM = xL + 2 * 128 * 4;
   const uint32_t bar_base = base + kFwdTileBytes + kBiasBytes + kXchBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kFwdStages + s); };
@@ -422,15 +425,15 @@ __global__ void __launch_bounds__(kThreads, 1) window_attn_fwd_kernel(const __gr
       for (int slot = 0; slot < nslots; ++slot, ++n) {
         const int b = n & 1;
         const uint32_t par = (n >> 1) & 1u;
-        const uint32_t t_p = lane_base + kFwdTmemP + 32 * b;
+        const uint32_t t_p = lane_base + kFwdTmemP + 32 * b, t_stat = lane_base + kFwdTmemStat + 4 * b;
         if (part == 0)
-          fwd_softmax_task<0>(rc, bias, sc2, lane_addr + b * 128, t_p, q, lane, b, par, xM, xL, xRowM, sfull_bar(b), sfree_bar(b),
+          fwd_softmax_task<0>(rc, bias, sc2, lane_addr + b * 128, t_p, q, lane, b, par, xM, t_stat, sfull_bar(b), sfree_bar(b),
                               ofree_bar(b), pfull_bar(b));
         else if (part == 1)
-          fwd_softmax_task<1>(rc, bias, sc2, lane_addr + b * 128, t_p, q, lane, b, par, xM, xL, xRowM, sfull_bar(b), sfree_bar(b),
+          fwd_softmax_task<1>(rc, bias, sc2, lane_addr + b * 128, t_p, q, lane, b, par, xM, t_stat, sfull_bar(b), sfree_bar(b),
                               ofree_bar(b), pfull_bar(b));
         else
-          fwd_softmax_task<2>(rc, bias, sc2, lane_addr + b * 128, t_p, q, lane, b, par, xM, xL, xRowM, sfull_bar(b), sfree_bar(b),
+          fwd_softmax_task<2>(rc, bias, sc2, lane_addr + b * 128, t_p, q, lane, b, par, xM, t_stat, sfull_bar(b), sfree_bar(b),
                               ofree_bar(b), pfull_bar(b));
       }
     }
@@ -439,7 +442,8 @@ __global__ void __launch_bounds__(kThreads, 1) window_attn_fwd_kernel(const __gr
     RowCtx rc;
     rc.row = q * 32 + lane; rc.ws = rc.row >> 6; rc.i = rc.row & 63;
     rc.row_hi = false; rc.col_hi = false;
-    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + 256 + 32 * rc.ws;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t lane_addr = lane_base + 256 + 32 * rc.ws;
     uint32_t n = 0;
     for (int unit = blockIdx.x; unit < a.units; unit += gridDim.x) {
       const int pair = static_cast<int>(a.div_nhp.div(static_cast<uint32_t>(unit)));
@@ -450,15 +454,15 @@ __global__ void __launch_bounds__(kThreads, 1) window_attn_fwd_kernel(const __gr
         const int b = n & 1;
         const uint32_t par = (n >> 1) & 1u;
         const int h = 2 * hp + slot;
-        mbar_wait(pfull_bar(b), par);            // the softmax warps' xL / xRowM of this task are visible
+        mbar_wait(pfull_bar(b), par);            // the softmax warps' row statistics of this task are in tensor memory
         mbar_wait(ofull_bar(b), par);
         tc_fence_after();
-        uint32_t r0[16], r1[16];
+        uint32_t r0[16], r1[16], st[4];
         load_row32(lane_addr + 64 * b, r0, r1);
-        const float* xl = xL + (b * 128 + rc.row) * 4;
-        const float l = (xl[0] + xl[1]) + xl[2];
-        const float m = xRowM[b * 128 + rc.row];
+        tmem_ld4(lane_base + kFwdTmemStat + 4 * b, st);
         tmem_ld_wait();
+        const float l = (__uint_as_float(st[0]) + __uint_as_float(st[1])) + __uint_as_float(st[2]);
+        const float m = __uint_as_float(st[3]);
         tc_fence_before();
         warp_arrive(ofree_bar(b), lane);
         if (rc.valid) {

@@ -411,6 +411,12 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
                "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
+__device__ __forceinline__ void tmem_st1(uint32_t taddr, uint32_t r) {          // one 32-bit column
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(r) : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // D[tmem] (+)= A[tmem] * B[smem desc]: the A operand comes from tensor memory (row i in lane i, two 16-bit K elements per
 // 32-bit column, 8 columns per K = 16 step)

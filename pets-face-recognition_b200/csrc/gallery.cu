@@ -694,6 +694,7 @@ __global__ void __launch_bounds__(256) exact_topk_kernel(const float* __restrict
       }
       __syncthreads();
       const int n = s_cnt;
+      __syncthreads();                                             // every thread has the SAME n before anyone appends again
       if (n > kExCap - kExBlock || r0 + kExBlock >= ng) {          // CTA-uniform: sort, keep the best k, tighten the cut
         for (int i = n + threadIdx.x; i < kExCap; i += blockDim.x) { buf[i].score = -INFINITY; buf[i].idx = INT_MAX; buf[i].pad = 0; }
         __syncthreads();
