@@ -172,10 +172,6 @@ __device__ __forceinline__ float pick32(const uint32_t (&a)[16], const uint32_t 
   return __uint_as_float((i & 1) ? t[1] : t[0]);
 }
 
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 // TMA load whose box lands at the same smem offset - and signals the mbarrier at the same offset - in every CTA of `mask`
 __device__ __forceinline__ void tma_load_2d_mc(uint32_t smem_dst, const void* tmap, uint32_t bar, int c_inner, int c_outer, uint16_t mask) {
   asm volatile(

@@ -40,6 +40,16 @@ int b200_epi16() {
   return on;
 }
 
+namespace gemm {
+int b200_cg2() {
+  static const int on = [] {
+    const char* e = getenv("B200_CG2");
+    return (e != nullptr && e[0] == '0') ? 0 : 1;
+  }();
+  return on;
+}
+}  // namespace gemm
+
 int b200_reverse_rows() {
   static const int on = [] {
     const char* e = getenv("B200_REVERSE");
@@ -570,6 +580,24 @@ extern "C" int b200_gemm_tn(const void* a, long long lda, const void* b, long lo
   B200_REQUIRE(!(mode == B200_EPI_GELU && eb != 2), "gemm_tn: the GELU epilogue writes bf16");
   gemm::Output od{out, ldo, eb, out2, ldo2, mode == B200_EPI_PARTIAL ? split_stride : 0, use_aux ? aux : nullptr, use_aux ? ldaux : 0};
   auto st = reinterpret_cast<cudaStream_t>(stream);
+  // CTA pairs for the compute-bound layers: K-major, unsplit, K >= 384 (six or more K blocks), whole tiles of >= 192 columns,
+  // at least two waves of row-block pairs (stages 3-4 at the bench's batch).  See gemm_core.cuh: CG2.
+  {
+    const int bn = block_n > 0 ? block_n : gemm::pick_block_n(N, K);
+    static const int min_k = [] { const char* e = getenv("B200_CG2_MINK"); return e != nullptr ? atoi(e) : 384; }();      // experiments
+    const bool pair_ok = gemm::b200_cg2() && is_bf16 && K >= min_k && bn >= 192 && bn % 32 == 0 && N % bn == 0 && M >= 2 * 128 && eb == 2 && !q8;
+    if (pair_ok) {
+      switch (mode) {
+        case B200_EPI_STORE: return gemm::launch<gemm::EpiLinear<B200_EPI_STORE>, 2, false, false, false, 8, true>(o, od, {bias}, st);
+        case B200_EPI_GELU:
+          if (out2 != nullptr) return gemm::launch<gemm::EpiLinear<B200_EPI_GELU>, 2, true, false, false, 8, true>(o, od, {bias}, st);
+          return gemm::launch<gemm::EpiLinear<B200_EPI_GELU>, 2, false, false, false, 8, true>(o, od, {bias}, st);
+        case B200_EPI_RESID: return gemm::launch<gemm::EpiLinear<B200_EPI_RESID>, 2, false, true, false, 8, true>(o, od, {bias}, st);
+        case B200_EPI_DGELU: return gemm::launch<gemm::EpiLinear<B200_EPI_DGELU>, 2, false, true, false, 8, true>(o, od, {bias}, st);
+        default: break;
+      }
+    }
+  }
   switch (mode) {
     case B200_EPI_STORE:
       // small-K bf16 layers (K <= 4 blocks of 64): sixteen epilogue warps (B200_EPI16=0 -> eight).  Measured (r01y): qkv of stage 1

@@ -73,11 +73,14 @@ struct CoreParams {
   int bias_smem;             // 1: the epilogue reads the bias from its smem copy (padded N <= kBiasFloats)
   int pipe_bytes;            // operand ring size = stages * stage_bytes (a multiple of 1024)
   uint32_t wait_ns;          // suspend-time hint of the producer / MMA-issuer barrier waits
+  int m_pairs;               // CTA-pair variant: pairs of row blocks = ceil(m_blocks / 2)
+  FastDiv div_mp;
+  uint32_t idesc2, idesc2_last;   // M = 256 instruction descriptors of the cta_group::2 MMA
 };
 
 // instruction descriptor, kind::f16: [4,6) D fmt (1=f32), [7,10) A fmt, [10,13) B fmt (0=f16, 1=bf16),
 // [15] A major, [16] B major (0 = K-major), [17,23) N>>3, [24,29) M>>4
-inline uint32_t make_idesc(bool is_bf16, int block_n, bool mn_major = false) {
+inline uint32_t make_idesc(bool is_bf16, int block_n, bool mn_major = false, int m = kBlockM) {
   uint32_t d = 0;
   d |= 1u << 4;
   d |= (is_bf16 ? 1u : 0u) << 7;
@@ -85,7 +88,7 @@ inline uint32_t make_idesc(bool is_bf16, int block_n, bool mn_major = false) {
   d |= (mn_major ? 1u : 0u) << 15;
   d |= (mn_major ? 1u : 0u) << 16;
   d |= static_cast<uint32_t>(block_n >> 3) << 17;
-  d |= static_cast<uint32_t>(kBlockM >> 4) << 24;
+  d |= static_cast<uint32_t>(m >> 4) << 24;
   return d;
 }
 
@@ -123,7 +126,12 @@ __device__ __forceinline__ float q8_dequant(uint32_t w) {
 //   EW        epilogue warps: 8 (two per scheduler, double-buffered staging boxes) or 16 (four per scheduler, one staging box
 //             each, plain epilogues only).  The small-K layers are bound by the latency chain of a box (barrier -> tcgen05.ld
 //             -> convert -> st.shared -> fence -> TMA store), and two warps per scheduler do not cover it.
-template <class Epi, int OUT_BYTES, bool DUAL, bool AUX, bool Q8 = false, int EW = kEpiWarps>
+//   CG2       CTA-pair variant (cta_group::2) for the compute-bound layers (K >= 384: stages 3-4).  A single-CTA MMA reads
+//             (128 + N) x 64 x 2 B of shared memory per K block while the TMA writes the same amount: at N = 256 that is 192 B per
+//             clock against the 128 B / clock the SM's shared memory delivers - the measured 47-65 % of tensor peak.  In a pair each
+//             CTA keeps its own 128 rows of A but only HALF of the B tile (the tensor cores of both SMs see all of it), the leader
+//             issues M = 256 MMAs for both, and the per-SM shared-memory traffic drops to the 128 B / clock that fits.
+template <class Epi, int OUT_BYTES, bool DUAL, bool AUX, bool Q8 = false, int EW = kEpiWarps, bool CG2 = false>
 __global__ void __launch_bounds__(64 + EW * 32, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_o2,
@@ -146,13 +154,16 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  static_assert(!CG2 || EW == 8, "the CTA-pair variant runs eight epilogue warps");
+  const uint32_t cta_rank = CG2 ? cluster_ctarank() : 0u;        // 0 = leader: issues the MMAs of the pair
+  const bool leader = cta_rank == 0u;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     tma_prefetch_desc(&tmap_o);
     for (int s = 0; s < kMaxStages; ++s) {
-      mbar_init(full_bar(s), 1);
+      mbar_init(full_bar(s), CG2 ? 2 : 1);   // pair: the leader's barrier counts both producers (and both CTAs' bytes)
       mbar_init(empty_bar(s), 1);
     }
     for (int w = 0; w < EW; ++w) {
@@ -161,13 +172,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), EW);          // one arrival per epilogue warp
+      mbar_init(tempty_bar(a), CG2 ? 2 * EW : EW);   // one arrival per epilogue warp (pair: of both CTAs, on the leader's barrier)
     }
     mbar_fence_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, kTmemCols);
-    tmem_relinquish();
+    if (CG2) { tmem_alloc_cg2(tmem_slot, kTmemCols); tmem_relinquish_cg2(); }
+    else { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
   }
   if (p.colsum_out != nullptr) {
     // Bias gradient for free: db[m] = sum_t dY[t, m] is the weight-gradient GEMM with an all-ones second operand.  One
@@ -178,14 +189,25 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  if (CG2) cluster_sync_all();      // the peer's barriers are initialised before anything arrives on them from this CTA
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   pdl_grid_sync();      // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
 
-  const int num_tiles = p.m_blocks * p.n_blocks * p.splits;
+  // The tile sequence: tile = tile0 + i * tstride.  Single CTA: one 128-row block per tile.  Pair: a "tile" is a pair of
+  // row blocks (2 m_pair, 2 m_pair + 1) x one column block, walked by both CTAs of the cluster; CTA `rank` owns row block
+  // 2 m_pair + rank (a row block past the end computes on zero-filled rows and its stores are clipped).
+  const int num_tiles = CG2 ? p.m_pairs * p.n_blocks : p.m_blocks * p.n_blocks * p.splits;
+  const int tile0 = CG2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int tstride = CG2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   auto decode = [&](int tile, int& n_blk, int& m_blk, int& split) {
     const uint32_t t1 = p.div_n.div(static_cast<uint32_t>(tile));            // tile / n_blocks
     n_blk = tile - static_cast<int>(t1) * p.n_blocks;
+    if (CG2) {
+      m_blk = 2 * static_cast<int>(t1) + static_cast<int>(cta_rank);
+      split = 0;
+      return;
+    }
     const uint32_t t2 = p.div_m.div(t1);                                     // tile / (n_blocks * m_blocks)
     m_blk = static_cast<int>(t1) - static_cast<int>(t2) * p.m_blocks;
     split = static_cast<int>(t2);
@@ -194,21 +216,30 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   // 128 / block_n columns], loaded as [64 x 64] boxes (one 128-B swizzle row = 64 columns) 8 KB apart.
   constexpr uint32_t kChunk = 64 * 64 * 2;
   const uint32_t tx_bytes = p.mn_major ? static_cast<uint32_t>((2 + p.b_chunks) * kChunk)
-                                       : static_cast<uint32_t>((kBlockM + p.block_n) * kBlockK * 2);
+                                       : static_cast<uint32_t>((kBlockM + p.block_n) * kBlockK * 2);       // pair: both CTAs' A + the whole B
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tstride) {
         int n_blk, m_blk, split;
         decode(tile, n_blk, m_blk, split);
         const int kb0 = split * p.k_blocks_per_split;
         const int kb1 = min(p.k_blocks, kb0 + p.k_blocks_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait_backoff(empty_bar(stage), phase ^ 1u, p.wait_ns);
-          mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
           const uint32_t sa = smem_base + stage * p.stage_bytes;
+          if (CG2) {
+            // this CTA's 128 rows of A and its half of the B tile; the bytes of both CTAs complete on the leader's barrier
+            if (leader) mbar_arrive_expect_tx(full_bar(stage), 2u * kABytes + static_cast<uint32_t>(p.block_n * kBlockK * 2));
+            tma_load_2d_cg2(sa, &tmap_a, full_bar(stage), kb * kBlockK, m_blk * kBlockM);
+            tma_load_2d_cg2(sa + kABytes, &tmap_b, full_bar(stage), kb * kBlockK, n_blk * p.block_n + static_cast<int>(cta_rank) * (p.block_n >> 1));
+            if (!leader) mbar_arrive_remote(full_bar(stage), 0u);
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            continue;
+          }
+          mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
           if (!p.mn_major) {
             tma_load_2d(sa, &tmap_a, full_bar(stage), kb * kBlockK, m_blk * kBlockM);
             tma_load_2d(sa + kABytes, &tmap_b, full_bar(stage), kb * kBlockK, n_blk * p.block_n);
@@ -222,12 +253,46 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (lane == 0 && CG2) {
+      if (leader) {
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = tile0; tile < num_tiles; tile += tstride) {
+          mbar_wait_backoff(tempty_bar(acc), acc_phase ^ 1u, p.wait_ns);      // both CTAs' epilogues have drained this stage
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kMaxBlockN);
+          for (int kb = 0; kb < p.k_blocks; ++kb) {
+            mbar_wait_backoff(full_bar(stage), phase, p.wait_ns);
+            tc_fence_after();
+            const uint32_t sa = smem_base + stage * p.stage_bytes;
+            const uint64_t da = make_sw128_desc(sa, 16, 1024);
+            const uint64_t db = make_sw128_desc(sa + kABytes, 16, 1024);
+            const int ksteps = (kb == p.k_blocks - 1) ? p.k_last_steps : kBlockK / 16;
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k)
+              if (k < ksteps) umma_f16_cg2(d_tmem, da + 2u * k, db + 2u * k, p.idesc2, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_commit_cg2(empty_bar(stage));                   // the slot is free again in BOTH CTAs
+            if (kb == p.k_blocks - 1) umma_commit_cg2(tfull_bar(acc));
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          }
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1u;
+        }
+        // the peer's last arrivals on this CTA's barriers must have landed before it may exit
+        for (int a2 = 0; a2 < 2; ++a2) {
+          mbar_wait_backoff(tempty_bar(acc), acc_phase ^ 1u, p.wait_ns);
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1u;
+        }
+      }
+    } else if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tstride) {
         int n_blk, m_blk, split;
         decode(tile, n_blk, m_blk, split);
         const int kb0 = split * p.k_blocks_per_split;
@@ -298,7 +363,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       tma_load_3d(stg + static_cast<uint32_t>(b) * kBoxBytes, &tmap_aux, aux_bar(ew, b), n_blk * p.block_n + box * p.box_cols,
                   m_blk * kBlockM + q * 32, 0);
     };
-    if (aux && lane == 0 && static_cast<int>(blockIdx.x) < num_tiles) issue_aux(blockIdx.x, box_lo, 0);
+    if (aux && lane == 0 && tile0 < num_tiles) issue_aux(tile0, box_lo, 0);
     // the epilogue's per-column vector (bias), zero-padded to the tile grid, once per CTA: the epilogue then reads it with
     // broadcast shared loads and needs no column guard
     const float* bias_s = reinterpret_cast<const float*>(smem_raw + (bias_base - smem_u32(smem_raw)));
@@ -306,7 +371,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       Epi::stage_columns(ep, p, const_cast<float*>(bias_s), static_cast<int>(threadIdx.x) - 64, EW * 32);
       asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
     }
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < num_tiles; tile += tstride) {
       int n_blk, m_blk, split;
       decode(tile, n_blk, m_blk, split);
       const int kb0 = split * p.k_blocks_per_split;
@@ -325,7 +390,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             bulk_wait_read<0>();
             if (aux) {
               const bool more_here = box + 1 < box_hi;
-              const int ntile = more_here ? tile : tile + static_cast<int>(gridDim.x);
+              const int ntile = more_here ? tile : tile + tstride;
               if (ntile < num_tiles) issue_aux(ntile, more_here ? box + 1 : box_lo, buf ^ 1);
             }
           } else if (DUAL) {
@@ -431,7 +496,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if (CG2 && !leader) mbar_arrive_remote(tempty_bar(acc), 0u);     // the leader's MMA thread waits for both CTAs
+        else mbar_arrive(tempty_bar(acc));
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
@@ -440,9 +508,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
+  if (CG2) cluster_sync_all();               // no CTA of the pair leaves (or frees TMEM) while the other can still reach it
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (CG2) tmem_dealloc_cg2(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -487,7 +557,9 @@ inline int pick_box_cols(int block_n, int elem_bytes) {
   return 16;
 }
 
-template <class Epi, int OUT_BYTES, bool DUAL, bool AUX, bool Q8 = false, int EW = kEpiWarps>
+int b200_cg2();   // 1 (default): compute-bound K-major layers run as CTA pairs; B200_CG2=0 -> single CTAs
+
+template <class Epi, int OUT_BYTES, bool DUAL, bool AUX, bool Q8 = false, int EW = kEpiWarps, bool CG2 = false>
 int launch(const Operands& o, const Output& out, const typename Epi::Params& ep, cudaStream_t stream) {
   static_assert(!Q8 || ((DUAL || AUX) && OUT_BYTES == 2), "Q8 qualifies the second output / the side input of a bf16 epilogue");
   B200_REQUIRE(out.elem_bytes == OUT_BYTES && (out.ptr2 != nullptr) == DUAL && (out.aux != nullptr) == AUX, "gemm: epilogue specialisation mismatch");
@@ -513,15 +585,22 @@ int launch(const Operands& o, const Output& out, const typename Epi::Params& ep,
   p.k_last_steps = (o.K - (p.k_blocks - 1) * kBlockK + 15) / 16;
   p.mn_major = o.mn_major ? 1 : 0;
   p.b_chunks = (p.block_n + 63) / 64;
-  const int b_bytes = o.mn_major ? p.b_chunks * 8192 : p.block_n * kBlockK * 2;
+  const int b_bytes = o.mn_major ? p.b_chunks * 8192 : (CG2 ? p.block_n / 2 : p.block_n) * kBlockK * 2;
   p.stage_bytes = (kABytes + b_bytes + 1023) / 1024 * 1024;
+  p.m_pairs = (p.m_blocks + 1) / 2;
+  p.div_mp = make_fastdiv(static_cast<uint32_t>(p.m_pairs));
+  p.idesc2 = make_idesc(o.is_bf16, p.block_n, false, 256);
+  p.idesc2_last = p.idesc2;
+  if (CG2)
+    B200_REQUIRE(!o.mn_major && p.splits == 1 && o.N % p.block_n == 0 && p.block_n % 32 == 0 && out.colsum == nullptr,
+                 "gemm: the CTA-pair variant needs a K-major, unsplit problem whose N is a multiple of the tile width");
 
   CUtensorMap ta, tb;
   int rc;
   if (!o.mn_major) {
     rc = encode_tmap_2d(&ta, o.is_bf16, o.a, o.K, o.M, o.lda, kBlockK, kBlockM);
     if (rc) return rc;
-    rc = encode_tmap_2d(&tb, o.is_bf16, o.b, o.K, o.N, o.ldb, kBlockK, p.block_n);
+    rc = encode_tmap_2d(&tb, o.is_bf16, o.b, o.K, o.N, o.ldb, kBlockK, CG2 ? p.block_n / 2 : p.block_n);
   } else {
     rc = encode_tmap_2d(&ta, o.is_bf16, o.a, o.M, o.K, o.lda, 64, kBlockK);
     if (rc) return rc;
@@ -570,11 +649,12 @@ int launch(const Operands& o, const Output& out, const typename Epi::Params& ep,
 
   static bool attr_done = false;   // per instantiation
   if (!attr_done) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<Epi, OUT_BYTES, DUAL, AUX, Q8, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    B200_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<Epi, OUT_BYTES, DUAL, AUX, Q8, EW, CG2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_done = true;
   }
-  const long long tiles = 1LL * p.m_blocks * p.n_blocks * p.splits;
+  const long long tiles = CG2 ? 1LL * p.m_pairs * p.n_blocks : 1LL * p.m_blocks * p.n_blocks * p.splits;
   int ctas = o.max_ctas > 0 ? o.max_ctas : b200_num_sms();
+  if (CG2) ctas /= 2;                       // clusters of two
   if (tiles < ctas) ctas = static_cast<int>(tiles);
   // A ragged last column block makes the tiles of one row block unequal (qkv of stage 1: 192 + 96 columns).  With the static
   // tile sequence (tile = cta + i * ctas, n fastest) a CTA count sharing a factor with n_blocks would hand some CTAs only
@@ -587,7 +667,23 @@ int launch(const Operands& o, const Output& out, const typename Epi::Params& ep,
   const double io_bytes = 2.0 * (1.0 * o.M + o.N) * o.K + 1.0 * o.M * o.N * p.splits * out.elem_bytes +
                           (out.ptr2 != nullptr ? (Q8 ? 1.0 : 2.0) * o.M * o.N : 0.0) + (out.aux != nullptr ? (Q8 ? 1.0 : 2.0) * o.M * o.N : 0.0);
   const bool prof = b200_prof_gemm_begin(stream, 2.0 * o.M * o.N * o.K, io_bytes);
-  launch_pdl(gemm_tn_kernel<Epi, OUT_BYTES, DUAL, AUX, Q8, EW>, dim3(ctas), dim3(64 + EW * 32), kSmemBytes, stream, ta, tb, to, to2, tx, p, ep);
+  if (CG2) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * ctas);
+    cfg.blockDim = dim3(64 + EW * 32);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = 2; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 2;
+    cudaLaunchKernelEx(&cfg, gemm_tn_kernel<Epi, OUT_BYTES, DUAL, AUX, Q8, EW, CG2>, ta, tb, to, to2, tx, p, ep);
+  } else {
+    launch_pdl(gemm_tn_kernel<Epi, OUT_BYTES, DUAL, AUX, Q8, EW, CG2>, dim3(ctas), dim3(64 + EW * 32), kSmemBytes, stream, ta, tb, to, to2, tx, p, ep);
+  }
   if (prof) b200_prof_gemm_end(stream);
   B200_LAUNCH_CHECK();
   return B200_OK;

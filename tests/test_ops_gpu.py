@@ -6,10 +6,13 @@ compared after the same bf16 rounding of the inputs, at ~2 bf16 ulps of the outp
 """
 import math
 
+from pathlib import Path
+
 import numpy as np
 import pytest
 import torch
 
+ROOT = Path(__file__).resolve().parents[1]
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
 
 DEV = 'cuda'
@@ -72,6 +75,37 @@ def test_gemm_epilogues():
     x = rnd(M, N, seed=8)
     out = ops.gemm_tn(a, b, mode=abi.EPI_DGELU, aux=x)          # aux = the derivative saved by the GELU epilogue
     assert rel_err(out, (a.float() @ b.float().t()) * x.float()) < 6e-3
+
+
+@pytest.mark.parametrize('M,N,K', [(1100, 384, 384), (6272, 1536, 384), (2000, 384, 1536), (50176, 1152, 384), (257, 768, 3072), (1153, 2304, 768)])
+def test_gemm_cta_pair_variant(M, N, K):
+    """The cta_group::2 kernel (stages 3-4: K >= 384, whole tiles of >= 192 columns): every epilogue against fp32 matmul, odd and
+    even numbers of row blocks (a phantom row block in the last pair), more tiles than clusters, and bit-equality with the
+    single-CTA kernel (B200_CG2 is read once per process, so that comparison runs in a child process)."""
+    import os, subprocess, sys
+    from b200 import abi, ops
+    a, b = rnd(M, K, seed=1, scale=0.5), rnd(N, K, seed=2, scale=0.1)
+    bias = rnd(N, seed=3, dtype=torch.float32)
+    pre = a.float() @ b.float().t() + bias
+    out = ops.gemm_tn(a, b, bias=bias)
+    assert rel_err(out, pre) < 6e-3
+    act, dact = ops.gemm_tn(a, b, bias=bias, mode=abi.EPI_GELU, want_grad=True)
+    pr = pre.clone().requires_grad_(True)
+    torch.nn.functional.gelu(pr).sum().backward()
+    assert rel_err(act, torch.nn.functional.gelu(pre)) < 6e-3 and rel_err(dact, pr.grad) < 6e-3
+    res = rnd(M, N, seed=7)
+    assert rel_err(ops.gemm_tn(a, b, bias=bias, mode=abi.EPI_RESID, aux=res), pre + res.float()) < 6e-3
+    x = rnd(M, N, seed=8)
+    assert rel_err(ops.gemm_tn(a, b, mode=abi.EPI_DGELU, aux=x), (a.float() @ b.float().t()) * x.float()) < 6e-3
+    if (M, N, K) == (1100, 384, 384):
+        code = ("import sys, torch; sys.path[:0] = %r; from b200 import ops; g = torch.Generator().manual_seed(1); "
+                "a = (torch.randn(1100, 384, generator=g) * 0.5).cuda().bfloat16(); g2 = torch.Generator().manual_seed(2); "
+                "b = (torch.randn(384, 384, generator=g2) * 0.1).cuda().bfloat16(); torch.save(ops.gemm_tn(a, b).cpu(), sys.argv[1])") % ([str(ROOT), str(ROOT / 'pets-face-recognition_b200')],)
+        import tempfile
+        with tempfile.TemporaryDirectory() as d:
+            subprocess.run([sys.executable, '-c', code, d + '/single.pt'], check=True, env=dict(os.environ, B200_CG2='0'), timeout=300)
+            single = torch.load(d + '/single.pt')
+        assert torch.equal(ops.gemm_tn(a, b).cpu(), single)
 
 
 @pytest.mark.parametrize('M,N,K', [(1024, 384, 96), (777, 768, 192), (130, 1536, 384), (50, 3072, 768)])
