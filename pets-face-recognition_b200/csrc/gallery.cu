@@ -44,7 +44,7 @@ constexpr int kBM = 128;            // queries per block
 constexpr int kBN = 256;            // gallery rows per tile
 constexpr int kBK = 64;
 constexpr int kMaxKB = 8;           // dim <= 512
-constexpr int kBStages = 3;
+constexpr int kBStages = 3;                  // single-CTA mode: three 32-KB gallery stages; CTA-pair mode: six 16-KB half tiles
 constexpr int kQSlab = kBM * kBK * 2;        // 16 KB
 constexpr int kBStage = kBN * kBK * 2;       // 32 KB
 constexpr int kHalf = kBN / 2;       // tile columns per epilogue warp
@@ -53,6 +53,7 @@ constexpr int kKP = 128;            // candidates kept per (query, chunk, column
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 64 + 32 * kEpiWarps;     // TMA warp, MMA warp, epilogue warps
 constexpr int kWitnessRows = 32 * kBN;            // rows of the witness pass: 2 halves x 64 groups of 64 = 128 witnesses
+constexpr int kMaxBStages = 2 * kBStages;
 constexpr int kSmem = kMaxKB * kQSlab + kBStages * kBStage + 256 + 1024;
 
 struct FilterParams {
@@ -172,64 +173,59 @@ __device__ __forceinline__ float pick32(const uint32_t (&a)[16], const uint32_t 
   return __uint_as_float((i & 1) ? t[1] : t[0]);
 }
 
-// TMA load whose box lands at the same smem offset - and signals the mbarrier at the same offset - in every CTA of `mask`
-__device__ __forceinline__ void tma_load_2d_mc(uint32_t smem_dst, const void* tmap, uint32_t bar, int c_inner, int c_outer, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_dst),
-      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c_inner), "r"(c_outer), "h"(mask)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
-               : "memory");
-}
-
-// CLUSTER CTAs (a thread-block cluster) work on CLUSTER different query blocks against the SAME gallery chunk in lock step:
-// each CTA fetches 1/CLUSTER of every gallery tile and TMA-multicasts it into the smem of all of them, so the L2 -> SM
-// traffic of the gallery stream (the bound of this kernel: 256 KB per 128 x 256 x 512 tile) drops by CLUSTER.
-template <int CLUSTER>
+// PAIR = 2: two CTAs of a cluster (one TPC) work on two consecutive query blocks against the SAME gallery chunk as one
+// M = 256 MMA (cta_group::2, see gemm_core.cuh: CG2): each CTA keeps its own resident query block but only HALF of every
+// gallery tile, so the shared-memory traffic per SM - the bound of the single-CTA kernel: (128 + 256) x 64 x 2 B read and
+// 256 x 64 x 2 B written per K block, 156 B per clock against the 128 B / clock an SM's shared memory delivers - drops to 94.
+template <int PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 cosine_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_g, const FilterParams p) {
   extern __shared__ uint8_t smem_raw[];
+  constexpr int kStages = PAIR * kBStages;                    // same bytes either way
+  constexpr int kStageBytes = kBStage / PAIR;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t q_base = smem_base;
   const uint32_t b_base = smem_base + p.kb * kQSlab;          // Q takes kb slabs; B stages follow
   const uint32_t bar_base = smem_base + kMaxKB * kQSlab + kBStages * kBStage;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (kBStages + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kBStages + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kBStages + 2 + a); };
-  const uint32_t qfull_bar = bar_base + 8u * (2 * kBStages + 4);
-  const uint32_t qempty_bar = bar_base + 8u * (2 * kBStages + 5);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kBStages + 6);
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxBStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kMaxBStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kMaxBStages + 2 + a); };
+  const uint32_t qfull_bar = bar_base + 8u * (2 * kMaxBStages + 4);
+  const uint32_t qempty_bar = bar_base + 8u * (2 * kMaxBStages + 5);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxBStages + 6);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int crank = PAIR > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const bool leader = crank == 0;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_g);
-    for (int s = 0; s < kBStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), CLUSTER); }   // every CTA of the cluster releases a slot
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kEpiWarps); }
-    mbar_init(qfull_bar, 1);
+    // pair: the leader's full / qfull barriers count both producers (and both CTAs' bytes), its tempty both CTAs' epilogues
+    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), PAIR); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), PAIR * kEpiWarps); }
+    mbar_init(qfull_bar, PAIR);
     mbar_init(qempty_bar, 1);
     mbar_fence_init();
   }
-  if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (warp == 2) {
+    if (PAIR > 1) { tmem_alloc_cg2(tmem_slot, 512); tmem_relinquish_cg2(); }
+    else { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  }
   tc_fence_before();
   __syncthreads();
+  if (PAIR > 1) cluster_sync_all();      // the peer's barriers are initialised before anything arrives on them from this CTA
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-  const int crank = CLUSTER > 1 ? static_cast<int>(cluster_ctarank()) : 0;
-  if (CLUSTER > 1) cluster_sync_all();      // peers' barriers are initialised before anything is multicast into this CTA
   pdl_grid_sync();
 
-  // work units: (group of CLUSTER consecutive query blocks, gallery chunk); CTA `crank` of a cluster takes query block
-  // group * CLUSTER + crank (a block past the end scores zero-filled queries and writes nothing)
-  const int q_groups = (p.q_blocks + CLUSTER - 1) / CLUSTER;
+  // work units: (group of PAIR consecutive query blocks, gallery chunk); CTA `crank` of a pair takes query block
+  // group * PAIR + crank (a block past the end scores zero-filled queries and writes nothing)
+  const int q_groups = (p.q_blocks + PAIR - 1) / PAIR;
   const int units = q_groups * p.chunks;
-  const int cluster_id = static_cast<int>(blockIdx.x) / CLUSTER, n_clusters = static_cast<int>(gridDim.x) / CLUSTER;
-  constexpr uint16_t kMask = static_cast<uint16_t>((1u << CLUSTER) - 1u);
-  constexpr int kSliceRows = kBN / CLUSTER;
+  const int cluster_id = static_cast<int>(blockIdx.x) / PAIR, n_clusters = static_cast<int>(gridDim.x) / PAIR;
+  constexpr int kSliceRows = kBN / PAIR;
   auto tiles_of = [&](int chunk) -> int {
     const long long g0 = p.g_begin + 1LL * chunk * p.chunk_rows;
     const long long g1 = min(p.ng, g0 + p.chunk_rows);
@@ -240,28 +236,37 @@ cosine_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0, qphase = 0;
       for (int unit = cluster_id; unit < units; unit += n_clusters) {
-        const int qb = (unit % q_groups) * CLUSTER + crank, chunk = unit / q_groups;
+        const int qb = (unit % q_groups) * PAIR + crank, chunk = unit / q_groups;
         mbar_wait_backoff(qempty_bar, qphase ^ 1u, p.wait_ns);
-        mbar_arrive_expect_tx(qfull_bar, static_cast<uint32_t>(p.kb * kQSlab));
-        for (int kb = 0; kb < p.kb; ++kb) tma_load_2d(q_base + kb * kQSlab, &tmap_q, qfull_bar, kb * kBK, qb * kBM);
+        if (PAIR == 1) {
+          mbar_arrive_expect_tx(qfull_bar, static_cast<uint32_t>(p.kb * kQSlab));
+          for (int kb = 0; kb < p.kb; ++kb) tma_load_2d(q_base + kb * kQSlab, &tmap_q, qfull_bar, kb * kBK, qb * kBM);
+        } else {
+          if (leader) mbar_arrive_expect_tx(qfull_bar, static_cast<uint32_t>(2 * p.kb * kQSlab));
+          for (int kb = 0; kb < p.kb; ++kb) tma_load_2d_cg2(q_base + kb * kQSlab, &tmap_q, qfull_bar, kb * kBK, qb * kBM);
+          if (!leader) mbar_arrive_remote(qfull_bar, 0u);
+        }
         qphase ^= 1u;
         const int nt = tiles_of(chunk);
         const long long g0 = p.g_begin + 1LL * chunk * p.chunk_rows;
         for (int t = 0; t < nt; ++t)
           for (int kb = 0; kb < p.kb; ++kb) {
             mbar_wait_backoff(empty_bar(stage), phase ^ 1u, p.wait_ns);
-            mbar_arrive_expect_tx(full_bar(stage), kBStage);       // the whole tile: CLUSTER slices, one from each CTA
-            if (CLUSTER == 1)
-              tma_load_2d(b_base + stage * kBStage, &tmap_g, full_bar(stage), kb * kBK, static_cast<int>(g0 + 1LL * t * kBN));
-            else
-              tma_load_2d_mc(b_base + stage * kBStage + crank * (kSliceRows * kBK * 2), &tmap_g, full_bar(stage), kb * kBK,
-                             static_cast<int>(g0 + 1LL * t * kBN) + crank * kSliceRows, kMask);
-            if (++stage == kBStages) { stage = 0; phase ^= 1u; }
+            if (PAIR == 1) {
+              mbar_arrive_expect_tx(full_bar(stage), kBStage);
+              tma_load_2d(b_base + stage * kStageBytes, &tmap_g, full_bar(stage), kb * kBK, static_cast<int>(g0 + 1LL * t * kBN));
+            } else {
+              if (leader) mbar_arrive_expect_tx(full_bar(stage), kBStage);       // the whole tile: one half from each CTA
+              tma_load_2d_cg2(b_base + stage * kStageBytes, &tmap_g, full_bar(stage), kb * kBK,
+                              static_cast<int>(g0 + 1LL * t * kBN) + crank * kSliceRows);
+              if (!leader) mbar_arrive_remote(full_bar(stage), 0u);
+            }
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (lane == 0 && leader) {
       int stage = 0; uint32_t phase = 0, qphase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int unit = cluster_id; unit < units; unit += n_clusters) {
@@ -278,19 +283,32 @@ cosine_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
             mbar_wait_backoff(full_bar(stage), phase, p.wait_ns);
             tc_fence_after();
             const uint64_t da = make_sw128_desc(q_base + kb * kQSlab, 16, 1024);
-            const uint64_t db = make_sw128_desc(b_base + stage * kBStage, 16, 1024);
+            const uint64_t db = make_sw128_desc(b_base + stage * kStageBytes, 16, 1024);
+            if (PAIR == 1) {
 #pragma unroll
-            for (int k = 0; k < kBK / 16; ++k) umma_f16(d_tmem, da + 2u * k, db + 2u * k, p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
-            if (CLUSTER == 1) umma_commit(empty_bar(stage));
-            else umma_commit_mc(empty_bar(stage), kMask);       // the slot is refilled by all CTAs: tell every producer
-            if (kb == p.kb - 1) umma_commit(tfull_bar(acc));
-            if (++stage == kBStages) { stage = 0; phase ^= 1u; }
+              for (int k = 0; k < kBK / 16; ++k) umma_f16(d_tmem, da + 2u * k, db + 2u * k, p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              umma_commit(empty_bar(stage));
+              if (kb == p.kb - 1) umma_commit(tfull_bar(acc));
+            } else {
+#pragma unroll
+              for (int k = 0; k < kBK / 16; ++k) umma_f16_cg2(d_tmem, da + 2u * k, db + 2u * k, p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              umma_commit_cg2(empty_bar(stage));                 // the slot is free again in both CTAs
+              if (kb == p.kb - 1) umma_commit_cg2(tfull_bar(acc));
+            }
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1u;
         }
-        umma_commit(qempty_bar);     // every MMA that read this unit's Q slabs has retired
+        if (PAIR == 1) umma_commit(qempty_bar);     // every MMA that read this unit's Q slabs has retired
+        else umma_commit_cg2(qempty_bar);
       }
+      if (PAIR > 1)        // the peer's last arrivals on this CTA's barriers must have landed before it may exit
+        for (int a2 = 0; a2 < 2; ++a2) {
+          mbar_wait_backoff(tempty_bar(acc), acc_phase ^ 1u, p.wait_ns);
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1u;
+        }
     }
   } else {
     const int q = warp & 3;                     // TMEM lane quadrant this warp may read
@@ -300,7 +318,7 @@ cosine_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     uint2* list = warp_lists + 1LL * lane * kCap;
     int acc = 0; uint32_t acc_phase = 0;
     for (int unit = cluster_id; unit < units; unit += n_clusters) {
-      const int qb = (unit % q_groups) * CLUSTER + crank, chunk = unit / q_groups;
+      const int qb = (unit % q_groups) * PAIR + crank, chunk = unit / q_groups;
       const long long qrow = 1LL * qb * kBM + row;
       const bool live = qrow < p.nq;
       const long long self_col = p.exclude_self ? (p.self_offset + qrow) : -(1LL << 62);
@@ -372,7 +390,10 @@ cosine_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        if (lane == 0) {
+          if (PAIR > 1 && !leader) mbar_arrive_remote(tempty_bar(acc), 0u);     // the leader's MMA thread waits for both CTAs
+          else mbar_arrive(tempty_bar(acc));
+        }
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
         // keep room for a full half tile of survivors
@@ -426,8 +447,12 @@ cosine_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   }
   tc_fence_before();
   __syncthreads();
-  if (CLUSTER > 1) cluster_sync_all();      // no CTA may leave while peers can still multicast into it / arrive on its barriers
-  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+  if (PAIR > 1) cluster_sync_all();      // no CTA of the pair leaves (or frees TMEM) while the other can still reach it
+  if (warp == 2) {
+    tc_fence_after();
+    if (PAIR > 1) tmem_dealloc_cg2(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -945,20 +970,30 @@ struct Layout {
 // more candidate appends per query and one more pair of lists to merge: with at least two query blocks per SM there is
 // one chunk; below that, enough (q_block, chunk) units to fill the SMs ~3 times, chunks >= 16 tiles, and the unit count
 // close to a multiple of the CTA count (the units are equal-sized: a ragged last wave is pure loss)
-void pick_chunks(long long rows, int q_blocks, int sms, int* chunks, long long* chunk_rows) {
+// CTA pairs (cta_group::2) whenever there are at least two query blocks (B200_GALLERY_PAIR=0: single CTAs, for A/B measurements)
+bool use_pair(int q_blocks) {
+  static const bool env_off = [] { const char* e = getenv("B200_GALLERY_PAIR"); return e != nullptr && e[0] == '0'; }();
+  return !env_off && q_blocks >= 2;
+}
+
+// How many chunks the gallery is cut into.  Work units are (query group, chunk) pairs dealt round-robin to `slots` CTAs (or
+// CTA pairs).  Few query groups need chunks to fill the machine at all; with many (>= 2 per slot) one chunk is best even when
+// the last wave is ragged: 391 query blocks x 125 k rows measured 11.2 ms in one chunk (2.64 waves) against 11.7 ms in three
+// (7.93 waves) - every extra chunk restarts the candidate lists from the witness threshold, and that costs more than the tail.
+void pick_chunks(long long rows, int q_groups, int slots, int* chunks, long long* chunk_rows) {
   const long long tiles = (rows + kBN - 1) / kBN;
-  long long best = 1;
-  if (q_blocks < 2 * sms) {
-    long long want = (3LL * sms + q_blocks - 1) / q_blocks;
-    const long long cap = std::max<long long>(1, std::min<long long>(tiles / 16, 31));
-    want = std::max<long long>(1, std::min(want, cap));
-    best = want;
-    double best_waste = 1e9;
-    for (long long c = want; c <= std::min(cap, want * 2); ++c) {
-      const long long units = c * q_blocks, ctas = std::min<long long>(units, sms);
-      const double waste = static_cast<double>((units + ctas - 1) / ctas * ctas - units) / units;
-      if (waste < best_waste - 1e-9) { best_waste = waste; best = c; }
-    }
+  const long long cap = std::max<long long>(1, std::min<long long>(tiles / 16, 31));
+  long long lo = 1, hi = 1;
+  if (q_groups < 2 * slots) {
+    lo = std::max<long long>(1, std::min<long long>((3LL * slots + q_groups - 1) / q_groups, cap));
+    hi = std::min(cap, lo * 2);
+  }
+  long long best = lo;
+  double best_waste = 1e9;
+  for (long long c = lo; c <= hi; ++c) {
+    const long long units = c * q_groups, ctas = std::min<long long>(units, slots);
+    const double waste = static_cast<double>((units + ctas - 1) / ctas * ctas - units) / units;
+    if (waste < best_waste - 1e-9) { best_waste = waste; best = c; }
   }
   const long long tpc = (tiles + best - 1) / best;
   *chunk_rows = tpc * kBN;
@@ -970,7 +1005,8 @@ Layout plan_layout(long long nq, long long ng) {
   L.q_blocks = static_cast<int>((nq + kBM - 1) / kBM);
   const int sms = b200_num_sms();
   L.witness_rows = (ng >= 4LL * kWitnessRows) ? kWitnessRows : 0;      // small galleries: the unseeded flood is cheaper
-  pick_chunks(ng, L.q_blocks, sms, &L.chunks, &L.chunk_rows);
+  if (use_pair(L.q_blocks)) pick_chunks(ng, (L.q_blocks + 1) / 2, sms / 2, &L.chunks, &L.chunk_rows);
+  else pick_chunks(ng, L.q_blocks, sms, &L.chunks, &L.chunk_rows);
   L.lists = 2 * L.chunks;
   long long off = 0;
   auto take = [&](long long bytes) { long long o = off; off = (off + bytes + 255) / 256 * 256; return o; };
@@ -985,13 +1021,11 @@ Layout plan_layout(long long nq, long long ng) {
   return L;
 }
 
-constexpr int kCluster = 4;
-
-template <int CLUSTER>
+template <int PAIR>
 int launch_one(const CUtensorMap& tq, const CUtensorMap& tg, const FilterParams& p, int ctas, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(cosine_filter_kernel<CLUSTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    B200_CHECK_CUDA(cudaFuncSetAttribute(cosine_filter_kernel<PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     attr_done = true;
   }
   cudaLaunchConfig_t cfg = {};
@@ -1003,63 +1037,41 @@ int launch_one(const CUtensorMap& tq, const CUtensorMap& tg, const FilterParams&
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   int n = 1;
-  if (CLUSTER > 1) {
+  if (PAIR > 1) {
     attr[1].id = cudaLaunchAttributeClusterDimension;
-    attr[1].val.clusterDim.x = CLUSTER; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+    attr[1].val.clusterDim.x = PAIR; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
     n = 2;
   }
   cfg.attrs = attr;
   cfg.numAttrs = n;
-  B200_CHECK_CUDA(cudaLaunchKernelEx(&cfg, cosine_filter_kernel<CLUSTER>, tq, tg, p));
+  B200_CHECK_CUDA(cudaLaunchKernelEx(&cfg, cosine_filter_kernel<PAIR>, tq, tg, p));
   b200_count_launch();
   return B200_OK;
 }
 
-// how many clusters of kCluster CTAs can be resident at once (the GPC layout strands a few SMs for clusters of 4)
-int max_clusters() {
-  static int cached = -1;
-  if (cached < 0) {
-    cudaFuncSetAttribute(cosine_filter_kernel<kCluster>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(b200_num_sms() / kCluster * kCluster);
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = kSmem;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = kCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, cosine_filter_kernel<kCluster>, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = 0; }
-    cached = n;
-  }
-  return cached;
-}
-
-// the passes of one top-k call; clusters when there are enough query blocks to fill them
-int launch_filter(const CUtensorMap& tq, const CUtensorMap& tg, const CUtensorMap& tg_slice, FilterParams p, const Layout& L, cudaStream_t st) {
+// the passes of one top-k call
+int launch_filter(const CUtensorMap& tq, const CUtensorMap& tg, const CUtensorMap& tg_half, FilterParams p, const Layout& L, cudaStream_t st) {
   const int sms = b200_num_sms();
-  const int ncl = max_clusters();
-  static const bool env_on = [] { const char* e = getenv("B200_GALLERY_CLUSTER"); return e != nullptr && e[0] == '1'; }();
-  const bool use_cluster = env_on && ncl > 0 && L.q_blocks >= 2 * kCluster;
-  auto run = [&](int units_single) -> int {
-    if (use_cluster) {
-      const int q_groups = (L.q_blocks + kCluster - 1) / kCluster;
-      const int units = q_groups * p.chunks;
-      return launch_one<kCluster>(tq, tg_slice, p, std::min(units, ncl) * kCluster, st);
+  const bool pair = use_pair(L.q_blocks);
+  auto run = [&](int q_blocks, int chunks) -> int {
+    if (pair) {
+      FilterParams pp = p;
+      pp.idesc = gemm::make_idesc(false, kBN, false, 256);
+      const int units = (q_blocks + 1) / 2 * chunks;
+      return launch_one<2>(tq, tg_half, pp, 2 * std::min(units, sms / 2), st);
     }
-    return launch_one<1>(tq, tg, p, std::min(units_single, sms), st);
+    return launch_one<1>(tq, tg, p, std::min(q_blocks * chunks, sms), st);
   };
   int rc;
   p.g_begin = 0;
   if (L.witness_rows > 0) {
     p.ng = L.witness_rows; p.chunks = 1; p.chunk_rows = L.witness_rows;
     p.witness = 1; p.tau_init = nullptr; p.tau_out = L.tau_ptr;
-    if ((rc = run(L.q_blocks))) return rc;
+    if ((rc = run(L.q_blocks, 1))) return rc;
   }
   p.ng = L.ng; p.chunks = L.chunks; p.chunk_rows = L.chunk_rows;
   p.witness = 0; p.tau_init = L.witness_rows ? L.tau_ptr : nullptr; p.tau_out = nullptr;
-  return run(L.q_blocks * L.chunks);
+  return run(L.q_blocks, L.chunks);
 }
 
 }  // namespace
@@ -1154,10 +1166,10 @@ static int cosine_topk_impl(const float* q, const void* q_unit_f16, const double
   if (rc) return rc;
   rc = gemm::encode_tmap_2d(&tg, false, g_unit_f16, dim, ng, dim, kBK, kBN);
   if (rc) return rc;
-  CUtensorMap tg_slice;      // one cluster CTA's share of a gallery tile
-  rc = gemm::encode_tmap_2d(&tg_slice, false, g_unit_f16, dim, ng, dim, kBK, kBN / kCluster);
+  CUtensorMap tg_half;       // one CTA's half of a gallery tile in pair mode
+  rc = gemm::encode_tmap_2d(&tg_half, false, g_unit_f16, dim, ng, dim, kBK, kBN / 2);
   if (rc) return rc;
-  rc = launch_filter(tq, tg, tg_slice, p, L, st);
+  rc = launch_filter(tq, tg, tg_half, p, L, st);
   if (rc) return rc;
   const int per_warp = kKP * static_cast<int>(sizeof(Cand)) + L.lists * kKP * 8;      // exact stage + candidate keys of one query
   const int wpc = std::max(1, std::min(8, (200 * 1024) / per_warp));                  // queries (warps) per CTA

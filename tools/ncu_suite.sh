@@ -16,5 +16,6 @@ cap attn_bwd window_attn_bwd 2 attn_bwd
 cap attn_fwd window_attn_fwd 2 attn_fwd
 cap ln_fwd layernorm_fwd 2 ln
 cap ln_bwd layernorm_bwd 2 ln
-cap gallery cosine_filter 1 gallery
+cap gallery_filter cosine_filter 3 gallery_bench
+cap gallery_rerank rerank_kernel 1 gallery_bench
 ls -la gpurun_out/

@@ -12,7 +12,9 @@ ALG = {'gemm_fc1': ("fc1 + GELU + GELU' (M=802816, N=384, K=96; bf16 in, two bf1
        'attn_fwd': ('window attention forward, stage 1', 4 * M * C * 2 + M * 3 * 4),
        'ln_fwd': ('LayerNorm forward C=96 (M=802816)', 2 * M * C * 2 + 2 * M * 4),
        'ln_bwd': ('LayerNorm backward C=96 (M=802816), residual input = dy in this driver', 3 * M * C * 2 + 2 * M * 4),
-       'gallery': ('cosine filter 8192 queries x 262144 gallery rows, 512-d fp16', (8192 + 262144) * 512 * 2)}
+       'gallery': ('cosine filter 8192 queries x 262144 gallery rows, 512-d fp16', (8192 + 262144) * 512 * 2),
+       'gallery_filter': ('cosine filter main pass, 50000 queries x 125000 gallery rows, 512-d fp16 (bench gallery leg)', (50000 + 125000) * 512 * 2),
+       'gallery_rerank': ('exact fp64 re-rank of 128 candidates per query, 50000 queries (fp32 rows gathered)', 50000 * 129 * 512 * 4)}
 SCALE = {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1, 'us': 1e-6, 'ms': 1e-3, 'ns': 1e-9, 's': 1}
 
 

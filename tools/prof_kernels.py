@@ -2,7 +2,7 @@
 
     ncu --set full --clock-control none --import-source on -k regex:<kernel> -c 1 -o gpurun_out/<name> python tools/prof_kernels.py <what>
 
-what: attn_bwd | attn_fwd | gemm_fc1 | gemm_qkv | gemm_fc2 | gemm_outproj | gemm_wgrad | gemm_wgrad_small | ln | gallery | gallery_big
+what: attn_bwd | attn_fwd | gemm_fc1 | gemm_qkv | gemm_fc2 | gemm_outproj | gemm_wgrad | gemm_wgrad_small | ln | gallery | gallery_bench | gallery_big
 Each op runs 3 times (the first launches warm the caches / instruction memory); capture with -s to skip warm-ups.
 """
 import sys
@@ -42,6 +42,10 @@ def main(what, stage=0, B=256):
         x, w = rnd(M, C), rnd(3 * C, C)
         for _ in range(3):
             ops.gemm_tn(x, w)
+    elif what == 'gemm_dqkv':          # data gradient of the qkv projection: K = 3C, N = C
+        x, w = rnd(M, 3 * C), rnd(C, 3 * C)
+        for _ in range(3):
+            ops.gemm_tn(x, w)
     elif what == 'gemm_fc2':
         x, w, b, r = rnd(M, 4 * C), rnd(C, 4 * C), torch.randn(C, device='cuda'), rnd(M, C)
         for _ in range(3):
@@ -69,6 +73,14 @@ def main(what, stage=0, B=256):
         gal = torch.randn(262144, 512, device='cuda', generator=g)
         for _ in range(2):
             gallery.cosine_topk(q, gal, 100)
+    elif what == 'gallery_bench':    # the bench leg's shape per GPU through the certified path (witness pass, filter, re-rank)
+        from b200 import gallery
+        gal = torch.randn(125000, 512, device='cuda', generator=g)
+        q = gal[:50000].contiguous()
+        gp = gallery.Prepared(gal, as_gallery=True)
+        qp = gallery.Prepared(q, as_gallery=False, frame_of=gp)
+        for _ in range(2):
+            gallery.cosine_topk(q, gal, 100, exclude_self_offset=0, q_prepared=qp, g_prepared=gp)
     elif what == 'gallery_big':      # the bench leg's size per GPU, timed with events (not for use under ncu)
         from b200 import gallery
         q = torch.randn(50000, 512, device='cuda', generator=g)
