@@ -238,6 +238,38 @@ int b200_pair_similarity(const float* emb, long long n, int dim, const long long
 int b200_recall_hits(const int* top_idx, long long nq, int k_stride, const long long* q_class, const long long* g_class,
                      const int* ks, int n_ks, unsigned long long* hits, void* stream);
 
+/* ---- convolutional FE backbone: torchvision.models.resnet50 with fc -> 512, the model() of the reference's FE configs
+ *      (configs/dog_fe/fe_dogs_config.py:96-109).  Activations: bf16 NHWC rows on a padded grid, (H + 2) x (W + 2) rows per
+ *      image with a ring of zero rows (H = 0: plain [rows, C] matrix); see csrc/convnet.cu ------------------------------ */
+/* Implicit convolution: out[r, n] = sum_t sum_c a[r + tap_shift[t], c] * b[n, t * C + c] (+ aux[r, n] with B200_EPI_RESID);
+ * a [M, C] bf16 (C % 64 == 0), b [N, taps * C] bf16, out / aux [M, N] bf16; rows outside [0, M) read as zero.  A 3x3 convolution
+ * on a padded grid is taps = 9, tap_shift = dy * (W + 2) + dx; its data gradient the same call with negated shifts. */
+int b200_gemm_taps(const void* a, long long lda, const void* b, long long ldb, int M, int N, int C, int taps, const int* tap_shift,
+                   int mode, void* out, long long ldo, const void* aux, long long ldaux, void* stream);
+int b200_bn_stats_blocks(long long rows);
+/* nn.BatchNorm2d, training mode: batch statistics over the interior rows (count of them given) -> out [4][C] = scale, shift,
+ * mean, rstd; running statistics (nullable) updated with `momentum` (unbiased variance).  scratch [blocks][2][C] floats. */
+int b200_bn_stats(const void* x, long long rows, int C, int H, int W, double count, const float* gamma, const float* beta,
+                  float* running_mean, float* running_var, float momentum, float eps, float* out, float* scratch, void* stream);
+/* y = [relu](x * scale + shift [+ residual]) on interior rows, zero on the ring */
+int b200_bn_apply(const void* x, const float* scale, const float* shift, const void* residual, int relu, long long rows, int C, int H,
+                  int W, void* y, void* stream);
+/* BatchNorm (+ ReLU when y is given) backward: sums [2][C] = dbeta, dgamma; dx; dz_out (nullable) = dy * [y > 0];
+ * count = 0: frozen (eval-mode) statistics, dx = gamma * rstd * dz */
+int b200_bn_backward(const void* dy, const void* y, const void* x, const float* stats, const float* gamma, long long rows, int C, int H,
+                     int W, double count, void* dx, void* dz_out, float* sums, float* scratch, void* stream);
+/* conv1 (7x7, stride 2, pad 3) patches: img [B, 3, H, W] uint8 (x / 255) or fp32 -> cols [B * H/2 * W/2, 160] bf16, column
+ * (r * 7 + s) * 3 + c, columns 147..159 zero */
+int b200_stem_im2col(const void* img, int is_u8, int B, int H, int W, void* cols, void* stream);
+/* bn1 + relu + MaxPool2d(3, 2, 1) fused: a [B * IH * IW, C] -> y on the padded (IH / 2, IW / 2) grid, tap [B * IH/2 * IW/2, C] u8 */
+int b200_stem_pool_fwd(const void* a, const float* scale, const float* shift, int B, int IH, int IW, int C, void* y, void* tap, void* stream);
+int b200_stem_pool_bwd(const void* dy, const void* tap, const void* a, const float* scale, const float* shift, int B, int IH, int IW,
+                       int C, void* dz, void* stream);
+/* stride-2 sampling between padded grids (pixels (2 i, 2 j) of the (H, W) grid) and its adjoint */
+int b200_grid_sample2(const void* src, int B, int H, int W, int C, int down, void* dst, void* stream);
+/* AdaptiveAvgPool2d(1) over the interior: forward x (grid) -> out [B, C]; backward x = d_out [B, C] -> out (grid) */
+int b200_grid_avgpool(const void* x, int B, int H, int W, int C, int backward, void* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

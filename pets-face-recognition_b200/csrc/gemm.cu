@@ -562,9 +562,10 @@ int reduce_or_defer(const float* partial, float* const* outs, int ny, long long 
 // ---------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------
-extern "C" int b200_gemm_tn(const void* a, long long lda, const void* b, long long ldb, int M, int N, int K, int is_bf16,
-                            int mode, void* out, long long ldo, int out_fp32, void* out2, long long ldo2, const float* bias,
-                            const void* aux, long long ldaux, int splits, long long split_stride, int block_n, void* stream) {
+static int gemm_tn_impl(const void* a, long long lda, const void* b, long long ldb, int M, int N, int K, int is_bf16,
+                        int mode, void* out, long long ldo, int out_fp32, void* out2, long long ldo2, const float* bias,
+                        const void* aux, long long ldaux, int splits, long long split_stride, int block_n, void* stream,
+                        int taps, const int* tap_shift) {
   B200_REQUIRE(N % 8 == 0, "gemm_tn: N must be a multiple of 8 (got %d)", N);
   B200_REQUIRE(mode >= B200_EPI_STORE && mode <= B200_EPI_DGELU_Q8, "gemm_tn: bad epilogue mode %d", mode);
   const bool q8 = mode == B200_EPI_GELU_Q8 || mode == B200_EPI_DGELU_Q8;      // the GELU derivative travels as 8-bit codes
@@ -575,6 +576,8 @@ extern "C" int b200_gemm_tn(const void* a, long long lda, const void* b, long lo
   if (mode != B200_EPI_GELU) out2 = nullptr;
   const int eb = (out_fp32 || mode == B200_EPI_PARTIAL) ? 4 : 2;
   gemm::Operands o{a, (int)lda, b, (int)ldb, M, N, K, is_bf16 != 0, block_n, splits, 0};
+  o.taps = taps;
+  for (int t = 0; t < taps; ++t) o.tap_shift[t] = tap_shift[t];
   const bool use_aux = mode == B200_EPI_RESID || mode == B200_EPI_DGELU;
   B200_REQUIRE(!(use_aux && eb != 2), "gemm_tn: RESID / DGELU epilogues write bf16");
   B200_REQUIRE(!(mode == B200_EPI_GELU && eb != 2), "gemm_tn: the GELU epilogue writes bf16");
@@ -615,6 +618,25 @@ extern "C" int b200_gemm_tn(const void* a, long long lda, const void* b, long lo
       return gemm::launch<gemm::EpiLinear<B200_EPI_DGELU>, 2, false, true>(o, od, {bias}, st);
     default: return gemm::launch<gemm::EpiLinear<B200_EPI_PARTIAL>, 4, false, false>(o, od, {bias}, st);
   }
+}
+
+extern "C" int b200_gemm_tn(const void* a, long long lda, const void* b, long long ldb, int M, int N, int K, int is_bf16,
+                            int mode, void* out, long long ldo, int out_fp32, void* out2, long long ldo2, const float* bias,
+                            const void* aux, long long ldaux, int splits, long long split_stride, int block_n, void* stream) {
+  return gemm_tn_impl(a, lda, b, ldb, M, N, K, is_bf16, mode, out, ldo, out_fp32, out2, ldo2, bias, aux, ldaux, splits, split_stride, block_n,
+                      stream, 0, nullptr);
+}
+
+// Implicit convolution on the tensor cores: out[r, n] = sum_t sum_c a[r + tap_shift[t], c] * b[n, t * C + c] (+ aux[r, n] with
+// B200_EPI_RESID) for bf16 a [M, C] (C a multiple of 64) and b [N, taps * C].  With the activations of a padded NHWC grid stored
+// as rows ((image, y, x) -> row, one zero ring around every image) a 3x3 convolution is the nine shifts (dy * padded_width + dx):
+// no im2col matrix exists anywhere, the TMA producer reads the shifted row blocks straight from the activation tensor (rows
+// outside [0, M) come back as zeros).  torchvision.models.resnet50 conv2 of every Bottleneck, as configs/dog_fe/fe_dogs_config.py:96-109 uses it.
+extern "C" int b200_gemm_taps(const void* a, long long lda, const void* b, long long ldb, int M, int N, int C, int taps, const int* tap_shift,
+                              int mode, void* out, long long ldo, const void* aux, long long ldaux, void* stream) {
+  B200_REQUIRE(taps >= 1 && taps <= 9 && tap_shift != nullptr && C % 64 == 0, "gemm_taps: taps in [1, 9], C a multiple of 64 (taps=%d C=%d)", taps, C);
+  B200_REQUIRE(mode == B200_EPI_STORE || mode == B200_EPI_RESID, "gemm_taps: STORE or RESID epilogue");
+  return gemm_tn_impl(a, lda, b, ldb, M, N, taps * C, 1, mode, out, ldo, 0, nullptr, 0, nullptr, aux, ldaux, 1, 0, 0, stream, taps, tap_shift);
 }
 
 // dW[N,K] (fp32 split partials) = dY[tokens,N]^T * X[tokens,K]: both operands are read in place, MN-major - no transposes.

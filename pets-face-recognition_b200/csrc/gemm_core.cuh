@@ -76,6 +76,10 @@ struct CoreParams {
   int m_pairs;               // CTA-pair variant: pairs of row blocks = ceil(m_blocks / 2)
   FastDiv div_mp;
   uint32_t idesc2, idesc2_last;   // M = 256 instruction descriptors of the cta_group::2 MMA
+  // Implicit convolution (K-major only): the contraction runs over `taps` filter taps x kb_per_tap K blocks of channels; tap t
+  // reads the rows of A shifted by tap_shift[t] (rows outside [0, M) are zero-filled by the TMA) - see b200_gemm_taps
+  int taps, kb_per_tap;
+  int tap_shift[9];
 };
 
 // instruction descriptor, kind::f16: [4,6) D fmt (1=f32), [7,10) A fmt, [10,13) B fmt (0=f16, 1=bf16),
@@ -230,10 +234,16 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait_backoff(empty_bar(stage), phase ^ 1u, p.wait_ns);
           const uint32_t sa = smem_base + stage * p.stage_bytes;
+          int a_col = kb * kBlockK, a_row = m_blk * kBlockM;
+          if (p.taps > 0) {                       // implicit convolution: K block -> (filter tap, channel block)
+            const int t = kb / p.kb_per_tap;
+            a_col = (kb - t * p.kb_per_tap) * kBlockK;
+            a_row += p.tap_shift[t];
+          }
           if (CG2) {
             // this CTA's 128 rows of A and its half of the B tile; the bytes of both CTAs complete on the leader's barrier
             if (leader) mbar_arrive_expect_tx(full_bar(stage), 2u * kABytes + static_cast<uint32_t>(p.block_n * kBlockK * 2));
-            tma_load_2d_cg2(sa, &tmap_a, full_bar(stage), kb * kBlockK, m_blk * kBlockM);
+            tma_load_2d_cg2(sa, &tmap_a, full_bar(stage), a_col, a_row);
             tma_load_2d_cg2(sa + kABytes, &tmap_b, full_bar(stage), kb * kBlockK, n_blk * p.block_n + static_cast<int>(cta_rank) * (p.block_n >> 1));
             if (!leader) mbar_arrive_remote(full_bar(stage), 0u);
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -241,7 +251,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
           mbar_arrive_expect_tx(full_bar(stage), tx_bytes);
           if (!p.mn_major) {
-            tma_load_2d(sa, &tmap_a, full_bar(stage), kb * kBlockK, m_blk * kBlockM);
+            tma_load_2d(sa, &tmap_a, full_bar(stage), a_col, a_row);
             tma_load_2d(sa + kABytes, &tmap_b, full_bar(stage), kb * kBlockK, n_blk * p.block_n);
           } else {
             for (int c = 0; c < 2; ++c) tma_load_2d(sa + c * kChunk, &tmap_a, full_bar(stage), m_blk * kBlockM + c * 64, kb * kBlockK);
@@ -536,6 +546,8 @@ struct Operands {
   int splits;                 // <= 1 = no split-K
   int max_ctas;               // 0 = #SMs
   bool mn_major = false;      // D = A^T B with the contraction over the ROWS of both operands (weight gradients)
+  int taps = 0;               // > 0: implicit convolution - A is [M, K / taps], tap t contributes its rows shifted by tap_shift[t]
+  int tap_shift[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 struct Output {
@@ -595,10 +607,18 @@ int launch(const Operands& o, const Output& out, const typename Epi::Params& ep,
     B200_REQUIRE(!o.mn_major && p.splits == 1 && o.N % p.block_n == 0 && p.block_n % 32 == 0 && out.colsum == nullptr,
                  "gemm: the CTA-pair variant needs a K-major, unsplit problem whose N is a multiple of the tile width");
 
+  p.taps = o.taps;
+  p.kb_per_tap = 0;
+  if (o.taps > 0) {
+    B200_REQUIRE(!o.mn_major && o.taps <= 9 && o.K % (o.taps * kBlockK) == 0 && p.splits == 1,
+                 "gemm: implicit convolution needs K-major operands and K / taps a multiple of 64 (K=%d taps=%d)", o.K, o.taps);
+    p.kb_per_tap = o.K / o.taps / kBlockK;
+    for (int t = 0; t < 9; ++t) p.tap_shift[t] = o.tap_shift[t];
+  }
   CUtensorMap ta, tb;
   int rc;
   if (!o.mn_major) {
-    rc = encode_tmap_2d(&ta, o.is_bf16, o.a, o.K, o.M, o.lda, kBlockK, kBlockM);
+    rc = encode_tmap_2d(&ta, o.is_bf16, o.a, o.taps > 0 ? o.K / o.taps : o.K, o.M, o.lda, kBlockK, kBlockM);
     if (rc) return rc;
     rc = encode_tmap_2d(&tb, o.is_bf16, o.b, o.K, o.N, o.ldb, kBlockK, CG2 ? p.block_n / 2 : p.block_n);
   } else {
