@@ -16,19 +16,19 @@ from b200.convnet import ConvNetEngine, ConvNetFunction
 class ResNet(torchvision.models.ResNet):
     def __init__(self, *args, **kwargs):
         super().__init__(*args, **kwargs)
-        self._engine = None
+        self._convnet = None
 
     @property
-    def engine(self) -> ConvNetEngine:
-        if self._engine is None:
-            object.__setattr__(self, '_engine', ConvNetEngine(self))      # not a sub-module: it only points back at this one
-        return self._engine
+    def convnet(self) -> ConvNetEngine:
+        if self._convnet is None:
+            object.__setattr__(self, "_convnet", ConvNetEngine(self))      # not a sub-module: it only points back at this one
+        return self._convnet
 
     def _forward_impl(self, x):
         params = [p for p in self.parameters()]
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
-            return ConvNetFunction.apply(self.engine, x, *params)
-        return self.engine.forward(x, False)
+            return ConvNetFunction.apply(self.convnet, x, *params)
+        return self.convnet.forward(x, False)
 
 
 def resnet50(pretrained=False, **kwargs):

@@ -213,3 +213,50 @@ def test_resnet50_has_no_cpu_fallback():
     from models import resnet50
     with pytest.raises(B200Error):
         resnet50().eval()(torch.zeros(1, 3, 224, 224))
+
+
+@pytest.mark.timeout(900)
+def test_resnet50_config_trains_validates_and_checkpoints(tmp_path):
+    """main.py's call sequence on the ResNet-50 synthetic config: the reference's model() hook (fc -> Linear(2048, 512)), its SGD
+    groups split on 'fc' in the parameter name, fit -> validation metrics -> checkpoints with torchvision's state-dict keys"""
+    import os
+    PKG = ROOT / 'pets-face-recognition_b200'
+    env = dict(SYNTH_TRAIN_IDS='8', SYNTH_VAL_IDS='6', SYNTH_PER_ID='4', SYNTH_BATCH='8', SYNTH_EPOCHS='2', SYNTH_WORKERS='0', SYNTH_PAIRS='30')
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        from engine import Controller
+        from utils import configure_trainer, get_config
+        cfg = get_config(PKG / 'configs/dog_fe/resnet50_dog_head_synth.py')
+        controller = Controller(cfg)
+        net = controller.model_loss.module
+        assert type(net).__name__ == 'ResNet' and net.fc.out_features == 512
+        opt = cfg.optimizer(controller.model_loss)[0][0]
+        assert [len(g['params']) for g in opt.param_groups] == [159, 2, 1]          # body / fc.weight + fc.bias / ArcFace weight
+        trainer = configure_trainer(cfg, None, tmp_path / 'ckpt')
+        w0 = net.fc.weight.detach().clone()
+        c0 = net.layer2[0].conv2.weight.detach().clone()
+        rm0 = net.layer3[1].bn2.running_mean.detach().clone()
+        trainer.fit(controller)
+        assert trainer.global_step == 2 * 4
+        for before, after in ((w0, net.fc.weight), (c0, net.layer2[0].conv2.weight), (rm0, net.layer3[1].bn2.running_mean)):
+            assert torch.isfinite(after).all() and not torch.equal(before.cpu(), after.detach().cpu())
+        assert int(net.bn1.num_batches_tracked) == 8
+        m = controller.last_metrics
+        for key in ('ROC AUC', 'Accuracy', 'Recall@K=5', 'Recall@K=10', 'Recall@K=100'):
+            assert key in m, key
+        sd = torch.load(sorted((tmp_path / 'ckpt').glob('epoch=*.ckpt'))[-1])
+        assert len(sd) == 321 and 'model_loss.module.layer4.2.bn3.running_var' in sd and 'model_loss.module.fc.bias' in sd
+        import torchvision
+        tv = torchvision.models.resnet50(weights=None)
+        tv.fc = torch.nn.Linear(2048, 512)
+        tv.load_state_dict({k[len('model_loss.module.'):]: v for k, v in sd.items() if k.startswith('model_loss.module.')})   # strict
+    finally:
+        os.chdir(cwd)
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
