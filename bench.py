@@ -386,6 +386,7 @@ def gpu_arm(args, rank, world, local_rank):
     extract = extract_leg(args, wrap, dev_batches, world, device) if not args.no_gallery else None
     rows_f = rows_f_leg(device) if (world == 1 and not args.no_gallery) else None
     pipeline = pipeline_leg(args, wrap, rank, world, device) if not args.no_gallery else None
+    resnet = resnet_leg(args, device, local_rank) if (world == 1 and not args.no_gallery) else None
 
     if rank != 0:
         return
@@ -443,6 +444,8 @@ def gpu_arm(args, rank, world, local_rank):
         line['gallery'] = gallery
     if pipeline is not None:
         line['pipeline'] = pipeline
+    if resnet is not None:
+        line['resnet50'] = resnet
     if world == 1 and not args.no_cpu_baseline:
         cb, steps_cb = 32, 2
         ips, _ = time_oracle(cb, 1, steps_cb)
@@ -485,6 +488,58 @@ def extract_leg(args, wrap, dev_batches, world, device):
     ms = t.item()
     return {'metric': 'FE extract images/sec (Swin-T forward, eval, bf16)', 'value': world * B / (ms * 1e-3), 'unit': 'images/s',
             'ms_per_batch': ms, 'batch_per_gpu': B, 'tflops': B * FWD_GFLOP * 1e9 / (ms * 1e-3) / 1e12, 'finite': bool(torch.isfinite(emb).all().item())}
+
+
+RESNET_FWD_GFLOP = 8.18          # torchvision resnet50 at 224 x 224: 4.09 GMAC per image (fc -> 512 included)
+
+
+def resnet_leg(args, device, local_rank):
+    """the FE backbone the reference's configs ship - torchvision's ResNet-50 with a 512-d fc
+    (configs/dog_fe/fe_dogs_config.py:96-109) - through the same loss wrapper, SGD groups and Trainer step as the main arm, at
+    the same per-GPU batch, uint8 images resident in HBM; then the eval-mode extraction.  N = 1 only."""
+    from engine.trainer import Trainer
+    from losses import SoftmaxBasedMetricLearning
+    from models import resnet50
+    torch.manual_seed(123)
+    model = resnet50()
+    model.fc = torch.nn.Linear(2048, 512)
+    wrap = SoftmaxBasedMetricLearning(model, num_class=NUM_CLASS, embedding_size=512, is_focal=True, arc_margin=True).to(device)
+    module = _Module(wrap)
+    opt = make_optimizer(wrap)
+    trainer = Trainer(gpus=[local_rank], strategy=None, max_epochs=1)
+    B = args.batch
+    g = torch.Generator(device=device).manual_seed(7)
+    batches = [{'x': torch.randint(0, 256, (B, 3, 224, 224), device=device, dtype=torch.uint8, generator=g),
+                'label': torch.randint(0, NUM_CLASS, (B,), device=device, generator=g)} for _ in range(2)]
+    steps = max(5, args.steps // 2)
+    for i in range(3):
+        loss = trainer.run_training_batch(module, batches[i % 2], [opt])
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(steps):
+        loss = trainer.run_training_batch(module, batches[i % 2], [opt])
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / steps
+    wrap.eval()
+    with torch.no_grad():
+        for i in range(2):
+            emb = wrap(batches[i % 2]['x'])
+        torch.cuda.synchronize()
+        ev0.record()
+        for i in range(steps):
+            emb = wrap(batches[i % 2]['x'])
+        ev1.record()
+        torch.cuda.synchronize()
+    ms_e = ev0.elapsed_time(ev1) / steps
+    out = {'metric': 'ResNet-50 FE (torchvision resnet50, fc -> 512) + ArcFace train step and eval extraction, bf16, synthetic uint8 images',
+           'batch_per_gpu': B, 'train_images_per_s': B / (ms * 1e-3), 'train_ms_per_step': ms, 'train_tflops': 3 * RESNET_FWD_GFLOP * B / ms,
+           'extract_images_per_s': B / (ms_e * 1e-3), 'extract_ms_per_batch': ms_e, 'extract_tflops': RESNET_FWD_GFLOP * B / ms_e,
+           'final_loss': float(loss), 'finite': bool(torch.isfinite(emb).all().item())}
+    del wrap, module, opt, trainer, batches, model
+    torch.cuda.empty_cache()
+    return out
 
 
 def _topk_spec_fp64_gpu(q, g, k, self_rows=None, chunk=32768):

@@ -246,6 +246,10 @@ int b200_recall_hits(const int* top_idx, long long nq, int k_stride, const long 
  * on a padded grid is taps = 9, tap_shift = dy * (W + 2) + dx; its data gradient the same call with negated shifts. */
 int b200_gemm_taps(const void* a, long long lda, const void* b, long long ldb, int M, int N, int C, int taps, const int* tap_shift,
                    int mode, void* out, long long ldo, const void* aux, long long ldaux, void* stream);
+/* its weight gradient: partial [splits][N][taps * C], dW[n, t * C + c] = sum_p dy[p, n] * x[p + tap_shift[t], c]; splits as
+ * b200_gemm_splits(tokens, splits) reports */
+int b200_gemm_wgrad_taps(const void* dy, long long ldy, const void* x, long long ldx, long long tokens, int N, int C, int taps,
+                         const int* tap_shift, float* partial, int splits, void* stream);
 int b200_bn_stats_blocks(long long rows);
 /* nn.BatchNorm2d, training mode: batch statistics over the interior rows (count of them given) -> out [4][C] = scale, shift,
  * mean, rstd; running statistics (nullable) updated with `momentum` (unbiased variance).  scratch [blocks][2][C] floats. */
@@ -254,10 +258,10 @@ int b200_bn_stats(const void* x, long long rows, int C, int H, int W, double cou
 /* y = [relu](x * scale + shift [+ residual]) on interior rows, zero on the ring */
 int b200_bn_apply(const void* x, const float* scale, const float* shift, const void* residual, int relu, long long rows, int C, int H,
                   int W, void* y, void* stream);
-/* BatchNorm (+ ReLU when y is given) backward: sums [2][C] = dbeta, dgamma; dx; dz_out (nullable) = dy * [y > 0];
+/* BatchNorm (+ ReLU when y is given; relu_from_x: the mask of y = relu(x * scale + shift) is recomputed from x) backward: sums [2][C] = dbeta, dgamma; dx; dz_out (nullable) = dy * [y > 0];
  * count = 0: frozen (eval-mode) statistics, dx = gamma * rstd * dz */
-int b200_bn_backward(const void* dy, const void* y, const void* x, const float* stats, const float* gamma, long long rows, int C, int H,
-                     int W, double count, void* dx, void* dz_out, float* sums, float* scratch, void* stream);
+int b200_bn_backward(const void* dy, const void* y, int relu_from_x, const void* x, const float* stats, const float* gamma, long long rows,
+                     int C, int H, int W, double count, void* dx, void* dz_out, float* sums, float* scratch, void* stream);
 /* conv1 (7x7, stride 2, pad 3) patches: img [B, 3, H, W] uint8 (x / 255) or fp32 -> cols [B * H/2 * W/2, 160] bf16, column
  * (r * 7 + s) * 3 + c, columns 147..159 zero */
 int b200_stem_im2col(const void* img, int is_u8, int B, int H, int W, void* cols, void* stream);
@@ -267,6 +271,8 @@ int b200_stem_pool_bwd(const void* dy, const void* tap, const void* a, const flo
                        int C, void* dz, void* stream);
 /* stride-2 sampling between padded grids (pixels (2 i, 2 j) of the (H, W) grid) and its adjoint */
 int b200_grid_sample2(const void* src, int B, int H, int W, int C, int down, void* dst, void* stream);
+/* patches of a stride-2 3x3 convolution: x on the (H, W) grid -> cols [rows of the (H / 2, W / 2) grid, 9 * C] (tap-major) */
+int b200_grid_patches_s2(const void* x, int B, int H, int W, int C, void* cols, void* stream);
 /* AdaptiveAvgPool2d(1) over the interior: forward x (grid) -> out [B, C]; backward x = d_out [B, C] -> out (grid) */
 int b200_grid_avgpool(const void* x, int B, int H, int W, int C, int backward, void* out, void* stream);
 

@@ -65,14 +65,16 @@ _PROTOS = {
     'b200_patch_gather_nhwc': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
     'b200_augment_train': (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     'b200_gemm_taps': (c_int, [c_vp, c_ll, c_vp, c_ll, c_int, c_int, c_int, c_int, C.POINTER(c_int), c_int, c_vp, c_ll, c_vp, c_ll, c_vp]),
+    'b200_gemm_wgrad_taps': (c_int, [c_vp, c_ll, c_vp, c_ll, c_ll, c_int, c_int, c_int, C.POINTER(c_int), c_vp, c_int, c_vp]),
     'b200_bn_stats_blocks': (c_int, [c_ll]),
     'b200_bn_stats': (c_int, [c_vp, c_ll, c_int, c_int, c_int, C.c_double, c_vp, c_vp, c_vp, c_vp, c_float, c_float, c_vp, c_vp, c_vp]),
     'b200_bn_apply': (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_ll, c_int, c_int, c_int, c_vp, c_vp]),
-    'b200_bn_backward': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, c_int, c_int, c_int, C.c_double, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'b200_bn_backward': (c_int, [c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_ll, c_int, c_int, c_int, C.c_double, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'b200_stem_im2col': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     'b200_stem_pool_fwd': (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
     'b200_stem_pool_bwd': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     'b200_grid_sample2': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    'b200_grid_patches_s2': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     'b200_grid_avgpool': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     'b200_mean_pool': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]),
     'b200_transpose16': (c_int, [c_vp, c_vp, c_ll, c_int, c_ll, c_ll, c_vp]),

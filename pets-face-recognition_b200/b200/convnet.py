@@ -62,13 +62,18 @@ class ConvNetEngine:
         self._token = 0
         self._shift_arrays: Dict[Tuple[int, int], C.Array] = {}
         self._frozen = False
+        self._counters: List[torch.Tensor] = []
+        self._eval_consts: Dict[int, tuple] = {}
 
     # ------------------------------------------------------------------ small wrappers over the C ABI
-    def _taps(self, a, w, W: int, sign: int, aux=None):
-        key = (W, sign)
-        arr = self._shift_arrays.get(key)
+    def _shift_array(self, W: int, sign: int):
+        arr = self._shift_arrays.get((W, sign))
         if arr is None:
-            arr = self._shift_arrays[key] = (C.c_int * 9)(*[sign * s for s in _shifts(W)])
+            arr = self._shift_arrays[(W, sign)] = (C.c_int * 9)(*[sign * s for s in _shifts(W)])
+        return arr
+
+    def _taps(self, a, w, W: int, sign: int, aux=None):
+        arr = self._shift_array(W, sign)
         M, Cin = a.shape
         N = w.shape[0]
         out = torch.empty(M, N, device=a.device, dtype=bf16)
@@ -89,14 +94,21 @@ class ConvNetEngine:
             check(lib().b200_bn_stats(ptr(x), rows, Cc, H, W, float(count), ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean) if track else None,
                                       ptr(bn.running_var) if track else None, momentum, float(bn.eps), ptr(out), ptr(self._scratch(rows, Cc, x.device)),
                                       stream_ptr()), 'bn_stats')
+            self._eval_consts.pop(id(bn), None)                     # the kernel just rewrote the running statistics in place
             if track and bn.num_batches_tracked is not None:
-                bn.num_batches_tracked += 1
+                self._counters.append(bn.num_batches_tracked)       # bumped together at the end of the forward (one launch)
         else:
+            # eval mode: constants of the running statistics, rebuilt only when one of the four tensors changes
+            key = (_plan._weight_epoch, bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version, bn.weight.data_ptr())
+            hit = self._eval_consts.get(id(bn))
+            if hit is not None and hit[0] == key:
+                return hit[1]
             rstd = torch.rsqrt(bn.running_var.float() + bn.eps)
             out[0] = bn.weight.detach() * rstd
             out[1] = bn.bias.detach() - bn.running_mean * out[0]
             out[2] = bn.running_mean
             out[3] = rstd
+            self._eval_consts[id(bn)] = (key, out)
         return out
 
     def _bn_apply(self, x, consts, H: int, W: int, relu: bool, residual=None):
@@ -105,12 +117,12 @@ class ConvNetEngine:
         check(lib().b200_bn_apply(ptr(x), ptr(consts[0]), ptr(consts[1]), ptr(residual), int(relu), rows, Cc, H, W, ptr(y), stream_ptr()), 'bn_apply')
         return y
 
-    def _bn_backward(self, dy, y, x, consts, gamma, H: int, W: int, count: int, want_dz: bool = False):
+    def _bn_backward(self, dy, y, x, consts, gamma, H: int, W: int, count: int, want_dz: bool = False, relu_from_x: bool = False):
         rows, Cc = x.shape
         dx = torch.empty_like(x)
         dz = torch.empty_like(x) if want_dz else None
         sums = torch.empty(2, Cc, device=x.device, dtype=torch.float32)
-        check(lib().b200_bn_backward(ptr(dy), ptr(y), ptr(x), ptr(consts), ptr(gamma), rows, Cc, H, W, 0.0 if self._frozen else float(count), ptr(dx), ptr(dz), ptr(sums),
+        check(lib().b200_bn_backward(ptr(dy), ptr(y), int(relu_from_x), ptr(x), ptr(consts), ptr(gamma), rows, Cc, H, W, 0.0 if self._frozen else float(count), ptr(dx), ptr(dz), ptr(sums),
                                      ptr(self._scratch(rows, Cc, x.device)), stream_ptr()), 'bn_backward')
         return dx, dz, sums
 
@@ -132,15 +144,16 @@ class ConvNetEngine:
         return ops.splitk_reduce(ops.gemm_wgrad(dy, x, splits=splits))
 
     def _wgrad_taps(self, dy, x, W: int):
-        """[9, N, K]: tap t pairs dy[p] with x[p + shift_t]; the rows that fall off either end are ring rows (dy = 0 there)"""
-        R = dy.shape[0]
-        outs = []
-        for s in _shifts(W):
-            if s >= 0:
-                outs.append(self._wgrad(dy[:R - s], x[s:]))
-            else:
-                outs.append(self._wgrad(dy[-s:], x[:R + s]))
-        return torch.stack(outs)
+        """[N, 9, K] fp32: dW[n, t, k] = sum_p dy[p, n] x[p + shift_t, k], one launch for the nine taps (rows that fall off either
+        end read as zero - they pair with ring rows of dy, which are zero anyway)"""
+        tokens, N = dy.shape
+        K = x.shape[1]
+        arr = self._shift_array(W, 1)
+        tiles = ((N + 127) // 128) * ((9 * K + 127) // 128)
+        splits = lib().b200_gemm_splits(tokens, max(1, min(tokens // 256, (2 * 148 + tiles - 1) // tiles)))
+        partial = torch.empty(splits, N, 9 * K, device=dy.device, dtype=torch.float32)
+        check(lib().b200_gemm_wgrad_taps(ptr(dy), dy.stride(0), ptr(x), x.stride(0), tokens, N, K, 9, arr, ptr(partial), splits, stream_ptr()), 'gemm_wgrad_taps')
+        return ops.splitk_reduce(partial).view(N, 9, K)
 
     # ------------------------------------------------------------------ forward
     def forward(self, img: torch.Tensor, save: bool) -> torch.Tensor:
@@ -179,6 +192,9 @@ class ConvNetEngine:
                 if save:
                     ctx['blocks'].append(rec)
 
+        if self._counters:
+            torch._foreach_add_(self._counters, 1)
+            self._counters = []
         pooled = torch.empty(B, x.shape[1], device=dev, dtype=bf16)
         check(lib().b200_grid_avgpool(ptr(x), B, H, W, x.shape[1], 0, ptr(pooled), stream_ptr()), 'grid_avgpool')
         fc = m.fc
@@ -268,14 +284,20 @@ class ConvNetEngine:
         bn_grad(blk.bn3, s3)
         conv_grad(blk.conv3, self._wgrad(da3, y2))
         dy2 = ops.gemm_tn(da3, wc.get(blk.conv3.weight, 'conv')[1])
-        da2, _, s2 = self._bn_backward(dy2, y2, a2, c2, blk.bn2.weight, Ho, Wo, n_out)
+        da2, _, s2 = self._bn_backward(dy2, None, a2, c2, blk.bn2.weight, Ho, Wo, n_out, relu_from_x=True)
         bn_grad(blk.bn2, s2)
         if stride == 2:
+            # weight gradient on the coarse grid against gathered patches (a quarter of the contraction of the fine grid)
+            cols = torch.empty(da2.shape[0], 9 * y1.shape[1], device=da2.device, dtype=bf16)
+            check(lib().b200_grid_patches_s2(ptr(y1), B, H, W, y1.shape[1], ptr(cols), stream_ptr()), 'grid_patches_s2')
+            g2 = self._wgrad(da2, cols).view(da2.shape[1], 9, y1.shape[1])
+            del cols
             da2 = self._sample(da2, B, H, W, False)
-        g2 = self._wgrad_taps(da2, y1, W)                                   # [9, Co, Ci]
-        grads[id(blk.conv2.weight)] = g2.permute(1, 2, 0).reshape(blk.conv2.weight.shape).contiguous()
+        else:
+            g2 = self._wgrad_taps(da2, y1, W)                               # [Co, 9, Ci]
+        grads[id(blk.conv2.weight)] = g2.permute(0, 2, 1).reshape(blk.conv2.weight.shape).contiguous()
         dy1 = self._taps(da2, wc.get(blk.conv2.weight, 'conv')[1], W, -1)
-        da1, _, s1 = self._bn_backward(dy1, y1, a1, c1, blk.bn1.weight, H, W, n_in)
+        da1, _, s1 = self._bn_backward(dy1, None, a1, c1, blk.bn1.weight, H, W, n_in, relu_from_x=True)
         bn_grad(blk.bn1, s1)
         conv_grad(blk.conv1, self._wgrad(da1, x))
         if blk.downsample is not None:

@@ -91,9 +91,13 @@ class FusedStep:
                 t.param_bf16 = 0
                 t.numel, t.lr, t.weight_decay, t.beta1, t.beta2, t.eps, t.step = p.numel(), lr, wd, b1, b2, eps, step
                 chunks.extend((i, o) for o in range(0, p.numel(), self._chunk))
-            raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
-            self._tensors_dev = raw.to(dev)
-            self._chunks_dev = torch.tensor(chunks, dtype=torch.int32).to(dev)
+            # pinned staging + asynchronous copies: a model whose gradient tensors are fresh allocations every step (the ResNet
+            # path: autograd owns them) rebuilds this table every step, and a pageable copy would stall the host until the whole
+            # backward has drained
+            raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).pin_memory()
+            chunk_t = torch.tensor(chunks, dtype=torch.int32).pin_memory()
+            self._tensors_dev = raw.to(dev, non_blocking=True)
+            self._chunks_dev = chunk_t.to(dev, non_blocking=True)
             self._n_chunks = len(chunks)
             self._key = key
         check(lib().b200_optimizer_step(self.kind, self._tensors_dev.data_ptr(), self._chunks_dev.data_ptr(), self._n_chunks,

@@ -59,8 +59,9 @@ constexpr int kStatThreads = 256;
 // Thread = (row lane, 8-channel chunk); C / 8 is a power of two <= 256.  partial: [blocks][2][C].
 template <int MODE>
 __global__ void __launch_bounds__(kStatThreads) bn_sums_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, const bf16* __restrict__ y,
-                                                               const float* __restrict__ mean, const float* __restrict__ rstd, long long rows,
-                                                               int C, int cpr_log2, Grid g, float* __restrict__ partial) {
+                                                               const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                               const float* __restrict__ relu_scale, const float* __restrict__ relu_shift,
+                                                               long long rows, int C, int cpr_log2, Grid g, float* __restrict__ partial) {
   pdl_grid_sync();
   __shared__ float red[kStatThreads * 16];
   const int cpr = 1 << cpr_log2;
@@ -70,24 +71,50 @@ __global__ void __launch_bounds__(kStatThreads) bn_sums_kernel(const bf16* __res
   float a[8], b[8], mu[8], rs[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { a[i] = 0.f; b[i] = 0.f; mu[i] = 0.f; rs[i] = 1.f; }
+  float sc[8], sh[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { sc[i] = 0.f; sh[i] = 0.f; }
   if (MODE == 1) { ld8f(mean + ch * 8, mu); ld8f(rstd + ch * 8, rs); }
-  for (long long r = r0 + rl; r < r1; r += lanes) {
-    if (!interior(g, r)) continue;
-    float xv[8];
-    unpack8(ldg16(x + r * C + ch * 8), xv);
-    if (MODE == 0) {
+  if (MODE == 1 && relu_scale != nullptr) { ld8f(relu_scale + ch * 8, sc); ld8f(relu_shift + ch * 8, sh); }
+  // four rows per iteration, every load issued before the arithmetic: the kernel is a pure stream and needs the loads in flight
+  constexpr int U = 4;
+  for (long long rb = r0 + rl; rb < r1; rb += 1LL * lanes * U) {
+    uint4 rx[U], rd[U], ry[U];
+    bool live[U];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { a[i] += xv[i]; b[i] = fmaf(xv[i], xv[i], b[i]); }
-    } else {
-      float dv[8], yv[8];
-      unpack8(ldg16(dy + r * C + ch * 8), dv);
-      if (y != nullptr) {
-        unpack8(ldg16(y + r * C + ch * 8), yv);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) dv[i] = yv[i] > 0.f ? dv[i] : 0.f;
+    for (int u = 0; u < U; ++u) {
+      const long long r = rb + 1LL * u * lanes;
+      live[u] = r < r1 && interior(g, r);
+      if (live[u]) {
+        rx[u] = ldg16(x + r * C + ch * 8);
+        if (MODE == 1) {
+          rd[u] = ldg16(dy + r * C + ch * 8);
+          if (y != nullptr) ry[u] = ldg16(y + r * C + ch * 8);
+        }
       }
+    }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { a[i] += dv[i]; b[i] = fmaf(dv[i], (xv[i] - mu[i]) * rs[i], b[i]); }
+    for (int u = 0; u < U; ++u) {
+      if (!live[u]) continue;
+      float xv[8];
+      unpack8(rx[u], xv);
+      if (MODE == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { a[i] += xv[i]; b[i] = fmaf(xv[i], xv[i], b[i]); }
+      } else {
+        float dv[8], yv[8];
+        unpack8(rd[u], dv);
+        if (y != nullptr) {
+          unpack8(ry[u], yv);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dv[i] = yv[i] > 0.f ? dv[i] : 0.f;
+        } else if (relu_scale != nullptr) {      // the ReLU mask from the BatchNorm input itself: y = relu(x * scale + shift)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dv[i] = fmaf(xv[i], sc[i], sh[i]) > 0.f ? dv[i] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { a[i] += dv[i]; b[i] = fmaf(dv[i], (xv[i] - mu[i]) * rs[i], b[i]); }
+      }
     }
   }
 #pragma unroll
@@ -103,16 +130,21 @@ __global__ void __launch_bounds__(kStatThreads) bn_sums_kernel(const bf16* __res
   }
 }
 
-// fold the CTA partials in double (fixed order: deterministic); MODE 0 also turns them into the normalisation constants
+// fold the CTA partials in double, one warp per channel (fixed order: deterministic); MODE 0 also turns them into the
+// normalisation constants
 template <int MODE>
-__global__ void bn_finalize_kernel(const float* __restrict__ partial, int blocks, int C, double count, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float* running_mean, float* running_var, float momentum, float eps,
-                                   float* __restrict__ out /* MODE 0: [4][C] scale, shift, mean, rstd; MODE 1: [2][C] sums */) {
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restrict__ partial, int blocks, int C, double count,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta, float* running_mean,
+                                                          float* running_var, float momentum, float eps,
+                                                          float* __restrict__ out /* MODE 0: [4][C] scale, shift, mean, rstd; MODE 1: [2][C] sums */) {
   pdl_grid_sync();
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (c >= C) return;
   double s0 = 0.0, s1 = 0.0;
-  for (int b = 0; b < blocks; ++b) { s0 += partial[2LL * b * C + c]; s1 += partial[2LL * b * C + C + c]; }
+  for (int b = lane; b < blocks; b += 32) { s0 += partial[2LL * b * C + c]; s1 += partial[2LL * b * C + C + c]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
+  if (lane != 0) return;
   if (MODE == 1) { out[c] = static_cast<float>(s0); out[C + c] = static_cast<float>(s1); return; }
   const double mean = s0 / count;
   double var = s1 / count - mean * mean;
@@ -162,6 +194,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const bf16* __restrict__ 
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ y, const bf16* __restrict__ x,
                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
                                                            const float* __restrict__ gamma, const float* __restrict__ sums, float inv_count,
+                                                           const float* __restrict__ relu_scale, const float* __restrict__ relu_shift,
                                                            long long rows, int C, int cpr_log2, Grid g, bf16* __restrict__ dx, bf16* dz_out) {
   pdl_grid_sync();
   const long long t = 1LL * blockIdx.x * blockDim.x + threadIdx.x;
@@ -182,6 +215,11 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restric
     unpack8(ldg16(y + off), yv);
 #pragma unroll
     for (int i = 0; i < 8; ++i) dv[i] = yv[i] > 0.f ? dv[i] : 0.f;
+  } else if (relu_scale != nullptr) {
+    float sc[8], sh[8];
+    ld8f(relu_scale + ch * 8, sc); ld8f(relu_shift + ch * 8, sh);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dv[i] = fmaf(xv[i], sc[i], sh[i]) > 0.f ? dv[i] : 0.f;
   }
   ld8f(mean + ch * 8, mu); ld8f(rstd + ch * 8, rs); ld8f(gamma + ch * 8, gm);
   ld8f(sums + ch * 8, s0); ld8f(sums + C + ch * 8, s1);
@@ -338,6 +376,31 @@ __global__ void __launch_bounds__(256) grid_sample_kernel(const bf16* __restrict
   *reinterpret_cast<uint4*>(dst + row * C + ch * 8) = v;
 }
 
+// Patches of a stride-2 3x3 convolution, for its weight gradient: cols[(b, py, px) on the (H/2, W/2) grid, t * C + c] =
+// x[(b, 2 (py - 1) + 1 + r - 1, 2 (px - 1) + 1 + s - 1) on the (H, W) grid, c], t = r * 3 + s; ring rows of the small grid are zero.
+// (The forward and the data gradient of these three convolutions run on the fine grid; only the weight gradient would pay four
+// times the contraction length for it.)
+__global__ void __launch_bounds__(256) grid_patches_s2_kernel(const bf16* __restrict__ x, int B, int H, int W, int C, bf16* __restrict__ cols) {
+  pdl_grid_sync();
+  const int cpr = C >> 3;
+  const int h = H / 2, w = W / 2;
+  const int Wp = W + 2, P = (H + 2) * Wp, wp = w + 2, pp = (h + 2) * wp;
+  const long long t = 1LL * blockIdx.x * blockDim.x + threadIdx.x;
+  const long long chunk = t / cpr;               // (row of the small grid, tap)
+  const int ch = static_cast<int>(t - chunk * cpr);
+  const long long row = chunk / 9;
+  const int tap = static_cast<int>(chunk - row * 9);
+  if (row >= 1LL * B * pp) return;
+  const int q = static_cast<int>(row % pp), b = static_cast<int>(row / pp);
+  const int py = q / wp, px = q - py * wp;
+  uint4 v = make_uint4(0u, 0u, 0u, 0u);
+  if (py >= 1 && py <= h && px >= 1 && px <= w) {
+    const int r = tap / 3, sft = tap - r * 3;
+    v = ldg16(x + (1LL * b * P + (2 * (py - 1) + r) * Wp + 2 * (px - 1) + sft) * C + ch * 8);      // padded coordinates: +1 - 1
+  }
+  *reinterpret_cast<uint4*>(cols + (row * 9 + tap) * C + ch * 8) = v;
+}
+
 __global__ void __launch_bounds__(256) grid_avgpool_fwd_kernel(const bf16* __restrict__ x, int B, int H, int W, int C, bf16* __restrict__ out) {
   pdl_grid_sync();
   const int cpr = C >> 3;
@@ -412,9 +475,10 @@ extern "C" int b200_bn_stats(const void* x, long long rows, int C, int H, int W,
   const int blocks = b200_bn_stats_blocks(rows);
   const Grid g = H > 0 ? make_grid(H, W) : Grid{0, 0, 0, 1};
   launch_pdl(bn_sums_kernel<0>, dim3(blocks), dim3(kStatThreads), 0, st, static_cast<const bf16*>(x), static_cast<const bf16*>(nullptr),
-             static_cast<const bf16*>(nullptr), static_cast<const float*>(nullptr), static_cast<const float*>(nullptr), rows, C, log2_exact(C / 8), g, scratch);
+             static_cast<const bf16*>(nullptr), static_cast<const float*>(nullptr), static_cast<const float*>(nullptr), static_cast<const float*>(nullptr),
+             static_cast<const float*>(nullptr), rows, C, log2_exact(C / 8), g, scratch);
   B200_LAUNCH_CHECK();
-  launch_pdl(bn_finalize_kernel<0>, dim3((C + 127) / 128), dim3(128), 0, st, static_cast<const float*>(scratch), blocks, C, count, gamma, beta,
+  launch_pdl(bn_finalize_kernel<0>, dim3((C + 7) / 8), dim3(256), 0, st, static_cast<const float*>(scratch), blocks, C, count, gamma, beta,
              running_mean, running_var, momentum, eps, out);
   B200_LAUNCH_CHECK();
   return B200_OK;
@@ -430,26 +494,29 @@ extern "C" int b200_bn_apply(const void* x, const float* scale, const float* shi
   return B200_OK;
 }
 
-// BatchNorm (+ ReLU when y is given) backward.  stats = the [4][C] block of b200_bn_stats (mean / rstd are read), sums [2][C]
+// BatchNorm (+ ReLU when y is given, or relu_from_x: y = relu(x * scale + shift) with no residual, mask recomputed) backward.  stats = the [4][C] block of b200_bn_stats (mean / rstd are read), sums [2][C]
 // receives dbeta = sum dz and dgamma = sum dz * xhat; dx [rows, C]; dz_out (may be null) = dy * [y > 0], the gradient that
 // continues along a residual connection.  count = number of interior rows the statistics were taken over, or 0 for frozen
 // statistics (eval-mode BatchNorm: mean / rstd are constants, dx = gamma * rstd * dz).  scratch as for b200_bn_stats.
-extern "C" int b200_bn_backward(const void* dy, const void* y, const void* x, const float* stats, const float* gamma, long long rows, int C, int H,
-                                int W, double count, void* dx, void* dz_out, float* sums, float* scratch, void* stream) {
+extern "C" int b200_bn_backward(const void* dy, const void* y, int relu_from_x, const void* x, const float* stats, const float* gamma, long long rows,
+                                int C, int H, int W, double count, void* dx, void* dz_out, float* sums, float* scratch, void* stream) {
   REQ_C(C); REQ_ALIGN(dy); REQ_ALIGN(y); REQ_ALIGN(x); REQ_ALIGN(dx); REQ_ALIGN(dz_out);
   auto st = reinterpret_cast<cudaStream_t>(stream);
   const int blocks = b200_bn_stats_blocks(rows);
   const Grid g = H > 0 ? make_grid(H, W) : Grid{0, 0, 0, 1};
   const float* mean = stats + 2 * C;
   const float* rstd = stats + 3 * C;
+  B200_REQUIRE(!(relu_from_x && y != nullptr), "bn_backward: the ReLU mask comes from y or from x, not both");
+  const float* rsc = relu_from_x ? stats : nullptr;          // y = relu(x * scale + shift) without a residual: the mask needs no y
+  const float* rsh = relu_from_x ? stats + C : nullptr;
   launch_pdl(bn_sums_kernel<1>, dim3(blocks), dim3(kStatThreads), 0, st, static_cast<const bf16*>(x), static_cast<const bf16*>(dy),
-             static_cast<const bf16*>(y), mean, rstd, rows, C, log2_exact(C / 8), g, scratch);
+             static_cast<const bf16*>(y), mean, rstd, rsc, rsh, rows, C, log2_exact(C / 8), g, scratch);
   B200_LAUNCH_CHECK();
-  launch_pdl(bn_finalize_kernel<1>, dim3((C + 127) / 128), dim3(128), 0, st, static_cast<const float*>(scratch), blocks, C, count,
+  launch_pdl(bn_finalize_kernel<1>, dim3((C + 7) / 8), dim3(256), 0, st, static_cast<const float*>(scratch), blocks, C, count,
              static_cast<const float*>(nullptr), static_cast<const float*>(nullptr), static_cast<float*>(nullptr), static_cast<float*>(nullptr), 0.f, 0.f, sums);
   B200_LAUNCH_CHECK();
   launch_pdl(bn_bwd_apply_kernel, dim3(blocks_for(rows * (C / 8))), dim3(256), 0, st, static_cast<const bf16*>(dy), static_cast<const bf16*>(y),
-             static_cast<const bf16*>(x), mean, rstd, gamma, static_cast<const float*>(sums), static_cast<float>(count > 0 ? 1.0 / count : 0.0), rows, C,
+             static_cast<const bf16*>(x), mean, rstd, gamma, static_cast<const float*>(sums), static_cast<float>(count > 0 ? 1.0 / count : 0.0), rsc, rsh, rows, C,
              log2_exact(C / 8), g, static_cast<bf16*>(dx), static_cast<bf16*>(dz_out));
   B200_LAUNCH_CHECK();
   return B200_OK;
@@ -501,6 +568,17 @@ extern "C" int b200_grid_sample2(const void* src, int B, int H, int W, int C, in
     const long long threads = 1LL * B * (H + 2) * (W + 2) * (C / 8);
     launch_pdl(grid_sample_kernel<false>, dim3(blocks_for(threads)), dim3(256), 0, st, static_cast<const bf16*>(src), B, H, W, C, static_cast<bf16*>(dst));
   }
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+/* x on the (H, W) grid -> cols [rows of the (H / 2, W / 2) grid, 9 * C]: the patches a stride-2 3x3 convolution reads */
+extern "C" int b200_grid_patches_s2(const void* x, int B, int H, int W, int C, void* cols, void* stream) {
+  REQ_C(C); REQ_ALIGN(x); REQ_ALIGN(cols);
+  B200_REQUIRE(H % 2 == 0 && W % 2 == 0, "grid_patches_s2: even grid sides wanted");
+  const long long threads = 1LL * B * (H / 2 + 2) * (W / 2 + 2) * 9 * (C / 8);
+  launch_pdl(grid_patches_s2_kernel, dim3(blocks_for(threads)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), static_cast<const bf16*>(x), B, H, W,
+             C, static_cast<bf16*>(cols));
   B200_LAUNCH_CHECK();
   return B200_OK;
 }

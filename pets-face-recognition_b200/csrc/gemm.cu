@@ -648,6 +648,21 @@ extern "C" int b200_gemm_wgrad(const void* dy, long long ldy, const void* x, lon
   return gemm::launch<gemm::EpiLinear<B200_EPI_PARTIAL>, 4, false, false>(o, od, {nullptr}, reinterpret_cast<cudaStream_t>(stream));
 }
 
+// Weight gradient of an implicit convolution (b200_gemm_taps): partial [splits][N][taps * C] with
+// dW[n, t * C + c] = sum_p dy[p, n] * x[p + tap_shift[t], c] (rows outside [0, tokens) read as zero).  One launch for all taps:
+// the column blocks of one split walk the same rows at the same time, so the nine shifted reads of x (and the nine of dy) are
+// served by L2.
+extern "C" int b200_gemm_wgrad_taps(const void* dy, long long ldy, const void* x, long long ldx, long long tokens, int N, int C, int taps,
+                                    const int* tap_shift, float* partial, int splits, void* stream) {
+  B200_REQUIRE(C % 64 == 0 && N > 0 && tokens > 0 && tokens < (1LL << 31) && taps >= 1 && taps <= 9, "gemm_wgrad_taps: bad shape tokens=%lld N=%d C=%d", tokens, N, C);
+  const int bn = 128;        // a tile spans two taps of a 64-channel layer (they share the dy tile); 128 keeps the operand ring deep
+  gemm::Operands o{dy, (int)ldy, x, (int)ldx, N, taps * C, static_cast<int>(tokens), true, bn, splits, 0, true};
+  o.taps = taps;
+  for (int t = 0; t < taps; ++t) o.tap_shift[t] = tap_shift[t];
+  gemm::Output od{partial, 1LL * taps * C, 4, nullptr, 0, 1LL * N * taps * C, nullptr, 0};
+  return gemm::launch<gemm::EpiLinear<B200_EPI_PARTIAL>, 4, false, false>(o, od, {nullptr}, reinterpret_cast<cudaStream_t>(stream));
+}
+
 // The same launch also producing the bias gradient db[N] = colsum(dY) as [splits][N] fp32 partial rows in `colsum_partial`
 // (an all-ones MMA inside the kernel: no second pass over dY).  *fused = 0 (and colsum_partial untouched) when the tile
 // shape leaves no spare TMEM columns for it (K > 240 with a 256-wide tile): the caller then runs b200_colsum.

@@ -78,7 +78,9 @@ struct CoreParams {
   uint32_t idesc2, idesc2_last;   // M = 256 instruction descriptors of the cta_group::2 MMA
   // Implicit convolution (K-major only): the contraction runs over `taps` filter taps x kb_per_tap K blocks of channels; tap t
   // reads the rows of A shifted by tap_shift[t] (rows outside [0, M) are zero-filled by the TMA) - see b200_gemm_taps
-  int taps, kb_per_tap;
+  // MN-major (weight gradient of such a convolution): the OUTPUT columns are (tap, channel) pairs, tap_cols channels per tap;
+  // a 64-column chunk of tap t reads the rows of B shifted by tap_shift[t] (one tile may span several taps: they share the A tile)
+  int taps, kb_per_tap, tap_cols;
   int tap_shift[9];
 };
 
@@ -255,8 +257,16 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             tma_load_2d(sa + kABytes, &tmap_b, full_bar(stage), kb * kBlockK, n_blk * p.block_n);
           } else {
             for (int c = 0; c < 2; ++c) tma_load_2d(sa + c * kChunk, &tmap_a, full_bar(stage), m_blk * kBlockM + c * 64, kb * kBlockK);
-            for (int c = 0; c < p.b_chunks; ++c)
-              tma_load_2d(sa + kABytes + c * kChunk, &tmap_b, full_bar(stage), n_blk * p.block_n + c * 64, kb * kBlockK);
+            for (int c = 0; c < p.b_chunks; ++c) {
+              int b_col = n_blk * p.block_n + c * 64, b_row = kb * kBlockK;
+              if (p.taps > 0) {                   // 64-column chunk -> (filter tap, channel chunk): shifted rows of the activation tensor
+                const int t = b_col / p.tap_cols;
+                b_col -= t * p.tap_cols;
+                b_row += p.tap_shift[t < p.taps ? t : 0];
+                if (t >= p.taps) b_col = p.tap_cols;        // past the last tap (ragged last tile): out of range -> zero fill
+              }
+              tma_load_2d(sa + kABytes + c * kChunk, &tmap_b, full_bar(stage), b_col, b_row);
+            }
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
@@ -609,10 +619,17 @@ int launch(const Operands& o, const Output& out, const typename Epi::Params& ep,
 
   p.taps = o.taps;
   p.kb_per_tap = 0;
+  p.tap_cols = 0;
   if (o.taps > 0) {
-    B200_REQUIRE(!o.mn_major && o.taps <= 9 && o.K % (o.taps * kBlockK) == 0 && p.splits == 1,
-                 "gemm: implicit convolution needs K-major operands and K / taps a multiple of 64 (K=%d taps=%d)", o.K, o.taps);
-    p.kb_per_tap = o.K / o.taps / kBlockK;
+    B200_REQUIRE(o.taps <= 9, "gemm: at most 9 filter taps");
+    if (!o.mn_major) {
+      B200_REQUIRE(o.K % (o.taps * kBlockK) == 0 && p.splits == 1, "gemm: implicit convolution needs K / taps a multiple of 64 (K=%d taps=%d)", o.K, o.taps);
+      p.kb_per_tap = o.K / o.taps / kBlockK;
+    } else {
+      p.tap_cols = o.N / o.taps;
+      B200_REQUIRE(o.N % o.taps == 0 && p.tap_cols % 64 == 0 && p.block_n % 64 == 0, "gemm: tap weight gradient needs channels per tap (%d) and the tile width (%d) in multiples of 64",
+                   p.tap_cols, p.block_n);
+    }
     for (int t = 0; t < 9; ++t) p.tap_shift[t] = o.tap_shift[t];
   }
   CUtensorMap ta, tb;
@@ -624,7 +641,7 @@ int launch(const Operands& o, const Output& out, const typename Epi::Params& ep,
   } else {
     rc = encode_tmap_2d(&ta, o.is_bf16, o.a, o.M, o.K, o.lda, 64, kBlockK);
     if (rc) return rc;
-    rc = encode_tmap_2d(&tb, o.is_bf16, o.b, o.N, o.K, o.ldb, 64, kBlockK);
+    rc = encode_tmap_2d(&tb, o.is_bf16, o.b, o.taps > 0 ? o.N / o.taps : o.N, o.K, o.ldb, 64, kBlockK);
   }
   if (rc) return rc;
 

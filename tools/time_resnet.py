@@ -49,7 +49,27 @@ def main():
 
     wrap.train()
     L = abi.lib()
+    if '--quick' in sys.argv:          # one warm-up and one step: for an ncu launch list
+        timed(step, reps=1, warm=1)
+        return
     ms = timed(step)
+    import time
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        step()
+    t_cpu = (time.perf_counter() - t0) / 3
+    torch.cuda.synchronize()
+    print(f'host time to ISSUE one step (no synchronisation): {t_cpu * 1e3:.2f} ms')
+    if '--cprofile' in sys.argv:
+        import cProfile, pstats
+        pr = cProfile.Profile()
+        pr.enable()
+        for _ in range(3):
+            step()
+        pr.disable()
+        torch.cuda.synchronize()
+        pstats.Stats(pr).sort_stats('cumulative').print_stats(28)
     abi.check(L.b200_prof_begin(0), 'prof_begin')
     step()
     import ctypes as C
