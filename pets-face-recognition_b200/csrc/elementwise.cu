@@ -657,9 +657,16 @@ extern "C" int b200_layernorm_fwd_windows(const void* x, const float* gamma, con
 
 // 128-thread CTAs; each CTA ends with a cross-warp reduction and one [3C] partial row, so CTAs are kept fat (>= 64
 // rows) and their number at the resident capacity (register-limited, see ln_bwd_ctas_per_sm)
+// widths of the form 24 * 2^k (Swin: 96 / 192 / 384): C / 24 lanes per row with three 16-B chunks each - no idle lanes and a
+// quarter of the per-row bookkeeping of the one-chunk-per-lane layout (B200_LN_BWD3=0: the older layout, for A/B runs)
+static bool ln_bwd_three_chunks(int C) {
+  static const bool on = [] { const char* e = getenv("B200_LN_BWD3"); return e == nullptr || e[0] != '0'; }();
+  return on && (C == 96 || C == 192 || C == 384);
+}
+
 extern "C" int b200_layernorm_bwd_blocks(long long M, int C) {
   long long b = (M + 63) / 64;
-  const int maxit = C <= 256 ? 1 : (C <= 512 ? 2 : (C <= 768 ? 3 : 6));
+  const int maxit = ln_bwd_three_chunks(C) ? 3 : (C <= 256 ? 1 : (C <= 512 ? 2 : (C <= 768 ? 3 : 6)));
   const int cap = b200_num_sms() * ln_bwd_ctas_per_sm(maxit);
   if (b > cap) b = cap;
   return b < 1 ? 1 : static_cast<int>(b);
@@ -681,7 +688,12 @@ static int layernorm_bwd_impl(const void* dy, const void* x, const float* gamma,
   auto DX = reinterpret_cast<bf16*>(dx_out);
   const bool wr = dres_colsum != nullptr;
   int rc;
-  if (C <= 128) rc = ln_bwd_launch<16, 1>(DY, X, gamma, mean, rstd, DR, DX, partial, M, C, blocks, wr, st, wm);
+  if (ln_bwd_three_chunks(C)) {
+    if (C == 96) rc = ln_bwd_launch<4, 3>(DY, X, gamma, mean, rstd, DR, DX, partial, M, C, blocks, wr, st, wm);
+    else if (C == 192) rc = ln_bwd_launch<8, 3>(DY, X, gamma, mean, rstd, DR, DX, partial, M, C, blocks, wr, st, wm);
+    else rc = ln_bwd_launch<16, 3>(DY, X, gamma, mean, rstd, DR, DX, partial, M, C, blocks, wr, st, wm);
+  }
+  else if (C <= 128) rc = ln_bwd_launch<16, 1>(DY, X, gamma, mean, rstd, DR, DX, partial, M, C, blocks, wr, st, wm);
   else if (C <= 256) rc = ln_bwd_launch<32, 1>(DY, X, gamma, mean, rstd, DR, DX, partial, M, C, blocks, wr, st, wm);
   else if (C <= 512) rc = ln_bwd_launch<32, 2>(DY, X, gamma, mean, rstd, DR, DX, partial, M, C, blocks, wr, st, wm);
   else if (C <= 768) rc = ln_bwd_launch<32, 3>(DY, X, gamma, mean, rstd, DR, DX, partial, M, C, blocks, wr, st, wm);

@@ -67,6 +67,24 @@ def main(what, stage=0, B=256):
         for _ in range(3):
             y, mean, rstd = ops.layernorm_fwd(x, gm, bt)
             ops.layernorm_bwd(y, x, gm, mean, rstd, dres=y)
+    elif what == 'time_ln':          # event-timed LayerNorm backward (with the residual-gradient add) at the four stage shapes
+        for st in range(4):
+            Cs, Ms = 96 << st, B * (56 >> st) ** 2
+            x, dy, dr = rnd(Ms, Cs), rnd(Ms, Cs), rnd(Ms, Cs)
+            gm, bt = torch.ones(Cs, device='cuda'), torch.zeros(Cs, device='cuda')
+            y, mean, rstd = ops.layernorm_fwd(x, gm, bt)
+            fn = lambda: ops.layernorm_bwd(dy, x, gm, mean, rstd, dres=dr, want_dres_colsum=True)
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(20):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) / 20 * 1e3
+            print(f'LN bwd C={Cs:4d} M={Ms:7d}: {us:7.1f} us  {4 * Ms * Cs * 2 / us / 1e3:7.0f} GB/s')
     elif what == 'gallery':
         from b200 import gallery
         q = torch.randn(8192, 512, device='cuda', generator=g)
