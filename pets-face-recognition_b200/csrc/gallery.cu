@@ -5,7 +5,7 @@
 //
 //  phase 1  cosine_filter_kernel: fp16 unit rows, Q block (128 queries x dim) resident in smem, gallery tiles of
 //           256 rows streamed by TMA, tcgen05.mma into two 256-column TMEM accumulators; the epilogue never
-//           writes the N x M score matrix: eight epilogue warps (a TMEM lane quadrant x a 128-column half each) let every
+//           writes the N x M score matrix: eight epilogue warps (a TMEM lane quadrant x a 128-column part each) let every
 //           thread own one query row: it compares its scores against a running threshold (max-tree over 32 scores, one
 //           compare), turns the rare survivors into a bit mask and appends them to a per-(row, half) candidate list,
 //           pruned warp-cooperatively by a radix select when it fills.
@@ -47,25 +47,28 @@ constexpr int kMaxKB = 8;           // dim <= 512
 constexpr int kBStages = 3;                  // single-CTA mode: three 32-KB gallery stages; CTA-pair mode: six 16-KB half tiles
 constexpr int kQSlab = kBM * kBK * 2;        // 16 KB
 constexpr int kBStage = kBN * kBK * 2;       // 32 KB
-constexpr int kHalf = kBN / 2;       // tile columns per epilogue warp
-constexpr int kCap = 384;           // candidate list capacity per (query row, column half) (entries of 8 B)
-constexpr int kKP = 128;            // candidates kept per (query, chunk, column half)
-constexpr int kEpiWarps = 8;
+constexpr int kParts = 2;            // column parts of a tile, each with its own epilogue warps and candidate lists (see kEpiWarps)
+constexpr int kHalf = kBN / kParts;  // tile columns per epilogue warp
+constexpr int kCap = 384;           // candidate list capacity per (query row, column part) (entries of 8 B)
+constexpr int kKP = 128;            // candidates kept per (query, chunk, column part)
+constexpr int kEpiWarps = 4 * kParts;   // a TMEM lane quadrant x a column part each.  Measured (r02zf): kParts = 4 (sixteen warps, 64-column
+                                        // parts, twice the lists) is SLOWER - 11.5 vs 11.1 ms at 50 k x 125 k, 53.8 vs 50.9 ms at 50 k x 1 M:
+                                        // every list keeps its own KP candidates, so the survivors (and prunes) nearly double
 constexpr int kThreads = 64 + 32 * kEpiWarps;     // TMA warp, MMA warp, epilogue warps
-constexpr int kWitnessRows = 32 * kBN;            // rows of the witness pass: 2 halves x 64 groups of 64 = 128 witnesses
+constexpr int kWitnessRows = 32 * kBN;            // rows of the witness pass: kParts parts x (32 * kHalf / 64) groups of 64 = 128 witnesses
 constexpr int kMaxBStages = 2 * kBStages;
 constexpr int kSmem = kMaxKB * kQSlab + kBStages * kBStage + 256 + 1024;
 
 struct FilterParams {
   long long nq;
   long long g_begin, ng;      // gallery rows [g_begin, ng) are scanned
-  const float* tau_init;      // [nq][2] starting threshold per query = min of the pair, or null (-inf)
-  float* tau_out;             // witness pass: [nq][2] receives each column half's minimum of group maxima
+  const float* tau_init;      // [nq][kParts] starting threshold per query = min over the parts, or null (-inf)
+  float* tau_out;             // witness pass: [nq][kParts] receives each column part's minimum of group maxima
   uint32_t* tau_shared;       // [nq] order-preserving keys (0 = unset): best threshold any (chunk, half) list of the query has
                               // reached - every list's KP-th best is a lower bound of the query's KP-th best overall, so
                               // the lists of one query, scanned concurrently by different warps / SMs, tighten each other
   int witness;                // 1: witness pass (no candidate lists)
-  int lists;                  // candidate lists per query = 2 * chunks; (chunk, half) fills list 2 * chunk + half
+  int lists;                  // candidate lists per query = kParts * chunks; (chunk, part) fills list kParts * chunk + part
   int kb;                     // dim / 64
   int chunks;                 // gallery chunks
   long long chunk_rows;       // multiple of 256
@@ -312,9 +315,9 @@ cosine_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     }
   } else {
     const int q = warp & 3;                     // TMEM lane quadrant this warp may read
-    const int half = (warp - 2) >> 2;           // column half of every tile
+    const int half = (warp - 2) >> 2;           // column part of every tile (the name dates from two parts)
     const int row = q * 32 + lane;
-    uint2* warp_lists = p.scratch + ((1LL * blockIdx.x * 2 + half) * kBM + q * 32) * kCap;
+    uint2* warp_lists = p.scratch + ((1LL * blockIdx.x * kParts + half) * kBM + q * 32) * kCap;
     uint2* list = warp_lists + 1LL * lane * kCap;
     int acc = 0; uint32_t acc_phase = 0;
     for (int unit = cluster_id; unit < units; unit += n_clusters) {
@@ -326,7 +329,11 @@ cosine_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       const long long g1 = min(p.ng, g0 + p.chunk_rows);
       const int nt = tiles_of(chunk);
       float tau = -INFINITY;
-      if (live && p.tau_init != nullptr) tau = fminf(p.tau_init[2 * qrow], p.tau_init[2 * qrow + 1]);
+      if (live && p.tau_init != nullptr) {
+        tau = p.tau_init[kParts * qrow];
+#pragma unroll
+        for (int j = 1; j < kParts; ++j) tau = fminf(tau, p.tau_init[kParts * qrow + j]);
+      }
       uint32_t* tau_g = (live && !p.witness) ? p.tau_shared + qrow : nullptr;
       uint32_t shared_key = tau_g != nullptr ? __ldcg(tau_g) : 0u;       // refreshed once per tile, applied one tile later
       int cnt = 0;
@@ -412,7 +419,7 @@ cosine_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       }
       if (p.witness) {
         // 1e-6 below the weakest witness: the filter compares with >, and a tie with the threshold must survive
-        if (live) p.tau_out[2 * qrow + half] = wmin - 1e-6f;
+        if (live) p.tau_out[kParts * qrow + half] = wmin - 1e-6f;
         continue;
       }
       // unit done: exact final prune, then hand the survivors (gallery indices) to phase 2, one row at a time, coalesced
@@ -431,7 +438,7 @@ cosine_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
         for (int r = 0; r < 32; ++r) {
           const int n = __shfl_sync(0xffffffffu, cnt, r);
           const long long rq = 1LL * qb * kBM + q * 32 + r;
-          const long long li = rq * p.lists + 2 * chunk + half;
+          const long long li = rq * p.lists + kParts * chunk + half;
           const uint2* src = warp_lists + 1LL * r * kCap;
           for (int i = lane; i < n; i += 32) {
             const uint2 e = src[i];
@@ -440,7 +447,7 @@ cosine_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
           }
           if (lane == 0) p.cand_cnt[li] = n;
         }
-        if (live) p.list_tau[qrow * p.lists + 2 * chunk + half] = tau;
+        if (live) p.list_tau[qrow * p.lists + kParts * chunk + half] = tau;
       }
       __syncwarp();
     }
@@ -982,7 +989,7 @@ bool use_pair(int q_blocks) {
 // (7.93 waves) - every extra chunk restarts the candidate lists from the witness threshold, and that costs more than the tail.
 void pick_chunks(long long rows, int q_groups, int slots, int* chunks, long long* chunk_rows) {
   const long long tiles = (rows + kBN - 1) / kBN;
-  const long long cap = std::max<long long>(1, std::min<long long>(tiles / 16, 31));
+  const long long cap = std::max<long long>(1, std::min<long long>(tiles / 16, 64 / kParts - 1));      // lists = kParts * chunks <= 64
   long long lo = 1, hi = 1;
   if (q_groups < 2 * slots) {
     lo = std::max<long long>(1, std::min<long long>((3LL * slots + q_groups - 1) / q_groups, cap));
@@ -1007,15 +1014,15 @@ Layout plan_layout(long long nq, long long ng) {
   L.witness_rows = (ng >= 4LL * kWitnessRows) ? kWitnessRows : 0;      // small galleries: the unseeded flood is cheaper
   if (use_pair(L.q_blocks)) pick_chunks(ng, (L.q_blocks + 1) / 2, sms / 2, &L.chunks, &L.chunk_rows);
   else pick_chunks(ng, L.q_blocks, sms, &L.chunks, &L.chunk_rows);
-  L.lists = 2 * L.chunks;
+  L.lists = kParts * L.chunks;
   long long off = 0;
   auto take = [&](long long bytes) { long long o = off; off = (off + bytes + 255) / 256 * 256; return o; };
-  L.scratch = take(1LL * sms * 2 * kBM * kCap * 8);
+  L.scratch = take(1LL * sms * kParts * kBM * kCap * 8);
   L.cand_idx = take(1LL * L.q_blocks * kBM * L.lists * kKP * 4);
   L.cand_score = take(1LL * L.q_blocks * kBM * L.lists * kKP * 4);
   L.cand_cnt = take(1LL * L.q_blocks * kBM * L.lists * 4);
   L.list_tau = take(1LL * L.q_blocks * kBM * L.lists * 4);
-  L.tau = take(1LL * L.q_blocks * kBM * 2 * 4);
+  L.tau = take(1LL * L.q_blocks * kBM * kParts * 4);
   L.tau_shared = take(1LL * L.q_blocks * kBM * 4);
   L.total = off;
   return L;

@@ -3,7 +3,8 @@
   1. data-parallel training step: averaged gradients / updated parameters of N ranks == one GPU over the whole batch;
   2. Trainer.fit under strategy='ddp': rank-sharded loader, rank 0 writes the checkpoint (ADVICE r1);
   3. gallery-sharded cosine top-k (BASELINE config 4 layout) == single-GPU pass, bit for bit;
-  4. leave-one-out Recall@K with row-sharded embeddings == single-GPU value.
+  4. leave-one-out Recall@K with row-sharded embeddings == single-GPU value;
+  5. the ResNet-50 FE through the same DDP trainer step == one GPU.
 Rank 0 prints 'MGPU CHECK OK' when everything holds."""
 import os
 import sys
@@ -135,6 +136,34 @@ def main():
     r_sh = gallery.recall_at_k_sharded(emb[gb[rank]:gb[rank + 1]], classes[gb[rank]:gb[rank + 1]], (10, 100))
     r_one = gallery.recall_at_k(emb, classes, (10, 100))
     assert r_sh == r_one, (r_sh, r_one)
+    # ---- 5. ResNet-50 FE under DDP (generic path: every parameter's gradient all-reduced from a post-accumulate hook).  BatchNorm
+    # statistics are per rank (as torch DDP without SyncBN), so every rank is fed the SAME batch: then the averaged gradients and
+    # the updated parameters must equal the single-GPU step.
+    from losses import SoftmaxBasedMetricLearning
+    from models import resnet50
+
+    def build_resnet():
+        torch.manual_seed(77)
+        net = resnet50()
+        net.fc = torch.nn.Linear(2048, 512)
+        return Mod(SoftmaxBasedMetricLearning(net, num_class=1000, embedding_size=512, is_focal=True, arc_margin=True).to(dev))
+
+    rimg, rlab = synth.synth_images(8, seed=6).to(dev), synth.synth_labels(8, 1000, seed=6).to(dev)
+    rmod = build_resnet()
+    ropt = torch.optim.SGD([p for p in rmod.parameters() if p.requires_grad], 5e-3, momentum=0.9)
+    tr5 = Trainer(gpus=[local], strategy='ddp', max_epochs=1)
+    tr5._allreduce_hooks(rmod)
+    tr5.run_training_batch(rmod, {'x': rimg, 'label': rlab}, [ropt])
+    torch.cuda.synchronize()
+    r_after = torch.cat([p.detach().flatten() for p in rmod.parameters()])
+    if rank == 0:
+        one = build_resnet()
+        oopt = torch.optim.SGD([p for p in one.parameters() if p.requires_grad], 5e-3, momentum=0.9)
+        Trainer(gpus=[local], max_epochs=1).run_training_batch(one, {'x': rimg, 'label': rlab}, [oopt])
+        o_after = torch.cat([p.detach().flatten() for p in one.parameters()])
+        rel = ((r_after - o_after).norm() / o_after.norm()).item()
+        print(f'ResNet-50 DDP step on {world} ranks vs 1 GPU: params rel-L2 {rel:.3e}')
+        assert rel < 1e-6, rel
     ok = torch.ones(1, device=dev)
     dist.all_reduce(ok)
     if rank == 0:
