@@ -250,6 +250,10 @@ int b200_gemm_taps(const void* a, long long lda, const void* b, long long ldb, i
  * b200_gemm_splits(tokens, splits) reports */
 int b200_gemm_wgrad_taps(const void* dy, long long ldy, const void* x, long long ldx, long long tokens, int N, int C, int taps,
                          const int* tap_shift, float* partial, int splits, void* stream);
+/* eval-mode convolution + BatchNorm (+ residual) (+ ReLU) in one launch: b = weights with the BatchNorm scale folded in, bias = its
+ * shift; out[r, n] = 0 on ring rows of the (H, W) grid (H = 0: none), else act(a . b + bias[n] (+ aux[r, n])).  taps <= 1: 1x1. */
+int b200_gemm_conv_bn(const void* a, long long lda, const void* b, long long ldb, int M, int N, int C, int taps, const int* tap_shift,
+                      const float* bias, int relu, int H, int W, const void* aux, long long ldaux, void* out, long long ldo, void* stream);
 int b200_bn_stats_blocks(long long rows);
 /* nn.BatchNorm2d, training mode: batch statistics over the interior rows (count of them given) -> out [4][C] = scale, shift,
  * mean, rstd; running statistics (nullable) updated with `momentum` (unbiased variance).  scratch [blocks][2][C] floats. */

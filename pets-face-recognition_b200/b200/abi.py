@@ -66,6 +66,8 @@ _PROTOS = {
     'b200_augment_train': (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     'b200_gemm_taps': (c_int, [c_vp, c_ll, c_vp, c_ll, c_int, c_int, c_int, c_int, C.POINTER(c_int), c_int, c_vp, c_ll, c_vp, c_ll, c_vp]),
     'b200_gemm_wgrad_taps': (c_int, [c_vp, c_ll, c_vp, c_ll, c_ll, c_int, c_int, c_int, C.POINTER(c_int), c_vp, c_int, c_vp]),
+    'b200_gemm_conv_bn': (c_int, [c_vp, c_ll, c_vp, c_ll, c_int, c_int, c_int, c_int, C.POINTER(c_int), c_vp, c_int, c_int, c_int, c_vp, c_ll,
+                                  c_vp, c_ll, c_vp]),
     'b200_bn_stats_blocks': (c_int, [c_ll]),
     'b200_bn_stats': (c_int, [c_vp, c_ll, c_int, c_int, c_int, C.c_double, c_vp, c_vp, c_vp, c_vp, c_float, c_float, c_vp, c_vp, c_vp]),
     'b200_bn_apply': (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_ll, c_int, c_int, c_int, c_vp, c_vp]),

@@ -64,6 +64,7 @@ class ConvNetEngine:
         self._frozen = False
         self._counters: List[torch.Tensor] = []
         self._eval_consts: Dict[int, tuple] = {}
+        self._folded_cache: Dict[int, tuple] = {}
 
     # ------------------------------------------------------------------ small wrappers over the C ABI
     def _shift_array(self, W: int, sign: int):
@@ -80,6 +81,47 @@ class ConvNetEngine:
         check(lib().b200_gemm_taps(ptr(a), a.stride(0), ptr(w), w.stride(0), M, N, Cin, 9, arr, abi.EPI_RESID if aux is not None else abi.EPI_STORE,
                                    ptr(out), N, ptr(aux), aux.stride(0) if aux is not None else 0, stream_ptr()), 'gemm_taps')
         return out
+
+    def _folded(self, conv, bn):
+        """eval mode: (bf16 [Co, (r, s, ci)] weights with the BatchNorm scale folded in, fp32 shift), rebuilt when a tensor changes"""
+        key = (_plan._weight_epoch, conv.weight._version, bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version,
+               conv.weight.data_ptr())
+        hit = self._folded_cache.get(id(conv))
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        scale = bn.weight.detach().float() * torch.rsqrt(bn.running_var.float() + bn.eps)
+        shift = (bn.bias.detach().float() - bn.running_mean.float() * scale).contiguous()
+        w = (conv.weight.detach().float() * scale[:, None, None, None]).permute(0, 2, 3, 1).reshape(conv.weight.shape[0], -1).to(bf16).contiguous()
+        self._folded_cache[id(conv)] = (key, (w, shift))
+        return w, shift
+
+    def _conv_bn(self, x, conv, bn, H: int, W: int, relu: bool, aux=None):
+        """eval mode: convolution (1x1 or 3x3 on the (H, W) grid) + BatchNorm (+ residual) (+ ReLU) in one GEMM launch"""
+        w, shift = self._folded(conv, bn)
+        M, Cin = x.shape
+        N = w.shape[0]
+        taps = 9 if conv.kernel_size == (3, 3) else 0
+        out = torch.empty(M, N, device=x.device, dtype=bf16)
+        check(lib().b200_gemm_conv_bn(ptr(x), x.stride(0), ptr(w), w.stride(0), M, N, Cin, taps, self._shift_array(W, 1) if taps else None, ptr(shift),
+                                      int(relu), H, W, ptr(aux), aux.stride(0) if aux is not None else 0, ptr(out), N, stream_ptr()), 'gemm_conv_bn')
+        return out
+
+    def _block_forward_eval(self, blk, x, B: int, H: int, W: int):
+        """inference: four launches per Bottleneck (five with a down-sampling branch), no BatchNorm pass of its own"""
+        stride = blk.conv2.stride[0]
+        if blk.conv1.stride[0] != 1 or blk.conv2.kernel_size != (3, 3) or blk.conv2.groups != 1 or blk.conv2.dilation[0] != 1 or stride not in (1, 2):
+            raise B200Error('ConvNetEngine supports the torchvision v1.5 Bottleneck (stride on the 3x3 convolution, no groups / dilation)')
+        y1 = self._conv_bn(x, blk.conv1, blk.bn1, H, W, True)
+        y2 = self._conv_bn(y1, blk.conv2, blk.bn2, H, W, True)
+        Ho, Wo = H // stride, W // stride
+        if stride == 2:
+            y2 = self._sample(y2, B, H, W, True)
+        if blk.downsample is not None:
+            xs = self._sample(x, B, H, W, True) if stride == 2 else x
+            idn = self._conv_bn(xs, blk.downsample[0], blk.downsample[1], Ho, Wo, False)
+        else:
+            idn = x
+        return self._conv_bn(y2, blk.conv3, blk.bn3, Ho, Wo, True, aux=idn), Ho, Wo
 
     def _scratch(self, rows: int, Cc: int, dev):
         return torch.empty(lib().b200_bn_stats_blocks(rows) * 2 * Cc, device=dev, dtype=torch.float32)
@@ -186,8 +228,12 @@ class ConvNetEngine:
         else:
             del cols, a0
 
+        fused_eval = not training and not save          # inference: BatchNorm folded into the convolution launches
         for layer in (m.layer1, m.layer2, m.layer3, m.layer4):
             for blk in layer:
+                if fused_eval:
+                    x, H, W = self._block_forward_eval(blk, x, B, H, W)
+                    continue
                 x, H, W, rec = self._block_forward(blk, x, B, H, W, training, save)
                 if save:
                     ctx['blocks'].append(rec)

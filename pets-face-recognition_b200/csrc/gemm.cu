@@ -307,6 +307,42 @@ struct EpiLinear {
 };
 
 // ---------------------------------------------------------------------------------------------
+// Convolution + folded BatchNorm epilogue of the eval-mode ResNet path (b200/convnet.py): the BatchNorm scale is folded into
+// the bf16 weights, its shift is the bias, and   out = ring(row) ? 0 : [relu](acc + bias (+ aux)).   Every thread of the
+// epilogue owns one output row, so the ring test (row -> (y, x) on the padded grid, two fast divisions) costs nothing
+// per element; zeroing the ring here is what lets the next 3x3 convolution read its padding from the same tensor.
+// ---------------------------------------------------------------------------------------------
+template <bool WITH_AUX>
+struct EpiConvBN {
+  using Lin = EpiLinear<WITH_AUX ? B200_EPI_RESID : B200_EPI_STORE>;
+  struct Params {
+    const float* bias;
+    int relu;
+    int H, W, Wp, P;           // padded grid: Wp = W + 2, P = (H + 2) * Wp; H = 0: no ring
+    FastDiv div_p, div_wp;
+  };
+  static bool wants_columns(const Params& ep) { return ep.bias != nullptr; }
+  __device__ static __forceinline__ void stage_columns(const Params& ep, const CoreParams& p, float* dst, int tid, int nthreads) {
+    Lin::stage_columns(typename Lin::Params{ep.bias}, p, dst, tid, nthreads);
+  }
+  template <bool DUAL>
+  __device__ static __forceinline__ void compute(const Params& ep, const CoreParams& p, const float* bias_s, int row, int col,
+                                                 const float (&v)[16], const float (&ax)[16], float (&o)[16], float (&o2)[16]) {
+    Lin::template compute<false>(typename Lin::Params{ep.bias}, p, bias_s, row, col, v, ax, o, o2);
+    bool keep = true;
+    if (ep.H > 0) {
+      const uint32_t r = static_cast<uint32_t>(row);
+      const uint32_t q = r - ep.div_p.div(r) * static_cast<uint32_t>(ep.P);
+      const uint32_t y = ep.div_wp.div(q), x = q - y * static_cast<uint32_t>(ep.Wp);
+      keep = y >= 1u && y <= static_cast<uint32_t>(ep.H) && x >= 1u && x <= static_cast<uint32_t>(ep.W);
+    }
+    const float lo = ep.relu ? 0.0f : -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o[i] = keep ? fmaxf(o[i], lo) : 0.0f;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
 // ArcFace / CosFace logits epilogue: operands are the unit-norm bf16 rows of the embeddings and of
 // the class weights, so the accumulator IS cos(theta).  Margin on the label column, then * s.
 // ---------------------------------------------------------------------------------------------
@@ -637,6 +673,35 @@ extern "C" int b200_gemm_taps(const void* a, long long lda, const void* b, long 
   B200_REQUIRE(taps >= 1 && taps <= 9 && tap_shift != nullptr && C % 64 == 0, "gemm_taps: taps in [1, 9], C a multiple of 64 (taps=%d C=%d)", taps, C);
   B200_REQUIRE(mode == B200_EPI_STORE || mode == B200_EPI_RESID, "gemm_taps: STORE or RESID epilogue");
   return gemm_tn_impl(a, lda, b, ldb, M, N, taps * C, 1, mode, out, ldo, 0, nullptr, 0, nullptr, aux, ldaux, 1, 0, 0, stream, taps, tap_shift);
+}
+
+// Eval-mode convolution + BatchNorm (+ residual) (+ ReLU) in one launch: out[r, n] = ring(r) ? 0 : act(sum a . b + bias[n] (+ aux[r, n])),
+// a [M, C] rows of the padded (H, W) grid, b [N, taps * C] = the convolution weights with the BatchNorm scale folded in,
+// bias = the BatchNorm shift.  taps = 0 / 1: a 1x1 convolution (plain GEMM, K = C); taps = 9 with tap_shift: 3x3 (b200_gemm_taps).
+extern "C" int b200_gemm_conv_bn(const void* a, long long lda, const void* b, long long ldb, int M, int N, int C, int taps, const int* tap_shift,
+                                 const float* bias, int relu, int H, int W, const void* aux, long long ldaux, void* out, long long ldo,
+                                 void* stream) {
+  B200_REQUIRE(N % 8 == 0 && C % 8 == 0 && taps >= 0 && taps <= 9, "gemm_conv_bn: bad shape N=%d C=%d taps=%d", N, C, taps);
+  if (taps <= 1) taps = 0;
+  B200_REQUIRE(taps == 0 || (tap_shift != nullptr && C % 64 == 0), "gemm_conv_bn: a tap convolution needs tap_shift and C %% 64 == 0");
+  B200_REQUIRE(aux == nullptr || ldaux % 8 == 0, "gemm_conv_bn: aux pitch must be a multiple of 8 elements");
+  const int K = taps > 0 ? taps * C : C;
+  gemm::Operands o{a, (int)lda, b, (int)ldb, M, N, K, true, 0, 1, 0};
+  o.taps = taps;
+  for (int t = 0; t < taps; ++t) o.tap_shift[t] = tap_shift[t];
+  gemm::Output od{out, ldo, 2, nullptr, 0, 0, aux, aux != nullptr ? ldaux : 0};
+  auto st = reinterpret_cast<cudaStream_t>(stream);
+  const int Wp = W + 2, P = (H + 2) * (W + 2);
+  const int bn = gemm::pick_block_n(N, K);
+  const bool pair = gemm::b200_cg2() && K >= 384 && bn >= 192 && bn % 32 == 0 && N % bn == 0 && M >= 2 * 128;      // as b200_gemm_tn
+  if (aux != nullptr) {
+    gemm::EpiConvBN<true>::Params ep{bias, relu, H, W, Wp, P, make_fastdiv(static_cast<uint32_t>(P)), make_fastdiv(static_cast<uint32_t>(Wp))};
+    if (pair) return gemm::launch<gemm::EpiConvBN<true>, 2, false, true, false, 8, true>(o, od, ep, st);
+    return gemm::launch<gemm::EpiConvBN<true>, 2, false, true>(o, od, ep, st);
+  }
+  gemm::EpiConvBN<false>::Params ep{bias, relu, H, W, Wp, P, make_fastdiv(static_cast<uint32_t>(P)), make_fastdiv(static_cast<uint32_t>(Wp))};
+  if (pair) return gemm::launch<gemm::EpiConvBN<false>, 2, false, false, false, 8, true>(o, od, ep, st);
+  return gemm::launch<gemm::EpiConvBN<false>, 2, false, false>(o, od, ep, st);
 }
 
 // dW[N,K] (fp32 split partials) = dY[tokens,N]^T * X[tokens,K]: both operands are read in place, MN-major - no transposes.
