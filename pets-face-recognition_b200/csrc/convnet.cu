@@ -233,31 +233,44 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restric
 }
 
 // ------------------------------------------------------------------------------------------------ stem
-// cols[(b, oy, ox), (r * 7 + s) * 3 + c] = img[b, c, 2 oy - 3 + r, 2 ox - 3 + s] (0 outside), columns 147..159 zero
+// cols[(b, oy, ox), (r * 7 + s) * 3 + c] = img[b, c, 2 oy - 3 + r, 2 ox - 3 + s] (0 outside), columns 147..159 zero.
+// One CTA per output row (b, oy): the 3 x 7 input row segments it needs are staged in shared memory with coalesced loads
+// (zero-padded by 3 pixels on either side), then every thread assembles 16-B chunks of the patch matrix from there and
+// writes them coalesced - the kernel is bound by the 1 GB of patches it writes at batch 256, not by byte gathers.
 template <bool U8>
 __global__ void __launch_bounds__(256) stem_im2col_kernel(const void* __restrict__ img, int B, int H, int W, int OH, int OW, bf16* __restrict__ cols) {
   pdl_grid_sync();
-  const long long t = 1LL * blockIdx.x * blockDim.x + threadIdx.x;
-  const long long row = t / 20;
-  if (row >= 1LL * B * OH * OW) return;
-  const int chunk = static_cast<int>(t - row * 20);
-  const int ox = static_cast<int>(row % OW), oy = static_cast<int>((row / OW) % OH), b = static_cast<int>(row / (1LL * OW * OH));
-  float v[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int k = chunk * 8 + i;
-    float val = 0.f;
-    if (k < 147) {
-      const int r = k / 21, rem = k - r * 21, s = rem / 3, c = rem - s * 3;
-      const int iy = 2 * oy - 3 + r, ix = 2 * ox - 3 + s;
-      if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
-        const long long idx = ((1LL * b * 3 + c) * H + iy) * W + ix;
-        val = U8 ? static_cast<float>(__ldg(static_cast<const uint8_t*>(img) + idx)) * (1.0f / 255.0f) : __ldg(static_cast<const float*>(img) + idx);
-      }
+  extern __shared__ float stem_tile[];               // [3][7][W + 6], already scaled to [0, 1]
+  const int b = blockIdx.x / OH, oy = blockIdx.x - b * OH;
+  const int Wt = W + 6;
+  for (int idx = threadIdx.x; idx < 21 * Wt; idx += blockDim.x) {
+    const int cr = idx / Wt, xx = idx - cr * Wt;
+    const int c = cr / 7, r = cr - c * 7;
+    const int iy = 2 * oy - 3 + r, ix = xx - 3;
+    float v = 0.f;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+      const long long g = ((1LL * b * 3 + c) * H + iy) * W + ix;
+      v = U8 ? static_cast<float>(__ldg(static_cast<const uint8_t*>(img) + g)) * (1.0f / 255.0f) : __ldg(static_cast<const float*>(img) + g);
     }
-    v[i] = val;
+    stem_tile[idx] = v;
   }
-  *reinterpret_cast<uint4*>(cols + row * 160 + chunk * 8) = pack8(v);
+  __syncthreads();
+  bf16* out = cols + (1LL * b * OH + oy) * OW * 160;
+  for (int j = threadIdx.x; j < OW * 20; j += blockDim.x) {
+    const int ox = j / 20, chunk = j - ox * 20;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = chunk * 8 + i;
+      float val = 0.f;
+      if (k < 147) {
+        const int r = k / 21, rem = k - r * 21, s2 = rem / 3, c = rem - s2 * 3;
+        val = stem_tile[(c * 7 + r) * Wt + 2 * ox + s2];
+      }
+      v[i] = val;
+    }
+    *reinterpret_cast<uint4*>(out + 8LL * j) = pack8(v);
+  }
 }
 
 // y[(b, py, px)] on the padded (OH/2 + 2) x (OW/2 + 2) grid = max over the 3x3 stride-2 pad-1 window of relu(a * scale + shift);
@@ -526,10 +539,11 @@ extern "C" int b200_stem_im2col(const void* img, int is_u8, int B, int H, int W,
   B200_REQUIRE(B > 0 && H % 2 == 0 && W % 2 == 0 && H >= 8 && W >= 8, "stem_im2col: even image sides wanted (got %d x %d)", H, W);
   REQ_ALIGN(cols);
   const int OH = H / 2, OW = W / 2;
-  const long long threads = 1LL * B * OH * OW * 20;
+  const size_t smem = sizeof(float) * 21 * (W + 6);
+  B200_REQUIRE(smem <= 48 * 1024 && 1LL * B * OH < (1LL << 31), "stem_im2col: image too wide (%d) or batch too large", W);
   auto st = reinterpret_cast<cudaStream_t>(stream);
-  if (is_u8) launch_pdl(stem_im2col_kernel<true>, dim3(blocks_for(threads)), dim3(256), 0, st, img, B, H, W, OH, OW, static_cast<bf16*>(cols));
-  else launch_pdl(stem_im2col_kernel<false>, dim3(blocks_for(threads)), dim3(256), 0, st, img, B, H, W, OH, OW, static_cast<bf16*>(cols));
+  if (is_u8) launch_pdl(stem_im2col_kernel<true>, dim3(static_cast<unsigned>(B * OH)), dim3(256), smem, st, img, B, H, W, OH, OW, static_cast<bf16*>(cols));
+  else launch_pdl(stem_im2col_kernel<false>, dim3(static_cast<unsigned>(B * OH)), dim3(256), smem, st, img, B, H, W, OH, OW, static_cast<bf16*>(cols));
   B200_LAUNCH_CHECK();
   return B200_OK;
 }

@@ -132,6 +132,29 @@ def test_resnet50_eval_forward_matches_torchvision():
     assert _rel(got_f, got) < 2e-2
 
 
+def test_resnet50_other_input_sizes_and_batches():
+    """256 x 256 body crops (configs/dog_fe/body_dog_fe.py feeds 256-pixel images), a single image, a float batch of 96 x 160"""
+    from models import resnet50
+    from oracle.resnet_oracle import build
+    dev = torch.device('cuda')
+    ref = build(seed=11).to(dev).eval()
+    ours = resnet50()
+    ours.fc = torch.nn.Linear(2048, 512)
+    ours.load_state_dict(ref.state_dict())
+    ours = ours.to(dev).eval()
+    g = torch.Generator(device=dev).manual_seed(4)
+    for shape in ((3, 3, 256, 256), (1, 3, 224, 224), (5, 3, 96, 160)):
+        x = torch.rand(shape, device=dev, generator=g)
+        with torch.no_grad():
+            want, got = ref(x), ours(x)
+        assert got.shape == want.shape
+        assert torch.nn.functional.cosine_similarity(got, want).min().item() > 0.999 and _rel(got, want) < 3e-2, shape
+    ours.train(); ref.train()
+    x = torch.rand(2, 3, 256, 256, device=dev, generator=g)          # training forward + backward on a non-224 grid
+    (ours(x) ** 2).mean().backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in ours.parameters())
+
+
 def _grad_rels(a, b):
     return {n: _rel(p.grad, q.grad) for (n, p), (_, q) in zip(a.named_parameters(), b.named_parameters())}
 
