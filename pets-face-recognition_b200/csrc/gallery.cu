@@ -56,6 +56,7 @@ constexpr int kEpiWarps = 4 * kParts;   // a TMEM lane quadrant x a column part 
                                         // every list keeps its own KP candidates, so the survivors (and prunes) nearly double
 constexpr int kThreads = 64 + 32 * kEpiWarps;     // TMA warp, MMA warp, epilogue warps
 constexpr int kWitnessRows = 32 * kBN;            // rows of the witness pass: kParts parts x (32 * kHalf / 64) groups of 64 = 128 witnesses
+constexpr int kSel2 = 512;           // candidates re-scored exactly in the second certification pass (see rerank_kernel)
 constexpr int kMaxBStages = 2 * kBStages;
 constexpr int kSmem = kMaxKB * kQSlab + kBStages * kBStage + 256 + 1024;
 
@@ -512,22 +513,29 @@ struct CertParams {             // all null / zero: no certificate
   int* uncert;                  // [1 + nq]: count, then the queries that could not be certified
 };
 
+// SEL = how many of the kept candidates (best by approximate score) are re-scored exactly: kKP for every query, then - only for
+// the queries that pass could not certify (`subset` = their list) - a second pass with SEL = kSel2, whose cut-off lies that
+// much further below the exact k-th score.  On concentrated embeddings (an untrained backbone: cosines of 0.997 between
+// unrelated images, 100 k+ rows) the first pass leaves most queries unproven and the second proves all of them at 1 / 400 of
+// the cost of the exact scan of the gallery.
+template <int SEL>
 __global__ void __launch_bounds__(256, 3) rerank_kernel(const float* __restrict__ q, const double* __restrict__ q_norm,
                                                      const float* __restrict__ g, const double* __restrict__ g_norm, int dim,
                                                      const int* __restrict__ cand_idx, const float* __restrict__ cand_score,
                                                      const int* __restrict__ cand_cnt, int lists, long long nq, int k,
                                                      long long g_index_base, int* __restrict__ out_idx, double* __restrict__ out_score,
-                                                     const CertParams cert) {
+                                                     const CertParams cert, const int* __restrict__ subset) {
   pdl_grid_sync();
   extern __shared__ __align__(16) uint8_t sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cap = lists * kKP;
-  uint8_t* mine = sm + static_cast<size_t>(warp) * (kKP * sizeof(Cand) + static_cast<size_t>(cap) * 8);
-  Cand* sel = reinterpret_cast<Cand*>(mine);                                                     // [kKP] exact stage
-  unsigned long long* keys = reinterpret_cast<unsigned long long*>(mine + kKP * sizeof(Cand));   // [cap] approximate stage
-  const long long qi = 1LL * blockIdx.x * (blockDim.x >> 5) + warp;
-  if (qi >= nq) return;
-  for (int i = lane; i < kKP; i += 32) { sel[i].score = -INFINITY; sel[i].idx = INT_MAX; sel[i].pad = 0; }
+  uint8_t* mine = sm + static_cast<size_t>(warp) * (SEL * sizeof(Cand) + static_cast<size_t>(cap) * 8);
+  Cand* sel = reinterpret_cast<Cand*>(mine);                                                     // [SEL] exact stage
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(mine + SEL * sizeof(Cand));   // [cap] approximate stage
+  const long long slot = 1LL * blockIdx.x * (blockDim.x >> 5) + warp;
+  if (slot >= (subset != nullptr ? static_cast<long long>(subset[0]) : nq)) return;
+  const long long qi = subset != nullptr ? subset[1 + slot] : slot;
+  for (int i = lane; i < SEL; i += 32) { sel[i].score = -INFINITY; sel[i].idx = INT_MAX; sel[i].pad = 0; }
   // unique order-preserving key: (approximate score desc, gallery index asc)  ==  larger key first
   int total = 0;
   for (int c = 0; c < lists; ++c) {
@@ -546,7 +554,7 @@ __global__ void __launch_bounds__(256, 3) rerank_kernel(const float* __restrict_
   unsigned long long thr = 0ULL;
   int cge = total;
 #pragma unroll 1
-  for (int bit = 62; bit >= 0 && cge > kKP; bit -= 2) {
+  for (int bit = 62; bit >= 0 && cge > SEL; bit -= 2) {
     const unsigned long long c1 = thr | (1ULL << bit), c2 = thr | (2ULL << bit), c3 = thr | (3ULL << bit);
     int n1 = 0, n2 = 0, n3 = 0;
     for (int i = lane; i < total; i += 32) {
@@ -558,9 +566,9 @@ __global__ void __launch_bounds__(256, 3) rerank_kernel(const float* __restrict_
     n1 = __reduce_add_sync(0xffffffffu, n1);
     n2 = __reduce_add_sync(0xffffffffu, n2);
     n3 = __reduce_add_sync(0xffffffffu, n3);
-    if (n3 >= kKP) { thr = c3; cge = n3; }
-    else if (n2 >= kKP) { thr = c2; cge = n2; }
-    else if (n1 >= kKP) { thr = c1; cge = n1; }
+    if (n3 >= SEL) { thr = c3; cge = n3; }
+    else if (n2 >= SEL) { thr = c2; cge = n2; }
+    else if (n1 >= SEL) { thr = c1; cge = n1; }
   }
   int nsel = 0;
   const uint32_t lt_mask = (1u << lane) - 1u;
@@ -569,10 +577,10 @@ __global__ void __launch_bounds__(256, 3) rerank_kernel(const float* __restrict_
     const bool keep = i < total && keys[i] >= thr;
     const uint32_t m = __ballot_sync(0xffffffffu, keep);
     const int pos = nsel + __popc(m & lt_mask);
-    if (keep && pos < kKP) sel[pos].idx = static_cast<int>(0xffffffffu - static_cast<uint32_t>(keys[i] & 0xffffffffULL));
+    if (keep && pos < SEL) sel[pos].idx = static_cast<int>(0xffffffffu - static_cast<uint32_t>(keys[i] & 0xffffffffULL));
     nsel += __popc(m);
   }
-  nsel = min(nsel, kKP);
+  nsel = min(nsel, SEL);
   __syncwarp();
   // level 2: exact fp64 cosine of those <= kKP candidates from the fp32 embeddings (fixed summation order: lane-strided
   // chains, xor tree).  The kernel is bound by the latency of the gathered gallery rows: the norms are fetched up front
@@ -625,7 +633,7 @@ __global__ void __launch_bounds__(256, 3) rerank_kernel(const float* __restrict_
     }
   }
   __syncwarp();
-  warp_bitonic_sort(sel, kKP, lane);
+  warp_bitonic_sort(sel, SEL, lane);
   for (int i = lane; i < k; i += 32) {
     const bool ok = i < nsel;
     out_idx[qi * k + i] = ok ? static_cast<int>(sel[i].idx + g_index_base) : -1;
@@ -636,7 +644,7 @@ __global__ void __launch_bounds__(256, 3) rerank_kernel(const float* __restrict_
     float a_cut = -INFINITY;
     for (int c = lane; c < lists; c += 32) a_cut = fmaxf(a_cut, cert.list_tau[qi * lists + c]);
     a_cut = warp_max(a_cut);
-    if (total > kKP) a_cut = fmaxf(a_cut, fkey_inv(static_cast<uint32_t>(thr >> 32)));
+    if (total > SEL) a_cut = fmaxf(a_cut, fkey_inv(static_cast<uint32_t>(thr >> 32)));
     // q^ . mu: the constant the centring removed from every score of this query
     double qmu = 0.0;
     if (cert.center != nullptr) {
@@ -966,6 +974,7 @@ __global__ void __launch_bounds__(256) pair_similarity_kernel(const float* __res
 struct Layout {
   long long scratch, cand_idx, cand_score, cand_cnt, list_tau, tau, tau_shared, total;
   int q_blocks, lists;
+  long long unc1;              // int [1 + nq]: the queries the first certification pass left open
   long long witness_rows;      // rows [0, witness_rows) seed the thresholds (0 = single pass, unseeded)
   int chunks;                  // gallery chunks of the list pass
   long long chunk_rows;
@@ -1024,6 +1033,7 @@ Layout plan_layout(long long nq, long long ng) {
   L.list_tau = take(1LL * L.q_blocks * kBM * L.lists * 4);
   L.tau = take(1LL * L.q_blocks * kBM * kParts * 4);
   L.tau_shared = take(1LL * L.q_blocks * kBM * 4);
+  L.unc1 = take(4LL * (1 + L.q_blocks * kBM));
   L.total = off;
   return L;
 }
@@ -1178,21 +1188,30 @@ static int cosine_topk_impl(const float* q, const void* q_unit_f16, const double
   if (rc) return rc;
   rc = launch_filter(tq, tg, tg_half, p, L, st);
   if (rc) return rc;
-  const int per_warp = kKP * static_cast<int>(sizeof(Cand)) + L.lists * kKP * 8;      // exact stage + candidate keys of one query
-  const int wpc = std::max(1, std::min(8, (200 * 1024) / per_warp));                  // queries (warps) per CTA
-  const int smem2 = wpc * per_warp;
-  B200_REQUIRE(per_warp <= 200 * 1024, "cosine_topk: too many candidate lists");
-  if (smem2 > 48 * 1024) B200_CHECK_CUDA(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
-  if (cert.uncert != nullptr) B200_CHECK_CUDA(cudaMemsetAsync(cert.uncert, 0, sizeof(int), st));
-  launch_pdl(rerank_kernel, dim3(static_cast<unsigned>((nq + wpc - 1) / wpc)), dim3(32 * wpc), smem2, st, q, q_norm, g, g_norm, dim, p.cand_idx,
-             p.cand_score, p.cand_cnt, L.lists, nq, k, g_index_base, out_idx, out_score, cert);
-  B200_LAUNCH_CHECK();
-  if (cert.uncert != nullptr) {
-    // the queries the certificate could not prove (normally none): exact scan; every CTA leaves at once when the list is empty
-    launch_pdl(exact_topk_kernel, dim3(static_cast<unsigned>(std::min<long long>(nq, 4LL * b200_num_sms()))), dim3(256), 0, st, q, q_norm, g, g_norm,
-               ng, dim, k, p.self_offset, p.exclude_self, g_index_base, cert.uncert, out_idx, out_score);
+  auto launch_rerank = [&](auto kernel, int sel, const CertParams& c, const int* subset) -> int {
+    const int per_warp = sel * static_cast<int>(sizeof(Cand)) + L.lists * kKP * 8;      // exact stage + candidate keys of one query
+    B200_REQUIRE(per_warp <= 200 * 1024, "cosine_topk: too many candidate lists");
+    const int wpc = std::max(1, std::min(8, (200 * 1024) / per_warp));                  // queries (warps) per CTA
+    const int smem2 = wpc * per_warp;
+    if (smem2 > 48 * 1024) B200_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+    launch_pdl(kernel, dim3(static_cast<unsigned>((nq + wpc - 1) / wpc)), dim3(32 * wpc), smem2, st, q, q_norm, g, g_norm, dim, p.cand_idx,
+               p.cand_score, p.cand_cnt, L.lists, nq, k, g_index_base, out_idx, out_score, c, subset);
     B200_LAUNCH_CHECK();
-  }
+    return B200_OK;
+  };
+  if (cert.uncert == nullptr) return launch_rerank(rerank_kernel<kKP>, kKP, cert, nullptr);
+  // certified: pass 1 leaves its open queries in the workspace list, pass 2 re-scores kSel2 candidates for those and leaves what
+  // it cannot prove either in the caller's list, which the exact scan of the gallery then serves (normally nobody)
+  int* unc1 = reinterpret_cast<int*>(ws + L.unc1);
+  B200_CHECK_CUDA(cudaMemsetAsync(unc1, 0, sizeof(int), st));
+  B200_CHECK_CUDA(cudaMemsetAsync(cert.uncert, 0, sizeof(int), st));
+  CertParams c1 = cert;
+  c1.uncert = unc1;
+  if ((rc = launch_rerank(rerank_kernel<kKP>, kKP, c1, nullptr))) return rc;
+  if ((rc = launch_rerank(rerank_kernel<kSel2>, kSel2, cert, unc1))) return rc;
+  launch_pdl(exact_topk_kernel, dim3(static_cast<unsigned>(std::min<long long>(nq, 4LL * b200_num_sms()))), dim3(256), 0, st, q, q_norm, g, g_norm,
+             ng, dim, k, p.self_offset, p.exclude_self, g_index_base, cert.uncert, out_idx, out_score);
+  B200_LAUNCH_CHECK();
   return B200_OK;
 }
 

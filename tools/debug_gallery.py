@@ -6,7 +6,7 @@ from bench import build_model
 dev = torch.device('cuda')
 wrap = build_model(1000, dev).eval()
 g = torch.Generator(device=dev).manual_seed(500)
-n_img = 12800
+n_img = int(sys.argv[1]) if len(sys.argv) > 1 else 12800
 imgs = torch.empty(n_img, 3, 224, 224, device=dev, dtype=torch.uint8)
 for lo in range(0, n_img // 2, 128):
     base = torch.nn.functional.interpolate(torch.rand(128, 3, 7, 7, device=dev, generator=g), size=224, mode='bilinear')
@@ -33,4 +33,7 @@ gap = t_sorted[:, 99] - a_sorted[:, 128].double()
 G1, Gr, dG1, dGr = gp.stats.double().tolist()
 E = qp.err[:, 0].double() * G1 + qp.err[:, 1].double() * Gr + qp.err[:, 2].double() * dG1 + qp.err[:, 3].double() * dGr
 print('gap(exact 100th - approx 129th): median %.3e min %.3e; E median %.3e max %.3e; would certify: %d' % (gap.median(), gap.min(), E.median(), E.max(), int((gap > E).sum())))
+for cut in (128, 256, 512, 1024, 2048):
+    gap_c = t_sorted[:, 99] - a_sorted[:, cut].double()
+    print('cut at approx rank %d: would certify %d of 2000' % (cut + 1, int((gap_c > E).sum())))
 print('score std among gallery for a query', t[0][t[0] > -1e8].std().item())
