@@ -223,7 +223,8 @@ int b200_cosine_topk(const float* q, const void* q_unit_f16, const double* q_nor
                      void* stream);
 /* b200_cosine_topk + exactness certificate: a query whose kept candidates cannot be PROVEN to contain the true top-k (bound on
  * |fp16 score - exact score| from the measured rounding residuals vs the margin between the pruning thresholds and the exact
- * k-th score) is re-done by an exact fp64 scan of the gallery.  uncertified: int [1 + nq] = count, then those queries. */
+ * k-th score) is first re-ranked again with 512 instead of 128 exactly re-scored candidates and, if still unproven, re-done by
+ * an exact fp64 scan of the gallery.  uncertified: int [1 + nq] = count of the queries that needed that scan, then their indices. */
 int b200_cosine_topk_certified(const float* q, const void* q_f16, const double* q_norm, const float* q_err, long long nq,
                                const float* g, const void* g_f16, const double* g_norm, const float* frame, float g_scale,
                                const float* g_stats, long long ng, int dim, int k, long long exclude_self_offset, long long g_index_base,
