@@ -57,6 +57,10 @@ struct Plan {
   // backward transients
   long long g_a, g_b, d_big, d_small, arena, demb16, dpooled;
   long long arena_bytes;               // partial-sum arena of the batched reductions (one batch per Swin block)
+  // backward: the weight-gradient GEMMs are off the critical chain (nothing but the optimizer reads them), so they run on a
+  // second stream and fill the tails of the chain's kernels; created on first use (B200_WGRAD_STREAM=0: everything in order)
+  mutable cudaStream_t side = nullptr;
+  mutable cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_done[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 ParamRef add_param(Plan& p, long long numel) {
@@ -178,7 +182,37 @@ void build(Plan& p) {
 struct Ctx {
   const Plan& p;
   const float* params; float* grads; bf16* wc; uint8_t* ws; cudaStream_t st; void* stv;
+  cudaStream_t side = nullptr;           // null: no second stream
+  mutable bool side_busy = false;        // the side stream holds work the main stream has not waited for yet
   mutable long long arena_used = 0;
+  // what the side stream launches next may read everything the main stream has been given so far
+  int fork() const {
+    if (side == nullptr) return B200_OK;
+    B200_CHECK_CUDA(cudaEventRecord(p.ev_fork, st));
+    B200_CHECK_CUDA(cudaStreamWaitEvent(side, p.ev_fork, 0));
+    return B200_OK;
+  }
+  // what the main stream launches next may overwrite the inputs / read the outputs of everything given to the side stream
+  int join() const {
+    if (side == nullptr || !side_busy) return B200_OK;
+    B200_CHECK_CUDA(cudaEventRecord(p.ev_join, side));
+    B200_CHECK_CUDA(cudaStreamWaitEvent(st, p.ev_join, 0));
+    side_busy = false;
+    return B200_OK;
+  }
+  void* wgrad_stream() const { if (side != nullptr) side_busy = true; return side != nullptr ? static_cast<void*>(side) : stv; }
+  // slot = which of a block's four weight gradients was just given to the side stream / must have finished before the main
+  // stream overwrites one of its operands
+  int done(int slot) const {
+    if (side == nullptr) return B200_OK;
+    B200_CHECK_CUDA(cudaEventRecord(p.ev_done[slot], side));
+    return B200_OK;
+  }
+  int wait(int slot) const {
+    if (side == nullptr) return B200_OK;
+    B200_CHECK_CUDA(cudaStreamWaitEvent(st, p.ev_done[slot], 0));
+    return B200_OK;
+  }
   // a slice of the partial-sum arena; when it runs out the recorded reductions are folded and the arena starts over
   float* take(long long bytes, int* rc) const {
     bytes = align_up(bytes, 256);
@@ -192,6 +226,8 @@ struct Ctx {
   }
   int flush(bool keep) const {
     arena_used = 0;
+    const int rc = join();               // the reductions read the partial sums the side stream's GEMMs write
+    if (rc) return rc;
     return b200_reduce_flush(stv, keep ? 1 : 0);
   }
   template <class T> T* W(long long off) const { return reinterpret_cast<T*>(ws + off); }
@@ -213,8 +249,10 @@ int linear_dgrad(const Ctx& c, const bf16* dy, long long M, int N, const bf16* w
 
 // dW[N,K] = dY[M,N]^T * X[M,K]: operands read in place (MN-major tcgen05 descriptors), split-K over the tokens,
 // fp32 partials reduced in a fixed order.
-int bias_grad(const Ctx& c, const bf16* dy, long long M, int N, float* db);
-// db (optional): the bias gradient colsum(dy), produced by the same kernel when the tile shape allows it
+int bias_grad(const Ctx& c, const bf16* dy, long long M, int N, float* db, void* stv);
+// db (optional): the bias gradient colsum(dy), produced by the same kernel when the tile shape allows it.
+// The GEMM goes to the side stream when there is one (call c.fork() where its inputs are final and c.join() before they are
+// overwritten); the reductions of its partial sums are recorded as always and run at the block's flush, after the join.
 int linear_wgrad(const Ctx& c, const bf16* dy, long long M, int N, const bf16* x, int K, float* dw, float* db = nullptr) {
   const int bn = (K <= 256) ? static_cast<int>(align_up(K, 16)) : 0;
   const int bn_eff = bn ? bn : 256;
@@ -226,24 +264,28 @@ int linear_wgrad(const Ctx& c, const bf16* dy, long long M, int N, const bf16* x
   int rc = 0;
   float* partial = c.take(1LL * splits * N * K * 4, &rc);
   RC(rc);
+  float* cs = nullptr;
+  if (db != nullptr) {
+    cs = c.take(1LL * splits * N * 4, &rc);
+    RC(rc);
+  }
+  void* wst = c.wgrad_stream();          // after the takes: a take may flush, and a flush joins
   if (db == nullptr) {
-    RC(b200_gemm_wgrad(dy, N, x, K, M, N, K, partial, splits, bn, c.stv));
+    RC(b200_gemm_wgrad(dy, N, x, K, M, N, K, partial, splits, bn, wst));
     return b200_splitk_reduce(partial, dw, 1LL * N * K, splits, 0, c.stv);
   }
-  float* cs = c.take(1LL * splits * N * 4, &rc);
-  RC(rc);
   int fused = 0;
-  RC(b200_gemm_wgrad_bias(dy, N, x, K, M, N, K, partial, cs, splits, bn, &fused, c.stv));
+  RC(b200_gemm_wgrad_bias(dy, N, x, K, M, N, K, partial, cs, splits, bn, &fused, wst));
   RC(b200_splitk_reduce(partial, dw, 1LL * N * K, splits, 0, c.stv));
   if (fused) return b200_splitk_reduce(cs, db, N, splits, 0, c.stv);
-  return bias_grad(c, dy, M, N, db);
+  return bias_grad(c, dy, M, N, db, wst);
 }
 
-int bias_grad(const Ctx& c, const bf16* dy, long long M, int N, float* db) {
+int bias_grad(const Ctx& c, const bf16* dy, long long M, int N, float* db, void* stv) {
   int rc = 0;
   float* partial = c.take(1LL * b200_colsum_blocks(M) * N * 4, &rc);
   RC(rc);
-  return b200_colsum(dy, N, M, N, db, partial, 0, c.stv);
+  return b200_colsum(dy, N, M, N, db, partial, 0, stv);
 }
 
 // LayerNorm backward with its partial rows in the arena.  win_shift >= 0: dy is in window-major order (LN1 of a block whose
@@ -325,8 +367,9 @@ int backward(const Ctx& c, const float* demb, int stage_hi, int stage_lo) {
     // ---- head: Linear <- LayerNorm <- mean pool  (models/swin.py:214-217, :224)
     bf16* d16 = c.W<bf16>(p.demb16);
     RC(b200_cast_f32_bf16(demb, d16, 1LL * p.B * p.num_classes, c.stv));
+    RC(c.fork());                                            // the head's weight gradient (side stream) reads d16
     RC(linear_wgrad(c, d16, p.B, p.num_classes, c.W<bf16>(p.pooled_n), L.C, c.G(p.head_w)));
-    RC(bias_grad(c, d16, p.B, p.num_classes, c.G(p.head_b)));
+    RC(bias_grad(c, d16, p.B, p.num_classes, c.G(p.head_b), c.stv));
     bf16* dpn = c.W<bf16>(p.dpooled);
     RC(linear_dgrad(c, d16, p.B, p.num_classes, c.wc + p.head_w16t, L.C, B200_EPI_STORE, dpn, nullptr));
     bf16* dpool = c.W<bf16>(p.d_small);
@@ -347,39 +390,54 @@ int backward(const Ctx& c, const float* demb, int stage_hi, int stage_lo) {
       bf16* dbig = c.W<bf16>(p.d_big);
       bf16* dsmall = c.W<bf16>(p.d_small);
       // ---- MLP: x_out = x_mid + W2 gelu(W1 LN2(x_mid) + b1) + b2
+      // The four weight gradients of a block go to the side stream (see Plan::side): fork() marks the point from which their
+      // operands are final, done(i) / wait(i) keep the main stream from overwriting an operand (g, dbig) before they have read it.
+      RC(c.fork());
       RC(linear_dgrad(c, g, M, C, c.wc + q.w216t, 4 * C, B200_EPI_DGELU, dbig, c.W<bf16>(a.hgrad)));   // d h_pre = (dy W2) o gelu'(h_pre)
       RC(linear_wgrad(c, g, M, C, c.W<bf16>(a.hact), 4 * C, c.G(q.w2)));
+      RC(c.done(0));
+      RC(c.fork());
       RC(linear_dgrad(c, dbig, M, 4 * C, c.wc + q.w116t, C, B200_EPI_STORE, dsmall, nullptr));        // d xn2
       RC(linear_wgrad(c, dbig, M, 4 * C, c.W<bf16>(a.xn2), C, c.G(q.w1), c.G(q.b1)));            // + d b1 = colsum(d h_pre)
+      RC(c.done(1));
       // g <- d x_mid; the same pass yields d b2 = colsum(g): g is dL/d(fc2 output)
+      RC(c.wait(0));
       RC(ln_bwd(c, dsmall, c.W<bf16>(a.xmid), c.P(q.ln2_w), c.W<float>(a.mean2), c.W<float>(a.rstd2), g, g,
                 c.G(q.ln2_w), c.G(q.ln2_b), c.G(q.b2), M, C));
       // ---- attention: x_mid = x_in + Wo attn(LN1(x_in)) + bo
+      RC(c.fork());
       RC(linear_dgrad(c, g, M, C, c.wc + q.wo16t, C, B200_EPI_STORE, dsmall, nullptr));               // d attn_out
       RC(linear_wgrad(c, g, M, C, c.W<bf16>(a.attn), C, c.G(q.wo)));
+      RC(c.done(2));
       {
         int rc = 0;
         float* scratch = c.take(b200_window_attn_bwd_scratch_floats(b200_window_attn_bwd_blocks(p.B, S.Hs, S.Hs, S.heads)) * 4, &rc);
         RC(rc);
+        RC(c.wait(1));
         RC(b200_window_attn_bwd(c.W<bf16>(a.qkv), c.P(q.pos), c.W<float>(a.lse), dsmall, dbig, c.G(q.pos), scratch, 0, p.B, S.Hs, S.Hs, C,
                                 S.heads, b & 1, c.stv));                                                // dbig <- d qkv
       }
+      RC(c.fork());
       RC(linear_dgrad(c, dbig, M, 3 * C, c.wc + q.wqkv16t, C, B200_EPI_STORE, dsmall, nullptr));      // d xn1
       RC(linear_wgrad(c, dbig, M, 3 * C, c.W<bf16>(a.xn1), C, c.G(q.wqkv)));
+      RC(c.done(3));
       // g <- d x_in; d bo = colsum(g before the update): g is dL/d(to_out output)
+      RC(c.wait(2));
       RC(ln_bwd_win(c, dsmall, x_in, c.P(q.ln1_w), c.W<float>(a.mean1), c.W<float>(a.rstd1), g, g, c.G(q.ln1_w), c.G(q.ln1_b), c.G(q.bo),
                     p.B, S.Hs, C, b & 1));
       RC(c.flush(true));                                     // the block's eight reductions: one launch
     }
     // ---- patch merging linear (models/swin.py:162-167)
+    RC(c.fork());
     RC(linear_wgrad(c, g, M, C, c.W<bf16>(S.cols), S.Kp, c.G(S.wp), c.G(S.bp)));
     if (s > 0) {
       bf16* dcols = c.W<bf16>(p.d_big);
       RC(linear_dgrad(c, g, M, C, c.wc + S.wp16t, S.Kp, B200_EPI_STORE, dcols, nullptr));
       RC(b200_patch_gather_nhwc(gbuf(s - 1), dcols, p.B, p.st[s - 1].Hs, p.st[s - 1].Hs, p.st[s - 1].C, 1, c.stv));
     }
+    RC(c.join());                                            // the patch-merging weight gradient reads g, which the next stage reuses
   }
-  return B200_OK;
+  return c.join();
 }
 
 // fp32 master weights -> the bf16 (and transposed bf16) copies the GEMMs read: one launch over a table of all matrices
@@ -456,7 +514,18 @@ extern "C" void* b200_swin_create(int batch, int img, int channels, int hidden_d
   return p;
 }
 
-extern "C" void b200_swin_destroy(void* plan) { delete reinterpret_cast<Plan*>(plan); }
+extern "C" void b200_swin_destroy(void* plan) {
+  Plan* p = reinterpret_cast<Plan*>(plan);
+  if (p == nullptr) return;
+  if (p->side != nullptr) {
+    cudaStreamSynchronize(p->side);
+    cudaStreamDestroy(p->side);
+    cudaEventDestroy(p->ev_fork);
+    cudaEventDestroy(p->ev_join);
+    for (auto& e : p->ev_done) cudaEventDestroy(e);
+  }
+  delete p;
+}
 
 extern "C" long long b200_swin_param_elems(const void* plan) { return reinterpret_cast<const Plan*>(plan)->n_params; }
 extern "C" int b200_swin_param_count(const void* plan) { return static_cast<int>(reinterpret_cast<const Plan*>(plan)->order.size()); }
@@ -494,10 +563,21 @@ extern "C" int b200_swin_backward(const void* plan, const float* params, const v
     return b200_set_error(B200_ERR_WORKSPACE, "swin_backward: workspace %lld < required %lld bytes", workspace_bytes, p->ws_bytes);
   Ctx c{*p, params, grads, reinterpret_cast<bf16*>(const_cast<void*>(wcache)), reinterpret_cast<uint8_t*>(workspace),
         reinterpret_cast<cudaStream_t>(stream), stream};
+  static const bool side_on = [] { const char* e = getenv("B200_WGRAD_STREAM"); return e == nullptr || e[0] != '0'; }();
+  if (side_on) {
+    if (p->side == nullptr) {
+      B200_CHECK_CUDA(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
+      B200_CHECK_CUDA(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+      B200_CHECK_CUDA(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
+      for (auto& e : p->ev_done) B200_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    c.side = p->side;
+  }
   // every fixed-order reduction of the pass is recorded and folded one batch per block (see Ctx::take / flush); whatever
   // happens, deferred mode ends with this call
   int rc = b200_reduce_defer_begin();
   if (rc == B200_OK) rc = backward(c, demb, stage_hi, stage_lo);
+  const int rc_join = c.join();          // also on the error path: nothing may stay behind on the side stream
   const int rc_flush = b200_reduce_flush(stream, 0);
-  return rc ? rc : rc_flush;
+  return rc ? rc : (rc_join ? rc_join : rc_flush);
 }
