@@ -422,7 +422,7 @@ def gpu_arm(args, rank, world, local_rank):
                                 'algorithmic_flops_per_step': gemm_fl.value / args.steps},
                      'peak_source': peak_src, 'launches_timed': int(gemm_n.value),
                      'kernel_ms_per_step': gemm_ms.value / args.steps, 'step_share': gemm_ms.value / ms_b if ms_b else None,
-                     'timed_region': f'{args.steps} further steps with per-launch events ({ms_b / args.steps:.2f} ms/step)',
+                     'timed_region': f'{args.steps} further steps with per-launch events, everything on one stream - the weight-gradient side stream of the backward is off while launches are timed one by one ({ms_b / args.steps:.2f} ms/step)',
                      'whole_step_frac': value / world * train_flops_per_image() / (peak_tf * 1e12) if peak_tf else None},
         'clocks': clocks,
     }

@@ -90,6 +90,7 @@ int splitk_reduce_multi(const float* partial, float* const* outs, int ny, long l
 // optional per-launch CUDA-event timing of the library's kernels by kind (bench.py roofline): no-ops unless enabled.
 // kinds: see B200_PROF_* in b200_fe.h; flops / bytes are the ALGORITHMIC work of the launch
 bool b200_prof_kind_begin(cudaStream_t stream, int kind, double flops, double bytes);
+bool b200_prof_timing();
 void b200_prof_kind_end(cudaStream_t stream);
 inline bool b200_prof_gemm_begin(cudaStream_t stream, double flops, double bytes) { return b200_prof_kind_begin(stream, 0, flops, bytes); }
 inline void b200_prof_gemm_end(cudaStream_t stream) { b200_prof_kind_end(stream); }

@@ -77,6 +77,7 @@ int b200_num_sms() {
 #include <vector>
 static std::atomic<long long> g_launches{0};
 static bool g_prof_gemm = false;
+bool b200_prof_timing() { return g_prof_gemm; }      // per-launch event timing is on (b200_prof_begin(1) .. b200_prof_end)
 struct GemmEv { cudaEvent_t a, b; double flops, bytes; int kind; };
 constexpr int kProfKinds = 8;
 static double g_kind_ms[kProfKinds], g_kind_flops[kProfKinds], g_kind_bytes[kProfKinds];

@@ -564,7 +564,9 @@ extern "C" int b200_swin_backward(const void* plan, const float* params, const v
   Ctx c{*p, params, grads, reinterpret_cast<bf16*>(const_cast<void*>(wcache)), reinterpret_cast<uint8_t*>(workspace),
         reinterpret_cast<cudaStream_t>(stream), stream};
   static const bool side_on = [] { const char* e = getenv("B200_WGRAD_STREAM"); return e == nullptr || e[0] != '0'; }();
-  if (side_on) {
+  // while launches are being timed one by one (bench.py's roofline region) everything stays on one stream: a kernel's
+  // event pair must bracket that kernel alone, not its competition with another stream for SMs
+  if (side_on && !b200_prof_timing()) {
     if (p->side == nullptr) {
       B200_CHECK_CUDA(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
       B200_CHECK_CUDA(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
