@@ -61,6 +61,8 @@ struct Plan {
   // second stream and fill the tails of the chain's kernels; created on first use (B200_WGRAD_STREAM=0: everything in order)
   mutable cudaStream_t side = nullptr;
   mutable cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_done[4] = {nullptr, nullptr, nullptr, nullptr};
+  mutable cudaEvent_t ev_red[2] = {nullptr, nullptr};      // the batched reduction that last read arena half 0 / 1
+  mutable int half = 0;                                      // arena half the next partial sums go to (persists across calls)
 };
 
 ParamRef add_param(Plan& p, long long numel) {
@@ -172,7 +174,7 @@ void build(Plan& p) {
     // own slice, the block's reductions are folded by ONE batched launch, then the arena is reused.
     p.arena_bytes = 4 * (1LL * 160 * 128 * 256 * 4) + 2 * (1LL * 8 * 160 * 3 * 1536 * 4) + 1LL * 2 * 160 * 4 * 1536 * 4 +
                     b200_window_attn_bwd_scratch_floats(b200_num_sms()) * 4 + (1 << 20);
-    p.arena = add_ws(p, p.arena_bytes);
+    p.arena = add_ws(p, 2 * p.arena_bytes);      // two halves: a block's reductions (side stream) run while the next block fills the other
     p.demb16 = add_ws(p, 1LL * p.B * p.num_classes * 2);
     p.dpooled = add_ws(p, 1LL * p.B * C4 * 2);
   }
@@ -220,15 +222,25 @@ struct Ctx {
       *rc = bytes > p.arena_bytes ? B200_ERR_INVALID : flush(true);
       if (*rc) return nullptr;
     }
-    float* ptr = reinterpret_cast<float*>(ws + p.arena + arena_used);
+    float* ptr = reinterpret_cast<float*>(ws + p.arena + (side != nullptr ? p.half * p.arena_bytes : 0) + arena_used);
     arena_used += bytes;
     return ptr;
   }
   int flush(bool keep) const {
     arena_used = 0;
-    const int rc = join();               // the reductions read the partial sums the side stream's GEMMs write
+    if (side == nullptr) return b200_reduce_flush(stv, keep ? 1 : 0);
+    // Two streams: the batched reduction follows the weight gradients on the side stream (it also reads partial sums the main
+    // stream produced: LayerNorm rows, the attention scratch - hence the fork) and the main stream moves on to the next block,
+    // which fills the other half of the arena; a half is written again only after the reduction that read it has run.
+    int rc = fork();
     if (rc) return rc;
-    return b200_reduce_flush(stv, keep ? 1 : 0);
+    rc = b200_reduce_flush(side, keep ? 1 : 0);
+    if (rc) return rc;
+    B200_CHECK_CUDA(cudaEventRecord(p.ev_red[p.half], side));
+    side_busy = true;
+    p.half ^= 1;
+    B200_CHECK_CUDA(cudaStreamWaitEvent(st, p.ev_red[p.half], 0));
+    return B200_OK;
   }
   template <class T> T* W(long long off) const { return reinterpret_cast<T*>(ws + off); }
   const float* P(const ParamRef& r) const { return params + r.off; }
@@ -393,6 +405,7 @@ int backward(const Ctx& c, const float* demb, int stage_hi, int stage_lo) {
       // The four weight gradients of a block go to the side stream (see Plan::side): fork() marks the point from which their
       // operands are final, done(i) / wait(i) keep the main stream from overwriting an operand (g, dbig) before they have read it.
       RC(c.fork());
+      RC(c.wait(3));                                         // the previous block's qkv weight gradient has read d_big
       RC(linear_dgrad(c, g, M, C, c.wc + q.w216t, 4 * C, B200_EPI_DGELU, dbig, c.W<bf16>(a.hgrad)));   // d h_pre = (dy W2) o gelu'(h_pre)
       RC(linear_wgrad(c, g, M, C, c.W<bf16>(a.hact), 4 * C, c.G(q.w2)));
       RC(c.done(0));
@@ -432,6 +445,7 @@ int backward(const Ctx& c, const float* demb, int stage_hi, int stage_lo) {
     RC(linear_wgrad(c, g, M, C, c.W<bf16>(S.cols), S.Kp, c.G(S.wp), c.G(S.bp)));
     if (s > 0) {
       bf16* dcols = c.W<bf16>(p.d_big);
+      RC(c.wait(3));                                         // the last block's qkv weight gradient has read d_big
       RC(linear_dgrad(c, g, M, C, c.wc + S.wp16t, S.Kp, B200_EPI_STORE, dcols, nullptr));
       RC(b200_patch_gather_nhwc(gbuf(s - 1), dcols, p.B, p.st[s - 1].Hs, p.st[s - 1].Hs, p.st[s - 1].C, 1, c.stv));
     }
@@ -523,6 +537,7 @@ extern "C" void b200_swin_destroy(void* plan) {
     cudaEventDestroy(p->ev_fork);
     cudaEventDestroy(p->ev_join);
     for (auto& e : p->ev_done) cudaEventDestroy(e);
+    for (auto& e : p->ev_red) cudaEventDestroy(e);
   }
   delete p;
 }
@@ -572,6 +587,7 @@ extern "C" int b200_swin_backward(const void* plan, const float* params, const v
       B200_CHECK_CUDA(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
       B200_CHECK_CUDA(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
       for (auto& e : p->ev_done) B200_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      for (auto& e : p->ev_red) B200_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
     c.side = p->side;
   }
