@@ -9,7 +9,10 @@ import numpy as np
 import pytest
 import torch
 
+from pathlib import Path
+
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
+ROOT = Path(__file__).resolve().parents[1]
 
 
 def rel(got, ref):
@@ -158,6 +161,51 @@ def test_batch_odd_sizes_and_repeatability(setup):
         c = wrap(x[:3])
     assert torch.equal(a, b)                                  # deterministic forward
     assert torch.allclose(a[:3], c, rtol=0, atol=0)           # rows independent of batch composition
+
+
+@pytest.mark.parametrize('batch', [6, 40])
+def test_backward_is_bit_reproducible_with_the_side_stream(setup, batch):
+    """The backward runs its weight gradients and batched reductions on a second stream (csrc/swin_plan.cu).  Every reduction
+    has a fixed order, so two runs from the same state must agree bit for bit - and with the single-stream order
+    (`B200_WGRAD_STREAM=0` in a child process): a missing event dependency would show up here long before it moved a tolerance."""
+    import os
+    import subprocess
+    import sys
+    g, sd, wrap, img, label = setup
+    from b200 import synth
+    x = synth.synth_images(batch, seed=21).cuda()
+    y = synth.synth_labels(batch, 1000, seed=21).cuda()
+    wrap.train()
+
+    def grads():
+        for p in wrap.parameters():
+            p.grad = None
+        wrap(x, y)['loss'].backward()
+        torch.cuda.synchronize()
+        return torch.cat([p.grad.flatten() for p in wrap.parameters() if p.grad is not None]).clone()
+
+    first = grads()
+    for _ in range(4):
+        assert torch.equal(grads(), first)
+    out = Path(os.environ.get('TMPDIR', '/tmp')) / f'b200_single_stream_grads_{batch}.pt'
+    code = (
+        "import sys, torch; sys.path[:0] = [%r, %r]\n"
+        "from b200 import synth\n"
+        "from losses import SoftmaxBasedMetricLearning\n"
+        "from models import swin_t\n"
+        "from oracle.swin_oracle import SwinSpec, param_shapes\n"
+        "m = swin_t(num_classes=512); m.load_state_dict(synth.synth_state_dict(param_shapes(SwinSpec()), seed=123))\n"
+        "w = SoftmaxBasedMetricLearning(m, num_class=1000, embedding_size=512, is_focal=True, arc_margin=True)\n"
+        "w.add_margin.weight.data.copy_(synth.synth_tensor('add_margin.weight', (1000, 512), seed=123)); w = w.cuda().train()\n"
+        "x = synth.synth_images(%d, seed=21).cuda(); y = synth.synth_labels(%d, 1000, seed=21).cuda()\n"
+        "w(x, y)['loss'].backward(); torch.cuda.synchronize()\n"
+        "torch.save(torch.cat([p.grad.flatten() for p in w.parameters() if p.grad is not None]).cpu(), %r)\n"
+    ) % (str(ROOT), str(ROOT / 'pets-face-recognition_b200'), batch, batch, str(out))
+    env = dict(os.environ, B200_WGRAD_STREAM='0')
+    r = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    single = torch.load(out)
+    assert torch.equal(single, first.cpu())
 
 
 def test_uint8_images_equal_totensor_floats(setup):
