@@ -73,6 +73,10 @@ struct FilterParams {
   int kb;                     // dim / 64
   int chunks;                 // gallery chunks
   long long chunk_rows;       // multiple of 256
+  // ragged last wave: the last `q_groups - full_groups` query groups are cut into tail_chunks chunks of tail_chunk_rows rows each
+  // (0: every group has p.chunks chunks) - see plan_layout
+  int full_groups, tail_chunks;
+  long long tail_chunk_rows;
   int q_blocks;
   long long self_offset;      // gallery row (self_offset + q) is excluded for query q
   int exclude_self;
@@ -227,20 +231,30 @@ cosine_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   // work units: (group of PAIR consecutive query blocks, gallery chunk); CTA `crank` of a pair takes query block
   // group * PAIR + crank (a block past the end scores zero-filled queries and writes nothing)
   const int q_groups = (p.q_blocks + PAIR - 1) / PAIR;
-  const int units = q_groups * p.chunks;
+  const int full_groups = p.tail_chunks > 0 ? p.full_groups : q_groups;
+  const int tail_groups = q_groups - full_groups;
+  const int units_full = full_groups * p.chunks;
+  const int units = units_full + tail_groups * p.tail_chunks;
   const int cluster_id = static_cast<int>(blockIdx.x) / PAIR, n_clusters = static_cast<int>(gridDim.x) / PAIR;
   constexpr int kSliceRows = kBN / PAIR;
-  auto tiles_of = [&](int chunk) -> int {
-    const long long g0 = p.g_begin + 1LL * chunk * p.chunk_rows;
-    const long long g1 = min(p.ng, g0 + p.chunk_rows);
-    return static_cast<int>((g1 - g0 + kBN - 1) / kBN);
+  struct Unit { int qg, chunk, nt; long long g0, g1; };
+  auto unit_of = [&](int unit) -> Unit {
+    Unit u;
+    long long rows;
+    if (unit < units_full) { u.chunk = unit / full_groups; u.qg = unit - u.chunk * full_groups; rows = p.chunk_rows; }
+    else { const int v = unit - units_full; u.chunk = v / tail_groups; u.qg = full_groups + v - u.chunk * tail_groups; rows = p.tail_chunk_rows; }
+    u.g0 = p.g_begin + 1LL * u.chunk * rows;
+    u.g1 = min(p.ng, u.g0 + rows);
+    u.nt = u.g1 > u.g0 ? static_cast<int>((u.g1 - u.g0 + kBN - 1) / kBN) : 0;
+    return u;
   };
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0, qphase = 0;
       for (int unit = cluster_id; unit < units; unit += n_clusters) {
-        const int qb = (unit % q_groups) * PAIR + crank, chunk = unit / q_groups;
+        const Unit u = unit_of(unit);
+        const int qb = u.qg * PAIR + crank;
         mbar_wait_backoff(qempty_bar, qphase ^ 1u, p.wait_ns);
         if (PAIR == 1) {
           mbar_arrive_expect_tx(qfull_bar, static_cast<uint32_t>(p.kb * kQSlab));
@@ -251,8 +265,8 @@ cosine_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
           if (!leader) mbar_arrive_remote(qfull_bar, 0u);
         }
         qphase ^= 1u;
-        const int nt = tiles_of(chunk);
-        const long long g0 = p.g_begin + 1LL * chunk * p.chunk_rows;
+        const int nt = u.nt;
+        const long long g0 = u.g0;
         for (int t = 0; t < nt; ++t)
           for (int kb = 0; kb < p.kb; ++kb) {
             mbar_wait_backoff(empty_bar(stage), phase ^ 1u, p.wait_ns);
@@ -274,11 +288,10 @@ cosine_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       int stage = 0; uint32_t phase = 0, qphase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int unit = cluster_id; unit < units; unit += n_clusters) {
-        const int chunk = unit / q_groups;
         mbar_wait_backoff(qfull_bar, qphase, p.wait_ns);
         qphase ^= 1u;
         tc_fence_after();
-        const int nt = tiles_of(chunk);
+        const int nt = unit_of(unit).nt;
         for (int t = 0; t < nt; ++t) {
           mbar_wait_backoff(tempty_bar(acc), acc_phase ^ 1u, p.wait_ns);
           tc_fence_after();
@@ -322,13 +335,13 @@ cosine_filter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     uint2* list = warp_lists + 1LL * lane * kCap;
     int acc = 0; uint32_t acc_phase = 0;
     for (int unit = cluster_id; unit < units; unit += n_clusters) {
-      const int qb = (unit % q_groups) * PAIR + crank, chunk = unit / q_groups;
+      const Unit u = unit_of(unit);
+      const int qb = u.qg * PAIR + crank, chunk = u.chunk;
       const long long qrow = 1LL * qb * kBM + row;
       const bool live = qrow < p.nq;
       const long long self_col = p.exclude_self ? (p.self_offset + qrow) : -(1LL << 62);
-      const long long g0 = p.g_begin + 1LL * chunk * p.chunk_rows;
-      const long long g1 = min(p.ng, g0 + p.chunk_rows);
-      const int nt = tiles_of(chunk);
+      const long long g0 = u.g0, g1 = u.g1;
+      const int nt = u.nt;
       float tau = -INFINITY;
       if (live && p.tau_init != nullptr) {
         tau = p.tau_init[kParts * qrow];
@@ -978,6 +991,8 @@ struct Layout {
   long long witness_rows;      // rows [0, witness_rows) seed the thresholds (0 = single pass, unseeded)
   int chunks;                  // gallery chunks of the list pass
   long long chunk_rows;
+  int full_groups = 0, tail_chunks = 0;      // ragged last wave (see plan_layout); tail_chunks = 0: off
+  long long tail_chunk_rows = 0;
   long long ng;                // gallery rows
   float* tau_ptr;              // [q_blocks*128][2] thresholds handed from the witness pass to the list pass
 };
@@ -1021,9 +1036,32 @@ Layout plan_layout(long long nq, long long ng) {
   L.q_blocks = static_cast<int>((nq + kBM - 1) / kBM);
   const int sms = b200_num_sms();
   L.witness_rows = (ng >= 4LL * kWitnessRows) ? kWitnessRows : 0;      // small galleries: the unseeded flood is cheaper
-  if (use_pair(L.q_blocks)) pick_chunks(ng, (L.q_blocks + 1) / 2, sms / 2, &L.chunks, &L.chunk_rows);
-  else pick_chunks(ng, L.q_blocks, sms, &L.chunks, &L.chunk_rows);
-  L.lists = kParts * L.chunks;
+  const int q_groups = use_pair(L.q_blocks) ? (L.q_blocks + 1) / 2 : L.q_blocks;
+  const int slots = use_pair(L.q_blocks) ? sms / 2 : sms;
+  pick_chunks(ng, q_groups, slots, &L.chunks, &L.chunk_rows);
+  // Ragged last wave.  With one chunk per query group the units are dealt in waves of `slots`; 196 groups on 74 CTA pairs are
+  // 2.65 waves, i.e. 26 pairs idle for a whole unit (12 % of the pass).  Only the r = q_groups mod slots groups of the last
+  // wave are cut into c gallery chunks - their r * c smaller units take ceil(r c / slots) / c of a unit time instead of 1 -
+  // so that the price of chunking (separate candidate lists, restarted thresholds) is paid by those queries alone.
+  // B200_GALLERY_TAIL=0 turns it off.
+  static const bool tail_on = [] { const char* e = getenv("B200_GALLERY_TAIL"); return e == nullptr || e[0] != '0'; }();
+  const long long tiles = (ng + kBN - 1) / kBN;
+  const int r = q_groups % slots;
+  if (tail_on && L.chunks == 1 && q_groups >= 2 * slots && r > 0 && tiles >= 64) {
+    int best_c = 1;
+    double best = 1.0;
+    for (int c = 2; c <= std::min<long long>(8, 64 / kParts - 1); ++c) {
+      const double t = static_cast<double>((1LL * r * c + slots - 1) / slots) / c;
+      if (t < best - 0.05) { best = t; best_c = c; }
+    }
+    if (best_c > 1) {
+      const long long tpc = (tiles + best_c - 1) / best_c;
+      L.full_groups = q_groups - r;
+      L.tail_chunks = static_cast<int>((tiles + tpc - 1) / tpc);
+      L.tail_chunk_rows = tpc * kBN;
+    }
+  }
+  L.lists = kParts * std::max(L.chunks, L.tail_chunks);
   long long off = 0;
   auto take = [&](long long bytes) { long long o = off; off = (off + bytes + 255) / 256 * 256; return o; };
   L.scratch = take(1LL * sms * kParts * kBM * kCap * 8);
@@ -1071,22 +1109,25 @@ int launch_filter(const CUtensorMap& tq, const CUtensorMap& tg, const CUtensorMa
   const int sms = b200_num_sms();
   const bool pair = use_pair(L.q_blocks);
   auto run = [&](int q_blocks, int chunks) -> int {
+    const int q_groups = pair ? (q_blocks + 1) / 2 : q_blocks;
+    const int units = p.tail_chunks > 0 ? p.full_groups * chunks + (q_groups - p.full_groups) * p.tail_chunks : q_groups * chunks;
     if (pair) {
       FilterParams pp = p;
       pp.idesc = gemm::make_idesc(false, kBN, false, 256);
-      const int units = (q_blocks + 1) / 2 * chunks;
       return launch_one<2>(tq, tg_half, pp, 2 * std::min(units, sms / 2), st);
     }
-    return launch_one<1>(tq, tg, p, std::min(q_blocks * chunks, sms), st);
+    return launch_one<1>(tq, tg, p, std::min(units, sms), st);
   };
   int rc;
   p.g_begin = 0;
   if (L.witness_rows > 0) {
     p.ng = L.witness_rows; p.chunks = 1; p.chunk_rows = L.witness_rows;
     p.witness = 1; p.tau_init = nullptr; p.tau_out = L.tau_ptr;
+    p.full_groups = 0; p.tail_chunks = 0; p.tail_chunk_rows = 0;
     if ((rc = run(L.q_blocks, 1))) return rc;
   }
   p.ng = L.ng; p.chunks = L.chunks; p.chunk_rows = L.chunk_rows;
+  p.full_groups = L.full_groups; p.tail_chunks = L.tail_chunks; p.tail_chunk_rows = L.tail_chunk_rows;
   p.witness = 0; p.tau_init = L.witness_rows ? L.tau_ptr : nullptr; p.tau_out = nullptr;
   return run(L.q_blocks, L.chunks);
 }
@@ -1178,6 +1219,12 @@ static int cosine_topk_impl(const float* q, const void* q_unit_f16, const double
   L.tau_ptr = reinterpret_cast<float*>(ws + L.tau);
   p.tau_shared = reinterpret_cast<uint32_t*>(ws + L.tau_shared);
   B200_CHECK_CUDA(cudaMemsetAsync(p.tau_shared, 0, sizeof(uint32_t) * L.q_blocks * kBM, st));
+  if (L.tail_chunks > 0) {
+    // queries of the full waves fill only their first kParts * chunks lists: the others must read as empty, and their
+    // thresholds as "nothing dropped" (0xff.. = NaN, which fmaxf ignores)
+    B200_CHECK_CUDA(cudaMemsetAsync(p.cand_cnt, 0, sizeof(int) * L.q_blocks * kBM * L.lists, st));
+    B200_CHECK_CUDA(cudaMemsetAsync(p.list_tau, 0xff, sizeof(float) * L.q_blocks * kBM * L.lists, st));
+  }
   CUtensorMap tq, tg;
   int rc = gemm::encode_tmap_2d(&tq, false, q_unit_f16, dim, nq, dim, kBK, kBM);
   if (rc) return rc;
