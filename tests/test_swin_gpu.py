@@ -171,11 +171,18 @@ def test_backward_is_bit_reproducible_with_the_side_stream(setup, batch):
     import os
     import subprocess
     import sys
-    g, sd, wrap, img, label = setup
     from b200 import synth
+    from losses import SoftmaxBasedMetricLearning
+    from models import swin_t
+    from oracle.swin_oracle import SwinSpec, param_shapes
+    # a model of its own: the module-scoped fixture has been stepped by the optimizer tests by the time this one runs
+    model = swin_t(num_classes=512)
+    model.load_state_dict(synth.synth_state_dict(param_shapes(SwinSpec()), seed=123))
+    wrap = SoftmaxBasedMetricLearning(model, num_class=1000, embedding_size=512, is_focal=True, arc_margin=True)
+    wrap.add_margin.weight.data.copy_(synth.synth_tensor('add_margin.weight', (1000, 512), seed=123))
+    wrap = wrap.cuda().train()
     x = synth.synth_images(batch, seed=21).cuda()
     y = synth.synth_labels(batch, 1000, seed=21).cuda()
-    wrap.train()
 
     def grads():
         for p in wrap.parameters():
