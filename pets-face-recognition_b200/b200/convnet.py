@@ -132,7 +132,11 @@ class ConvNetEngine:
         out = torch.empty(4, Cc, device=x.device, dtype=torch.float32)
         if training:
             track = bn.track_running_stats and bn.running_mean is not None
-            momentum = 0.1 if bn.momentum is None else float(bn.momentum)
+            if bn.momentum is None:           # nn.BatchNorm2d: cumulative moving average, factor 1 / (batches seen, this one included)
+                seen = int(bn.num_batches_tracked) if (track and bn.num_batches_tracked is not None) else 0
+                momentum = 1.0 / (seen + 1)
+            else:
+                momentum = float(bn.momentum)
             check(lib().b200_bn_stats(ptr(x), rows, Cc, H, W, float(count), ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean) if track else None,
                                       ptr(bn.running_var) if track else None, momentum, float(bn.eps), ptr(out), ptr(self._scratch(rows, Cc, x.device)),
                                       stream_ptr()), 'bn_stats')
@@ -140,6 +144,8 @@ class ConvNetEngine:
             if track and bn.num_batches_tracked is not None:
                 self._counters.append(bn.num_batches_tracked)       # bumped together at the end of the forward (one launch)
         else:
+            if bn.running_mean is None or bn.running_var is None:
+                raise B200Error('eval-mode BatchNorm without running statistics (track_running_stats=False) is not built')
             # eval mode: constants of the running statistics, rebuilt only when one of the four tensors changes
             key = (_plan._weight_epoch, bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version, bn.weight.data_ptr())
             hit = self._eval_consts.get(id(bn))
