@@ -84,6 +84,8 @@ class ConvNetEngine:
 
     def _folded(self, conv, bn):
         """eval mode: (bf16 [Co, (r, s, ci)] weights with the BatchNorm scale folded in, fp32 shift), rebuilt when a tensor changes"""
+        if bn.running_mean is None or bn.running_var is None:
+            raise B200Error('eval-mode BatchNorm without running statistics (track_running_stats=False) is not built')
         key = (_plan._weight_epoch, conv.weight._version, bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version,
                conv.weight.data_ptr())
         hit = self._folded_cache.get(id(conv))
