@@ -395,6 +395,10 @@ def gpu_arm(args, rank, world, local_rank):
     achieved_gbs = gemm_by.value / (gemm_ms.value * 1e-3) / 1e9 if gemm_ms.value > 0 else 0.0
     # the GEMM launches of this network are mostly small-K (96..768): in aggregate their algorithmic HBM time exceeds their
     # tensor-core time, so the binding roofline is whichever fraction is larger; both are reported
+    grad_exchange = None
+    if world > 1:
+        grad_exchange = ('copy-engine pushes into every rank\'s peer arena (CUDA IPC over NVLink) under the backward + slot sum inside the '
+                         'optimizer kernel (b200/peer.py)') if trainer.ddp_mode == 'p2p' else 'per-stage NCCL all-reduce on a side stream'
     hbm_bound = peak_hbm and peak_tf and achieved_gbs / peak_hbm >= achieved_tf / peak_tf
     traffic = ncu_traffic()
     line = {
@@ -403,7 +407,7 @@ def gpu_arm(args, rank, world, local_rank):
         'data': 'synthetic',
         'config': {'workload': f'configs[1]: dog-head FE training step, Swin-T 224x224 + ArcFace(C={NUM_CLASS}, s=64, m=0.5) + mean CE + '
                                f'SGD(momentum 0.9, 3 param groups), per-GPU batch {B}, global batch {B * world}',
-                   'parallelism': f'dp{world}', 'l2': 'inputs larger than L2 (154 MB of images per batch, two batches alternated; '
+                   'parallelism': f'dp{world}', 'grad_exchange': grad_exchange, 'l2': 'inputs larger than L2 (154 MB of images per batch, two batches alternated; '
                                                       'each step streams > 10 GB of activations)',
                    'flops_per_image': train_flops_per_image(), 'final_loss': final_loss},
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
@@ -459,6 +463,7 @@ def gpu_arm(args, rank, world, local_rank):
         except Exception as e:          # a baseline, not the product: report why it is missing and go on
             line['cpu_baseline']['gpu_eager'] = {'unavailable': f'{type(e).__name__}: {str(e)[:160]}'}
     emit(line)
+    trainer.close()
 
 
 def extract_leg(args, wrap, dev_batches, world, device):

@@ -186,6 +186,21 @@ int b200_opt_chunk_elems(void);
  * is uploaded once and not once per step */
 int b200_optimizer_step(int kind, const void* tensors_dev, const void* chunks_dev, int n_chunks, float grad_scale, int step_offset,
                         void* stream);
+/* The same step with the gradient of every tensor taken as the sum of n_src copies: copy r of element i is read at
+ * grad[src_shift + r * src_stride + i] (elements).  This is the data-parallel step: the copies are the ranks' slots of the
+ * peer arena below, summed in slot order on every rank, so the all-reduce is folded into the optimizer pass. */
+int b200_optimizer_step_sum(int kind, const void* tensors_dev, const void* chunks_dev, int n_chunks, float grad_scale, int step_offset,
+                            int n_src, long long src_stride, long long src_shift, void* stream);
+
+/* ---- gradient exchange over NVLink peer memory: replaces the bucketed NCCL all-reduce that Lightning's DDPPlugin /
+ *      torch DDP run for the reference (utils/__init__.py:114-119, get_strategy).  One process per GPU; the arena of a rank is
+ *      cudaMalloc'ed memory exported through CUDA IPC (64-byte handle), opened by the other ranks of the node, and written by
+ *      them with asynchronous peer copies (copy engines, no SMs).  Host protocol: b200/peer.py. -------------------------- */
+int b200_peer_alloc(long long bytes, void** ptr, unsigned char* handle64);  /* cudaMalloc + cudaIpcGetMemHandle            */
+int b200_peer_open(const unsigned char* handle64, void** ptr);              /* cudaIpcOpenMemHandle (lazy peer access)     */
+int b200_peer_close(void* ptr);                                             /* of a pointer returned by b200_peer_open     */
+int b200_peer_free(void* ptr);                                              /* of a pointer returned by b200_peer_alloc    */
+int b200_peer_copy(void* dst, const void* src, long long bytes, void* stream); /* cudaMemcpyAsync, either side may be a peer's */
 
 /* ---- whole Swin backbone (models/swin.py:196-225): plan = shapes + buffer layout, no memory of its own --------- */
 void* b200_swin_create(int batch, int img, int channels, int hidden_dim, const int* layers, const int* heads,

@@ -97,6 +97,12 @@ _PROTOS = {
     'b200_unit_rows_bwd': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, c_int, c_int, c_vp]),
     'b200_opt_chunk_elems': (c_int, []),
     'b200_optimizer_step': (c_int, [c_int, c_vp, c_vp, c_int, c_float, c_int, c_vp]),
+    'b200_optimizer_step_sum': (c_int, [c_int, c_vp, c_vp, c_int, c_float, c_int, c_int, c_ll, c_ll, c_vp]),
+    'b200_peer_alloc': (c_int, [c_ll, C.POINTER(c_vp), C.c_char_p]),
+    'b200_peer_open': (c_int, [C.c_char_p, C.POINTER(c_vp)]),
+    'b200_peer_close': (c_int, [c_vp]),
+    'b200_peer_free': (c_int, [c_vp]),
+    'b200_peer_copy': (c_int, [c_vp, c_vp, c_ll, c_vp]),
     'b200_swin_create': (c_vp, [c_int, c_int, c_int, c_int, C.POINTER(c_int), C.POINTER(c_int), C.POINTER(c_int), c_int, c_int,
                                 c_int, c_int]),
     'b200_swin_destroy': (None, [c_vp]),

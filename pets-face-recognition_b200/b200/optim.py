@@ -37,7 +37,7 @@ class FusedStep:
         self._base_steps = []
         self._chunk = lib().b200_opt_chunk_elems()
 
-    def _entries(self):
+    def _entries(self, grad_src=None):
         out = []
         for g in self.opt.param_groups:
             for p in g['params']:
@@ -46,12 +46,14 @@ class FusedStep:
                 if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous() or not p.grad.is_contiguous():
                     raise B200Error('fused optimizer step needs contiguous fp32 CUDA parameters and gradients')
                 st = self.opt.state[p]
+                # data parallel: the gradient is read from the peer arena (the sum of every rank's slot), not from p.grad
+                gptr = p.grad.data_ptr() if grad_src is None else grad_src.ptr_of(p)
                 if self.kind == abi.OPT_SGD:
                     mom = float(g.get('momentum', 0.0))
                     first = 'momentum_buffer' not in st or st['momentum_buffer'] is None
                     if first:
                         st['momentum_buffer'] = torch.zeros_like(p)
-                    out.append((p, p.grad, st['momentum_buffer'], None, float(g['lr']), float(g.get('weight_decay', 0.0)), mom, 0.0,
+                    out.append((p, gptr, st['momentum_buffer'], None, float(g['lr']), float(g.get('weight_decay', 0.0)), mom, 0.0,
                                 0.0, 0 if first else 1))
                 else:
                     if 'step' not in st:
@@ -59,20 +61,21 @@ class FusedStep:
                         st['exp_avg'] = torch.zeros_like(p)
                         st['exp_avg_sq'] = torch.zeros_like(p)
                     b1, b2 = g['betas']
-                    out.append((p, p.grad, st['exp_avg'], st['exp_avg_sq'], float(g['lr']), float(g.get('weight_decay', 0.0)),
+                    out.append((p, gptr, st['exp_avg'], st['exp_avg_sq'], float(g['lr']), float(g.get('weight_decay', 0.0)),
                                 float(b1), float(b2), float(g['eps']), int(st['step'].item())))
         return out
 
     @torch.no_grad()
-    def step(self, grad_scale: float = 1.0) -> None:
-        ents = self._entries()
+    def step(self, grad_scale: float = 1.0, grad_src=None) -> None:
+        """grad_src (b200/peer.py: ArenaGradSource): take every gradient as the sum of `n_src` arena slots instead of p.grad."""
+        ents = self._entries(grad_src)
         if not ents:
             return
         dev = ents[0][0].device
         # The device table is rebuilt only when a pointer or a hyper-parameter changes.  The step counters are NOT part of the
         # key: the kernel adds `offset` (steps since the table was written) to the stored ones, so AdamW's per-step counter
         # and SGD's first-step flag do not force a rebuild + pageable H2D copy every step.
-        key = tuple((e[0].data_ptr(), e[1].data_ptr(), e[2].data_ptr(), e[4], e[5], e[6], e[7], e[8]) for e in ents)
+        key = tuple((e[0].data_ptr(), e[1], e[2].data_ptr(), e[4], e[5], e[6], e[7], e[8]) for e in ents)
         offset = self._since_build
         if key == self._key:
             if self.kind == abi.OPT_ADAMW:
@@ -86,7 +89,7 @@ class FusedStep:
             chunks = []
             for i, (p, g, s1, s2, lr, wd, b1, b2, eps, step) in enumerate(ents):
                 t = arr[i]
-                t.param, t.grad, t.state1 = p.data_ptr(), g.data_ptr(), s1.data_ptr()
+                t.param, t.grad, t.state1 = p.data_ptr(), g, s1.data_ptr()
                 t.state2 = s2.data_ptr() if s2 is not None else 0
                 t.param_bf16 = 0
                 t.numel, t.lr, t.weight_decay, t.beta1, t.beta2, t.eps, t.step = p.numel(), lr, wd, b1, b2, eps, step
@@ -100,8 +103,10 @@ class FusedStep:
             self._chunks_dev = chunk_t.to(dev, non_blocking=True)
             self._n_chunks = len(chunks)
             self._key = key
-        check(lib().b200_optimizer_step(self.kind, self._tensors_dev.data_ptr(), self._chunks_dev.data_ptr(), self._n_chunks,
-                                        float(grad_scale), int(offset), stream_ptr()), 'optimizer_step')
+        n_src, stride, shift = (1, 0, 0) if grad_src is None else (grad_src.n_src, grad_src.stride, grad_src.shift)
+        check(lib().b200_optimizer_step_sum(self.kind, self._tensors_dev.data_ptr(), self._chunks_dev.data_ptr(), self._n_chunks,
+                                            float(grad_scale), int(offset), int(n_src), int(stride), int(shift), stream_ptr()),
+              'optimizer_step')
         self._since_build += 1
         self.opt._opt_called = True          # what optimizer.step() would set: lr_scheduler.step() checks it (order warning)
         if self.kind == abi.OPT_ADAMW:

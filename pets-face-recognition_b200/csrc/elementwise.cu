@@ -511,9 +511,32 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x,
 // ---------------------------------------------------------------------------------------------
 constexpr int kChunk = 4096;
 
+// Where the gradient of a step lives.  n_src == 1: in B200OptTensor.grad.  n_src > 1 (data parallel, csrc/peer.cu): every
+// rank's copy sits in its own slot of the peer arena, `stride` elements apart, `shift` elements past the table's pointer (the
+// arena is double-buffered); the kernel adds the slots in slot order - identical on every rank - so the gradient all-reduce
+// is folded into the optimizer pass.
+struct GradSrc {
+  int n_src;
+  long long stride, shift;
+};
+__device__ __forceinline__ float load_grad(const float* __restrict__ g, long long i, const GradSrc& gs) {
+  const float* q = g + gs.shift + i;
+  float v = q[0];
+  if (gs.n_src == 8) {          // a full node: all eight loads in flight before the first add (same slot order as the loop)
+    float s[7];
+#pragma unroll
+    for (int r = 0; r < 7; ++r) s[r] = q[(r + 1) * gs.stride];
+#pragma unroll
+    for (int r = 0; r < 7; ++r) v += s[r];
+    return v;
+  }
+  for (int r = 1; r < gs.n_src; ++r) v += q[r * gs.stride];
+  return v;
+}
+
 // torch.optim.SGD(momentum, dampening 0, no nesterov): g += wd * p; buf = first ? g : mom * buf + g; p -= lr * buf
 __global__ void __launch_bounds__(256) sgd_kernel(const B200OptTensor* __restrict__ tensors, const int2* __restrict__ chunks,
-                                                  float grad_scale, int step_offset) {
+                                                  float grad_scale, int step_offset, const GradSrc gs) {
   pdl_grid_sync();
   const int2 ck = chunks[blockIdx.x];
   const B200OptTensor t = tensors[ck.x];
@@ -524,7 +547,7 @@ __global__ void __launch_bounds__(256) sgd_kernel(const B200OptTensor* __restric
   const long long end = min(t.numel, 1LL * ck.y + kChunk);
   for (long long i = ck.y + threadIdx.x; i < end; i += blockDim.x) {
     float pv = p[i];
-    float gv = g[i] * grad_scale + t.weight_decay * pv;
+    float gv = load_grad(g, i, gs) * grad_scale + t.weight_decay * pv;
     const float bv = (t.step + step_offset) == 0 ? gv : t.beta1 * buf[i] + gv;
     buf[i] = bv;
     pv -= t.lr * bv;
@@ -536,7 +559,7 @@ __global__ void __launch_bounds__(256) sgd_kernel(const B200OptTensor* __restric
 // torch.optim.AdamW: p *= 1 - lr*wd; m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
 // p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
 __global__ void __launch_bounds__(256) adamw_kernel(const B200OptTensor* __restrict__ tensors, const int2* __restrict__ chunks,
-                                                    float grad_scale, int step_offset) {
+                                                    float grad_scale, int step_offset, const GradSrc gs) {
   pdl_grid_sync();
   const int2 ck = chunks[blockIdx.x];
   const B200OptTensor t = tensors[ck.x];
@@ -551,7 +574,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(const B200OptTensor* __restr
   const long long end = min(t.numel, 1LL * ck.y + kChunk);
   for (long long i = ck.y + threadIdx.x; i < end; i += blockDim.x) {
     float pv = p[i] * (1.0f - t.lr * t.weight_decay);
-    const float gv = g[i] * grad_scale;
+    const float gv = load_grad(g, i, gs) * grad_scale;
     const float mv = t.beta1 * m[i] + (1.0f - t.beta1) * gv;
     const float vv = t.beta2 * v[i] + (1.0f - t.beta2) * gv * gv;
     m[i] = mv; v[i] = vv;
@@ -860,15 +883,22 @@ extern "C" int b200_colsum(const void* x, long long ld, long long M, int N, floa
 
 extern "C" int b200_opt_chunk_elems(void) { return kChunk; }
 
-extern "C" int b200_optimizer_step(int kind, const void* tensors_dev, const void* chunks_dev, int n_chunks, float grad_scale,
-                                   int step_offset, void* stream) {
+extern "C" int b200_optimizer_step_sum(int kind, const void* tensors_dev, const void* chunks_dev, int n_chunks, float grad_scale,
+                                       int step_offset, int n_src, long long src_stride, long long src_shift, void* stream) {
+  B200_REQUIRE(n_src >= 1 && n_src <= 64 && src_stride >= 0 && src_shift >= 0, "optimizer_step: bad gradient sources (n_src %d)", n_src);
   if (n_chunks == 0) return B200_OK;
   auto st = reinterpret_cast<cudaStream_t>(stream);
   auto T = reinterpret_cast<const B200OptTensor*>(tensors_dev);
   auto Ck = reinterpret_cast<const int2*>(chunks_dev);
-  if (kind == B200_OPT_SGD) launch_pdl(sgd_kernel, dim3(n_chunks), dim3(256), 0, st, T, Ck, grad_scale, step_offset);
-  else if (kind == B200_OPT_ADAMW) launch_pdl(adamw_kernel, dim3(n_chunks), dim3(256), 0, st, T, Ck, grad_scale, step_offset);
+  const GradSrc gs{n_src, src_stride, src_shift};
+  if (kind == B200_OPT_SGD) launch_pdl(sgd_kernel, dim3(n_chunks), dim3(256), 0, st, T, Ck, grad_scale, step_offset, gs);
+  else if (kind == B200_OPT_ADAMW) launch_pdl(adamw_kernel, dim3(n_chunks), dim3(256), 0, st, T, Ck, grad_scale, step_offset, gs);
   else return b200_set_error(B200_ERR_INVALID, "optimizer_step: unknown kind %d", kind);
   B200_LAUNCH_CHECK();
   return B200_OK;
+}
+
+extern "C" int b200_optimizer_step(int kind, const void* tensors_dev, const void* chunks_dev, int n_chunks, float grad_scale,
+                                   int step_offset, void* stream) {
+  return b200_optimizer_step_sum(kind, tensors_dev, chunks_dev, n_chunks, grad_scale, step_offset, 1, 0, 0, stream);
 }

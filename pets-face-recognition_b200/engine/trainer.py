@@ -9,9 +9,10 @@ Behaviours re-created from PL 1.5.9 as the reference relies on them (SURVEY.md a
     checkpoints use, eval_fe_dog_head_sgd.py:18-21).
 B200 specifics: the optimizer arithmetic is one fused multi-tensor kernel (b200/optim.py) driven by the config's own
 torch.optim object; host batches are staged through pinned memory on a copy stream one step ahead; with
-strategy='ddp' (one process per GPU, torchrun-style env) gradients are all-reduced with NCCL per stage bucket on a
-side stream, launched as soon as each stage's backward has been enqueued, and the 1/world factor is folded into
-the optimizer kernel.
+strategy='ddp' (one process per GPU, torchrun-style env) every rank pushes its gradients, per stage bucket and as soon
+as each stage's backward has been enqueued, into the other ranks' peer arenas with the copy engines (NVLink / NVSwitch,
+b200/peer.py), and the optimizer kernel sums the ranks' copies and folds in the 1/world factor (B200_DDP=nccl: the same
+buckets through NCCL all-reduces on a side stream).
 """
 from __future__ import annotations
 
@@ -43,6 +44,13 @@ def _pin(batch):
     if isinstance(batch, (list, tuple)):
         return type(batch)(_pin(v) for v in batch)
     return batch
+
+
+def _outside_grad_ready(param) -> None:
+    """post-accumulate hook of a parameter outside the native engines (DDP only): hand the finished gradient to the Trainer."""
+    owner = getattr(param, '_b200_ddp_owner', None)
+    if owner is not None and param.grad is not None:
+        owner._on_outside_grad(param)
 
 
 class _Prefetcher:
@@ -165,6 +173,8 @@ class Trainer:
         self.global_step = 0
         self.world_size, self.rank = 1, 0
         self._comm_stream = None
+        self.ddp_mode, self._peer_state = 'nccl', None
+        self._early_reduced = set()
         self._fused: Dict[int, FusedStep] = {}
         self.device = self._pick_device()
         if strategy is not None:
@@ -193,56 +203,105 @@ class Trainer:
 
     # ------------------------------------------------------------------ the hot step
     def _allreduce_hooks(self, module):
-        """Install the per-stage gradient bucket all-reduce on every native Swin engine inside `module`."""
+        """Install the data-parallel gradient exchange on `module` (idempotent per Trainer).
+
+        Native Swin engines (default, B200_DDP=p2p): per-stage buckets of the flat gradient - and the parameters outside the
+        engines, e.g. the ArcFace weight, from post-accumulate hooks: their gradient is the FIRST thing backward produces -
+        are pushed into every rank's peer arena by the copy engines as soon as they are final (b200/peer.py), and the
+        optimizer kernel sums the ranks' slots.  B200_DDP=nccl, CPU / gloo runs and models without a native engine (the
+        ResNet path: hundreds of autograd-owned gradient tensors) all-reduce with torch.distributed instead: per stage bucket
+        / per parameter on a side stream, launched as early."""
         if self.world_size == 1:
             return []
         import torch.distributed as dist
         engines = [m.engine for m in module.modules() if hasattr(m, '_engine') and hasattr(m, 'engine')]
         if self._comm_stream is None and self.device.type == 'cuda':
             self._comm_stream = torch.cuda.Stream(device=self.device)
-        for eng in engines:
-            def hook(stage, flat_grad, eng=eng):
-                begin, end = eng.stage_param_range(stage)
-                if self._comm_stream is None:
-                    dist.all_reduce(flat_grad[begin:end])
-                    return
-                ev = torch.cuda.Event()
-                ev.record()
-                with torch.cuda.stream(self._comm_stream):
-                    self._comm_stream.wait_event(ev)
-                    dist.all_reduce(flat_grad[begin:end])
-            eng.grad_hook = hook
-        # parameters outside the native engines (the ArcFace / CosFace weight, 20 MB at C = 10,000): their gradient is the
-        # FIRST thing backward produces, so its all-reduce is launched from a post-accumulate hook and runs under the whole
-        # backbone backward instead of after it
         covered = set()
         for eng in engines:
             covered.update(id(p) for p in eng.params)
+        outside = [p for p in module.parameters() if p.requires_grad and id(p) not in covered]
+        use_p2p = bool(engines) and self.device.type == 'cuda' and os.environ.get('B200_DDP', 'p2p') != 'nccl'
+        self.ddp_mode = 'p2p' if use_p2p else 'nccl'
+        self._peer_state = {'engines': engines, 'outside': outside, 'source': None} if use_p2p else None
+
+        for k, eng in enumerate(engines):
+            def hook(stage, flat_grad, eng=eng, k=k):
+                begin, end = eng.stage_param_range(stage)
+                if self.ddp_mode == 'p2p':
+                    src = self._peer_source()
+                    src.exchange.push(flat_grad[begin:end], src.offsets[('engine', k)] + begin)
+                else:
+                    self._reduce_async(flat_grad[begin:end])
+            eng.grad_hook = hook
         self._early_reduced = set()
-        for prm in module.parameters():
-            if prm.requires_grad and id(prm) not in covered and not getattr(prm, '_b200_ddp_hook', False):
-                def early(param):
-                    if param.grad is None:
-                        return
-                    if self._comm_stream is None:
-                        dist.all_reduce(param.grad)
-                    else:
-                        ev = torch.cuda.Event()
-                        ev.record()
-                        with torch.cuda.stream(self._comm_stream):
-                            self._comm_stream.wait_event(ev)
-                            dist.all_reduce(param.grad)
-                    self._early_reduced.add(id(param))
-                prm.register_post_accumulate_grad_hook(early)
-                prm._b200_ddp_hook = True
+        for prm in outside:
+            if getattr(prm, '_b200_ddp_owner', None) is None:
+                prm.register_post_accumulate_grad_hook(_outside_grad_ready)
+            prm._b200_ddp_owner = self           # the hook serves whichever Trainer installed itself last
         return engines
+
+    def _reduce_async(self, t) -> None:
+        import torch.distributed as dist
+        if self._comm_stream is None:
+            dist.all_reduce(t)
+            return
+        ev = torch.cuda.Event()
+        ev.record()
+        with torch.cuda.stream(self._comm_stream):
+            self._comm_stream.wait_event(ev)
+            dist.all_reduce(t)
+
+    def _on_outside_grad(self, param) -> None:
+        if self.ddp_mode == 'p2p':
+            src = self._peer_source()
+            src.exchange.push(param.grad, src.offsets[id(param)])
+        else:
+            self._reduce_async(param.grad)
+        self._early_reduced.add(id(param))
+
+    def _peer_source(self):
+        """The peer arena of this trainer's module, built at the first gradient push (the flat layouts of the native engines
+        exist once a forward has run).  Collective: every rank gets here at the same point of its first backward."""
+        st = self._peer_state
+        if st is None:
+            return None
+        if st['source'] is None:
+            from b200 import peer
+            segments = [(('engine', k), eng.total) for k, eng in enumerate(st['engines'])] + [(id(p), p.numel()) for p in st['outside']]
+            offsets, total = peer.build_layout(segments)
+            for k, eng in enumerate(st['engines']):
+                base = offsets[('engine', k)]
+                for prm, o in zip(eng.params, eng.offsets):
+                    offsets[id(prm)] = base + o
+            try:
+                st['source'] = peer.ArenaGradSource(peer.PeerGradExchange(total, self.device), offsets)
+            except peer.B200Error as e:
+                # decided collectively inside PeerGradExchange: every rank lands here together.  NCCL is a transport of equal
+                # standing (the round-1 path), not a degraded compute path - but say so.
+                import sys
+                if self.rank == 0:
+                    sys.stderr.write(f'[b200] DDP: {e}; gradients go through NCCL all-reduce instead\n')
+                self.ddp_mode, self._peer_state = 'nccl', None
+                return None
+        return st['source']
+
+    def close(self) -> None:
+        """Release the peer arena (collective under DDP).  Optional: process exit frees it as well."""
+        st = getattr(self, '_peer_state', None)
+        if st is not None and st['source'] is not None:
+            st['source'].exchange.close()
+            st['source'] = None
 
     def run_training_batch(self, module, batch, optimizers) -> torch.Tensor:
         """One optimizer step == PL's optimizer.step(closure): training_step -> zero_grad -> backward -> step."""
         for opt in optimizers:
             opt.zero_grad(set_to_none=True)
         loss = module.training_step(batch, self.global_step)
+        if self.ddp_mode == 'p2p':
+            self._peer_source()               # first step: build the arena here, on the calling thread, not inside backward
         loss.backward()
+        grad_src = None
         if self.world_size > 1:
             import torch.distributed as dist
             covered = set()
@@ -250,23 +309,28 @@ class Trainer:
                 if hasattr(m, '_engine') and m._engine is not None and m._engine.last_flat_grad is not None:
                     covered.update(id(p) for p in m._engine.params)
             early = getattr(self, '_early_reduced', set())
-            rest = [p.grad for p in module.parameters() if p.grad is not None and id(p) not in covered and id(p) not in early]
+            rest = [p for p in module.parameters() if p.grad is not None and id(p) not in covered and id(p) not in early]
             self._early_reduced = set()
-            if self._comm_stream is not None:
+            if self.ddp_mode == 'p2p':
+                grad_src = self._peer_source()
+                for p in rest:
+                    grad_src.exchange.push(p.grad, grad_src.offsets[id(p)])
+                grad_src.shift = grad_src.exchange.finish()
+            elif self._comm_stream is not None:
                 ev = torch.cuda.Event(); ev.record()
                 with torch.cuda.stream(self._comm_stream):
                     self._comm_stream.wait_event(ev)
-                    for g in rest:
-                        dist.all_reduce(g)
+                    for p in rest:
+                        dist.all_reduce(p.grad)
                 torch.cuda.current_stream().wait_stream(self._comm_stream)
             else:
-                for g in rest:
-                    dist.all_reduce(g)
+                for p in rest:
+                    dist.all_reduce(p.grad)
         for opt in optimizers:
             fused = self._fused.get(id(opt))
             if fused is None:
                 fused = self._fused[id(opt)] = FusedStep(opt)
-            fused.step(grad_scale=1.0 / self.world_size)
+            fused.step(grad_scale=1.0 / self.world_size, grad_src=grad_src)
         self.global_step += 1
         return loss.detach()
 

@@ -313,3 +313,25 @@ def test_sharded_eval_gather_and_recall_world2_gloo(tmp_path):
     assert a == b
     for k in (2, 5):
         assert a[f'Recall@K={k}'] == pytest.approx(full[f'Recall@K={k}'], abs=1e-12)
+
+
+def test_peer_arena_layout_and_gradient_source():
+    """Host arithmetic of the peer gradient exchange (b200/peer.py): aligned segment layout, optimizer-table pointers."""
+    from b200 import peer
+    offsets, total = peer.build_layout([(('engine', 0), 1000), ('w', 64), ('b', 1)])
+    assert offsets == {('engine', 0): 0, 'w': 1024, 'b': 1088} and total == 1152
+    with pytest.raises(peer.B200Error):
+        peer.build_layout([('a', 3), ('a', 4)])
+
+    class FakeExchange:
+        world, total = 4, 1152
+
+        def grad_ptr(self, off):
+            return 0x1000 + 4 * off
+    prm = torch.nn.Parameter(torch.zeros(3))
+    src = peer.ArenaGradSource(FakeExchange(), {id(prm): 1088})
+    assert (src.n_src, src.stride, src.shift) == (4, 1152, 0) and src.ptr_of(prm) == 0x1000 + 4 * 1088
+    with pytest.raises(peer.B200Error):
+        src.ptr_of(torch.nn.Parameter(torch.zeros(1)))
+    with pytest.raises(peer.B200Error):                       # no CPU transport: gloo runs keep the all-reduce path
+        peer.PeerGradExchange(1152, torch.device('cpu'))

@@ -1,6 +1,7 @@
 """Worker of tests/test_multigpu_gpu.py - one process per GPU under torchrun (NCCL).  Real kernels on every rank:
 
-  1. data-parallel training step: averaged gradients / updated parameters of N ranks == one GPU over the whole batch;
+  1. data-parallel training steps: averaged gradients / updated parameters of N ranks == one GPU over the whole batch, and the
+     peer-arena gradient exchange (copy-engine pushes + slot sum in the optimizer kernel) == the NCCL all-reduce path bit for bit;
   2. Trainer.fit under strategy='ddp': rank-sharded loader, rank 0 writes the checkpoint;
   3. gallery-sharded cosine top-k (BASELINE config 4 layout) == single-GPU pass, bit for bit;
   4. leave-one-out Recall@K with row-sharded embeddings == single-GPU value;
@@ -78,33 +79,61 @@ def main():
     from engine.trainer import Trainer
     dev = torch.device('cuda', local)
 
-    # ---- 1. DDP step == single GPU
-    per = 16
-    img = synth.synth_images(per * world, seed=5).to(dev)
-    lab = synth.synth_labels(per * world, 1000, seed=5).to(dev)
-    mod = Mod(build(dev))
-    opt = torch.optim.SGD([p for p in mod.parameters() if p.requires_grad], 5e-3, momentum=0.9)
-    tr = Trainer(gpus=[local], strategy='ddp', max_epochs=1)
-    tr._allreduce_hooks(mod)
-    sl = slice(rank * per, (rank + 1) * per)
-    tr.run_training_batch(mod, {'x': img[sl], 'label': lab[sl]}, [opt])
-    torch.cuda.synchronize()
-    after = torch.cat([p.detach().flatten() for p in mod.parameters() if p.requires_grad])
-    grads = torch.cat([p.grad.flatten() / world for p in mod.parameters() if p.grad is not None])
-    ref_after = after.clone()
-    dist.broadcast(ref_after, 0)
-    flags = torch.tensor([int(torch.equal(ref_after, after))], device=dev)
-    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    # ---- 1. DDP steps == single GPU; the peer-arena exchange (default) == the NCCL all-reduce path, bit for bit
+    per, n_steps = 16, 3
+    img = synth.synth_images(per * world * n_steps, seed=5).to(dev)
+    lab = synth.synth_labels(per * world * n_steps, 1000, seed=5).to(dev)
+
+    def ddp_run(mode, steps):
+        os.environ['B200_DDP'] = mode
+        mod = Mod(build(dev))
+        opt = torch.optim.SGD([p for p in mod.parameters() if p.requires_grad], 5e-3, momentum=0.9)
+        tr = Trainer(gpus=[local], strategy='ddp', max_epochs=1)
+        tr._allreduce_hooks(mod)
+        assert tr.ddp_mode == mode, (tr.ddp_mode, mode)
+        for s in range(steps):
+            lo = (s * world + rank) * per
+            tr.run_training_batch(mod, {'x': img[lo:lo + per], 'label': lab[lo:lo + per]}, [opt])
+        torch.cuda.synchronize()
+        after = torch.cat([p.detach().flatten() for p in mod.parameters() if p.requires_grad])
+        mom = torch.cat([opt.state[p]['momentum_buffer'].flatten() for p in mod.parameters() if p.requires_grad and p.grad is not None])
+        tr.close()
+        return after, mom
+
+    def same_on_all_ranks(t):
+        ref = t.clone()
+        dist.broadcast(ref, 0)
+        flag = torch.tensor([int(torch.equal(ref, t))], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        return bool(flag.item())
+
+    after, grads = ddp_run('p2p', 1)               # first step, no weight decay: the momentum buffer IS the averaged gradient
+    after_nccl, grads_nccl = ddp_run('nccl', 1)
+    identical = same_on_all_ranks(after)
+    assert torch.equal(after, after_nccl) and torch.equal(grads, grads_nccl), 'peer-arena step differs from the NCCL all-reduce step'
+    after3, _ = ddp_run('p2p', n_steps)            # three steps: both arena buffers, momentum, the bf16 weight cache refresh
+    after3_nccl, _ = ddp_run('nccl', n_steps)
+    identical3 = same_on_all_ranks(after3)
+    if world == 2:                                 # two addends commute: the slot-order sum equals NCCL's sum bit for bit
+        assert torch.equal(after3, after3_nccl), 'peer-arena trajectory differs from the NCCL one'
+    os.environ.pop('B200_DDP', None)
     if rank == 0:
         single = Mod(build(dev))
         opt1 = torch.optim.SGD([p for p in single.parameters() if p.requires_grad], 5e-3, momentum=0.9)
-        Trainer(gpus=[local], max_epochs=1).run_training_batch(single, {'x': img, 'label': lab}, [opt1])
+        tr1 = Trainer(gpus=[local], max_epochs=1)
+        tr1.run_training_batch(single, {'x': img[:per * world], 'label': lab[:per * world]}, [opt1])
         g1 = torch.cat([p.grad.flatten() for p in single.parameters() if p.grad is not None])
         a1 = torch.cat([p.detach().flatten() for p in single.parameters() if p.requires_grad])
         rel_g = ((grads - g1).norm() / g1.norm()).item()
         rel_p = ((after - a1).norm() / a1.norm()).item()
-        print(f'world {world}: ranks identical {bool(flags.item())}; grad rel-L2 vs 1 GPU {rel_g:.3e}; params rel-L2 {rel_p:.3e}')
-        assert flags.item() == 1 and rel_g < 1e-3 and rel_p < 1e-6, (rel_g, rel_p)
+        for s in range(1, n_steps):
+            lo = s * world * per
+            tr1.run_training_batch(single, {'x': img[lo:lo + per * world], 'label': lab[lo:lo + per * world]}, [opt1])
+        a3 = torch.cat([p.detach().flatten() for p in single.parameters() if p.requires_grad])
+        rel_p3 = ((after3 - a3).norm() / a3.norm()).item()
+        print(f'world {world}: ranks identical {identical} / {identical3}; grad rel-L2 vs 1 GPU {rel_g:.3e}; params rel-L2 {rel_p:.3e} '
+              f'(after {n_steps} steps {rel_p3:.3e}); peer arena == NCCL bit for bit')
+        assert identical and identical3 and rel_g < 1e-3 and rel_p < 1e-6 and rel_p3 < 1e-5, (rel_g, rel_p, rel_p3)
         del single
 
     # ---- 2. fit(): sharded loader + rank-0 checkpoint
