@@ -388,6 +388,8 @@ def gpu_arm(args, rank, world, local_rank):
     pipeline = pipeline_leg(args, wrap, rank, world, device) if not args.no_gallery else None
     resnet = resnet_leg(args, device, local_rank) if (world == 1 and not args.no_gallery) else None
 
+    ddp_mode = trainer.ddp_mode
+    trainer.close()            # collective: before the other ranks leave
     if rank != 0:
         return
     peak_tf, peak_hbm, peak_src = peaks()
@@ -398,7 +400,7 @@ def gpu_arm(args, rank, world, local_rank):
     grad_exchange = None
     if world > 1:
         grad_exchange = ('copy-engine pushes into every rank\'s peer arena (CUDA IPC over NVLink) under the backward + slot sum inside the '
-                         'optimizer kernel (b200/peer.py)') if trainer.ddp_mode == 'p2p' else 'per-stage NCCL all-reduce on a side stream'
+                         'optimizer kernel (b200/peer.py)') if ddp_mode == 'p2p' else 'per-stage NCCL all-reduce on a side stream'
     hbm_bound = peak_hbm and peak_tf and achieved_gbs / peak_hbm >= achieved_tf / peak_tf
     traffic = ncu_traffic()
     line = {
@@ -463,7 +465,6 @@ def gpu_arm(args, rank, world, local_rank):
         except Exception as e:          # a baseline, not the product: report why it is missing and go on
             line['cpu_baseline']['gpu_eager'] = {'unavailable': f'{type(e).__name__}: {str(e)[:160]}'}
     emit(line)
-    trainer.close()
 
 
 def extract_leg(args, wrap, dev_batches, world, device):

@@ -174,6 +174,8 @@ class Trainer:
         self.world_size, self.rank = 1, 0
         self._comm_stream = None
         self.ddp_mode, self._peer_state = 'nccl', None
+        # B200_TRACE_STEP=1: host time stamps per step [start, forward enqueued, backward enqueued, exchange closed, optimizer enqueued]
+        self._trace = [] if os.environ.get('B200_TRACE_STEP') else None
         self._early_reduced = set()
         self._fused: Dict[int, FusedStep] = {}
         self.device = self._pick_device()
@@ -295,12 +297,19 @@ class Trainer:
 
     def run_training_batch(self, module, batch, optimizers) -> torch.Tensor:
         """One optimizer step == PL's optimizer.step(closure): training_step -> zero_grad -> backward -> step."""
+        trace = self._trace
+        if trace is not None:
+            trace.append([time.perf_counter()])
         for opt in optimizers:
             opt.zero_grad(set_to_none=True)
         loss = module.training_step(batch, self.global_step)
         if self.ddp_mode == 'p2p':
             self._peer_source()               # first step: build the arena here, on the calling thread, not inside backward
+        if trace is not None:
+            trace[-1].append(time.perf_counter())
         loss.backward()
+        if trace is not None:
+            trace[-1].append(time.perf_counter())
         grad_src = None
         if self.world_size > 1:
             import torch.distributed as dist
@@ -326,11 +335,15 @@ class Trainer:
             else:
                 for p in rest:
                     dist.all_reduce(p.grad)
+        if trace is not None:
+            trace[-1].append(time.perf_counter())
         for opt in optimizers:
             fused = self._fused.get(id(opt))
             if fused is None:
                 fused = self._fused[id(opt)] = FusedStep(opt)
             fused.step(grad_scale=1.0 / self.world_size, grad_src=grad_src)
+        if trace is not None:
+            trace[-1].append(time.perf_counter())
         self.global_step += 1
         return loss.detach()
 

@@ -133,7 +133,7 @@ def main():
         rel_p3 = ((after3 - a3).norm() / a3.norm()).item()
         print(f'world {world}: ranks identical {identical} / {identical3}; grad rel-L2 vs 1 GPU {rel_g:.3e}; params rel-L2 {rel_p:.3e} '
               f'(after {n_steps} steps {rel_p3:.3e}); peer arena == NCCL bit for bit')
-        assert identical and identical3 and rel_g < 1e-3 and rel_p < 1e-6 and rel_p3 < 1e-5, (rel_g, rel_p, rel_p3)
+        assert identical and identical3 and rel_g < 1e-3 and rel_p < 1e-6 and rel_p3 < 1e-4, (rel_g, rel_p, rel_p3)
         del single
 
     # ---- 2. fit(): sharded loader + rank-0 checkpoint
