@@ -150,6 +150,58 @@ def test_fused_adamw_matches_torch():
         torch.testing.assert_close(p.detach(), c.detach(), rtol=2e-5, atol=2e-6)
 
 
+@pytest.mark.parametrize('kind,world', [('sgd', 2), ('sgd', 8), ('adamw', 3)])
+def test_optimizer_sums_the_slots_of_a_peer_arena(kind, world):
+    """The data-parallel step on ONE GPU: `world` gradient copies pushed into the slots of a (double-buffered) peer arena with
+    b200_peer_copy, summed in slot order inside the optimizer kernel (b200_optimizer_step_sum) == the single-source kernel on the
+    gradient pre-summed in the same order, bit for bit, for both arena buffers."""
+    import ctypes as C
+    from b200 import abi, peer
+    from b200.optim import FusedStep
+    torch.manual_seed(3)
+    shapes = [(300, 37), (5,), (4097,)]
+    ps = [torch.randn(*sh, device='cuda', requires_grad=True) for sh in shapes]
+    cs = [p.detach().clone().requires_grad_(True) for p in ps]
+    make = (lambda prm: torch.optim.SGD(prm, lr=1e-2, momentum=0.9, weight_decay=1e-4)) if kind == 'sgd' else \
+           (lambda prm: torch.optim.AdamW(prm, lr=1e-3, weight_decay=1e-2))
+    o1, o2 = make(ps), make(cs)
+    offsets, total = peer.build_layout([(id(p), p.numel()) for p in ps])
+    own, handle = C.c_void_p(), C.create_string_buffer(64)
+    abi.check(abi.lib().b200_peer_alloc(2 * world * total * 4, C.byref(own), handle), 'peer_alloc')
+    assert any(handle.raw)                                     # a real CUDA IPC handle came back
+
+    class OneGpuExchange:                                      # the addressing of peer.PeerGradExchange without the peers
+        pass
+    ex = OneGpuExchange()
+    ex.world, ex.total = world, total
+    ex.grad_ptr = lambda off: own.value + 4 * off
+    src = peer.ArenaGradSource(ex, offsets)
+    f1, f2 = FusedStep(o1), FusedStep(o2)
+    st = torch.cuda.current_stream().cuda_stream
+    try:
+        for it in range(4):
+            buf = it % 2
+            for p, c in zip(ps, cs):
+                parts = [torch.randn_like(p) for _ in range(world)]
+                for r, g in enumerate(parts):
+                    dst = own.value + 4 * ((buf * world + r) * total + offsets[id(p)])
+                    abi.check(abi.lib().b200_peer_copy(dst, g.data_ptr(), 4 * g.numel(), st), 'peer_copy')
+                acc = parts[0].clone()
+                for g in parts[1:]:
+                    acc += g
+                c.grad = acc
+                p.grad = parts[0]                             # the rank-local gradient: must NOT be what the step uses
+            src.shift = buf * world * total
+            f1.step(grad_scale=1.0 / world, grad_src=src)
+            f2.step(grad_scale=1.0 / world)
+        torch.cuda.synchronize()
+        for p, c in zip(ps, cs):
+            assert torch.equal(p.detach(), c.detach())
+    finally:
+        torch.cuda.synchronize()
+        abi.check(abi.lib().b200_peer_free(own), 'peer_free')
+
+
 def test_batch_odd_sizes_and_repeatability(setup):
     g, sd, wrap, img, label = setup
     from b200 import synth
