@@ -28,9 +28,11 @@ int b200_set_error(int code, const char* fmt, ...);
 #define B200_CHECK_CUDA(expr)                                                              \
   do {                                                                                     \
     cudaError_t _e = (expr);                                                               \
-    if (_e != cudaSuccess)                                                                 \
+    if (_e != cudaSuccess) {                                                               \
+      (void)cudaGetLastError(); /* reported here: must not resurface at the next launch check */ \
       return b200_set_error(B200_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr,   \
                             cudaGetErrorString(_e));                                       \
+    }                                                                                      \
   } while (0)
 
 #define B200_REQUIRE(cond, ...)                                              \

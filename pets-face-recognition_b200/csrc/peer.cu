@@ -23,6 +23,7 @@ int b200_peer_alloc(long long bytes, void** ptr, unsigned char* handle64) {
   cudaIpcMemHandle_t h;
   cudaError_t e = cudaIpcGetMemHandle(&h, p);
   if (e != cudaSuccess) {
+    (void)cudaGetLastError();
     cudaFree(p);
     return b200_set_error(B200_ERR_CUDA, "peer_alloc: cudaIpcGetMemHandle -> %s", cudaGetErrorString(e));
   }
