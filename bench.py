@@ -460,6 +460,11 @@ def gpu_arm(args, rank, world, local_rank):
                                           f'oracle/ port, fp32, {torch.get_num_threads()} threads'}
         if rows_f is not None:
             line['cpu_baseline'].update(rows_f_cpu())
+        if gallery is not None:
+            try:
+                line['cpu_baseline']['gallery'] = gallery_cpu(rows=args.gallery_rows)
+            except Exception as e:      # a baseline, not the product
+                line['cpu_baseline']['gallery'] = {'unavailable': f'{type(e).__name__}: {str(e)[:160]}'}
         try:
             line['cpu_baseline']['gpu_eager'] = time_oracle_gpu_eager(torch.device('cuda', 0))
         except Exception as e:          # a baseline, not the product: report why it is missing and go on
@@ -719,6 +724,32 @@ def rows_f_cpu():
     dt2 = time.perf_counter() - t1
     return {'tsv_scoring': {'value': 4 * 1000 / dt, 'unit': 'folder pairs/s', 'sample': '4 enroll x 2,000 verify folders, reference loop (oracle port)'},
             'pair_scoring': {'value': 20000 / dt2, 'unit': 'pairs/s', 'sample': 'similarity_f over 20,000 gathered tensor pairs (oracle port)'}}
+
+
+def gallery_cpu(rows=125000, queries=2000, loop_n=400):
+    """the reference's gallery ranking on the host cores, on a bounded sample - its leave-one-out loop
+    statement for statement (oracle.rank_oracle.recall_at_k_loop = engine/controller.py:77-91) on `loop_n` embeddings, and the
+    vectorised fp32 restatement (normalize -> chunked matmul -> topk(100)) against a shard of the size the GPU leg uses."""
+    from oracle import rank_oracle
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = torch.Generator().manual_seed(11)
+    emb = torch.nn.functional.normalize(torch.randn(loop_n, 512, generator=g))
+    classes = torch.arange(loop_n) // 2
+    t0 = time.perf_counter()
+    rank_oracle.recall_at_k_loop(emb, classes, (10, 100))
+    dt_loop = time.perf_counter() - t0
+    gal = torch.randn(rows, 512, generator=g)
+    q = torch.randn(queries, 512, generator=g)
+    rank_oracle.gallery_match_vectorised(q[:64], gal, 100, chunk=64)                  # warm-up
+    t1 = time.perf_counter()
+    rank_oracle.gallery_match_vectorised(q, gal, 100, chunk=1000)
+    dt_vec = time.perf_counter() - t1
+    return {'value': queries / dt_vec, 'unit': 'queries/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+            'sample': f'{queries} queries x {rows} gallery rows x 512, vectorised fp32 restatement (F.normalize -> chunked matmul -> '
+                      f'topk(100)), oracle/rank_oracle.py:gallery_match_vectorised',
+            'reference_loop': {'value': loop_n / dt_loop, 'unit': 'queries/s', 'us_per_gallery_row': dt_loop / (loop_n * (loop_n - 1)) * 1e6,
+                               'sample': f'leave-one-out loop of engine/controller.py:77-91, statement for statement, on {loop_n} embeddings '
+                                         f'(similarity_f over a Python list of tensor pairs + full argsort per query)'}}
 
 
 def gallery_leg(args, rank, world, device):
