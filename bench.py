@@ -112,6 +112,21 @@ def time_oracle(batch, warmup, steps):
     return batch * steps / dt, dt / steps
 
 
+def time_oracle_extract(batch=32, steps=2):
+    """the oracle port's eval forward (embedding extraction) on the host cores, bounded sample."""
+    from oracle.swin_oracle import swin_forward
+    torch.set_num_threads(os.cpu_count() or 1)
+    spec, sd, _, img, _ = oracle_train_setup(batch)
+    with torch.no_grad():
+        swin_forward(sd, img, spec)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            swin_forward(sd, img, spec)
+        dt = time.perf_counter() - t0
+    return {'value': batch * steps / dt, 'unit': 'images/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+            'sample': f'{steps} eval forwards of batch {batch} after 1 warm-up, oracle/ port, fp32'}
+
+
 def time_oracle_gpu_eager(device, batch=256, steps=3):
     """SURVEY.md 8(d) 'GPU-side bar': the same oracle port (plain PyTorch ops: cuBLAS / ATen kernels) on the B200 under
     torch.autocast(bfloat16) - what the reference's own modules would do on this GPU.  Part of the baseline leg; never on
@@ -460,6 +475,11 @@ def gpu_arm(args, rank, world, local_rank):
                                           f'oracle/ port, fp32, {torch.get_num_threads()} threads'}
         if rows_f is not None:
             line['cpu_baseline'].update(rows_f_cpu())
+        if extract is not None:
+            try:
+                line['cpu_baseline']['extract'] = time_oracle_extract()
+            except Exception as e:      # a baseline, not the product
+                line['cpu_baseline']['extract'] = {'unavailable': f'{type(e).__name__}: {str(e)[:160]}'}
         if gallery is not None:
             try:
                 line['cpu_baseline']['gallery'] = gallery_cpu(rows=args.gallery_rows)
