@@ -315,6 +315,50 @@ def test_sharded_eval_gather_and_recall_world2_gloo(tmp_path):
         assert a[f'Recall@K={k}'] == pytest.approx(full[f'Recall@K={k}'], abs=1e-12)
 
 
+def _grad_hook_worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path[:0] = [str(ROOT), str(PKG)]
+    import torch.distributed as dist
+    from engine import Trainer
+    tr = Trainer(gpus=0, strategy='ddp')                       # CPU + gloo: no native engine, no peer memory -> all-reduce transport
+    torch.manual_seed(5)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 4), torch.nn.Tanh(), torch.nn.Linear(4, 3))
+    frozen = net[0].bias
+    frozen.requires_grad_(False)
+    assert tr._allreduce_hooks(net) == [] and tr.ddp_mode == 'nccl' and tr._peer_state is None
+    tr2 = Trainer(gpus=0, strategy='ddp')
+    tr2._allreduce_hooks(net)                                  # a second Trainer takes the hooks over: still ONE reduction per gradient
+    x = torch.full((5, 6), float(rank + 1))
+    net(x).square().sum().backward()
+    grads = [p.grad.clone() for p in net.parameters() if p.requires_grad]
+    torch.save({'grads': grads, 'early': len(tr2._early_reduced), 'old_early': len(tr._early_reduced), 'frozen_grad': frozen.grad},
+               Path(tmp) / f'g{rank}.pt')
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_ddp_gradient_hooks_world2_gloo(tmp_path):
+    """Parameters outside the native engines are reduced from post-accumulate hooks (engine/trainer.py): under gloo the summed
+    gradients must equal the sum of the two ranks' single-process gradients, reduced exactly once, frozen parameters untouched."""
+    import torch.multiprocessing as mp
+    port = 33500 + (os.getpid() % 2000)
+    mp.spawn(_grad_hook_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a, b = (torch.load(tmp_path / f'g{r}.pt', weights_only=False) for r in range(2))
+    torch.manual_seed(5)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 4), torch.nn.Tanh(), torch.nn.Linear(4, 3))
+    net[0].bias.requires_grad_(False)
+    want = None
+    for r in range(2):
+        net.zero_grad()
+        net(torch.full((5, 6), float(r + 1))).square().sum().backward()
+        g = [p.grad.clone() for p in net.parameters() if p.requires_grad]
+        want = g if want is None else [w + v for w, v in zip(want, g)]
+    assert a['early'] == b['early'] == 3 and a['old_early'] == 0 and a['frozen_grad'] is None
+    for ga, gb, w in zip(a['grads'], b['grads'], want):
+        assert torch.equal(ga, gb)
+        torch.testing.assert_close(ga, w, rtol=1e-6, atol=1e-7)
+
+
 def test_peer_arena_layout_and_gradient_source():
     """Host arithmetic of the peer gradient exchange (b200/peer.py): aligned segment layout, optimizer-table pointers."""
     from b200 import peer
