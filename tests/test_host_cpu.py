@@ -379,3 +379,77 @@ def test_peer_arena_layout_and_gradient_source():
         src.ptr_of(torch.nn.Parameter(torch.zeros(1)))
     with pytest.raises(peer.B200Error):                       # no CPU transport: gloo runs keep the all-reduce path
         peer.PeerGradExchange(1152, torch.device('cpu'))
+
+
+def test_peer_exchange_addressing_ring_order_and_double_buffer(monkeypatch):
+    """The push protocol of b200/peer.py without a GPU: every bucket goes into slot `rank` of EVERY rank's arena (ring order
+    starting at the next rank), the two arena buffers alternate per step, finish() hands the optimizer the shift of the buffer
+    that was just filled, and segments outside the layout are refused."""
+    import contextlib
+    from b200 import peer
+    copies, barriers = [], []
+
+    class FakeLib:
+        def b200_peer_copy(self, dst, src, nbytes, stream):
+            copies.append((dst, src, nbytes, stream))
+            return 0
+
+    class Ev:
+        def record(self):
+            pass
+
+    class St:
+        cuda_stream = 7
+
+        def wait_event(self, ev):
+            pass
+
+        def wait_stream(self, s):
+            pass
+
+    class Dist:
+        def all_reduce(self, t, group=None):
+            barriers.append(len(copies))
+
+    class Grad:                                                # the slice of a CUDA tensor push() looks at
+        is_cuda, dtype = True, torch.float32
+
+        def __init__(self, n, ptr):
+            self.n, self.ptr = n, ptr
+
+        def is_contiguous(self):
+            return True
+
+        def numel(self):
+            return self.n
+
+        def data_ptr(self):
+            return self.ptr
+    monkeypatch.setattr(peer, 'lib', lambda: FakeLib())
+    monkeypatch.setattr(peer.torch.cuda, 'Event', Ev)
+    monkeypatch.setattr(peer.torch.cuda, 'stream', lambda s: contextlib.nullcontext())
+    monkeypatch.setattr(peer.torch.cuda, 'current_stream', lambda *a: St())
+    world, rank, total = 4, 1, 256
+    ex = object.__new__(peer.PeerGradExchange)
+    ex.world, ex.rank, ex.total, ex.buf, ex.group, ex.dist, ex._flag = world, rank, total, 0, None, Dist(), None
+    ex.ptrs = [0x10000000 * (r + 1) for r in range(world)]
+    ex.stream = St()
+    ex._own = type('P', (), {'value': ex.ptrs[rank]})()
+
+    ex.push(Grad(128, 0xABC0), 64)
+    slot = (0 * world + rank) * total + 64
+    assert copies == [(ex.ptrs[r] + 4 * slot, 0xABC0, 512, 7) for r in (2, 3, 0, 1)]       # ring order, own arena last
+    assert ex.finish() == 0 and ex.buf == 1 and barriers == [4]                            # the barrier follows the copies
+    copies.clear()
+    ex.push(Grad(256, 0xDEF0), 0)
+    slot = (1 * world + rank) * total
+    assert [c[0] for c in copies] == [ex.ptrs[r] + 4 * slot for r in (2, 3, 0, 1)]         # second step: the other buffer
+    assert ex.finish() == world * total and ex.buf == 0
+    assert ex.grad_ptr(64) == ex.ptrs[rank] + 256                                          # optimizer table: buffer 0, slot 0
+    for bad_off, n in ((200, 128), (32, 16), (-64, 16)):                                   # past the end / misaligned / negative
+        with pytest.raises(peer.B200Error):
+            ex.push(Grad(n, 0x1000), bad_off)
+    with pytest.raises(peer.B200Error):
+        g = Grad(16, 0x1000)
+        g.dtype = torch.float16
+        ex.push(g, 0)
